@@ -1,0 +1,220 @@
+/*
+ * posegen_b200 — C ABI of the B200-native A-NeRF volumetric renderer.
+ *
+ * This is the drop-in boundary for ONE hot path of mgholamikn/PoseGen:
+ * `RayCaster.render_rays` (reference core/raycasters.py:361-474) and the stages it
+ * calls.  The reference is pure Python/PyTorch and has no FFI of its own; the entry
+ * points below are what a binding for that path would bind (see INTEGRATION.md for
+ * the ctypes stub that replaces `core.raycasters.RayCaster.forward`).
+ *
+ * Conventions
+ *   - plain C, no torch types: device pointers + sizes + a CUDA stream handle
+ *     (`void*`, i.e. a `cudaStream_t`; NULL = legacy default stream);
+ *   - every function returns 0 on success, a negative PGN_E_* code on failure;
+ *     `pgn_last_error()` returns a thread-local message for the last failure;
+ *   - no allocation on the hot path: the caller passes a workspace of
+ *     `pgn_workspace_bytes()` bytes; outputs are caller-allocated;
+ *   - all tensors are fp32, row-major, contiguous unless a stride is given;
+ *   - re-entrant per context; one context per device per thread
+ *     (nn.DataParallel calls replicas from one Python thread per GPU,
+ *     reference core/raycasters.py:157).
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails with
+ *     PGN_E_CUDA.
+ */
+#ifndef POSEGEN_B200_H
+#define POSEGEN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PGN_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define PGN_API __attribute__((visibility("default")))
+#else
+#define PGN_API
+#endif
+
+#define PGN_OK          0
+#define PGN_E_INVALID  -1   /* bad argument / unsupported configuration */
+#define PGN_E_CUDA     -2   /* CUDA runtime error (message in pgn_last_error) */
+#define PGN_E_STATE    -3   /* weights / scalars not uploaded yet */
+#define PGN_E_KERNEL   -4   /* device-side watchdog tripped (pipeline stall) */
+
+#define PGN_N_JOINTS     24
+#define PGN_RAY_STRIDE   11  /* o(3) d(3) near far viewdirs(3): core/trainer.py:118-137 */
+#define PGN_NET_COARSE    0
+#define PGN_NET_FINE      1
+#define PGN_N_LINEAR     12  /* linear layers per NeRF, order below */
+
+/* precision of the MLP stage */
+#define PGN_PRECISION_FP32  0   /* fp32 CUDA-core path: 1e-3 parity tier        */
+#define PGN_PRECISION_BF16  1   /* bf16 tcgen05 tensor-core path: 2e-2 / 40 dB  */
+
+typedef struct pgn_context pgn_context;
+
+/* Model hyper-parameters (frozen table: SURVEY.md §8d; reference
+ * configs/surreal/surreal.txt + run_nerf.py:186-490 defaults).  Only the surreal.txt
+ * architecture is implemented; pgn_create rejects anything else. */
+typedef struct pgn_config {
+  int32_t n_joints;        /* 24 */
+  int32_t n_samples;       /* 64  (N_samples)     */
+  int32_t n_importance;    /* 16  (N_importance)  */
+  int32_t multires;        /* 7   (distance PE frequencies) */
+  int32_t multires_views;  /* 4   (view PE frequencies)     */
+  int32_t net_depth;       /* 8 */
+  int32_t net_width;       /* 256 */
+  int32_t skip_layer;      /* 4 */
+  int32_t device;          /* CUDA device ordinal */
+} pgn_config;
+
+/* One NeRF MLP's parameters in nn.Linear layout ([out,in] row-major weight, [out] bias),
+ * in this order (reference core/networks/nerf.py:57-88):
+ *   0..7  pts_linears.0-7   (432->256, 4x 256->256, 688->256, 2x 256->256)
+ *   8     alpha_linear      (256->1)
+ *   9     feature_linear    (256->256)
+ *   10    views_linears.0   (904->128)
+ *   11    rgb_linear        (128->3)
+ * Pointers may be host or device memory (flag in pgn_upload_weights). */
+typedef struct pgn_net_weights {
+  const float* weight[PGN_N_LINEAR];
+  const float* bias[PGN_N_LINEAR];
+} pgn_net_weights;
+
+/* Inputs of one render call.  Replaces the arguments of RayCaster.render_rays
+ * (core/raycasters.py:361-381).  kp_batch / bones / subject_idxs / cams are not
+ * part of the ABI: the surreal.txt encoders ignore them (core/encoders.py:110-122,
+ * 181-193) and opt_framecode is off. */
+typedef struct pgn_render_inputs {
+  const float*   ray_batch;    /* device [n_rays, 11] */
+  int64_t        n_rays;
+  const float*   skts;         /* device; world->joint-local 4x4 per joint        */
+  int64_t        skts_stride;  /* floats between consecutive rays' skts: 384 for the
+                                  reference's per-ray layout [N,24,4,4], 0 when one
+                                  pose is shared (the expand() view of run_nerf.py:63-90) */
+  const float*   cyls;         /* device; (cx, cz, R, top, bot) per ray            */
+  int64_t        cyls_stride;  /* 5 or 0 */
+  const int32_t* pose_idx;     /* optional device [n_rays]: when non-NULL the pose of
+                                  ray i is pose_idx[i] and skts/cyls are indexed
+                                  [pose,24,4,4] / [pose,5] (strides ignored)          */
+  int64_t        nanfill_chunk;/* rays per chunk for the missed-cylinder near/far fill
+                                  (core/utils/ray_utils.py:328-342 takes the mean over
+                                  the batchify chunk); <=0 => whole call               */
+  int32_t        precision;    /* PGN_PRECISION_* */
+} pgn_render_inputs;
+
+/* Outputs of one render call (core/raycasters.py:711-724).  Any pointer may be NULL
+ * to skip that output.  Optional taps are for stage-level parity tests. */
+typedef struct pgn_render_outputs {
+  float* rgb_map;    /* [n,3]  */
+  float* disp_map;   /* [n]    */
+  float* acc_map;    /* [n]    */
+  float* alpha;      /* [n,80] per-sample fine alpha   */
+  float* rgb0;       /* [n,3]  */
+  float* disp0;      /* [n]    */
+  float* acc0;       /* [n]    */
+  float* alpha0;     /* [n,64] per-sample coarse alpha */
+  /* taps */
+  float*   z_samples;  /* [n,16] importance samples (before the merge sort) */
+  float*   z_fine;     /* [n,80] merged, sorted z                           */
+  int32_t* pdf_inds;   /* [n,16] searchsorted(cdf,u,right) bin indices      */
+  float*   weights0;   /* [n,64] coarse compositing weights                 */
+  float*   raw0;       /* [n,64,4] coarse network output (rgb_raw, sigma_raw) */
+  float*   raw;        /* [n,80,4] fine network output                      */
+  float*   near_far;   /* [n,2] near/far after the cylinder intersection    */
+} pgn_render_outputs;
+
+/* ------------------------------------------------------------------ lifecycle */
+PGN_API int  pgn_abi_version(void);
+PGN_API const char* pgn_last_error(void);
+
+/* replaces create_raycaster's module construction (core/raycasters.py:17-109) */
+PGN_API int  pgn_create(const pgn_config* cfg, pgn_context** out);
+PGN_API void pgn_destroy(pgn_context* ctx);
+
+/* replaces RayCaster.load_state_dict / parameter refresh after optimizer.step
+ * (core/raycasters.py:768-788): repacks one net into the kernel layouts
+ * (fp32 transposed for the CUDA-core path; bf16 UMMA K-major slabs for tcgen05). */
+PGN_API int  pgn_upload_weights(pgn_context* ctx, int net_id, const pgn_net_weights* w,
+                        int pointers_are_device, void* stream);
+
+/* embedder scalars: tau buffers and cutoff distances of embed_fn / embeddirs_fn
+ * (core/cutoff_embedder.py:83-95,181-183), density_scale and rgb_eps
+ * (core/networks/nerf.py:150-151).  cutoff arrays are HOST pointers [24]. */
+PGN_API int  pgn_set_embed_scalars(pgn_context* ctx, float tau_v, float tau_d,
+                           const float* cutoff_v, const float* cutoff_d,
+                           float density_scale, float rgb_eps);
+
+/* ------------------------------------------------------------------- hot path */
+PGN_API size_t pgn_workspace_bytes(const pgn_context* ctx, int64_t n_rays);
+
+/* replaces RayCaster.render_rays (eval path: perturb=0, raw_noise_std=0,
+ * ray_noise_std=0; core/raycasters.py:361-474).  Asynchronous on `stream`. */
+PGN_API int  pgn_render_forward(pgn_context* ctx, const pgn_render_inputs* in,
+                        const pgn_render_outputs* out,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* number of kernel launches issued by this context since creation
+ * (bench.py reports it as gpu_launches) */
+PGN_API int64_t pgn_launch_count(const pgn_context* ctx);
+
+/* after a stream sync: 0 if no device-side watchdog tripped since the last call */
+PGN_API int  pgn_check_device_status(pgn_context* ctx);
+
+/* ------------------------------------------------- stage-level entry points
+ * (unit parity against the oracle; each replaces one reference function) */
+
+/* get_near_far_in_cylinder (core/utils/ray_utils.py:292-344) incl. NaN fill.
+ * near_far: device [n,2]. */
+PGN_API int  pgn_near_far(pgn_context* ctx, const pgn_render_inputs* in, float* near_far, void* stream);
+
+/* encode_inputs (core/raycasters.py:476-555) for explicit z values:
+ * z [n, n_z] -> enc [n, n_z, 1080] in the reference channel order
+ * ([0,360) v_emb k*24+j | [360,432) r j*3+c | [432,1080) d_emb k*72+j*3+c). */
+PGN_API int  pgn_encode(pgn_context* ctx, const pgn_render_inputs* in, const float* z, int32_t n_z,
+                float* enc, void* stream);
+
+/* NeRF.forward (core/networks/nerf.py:133-148) on explicit encodings:
+ * enc [m,1080] -> raw [m,4].  precision selects the MLP engine. */
+PGN_API int  pgn_mlp(pgn_context* ctx, int net_id, const float* enc, int64_t m, float* raw,
+             int32_t precision, void* stream);
+
+/* NeRF.raw2outputs (core/networks/nerf.py:150-205): raw [n,s,4], z [n,s], rays_d taken
+ * from in->ray_batch.  Any output may be NULL. */
+PGN_API int  pgn_composite(pgn_context* ctx, const pgn_render_inputs* in, const float* raw, const float* z,
+                   int32_t s, float* rgb_map, float* disp_map, float* acc_map,
+                   float* weights, float* alpha, void* stream);
+
+/* isample_from_lineseg + sample_pdf, det=True (core/utils/ray_utils.py:157-201,255-289):
+ * z [n,64], weights [n,64] -> z_samples [n,16], z_sorted [n,80], pdf_inds [n,16],
+ * sorted_idxs [n,80] (position in cat[z, z_samples] of each sorted element). */
+PGN_API int  pgn_sample_pdf(pgn_context* ctx, const float* z, const float* weights, int64_t n,
+                    float* z_samples, float* z_sorted, int32_t* pdf_inds, int32_t* sorted_idxs,
+                    void* stream);
+
+/* "next" row 1: on-device pixel rays for a bbox
+ * (get_rays + kp_to_valid_rays, core/utils/ray_utils.py:6-28,83-136).
+ * c2w: HOST [3,4] row-major.  Writes ray_batch [ (y1-y0)*(x1-x0), 11 ]. */
+PGN_API int  pgn_generate_rays(pgn_context* ctx, int32_t H, int32_t W, float focal, const float* c2w,
+                       int32_t x0, int32_t y0, int32_t x1, int32_t y1, float* ray_batch, void* stream);
+
+/* white/constant background composite + scatter into the full frame
+ * (run_nerf.py:100-133): image[valid] = rgb + (1-acc)*bg.  image: device [H*W,3]
+ * pre-filled by this call with `bg`. */
+PGN_API int  pgn_compose_frame(pgn_context* ctx, int32_t H, int32_t W, int32_t x0, int32_t y0, int32_t x1, int32_t y1,
+                       const float* rgb_map, const float* acc_map, float bg, float* image, void* stream);
+
+/* bring-up probe of the tcgen05 plumbing: D[128,N] = A[128,K] * B[N,K]^T with bf16 inputs
+ * and fp32 accumulation, one CTA.  variant bit 0 swaps the descriptor LBO/SBO fields
+ * (expected to be WRONG; kept so tests can assert the documented convention). */
+PGN_API int  pgn_debug_umma_gemm(pgn_context* ctx, const float* A, const float* B, float* D, int32_t K, int32_t N,
+                                 int32_t variant, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POSEGEN_B200_H */

@@ -1,0 +1,327 @@
+// C ABI of posegen_b200 (include/posegen_b200.h): context, weight repacking, launches.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdarg>
+#include <cstring>
+#include <new>
+#include "../../include/posegen_b200.h"
+#include "pgn_kernels.h"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define PGN_CUDA(expr)                                                                              \
+  do {                                                                                              \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess) return fail(PGN_E_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                                       __FILE__, __LINE__);                                         \
+  } while (0)
+
+// (out, in) of the 12 linear layers, include/posegen_b200.h order
+const int kOut[PGN_N_LINEAR] = {256, 256, 256, 256, 256, 256, 256, 256, 1, 256, 128, 3};
+const int kIn[PGN_N_LINEAR]  = {432, 256, 256, 256, 256, 688, 256, 256, 256, 256, 904, 128};
+
+size_t weight_floats() { size_t t = 0; for (int i = 0; i < PGN_N_LINEAR; ++i) t += (size_t)kOut[i] * kIn[i]; return t; }
+size_t bias_floats() { size_t t = 0; for (int i = 0; i < PGN_N_LINEAR; ++i) t += kOut[i]; return t; }
+
+}  // namespace
+
+struct pgn_context {
+  pgn_config cfg;
+  int num_sms;
+  PgnScalars h_sc;
+  PgnScalars* d_sc;
+  bool have_sc;
+  bool have_w[2];
+  // raw copies of the parameters (nn.Linear layout) on the device
+  float* d_w[2];
+  float* d_b[2];
+  const float* w_ptr[2][PGN_N_LINEAR];
+  const float* b_ptr[2][PGN_N_LINEAR];
+  // fp32 engine: transposed weights
+  float* d_wt[2];
+  PgnFp32Net fp32[2];
+  // bf16 engine
+  __nv_bfloat16* d_wstream[2];
+  float* d_bf16_aux[2];     // bias[9*256] | w_alpha[256] | w_rgb[384]
+  float* d_fold;
+  PgnBf16Net bf16[2];
+  int* d_status;
+  float* d_c2w;
+  int64_t launches;
+};
+
+extern "C" {
+
+int pgn_abi_version(void) { return PGN_ABI_VERSION; }
+const char* pgn_last_error(void) { return g_err; }
+
+int pgn_create(const pgn_config* cfg, pgn_context** out) {
+  if (!cfg || !out) return fail(PGN_E_INVALID, "pgn_create: null argument");
+  if (cfg->n_joints != PGN_J || cfg->n_samples != PGN_S || cfg->n_importance != PGN_I || cfg->multires != PGN_LV ||
+      cfg->multires_views != PGN_LD || cfg->net_depth != 8 || cfg->net_width != PGN_W || cfg->skip_layer != 4)
+    return fail(PGN_E_INVALID, "pgn_create: only the surreal.txt architecture is supported "
+                "(24 joints, 64+16 samples, multires 7/4, 8x256 MLP, skip 4)");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(PGN_E_CUDA, "pgn_create: no CUDA device (%s); posegen_b200 has no CPU fallback",
+                e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(PGN_E_INVALID, "pgn_create: bad device ordinal %d", cfg->device);
+  PGN_CUDA(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  PGN_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10) return fail(PGN_E_INVALID, "pgn_create: device is sm_%d%d; this library is built for sm_100a only", prop.major, prop.minor);
+  pgn_context* c = new (std::nothrow) pgn_context();
+  if (!c) return fail(PGN_E_INVALID, "pgn_create: out of host memory");
+  memset(c, 0, sizeof(*c));
+  c->cfg = *cfg;
+  c->num_sms = prop.multiProcessorCount;
+  for (int i = 0; i < PGN_S; ++i) c->h_sc.t_coarse[i] = pgn_linspace01(i, PGN_S);
+  for (int i = 0; i < PGN_I; ++i) c->h_sc.u_det[i] = pgn_linspace01(i, PGN_I);
+  PGN_CUDA(cudaMalloc(&c->d_sc, sizeof(PgnScalars)));
+  PGN_CUDA(cudaMalloc(&c->d_status, sizeof(int)));
+  PGN_CUDA(cudaMemset(c->d_status, 0, sizeof(int)));
+  PGN_CUDA(cudaMalloc(&c->d_c2w, 12 * sizeof(float)));
+  PGN_CUDA(cudaMalloc(&c->d_fold, (128 * 256 + 128) * sizeof(float)));
+  for (int n = 0; n < 2; ++n) {
+    PGN_CUDA(cudaMalloc(&c->d_w[n], weight_floats() * sizeof(float)));
+    PGN_CUDA(cudaMalloc(&c->d_b[n], bias_floats() * sizeof(float)));
+    PGN_CUDA(cudaMalloc(&c->d_wt[n], weight_floats() * sizeof(float)));
+    PGN_CUDA(cudaMalloc(&c->d_wstream[n], pgn_bf16_wstream_elems() * sizeof(__nv_bfloat16)));
+    PGN_CUDA(cudaMalloc(&c->d_bf16_aux[n], (9 * 256 + 256 + 384) * sizeof(float)));
+    size_t wo = 0, bo = 0;
+    for (int l = 0; l < PGN_N_LINEAR; ++l) {
+      c->w_ptr[n][l] = c->d_w[n] + wo;
+      c->b_ptr[n][l] = c->d_b[n] + bo;
+      c->fp32[n].wt[l] = c->d_wt[n] + wo;
+      c->fp32[n].b[l] = c->d_b[n] + bo;
+      wo += (size_t)kOut[l] * kIn[l];
+      bo += kOut[l];
+    }
+    c->fp32[n].w_alpha = c->w_ptr[n][8];
+    c->fp32[n].b_alpha = c->b_ptr[n][8];
+    c->fp32[n].w_rgb = c->w_ptr[n][11];
+    c->fp32[n].b_rgb = c->b_ptr[n][11];
+    c->bf16[n].wstream = c->d_wstream[n];
+    c->bf16[n].bias = c->d_bf16_aux[n];
+    c->bf16[n].w_alpha = c->d_bf16_aux[n] + 9 * 256;
+    c->bf16[n].w_rgb = c->d_bf16_aux[n] + 9 * 256 + 256;
+    c->bf16[n].b_alpha = c->b_ptr[n][8];
+    c->bf16[n].b_rgb = c->b_ptr[n][11];
+  }
+  *out = c;
+  return PGN_OK;
+}
+
+void pgn_destroy(pgn_context* c) {
+  if (!c) return;
+  cudaSetDevice(c->cfg.device);
+  cudaFree(c->d_sc); cudaFree(c->d_status); cudaFree(c->d_c2w); cudaFree(c->d_fold);
+  for (int n = 0; n < 2; ++n) {
+    cudaFree(c->d_w[n]); cudaFree(c->d_b[n]); cudaFree(c->d_wt[n]); cudaFree(c->d_wstream[n]); cudaFree(c->d_bf16_aux[n]);
+  }
+  delete c;
+}
+
+int pgn_upload_weights(pgn_context* c, int net_id, const pgn_net_weights* w, int pointers_are_device, void* stream_) {
+  if (!c || !w || net_id < 0 || net_id > 1) return fail(PGN_E_INVALID, "pgn_upload_weights: bad argument");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  PGN_CUDA(cudaSetDevice(c->cfg.device));
+  const cudaMemcpyKind kind = pointers_are_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  for (int l = 0; l < PGN_N_LINEAR; ++l) {
+    if (!w->weight[l] || !w->bias[l]) return fail(PGN_E_INVALID, "pgn_upload_weights: null tensor %d", l);
+    PGN_CUDA(cudaMemcpyAsync((void*)c->w_ptr[net_id][l], w->weight[l], (size_t)kOut[l] * kIn[l] * sizeof(float), kind, stream));
+    PGN_CUDA(cudaMemcpyAsync((void*)c->b_ptr[net_id][l], w->bias[l], (size_t)kOut[l] * sizeof(float), kind, stream));
+  }
+  for (int l = 0; l < PGN_N_LINEAR; ++l) {
+    if (l == 8 || l == 11) continue;   // small heads keep nn.Linear layout
+    PGN_CUDA(pgn_launch_transpose(c->w_ptr[net_id][l], kOut[l], kIn[l], (float*)c->fp32[net_id].wt[l], stream));
+    c->launches++;
+  }
+  PGN_CUDA(pgn_pack_bf16_net(c->w_ptr[net_id], c->b_ptr[net_id], c->d_wstream[net_id], c->d_bf16_aux[net_id],
+                             c->d_bf16_aux[net_id] + 9 * 256, c->d_bf16_aux[net_id] + 9 * 256 + 256, c->d_fold, stream));
+  c->launches += 2;
+  c->have_w[net_id] = true;
+  return PGN_OK;
+}
+
+int pgn_set_embed_scalars(pgn_context* c, float tau_v, float tau_d, const float* cutoff_v, const float* cutoff_d,
+                          float density_scale, float rgb_eps) {
+  if (!c || !cutoff_v || !cutoff_d) return fail(PGN_E_INVALID, "pgn_set_embed_scalars: null argument");
+  if (!(density_scale > 0.f)) return fail(PGN_E_INVALID, "pgn_set_embed_scalars: density_scale must be > 0");
+  PGN_CUDA(cudaSetDevice(c->cfg.device));
+  c->h_sc.tau_v = tau_v; c->h_sc.tau_d = tau_d;
+  memcpy(c->h_sc.cutoff_v, cutoff_v, PGN_J * sizeof(float));
+  memcpy(c->h_sc.cutoff_d, cutoff_d, PGN_J * sizeof(float));
+  c->h_sc.density_scale = density_scale; c->h_sc.rgb_eps = rgb_eps;
+  PGN_CUDA(cudaMemcpy(c->d_sc, &c->h_sc, sizeof(PgnScalars), cudaMemcpyHostToDevice));
+  c->have_sc = true;
+  return PGN_OK;
+}
+
+size_t pgn_workspace_bytes(const pgn_context* c, int64_t n_rays) {
+  (void)c;
+  if (n_rays < 0) n_rays = 0;
+  return ((size_t)n_rays * 2 * sizeof(float) + 255) / 256 * 256 + 256;
+}
+
+static int check_inputs(const pgn_context* c, const pgn_render_inputs* in, const char* who) {
+  if (!c || !in) return fail(PGN_E_INVALID, "%s: null argument", who);
+  if (in->n_rays < 0) return fail(PGN_E_INVALID, "%s: negative n_rays", who);
+  if (in->n_rays > 0 && (!in->ray_batch || !in->skts || !in->cyls)) return fail(PGN_E_INVALID, "%s: null input tensor", who);
+  if (!in->pose_idx) {
+    if (in->skts_stride != 0 && in->skts_stride != PGN_J * 16) return fail(PGN_E_INVALID, "%s: skts_stride must be 0 or 384", who);
+    if (in->cyls_stride != 0 && in->cyls_stride != 5) return fail(PGN_E_INVALID, "%s: cyls_stride must be 0 or 5", who);
+  }
+  return PGN_OK;
+}
+
+static PgnRayRefs make_refs(const pgn_render_inputs* in) {
+  PgnRayRefs r;
+  r.ray_batch = in->ray_batch; r.n_rays = in->n_rays; r.skts = in->skts; r.skts_stride = in->skts_stride;
+  r.cyls = in->cyls; r.cyls_stride = in->cyls_stride; r.pose_idx = in->pose_idx;
+  return r;
+}
+
+int pgn_render_forward(pgn_context* c, const pgn_render_inputs* in, const pgn_render_outputs* out,
+                       void* workspace, size_t workspace_bytes, void* stream_) {
+  int rc = check_inputs(c, in, "pgn_render_forward");
+  if (rc) return rc;
+  if (!out) return fail(PGN_E_INVALID, "pgn_render_forward: null outputs");
+  if (!c->have_sc || !c->have_w[0] || !c->have_w[1]) return fail(PGN_E_STATE, "pgn_render_forward: weights/scalars not uploaded");
+  if (in->precision != PGN_PRECISION_FP32 && in->precision != PGN_PRECISION_BF16) return fail(PGN_E_INVALID, "pgn_render_forward: bad precision");
+  if (in->n_rays == 0) return PGN_OK;
+  if (!workspace || workspace_bytes < pgn_workspace_bytes(c, in->n_rays)) return fail(PGN_E_INVALID, "pgn_render_forward: workspace too small");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  PGN_CUDA(cudaSetDevice(c->cfg.device));
+  const PgnRayRefs refs = make_refs(in);
+  float* near_far = (float*)workspace;
+  PGN_CUDA(pgn_launch_near_far(refs, in->nanfill_chunk, near_far, stream));
+  c->launches++;
+  PgnOutputs o;
+  o.rgb_map = out->rgb_map; o.disp_map = out->disp_map; o.acc_map = out->acc_map; o.alpha = out->alpha;
+  o.rgb0 = out->rgb0; o.disp0 = out->disp0; o.acc0 = out->acc0; o.alpha0 = out->alpha0;
+  o.z_samples = out->z_samples; o.z_fine = out->z_fine; o.pdf_inds = out->pdf_inds; o.weights0 = out->weights0;
+  o.raw0 = out->raw0; o.raw = out->raw; o.near_far = out->near_far;
+  if (out->near_far)
+    PGN_CUDA(cudaMemcpyAsync(out->near_far, near_far, (size_t)in->n_rays * 2 * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+  if (in->precision == PGN_PRECISION_FP32)
+    PGN_CUDA(pgn_launch_render_fp32(refs, o, c->fp32[0], c->fp32[1], c->d_sc, near_far, c->num_sms, stream));
+  else
+    PGN_CUDA(pgn_launch_render_bf16(refs, o, c->bf16[0], c->bf16[1], c->d_sc, near_far, c->d_status, c->num_sms, stream));
+  c->launches++;
+  return PGN_OK;
+}
+
+int64_t pgn_launch_count(const pgn_context* c) { return c ? c->launches : 0; }
+
+int pgn_check_device_status(pgn_context* c) {
+  if (!c) return fail(PGN_E_INVALID, "pgn_check_device_status: null context");
+  PGN_CUDA(cudaSetDevice(c->cfg.device));
+  int st = 0;
+  PGN_CUDA(cudaMemcpy(&st, c->d_status, sizeof(int), cudaMemcpyDeviceToHost));
+  if (st != 0) {
+    cudaMemset(c->d_status, 0, sizeof(int));
+    return fail(PGN_E_KERNEL, "device watchdog tripped: pipeline wait code %d", st);
+  }
+  return PGN_OK;
+}
+
+int pgn_near_far(pgn_context* c, const pgn_render_inputs* in, float* near_far, void* stream) {
+  int rc = check_inputs(c, in, "pgn_near_far");
+  if (rc) return rc;
+  if (!near_far) return fail(PGN_E_INVALID, "pgn_near_far: null output");
+  PGN_CUDA(cudaSetDevice(c->cfg.device));
+  PGN_CUDA(pgn_launch_near_far(make_refs(in), in->nanfill_chunk, near_far, (cudaStream_t)stream));
+  c->launches++;
+  return PGN_OK;
+}
+
+int pgn_encode(pgn_context* c, const pgn_render_inputs* in, const float* z, int32_t n_z, float* enc, void* stream) {
+  int rc = check_inputs(c, in, "pgn_encode");
+  if (rc) return rc;
+  if (!z || !enc || n_z <= 0) return fail(PGN_E_INVALID, "pgn_encode: bad argument");
+  if (!c->have_sc) return fail(PGN_E_STATE, "pgn_encode: scalars not set");
+  PGN_CUDA(cudaSetDevice(c->cfg.device));
+  PGN_CUDA(pgn_launch_encode(make_refs(in), c->d_sc, z, n_z, enc, (cudaStream_t)stream));
+  c->launches++;
+  return PGN_OK;
+}
+
+int pgn_mlp(pgn_context* c, int net_id, const float* enc, int64_t m, float* raw, int32_t precision, void* stream) {
+  if (!c || !enc || !raw || net_id < 0 || net_id > 1 || m < 0) return fail(PGN_E_INVALID, "pgn_mlp: bad argument");
+  if (!c->have_w[net_id]) return fail(PGN_E_STATE, "pgn_mlp: weights not uploaded");
+  PGN_CUDA(cudaSetDevice(c->cfg.device));
+  if (precision == PGN_PRECISION_FP32)
+    PGN_CUDA(pgn_launch_mlp_fp32(c->fp32[net_id], enc, m, raw, c->num_sms, (cudaStream_t)stream));
+  else if (precision == PGN_PRECISION_BF16)
+    PGN_CUDA(pgn_launch_mlp_bf16(c->bf16[net_id], enc, m, raw, c->d_sc, c->d_status, c->num_sms, (cudaStream_t)stream));
+  else return fail(PGN_E_INVALID, "pgn_mlp: bad precision");
+  c->launches++;
+  return PGN_OK;
+}
+
+int pgn_composite(pgn_context* c, const pgn_render_inputs* in, const float* raw, const float* z, int32_t s,
+                  float* rgb_map, float* disp_map, float* acc_map, float* weights, float* alpha, void* stream) {
+  int rc = check_inputs(c, in, "pgn_composite");
+  if (rc) return rc;
+  if (!raw || !z || (s != PGN_S && s != PGN_T)) return fail(PGN_E_INVALID, "pgn_composite: s must be 64 or 80");
+  if (!c->have_sc) return fail(PGN_E_STATE, "pgn_composite: scalars not set");
+  PGN_CUDA(cudaSetDevice(c->cfg.device));
+  PGN_CUDA(pgn_launch_composite(make_refs(in), c->d_sc, raw, z, s, rgb_map, disp_map, acc_map, weights, alpha, (cudaStream_t)stream));
+  c->launches++;
+  return PGN_OK;
+}
+
+int pgn_sample_pdf(pgn_context* c, const float* z, const float* weights, int64_t n, float* z_samples, float* z_sorted,
+                   int32_t* pdf_inds, int32_t* sorted_idxs, void* stream) {
+  if (!c || !z || !weights || n < 0) return fail(PGN_E_INVALID, "pgn_sample_pdf: bad argument");
+  PGN_CUDA(cudaSetDevice(c->cfg.device));
+  if (!c->have_sc) {  // only the linspace tables are needed
+    PGN_CUDA(cudaMemcpy(c->d_sc, &c->h_sc, sizeof(PgnScalars), cudaMemcpyHostToDevice));
+  }
+  PGN_CUDA(pgn_launch_sample_pdf(c->d_sc, z, weights, n, z_samples, z_sorted, pdf_inds, sorted_idxs, (cudaStream_t)stream));
+  c->launches++;
+  return PGN_OK;
+}
+
+int pgn_generate_rays(pgn_context* c, int32_t H, int32_t W, float focal, const float* c2w, int32_t x0, int32_t y0,
+                      int32_t x1, int32_t y1, float* ray_batch, void* stream_) {
+  if (!c || !c2w || !ray_batch || x1 < x0 || y1 < y0) return fail(PGN_E_INVALID, "pgn_generate_rays: bad argument");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  PGN_CUDA(cudaSetDevice(c->cfg.device));
+  PGN_CUDA(cudaMemcpyAsync(c->d_c2w, c2w, 12 * sizeof(float), cudaMemcpyHostToDevice, stream));
+  PGN_CUDA(pgn_launch_generate_rays(H, W, focal, c->d_c2w, x0, y0, x1, y1, ray_batch, stream));
+  c->launches++;
+  return PGN_OK;
+}
+
+int pgn_compose_frame(pgn_context* c, int32_t H, int32_t W, int32_t x0, int32_t y0, int32_t x1, int32_t y1,
+                      const float* rgb_map, const float* acc_map, float bg, float* image, void* stream) {
+  if (!c || !image || ((x1 > x0 && y1 > y0) && (!rgb_map || !acc_map))) return fail(PGN_E_INVALID, "pgn_compose_frame: bad argument");
+  PGN_CUDA(cudaSetDevice(c->cfg.device));
+  PGN_CUDA(pgn_launch_compose_frame(H, W, x0, y0, x1, y1, rgb_map, acc_map, bg, image, (cudaStream_t)stream));
+  c->launches++;
+  return PGN_OK;
+}
+
+int pgn_debug_umma_gemm(pgn_context* c, const float* A, const float* B, float* D, int32_t K, int32_t N,
+                        int32_t variant, void* stream) {
+  if (!c || !A || !B || !D || K <= 0 || K % 16 || N < 16 || N > 256 || N % 16) return fail(PGN_E_INVALID, "pgn_debug_umma_gemm: bad argument");
+  if ((size_t)(K / 8) * 2048 + (size_t)(K / 8) * N * 16 > 200 * 1024) return fail(PGN_E_INVALID, "pgn_debug_umma_gemm: K too large");
+  PGN_CUDA(cudaSetDevice(c->cfg.device));
+  PGN_CUDA(pgn_launch_probe_umma(A, B, D, K, N, variant, c->d_status, (cudaStream_t)stream));
+  c->launches++;
+  return PGN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,322 @@
+// Shared device code of the posegen_b200 renderer: parameter blocks and the
+// per-ray / per-sample math every kernel uses (near/far, z tables, joint-frame
+// geometry, cutoff window, compositing, inverse-CDF resampling).
+//
+// Each function cites the reference lines it re-implements (paths relative to the
+// reference repo).  fp32 throughout; the places where the reference's unfused
+// multiply/add order is observable (near/far, z, pts) use explicit _rn intrinsics so
+// nvcc cannot contract them into FMAs.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#define PGN_J 24          // joints
+#define PGN_S 64          // coarse samples
+#define PGN_I 16          // importance samples
+#define PGN_T 80          // S + I
+#define PGN_LV 7          // multires (distance PE)
+#define PGN_LD 4          // multires_views
+#define PGN_ENC 1080      // 360 + 72 + 648
+#define PGN_ENC_P 432     // density-net input
+#define PGN_ENC_D 648     // view input
+#define PGN_W 256
+
+struct PgnScalars {
+  float tau_v, tau_d;
+  float cutoff_v[PGN_J];
+  float cutoff_d[PGN_J];
+  float density_scale, rgb_eps;
+  float t_coarse[PGN_S];   // torch.linspace(0,1,64)
+  float u_det[PGN_I];      // torch.linspace(0,1,16)
+};
+
+struct PgnRayRefs {
+  const float*   ray_batch;     // [n,11]
+  long long      n_rays;
+  const float*   skts;
+  long long      skts_stride;
+  const float*   cyls;
+  long long      cyls_stride;
+  const int*     pose_idx;
+};
+
+struct PgnOutputs {
+  float *rgb_map, *disp_map, *acc_map, *alpha, *rgb0, *disp0, *acc0, *alpha0;
+  float *z_samples, *z_fine; int *pdf_inds; float *weights0, *raw0, *raw, *near_far;
+};
+
+__device__ __forceinline__ const float* pgn_ray_skts(const PgnRayRefs& r, long long i) {
+  if (r.pose_idx) return r.skts + (long long)r.pose_idx[i] * (PGN_J * 16);
+  return r.skts + i * r.skts_stride;
+}
+__device__ __forceinline__ const float* pgn_ray_cyl(const PgnRayRefs& r, long long i) {
+  if (r.pose_idx) return r.cyls + (long long)r.pose_idx[i] * 5;
+  return r.cyls + i * r.cyls_stride;
+}
+
+// torch.linspace(start=0,end=1,steps=n) on CPU: symmetric evaluation around the midpoint.
+__host__ __device__ inline float pgn_linspace01(int i, int n) {
+  float step = 1.0f / (float)(n - 1);
+  return (i < n / 2) ? step * (float)i : 1.0f - step * (float)(n - 1 - i);
+}
+
+// ---------------------------------------------------------------------------
+// get_near_far_in_cylinder, core/utils/ray_utils.py:292-344 (without the NaN fill)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void pgn_near_far_ray(const float* __restrict__ rb, const float* __restrict__ cyl,
+                                                 float& new_near, float& new_far) {
+  const float ox = rb[0], oz = rb[2], dx = rb[3], dz = rb[5], near = rb[6], far = rb[7];
+  const float rnx = __fadd_rn(ox, __fmul_rn(dx, near)), rnz = __fadd_rn(oz, __fmul_rn(dz, near));
+  const float rfx = __fadd_rn(ox, __fmul_rn(dx, far)),  rfz = __fadd_rn(oz, __fmul_rn(dz, far));
+  const float ncx = __fsub_rn(cyl[0], rnx), ncz = __fsub_rn(cyl[1], rnz);
+  const float nfx = __fsub_rn(rfx, rnx),    nfz = __fsub_rn(rfz, rnz);
+  const float nf_norm = __fsqrt_rn(__fadd_rn(__fmul_rn(nfx, nfx), __fmul_rn(nfz, nfz)));
+  const float scale   = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dz, dz)));
+  const float cross = __fsub_rn(__fmul_rn(ncx, nfz), __fmul_rn(ncz, nfx));
+  const float dist = __fdiv_rn(fabsf(cross), nf_norm);
+  const float R = cyl[2];
+  const float Q = __fsqrt_rn(__fsub_rn(__fmul_rn(R, R), __fmul_rn(dist, dist)));   // NaN if the ray misses
+  const float K = __fdiv_rn(__fadd_rn(__fmul_rn(ncx, nfx), __fmul_rn(ncz, nfz)), nf_norm);
+  const float mask = (Q < K) ? 1.0f : 0.0f;
+  new_near = __fadd_rn(near, __fdiv_rn(__fmul_rn(mask, __fsub_rn(K, Q)), scale));
+  new_far  = __fadd_rn(near, __fdiv_rn(__fadd_rn(K, Q), scale));
+}
+
+// sample_from_lineseg, core/utils/ray_utils.py:204-251 (perturb=0, lindisp=False)
+__device__ __forceinline__ float pgn_coarse_z(float near, float far, float t) {
+  return __fadd_rn(__fmul_rn(near, __fsub_rn(1.0f, t)), __fmul_rn(far, t));
+}
+
+// ---------------------------------------------------------------------------
+// Joint-frame geometry of one (sample, joint):
+//   pts = o + d*z                                   core/raycasters.py:658
+//   pts_t = R_j pts + t_j                           core/encoders.py:8-23
+//   v = ||pts_t||, r = pts_t / max(v, 1e-12)        core/encoders.py:110-122,181-193
+//   w = 1 - sigmoid(tau * (v - cutoff_j))           core/cutoff_embedder.py:148-156
+// skt points at the joint's 4x4 (row-major).
+// ---------------------------------------------------------------------------
+struct PgnJointGeom { float v, w, rx, ry, rz; };
+
+template <bool kFast>
+__device__ __forceinline__ float pgn_window(float v, float tau, float cutoff) {
+  const float x = tau * (v - cutoff);
+  if (kFast) return 1.0f - __fdividef(1.0f, 1.0f + __expf(-x));
+  return 1.0f - 1.0f / (1.0f + expf(-x));
+}
+
+template <bool kFast>
+__device__ __forceinline__ PgnJointGeom pgn_joint_geom(const float4 m0, const float4 m1, const float4 m2,
+                                                       float px, float py, float pz, float tau, float cutoff) {
+  PgnJointGeom g;
+  const float x = fmaf(m0.z, pz, fmaf(m0.y, py, m0.x * px)) + m0.w;
+  const float y = fmaf(m1.z, pz, fmaf(m1.y, py, m1.x * px)) + m1.w;
+  const float z = fmaf(m2.z, pz, fmaf(m2.y, py, m2.x * px)) + m2.w;
+  const float n2 = fmaf(z, z, fmaf(y, y, x * x));
+  g.v = sqrtf(n2);
+  if (kFast) {
+    const float inv = __fdividef(1.0f, fmaxf(g.v, 1e-12f));
+    g.rx = x * inv; g.ry = y * inv; g.rz = z * inv;
+  } else {
+    const float den = fmaxf(g.v, 1e-12f);
+    g.rx = x / den; g.ry = y / den; g.rz = z / den;
+  }
+  g.w = pgn_window<kFast>(g.v, tau, cutoff);
+  return g;
+}
+
+__device__ __forceinline__ void pgn_sample_point(const float* o, const float* d, float z, float& px, float& py, float& pz) {
+  px = __fadd_rn(o[0], __fmul_rn(d[0], z));
+  py = __fadd_rn(o[1], __fmul_rn(d[1], z));
+  pz = __fadd_rn(o[2], __fmul_rn(d[2], z));
+}
+
+// normalised ray direction in a joint frame: F.normalize(R_j d), core/encoders.py:25-37,181-193
+__device__ __forceinline__ void pgn_joint_dir(const float4 m0, const float4 m1, const float4 m2,
+                                              const float* d, float& x, float& y, float& z) {
+  x = fmaf(m0.z, d[2], fmaf(m0.y, d[1], m0.x * d[0]));
+  y = fmaf(m1.z, d[2], fmaf(m1.y, d[1], m1.x * d[0]));
+  z = fmaf(m2.z, d[2], fmaf(m2.y, d[1], m2.x * d[0]));
+  const float den = fmaxf(sqrtf(fmaf(z, z, fmaf(y, y, x * x))), 1e-12f);
+  x = x / den; y = y / den; z = z / den;
+}
+
+// ---------------------------------------------------------------------------
+// Reference channel order of the 1080-vector:
+//   [0,360)    v-embed   c = k*24 + j,        k in {x, sin(2^0 x), cos(2^0 x), ... sin(2^6 x), cos(2^6 x)}, all * w_j
+//   [360,432)  r         c = 360 + j*3 + a
+//   [432,1080) d-embed   c = 432 + k*72 + j*3 + a, k in {x, sin(2^0 x), cos(2^0 x), ... cos(2^3 x)}, all * w_j
+// pgn_pe_term(x, k): k-th row of the positional encoding of scalar x (accurate sinf/cosf;
+// x * 2^f is exact in fp32, matching cutoff_embedder.py:139 inputs_freq = freq_bands * inputs).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float pgn_pe_term(float x, int k) {
+  if (k == 0) return x;
+  const int f = (k - 1) >> 1;
+  const float a = x * (float)(1 << f);
+  return ((k - 1) & 1) ? cosf(a) : sinf(a);
+}
+
+// ---------------------------------------------------------------------------
+// Warp-level compositing of one ray (raw2outputs, core/networks/nerf.py:150-205).
+// The calling warp owns the ray; sample i is handled by lane i / CH (CH consecutive
+// samples per lane) so the transmittance is a per-lane sequential product followed by
+// a warp-level exclusive prefix product over the lane totals.
+//   raw: smem/global [S][4] (rgb_raw, sigma_raw);  z: [S]
+// Outputs through pointers (any may be null); weights_out/alpha_out indexed [S].
+// ---------------------------------------------------------------------------
+template <int S>
+__device__ __forceinline__ void pgn_composite_warp(const float* __restrict__ raw, const float* __restrict__ z,
+                                                   float dnorm, float density_scale, float rgb_eps, int lane,
+                                                   float* rgb3, float* disp, float* acc,
+                                                   float* weights_out, float* alpha_out) {
+  constexpr int CH = (S + 31) / 32;
+  float a[CH], p[CH];
+  float lane_prod = 1.0f;
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    const int i = lane * CH + c;
+    float al = 0.0f;
+    if (i < S) {
+      float dist = (i + 1 < S) ? __fsub_rn(z[i + 1], z[i]) : 1e10f;
+      dist = __fmul_rn(dist, dnorm);
+      const float sig = fmaxf(raw[i * 4 + 3] / density_scale, 0.0f);
+      al = 1.0f - expf(-__fmul_rn(sig, dist));
+    }
+    a[c] = al;
+    p[c] = lane_prod;                                   // product of earlier samples in this lane
+    if (i < S) lane_prod = lane_prod * (__fadd_rn(__fsub_rn(1.0f, al), 1e-10f));
+  }
+  // exclusive prefix product of lane totals
+  float incl = lane_prod;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const float up = __shfl_up_sync(0xffffffffu, incl, off);
+    if (lane >= off) incl *= up;
+  }
+  float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+  if (lane == 0) excl = 1.0f;
+  float sr = 0.f, sg = 0.f, sb = 0.f, sw = 0.f, sd = 0.f;
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    const int i = lane * CH + c;
+    if (i < S) {
+      const float w = a[c] * (excl * p[c]);
+      if (weights_out) weights_out[i] = w;
+      if (alpha_out) alpha_out[i] = a[c];
+      const float k = 1.0f + 2.0f * rgb_eps;
+      const float r = (1.0f / (1.0f + expf(-raw[i * 4 + 0]))) * k - rgb_eps;
+      const float g = (1.0f / (1.0f + expf(-raw[i * 4 + 1]))) * k - rgb_eps;
+      const float b = (1.0f / (1.0f + expf(-raw[i * 4 + 2]))) * k - rgb_eps;
+      sr = fmaf(w, r, sr); sg = fmaf(w, g, sg); sb = fmaf(w, b, sb);
+      sw += w; sd = fmaf(w, z[i], sd);
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    sr += __shfl_xor_sync(0xffffffffu, sr, off);
+    sg += __shfl_xor_sync(0xffffffffu, sg, off);
+    sb += __shfl_xor_sync(0xffffffffu, sb, off);
+    sw += __shfl_xor_sync(0xffffffffu, sw, off);
+    sd += __shfl_xor_sync(0xffffffffu, sd, off);
+  }
+  if (lane == 0) {
+    if (rgb3) { rgb3[0] = sr; rgb3[1] = sg; rgb3[2] = sb; }
+    if (disp) {
+      // 1/max(1e-10, depth/(acc+1e-10)), zeroed where isclose(acc, 0) (atol 1e-8)
+      float dv = 1.0f / fmaxf(1e-10f, sd / (sw + 1e-10f));
+      if (fabsf(sw) <= 1e-8f) dv = 0.0f;
+      *disp = dv;
+    }
+    if (acc) *acc = fminf(sw, 1.0f);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Warp-level inverse-CDF resampling of one ray (det=True):
+//   sample_pdf            core/utils/ray_utils.py:157-201
+//   isample_from_lineseg  core/utils/ray_utils.py:255-289
+// z[64], weights[64] -> z_samples[16], z_sorted[80] (+ optional pdf_inds[16], sorted_idxs[80]).
+// scratch: 2*64 floats of shared memory private to the warp (cdf | bins).
+// Summation order (documented in DESIGN.md): sum and cumsum are accumulated in fp64 and
+// rounded once to fp32 (torch CPU cumsum accumulates float in double).
+// The search is a warp ballot: ind = #{k : cdf[k] <= u}.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void pgn_sample_pdf_warp(const float* __restrict__ z, const float* __restrict__ weights,
+                                                    const float* __restrict__ u_det, int lane, float* scratch,
+                                                    float* z_samples, float* z_sorted,
+                                                    int* pdf_inds, int* sorted_idxs) {
+  float* cdf = scratch;        // [63] (+1 pad)
+  float* bins = scratch + 64;  // [63]
+  // pdf over the 62 interior weights; lane handles k = lane and lane+32
+  float w0 = (lane < 62) ? __fadd_rn(weights[1 + lane], 1e-5f) : 0.0f;
+  float w1 = (lane + 32 < 62) ? __fadd_rn(weights[1 + lane + 32], 1e-5f) : 0.0f;
+  double s = (double)w0 + (double)w1;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  const float total = (float)s;
+  const float p0 = (lane < 62) ? __fdiv_rn(w0, total) : 0.0f;
+  const float p1 = (lane + 32 < 62) ? __fdiv_rn(w1, total) : 0.0f;
+  // inclusive scan in double over index order: first all p0 (k=0..31), then p1 (k=32..61)
+  double c0 = (double)p0;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const double up = __shfl_up_sync(0xffffffffu, c0, off);
+    if (lane >= off) c0 += up;
+  }
+  const double first_half = __shfl_sync(0xffffffffu, c0, 31);
+  double c1 = (double)p1;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const double up = __shfl_up_sync(0xffffffffu, c1, off);
+    if (lane >= off) c1 += up;
+  }
+  c1 += first_half;
+  if (lane == 0) cdf[0] = 0.0f;
+  cdf[1 + lane] = (float)c0;                         // k = lane      -> cdf index lane+1 (1..32)
+  if (lane + 32 < 62) cdf[33 + lane] = (float)c1;    // k = lane+32   -> cdf index 33..62
+  // bins = midpoints of z (63)
+  bins[lane] = __fmul_rn(0.5f, __fadd_rn(z[lane + 1], z[lane]));
+  if (lane + 32 < 63) bins[lane + 32] = __fmul_rn(0.5f, __fadd_rn(z[lane + 33], z[lane + 32]));
+  __syncwarp();
+  const float ca = cdf[lane];
+  const float cb = (lane + 32 < 63) ? cdf[lane + 32] : INFINITY;
+  float my_sample = 0.0f;
+#pragma unroll
+  for (int k = 0; k < PGN_I; ++k) {
+    const float u = u_det[k];
+    const int ind = __popc(__ballot_sync(0xffffffffu, ca <= u)) + __popc(__ballot_sync(0xffffffffu, cb <= u));
+    if (lane == k) {
+      const int below = max(ind - 1, 0), above = min(ind, 62);
+      const float cdb = cdf[below], cda = cdf[above];
+      float denom = __fsub_rn(cda, cdb);
+      if (denom < 1e-5f) denom = 1.0f;
+      const float t = __fdiv_rn(__fsub_rn(u, cdb), denom);
+      my_sample = __fadd_rn(bins[below], __fmul_rn(t, __fsub_rn(bins[above], bins[below])));
+      if (pdf_inds) pdf_inds[k] = ind;
+    }
+  }
+  if (lane < PGN_I && z_samples) z_samples[lane] = my_sample;
+  // merge: rank of coarse z_i = i + #{samples < z_i}; rank of sample k = k + #{z_i <= sample_k}
+  __syncwarp();
+  float* samp = scratch;        // reuse (cdf no longer needed): samples in scratch[0..15]
+  __syncwarp();
+  if (lane < PGN_I) samp[lane] = my_sample;
+  __syncwarp();
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int i = lane + 32 * h;
+    const float zi = z[i];
+    int r = i;
+#pragma unroll
+    for (int k = 0; k < PGN_I; ++k) r += (samp[k] < zi) ? 1 : 0;
+    z_sorted[r] = zi;
+    if (sorted_idxs) sorted_idxs[r] = i;
+  }
+  if (lane < PGN_I) {
+    int r = lane;
+    for (int i = 0; i < PGN_S; ++i) r += (z[i] <= my_sample) ? 1 : 0;
+    z_sorted[r] = my_sample;
+    if (sorted_idxs) sorted_idxs[r] = PGN_S + lane;
+  }
+  __syncwarp();
+}

@@ -1,0 +1,67 @@
+// Internal (C++) interface between the C-ABI layer (pgn_api.cu) and the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include "pgn_common.cuh"
+
+// ---- fp32 CUDA-core engine -------------------------------------------------
+// wt[l]: transposed weights [K][N] of linear l (PGN linear order, include/posegen_b200.h);
+// small heads keep nn.Linear layout.
+struct PgnFp32Net {
+  const float* wt[12];
+  const float* b[12];
+  const float* w_alpha;  // [1][256]
+  const float* b_alpha;
+  const float* w_rgb;    // [3][128]
+  const float* b_rgb;
+};
+
+size_t pgn_fp32_smem_bytes();
+cudaError_t pgn_launch_render_fp32(const PgnRayRefs& rays, const PgnOutputs& out, const PgnFp32Net& nc,
+                                   const PgnFp32Net& nf, const PgnScalars* sc_dev, const float* near_far,
+                                   int num_sms, cudaStream_t stream);
+cudaError_t pgn_launch_mlp_fp32(const PgnFp32Net& net, const float* enc, long long m, float* raw,
+                                int num_sms, cudaStream_t stream);
+
+// ---- bf16 tcgen05 engine ---------------------------------------------------
+// The packed weight stream of one net: UMMA K-major slabs in consumption order
+// (layout documented in pgn_render_bf16.cu / DESIGN.md) + fp32 epilogue vectors.
+struct PgnBf16Net {
+  const __nv_bfloat16* wstream;   // packed slabs
+  const float* bias;              // [9][256] biases of the 9 MMA layers (view layer uses 128)
+  const float* w_alpha;           // [256]
+  const float* w_rgb;             // [3][128]
+  const float* b_alpha;           // [1]
+  const float* b_rgb;             // [3]
+};
+
+size_t pgn_bf16_wstream_elems();
+// pack one net (device fp32 nn.Linear tensors) into wstream/bias; runs on `stream`
+cudaError_t pgn_pack_bf16_net(const float* const* w_dev, const float* const* b_dev, __nv_bfloat16* wstream,
+                              float* bias, float* w_alpha, float* w_rgb, float* fold_tmp, cudaStream_t stream);
+cudaError_t pgn_launch_render_bf16(const PgnRayRefs& rays, const PgnOutputs& out, const PgnBf16Net& nc,
+                                   const PgnBf16Net& nf, const PgnScalars* sc_dev, const float* near_far,
+                                   int* status, int num_sms, cudaStream_t stream);
+cudaError_t pgn_launch_mlp_bf16(const PgnBf16Net& net, const float* enc, long long m, float* raw,
+                                const PgnScalars* sc_dev, int* status, int num_sms, cudaStream_t stream);
+
+// ---- stage kernels ---------------------------------------------------------
+cudaError_t pgn_launch_near_far(const PgnRayRefs& rays, long long chunk, float* near_far, cudaStream_t stream);
+cudaError_t pgn_launch_encode(const PgnRayRefs& rays, const PgnScalars* sc_dev, const float* z, int n_z,
+                              float* enc, cudaStream_t stream);
+cudaError_t pgn_launch_composite(const PgnRayRefs& rays, const PgnScalars* sc_dev, const float* raw, const float* z,
+                                 int s, float* rgb, float* disp, float* acc, float* weights, float* alpha,
+                                 cudaStream_t stream);
+cudaError_t pgn_launch_sample_pdf(const PgnScalars* sc_dev, const float* z, const float* weights, long long n,
+                                  float* z_samples, float* z_sorted, int* pdf_inds, int* sorted_idxs,
+                                  cudaStream_t stream);
+cudaError_t pgn_launch_transpose(const float* w, int out_f, int in_f, float* wt, cudaStream_t stream);
+cudaError_t pgn_launch_generate_rays(int H, int W, float focal, const float* c2w12_dev, int x0, int y0, int x1, int y1,
+                                     float* ray_batch, cudaStream_t stream);
+cudaError_t pgn_launch_compose_frame(int H, int W, int x0, int y0, int x1, int y1, const float* rgb, const float* acc,
+                                     float bg, float* image, cudaStream_t stream);
+
+// bring-up probe (pgn_probe.cu)
+cudaError_t pgn_launch_probe_umma(const float* A, const float* B, float* D, int K, int N, int variant, int* status,
+                                  cudaStream_t stream);

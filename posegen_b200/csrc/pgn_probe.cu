@@ -1,0 +1,70 @@
+// Bring-up probe for the tcgen05 plumbing used by pgn_render_bf16.cu: one CTA computes
+// D[128][N] = A[128][K] * B[N][K]^T (bf16 inputs, fp32 accumulate) with the same shared
+// memory layout ([k/8][row][8], SWIZZLE_NONE K-major), descriptors, commit/mbarrier and
+// TMEM load path as the render kernel.  `variant` bit 0 swaps the LBO/SBO fields so a
+// single GPU run settles the descriptor convention.
+#include "pgn_umma.cuh"
+#include "pgn_kernels.h"
+
+using namespace pgn;
+
+__global__ void __launch_bounds__(128, 1)
+pgn_probe_umma_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D, int K, int N,
+                      int variant, int* __restrict__ status_g) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem;                          // K/8 runs of 128 rows x 16 B
+  uint8_t* sB = smem + (size_t)(K / 8) * 2048; // K/8 runs of N rows x 16 B
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  volatile int* status = status_g;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < 128 * K; i += 128) {
+    const int r = i / K, k = i % K;
+    *reinterpret_cast<__nv_bfloat16*>(sA + (size_t)(k / 8) * 2048 + r * 16 + (k % 8) * 2) = __float2bfloat16_rn(A[i]);
+  }
+  for (int i = tid; i < N * K; i += 128) {
+    const int n = i / K, k = i % K;
+    *reinterpret_cast<__nv_bfloat16*>(sB + (size_t)(k / 8) * (N * 16) + n * 16 + (k % 8) * 2) = __float2bfloat16_rn(B[i]);
+  }
+  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  if (warp == 0) { tmem_alloc(&tmem_slot, 256); tmem_relinquish(); }
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  if (tid == 0) {
+    const uint32_t idesc = umma_idesc_bf16(128, N);
+    for (int ks = 0; ks < K / 16; ++ks) {
+      const uint32_t a_addr = smem_u32(sA) + ks * 2 * 2048;
+      const uint32_t b_addr = smem_u32(sB) + ks * 2 * (N * 16);
+      uint64_t ad, bd;
+      if (variant & 1) { ad = umma_smem_desc(a_addr, 128, 2048); bd = umma_smem_desc(b_addr, 128, N * 16); }
+      else             { ad = umma_smem_desc(a_addr, 2048, 128); bd = umma_smem_desc(b_addr, N * 16, 128); }
+      umma_bf16(tmem, ad, bd, idesc, ks > 0 ? 1u : 0u);
+    }
+    umma_commit(&bar);
+  }
+  __syncwarp();
+  mbar_wait(&bar, 0, status, 901);
+  tc_fence_after_sync();
+  const int row = warp * 32 + lane;
+  for (int c0 = 0; c0 < N; c0 += 32) {
+    uint32_t v[32];
+    tmem_ld_32x32(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+    tmem_ld_wait();
+    for (int i = 0; i < 32; ++i) D[(size_t)row * N + c0 + i] = __uint_as_float(v[i]);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after_sync(); tmem_dealloc(tmem, 256); }
+}
+
+cudaError_t pgn_launch_probe_umma(const float* A, const float* B, float* D, int K, int N, int variant, int* status,
+                                  cudaStream_t stream) {
+  const size_t smem = (size_t)(K / 8) * 2048 + (size_t)(K / 8) * N * 16 + 1024;
+  cudaError_t e = cudaFuncSetAttribute(pgn_probe_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  pgn_probe_umma_kernel<<<1, 128, smem, stream>>>(A, B, D, K, N, variant, status);
+  return cudaGetLastError();
+}

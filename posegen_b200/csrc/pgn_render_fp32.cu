@@ -1,0 +1,417 @@
+// fp32 CUDA-core render path (PGN_PRECISION_FP32): the 1e-3 parity tier.
+//
+// One persistent CTA per SM renders groups of 4 rays end to end:
+//   near/far (precomputed) -> coarse z -> [per 64-row tile: joint-frame geometry ->
+//   cutoff PE generated chunk-by-chunk straight into the GEMM's A stage -> 8x256 trunk,
+//   alpha head, feature, view branch, rgb head] -> compositing -> inverse-CDF
+//   resampling + merge -> the same MLP pipeline with the fine net on 80 samples ->
+//   compositing -> outputs.
+// Nothing of size samples x joints x embedding is written to global memory.
+//
+// Follows, stage by stage: core/raycasters.py:361-474 (render_rays), core/encoders.py,
+// core/cutoff_embedder.py:111-174, core/networks/nerf.py:94-205, core/utils/ray_utils.py:157-289.
+#include "pgn_common.cuh"
+#include "pgn_kernels.h"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kRPG = 4;            // rays per group
+constexpr int kTM = 64;            // rows per MLP tile
+constexpr int kKC = 16;            // K chunk
+constexpr int kHStride = kTM;      // h[k][row]
+
+struct Smem {
+  float h[2][PGN_W * kHStride];          // activations, k-major
+  float gv[PGN_J * kTM], gw[PGN_J * kTM], gwd[PGN_J * kTM], grx[PGN_J * kTM], gry[PGN_J * kTM], grz[PGN_J * kTM];
+  float dtab[kRPG][PGN_ENC_D];           // per-ray PE of the joint-frame view dirs (un-windowed)
+  float Bs[2][kKC * PGN_W];
+  float As[2][kKC * kTM];
+  float zc[kRPG][PGN_S];
+  float zf[kRPG][PGN_T];
+  float raw[kRPG][PGN_T * 4];
+  float wts[kRPG][PGN_S];
+  float scratch[kRPG][128];
+  float ray_o[kRPG][3], ray_d[kRPG][3], dnorm[kRPG];
+  float part[kTM * 4];                   // per-row network output (rgb_raw, sigma_raw)
+};
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// A-operand sources -----------------------------------------------------------
+enum ASrc { A_FROM_H = 0, A_ENC_P = 1, A_ENC_D = 2, A_GLOBAL = 3 };
+
+// value of encoded column `col` (reference channel order) for tile row `row`
+__device__ __forceinline__ float enc_value(const Smem& sm, int row, int ray_local, int col) {
+  if (col < 360) {
+    const int k = col / PGN_J, j = col - k * PGN_J;
+    return sm.gw[j * kTM + row] * pgn_pe_term(sm.gv[j * kTM + row], k);
+  } else if (col < PGN_ENC_P) {
+    const int c = col - 360, j = c / 3, a = c - j * 3;
+    return a == 0 ? sm.grx[j * kTM + row] : (a == 1 ? sm.gry[j * kTM + row] : sm.grz[j * kTM + row]);
+  } else {
+    const int c = col - PGN_ENC_P;
+    const int j = (c % 72) / 3;
+    return sm.gwd[j * kTM + row] * sm.dtab[ray_local][c];
+  }
+}
+
+// One dense layer on a 64-row tile: out[n][row] = act(sum_k A[k][row] * Wt[k][n] + b[n]).
+// Segments of K are given as (source, k_count) pairs; Wt rows follow the same order.
+struct Seg { int src; int k; int col0; };
+
+template <int N>   // N = 256 or 128
+__device__ void dense_layer(Smem& sm, const Seg* segs, int nseg, const float* __restrict__ Wt,
+                            const float* __restrict__ bias, bool relu, const float* h_in, float* h_out,
+                            const int* row_ray, const float* __restrict__ a_global, int a_ld, int rows_valid) {
+  constexpr int NPT = N / 32;                 // output columns per thread
+  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+  float acc[8][NPT];
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+#pragma unroll
+    for (int c = 0; c < NPT; ++c) acc[r][c] = 0.f;
+
+  int ktot = 0;
+  for (int s = 0; s < nseg; ++s) ktot += segs[s].k;
+  const int nchunks = (ktot + kKC - 1) / kKC;
+
+  auto load_B = [&](int chunk, int buf) {
+    const int k0 = chunk * kKC;
+    const int kv = min(kKC, ktot - k0);
+    const float* src = Wt + (size_t)k0 * N;
+    const int n16 = kv * N / 4;               // 16-byte packets
+    for (int p = tid; p < n16; p += kThreads) cp_async16(&sm.Bs[buf][p * 4], src + p * 4);
+    cp_async_commit();
+  };
+  // locate segment for absolute k
+  auto seg_of = [&](int k, int& src, int& col) {
+    int base = 0;
+    for (int s = 0; s < nseg; ++s) {
+      if (k < base + segs[s].k) { src = segs[s].src; col = segs[s].col0 + (k - base); return; }
+      base += segs[s].k;
+    }
+    src = -1; col = 0;
+  };
+
+  load_B(0, 0);
+  for (int chunk = 0; chunk < nchunks; ++chunk) {
+    const int buf = chunk & 1;
+    if (chunk + 1 < nchunks) load_B(chunk + 1, buf ^ 1);
+    const int k0 = chunk * kKC;
+    const int kv = min(kKC, ktot - k0);
+    // stage generated / global A columns of this chunk
+    {
+      const int row = tid & (kTM - 1);
+      for (int kk = tid >> 6; kk < kv; kk += kThreads / kTM) {
+        int src, col;
+        seg_of(k0 + kk, src, col);
+        float v = 0.f;
+        if (src == A_ENC_P || src == A_ENC_D) v = enc_value(sm, row, row_ray[row], col);
+        else if (src == A_GLOBAL) v = (row < rows_valid) ? a_global[(size_t)row * a_ld + col] : 0.f;
+        else v = h_in[col * kHStride + row];
+        sm.As[buf][kk * kTM + row] = v;
+      }
+    }
+    if (chunk + 1 < nchunks) cp_async_wait<1>(); else cp_async_wait<0>();
+    __syncthreads();
+    const float* Ab = sm.As[buf];
+    const float* Bb = sm.Bs[buf];
+#pragma unroll 4
+    for (int kk = 0; kk < kv; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(Ab + kk * kTM + ty * 8);
+      const float4 a1 = *reinterpret_cast<const float4*>(Ab + kk * kTM + ty * 8 + 4);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      float bv[NPT];
+#pragma unroll
+      for (int c4 = 0; c4 < NPT / 4; ++c4) {
+        const float4 b = *reinterpret_cast<const float4*>(Bb + kk * N + tx * NPT + c4 * 4);
+        bv[c4 * 4 + 0] = b.x; bv[c4 * 4 + 1] = b.y; bv[c4 * 4 + 2] = b.z; bv[c4 * 4 + 3] = b.w;
+      }
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c < NPT; ++c) acc[r][c] = fmaf(av[r], bv[c], acc[r][c]);
+    }
+    __syncthreads();
+  }
+  // epilogue: bias (+ReLU), store k-major for the next layer
+#pragma unroll
+  for (int c = 0; c < NPT; ++c) {
+    const int n = tx * NPT + c;
+    const float b = bias[n];
+    float o[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      float v = acc[r][c] + b;
+      o[r] = relu ? fmaxf(v, 0.f) : v;
+    }
+    float4* dst = reinterpret_cast<float4*>(h_out + n * kHStride + ty * 8);
+    dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+    dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+  }
+  __syncthreads();
+}
+
+// tiny heads: out[row][o] = sum_k h[k][row] * W[o][k] + b[o], NOUT in {1,3}; 4 threads per row
+template <int NOUT>
+__device__ void small_head(Smem& sm, const float* h, int K, const float* __restrict__ W,
+                           const float* __restrict__ b, float* out_row4 /* [row][4] */, int out_off) {
+  const int tid = threadIdx.x;
+  const int row = tid >> 2, q = tid & 3;
+  float acc[NOUT];
+#pragma unroll
+  for (int o = 0; o < NOUT; ++o) acc[o] = 0.f;
+  const int kq = K / 4;
+  for (int k = q * kq; k < (q + 1) * kq; ++k) {
+    const float hv = h[k * kHStride + row];
+#pragma unroll
+    for (int o = 0; o < NOUT; ++o) acc[o] = fmaf(hv, W[o * K + k], acc[o]);
+  }
+#pragma unroll
+  for (int o = 0; o < NOUT; ++o) {
+    acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], 1);
+    acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], 2);
+  }
+  if (q == 0) {
+#pragma unroll
+    for (int o = 0; o < NOUT; ++o) out_row4[row * 4 + out_off + o] = acc[o] + b[o];
+  }
+  __syncthreads();
+}
+
+// Full NeRF.forward (core/networks/nerf.py:133-148) on a 64-row tile.  Result in sm.part[row*4 + {r,g,b,sigma}].
+__device__ void mlp_tile(Smem& sm, const PgnFp32Net& net, const int* row_ray, bool from_global,
+                         const float* a_global, int rows_valid) {
+  float* hA = sm.h[0];
+  float* hB = sm.h[1];
+  const int srcP = from_global ? A_GLOBAL : A_ENC_P;
+  const int srcD = from_global ? A_GLOBAL : A_ENC_D;
+  {  // pts_linears.0 : 432 -> 256
+    Seg s[1] = {{srcP, PGN_ENC_P, 0}};
+    dense_layer<256>(sm, s, 1, net.wt[0], net.b[0], true, nullptr, hA, row_ray, a_global, PGN_ENC, rows_valid);
+  }
+  float* cur = hA; float* nxt = hB;
+  for (int l = 1; l <= 4; ++l) {
+    Seg s[1] = {{A_FROM_H, 256, 0}};
+    dense_layer<256>(sm, s, 1, net.wt[l], net.b[l], true, cur, nxt, row_ray, a_global, PGN_ENC, rows_valid);
+    float* t = cur; cur = nxt; nxt = t;
+  }
+  {  // pts_linears.5 : [input_pts(432) | h(256)] -> 256   (skip concat, nerf.py:100-101)
+    Seg s[2] = {{srcP, PGN_ENC_P, 0}, {A_FROM_H, 256, 0}};
+    dense_layer<256>(sm, s, 2, net.wt[5], net.b[5], true, cur, nxt, row_ray, a_global, PGN_ENC, rows_valid);
+    float* t = cur; cur = nxt; nxt = t;
+  }
+  for (int l = 6; l <= 7; ++l) {
+    Seg s[1] = {{A_FROM_H, 256, 0}};
+    dense_layer<256>(sm, s, 1, net.wt[l], net.b[l], true, cur, nxt, row_ray, a_global, PGN_ENC, rows_valid);
+    float* t = cur; cur = nxt; nxt = t;
+  }
+  // alpha_linear 256 -> 1 (raw layout: rgb at 0..2, sigma at 3)
+  small_head<1>(sm, cur, 256, net.w_alpha, net.b_alpha, sm.part, 3);
+  {  // feature_linear 256 -> 256, no activation
+    Seg s[1] = {{A_FROM_H, 256, 0}};
+    dense_layer<256>(sm, s, 1, net.wt[9], net.b[9], false, cur, nxt, row_ray, a_global, PGN_ENC, rows_valid);
+    float* t = cur; cur = nxt; nxt = t;
+  }
+  {  // views_linears.0 : [feature(256) | input_views(648)] -> 128, ReLU
+    Seg s[2] = {{A_FROM_H, 256, 0}, {srcD, PGN_ENC_D, PGN_ENC_P}};
+    dense_layer<128>(sm, s, 2, net.wt[10], net.b[10], true, cur, nxt, row_ray, a_global, PGN_ENC, rows_valid);
+    float* t = cur; cur = nxt; nxt = t;
+  }
+  small_head<3>(sm, cur, 128, net.w_rgb, net.b_rgb, sm.part, 0);
+}
+
+// per-tile geometry cache: (v, w, r) of every (row, joint); core/encoders.py + cutoff window
+__device__ void tile_geometry(Smem& sm, const PgnRayRefs& rays, const PgnScalars& sc, long long ray0,
+                              int rows_per_ray, int row0, const float* zbase, int zstride, int total_rows) {
+  for (int item = threadIdx.x; item < kTM * PGN_J; item += kThreads) {
+    const int row = item & (kTM - 1), j = item >> 6;
+    const int grow = row0 + row;
+    float v = 0.f, w = 0.f, wd = 0.f, rx = 0.f, ry = 0.f, rz = 0.f;
+    if (grow < total_rows) {
+      const int rl = grow / rows_per_ray, s = grow - rl * rows_per_ray;
+      const float4* m = reinterpret_cast<const float4*>(pgn_ray_skts(rays, ray0 + rl) + j * 16);
+      float px, py, pz;
+      pgn_sample_point(sm.ray_o[rl], sm.ray_d[rl], zbase[rl * zstride + s], px, py, pz);
+      const PgnJointGeom g = pgn_joint_geom<false>(__ldg(m), __ldg(m + 1), __ldg(m + 2), px, py, pz, sc.tau_v, sc.cutoff_v[j]);
+      v = g.v; rx = g.rx; ry = g.ry; rz = g.rz; w = g.w;
+      // embed_fn and embeddirs_fn own separate (tau, cutoff_dist) buffers (core/raycasters.py:30-79)
+      wd = pgn_window<false>(g.v, sc.tau_d, sc.cutoff_d[j]);
+    }
+    sm.gv[j * kTM + row] = v; sm.gw[j * kTM + row] = w; sm.gwd[j * kTM + row] = wd;
+    sm.grx[j * kTM + row] = rx; sm.gry[j * kTM + row] = ry; sm.grz[j * kTM + row] = rz;
+  }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// fused render kernel
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 1)
+pgn_render_fp32_kernel(PgnRayRefs rays, PgnOutputs out, PgnFp32Net net_c, PgnFp32Net net_f,
+                       const PgnScalars* __restrict__ scp, const float* __restrict__ near_far) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+  __shared__ int row_ray[kTM];
+  const PgnScalars& sc = *scp;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long n_groups = (rays.n_rays + kRPG - 1) / kRPG;
+
+  for (long long g = blockIdx.x; g < n_groups; g += gridDim.x) {
+    const long long ray0 = g * kRPG;
+    const int nr = (int)min((long long)kRPG, rays.n_rays - ray0);
+    __syncthreads();
+    // ---- ray setup + coarse z + view-direction PE table
+    if (tid < kRPG * 3) {
+      const int rl = tid / 3, a = tid % 3;
+      if (rl < nr) {
+        sm.ray_o[rl][a] = rays.ray_batch[(ray0 + rl) * 11 + a];
+        sm.ray_d[rl][a] = rays.ray_batch[(ray0 + rl) * 11 + 3 + a];
+      } else { sm.ray_o[rl][a] = 0.f; sm.ray_d[rl][a] = (a == 2) ? 1.f : 0.f; }
+    }
+    __syncthreads();
+    if (tid < kRPG) {
+      const float* d = sm.ray_d[tid];
+      sm.dnorm[tid] = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);   // torch.norm(rays_d)
+    }
+    for (int i = tid; i < kRPG * PGN_S; i += kThreads) {
+      const int rl = i / PGN_S, s = i % PGN_S;
+      float z = 0.f;
+      if (rl < nr) z = pgn_coarse_z(near_far[(ray0 + rl) * 2], near_far[(ray0 + rl) * 2 + 1], sc.t_coarse[s]);
+      sm.zc[rl][s] = z;
+    }
+    for (int i = tid; i < kRPG * PGN_J; i += kThreads) {
+      const int rl = i / PGN_J, j = i % PGN_J;
+      if (rl < nr) {
+        const float4* m = reinterpret_cast<const float4*>(pgn_ray_skts(rays, ray0 + rl) + j * 16);
+        float dj[3];
+        pgn_joint_dir(__ldg(m), __ldg(m + 1), __ldg(m + 2), sm.ray_d[rl], dj[0], dj[1], dj[2]);
+        for (int k = 0; k < 1 + 2 * PGN_LD; ++k)
+          for (int a = 0; a < 3; ++a) sm.dtab[rl][k * 72 + j * 3 + a] = pgn_pe_term(dj[a], k);
+      }
+    }
+    __syncthreads();
+
+    // ---- two passes: coarse (64 samples, net_c) then fine (80 samples, net_f)
+    for (int pass = 0; pass < 2; ++pass) {
+      const int S = pass == 0 ? PGN_S : PGN_T;
+      const float* zbase = pass == 0 ? &sm.zc[0][0] : &sm.zf[0][0];
+      const PgnFp32Net& net = pass == 0 ? net_c : net_f;
+      const int total_rows = nr * S;
+      for (int row0 = 0; row0 < total_rows; row0 += kTM) {
+        if (tid < kTM) row_ray[tid] = min((row0 + tid) / S, kRPG - 1);
+        tile_geometry(sm, rays, sc, ray0, S, row0, zbase, S, total_rows);
+        __syncthreads();
+        mlp_tile(sm, net, row_ray, false, nullptr, kTM);
+        if (tid < kTM) {
+          const int grow = row0 + tid;
+          if (grow < total_rows) {
+            const int rl = grow / S, s = grow % S;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) sm.raw[rl][s * 4 + c] = sm.part[tid * 4 + c];
+          }
+        }
+        __syncthreads();
+      }
+      // ---- compositing (+ resampling after the coarse pass): one warp per ray
+      if (warp < nr) {
+        const int rl = warp;
+        const long long ri = ray0 + rl;
+        float rgb3[3], disp, acc;
+        if (pass == 0) {
+          float* a0 = out.alpha0 ? out.alpha0 + ri * PGN_S : nullptr;
+          pgn_composite_warp<PGN_S>(sm.raw[rl], sm.zc[rl], sm.dnorm[rl], sc.density_scale, sc.rgb_eps, lane,
+                                    rgb3, &disp, &acc, sm.wts[rl], a0);
+          if (lane == 0) {
+            if (out.rgb0) { out.rgb0[ri * 3] = rgb3[0]; out.rgb0[ri * 3 + 1] = rgb3[1]; out.rgb0[ri * 3 + 2] = rgb3[2]; }
+            if (out.disp0) out.disp0[ri] = disp;
+            if (out.acc0) out.acc0[ri] = acc;
+          }
+          __syncwarp();
+          if (out.weights0) { out.weights0[ri * PGN_S + lane] = sm.wts[rl][lane]; out.weights0[ri * PGN_S + lane + 32] = sm.wts[rl][lane + 32]; }
+          if (out.raw0) for (int i = lane; i < PGN_S * 4; i += 32) out.raw0[ri * PGN_S * 4 + i] = sm.raw[rl][i];
+          pgn_sample_pdf_warp(sm.zc[rl], sm.wts[rl], sc.u_det, lane, sm.scratch[rl],
+                              out.z_samples ? out.z_samples + ri * PGN_I : nullptr, sm.zf[rl],
+                              out.pdf_inds ? out.pdf_inds + ri * PGN_I : nullptr, nullptr);
+          if (out.z_fine) for (int i = lane; i < PGN_T; i += 32) out.z_fine[ri * PGN_T + i] = sm.zf[rl][i];
+        } else {
+          float* a1 = out.alpha ? out.alpha + ri * PGN_T : nullptr;
+          pgn_composite_warp<PGN_T>(sm.raw[rl], sm.zf[rl], sm.dnorm[rl], sc.density_scale, sc.rgb_eps, lane,
+                                    rgb3, &disp, &acc, nullptr, a1);
+          if (lane == 0) {
+            if (out.rgb_map) { out.rgb_map[ri * 3] = rgb3[0]; out.rgb_map[ri * 3 + 1] = rgb3[1]; out.rgb_map[ri * 3 + 2] = rgb3[2]; }
+            if (out.disp_map) out.disp_map[ri] = disp;
+            if (out.acc_map) out.acc_map[ri] = acc;
+          }
+          if (out.raw) for (int i = lane; i < PGN_T * 4; i += 32) out.raw[ri * PGN_T * 4 + i] = sm.raw[rl][i];
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// stage kernel: NeRF.forward on explicit encodings (pgn_mlp, fp32 engine)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 1)
+pgn_mlp_fp32_kernel(PgnFp32Net net, const float* __restrict__ enc, long long m, float* __restrict__ raw) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+  __shared__ int row_ray[kTM];
+  const long long n_tiles = (m + kTM - 1) / kTM;
+  for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const long long row0 = t * kTM;
+    const int rows_valid = (int)min((long long)kTM, m - row0);
+    if (threadIdx.x < kTM) row_ray[threadIdx.x] = 0;
+    __syncthreads();
+    mlp_tile(sm, net, row_ray, true, enc + row0 * PGN_ENC, rows_valid);
+    if (threadIdx.x < rows_valid) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) raw[(row0 + threadIdx.x) * 4 + c] = sm.part[threadIdx.x * 4 + c];
+    }
+    __syncthreads();
+  }
+}
+
+size_t pgn_fp32_smem_bytes() { return sizeof(Smem); }
+
+cudaError_t pgn_launch_render_fp32(const PgnRayRefs& rays, const PgnOutputs& out, const PgnFp32Net& nc,
+                                   const PgnFp32Net& nf, const PgnScalars* sc_dev, const float* near_far,
+                                   int num_sms, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(pgn_render_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(pgn_mlp_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const long long n_groups = (rays.n_rays + kRPG - 1) / kRPG;
+  if (n_groups == 0) return cudaSuccess;
+  const int grid = (int)min((long long)num_sms, n_groups);
+  pgn_render_fp32_kernel<<<grid, kThreads, sizeof(Smem), stream>>>(rays, out, nc, nf, sc_dev, near_far);
+  return cudaGetLastError();
+}
+
+cudaError_t pgn_launch_mlp_fp32(const PgnFp32Net& net, const float* enc, long long m, float* raw,
+                                int num_sms, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(pgn_mlp_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const long long n_tiles = (m + kTM - 1) / kTM;
+  if (n_tiles == 0) return cudaSuccess;
+  const int grid = (int)min((long long)num_sms, n_tiles);
+  pgn_mlp_fp32_kernel<<<grid, kThreads, sizeof(Smem), stream>>>(net, enc, m, raw);
+  return cudaGetLastError();
+}

@@ -1,0 +1,244 @@
+"""Thin Python handle on a `pgn_context` (include/posegen_b200.h).
+
+PyTorch is used only for device memory and streams: every tensor handed to the C ABI is a
+contiguous fp32 CUDA tensor, passed as a raw pointer together with the current stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib
+from .synthetic import NERF_LAYERS
+
+T, S, I, J = 80, 64, 16, 24
+# include/posegen_b200.h order of the 12 linear layers
+LINEAR_ORDER = [f"pts_linears.{i}" for i in range(8)] + ["alpha_linear", "feature_linear", "views_linears.0", "rgb_linear"]
+_SHAPES = {name: (o, i) for name, o, i in NERF_LAYERS}
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _check_f32_cuda(t: torch.Tensor, name: str):
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor (posegen_b200 has no CPU path)")
+    if t.dtype != torch.float32:
+        raise ValueError(f"{name} must be float32, got {t.dtype}")
+
+
+class Engine:
+    """One renderer context on one CUDA device."""
+
+    def __init__(self, device: Optional[torch.device] = None):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("posegen_b200 requires a CUDA device (no CPU fallback)")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        cfg = _lib.Config(J, S, I, 7, 4, 8, 256, 4, self.device.index)
+        handle = C.c_void_p()
+        _lib.check(self.lib.pgn_create(C.byref(cfg), C.byref(handle)))
+        self.handle = handle
+        self._workspace = None
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.pgn_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ state
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def upload_net(self, net_id: int, state: Dict[str, torch.Tensor]):
+        """state: '<layer>.weight' / '<layer>.bias' tensors (host or device, any float dtype)."""
+        w = _lib.NetWeights()
+        keep = []
+        on_device = None
+        for k, name in enumerate(LINEAR_ORDER):
+            for kind, arr in (("weight", w.weight), ("bias", w.bias)):
+                t = torch.as_tensor(state[f"{name}.{kind}"]).detach()
+                exp = _SHAPES[name] if kind == "weight" else (_SHAPES[name][0],)
+                if tuple(t.shape) != exp:
+                    raise ValueError(f"{name}.{kind}: expected shape {exp}, got {tuple(t.shape)}")
+                t = t.to(dtype=torch.float32).contiguous()
+                if on_device is None:
+                    on_device = t.is_cuda
+                if t.is_cuda != on_device:
+                    t = t.to(self.device) if on_device else t.cpu()
+                keep.append(t)
+                arr[k] = t.data_ptr()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.pgn_upload_weights(self.handle, net_id, C.byref(w), 1 if on_device else 0, self._stream()))
+            if not on_device:
+                torch.cuda.current_stream(self.device).synchronize()   # host staging must outlive the copies
+
+    def set_scalars(self, tau_v: float, tau_d: float, cutoff_v, cutoff_d, density_scale: float = 1.0, rgb_eps: float = 1e-3):
+        cv = (C.c_float * J)(*[float(x) for x in cutoff_v])
+        cd = (C.c_float * J)(*[float(x) for x in cutoff_d])
+        _lib.check(self.lib.pgn_set_embed_scalars(self.handle, float(tau_v), float(tau_d), cv, cd,
+                                                  float(density_scale), float(rgb_eps)))
+
+    def load_checkpoint(self, ckpt: dict, density_scale: float = 1.0):
+        """ckpt with the reference key names (core/raycasters.py:752-766)."""
+        self.upload_net(0, ckpt["network_fn_state_dict"])
+        self.upload_net(1, ckpt["network_fine_state_dict"])
+        e, d = ckpt["embed_state_dict"], ckpt["embeddirs_state_dict"]
+        self.set_scalars(float(torch.as_tensor(e["tau"])), float(torch.as_tensor(d["tau"])),
+                         torch.as_tensor(e["cutoff_dist"]).flatten().tolist(),
+                         torch.as_tensor(d["cutoff_dist"]).flatten().tolist(), density_scale)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.pgn_launch_count(self.handle))
+
+    def check_status(self):
+        _lib.check(self.lib.pgn_check_device_status(self.handle))
+
+    # ------------------------------------------------------------------ inputs
+    def _inputs(self, ray_batch, skts, cyls, pose_idx=None, nanfill_chunk=0, precision="bf16"):
+        _check_f32_cuda(ray_batch, "ray_batch")
+        n = ray_batch.shape[0]
+        if ray_batch.dim() != 2 or ray_batch.shape[1] != 11:
+            raise ValueError(f"ray_batch must be [N,11], got {tuple(ray_batch.shape)}")
+        ray_batch = ray_batch.contiguous()
+        keep = [ray_batch]
+        inp = _lib.RenderInputs()
+        inp.ray_batch = ray_batch.data_ptr()
+        inp.n_rays = n
+
+        def per_ray(t, tail, name):
+            """-> (tensor, stride) accepting [*tail], [1,*tail] / stride-0 expands, or [N,*tail]."""
+            _check_f32_cuda(t, name)
+            numel = 1
+            for x in tail:
+                numel *= x
+            if tuple(t.shape) == tuple(tail):
+                return t.contiguous(), 0
+            if tuple(t.shape[1:]) != tuple(tail):
+                raise ValueError(f"{name}: expected [...,{tail}], got {tuple(t.shape)}")
+            if t.shape[0] == 1 or (t.shape[0] == n and t.stride(0) == 0):
+                return t[0].contiguous(), 0
+            if t.shape[0] != n:
+                raise ValueError(f"{name}: leading dim {t.shape[0]} != n_rays {n}")
+            return t.contiguous(), numel
+
+        if pose_idx is not None:
+            _check_f32_cuda(skts, "skts")
+            skts_t, cyls_t = skts.contiguous(), cyls.contiguous()
+            pose_idx = pose_idx.to(device=ray_batch.device, dtype=torch.int32).contiguous()
+            if pose_idx.numel() != n:
+                raise ValueError("pose_idx must have one entry per ray")
+            inp.pose_idx = pose_idx.data_ptr()
+            keep.append(pose_idx)
+            s_stride = c_stride = 0
+        else:
+            skts_t, s_stride = per_ray(skts, (J, 4, 4), "skts")
+            cyls_t, c_stride = per_ray(cyls, (5,), "cyls")
+        keep += [skts_t, cyls_t]
+        inp.skts, inp.skts_stride = skts_t.data_ptr(), s_stride
+        inp.cyls, inp.cyls_stride = cyls_t.data_ptr(), c_stride
+        inp.nanfill_chunk = int(nanfill_chunk)
+        inp.precision = {"fp32": _lib.PRECISION_FP32, "bf16": _lib.PRECISION_BF16}[precision]
+        return inp, keep
+
+    # ---------------------------------------------------------------- hot path
+    def render(self, ray_batch, skts, cyls, pose_idx=None, nanfill_chunk=0, precision="bf16",
+               return_alpha=True, taps=False) -> Dict[str, torch.Tensor]:
+        """pgn_render_forward: the reference's RayCaster.render_rays (eval path)."""
+        inp, keep = self._inputs(ray_batch, skts, cyls, pose_idx, nanfill_chunk, precision)
+        n, dev = inp.n_rays, ray_batch.device
+        f = lambda *sh: torch.empty(sh, dtype=torch.float32, device=dev)  # noqa: E731
+        ret = {"rgb_map": f(n, 3), "disp_map": f(n), "acc_map": f(n), "rgb0": f(n, 3), "disp0": f(n), "acc0": f(n)}
+        if return_alpha:
+            ret["alpha"], ret["alpha0"] = f(n, T), f(n, S)
+        if taps:
+            ret.update(z_samples=f(n, I), z_fine=f(n, T), weights0=f(n, S), raw0=f(n, S, 4), raw=f(n, T, 4),
+                       near_far=f(n, 2), pdf_inds=torch.empty((n, I), dtype=torch.int32, device=dev))
+        out = _lib.RenderOutputs()
+        for k, v in ret.items():
+            setattr(out, k, v.data_ptr())
+        need = self.lib.pgn_workspace_bytes(self.handle, n)
+        if self._workspace is None or self._workspace.numel() < need or self._workspace.device != dev:
+            self._workspace = torch.empty(max(need, 1 << 20), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(self.lib.pgn_render_forward(self.handle, C.byref(inp), C.byref(out),
+                                                   C.c_void_p(self._workspace.data_ptr()), self._workspace.numel(),
+                                                   self._stream()))
+        return ret
+
+    # ------------------------------------------------------ stage entry points
+    def near_far(self, ray_batch, skts, cyls, nanfill_chunk=0):
+        inp, keep = self._inputs(ray_batch, skts, cyls, None, nanfill_chunk)
+        out = torch.empty((inp.n_rays, 2), dtype=torch.float32, device=ray_batch.device)
+        _lib.check(self.lib.pgn_near_far(self.handle, C.byref(inp), _ptr(out), self._stream()))
+        return out
+
+    def encode(self, ray_batch, skts, cyls, z):
+        inp, keep = self._inputs(ray_batch, skts, cyls)
+        z = z.contiguous()
+        enc = torch.empty((inp.n_rays, z.shape[1], 1080), dtype=torch.float32, device=z.device)
+        _lib.check(self.lib.pgn_encode(self.handle, C.byref(inp), _ptr(z), z.shape[1], _ptr(enc), self._stream()))
+        return enc
+
+    def mlp(self, net_id, enc, precision="bf16"):
+        _check_f32_cuda(enc, "enc")
+        enc2 = enc.reshape(-1, 1080).contiguous()
+        raw = torch.empty((enc2.shape[0], 4), dtype=torch.float32, device=enc.device)
+        prec = {"fp32": _lib.PRECISION_FP32, "bf16": _lib.PRECISION_BF16}[precision]
+        _lib.check(self.lib.pgn_mlp(self.handle, net_id, _ptr(enc2), enc2.shape[0], _ptr(raw), prec, self._stream()))
+        return raw.reshape(*enc.shape[:-1], 4)
+
+    def composite(self, ray_batch, skts, cyls, raw, z):
+        inp, keep = self._inputs(ray_batch, skts, cyls)
+        n, s = z.shape
+        dev = z.device
+        f = lambda *sh: torch.empty(sh, dtype=torch.float32, device=dev)  # noqa: E731
+        ret = {"rgb_map": f(n, 3), "disp_map": f(n), "acc_map": f(n), "weights": f(n, s), "alpha": f(n, s)}
+        _lib.check(self.lib.pgn_composite(self.handle, C.byref(inp), _ptr(raw.contiguous()), _ptr(z.contiguous()), s,
+                                          _ptr(ret["rgb_map"]), _ptr(ret["disp_map"]), _ptr(ret["acc_map"]),
+                                          _ptr(ret["weights"]), _ptr(ret["alpha"]), self._stream()))
+        return ret
+
+    def sample_pdf(self, z, weights):
+        _check_f32_cuda(z, "z")
+        n, dev = z.shape[0], z.device
+        ret = {"z_samples": torch.empty((n, I), dtype=torch.float32, device=dev),
+               "z_sorted": torch.empty((n, T), dtype=torch.float32, device=dev),
+               "pdf_inds": torch.empty((n, I), dtype=torch.int32, device=dev),
+               "sorted_idxs": torch.empty((n, T), dtype=torch.int32, device=dev)}
+        _lib.check(self.lib.pgn_sample_pdf(self.handle, _ptr(z.contiguous()), _ptr(weights.contiguous()), n,
+                                           _ptr(ret["z_samples"]), _ptr(ret["z_sorted"]), _ptr(ret["pdf_inds"]),
+                                           _ptr(ret["sorted_idxs"]), self._stream()))
+        return ret
+
+    def generate_rays(self, H, W, focal, c2w, x0, y0, x1, y1):
+        c = (C.c_float * 12)(*[float(v) for v in torch.as_tensor(c2w)[:3, :4].reshape(-1).tolist()])
+        n = max(x1 - x0, 0) * max(y1 - y0, 0)
+        rb = torch.empty((n, 11), dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.pgn_generate_rays(self.handle, H, W, float(focal), c, x0, y0, x1, y1, _ptr(rb), self._stream()))
+        return rb
+
+    def compose_frame(self, H, W, x0, y0, x1, y1, rgb_map, acc_map, bg=1.0):
+        img = torch.empty((H * W, 3), dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.pgn_compose_frame(self.handle, H, W, x0, y0, x1, y1, _ptr(rgb_map), _ptr(acc_map), float(bg),
+                                              _ptr(img), self._stream()))
+        return img.view(H, W, 3)
+
+    def debug_umma_gemm(self, A, B, variant=0):
+        K, N = A.shape[1], B.shape[0]
+        D = torch.empty((128, N), dtype=torch.float32, device=A.device)
+        _lib.check(self.lib.pgn_debug_umma_gemm(self.handle, _ptr(A.contiguous()), _ptr(B.contiguous()), _ptr(D), K, N,
+                                                variant, self._stream()))
+        return D

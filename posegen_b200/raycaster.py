@@ -1,0 +1,299 @@
+"""Drop-in for PoseGen's `core.raycasters` on the render path.
+
+Same constructor, factory, call signature, return dict and checkpoint keys as the
+reference (`core/raycasters.py:17-184,326-794`), but `forward` hands the whole
+`render_rays` pipeline to the sm_100a library through the C ABI (posegen_b200.engine).
+
+What is kept in Python (host-side only, mirrors the reference objects so that
+`run_gan.py` / `run_nerf.py` callers keep working):
+  * `NeRF`            parameter container with the reference's state_dict names
+                      (core/networks/nerf.py:57-88); its math lives in the CUDA kernels;
+  * `CutoffEmbedder`  tau buffer + cutoff_dist parameter and the tau schedule
+                      (core/cutoff_embedder.py:83-95,176-183);
+  * `Embedder`        the plain (identity for multires_bones=0) bone embedder;
+  * `RayCaster`       forward / state_dict / load_state_dict / get_networks / get_embed_fns /
+                      update_embed_fns (core/raycasters.py:326-794).
+Unsupported reference options raise NotImplementedError (never a silent fallback).
+"""
+from __future__ import annotations
+
+from types import SimpleNamespace
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from .engine import Engine, LINEAR_ORDER
+
+N_JOINTS = 24
+
+
+# ----------------------------------------------------------------------------- modules
+class NeRF(nn.Module):
+    """Parameter container of one A-NeRF MLP (surreal.txt shapes).  forward() is not
+    implemented on purpose: the network only runs inside the fused CUDA kernels."""
+
+    def __init__(self, D=8, W=256, input_ch=360, input_ch_bones=72, input_ch_views=648, output_ch=5,
+                 skips=(4,), use_viewdirs=True, use_framecode=False, framecode_ch=16, n_framecodes=0,
+                 skel_type=None, density_scale=1.0):
+        super().__init__()
+        if (D, W, input_ch, input_ch_bones, input_ch_views, tuple(skips), use_viewdirs, use_framecode) != \
+                (8, 256, 360, 72, 648, (4,), True, False):
+            raise NotImplementedError("posegen_b200 implements the configs/surreal/surreal.txt A-NeRF only "
+                                      "(8x256, skip 4, 360+72 | 648 inputs, viewdirs, no frame codes)")
+        self.D, self.W = D, W
+        self.input_ch, self.input_ch_bones, self.input_ch_views = input_ch, input_ch_bones, input_ch_views
+        self.skips, self.use_viewdirs, self.use_framecode = list(skips), use_viewdirs, use_framecode
+        self.output_ch, self.skel_type, self.density_scale = output_ch, skel_type, density_scale
+        dnet = input_ch + input_ch_bones
+        layers = [nn.Linear(dnet, W)]
+        for i in range(D - 1):
+            layers.append(nn.Linear(W + dnet if i in self.skips else W, W))
+        self.pts_linears = nn.ModuleList(layers)
+        self.alpha_linear = nn.Linear(W, 1)
+        self.views_linears = nn.ModuleList([nn.Linear(input_ch_views + W, W // 2)])
+        self.feature_linear = nn.Linear(W, W)
+        self.rgb_linear = nn.Linear(W // 2, 3)
+
+    def forward(self, *a, **k):
+        raise NotImplementedError("NeRF.forward runs only inside posegen_b200's fused CUDA kernels "
+                                  "(use RayCaster.forward or Engine.mlp)")
+
+
+class Embedder(nn.Module):
+    """Plain positional embedder (core/cutoff_embedder.py:9-58); identity when multires=0."""
+
+    def __init__(self, input_dims, multires):
+        super().__init__()
+        self.input_dims, self.multires = input_dims, multires
+        self.out_dim = input_dims * (1 + 2 * multires)
+
+    def update_threshold(self, *a, **k):
+        pass
+
+    def get_tau(self):
+        return 0.0
+
+
+class CutoffEmbedder(Embedder):
+    """tau / cutoff_dist holder with the reference's schedule (core/cutoff_embedder.py:61-195)."""
+
+    def __init__(self, input_dims, multires, cutoff_dist, cutoff_dim=N_JOINTS, dist_inputs=False):
+        super().__init__(input_dims, multires)
+        self.dist_inputs = dist_inputs
+        self.cutoff_dist = nn.Parameter(torch.ones(cutoff_dim) * cutoff_dist, requires_grad=False)
+        self.init_tau = 20.
+        self.register_buffer("tau", torch.tensor(self.init_tau))
+
+    def get_tau(self):
+        return self.tau.item()
+
+    def update_threshold(self, global_step, tau_step, tau_rate, alpha_step=None, alpha_target=None):
+        self.update_tau(global_step, tau_step, tau_rate)
+
+    def update_tau(self, global_step, step, rate):
+        # tau = min(2000, 20 * rate^(step/(1000*cutoff_step)))  (cutoff_embedder.py:181-183)
+        self.tau = (self.init_tau * torch.ones_like(self.tau) * rate ** (global_step / float(step * 1000))).clamp(max=2000.)
+
+
+class _EncoderTag:
+    """Stand-in for the reference encoder modules passed around in preproc_kwargs
+    (core/encoders.py); only their names are observable by callers."""
+
+    def __init__(self, name, dims):
+        self.encoder_name, self.dims = name, dims
+
+
+# ----------------------------------------------------------------------------- RayCaster
+class RayCaster(nn.Module):
+    """core.raycasters.RayCaster with the render path executed by the B200 library.
+
+    precision: "bf16" (tcgen05 tensor-core path, default) or "fp32" (CUDA-core parity tier).
+    """
+
+    def __init__(self, network, embed_fn, embedbones_fn, embeddirs_fn, network_fine=None,
+                 joint_coords=None, single_net=False, precision="bf16"):
+        super().__init__()
+        if single_net or network_fine is None or network_fine is network:
+            raise NotImplementedError("single_net / no fine network is not implemented (surreal.txt uses two nets)")
+        self.network, self.network_fine = network, network_fine
+        self.embed_fn, self.embedbones_fn, self.embeddirs_fn = embed_fn, embedbones_fn, embeddirs_fn
+        if joint_coords is not None:
+            n_j = joint_coords.shape[-3]
+            self.register_buffer("joint_coords", torch.as_tensor(joint_coords).reshape(-1, n_j, 3, 3))
+        self.single_net = single_net
+        self.precision = precision
+        self.return_alpha = True
+        self._engines = {}
+        self._uploaded = {}
+
+    # -- engine / weight sync ---------------------------------------------------
+    def _param_signature(self):
+        taus = (self.embed_fn.tau, self.embeddirs_fn.tau)
+        return tuple([p._version for p in self.parameters()] + [t._version for t in taus] + [t.data_ptr() for t in taus])
+
+    def engine(self, device) -> Engine:
+        device = torch.device(device)
+        key = device.index if device.index is not None else torch.cuda.current_device()
+        if key not in self._engines:
+            self._engines[key] = Engine(torch.device("cuda", key))
+        eng = self._engines[key]
+        sig = (self._param_signature(), tuple(p.data_ptr() for p in self.parameters()))
+        if self._uploaded.get(key) != sig:
+            eng.upload_net(0, self.network.state_dict())
+            eng.upload_net(1, self.network_fine.state_dict())
+            eng.set_scalars(float(self.embed_fn.tau), float(self.embeddirs_fn.tau),
+                            self.embed_fn.cutoff_dist.detach().flatten().tolist(),
+                            self.embeddirs_fn.cutoff_dist.detach().flatten().tolist(),
+                            float(self.network.density_scale))
+            self._uploaded[key] = sig
+        return eng
+
+    # -- forward -------------------------------------------------------------------
+    def forward(self, *args, fwd_type="", **kwargs):
+        if fwd_type in ("density", "density_color", "mesh"):
+            raise NotImplementedError(f"fwd_type={fwd_type!r} (density-only queries, core/raycasters.py:579-648) "
+                                      "is a later scope row (SURVEY.md §8f-5)")
+        return self.render_rays(*args, **kwargs)
+
+    @torch.no_grad()
+    def render_rays(self, ray_batch, N_samples, kp_batch=None, skts=None, cyls=None, bones=None, cams=None,
+                    subject_idxs=None, retraw=False, lindisp=False, perturb=0., N_importance=0,
+                    network_fine=None, raw_noise_std=0., ray_noise_std=0., verbose=False, ext_scale=0.001,
+                    pytest=False, preproc_kwargs=None, nerf_type="nerf", use_viewdirs=True,
+                    precision=None, nanfill_chunk=None, **_ignored):
+        if self.training and (perturb or raw_noise_std or ray_noise_std):
+            raise NotImplementedError("training-time sampling noise (perturb / raw_noise_std / ray_noise_std) and the "
+                                      "backward pass are not implemented yet; call .eval() for rendering")
+        if perturb or raw_noise_std or ray_noise_std or lindisp:
+            raise NotImplementedError("perturb / raw_noise_std / ray_noise_std / lindisp must be 0/False on the render path")
+        if N_samples != 64 or N_importance != 16:
+            raise NotImplementedError("only N_samples=64, N_importance=16 (surreal.txt) is implemented")
+        if cams is not None:
+            raise NotImplementedError("frame codes (opt_framecode) are not part of the surreal.txt path")
+        if skts is None or cyls is None:
+            raise ValueError("skts and cyls are required (skeleton-relative encoding / cylinder near-far)")
+        if not ray_batch.is_cuda:
+            raise RuntimeError("posegen_b200.RayCaster needs CUDA tensors (the reference moves each chunk with "
+                               ".to('cuda') in batchify_rays, core/trainer.py:70-74); there is no CPU fallback")
+        eng = self.engine(ray_batch.device)
+        n = ray_batch.shape[0]
+        ret = eng.render(ray_batch.float(), skts.to(ray_batch.device).float(), cyls.to(ray_batch.device).float(),
+                         nanfill_chunk=n if nanfill_chunk is None else nanfill_chunk,
+                         precision=precision or self.precision, return_alpha=self.return_alpha)
+        if not self.return_alpha:
+            ret["alpha"] = ret["alpha0"] = None
+        return ret
+
+    # -- reference API surface -------------------------------------------------------
+    def get_networks(self):
+        return self.network, self.network_fine
+
+    def get_embed_fns(self):
+        return self.embed_fn, self.embedbones_fn, self.embeddirs_fn
+
+    def update_embed_fns(self, global_step, args):
+        for fn in (self.embed_fn, self.embeddirs_fn, self.embedbones_fn):
+            if fn is not None:
+                fn.update_threshold(global_step, args.cutoff_step, args.cutoff_rate,
+                                    getattr(args, "freq_schedule_step", None), args.multires - 1)
+
+    def state_dict(self, *a, **k):
+        # key naming rules of core/raycasters.py:752-766
+        return {"network_fn_state_dict": self.network.state_dict(),
+                "network_fine_state_dict": self.network_fine.state_dict(),
+                "embed_state_dict": self.embed_fn.state_dict(),
+                "embedbones_state_dict": self.embedbones_fn.state_dict() if self.embedbones_fn is not None else {},
+                "embeddirs_state_dict": self.embeddirs_fn.state_dict()}
+
+    def load_state_dict(self, ckpt, strict=True):
+        def conv(sd):
+            return {k: torch.as_tensor(v) for k, v in sd.items()}
+        self.network.load_state_dict(conv(ckpt["network_fn_state_dict"]), strict=strict)
+        self.network_fine.load_state_dict(conv(ckpt["network_fine_state_dict"]), strict=strict)
+        for fn, key in ((self.embed_fn, "embed_state_dict"), (self.embeddirs_fn, "embeddirs_state_dict")):
+            if key in ckpt:
+                fn.load_state_dict(conv(ckpt[key]), strict=strict)
+        self._uploaded.clear()
+
+
+# ----------------------------------------------------------------------------- factory
+SURREAL_ARGS = dict(
+    netdepth=8, netwidth=256, multires=7, multires_views=4, multires_bones=0, i_embed=0,
+    use_viewdirs=True, use_cutoff=True, cutoff_viewdir=True, cutoff_inputs=True, cutoff_bones=False,
+    normalize_cutoff=False, opt_cutoff=False, cut_to_dist=False, cutoff_shift=False, freq_schedule=False,
+    init_freq=0., cutoff_mm=500., ext_scale=0.001, kp_dist_type="reldist", bone_type="reldir", view_type="relray",
+    pts_tr_type="local", density_type="relu", density_scale=1.0, opt_framecode=False, framecode_size=16,
+    n_framecodes=None, single_net=False, N_samples=64, N_importance=16, perturb=1.0, raw_noise_std=1.0,
+    ray_noise_std=0., lindisp=False, nerf_type="nerf", lrate=5e-4, chunk=4096, cutoff_step=250, cutoff_rate=10.,
+    no_reload=True, ft_path=None, finetune=False, debug=False, weight_decay=None, white_bkgd=False,
+)
+
+
+def surreal_args(**overrides) -> SimpleNamespace:
+    """The frozen configs/surreal/surreal.txt + run_nerf.py parser defaults."""
+    d = dict(SURREAL_ARGS)
+    d.update(overrides)
+    return SimpleNamespace(**d)
+
+
+def _require(args, **expected):
+    for k, v in expected.items():
+        got = getattr(args, k, v)
+        if got != v:
+            raise NotImplementedError(f"create_raycaster: {k}={got!r} is not implemented (surreal.txt uses {v!r})")
+
+
+def create_raycaster(args, data_attrs, device=None, precision="bf16"):
+    """core/raycasters.py:17-184: returns (render_kwargs_train, render_kwargs_test, start, grad_vars,
+    optimizer, loaded_ckpt) with the B200 RayCaster inside."""
+    _require(args, netdepth=8, netwidth=256, multires=7, multires_views=4, multires_bones=0, use_viewdirs=True,
+             use_cutoff=True, cutoff_viewdir=True, cutoff_inputs=True, kp_dist_type="reldist", bone_type="reldir",
+             view_type="relray", pts_tr_type="local", density_type="relu", opt_framecode=False, single_net=False,
+             N_importance=16, N_samples=64)
+    cutoff = args.cutoff_mm * args.ext_scale
+    embed_fn = CutoffEmbedder(N_JOINTS, args.multires, cutoff, dist_inputs=False)
+    embedbones_fn = Embedder(N_JOINTS * 3, args.multires_bones)
+    embeddirs_fn = CutoffEmbedder(N_JOINTS * 3, args.multires_views, cutoff, dist_inputs=True)
+    kw = dict(D=args.netdepth, W=args.netwidth, input_ch=embed_fn.out_dim, input_ch_bones=embedbones_fn.out_dim,
+              input_ch_views=embeddirs_fn.out_dim, output_ch=5, skips=(4,), use_viewdirs=True,
+              skel_type=data_attrs.get("skel_type"), density_scale=args.density_scale)
+    model, model_fine = NeRF(**kw), NeRF(**kw)
+    ray_caster = RayCaster(model, embed_fn, embedbones_fn, embeddirs_fn, network_fine=model_fine,
+                           joint_coords=torch.as_tensor(data_attrs["joint_coords"]) if "joint_coords" in data_attrs else None,
+                           single_net=False, precision=precision)
+    if device is not None:
+        ray_caster = ray_caster.to(device)
+    grad_vars = [p for p in ray_caster.parameters() if p.requires_grad]
+    optimizer = torch.optim.Adam(params=grad_vars, lr=args.lrate, betas=(0.9, 0.999))
+    start, loaded_ckpt = 0, None
+    ft_path = getattr(args, "ft_path", None)
+    if ft_path not in (None, "None") and not getattr(args, "no_reload", False):
+        loaded_ckpt = torch.load(ft_path, map_location="cpu")
+        ray_caster.load_state_dict(loaded_ckpt)
+        start = 0 if getattr(args, "finetune", False) else loaded_ckpt.get("global_step", 0)
+    preproc_kwargs = {
+        "pts_tr_fn": _EncoderTag("W2LEncoder", N_JOINTS), "kp_input_fn": _EncoderTag("RelDist", N_JOINTS),
+        "view_input_fn": _EncoderTag("VecNorm", N_JOINTS * 3), "bone_input_fn": _EncoderTag("VecNorm", N_JOINTS * 3),
+        "density_scale": args.density_scale, "density_fn": torch.nn.functional.relu,
+    }
+    render_kwargs_train = {
+        "ray_caster": ray_caster, "perturb": args.perturb, "N_importance": args.N_importance,
+        "N_samples": args.N_samples, "use_viewdirs": args.use_viewdirs, "raw_noise_std": args.raw_noise_std,
+        "ray_noise_std": args.ray_noise_std, "ext_scale": args.ext_scale, "preproc_kwargs": preproc_kwargs,
+        "lindisp": args.lindisp, "nerf_type": args.nerf_type,
+    }
+    render_kwargs_test = dict(render_kwargs_train)
+    render_kwargs_test.update(perturb=False, raw_noise_std=0., ray_noise_std=0.)
+    optimizer.zero_grad()
+    return render_kwargs_train, render_kwargs_test, start, grad_vars, optimizer, loaded_ckpt
+
+
+def raycaster_from_checkpoint(ckpt: dict, device="cuda", precision="bf16") -> RayCaster:
+    """Build a RayCaster and load a reference-format checkpoint dict (key names of
+    core/raycasters.py:752-766), e.g. posegen_b200.synthetic.synthetic_raycaster_state()."""
+    _, kw_test, _, _, _, _ = create_raycaster(surreal_args(), {"skel_type": None}, device=device, precision=precision)
+    rc = kw_test["ray_caster"]
+    rc.load_state_dict(ckpt)
+    rc.eval()
+    return rc
