@@ -55,10 +55,11 @@ __device__ __forceinline__ const float* pgn_ray_cyl(const PgnRayRefs& r, long lo
   return r.cyls + i * r.cyls_stride;
 }
 
-// torch.linspace(start=0,end=1,steps=n) on CPU: symmetric evaluation around the midpoint.
+// torch.linspace(start=0,end=1,steps=n) on CPU: symmetric evaluation around the midpoint; the
+// upper half is end - step*(n-1-i) evaluated with ONE rounding (the vectorised kernel fuses it).
 __host__ __device__ inline float pgn_linspace01(int i, int n) {
   float step = 1.0f / (float)(n - 1);
-  return (i < n / 2) ? step * (float)i : 1.0f - step * (float)(n - 1 - i);
+  return (i < n / 2) ? step * (float)i : fmaf(-step, (float)(n - 1 - i), 1.0f);
 }
 
 // ---------------------------------------------------------------------------

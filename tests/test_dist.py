@@ -1,0 +1,43 @@
+"""CPU: the N>1 sharding / gather path with world_size 2 over gloo."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from posegen_b200 import dist as pdist
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, n_jobs, ok):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    r, w, _ = pdist.init_process_group("gloo")
+    mine = pdist.shard_indices(n_jobs, r, w)
+    frames = torch.stack([torch.full((4, 4, 3), float(i)) for i in mine]) if mine else torch.zeros(0, 4, 4, 3)
+    full = pdist.gather_frames(frames, n_jobs, r, w)
+    expect = torch.stack([torch.full((4, 4, 3), float(i)) for i in range(n_jobs)])
+    good = torch.equal(full, expect)
+    good &= pdist.max_over_ranks(float(r + 1)) == float(w)
+    ok[rank] = int(good)
+    dist.destroy_process_group()
+
+
+def test_shard_indices_partition():
+    for world in (1, 2, 4, 8):
+        seen = sorted(i for r in range(world) for i in pdist.shard_indices(256, r, world))
+        assert seen == list(range(256))
+        assert pdist.shard_counts(256, world) == [256 // world] * world
+    assert pdist.shard_counts(5, 2) == [3, 2]
+
+
+def test_gather_frames_world2_gloo():
+    port = _free_port()
+    ok = mp.get_context("spawn").Array("i", [0, 0])
+    mp.spawn(_worker, args=(2, port, 5, ok), nprocs=2, join=True)
+    assert list(ok) == [1, 1]

@@ -1,0 +1,123 @@
+"""CPU: host logic, C-ABI surface, layout tables (no compute calls: there is no GPU here)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+from posegen_b200 import _lib, raycaster as rcmod, synthetic as syn
+from tests import parity_util as pu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_header_symbol(lib_path):
+    header = open(os.path.join(ROOT, "include", "posegen_b200.h")).read()
+    declared = sorted(set(re.findall(r"PGN_API\s+[\w\s\*]+?\b(pgn_\w+)\s*\(", header)))
+    assert declared == sorted(_lib.EXPORTED)
+    lib = ctypes.CDLL(lib_path)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} not exported by {lib_path}"
+    assert lib.pgn_abi_version() == 1
+
+
+def test_no_cpu_fallback_without_gpu(lib_path):
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    lib = _lib.load()
+    cfg = _lib.Config(24, 64, 16, 7, 4, 8, 256, 4, 0)
+    h = ctypes.c_void_p()
+    rc = lib.pgn_create(ctypes.byref(cfg), ctypes.byref(h))
+    assert rc == _lib.PGN_E_CUDA
+    assert b"no CPU fallback" in lib.pgn_last_error()
+    with pytest.raises(RuntimeError):
+        from posegen_b200.engine import Engine
+        Engine()
+
+
+def test_create_rejects_other_architectures(lib_path):
+    lib = _lib.load()
+    cfg = _lib.Config(24, 128, 16, 7, 4, 8, 256, 4, 0)
+    h = ctypes.c_void_p()
+    assert lib.pgn_create(ctypes.byref(cfg), ctypes.byref(h)) == _lib.PGN_E_INVALID
+
+
+def test_linspace_tables_match_torch():
+    # pgn_linspace01 (pgn_common.cuh) restated: symmetric evaluation like torch.linspace on CPU
+    def lin(n):
+        step = np.float32(1.0) / np.float32(n - 1)
+        return np.array([step * np.float32(i) if i < n // 2 else np.float32(1.0 - float(step) * (n - 1 - i))  # fused
+                         for i in range(n)], dtype=np.float32)
+    assert np.array_equal(lin(64), torch.linspace(0., 1., 64).numpy())
+    assert np.array_equal(lin(16), torch.linspace(0., 1., 16).numpy())
+
+
+def test_bf16_k_permutations_are_bijections():
+    src = r'''
+#include <cstdio>
+#include "pgn_bf16_layout.h"
+int main() {
+  for (int k = 0; k < 432; ++k) printf("%d ", pgn_xperm_refcol(k));
+  printf("\n");
+  for (int q = 0; q < 672; ++q) printf("%d ", pgn_dperm_refcol(q));
+  printf("\n%zu\n", pgn_wstream_elems());
+  int ks = 0; for (int L = 0; L < 9; ++L) ks += pgn_layer_ksteps(L);
+  printf("%d\n", ks);
+}'''
+    with tempfile.TemporaryDirectory() as tmp:
+        cpp = os.path.join(tmp, "t.cpp")
+        open(cpp, "w").write(src)
+        exe = os.path.join(tmp, "t")
+        subprocess.run(["g++", "-std=c++17", "-I", os.path.join(ROOT, "posegen_b200", "csrc"), cpp, "-o", exe], check=True)
+        lines = subprocess.run([exe], capture_output=True, text=True, check=True).stdout.strip().split("\n")
+    x = [int(v) for v in lines[0].split()]
+    d = [int(v) for v in lines[1].split()]
+    assert sorted(x) == list(range(432))
+    assert sorted(v for v in d if v >= 0) == list(range(432, 1080)) and d.count(-1) == 24
+    assert int(lines[2]) == 798720      # bf16 elements per net = tensor MACs per sample
+    assert int(lines[3]) == 224
+
+
+def test_raycaster_drop_in_surface():
+    kw_train, kw_test, start, grad_vars, optim, ckpt = rcmod.create_raycaster(rcmod.surreal_args(), {"skel_type": None})
+    rc = kw_test["ray_caster"]
+    assert sum(p.numel() for p in rc.parameters()) == 1728568
+    assert list(rc.state_dict().keys()) == ["network_fn_state_dict", "network_fine_state_dict", "embed_state_dict",
+                                            "embedbones_state_dict", "embeddirs_state_dict"]
+    assert kw_test["perturb"] is False and kw_test["raw_noise_std"] == 0.
+    assert set(rc.state_dict()["embed_state_dict"].keys()) == {"cutoff_dist", "tau"}
+    state = syn.synthetic_raycaster_state(3, alpha_gain=400.)
+    rc.load_state_dict(state)
+    got = rc.state_dict()["network_fine_state_dict"]["pts_linears.5.weight"].numpy()
+    assert np.array_equal(got, state["network_fine_state_dict"]["pts_linears.5.weight"])
+    # tau schedule of core/cutoff_embedder.py:181-183
+    rc.update_embed_fns(250000, rcmod.surreal_args())
+    assert abs(rc.embed_fn.get_tau() - 200.0) < 1e-3
+    rc.update_embed_fns(10 ** 7, rcmod.surreal_args())
+    assert rc.embed_fn.get_tau() == 2000.0
+    with pytest.raises(RuntimeError):
+        rc.eval()(torch.zeros(4, 11), N_samples=64, N_importance=16, kp_batch=None,
+                  skts=torch.zeros(4, 24, 4, 4), cyls=torch.zeros(4, 5))      # CPU tensors: no fallback
+
+
+def test_unsupported_options_raise():
+    with pytest.raises(NotImplementedError):
+        rcmod.create_raycaster(rcmod.surreal_args(N_samples=128), {"skel_type": None})
+    with pytest.raises(NotImplementedError):
+        rcmod.NeRF(D=4)
+
+
+def test_synthetic_geometry_properties():
+    pose = syn.synthetic_pose(7)
+    ident = pose.skts.astype(np.float64) @ pose.l2ws.astype(np.float64)
+    assert np.abs(ident - np.eye(4)).max() < 1e-5
+    frame = syn.synthetic_frame(7, 64, 64)
+    assert frame.rays_o.shape == frame.rays_d.shape == (len(frame.valid_idx), 3)
+    assert 0.5 < len(frame.valid_idx) / (64 * 64) <= 1.0
+    full = syn.synthetic_frame(7, 64, 64, full_frame=True)
+    assert len(full.valid_idx) == 64 * 64
