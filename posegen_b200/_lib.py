@@ -21,7 +21,7 @@ EXPORTED = [
     "pgn_abi_version", "pgn_last_error", "pgn_create", "pgn_destroy", "pgn_upload_weights",
     "pgn_set_embed_scalars", "pgn_workspace_bytes", "pgn_render_forward", "pgn_launch_count",
     "pgn_check_device_status", "pgn_near_far", "pgn_encode", "pgn_mlp", "pgn_composite",
-    "pgn_sample_pdf", "pgn_generate_rays", "pgn_compose_frame", "pgn_debug_umma_gemm",
+    "pgn_sample_pdf", "pgn_generate_rays", "pgn_compose_frame", "pgn_debug_umma_gemm", "pgn_debug_phase_timers",
 ]
 
 
@@ -85,6 +85,7 @@ def load() -> C.CDLL:
     lib.pgn_generate_rays.argtypes = [vp, i32, i32, f32, C.POINTER(f32), i32, i32, i32, i32, vp, vp]
     lib.pgn_compose_frame.argtypes = [vp, i32, i32, i32, i32, i32, i32, vp, vp, f32, vp, vp]
     lib.pgn_debug_umma_gemm.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp]
+    lib.pgn_debug_phase_timers.argtypes = [vp, i32, C.POINTER(C.c_uint64)]
     for name in EXPORTED:
         fn = getattr(lib, name)
         if fn.restype is C.c_int and name not in ("pgn_abi_version",):

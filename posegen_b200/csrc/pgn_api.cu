@@ -55,6 +55,8 @@ struct pgn_context {
   float* d_fold;
   PgnBf16Net bf16[2];
   int* d_status;
+  unsigned long long* d_prof;   // optional phase timers [num_sms][16]
+  bool prof_on;
   float* d_c2w;
   int64_t launches;
 };
@@ -90,6 +92,8 @@ int pgn_create(const pgn_config* cfg, pgn_context** out) {
   PGN_CUDA(cudaMalloc(&c->d_sc, sizeof(PgnScalars)));
   PGN_CUDA(cudaMalloc(&c->d_status, sizeof(int)));
   PGN_CUDA(cudaMemset(c->d_status, 0, sizeof(int)));
+  PGN_CUDA(cudaMalloc(&c->d_prof, (size_t)c->num_sms * 16 * sizeof(unsigned long long)));
+  PGN_CUDA(cudaMemset(c->d_prof, 0, (size_t)c->num_sms * 16 * sizeof(unsigned long long)));
   PGN_CUDA(cudaMalloc(&c->d_c2w, 12 * sizeof(float)));
   PGN_CUDA(cudaMalloc(&c->d_fold, (128 * 256 + 128) * sizeof(float)));
   for (int n = 0; n < 2; ++n) {
@@ -217,7 +221,7 @@ int pgn_render_forward(pgn_context* c, const pgn_render_inputs* in, const pgn_re
   if (in->precision == PGN_PRECISION_FP32)
     PGN_CUDA(pgn_launch_render_fp32(refs, o, c->fp32[0], c->fp32[1], c->d_sc, near_far, c->num_sms, stream));
   else
-    PGN_CUDA(pgn_launch_render_bf16(refs, o, c->bf16[0], c->bf16[1], c->d_sc, near_far, c->d_status, c->num_sms, stream));
+    PGN_CUDA(pgn_launch_render_bf16(refs, o, c->bf16[0], c->bf16[1], c->d_sc, near_far, c->d_status, c->prof_on ? c->d_prof : nullptr, c->num_sms, stream));
   c->launches++;
   return PGN_OK;
 }
@@ -311,6 +315,20 @@ int pgn_compose_frame(pgn_context* c, int32_t H, int32_t W, int32_t x0, int32_t 
   PGN_CUDA(cudaSetDevice(c->cfg.device));
   PGN_CUDA(pgn_launch_compose_frame(H, W, x0, y0, x1, y1, rgb_map, acc_map, bg, image, (cudaStream_t)stream));
   c->launches++;
+  return PGN_OK;
+}
+
+int pgn_debug_phase_timers(pgn_context* c, int32_t enable, uint64_t* out16) {
+  if (!c) return fail(PGN_E_INVALID, "pgn_debug_phase_timers: null context");
+  PGN_CUDA(cudaSetDevice(c->cfg.device));
+  if (out16) {
+    const size_t n = (size_t)c->num_sms * 16;
+    unsigned long long* h = new unsigned long long[n];
+    PGN_CUDA(cudaMemcpy(h, c->d_prof, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 16; ++k) { unsigned long long s = 0; for (int b = 0; b < c->num_sms; ++b) s += h[(size_t)b * 16 + k]; out16[k] = s / (unsigned long long)c->num_sms; }
+    delete[] h;
+  }
+  c->prof_on = enable != 0;
   return PGN_OK;
 }
 

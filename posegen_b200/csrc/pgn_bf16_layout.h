@@ -9,7 +9,8 @@
 //   8      feature∘views        128   256 | 672 d    (joint-major, 27 + 1 zero pad per joint)
 // Stream = layers in order; per layer [kstep][khalf][n][8] bf16, i.e. each K=16 step is two
 // "runs" (8 consecutive k for all n rows) -> UMMA K-major SWIZZLE_NONE with LBO = n*16 B, SBO = 128 B.
-// The producer moves `ks_per_fill` K-steps per bulk copy (<= 32 KB).
+// The producer moves `ks_per_fill` K-steps per bulk copy (8 KB) into a deep ring so that many
+// copies are in flight (the stream is L2-latency bound, not bandwidth bound, at shallow depth).
 #pragma once
 #include <stddef.h>
 
@@ -22,7 +23,7 @@ __host__ __device__ constexpr int pgn_layer_n(int L) { return L == 8 ? 128 : 256
 __host__ __device__ constexpr int pgn_layer_kact(int L) { return L == 0 ? 0 : 256; }
 __host__ __device__ constexpr int pgn_layer_kenc(int L) { return (L == 0 || L == 5) ? 432 : (L == 8 ? 672 : 0); }
 __host__ __device__ constexpr int pgn_layer_ksteps(int L) { return (pgn_layer_kact(L) + pgn_layer_kenc(L)) / 16; }
-__host__ __device__ constexpr int pgn_ks_per_fill(int L) { return L == 8 ? 8 : 4; }
+__host__ __device__ constexpr int pgn_ks_per_fill(int L) { return L == 8 ? 2 : 1; }   // 8 KB per bulk copy
 __host__ __device__ constexpr size_t pgn_wstream_elems() {
   size_t t = 0;
   for (int L = 0; L < 9; ++L) t += (size_t)pgn_layer_n(L) * pgn_layer_ksteps(L) * 16;

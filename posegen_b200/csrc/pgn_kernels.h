@@ -42,7 +42,7 @@ cudaError_t pgn_pack_bf16_net(const float* const* w_dev, const float* const* b_d
                               float* bias, float* w_alpha, float* w_rgb, float* fold_tmp, cudaStream_t stream);
 cudaError_t pgn_launch_render_bf16(const PgnRayRefs& rays, const PgnOutputs& out, const PgnBf16Net& nc,
                                    const PgnBf16Net& nf, const PgnScalars* sc_dev, const float* near_far,
-                                   int* status, int num_sms, cudaStream_t stream);
+                                   int* status, unsigned long long* prof, int num_sms, cudaStream_t stream);
 cudaError_t pgn_launch_mlp_bf16(const PgnBf16Net& net, const float* enc, long long m, float* raw,
                                 const PgnScalars* sc_dev, int* status, int num_sms, cudaStream_t stream);
 

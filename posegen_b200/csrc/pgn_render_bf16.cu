@@ -40,8 +40,8 @@ constexpr int kTM = 128;                // rows per tile (UMMA M)
 constexpr int kRunBytes = kTM * 16;     // one 8-wide K run of all 128 rows
 constexpr int kActBytes = 256 / 8 * kRunBytes;          // 65536
 constexpr int kStgBytes = 18 * kRunBytes;               // 36864 (144 K)
-constexpr int kWStages = 2;
-constexpr int kWStageBytes = 32768;
+constexpr int kWStages = 8;
+constexpr int kWStageBytes = 8192;
 constexpr int kTmemCols = 256;
 constexpr int kMaxTileRays = 3;
 
@@ -223,13 +223,20 @@ __device__ __forceinline__ void compute_arrive(uint64_t* bar) {
 }
 __device__ __forceinline__ void compute_bar_sync() { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }
 
+// optional phase timers (cycles, one elected thread per role, accumulated per CTA):
+//  0 issuer wait w_full | 1 issuer wait stg_full | 2 issuer wait act_ready | 3 issuer total
+//  4 producer wait w_empty | 5 producer total
+//  6 encode_x | 7 encode_d | 8 epilogue | 9 wait acc_full | 10 wait stg_empty | 11 composite+setup | 12 compute total
+#define PROF_T0() const long long _pt0 = prof ? clock64() : 0
+#define PROF_ADD(slot) do { if (prof) pacc[slot] += (unsigned long long)(clock64() - _pt0); } while (0)
+
 // ------------------------------------------------------------------ the kernel
 template <bool kStage>
 __global__ void __launch_bounds__(kThreads, 1)
 pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf16Net net_f,
                        const PgnScalars* __restrict__ scp, const float* __restrict__ near_far,
                        const float* __restrict__ enc_global, long long enc_rows_total, float* __restrict__ raw_global,
-                       int* __restrict__ status_g) {
+                       int* __restrict__ status_g, unsigned long long* __restrict__ prof) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   volatile int* status = status_g;
@@ -255,6 +262,8 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = sm.tmem_base;
+  unsigned long long pacc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  const long long kernel_t0 = prof ? clock64() : 0;
 
   if (warp == kProducerWarp) {
     // ===================== weight producer =====================
@@ -274,7 +283,7 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
                 const int nks = min(kpf, ks_total - ks);
                 const uint32_t bytes = (uint32_t)nks * n * 32u;
                 const int stage = wfill % kWStages;
-                if (!mbar_wait(&sm.w_empty[stage], ((wfill / kWStages) & 1) ^ 1, status, 101)) goto done;
+                { PROF_T0(); const bool okw = mbar_wait(&sm.w_empty[stage], ((wfill / kWStages) & 1) ^ 1, status, 101); PROF_ADD(4); if (!okw) goto done; }
                 mbar_arrive_expect_tx(&sm.w_full[stage], bytes);
                 bulk_g2s(sm.wring[stage], wsrc + off, bytes, &sm.w_full[stage]);
                 off += bytes;
@@ -302,7 +311,7 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
               const int chunk_ks = (L == 8) ? 7 : 9;
               const uint32_t idesc = umma_idesc_bf16(kTM, n);
               if (ks_act > 0) {
-                if (!mbar_wait(&sm.act_ready, act_n & 1, status, 201)) goto done;
+                { PROF_T0(); const bool okw = mbar_wait(&sm.act_ready, act_n & 1, status, 201); PROF_ADD(2); if (!okw) goto done; }
                 ++act_n;
                 tc_fence_after_sync();
               }
@@ -311,7 +320,7 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
                 const int kf = ks % kpf;
                 if (kf == 0) {
                   stage = wfill % kWStages;
-                  if (!mbar_wait(&sm.w_full[stage], (wfill / kWStages) & 1, status, 202)) goto done;
+                  { PROF_T0(); const bool okw = mbar_wait(&sm.w_full[stage], (wfill / kWStages) & 1, status, 202); PROF_ADD(0); if (!okw) goto done; }
                   tc_fence_after_sync();
                 }
                 uint32_t a_addr;
@@ -321,7 +330,7 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
                 } else {
                   const int e = ks - ks_act, ce = e % chunk_ks;
                   if (ce == 0) {
-                    if (!mbar_wait(&sm.stg_full, stg_n & 1, status, 203)) goto done;
+                    { PROF_T0(); const bool okw = mbar_wait(&sm.stg_full, stg_n & 1, status, 203); PROF_ADD(1); if (!okw) goto done; }
                     ++stg_n;
                     tc_fence_after_sync();
                   }
@@ -330,11 +339,13 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
                 }
                 const uint64_t adesc = umma_smem_desc(a_addr, kRunBytes, 128);
                 const uint64_t bdesc = umma_smem_desc(smem_u32(sm.wring[stage]) + (uint32_t)kf * n * 32u, (uint32_t)n * 16u, 128);
-                umma_bf16(tmem_base, adesc, bdesc, idesc, ks > 0 ? 1u : 0u);
-                if (chunk_end) umma_commit(&sm.stg_empty);
-                if (kf == kpf - 1 || ks == ks_total - 1) { umma_commit(&sm.w_empty[stage]); ++wfill; }
+                { PROF_T0(); umma_bf16(tmem_base, adesc, bdesc, idesc, ks > 0 ? 1u : 0u); PROF_ADD(13); }
+                { PROF_T0();
+                  if (chunk_end) umma_commit(&sm.stg_empty);
+                  if (kf == kpf - 1 || ks == ks_total - 1) { umma_commit(&sm.w_empty[stage]); ++wfill; }
+                  PROF_ADD(14); }
               }
-              umma_commit(&sm.acc_full);
+              { PROF_T0(); umma_commit(&sm.acc_full); PROF_ADD(14); }
             }
           }
         }
@@ -403,39 +414,40 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
           }
           // ---- L0: x chunks
           for (int c = 0; c < 3; ++c) {
-            if (!mbar_wait(&sm.stg_empty, (stg_n & 1) ^ 1, status, 301)) goto done;
-            encode_x_chunk<kStage>(sm, rays, sc, tc, c, row, half, false, enc_rows, rows_valid);
-            compute_arrive(&sm.stg_full);
+            { PROF_T0(); const bool okw = mbar_wait(&sm.stg_empty, (stg_n & 1) ^ 1, status, 301); PROF_ADD(10); if (!okw) goto done; }
+            { PROF_T0(); encode_x_chunk<kStage>(sm, rays, sc, tc, c, row, half, false, enc_rows, rows_valid);
+              compute_arrive(&sm.stg_full); PROF_ADD(6); }
             ++stg_n;
           }
           for (int L = 0; L < 8; ++L) {
             if (L == 5) {
               for (int c = 0; c < 3; ++c) {
-                if (!mbar_wait(&sm.stg_empty, (stg_n & 1) ^ 1, status, 302)) goto done;
-                encode_x_chunk<kStage>(sm, rays, sc, tc, c, row, half, true, enc_rows, rows_valid);
-                compute_arrive(&sm.stg_full);
+                { PROF_T0(); const bool okw = mbar_wait(&sm.stg_empty, (stg_n & 1) ^ 1, status, 302); PROF_ADD(10); if (!okw) goto done; }
+                { PROF_T0(); encode_x_chunk<kStage>(sm, rays, sc, tc, c, row, half, true, enc_rows, rows_valid);
+                  compute_arrive(&sm.stg_full); PROF_ADD(6); }
                 ++stg_n;
               }
             }
-            if (!mbar_wait(&sm.acc_full, acc_n & 1, status, 303)) goto done;
+            { PROF_T0(); const bool okw = mbar_wait(&sm.acc_full, acc_n & 1, status, 303); PROF_ADD(9); if (!okw) goto done; }
             ++acc_n;
             tc_fence_after_sync();
-            if (L == 7) epilogue<1>(sm, tmem_base, L, warp, lane);
-            else epilogue<0>(sm, tmem_base, L, warp, lane);
-            compute_arrive(&sm.act_ready);
+            { PROF_T0();
+              if (L == 7) epilogue<1>(sm, tmem_base, L, warp, lane);
+              else epilogue<0>(sm, tmem_base, L, warp, lane);
+              compute_arrive(&sm.act_ready); PROF_ADD(8); }
           }
           // ---- V: d chunks
           compute_bar_sync();               // wcache (written during L5's encode) visible to all
           for (int c = 0; c < 6; ++c) {
-            if (!mbar_wait(&sm.stg_empty, (stg_n & 1) ^ 1, status, 304)) goto done;
-            encode_d_chunk<kStage>(sm, tc, c, row, half, tile_ray0, enc_rows, rows_valid);
-            compute_arrive(&sm.stg_full);
+            { PROF_T0(); const bool okw = mbar_wait(&sm.stg_empty, (stg_n & 1) ^ 1, status, 304); PROF_ADD(10); if (!okw) goto done; }
+            { PROF_T0(); encode_d_chunk<kStage>(sm, tc, c, row, half, tile_ray0, enc_rows, rows_valid);
+              compute_arrive(&sm.stg_full); PROF_ADD(7); }
             ++stg_n;
           }
-          if (!mbar_wait(&sm.acc_full, acc_n & 1, status, 305)) goto done;
+          { PROF_T0(); const bool okw = mbar_wait(&sm.acc_full, acc_n & 1, status, 305); PROF_ADD(9); if (!okw) goto done; }
           ++acc_n;
           tc_fence_after_sync();
-          epilogue<2>(sm, tmem_base, 8, warp, lane);
+          { PROF_T0(); epilogue<2>(sm, tmem_base, 8, warp, lane); PROF_ADD(8); }
           tc_fence_before_sync();
           compute_bar_sync();
           if (tid < kTM) {
@@ -500,6 +512,13 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
     }
   }
 done:
+  if (prof) {
+    unsigned long long* pp = prof + (size_t)blockIdx.x * 16;
+    const unsigned long long total = (unsigned long long)(clock64() - kernel_t0);
+    if (warp == kIssuerWarp && lane == 0) { pp[0] = pacc[0]; pp[1] = pacc[1]; pp[2] = pacc[2]; pp[3] = total; pp[13] = pacc[13]; pp[14] = pacc[14]; }
+    if (warp == kProducerWarp && lane == 0) { pp[4] = pacc[4]; pp[5] = total; }
+    if (tid == 0) { for (int i = 6; i <= 10; ++i) pp[i] = pacc[i]; pp[12] = total; }
+  }
   tc_fence_before_sync();
   __syncthreads();
   if (warp == kIssuerWarp) {
@@ -593,14 +612,14 @@ static cudaError_t configure_bf16() {
 
 cudaError_t pgn_launch_render_bf16(const PgnRayRefs& rays, const PgnOutputs& out, const PgnBf16Net& nc,
                                    const PgnBf16Net& nf, const PgnScalars* sc_dev, const float* near_far,
-                                   int* status, int num_sms, cudaStream_t stream) {
+                                   int* status, unsigned long long* prof, int num_sms, cudaStream_t stream) {
   cudaError_t e = configure_bf16();
   if (e != cudaSuccess) return e;
   const long long n_groups = (rays.n_rays + kRPG - 1) / kRPG;
   if (n_groups == 0) return cudaSuccess;
   const int grid = (int)min((long long)num_sms, n_groups);
   pgn_render_bf16_kernel<false><<<grid, kThreads, sizeof(Smem) + 1024, stream>>>(rays, out, nc, nf, sc_dev, near_far,
-                                                                                 nullptr, 0, nullptr, status);
+                                                                                 nullptr, 0, nullptr, status, prof);
   return cudaGetLastError();
 }
 
@@ -614,6 +633,6 @@ cudaError_t pgn_launch_mlp_bf16(const PgnBf16Net& net, const float* enc, long lo
   PgnRayRefs rays{};
   PgnOutputs out{};
   pgn_render_bf16_kernel<true><<<grid, kThreads, sizeof(Smem) + 1024, stream>>>(rays, out, net, net, sc_dev, nullptr,
-                                                                                enc, m, raw, status);
+                                                                                enc, m, raw, status, nullptr);
   return cudaGetLastError();
 }

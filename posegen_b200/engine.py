@@ -236,6 +236,16 @@ class Engine:
                                               _ptr(img), self._stream()))
         return img.view(H, W, 3)
 
+    PHASES = ["issuer_wait_weights", "issuer_wait_staging", "issuer_wait_act", "issuer_total", "producer_wait_slot",
+              "producer_total", "encode_x", "encode_d", "epilogue", "wait_acc", "wait_stg_free", "-", "compute_total",
+              "issuer_mma_issue", "issuer_commit", "-"]
+
+    def phase_timers(self, enable=True, read=False):
+        """Enable/disable the bf16 kernel's phase timers; read=True returns the last launch's averages (cycles)."""
+        buf = (C.c_uint64 * 16)()
+        _lib.check(self.lib.pgn_debug_phase_timers(self.handle, 1 if enable else 0, buf if read else None))
+        return {n: int(buf[i]) for i, n in enumerate(self.PHASES) if n != "-"} if read else None
+
     def debug_umma_gemm(self, A, B, variant=0):
         K, N = A.shape[1], B.shape[0]
         D = torch.empty((128, N), dtype=torch.float32, device=A.device)

@@ -21,7 +21,7 @@ def case_a(engine):
     return dict(g=g, ckpt=ckpt, rb=t(rb), sk=t(frame.pose.skts), cy=t(cyl), ref=ref, taps=taps)
 
 
-@pytest.mark.parametrize("K,N", [(16, 256), (64, 256), (256, 256), (432, 256), (112, 128), (928, 128)])
+@pytest.mark.parametrize("K,N", [(16, 256), (64, 256), (256, 256), (208, 256), (112, 128), (384, 128)])
 def test_tcgen05_probe_gemm(engine, K, N):
     torch.manual_seed(K * 1000 + N)
     A, B = torch.randn(128, K, device="cuda"), torch.randn(N, K, device="cuda")
@@ -82,8 +82,10 @@ def test_mlp_bf16_tensor_engine(engine, case_a, net_id):
     engine.check_status()
     raw = raw.cpu().numpy()
     # bf16 inputs/activations: 2e-2 of the output scale (sigma head x400 => absolute scale ~ 4)
-    assert pu.max_abs(raw[:, :3], ref[:, :3]) <= 2e-2 * max(1e-1, np.abs(ref[:, :3]).max())
-    assert pu.max_abs(raw[:, 3], ref[:, 3]) <= 2e-2 * np.abs(ref[:, 3]).max()
+    # bf16 inputs/activations: raw outputs move by ~1e-4 at default init (SURVEY.md §8d measured 5e-4 / 1.2e-3
+    # for the reference under bf16 autocast); the alpha head of this fixture is boosted x400
+    assert pu.max_abs(raw[:, :3], ref[:, :3]) <= 2e-3
+    assert pu.max_abs(raw[:, 3], ref[:, 3]) <= 400 * 5e-4
 
 
 def test_composite_matches_raw2outputs(engine, case_a):

@@ -169,7 +169,28 @@ def step_time(eng, precisions=("bf16", "fp32")):
                 tflops=round(n * 248205312 / ms * 1e3 / 1e12, 2))
 
 
-STEPS = {"probe": step_probe, "stages": step_stages, "mlp": step_mlp, "render": step_render, "time": step_time}
+def step_phases(eng, precisions=("bf16",)):
+    ckpt = syn.synthetic_raycaster_state(0, alpha_gain=400.)
+    eng.load_checkpoint(ckpt)
+    dev = eng.device
+    frame = syn.synthetic_frame(5, 512, 512)
+    rb = torch.as_tensor(syn.ray_batch(frame.rays_o, frame.rays_d), device=dev)
+    sk, cy = torch.as_tensor(frame.pose.skts, device=dev), torch.as_tensor(frame.pose.cyl, device=dev)
+    eng.phase_timers(True)
+    for _ in range(2):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        eng.render(rb, sk, cy, nanfill_chunk=4096, precision="bf16", return_alpha=False)
+        e1.record()
+        torch.cuda.synchronize()
+    t = eng.phase_timers(False, read=True)
+    n = rb.shape[0]
+    tiles_per_cta = (n / 8) * 9 / 148
+    log("phases", ms=round(e0.elapsed_time(e1), 3), n_rays=n, tiles_per_cta=round(tiles_per_cta, 1),
+        **{k: round(v / tiles_per_cta) for k, v in t.items()})
+
+
+STEPS = {"phases": step_phases, "probe": step_probe, "stages": step_stages, "mlp": step_mlp, "render": step_render, "time": step_time}
 
 if __name__ == "__main__":
     eng = Engine()
