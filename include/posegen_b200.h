@@ -215,8 +215,9 @@ PGN_API int  pgn_compose_frame(pgn_context* ctx, int32_t H, int32_t W, int32_t x
 PGN_API int  pgn_debug_phase_timers(pgn_context* ctx, int32_t enable, uint64_t* out16);
 
 /* bring-up probe of the tcgen05 plumbing: D[128,N] = A[128,K] * B[N,K]^T with bf16 inputs
- * and fp32 accumulation, one CTA.  variant bit 0 swaps the descriptor LBO/SBO fields
- * (expected to be WRONG; kept so tests can assert the documented convention). */
+ * and fp32 accumulation, one CTA.  variant bit 1 selects the CTA-pair form (cta_group::2, UMMA M=256):
+ * A is [256,K], D is [256,N], two CTAs of one cluster each stage half of A and half of B.
+ * (variant bit 0 swaps the descriptor LBO/SBO fields: known-bad, faults; bring-up only.) */
 PGN_API int  pgn_debug_umma_gemm(pgn_context* ctx, const float* A, const float* B, float* D, int32_t K, int32_t N,
                                  int32_t variant, void* stream);
 

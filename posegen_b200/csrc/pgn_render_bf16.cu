@@ -40,7 +40,7 @@ constexpr int kTM = 128;                // rows per tile (UMMA M)
 constexpr int kRunBytes = kTM * 16;     // one 8-wide K run of all 128 rows
 constexpr int kActBytes = 256 / 8 * kRunBytes;          // 65536
 constexpr int kStgBytes = 18 * kRunBytes;               // 36864 (144 K)
-constexpr int kWStages = 8;
+constexpr int kWStages = 8;             // 8 x 8 KB = one full 256x256 layer half per CTA
 constexpr int kWStageBytes = 8192;
 constexpr int kTmemCols = 256;
 constexpr int kMaxTileRays = 3;
@@ -216,23 +216,30 @@ __device__ __forceinline__ void epilogue(Smem& sm, uint32_t tmem_base, int layer
   if (MODE == 2) { sm.part[half][row][0] = r0; sm.part[half][row][1] = r1; sm.part[half][row][2] = r2; }
 }
 
+// "my part of the A operand is written / my TMEM reads are done" -> the LEADER CTA's barrier
 __device__ __forceinline__ void compute_arrive(uint64_t* bar) {
   tc_fence_before_sync();
   fence_proxy_async_smem();
-  mbar_arrive(bar);
+  mbar_arrive_cluster(bar, 0);
 }
 __device__ __forceinline__ void compute_bar_sync() { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }
 
 // optional phase timers (cycles, one elected thread per role, accumulated per CTA):
 //  0 issuer wait w_full | 1 issuer wait stg_full | 2 issuer wait act_ready | 3 issuer total
 //  4 producer wait w_empty | 5 producer total
-//  6 encode_x | 7 encode_d | 8 epilogue | 9 wait acc_full | 10 wait stg_empty | 11 composite+setup | 12 compute total
+//  6 encode_x | 7 encode_d | 8 epilogue | 9 wait acc_full | 10 wait stg_empty | 12 compute total
+//  13 issuer MMA issue | 14 issuer commits
 #define PROF_T0() const long long _pt0 = prof ? clock64() : 0
 #define PROF_ADD(slot) do { if (prof) pacc[slot] += (unsigned long long)(clock64() - _pt0); } while (0)
 
+// Static per-cluster-iteration schedule: the two CTAs of a pair always run the same tile sequence
+// (4 coarse + 5 fine pair-tiles; rows beyond a CTA's rays are masked), so the leader's issuer, both
+// weight producers, the peer's relay and both sets of compute warps stay in lock-step by construction.
+__device__ __forceinline__ int tiles_in_pass(int pass) { return pass == 0 ? (kRPG * PGN_S) / kTM : (kRPG * PGN_T) / kTM; }
+
 // ------------------------------------------------------------------ the kernel
 template <bool kStage>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf16Net net_f,
                        const PgnScalars* __restrict__ scp, const float* __restrict__ near_far,
                        const float* __restrict__ enc_global, long long enc_rows_total, float* __restrict__ raw_global,
@@ -241,52 +248,55 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
   Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   volatile int* status = status_g;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
   const PgnScalars& sc = *scp;
+  const long long n_clusters = gridDim.x >> 1, cluster_id = blockIdx.x >> 1;
 
-  // work decomposition shared by all roles
-  const long long n_groups = kStage ? (enc_rows_total + kTM - 1) / kTM : (rays.n_rays + kRPG - 1) / kRPG;
+  // work units: a "pair-group" = two ray groups (one per CTA); stage mode: two 128-row tiles
+  const long long n_units = kStage ? (enc_rows_total + kTM - 1) / kTM : (rays.n_rays + kRPG - 1) / kRPG;
+  const long long n_pairs = (n_units + 1) / 2;
+  const int n_pass = kStage ? 1 : 2;
 
   if (tid == 0) {
-    for (int s = 0; s < kWStages; ++s) { mbar_init(&sm.w_full[s], 1); mbar_init(&sm.w_empty[s], 1); }
-    mbar_init(&sm.stg_full, kComputeThreads);
+    for (int s = 0; s < kWStages; ++s) { mbar_init(&sm.w_full[s], rank == 0 ? 2 : 1); mbar_init(&sm.w_empty[s], 1); }
+    mbar_init(&sm.stg_full, 2 * kComputeThreads);
     mbar_init(&sm.stg_empty, 1);
-    mbar_init(&sm.act_ready, kComputeThreads);
+    mbar_init(&sm.act_ready, 2 * kComputeThreads);
     mbar_init(&sm.acc_full, 1);
     fence_mbar_init();
   }
   if (warp == kIssuerWarp) {
-    tmem_alloc(&sm.tmem_base, kTmemCols);
-    tmem_relinquish();
+    tmem_alloc_2cta(&sm.tmem_base, kTmemCols);
+    tmem_relinquish_2cta();
   }
   tc_fence_before_sync();
   __syncthreads();
+  cluster_sync_all();
   tc_fence_after_sync();
   const uint32_t tmem_base = sm.tmem_base;
   unsigned long long pacc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   const long long kernel_t0 = prof ? clock64() : 0;
 
   if (warp == kProducerWarp) {
-    // ===================== weight producer =====================
+    // ===================== weight producer (each CTA streams ITS N-half of every fill) =====================
     if (lane == 0) {
       uint32_t wfill = 0;
-      for (long long g = blockIdx.x; g < n_groups; g += gridDim.x) {
-        const int nr = kStage ? 0 : (int)min((long long)kRPG, rays.n_rays - g * kRPG);
-        for (int pass = 0; pass < (kStage ? 1 : 2); ++pass) {
-          const int S = pass == 0 ? PGN_S : PGN_T;
-          const int ntiles = kStage ? 1 : (nr * S + kTM - 1) / kTM;
+      for (long long u = cluster_id; u < n_pairs; u += n_clusters) {
+        for (int pass = 0; pass < n_pass; ++pass) {
+          const int ntiles = kStage ? 1 : tiles_in_pass(pass);
           const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(pass == 0 ? net_c.wstream : net_f.wstream);
           for (int t = 0; t < ntiles; ++t) {
             size_t off = 0;
             for (int L = 0; L < 9; ++L) {
-              const int n = pgn_layer_n(L), ks_total = pgn_layer_ksteps(L), kpf = pgn_ks_per_fill(L);
+              const int nh = pgn_layer_n(L) / 2, ks_total = pgn_layer_ksteps(L), kpf = pgn_ks_per_fill(L);
               for (int ks = 0; ks < ks_total; ks += kpf) {
                 const int nks = min(kpf, ks_total - ks);
-                const uint32_t bytes = (uint32_t)nks * n * 32u;
+                const uint32_t bytes = (uint32_t)nks * nh * 32u;          // this CTA's half of the fill
                 const int stage = wfill % kWStages;
                 { PROF_T0(); const bool okw = mbar_wait(&sm.w_empty[stage], ((wfill / kWStages) & 1) ^ 1, status, 101); PROF_ADD(4); if (!okw) goto done; }
                 mbar_arrive_expect_tx(&sm.w_full[stage], bytes);
-                bulk_g2s(sm.wring[stage], wsrc + off, bytes, &sm.w_full[stage]);
-                off += bytes;
+                bulk_g2s(sm.wring[stage], wsrc + off + (size_t)rank * bytes, bytes, &sm.w_full[stage]);
+                off += 2u * bytes;
                 ++wfill;
               }
             }
@@ -295,23 +305,40 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
       }
     }
   } else if (warp == kIssuerWarp) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      uint32_t wfill = 0, stg_n = 0, act_n = 0;
-      const uint32_t act_addr = smem_u32(sm.act), stg_addr = smem_u32(sm.stg);
-      for (long long g = blockIdx.x; g < n_groups; g += gridDim.x) {
-        const int nr = kStage ? 0 : (int)min((long long)kRPG, rays.n_rays - g * kRPG);
-        for (int pass = 0; pass < (kStage ? 1 : 2); ++pass) {
-          const int S = pass == 0 ? PGN_S : PGN_T;
-          const int ntiles = kStage ? 1 : (nr * S + kTM - 1) / kTM;
+    if (lane == 0 && rank == 1) {
+      // ===================== peer relay: "my half of fill f has landed" -> leader's w_full =====================
+      uint32_t wfill = 0;
+      for (long long u = cluster_id; u < n_pairs; u += n_clusters) {
+        for (int pass = 0; pass < n_pass; ++pass) {
+          const int ntiles = kStage ? 1 : tiles_in_pass(pass);
           for (int t = 0; t < ntiles; ++t) {
             for (int L = 0; L < 9; ++L) {
-              const int n = pgn_layer_n(L), ks_total = pgn_layer_ksteps(L), kpf = pgn_ks_per_fill(L);
+              const int ks_total = pgn_layer_ksteps(L), kpf = pgn_ks_per_fill(L);
+              for (int ks = 0; ks < ks_total; ks += kpf) {
+                const int stage = wfill % kWStages;
+                if (!mbar_wait(&sm.w_full[stage], (wfill / kWStages) & 1, status, 401)) goto done;
+                mbar_arrive_cluster(&sm.w_full[stage], 0);
+                ++wfill;
+              }
+            }
+          }
+        }
+      }
+    } else if (lane == 0) {
+      // ===================== MMA issuer (leader CTA): UMMA M=256 over both CTAs =====================
+      uint32_t wfill = 0, stg_n = 0, act_n = 0;
+      const uint32_t act_addr = smem_u32(sm.act), stg_addr = smem_u32(sm.stg);
+      for (long long u = cluster_id; u < n_pairs; u += n_clusters) {
+        for (int pass = 0; pass < n_pass; ++pass) {
+          const int ntiles = kStage ? 1 : tiles_in_pass(pass);
+          for (int t = 0; t < ntiles; ++t) {
+            for (int L = 0; L < 9; ++L) {
+              const int n = pgn_layer_n(L), nh = n / 2, ks_total = pgn_layer_ksteps(L), kpf = pgn_ks_per_fill(L);
               const int ks_act = pgn_layer_kact(L) / 16;
               const int chunk_ks = (L == 8) ? 7 : 9;
-              const uint32_t idesc = umma_idesc_bf16(kTM, n);
+              const uint32_t idesc = umma_idesc_bf16(2 * kTM, n);
               if (ks_act > 0) {
-                { PROF_T0(); const bool okw = mbar_wait(&sm.act_ready, act_n & 1, status, 201); PROF_ADD(2); if (!okw) goto done; }
+                { PROF_T0(); const bool okw = mbar_wait_cluster(&sm.act_ready, act_n & 1, status, 201); PROF_ADD(2); if (!okw) goto done; }
                 ++act_n;
                 tc_fence_after_sync();
               }
@@ -320,7 +347,7 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
                 const int kf = ks % kpf;
                 if (kf == 0) {
                   stage = wfill % kWStages;
-                  { PROF_T0(); const bool okw = mbar_wait(&sm.w_full[stage], (wfill / kWStages) & 1, status, 202); PROF_ADD(0); if (!okw) goto done; }
+                  { PROF_T0(); const bool okw = mbar_wait_cluster(&sm.w_full[stage], (wfill / kWStages) & 1, status, 202); PROF_ADD(0); if (!okw) goto done; }
                   tc_fence_after_sync();
                 }
                 uint32_t a_addr;
@@ -330,7 +357,7 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
                 } else {
                   const int e = ks - ks_act, ce = e % chunk_ks;
                   if (ce == 0) {
-                    { PROF_T0(); const bool okw = mbar_wait(&sm.stg_full, stg_n & 1, status, 203); PROF_ADD(1); if (!okw) goto done; }
+                    { PROF_T0(); const bool okw = mbar_wait_cluster(&sm.stg_full, stg_n & 1, status, 203); PROF_ADD(1); if (!okw) goto done; }
                     ++stg_n;
                     tc_fence_after_sync();
                   }
@@ -338,14 +365,14 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
                   chunk_end = (ce == chunk_ks - 1);
                 }
                 const uint64_t adesc = umma_smem_desc(a_addr, kRunBytes, 128);
-                const uint64_t bdesc = umma_smem_desc(smem_u32(sm.wring[stage]) + (uint32_t)kf * n * 32u, (uint32_t)n * 16u, 128);
-                { PROF_T0(); umma_bf16(tmem_base, adesc, bdesc, idesc, ks > 0 ? 1u : 0u); PROF_ADD(13); }
+                const uint64_t bdesc = umma_smem_desc(smem_u32(sm.wring[stage]) + (uint32_t)kf * nh * 32u, (uint32_t)nh * 16u, 128);
+                { PROF_T0(); umma_bf16_2cta(tmem_base, adesc, bdesc, idesc, ks > 0 ? 1u : 0u); PROF_ADD(13); }
                 { PROF_T0();
-                  if (chunk_end) umma_commit(&sm.stg_empty);
-                  if (kf == kpf - 1 || ks == ks_total - 1) { umma_commit(&sm.w_empty[stage]); ++wfill; }
+                  if (chunk_end) umma_commit_2cta(&sm.stg_empty);
+                  if (kf == kpf - 1 || ks == ks_total - 1) { umma_commit_2cta(&sm.w_empty[stage]); ++wfill; }
                   PROF_ADD(14); }
               }
-              { PROF_T0(); umma_commit(&sm.acc_full); PROF_ADD(14); }
+              { PROF_T0(); umma_commit_2cta(&sm.acc_full); PROF_ADD(14); }
             }
           }
         }
@@ -355,9 +382,10 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
     // ===================== compute warps (encode, epilogue, composite) =====================
     uint32_t stg_n = 0, acc_n = 0;
     const int row = tid & (kTM - 1), half = tid >> 7;
-    for (long long g = blockIdx.x; g < n_groups; g += gridDim.x) {
-      const long long ray0 = g * kRPG;
-      const int nr = kStage ? 0 : (int)min((long long)kRPG, rays.n_rays - ray0);
+    for (long long u = cluster_id; u < n_pairs; u += n_clusters) {
+      const long long unit = 2 * u + rank;                 // this CTA's ray group (or stage tile)
+      const long long ray0 = unit * kRPG;
+      const int nr = kStage ? 0 : (int)max(0ll, min((long long)kRPG, rays.n_rays - ray0));
       if (!kStage) {
         compute_bar_sync();
         if (tid < kRPG * 3) {
@@ -377,11 +405,11 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
           sm.zc[rl][s] = (rl < nr) ? pgn_coarse_z(near_far[(ray0 + rl) * 2], near_far[(ray0 + rl) * 2 + 1], sc.t_coarse[s]) : 0.f;
         }
       }
-      for (int pass = 0; pass < (kStage ? 1 : 2); ++pass) {
+      for (int pass = 0; pass < n_pass; ++pass) {
         const int S = pass == 0 ? PGN_S : PGN_T;
         const PgnBf16Net& net = pass == 0 ? net_c : net_f;
         const int total_rows = kStage ? kTM : nr * S;
-        const int ntiles = kStage ? 1 : (total_rows + kTM - 1) / kTM;
+        const int ntiles = kStage ? 1 : tiles_in_pass(pass);
         // epilogue vectors of this net
         compute_bar_sync();
         for (int i = tid; i < 9 * 256; i += kComputeThreads) sm.bias[i] = net.bias[i];
@@ -391,9 +419,9 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
 
         for (int t = 0; t < ntiles; ++t) {
           TileCtx tc{ray0, S, t * kTM, total_rows};
-          const float* enc_rows = kStage ? enc_global + (size_t)g * kTM * PGN_ENC : nullptr;
-          const int rows_valid = kStage ? (int)min((long long)kTM, enc_rows_total - g * kTM) : kTM;
-          const int tile_ray0 = kStage ? 0 : tc.row0 / S;
+          const float* enc_rows = kStage ? enc_global + (size_t)unit * kTM * PGN_ENC : nullptr;
+          const int rows_valid = kStage ? (int)max(0ll, min((long long)kTM, enc_rows_total - unit * kTM)) : kTM;
+          const int tile_ray0 = kStage ? 0 : min(tc.row0 / S, kRPG - 1);
           if (!kStage) {
             // PE table of the joint-frame view directions for the <=3 rays of this tile
             const int tile_ray1 = min((tc.row0 + kTM - 1) / S, nr - 1);
@@ -457,7 +485,7 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
             const float sg = sm.part[0][tid][3] + sm.part[1][tid][3] + net.b_alpha[0];
             if (kStage) {
               if (tid < rows_valid) {
-                float* o = raw_global + ((size_t)g * kTM + tid) * 4;
+                float* o = raw_global + ((size_t)unit * kTM + tid) * 4;
                 o[0] = r0; o[1] = r1; o[2] = r2; o[3] = sg;
               }
             } else {
@@ -521,10 +549,11 @@ done:
   }
   tc_fence_before_sync();
   __syncthreads();
+  __syncwarp();
+  cluster_sync_all();                 // the peer's TMEM/smem must stay alive until every MMA has retired
   if (warp == kIssuerWarp) {
-    __syncwarp();
     tc_fence_after_sync();
-    tmem_dealloc(tmem_base, kTmemCols);
+    tmem_dealloc_2cta(tmem_base, kTmemCols);
   }
 }
 
@@ -559,12 +588,21 @@ __global__ void pgn_pack_wstream_kernel(PackPtrs p, const float* __restrict__ fo
       if (off < le) break;
       off -= le;
     }
-    const int n_l = pgn_layer_n(L);
-    // within layer: [kstep][khalf][n][8]
-    const int e = (int)(off & 7);
-    const int n = (int)((off >> 3) % n_l);
-    const int kh = (int)((off / (8 * (size_t)n_l)) & 1);
-    const int ks = (int)(off / (16 * (size_t)n_l));
+    const int n_l = pgn_layer_n(L), nh = n_l / 2, kpf = pgn_ks_per_fill(L), ks_total = pgn_layer_ksteps(L);
+    // within layer: fills of kpf K-steps; within a fill: [cta rank][kstep][khalf][n_local (N/2)][8]
+    const size_t full_fill = (size_t)kpf * n_l * 16;
+    const int f = (int)(off / full_fill);
+    const int nks = min(kpf, ks_total - f * kpf);
+    size_t r = off - (size_t)f * full_fill;
+    const size_t per_rank = (size_t)nks * nh * 16;
+    const int crank = (int)(r / per_rank);
+    r -= (size_t)crank * per_rank;
+    const int ks = f * kpf + (int)(r / ((size_t)nh * 16));
+    r %= (size_t)nh * 16;
+    const int kh = (int)(r / ((size_t)nh * 8));
+    r %= (size_t)nh * 8;
+    const int n = crank * nh + (int)(r >> 3);
+    const int e = (int)(r & 7);
     const int kp = ks * 16 + kh * 8 + e;
     float v = 0.f;
     if (L == 0) v = p.w[0][(size_t)n * 432 + pgn_xperm_refcol(kp)];
@@ -617,7 +655,8 @@ cudaError_t pgn_launch_render_bf16(const PgnRayRefs& rays, const PgnOutputs& out
   if (e != cudaSuccess) return e;
   const long long n_groups = (rays.n_rays + kRPG - 1) / kRPG;
   if (n_groups == 0) return cudaSuccess;
-  const int grid = (int)min((long long)num_sms, n_groups);
+  const long long n_pairs = (n_groups + 1) / 2;
+  const int grid = 2 * (int)min((long long)(num_sms / 2), n_pairs);      // clusters of 2 CTAs
   pgn_render_bf16_kernel<false><<<grid, kThreads, sizeof(Smem) + 1024, stream>>>(rays, out, nc, nf, sc_dev, near_far,
                                                                                  nullptr, 0, nullptr, status, prof);
   return cudaGetLastError();
@@ -629,7 +668,7 @@ cudaError_t pgn_launch_mlp_bf16(const PgnBf16Net& net, const float* enc, long lo
   if (e != cudaSuccess) return e;
   const long long n_tiles = (m + kTM - 1) / kTM;
   if (n_tiles == 0) return cudaSuccess;
-  const int grid = (int)min((long long)num_sms, n_tiles);
+  const int grid = 2 * (int)min((long long)(num_sms / 2), (n_tiles + 1) / 2);
   PgnRayRefs rays{};
   PgnOutputs out{};
   pgn_render_bf16_kernel<true><<<grid, kThreads, sizeof(Smem) + 1024, stream>>>(rays, out, net, net, sc_dev, nullptr,
