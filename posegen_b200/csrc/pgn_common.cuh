@@ -233,6 +233,88 @@ __device__ __forceinline__ void pgn_composite_warp(const float* __restrict__ raw
 }
 
 // ---------------------------------------------------------------------------
+// Incremental form of the same compositing (raw2outputs) for samples [s0, s1) of one ray whose
+// earlier samples were composited before: `carry` = {T before s0, sum w*r, sum w*g, sum w*b,
+// sum w, sum w*z}.  Used by the tensor-core kernel, whose 128-row tiles cut fine rays (80
+// samples) at arbitrary positions, so no per-ray raw buffer has to be kept.
+//   raw_seg: rows of samples s0..s1-1 ([i - s0][4]);  z: the ray's full z array [S].
+// All lanes of the warp must call it; carry is updated by lane 0 (then __syncwarp()).
+// ---------------------------------------------------------------------------
+template <int S>
+__device__ __forceinline__ void pgn_composite_segment_warp(const float* __restrict__ raw_seg, const float* __restrict__ z,
+                                                           int s0, int s1, float dnorm, float density_scale, float rgb_eps,
+                                                           int lane, float* carry, float* weights_out, float* alpha_out) {
+  constexpr int CH = 3;                                  // up to 96 samples per call
+  float a[CH], p[CH];
+  float lane_prod = 1.0f;
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    const int i = s0 + lane * CH + c;
+    float al = 0.0f;
+    if (i < s1) {
+      float dist = (i + 1 < S) ? __fsub_rn(z[i + 1], z[i]) : 1e10f;
+      dist = __fmul_rn(dist, dnorm);
+      const float sig = fmaxf(raw_seg[(i - s0) * 4 + 3] / density_scale, 0.0f);
+      al = 1.0f - expf(-__fmul_rn(sig, dist));
+    }
+    a[c] = al;
+    p[c] = lane_prod;
+    if (i < s1) lane_prod = lane_prod * (__fadd_rn(__fsub_rn(1.0f, al), 1e-10f));
+  }
+  float incl = lane_prod;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const float up = __shfl_up_sync(0xffffffffu, incl, off);
+    if (lane >= off) incl *= up;
+  }
+  float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+  if (lane == 0) excl = 1.0f;
+  const float t_in = carry[0];
+  const float seg_prod = __shfl_sync(0xffffffffu, incl, 31);
+  float sr = 0.f, sg = 0.f, sb = 0.f, sw = 0.f, sd = 0.f;
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    const int i = s0 + lane * CH + c;
+    if (i < s1) {
+      const float w = a[c] * (t_in * (excl * p[c]));
+      if (weights_out) weights_out[i] = w;
+      if (alpha_out) alpha_out[i] = a[c];
+      const float k = 1.0f + 2.0f * rgb_eps;
+      const float* rw = raw_seg + (i - s0) * 4;
+      const float r = (1.0f / (1.0f + expf(-rw[0]))) * k - rgb_eps;
+      const float g = (1.0f / (1.0f + expf(-rw[1]))) * k - rgb_eps;
+      const float b = (1.0f / (1.0f + expf(-rw[2]))) * k - rgb_eps;
+      sr = fmaf(w, r, sr); sg = fmaf(w, g, sg); sb = fmaf(w, b, sb);
+      sw += w; sd = fmaf(w, z[i], sd);
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    sr += __shfl_xor_sync(0xffffffffu, sr, off);
+    sg += __shfl_xor_sync(0xffffffffu, sg, off);
+    sb += __shfl_xor_sync(0xffffffffu, sb, off);
+    sw += __shfl_xor_sync(0xffffffffu, sw, off);
+    sd += __shfl_xor_sync(0xffffffffu, sd, off);
+  }
+  __syncwarp();
+  if (lane == 0) {
+    carry[0] = t_in * seg_prod;
+    carry[1] += sr; carry[2] += sg; carry[3] += sb; carry[4] += sw; carry[5] += sd;
+  }
+  __syncwarp();
+}
+
+// outputs of a finished ray from its carry (nerf.py:188-203)
+__device__ __forceinline__ void pgn_composite_finalize(const float* carry, float* rgb3, float* disp, float* acc) {
+  const float sw = carry[4], sd = carry[5];
+  rgb3[0] = carry[1]; rgb3[1] = carry[2]; rgb3[2] = carry[3];
+  float dv = 1.0f / fmaxf(1e-10f, sd / (sw + 1e-10f));
+  if (fabsf(sw) <= 1e-8f) dv = 0.0f;
+  *disp = dv;
+  *acc = fminf(sw, 1.0f);
+}
+
+// ---------------------------------------------------------------------------
 // Warp-level inverse-CDF resampling of one ray (det=True):
 //   sample_pdf            core/utils/ray_utils.py:157-201
 //   isample_from_lineseg  core/utils/ray_utils.py:255-289

@@ -1,27 +1,33 @@
-// bf16 tensor-core render path (PGN_PRECISION_BF16): fused per-ray-tile pipeline on
-// tcgen05 (UMMA M=128, fp32 accumulators in TMEM), weights streamed by the TMA engine
-// (cp.async.bulk) as pre-packed K-major slabs, activations resident in shared memory.
+// bf16 tensor-core render path (PGN_PRECISION_BF16): fused per-ray-tile pipeline on tcgen05.
 //
-// One persistent CTA per SM renders groups of 8 rays:
-//   coarse: 8x64 samples  = 4 tiles of 128 rows        (network_fn)
-//   composite -> inverse-CDF resample -> merge (warp per ray)
-//   fine:   8x80 samples  = 5 tiles of 128 rows        (network_fine)
-//   composite -> outputs
-// Per 128-row tile, 9 tensor-core layers (K-steps of 16):
-//   L0  x_p(432)            -> 256  ReLU      A generated on the fly (skeleton-relative
-//   L1-4 h(256)             -> 256  ReLU        encoding + cutoff PE, 8 joints per chunk)
-//   L5  h(256) | x_p(432)   -> 256  ReLU      (skip concat as two accumulating K ranges)
-//   L6-7 h(256)             -> 256  ReLU      (sigma head folded into L7's epilogue, fp32)
-//   V   h7(256) | d(672)    -> 128  ReLU      (feature_linear folded into views_linears[0];
-//                                              rgb head folded into the epilogue, fp32)
-// The samples x joints x embedding tensor only ever exists as 36 KB chunks in shared memory.
+// Execution model
+//   * CTA pairs (clusters of 2, cta_group::2): one UMMA covers M=256 rows (128 per CTA), fp32
+//     accumulators in TMEM; the weight (B) operand is split along N between the two CTAs, so each
+//     SM streams only half of every layer from L2 (cp.async.bulk into a 5-deep ring).
+//   * two tiles in flight per CTA ("slots": 2 x 256 TMEM columns, 2 x 64 KB activation buffers):
+//     while the tensor core runs a layer of one slot, the CUDA cores run the epilogue / encoding of
+//     the other.  A static interleaving of the two slots' layer jobs is followed by every role.
+//   * each CTA renders groups of 8 rays: 4 coarse tiles (8x64 samples, network_fn) and 5 fine tiles
+//     (8x80 samples, network_fine); tile order C(g0) | F(g,0) C(g+1,0) F(g,1) C(g+1,1) ... so the
+//     resampling of group g+1 is hidden behind the fine pass of group g.
+//   * per 128-row tile, 9 tensor-core layers (K-steps of 16):
+//       L0   x_p(480)            -> 256 ReLU   A generated on the fly (skeleton-relative encoding +
+//       L1-4 h(256)              -> 256 ReLU     cutoff PE, 4 joints per 20 KB chunk)
+//       L5   h(256) | x_p(480)   -> 256 ReLU   (skip concat = two accumulating K ranges)
+//       L6-7 h(256)              -> 256 ReLU   (sigma head folded into L7's epilogue, fp32)
+//       V    h7(256) | d(768)    -> 128 ReLU   (feature_linear folded into views_linears[0]; rgb head
+//                                               folded into the epilogue, fp32)
+//   * compositing is incremental (carry per ray), inverse-CDF resampling is a warp per ray; the
+//     samples x joints x embedding tensor only ever exists as 20 KB chunks in shared memory and the
+//     per-sample network outputs never leave the SM.
 //
-// Warp roles (320 threads): warps 0-7 encode + epilogue (warp w owns TMEM lanes
-// 32*(w%4).., column half w/4), warp 8 = weight producer (one elected lane issues bulk
-// copies), warp 9 = MMA issuer (one elected lane) and TMEM allocator.
+// Warp roles (320 threads): warps 0-7 encode + epilogue + compositing (warp w owns TMEM lanes
+// 32*(w%4).., column half w/4), warp 8 = weight producer (one lane issues bulk copies), warp 9 =
+// MMA issuer in the leader CTA / "my half landed" relay in the peer CTA, and TMEM allocator.
 //
 // Reference semantics: core/raycasters.py:361-474, core/encoders.py:8-37,110-122,181-193,
 // core/cutoff_embedder.py:111-174, core/networks/nerf.py:94-205, core/utils/ray_utils.py:157-289.
+#include <cuda_fp16.h>
 #include "pgn_common.cuh"
 #include "pgn_kernels.h"
 #include "pgn_umma.cuh"
@@ -35,112 +41,196 @@ constexpr int kComputeThreads = 256;
 constexpr int kThreads = 320;
 constexpr int kProducerWarp = 8;
 constexpr int kIssuerWarp = 9;
-constexpr int kRPG = 8;                 // rays per group
-constexpr int kTM = 128;                // rows per tile (UMMA M)
+constexpr int kRPG = 8;                 // rays per group (per CTA)
+constexpr int kTM = 128;                // rows per CTA tile (UMMA M = 256 over the pair)
 constexpr int kRunBytes = kTM * 16;     // one 8-wide K run of all 128 rows
-constexpr int kActBytes = 256 / 8 * kRunBytes;          // 65536
-constexpr int kStgBytes = 18 * kRunBytes;               // 36864 (144 K)
-constexpr int kWStages = 8;             // 8 x 8 KB = one full 256x256 layer half per CTA
+constexpr int kActBytes = 256 / 8 * kRunBytes;                 // 65536
+constexpr int kStgBytes = (PGN_X_CHUNK_K / 8) * kRunBytes;     // 20480
+constexpr int kWStages = 5;
 constexpr int kWStageBytes = 8192;
-constexpr int kTmemCols = 256;
+constexpr int kTmemCols = 512;          // two 256-column accumulators
 constexpr int kMaxTileRays = 3;
+constexpr int kLag = 5;                 // slot 1 trails slot 0 by ~half a tile
 
 struct __align__(128) Smem {
-  uint8_t act[kActBytes];
+  uint8_t act[2][kActBytes];
   uint8_t stg[kStgBytes];
   uint8_t wring[kWStages][kWStageBytes];
-  float bias[9 * 256];
-  float w_alpha[256];
-  float w_rgb[3 * 128];
-  float wcache[PGN_J * kTM];            // d-window per (joint,row)
-  float dtab[kMaxTileRays][PGN_J * 28]; // PE of joint-frame view dirs per ray of the tile
-  float zc[kRPG][PGN_S];
-  float zf[kRPG][PGN_T];
-  float raw[kRPG][PGN_T * 4];
-  float wts[kRPG][PGN_S];
-  float scratch[kRPG][128];
-  float part[2][kTM][4];                // per column-half partial (rgb, sigma)
-  float ray_o[kRPG][3], ray_d[kRPG][3], dnorm[kRPG];
+  __half wcache[2][PGN_J * kTM];                 // d-window per (joint,row), per slot
+  __half dtab[2][kMaxTileRays][PGN_J * 32];      // PE of joint-frame view dirs per ray of the tile (27 + 5 zeros)
+  float zf[2][kRPG][PGN_T];                      // merged z of the fine pass, per group parity
+  float carry[2][kRPG][8];                       // incremental compositing state of the fine rays
+  float part[2][kTM][4];                         // per slot: raw rows (rgb_raw, sigma_raw), accumulated by both column halves
+  uint8_t ones[2 * kRunBytes];                   // constant A operand of the bias K-step: k = 0,1 -> 1.0, else 0
+  float cscratch[2][256];                        // coarse compositing: z[64] | weights[64] | sample_pdf scratch[128]
   uint64_t w_full[kWStages], w_empty[kWStages];
-  uint64_t stg_full, stg_empty, act_ready, acc_full;
+  uint64_t stg_full, stg_empty, act_ready[2], acc_full[2];
   uint32_t tmem_base;
 };
 
+// ------------------------------------------------------------------ static schedule
+// Tile sequence of one cluster (identical in every role of both CTAs).
+struct TileIter {
+  int n, i, k;
+  bool stage;
+  __device__ TileIter() {}
+  __device__ TileIter(int n_, bool stage_) : n(n_), i(-1), k(0), stage(stage_) {}
+  __device__ bool next(int& g, int& pass, int& t) {
+    if (stage) { if (k >= n) return false; g = k++; pass = 0; t = 0; return true; }
+    for (;;) {
+      if (i < 0) {
+        if (n == 0) return false;
+        if (k < 4) { g = 0; pass = 0; t = k++; return true; }
+        i = 0; k = 0;
+        continue;
+      }
+      if (i >= n) return false;
+      if (k >= 9) { ++i; k = 0; continue; }
+      const int kk = k++;
+      if ((kk & 1) == 0) { g = i; pass = 1; t = kk >> 1; return true; }
+      if (i + 1 < n) { g = i + 1; pass = 0; t = kk >> 1; return true; }
+    }
+  }
+};
+
+struct Job { int slot, g, pass, t, L; };
+
+// Merged layer-job order of the two slots: slot s owns tiles s, s+2, s+4, ... of the sequence; after a
+// prologue of kLag slot-0 jobs the two job streams alternate strictly.
+struct JobIter {
+  TileIter it[2];
+  int g[2], pass[2], t[2], L[2];
+  bool valid[2];
+  int emitted0, turn;
+  __device__ JobIter(int n, bool stage) {
+    it[0] = TileIter(n, stage); it[1] = TileIter(n, stage);
+    valid[0] = it[0].next(g[0], pass[0], t[0]);
+    int a, b, c;
+    valid[1] = it[1].next(a, b, c) && it[1].next(g[1], pass[1], t[1]);
+    L[0] = L[1] = 0; emitted0 = 0; turn = 1;
+  }
+  __device__ bool next(Job& j) {
+    int s;
+    if (valid[0] && emitted0 < kLag) { s = 0; ++emitted0; }
+    else {
+      s = valid[turn] ? turn : (turn ^ 1);
+      if (!valid[s]) return false;
+      turn = s ^ 1;
+    }
+    j.slot = s; j.g = g[s]; j.pass = pass[s]; j.t = t[s]; j.L = L[s];
+    if (++L[s] == 9) {
+      L[s] = 0;
+      int a, b, c;
+      valid[s] = it[s].next(a, b, c) && it[s].next(g[s], pass[s], t[s]);
+    }
+    return true;
+  }
+};
+
+static_assert(sizeof(Smem) + 1024 <= 232448, "shared memory budget of one CTA exceeded");
+
 struct TileCtx {
-  long long ray0;     // first ray of the group
+  long long ray0;     // first ray of this CTA's group
+  int nr;             // valid rays in the group (0..8)
   int S;              // samples per ray in this pass
+  int pass;
   int row0;           // first row of the tile within the group pass
   int total_rows;     // valid rows in the group pass
+  int buf;            // group parity: zf / carry buffer
+  int tile_ray0;      // first ray (local) touched by the tile
 };
 
 // ------------------------------------------------------------------ encode (compute warps)
-// x chunk c (joints 8c..8c+7): thread (row, half) produces joints 8c+4*half..+3 -> 72 values
-// = 9 runs of 8 at run index half*9+r.
+// x chunk c (joints 4c..4c+3): thread (row, half) produces joints 4c+2*half, +1 -> 36 values + 4 zeros
+// = 5 runs of 8 at run index half*5+r.
+struct RowCtx { bool valid; float px, py, pz; const float* skt; };
+
+// per-row state shared by all chunks of one layer: sample position and the pose's transforms
+__device__ __forceinline__ RowCtx make_row_ctx(const Smem& sm, const PgnRayRefs& rays, const PgnScalars& sc, const TileCtx& tc,
+                                               const float* __restrict__ near_far, int row) {
+  RowCtx rc;
+  const int grow = tc.row0 + row;
+  rc.valid = grow < tc.total_rows;
+  rc.px = rc.py = rc.pz = 0.f;
+  rc.skt = rays.skts;
+  if (rc.valid) {
+    const int rl = grow / tc.S, s = grow - rl * tc.S;
+    const long long ri = tc.ray0 + rl;
+    const float* rb = rays.ray_batch + ri * 11;
+    const float o[3] = {__ldg(rb), __ldg(rb + 1), __ldg(rb + 2)};
+    const float d[3] = {__ldg(rb + 3), __ldg(rb + 4), __ldg(rb + 5)};
+    const float z = (tc.pass == 0) ? pgn_coarse_z(__ldg(near_far + ri * 2), __ldg(near_far + ri * 2 + 1), sc.t_coarse[s])
+                                   : sm.zf[tc.buf][rl][s];
+    pgn_sample_point(o, d, z, rc.px, rc.py, rc.pz);
+    rc.skt = pgn_ray_skts(rays, ri);
+  }
+  return rc;
+}
+
 template <bool kStage>
-__device__ __forceinline__ void encode_x_chunk(Smem& sm, const PgnRayRefs& rays, const PgnScalars& sc, const TileCtx& tc,
-                                               int chunk, int row, int half, bool write_wcache,
-                                               const float* __restrict__ enc_rows, int rows_valid) {
-  uint32_t packed[36];
+__device__ __forceinline__ void encode_x_compute(Smem& sm, const PgnScalars& sc, const RowCtx& rc, int slot, int chunk, int row, int half,
+                                                 bool write_wcache, const float* __restrict__ enc_rows, int rows_valid,
+                                                 uint32_t (&packed)[20]) {
   if (kStage) {
 #pragma unroll
-    for (int i = 0; i < 36; ++i) {
-      const int kp = chunk * 144 + half * 72 + 2 * i;
+    for (int i = 0; i < 20; ++i) {
+      const int kp = chunk * PGN_X_CHUNK_K + half * 40 + 2 * i;
+      const int ca = pgn_xperm_refcol(kp), cb = pgn_xperm_refcol(kp + 1);
       float a = 0.f, b = 0.f;
       if (row < rows_valid) {
-        a = enc_rows[(size_t)row * PGN_ENC + pgn_xperm_refcol(kp)];
-        b = enc_rows[(size_t)row * PGN_ENC + pgn_xperm_refcol(kp + 1)];
+        if (ca >= 0) a = enc_rows[(size_t)row * PGN_ENC + ca];
+        if (cb >= 0) b = enc_rows[(size_t)row * PGN_ENC + cb];
       }
       packed[i] = pack_bf16x2(a, b);
     }
   } else {
-    const int grow = tc.row0 + row;
-    const bool valid = grow < tc.total_rows;
-    const int rl = valid ? grow / tc.S : 0;
-    const int s = valid ? grow - rl * tc.S : 0;
-    const float z = (tc.S == PGN_S) ? sm.zc[rl][s] : sm.zf[rl][s];
-    float px, py, pz;
-    pgn_sample_point(sm.ray_o[rl], sm.ray_d[rl], z, px, py, pz);
-    const float* skt = pgn_ray_skts(rays, tc.ray0 + rl);
 #pragma unroll
-    for (int jj = 0; jj < 4; ++jj) {
-      const int j = chunk * 8 + half * 4 + jj;
-      const float4* m = reinterpret_cast<const float4*>(skt + j * 16);
-      PgnJointGeom g = pgn_joint_geom<true>(__ldg(m), __ldg(m + 1), __ldg(m + 2), px, py, pz, sc.tau_v, sc.cutoff_v[j]);
-      if (!valid) { g.v = 0.f; g.w = 0.f; g.rx = g.ry = g.rz = 0.f; }
-      if (write_wcache) sm.wcache[j * kTM + row] = valid ? pgn_window<true>(g.v, sc.tau_d, sc.cutoff_d[j]) : 0.f;
-      float sn, cs;
-      __sincosf(g.v, &sn, &cs);
+    for (int jj = 0; jj < 2; ++jj) {
+      const int j = chunk * 4 + half * 2 + jj;
       float vals[18];
-      vals[0] = g.v * g.w;
+      if (rc.valid) {
+        const float4* m = reinterpret_cast<const float4*>(rc.skt + j * 16);
+        const PgnJointGeom g = pgn_joint_geom<true>(__ldg(m), __ldg(m + 1), __ldg(m + 2), rc.px, rc.py, rc.pz, sc.tau_v, sc.cutoff_v[j]);
+        if (write_wcache) sm.wcache[slot][j * kTM + row] = __float2half_rn(pgn_window<true>(g.v, sc.tau_d, sc.cutoff_d[j]));
+        float sn, cs;
+        __sincosf(g.v, &sn, &cs);
+        vals[0] = g.v * g.w;
 #pragma unroll
-      for (int f = 0; f < PGN_LV; ++f) {
-        vals[1 + 2 * f] = sn * g.w;
-        vals[2 + 2 * f] = cs * g.w;
-        const float s2 = 2.f * sn * cs;
-        const float c2 = fmaf(cs, cs, -sn * sn);
-        sn = s2; cs = c2;
+        for (int f = 0; f < PGN_LV; ++f) {
+          vals[1 + 2 * f] = sn * g.w;
+          vals[2 + 2 * f] = cs * g.w;
+          const float s2 = 2.f * sn * cs;
+          const float c2 = fmaf(cs, cs, -sn * sn);
+          sn = s2; cs = c2;
+        }
+        vals[15] = g.rx; vals[16] = g.ry; vals[17] = g.rz;
+      } else {
+        if (write_wcache) sm.wcache[slot][j * kTM + row] = __float2half_rn(0.f);
+#pragma unroll
+        for (int i = 0; i < 18; ++i) vals[i] = 0.f;
       }
-      vals[15] = g.rx; vals[16] = g.ry; vals[17] = g.rz;
 #pragma unroll
       for (int i = 0; i < 9; ++i) packed[jj * 9 + i] = pack_bf16x2(vals[2 * i], vals[2 * i + 1]);
     }
+    packed[18] = 0u; packed[19] = 0u;
   }
-  uint8_t* base = sm.stg + (size_t)(half * 9) * kRunBytes + row * 16;
+}
+__device__ __forceinline__ void encode_x_store(Smem& sm, int row, int half, const uint32_t (&packed)[20]) {
+  uint8_t* base = sm.stg + (size_t)(half * 5) * kRunBytes + row * 16;
 #pragma unroll
-  for (int r = 0; r < 9; ++r)
+  for (int r = 0; r < 5; ++r)
     *reinterpret_cast<uint4*>(base + r * kRunBytes) = make_uint4(packed[4 * r], packed[4 * r + 1], packed[4 * r + 2], packed[4 * r + 3]);
 }
 
-// d chunk c (joints 4c..4c+3): thread (row, half) produces joints 4c+2*half, +1 -> 56 values
-// = 7 runs at run index half*7+r.
+// d chunk c (joints 2c, 2c+1): thread (row, half) produces joint 2c+half -> 27 values + 5 zeros
+// = 4 runs at run index half*4+r.
 template <bool kStage>
-__device__ __forceinline__ void encode_d_chunk(Smem& sm, const TileCtx& tc, int chunk, int row, int half, int tile_ray0,
-                                               const float* __restrict__ enc_rows, int rows_valid) {
-  uint32_t packed[28];
+__device__ __forceinline__ void encode_d_compute(Smem& sm, const TileCtx& tc, int slot, int chunk, int row, int half,
+                                                 const float* __restrict__ enc_rows, int rows_valid, uint32_t (&packed)[20]) {
   if (kStage) {
 #pragma unroll
-    for (int i = 0; i < 28; ++i) {
-      const int q = chunk * 112 + half * 56 + 2 * i;
+    for (int i = 0; i < 16; ++i) {
+      const int q = chunk * PGN_D_CHUNK_K + half * 32 + 2 * i;
       const int ca = pgn_dperm_refcol(q), cb = pgn_dperm_refcol(q + 1);
       float a = 0.f, b = 0.f;
       if (row < rows_valid) {
@@ -152,90 +242,106 @@ __device__ __forceinline__ void encode_d_chunk(Smem& sm, const TileCtx& tc, int 
   } else {
     const int grow = tc.row0 + row;
     const bool valid = grow < tc.total_rows;
-    const int rl = valid ? grow / tc.S : tile_ray0;
-    const int tr = min(max(rl - tile_ray0, 0), kMaxTileRays - 1);
+    const int rl = valid ? grow / tc.S : tc.tile_ray0;
+    const int tr = min(max(rl - tc.tile_ray0, 0), kMaxTileRays - 1);
+    const int j = chunk * 2 + half;
+    const float wd = valid ? __half2float(sm.wcache[slot][j * kTM + row]) : 0.f;
+    const uint4* tab = reinterpret_cast<const uint4*>(&sm.dtab[slot][tr][j * 32]);   // 32 halfs = 4 x 16 B
 #pragma unroll
-    for (int jj = 0; jj < 2; ++jj) {
-      const int j = chunk * 4 + half * 2 + jj;
-      const float wd = sm.wcache[j * kTM + row];
-      const float4* tab = reinterpret_cast<const float4*>(&sm.dtab[tr][j * 28]);
+    for (int i = 0; i < 4; ++i) {
+      const uint4 t = tab[i];
+      const uint32_t w4[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
-      for (int i = 0; i < 7; ++i) {
-        const float4 t = tab[i];
-        packed[jj * 14 + 2 * i] = pack_bf16x2(t.x * wd, t.y * wd);
-        packed[jj * 14 + 2 * i + 1] = pack_bf16x2(t.z * wd, t.w * wd);
+      for (int e = 0; e < 4; ++e) {
+        const __half2 h2 = *reinterpret_cast<const __half2*>(&w4[e]);
+        const float2 f2 = __half22float2(h2);
+        packed[i * 4 + e] = pack_bf16x2(f2.x * wd, f2.y * wd);
       }
     }
   }
-  uint8_t* base = sm.stg + (size_t)(half * 7) * kRunBytes + row * 16;
+}
+__device__ __forceinline__ void encode_d_store(Smem& sm, int row, int half, const uint32_t (&packed)[20]) {
+  uint8_t* base = sm.stg + (size_t)(half * 4) * kRunBytes + row * 16;
 #pragma unroll
-  for (int r = 0; r < 7; ++r)
+  for (int r = 0; r < 4; ++r)
     *reinterpret_cast<uint4*>(base + r * kRunBytes) = make_uint4(packed[4 * r], packed[4 * r + 1], packed[4 * r + 2], packed[4 * r + 3]);
 }
 
 // ------------------------------------------------------------------ epilogue (compute warps)
-// MODE 0: hidden layer -> act (bf16, ReLU).  MODE 1: same + sigma partial.  MODE 2: view layer -> rgb partial.
+// The bias is already in the accumulator (bias K-step), so a hidden layer is TMEM -> ReLU+bf16 -> smem.
+// MODE 0: hidden layer -> act.  MODE 1: same + sigma head (fp32).  MODE 2: view layer -> rgb head (fp32).
+// TMEM loads of the next 32-column batch are issued before the current batch is processed.
 template <int MODE>
-__device__ __forceinline__ void epilogue(Smem& sm, uint32_t tmem_base, int layer, int warp, int lane) {
+__device__ __forceinline__ void epilogue(Smem& sm, uint32_t tmem_acc, int slot, const float* __restrict__ w_alpha,
+                                         const float* __restrict__ w_rgb, int warp, int lane) {
   const int q = warp & 3, half = warp >> 2;
   const int row = q * 32 + lane;
   constexpr int kCols = (MODE == 2) ? 64 : 128;        // columns per thread
+  constexpr int kBatches = kCols / 32;
   const int col0 = half * kCols;
-  const float* bias = sm.bias + layer * 256;
+  const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)col0;
   float sig = 0.f, r0 = 0.f, r1 = 0.f, r2 = 0.f;
-#pragma unroll 1
-  for (int b = 0; b < kCols / 32; ++b) {
-    uint32_t v[32];
-    const int c0 = col0 + b * 32;
-    tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-    tmem_ld_wait();
-    float x[32];
+  uint32_t v[2][32];
+  tmem_ld_32x32(taddr, v[0]);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) x[i] = fmaxf(__uint_as_float(v[i]) + bias[c0 + i], 0.f);
+  for (int b = 0; b < kBatches; ++b) {
+    tmem_ld_wait();
+    if (b + 1 < kBatches) tmem_ld_32x32(taddr + (uint32_t)(b + 1) * 32, v[(b + 1) & 1]);
+    const int c0 = col0 + b * 32;
+    const uint32_t* vb = v[b & 1];
     if (MODE == 1) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) sig = fmaf(x[i], sm.w_alpha[c0 + i], sig);
+      for (int i4 = 0; i4 < 8; ++i4) {
+        const float4 wa = __ldg(reinterpret_cast<const float4*>(w_alpha + c0) + i4);
+        sig = fmaf(fmaxf(__uint_as_float(vb[4 * i4]), 0.f), wa.x, sig);
+        sig = fmaf(fmaxf(__uint_as_float(vb[4 * i4 + 1]), 0.f), wa.y, sig);
+        sig = fmaf(fmaxf(__uint_as_float(vb[4 * i4 + 2]), 0.f), wa.z, sig);
+        sig = fmaf(fmaxf(__uint_as_float(vb[4 * i4 + 3]), 0.f), wa.w, sig);
+      }
     }
     if (MODE == 2) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        r0 = fmaf(x[i], sm.w_rgb[c0 + i], r0);
-        r1 = fmaf(x[i], sm.w_rgb[128 + c0 + i], r1);
-        r2 = fmaf(x[i], sm.w_rgb[256 + c0 + i], r2);
+      for (int i4 = 0; i4 < 8; ++i4) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(w_rgb + c0) + i4);
+        const float4 g = __ldg(reinterpret_cast<const float4*>(w_rgb + 128 + c0) + i4);
+        const float4 c = __ldg(reinterpret_cast<const float4*>(w_rgb + 256 + c0) + i4);
+        const float x0 = fmaxf(__uint_as_float(vb[4 * i4]), 0.f), x1 = fmaxf(__uint_as_float(vb[4 * i4 + 1]), 0.f);
+        const float x2 = fmaxf(__uint_as_float(vb[4 * i4 + 2]), 0.f), x3 = fmaxf(__uint_as_float(vb[4 * i4 + 3]), 0.f);
+        r0 = fmaf(x0, a.x, r0); r0 = fmaf(x1, a.y, r0); r0 = fmaf(x2, a.z, r0); r0 = fmaf(x3, a.w, r0);
+        r1 = fmaf(x0, g.x, r1); r1 = fmaf(x1, g.y, r1); r1 = fmaf(x2, g.z, r1); r1 = fmaf(x3, g.w, r1);
+        r2 = fmaf(x0, c.x, r2); r2 = fmaf(x1, c.y, r2); r2 = fmaf(x2, c.z, r2); r2 = fmaf(x3, c.w, r2);
       }
     } else {
-      uint8_t* dst = sm.act + (size_t)(c0 >> 3) * kRunBytes + row * 16;
+      uint8_t* dst = sm.act[slot] + (size_t)(c0 >> 3) * kRunBytes + row * 16;
 #pragma unroll
       for (int g = 0; g < 4; ++g)
         *reinterpret_cast<uint4*>(dst + g * kRunBytes) =
-            make_uint4(pack_bf16x2(x[8 * g], x[8 * g + 1]), pack_bf16x2(x[8 * g + 2], x[8 * g + 3]),
-                       pack_bf16x2(x[8 * g + 4], x[8 * g + 5]), pack_bf16x2(x[8 * g + 6], x[8 * g + 7]));
+            make_uint4(pack_relu_bf16x2(__uint_as_float(vb[8 * g]), __uint_as_float(vb[8 * g + 1])),
+                       pack_relu_bf16x2(__uint_as_float(vb[8 * g + 2]), __uint_as_float(vb[8 * g + 3])),
+                       pack_relu_bf16x2(__uint_as_float(vb[8 * g + 4]), __uint_as_float(vb[8 * g + 5])),
+                       pack_relu_bf16x2(__uint_as_float(vb[8 * g + 6]), __uint_as_float(vb[8 * g + 7])));
     }
   }
-  if (MODE == 1) sm.part[half][row][3] = sig;
-  if (MODE == 2) { sm.part[half][row][0] = r0; sm.part[half][row][1] = r1; sm.part[half][row][2] = r2; }
+  if (MODE == 1) atomicAdd(&sm.part[slot][row][3], sig);
+  if (MODE == 2) { atomicAdd(&sm.part[slot][row][0], r0); atomicAdd(&sm.part[slot][row][1], r1); atomicAdd(&sm.part[slot][row][2], r2); }
 }
 
 // "my part of the A operand is written / my TMEM reads are done" -> the LEADER CTA's barrier
-__device__ __forceinline__ void compute_arrive(uint64_t* bar) {
+// (one elected arrive per warp: every lane fences its own writes, __syncwarp orders them before lane 0's release)
+__device__ __forceinline__ void compute_arrive(uint64_t* bar, int lane) {
   tc_fence_before_sync();
   fence_proxy_async_smem();
-  mbar_arrive_cluster(bar, 0);
+  __syncwarp();
+  if (lane == 0) mbar_arrive_cluster(bar, 0);
 }
 __device__ __forceinline__ void compute_bar_sync() { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }
 
 // optional phase timers (cycles, one elected thread per role, accumulated per CTA):
 //  0 issuer wait w_full | 1 issuer wait stg_full | 2 issuer wait act_ready | 3 issuer total
 //  4 producer wait w_empty | 5 producer total
-//  6 encode_x | 7 encode_d | 8 epilogue | 9 wait acc_full | 10 wait stg_empty | 12 compute total
-//  13 issuer MMA issue | 14 issuer commits
+//  6 encode_x | 7 encode_d | 8 epilogue | 9 wait acc_full | 10 wait stg_empty | 11 composite | 12 compute total
 #define PROF_T0() const long long _pt0 = prof ? clock64() : 0
 #define PROF_ADD(slot) do { if (prof) pacc[slot] += (unsigned long long)(clock64() - _pt0); } while (0)
-
-// Static per-cluster-iteration schedule: the two CTAs of a pair always run the same tile sequence
-// (4 coarse + 5 fine pair-tiles; rows beyond a CTA's rays are masked), so the leader's issuer, both
-// weight producers, the peer's relay and both sets of compute warps stay in lock-step by construction.
-__device__ __forceinline__ int tiles_in_pass(int pass) { return pass == 0 ? (kRPG * PGN_S) / kTM : (kRPG * PGN_T) / kTM; }
 
 // ------------------------------------------------------------------ the kernel
 template <bool kStage>
@@ -252,23 +358,28 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
   const PgnScalars& sc = *scp;
   const long long n_clusters = gridDim.x >> 1, cluster_id = blockIdx.x >> 1;
 
-  // work units: a "pair-group" = two ray groups (one per CTA); stage mode: two 128-row tiles
+  // work units: ray groups of 8 (stage mode: 128-row tiles); a pair-unit = one unit per CTA of the pair
   const long long n_units = kStage ? (enc_rows_total + kTM - 1) / kTM : (rays.n_rays + kRPG - 1) / kRPG;
   const long long n_pairs = (n_units + 1) / 2;
-  const int n_pass = kStage ? 1 : 2;
+  const int n_local = (int)((n_pairs > cluster_id) ? (n_pairs - cluster_id + n_clusters - 1) / n_clusters : 0);
 
   if (tid == 0) {
     for (int s = 0; s < kWStages; ++s) { mbar_init(&sm.w_full[s], rank == 0 ? 2 : 1); mbar_init(&sm.w_empty[s], 1); }
-    mbar_init(&sm.stg_full, 2 * kComputeThreads);
+    mbar_init(&sm.stg_full, 2 * (kComputeThreads / 32));
     mbar_init(&sm.stg_empty, 1);
-    mbar_init(&sm.act_ready, 2 * kComputeThreads);
-    mbar_init(&sm.acc_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&sm.act_ready[s], 2 * (kComputeThreads / 32)); mbar_init(&sm.acc_full[s], 1); }
     fence_mbar_init();
   }
   if (warp == kIssuerWarp) {
     tmem_alloc_2cta(&sm.tmem_base, kTmemCols);
     tmem_relinquish_2cta();
   }
+  if (tid < kTM) {     // constant A operand of the bias K-step; zeroed head accumulators
+    *reinterpret_cast<uint4*>(sm.ones + tid * 16) = make_uint4(0x3F803F80u, 0u, 0u, 0u);      // bf16 (1.0, 1.0, 0...)
+    *reinterpret_cast<uint4*>(sm.ones + kRunBytes + tid * 16) = make_uint4(0u, 0u, 0u, 0u);
+    for (int s = 0; s < 2; ++s) *reinterpret_cast<float4*>(sm.part[s][tid]) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  fence_proxy_async_smem();
   tc_fence_before_sync();
   __syncthreads();
   cluster_sync_all();
@@ -281,26 +392,23 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
     // ===================== weight producer (each CTA streams ITS N-half of every fill) =====================
     if (lane == 0) {
       uint32_t wfill = 0;
-      for (long long u = cluster_id; u < n_pairs; u += n_clusters) {
-        for (int pass = 0; pass < n_pass; ++pass) {
-          const int ntiles = kStage ? 1 : tiles_in_pass(pass);
-          const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(pass == 0 ? net_c.wstream : net_f.wstream);
-          for (int t = 0; t < ntiles; ++t) {
-            size_t off = 0;
-            for (int L = 0; L < 9; ++L) {
-              const int nh = pgn_layer_n(L) / 2, ks_total = pgn_layer_ksteps(L), kpf = pgn_ks_per_fill(L);
-              for (int ks = 0; ks < ks_total; ks += kpf) {
-                const int nks = min(kpf, ks_total - ks);
-                const uint32_t bytes = (uint32_t)nks * nh * 32u;          // this CTA's half of the fill
-                const int stage = wfill % kWStages;
-                { PROF_T0(); const bool okw = mbar_wait(&sm.w_empty[stage], ((wfill / kWStages) & 1) ^ 1, status, 101); PROF_ADD(4); if (!okw) goto done; }
-                mbar_arrive_expect_tx(&sm.w_full[stage], bytes);
-                bulk_g2s(sm.wring[stage], wsrc + off + (size_t)rank * bytes, bytes, &sm.w_full[stage]);
-                off += 2u * bytes;
-                ++wfill;
-              }
-            }
-          }
+      JobIter ji(n_local, kStage);
+      Job j;
+      // byte offset of each layer inside the packed stream
+      while (ji.next(j)) {
+        const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(j.pass == 0 ? net_c.wstream : net_f.wstream);
+        size_t off = 0;
+        for (int L = 0; L < j.L; ++L) off += (size_t)pgn_layer_n(L) * pgn_layer_ksteps(L) * 32;
+        const int nh = pgn_layer_n(j.L) / 2, ks_total = pgn_layer_ksteps(j.L), kpf = pgn_ks_per_fill(j.L);
+        for (int ks = 0; ks < ks_total; ks += kpf) {
+          const int nks = min(kpf, ks_total - ks);
+          const uint32_t bytes = (uint32_t)nks * nh * 32u;          // this CTA's half of the fill
+          const int stage = wfill % kWStages;
+          { PROF_T0(); const bool okw = mbar_wait(&sm.w_empty[stage], ((wfill / kWStages) & 1) ^ 1, status, 101); PROF_ADD(4); if (!okw) goto done; }
+          mbar_arrive_expect_tx(&sm.w_full[stage], bytes);
+          bulk_g2s(sm.wring[stage], wsrc + off + (size_t)rank * bytes, bytes, &sm.w_full[stage]);
+          off += 2u * bytes;
+          ++wfill;
         }
       }
     }
@@ -308,244 +416,266 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
     if (lane == 0 && rank == 1) {
       // ===================== peer relay: "my half of fill f has landed" -> leader's w_full =====================
       uint32_t wfill = 0;
-      for (long long u = cluster_id; u < n_pairs; u += n_clusters) {
-        for (int pass = 0; pass < n_pass; ++pass) {
-          const int ntiles = kStage ? 1 : tiles_in_pass(pass);
-          for (int t = 0; t < ntiles; ++t) {
-            for (int L = 0; L < 9; ++L) {
-              const int ks_total = pgn_layer_ksteps(L), kpf = pgn_ks_per_fill(L);
-              for (int ks = 0; ks < ks_total; ks += kpf) {
-                const int stage = wfill % kWStages;
-                if (!mbar_wait(&sm.w_full[stage], (wfill / kWStages) & 1, status, 401)) goto done;
-                mbar_arrive_cluster(&sm.w_full[stage], 0);
-                ++wfill;
-              }
-            }
-          }
+      JobIter ji(n_local, kStage);
+      Job j;
+      while (ji.next(j)) {
+        const int ks_total = pgn_layer_ksteps(j.L), kpf = pgn_ks_per_fill(j.L);
+        for (int ks = 0; ks < ks_total; ks += kpf) {
+          const int stage = wfill % kWStages;
+          if (!mbar_wait(&sm.w_full[stage], (wfill / kWStages) & 1, status, 401)) goto done;
+          mbar_arrive_cluster(&sm.w_full[stage], 0);
+          ++wfill;
         }
       }
     } else if (lane == 0) {
       // ===================== MMA issuer (leader CTA): UMMA M=256 over both CTAs =====================
-      uint32_t wfill = 0, stg_n = 0, act_n = 0;
-      const uint32_t act_addr = smem_u32(sm.act), stg_addr = smem_u32(sm.stg);
-      for (long long u = cluster_id; u < n_pairs; u += n_clusters) {
-        for (int pass = 0; pass < n_pass; ++pass) {
-          const int ntiles = kStage ? 1 : tiles_in_pass(pass);
-          for (int t = 0; t < ntiles; ++t) {
-            for (int L = 0; L < 9; ++L) {
-              const int n = pgn_layer_n(L), nh = n / 2, ks_total = pgn_layer_ksteps(L), kpf = pgn_ks_per_fill(L);
-              const int ks_act = pgn_layer_kact(L) / 16;
-              const int chunk_ks = (L == 8) ? 7 : 9;
-              const uint32_t idesc = umma_idesc_bf16(2 * kTM, n);
-              if (ks_act > 0) {
-                { PROF_T0(); const bool okw = mbar_wait_cluster(&sm.act_ready, act_n & 1, status, 201); PROF_ADD(2); if (!okw) goto done; }
-                ++act_n;
-                tc_fence_after_sync();
-              }
-              int stage = 0;
-              for (int ks = 0; ks < ks_total; ++ks) {
-                const int kf = ks % kpf;
-                if (kf == 0) {
-                  stage = wfill % kWStages;
-                  { PROF_T0(); const bool okw = mbar_wait_cluster(&sm.w_full[stage], (wfill / kWStages) & 1, status, 202); PROF_ADD(0); if (!okw) goto done; }
-                  tc_fence_after_sync();
-                }
-                uint32_t a_addr;
-                bool chunk_end = false;
-                if (ks < ks_act) {
-                  a_addr = act_addr + (uint32_t)ks * 2 * kRunBytes;
-                } else {
-                  const int e = ks - ks_act, ce = e % chunk_ks;
-                  if (ce == 0) {
-                    { PROF_T0(); const bool okw = mbar_wait_cluster(&sm.stg_full, stg_n & 1, status, 203); PROF_ADD(1); if (!okw) goto done; }
-                    ++stg_n;
-                    tc_fence_after_sync();
-                  }
-                  a_addr = stg_addr + (uint32_t)ce * 2 * kRunBytes;
-                  chunk_end = (ce == chunk_ks - 1);
-                }
-                const uint64_t adesc = umma_smem_desc(a_addr, kRunBytes, 128);
-                const uint64_t bdesc = umma_smem_desc(smem_u32(sm.wring[stage]) + (uint32_t)kf * nh * 32u, (uint32_t)nh * 16u, 128);
-                { PROF_T0(); umma_bf16_2cta(tmem_base, adesc, bdesc, idesc, ks > 0 ? 1u : 0u); PROF_ADD(13); }
-                { PROF_T0();
-                  if (chunk_end) umma_commit_2cta(&sm.stg_empty);
-                  if (kf == kpf - 1 || ks == ks_total - 1) { umma_commit_2cta(&sm.w_empty[stage]); ++wfill; }
-                  PROF_ADD(14); }
-              }
-              { PROF_T0(); umma_commit_2cta(&sm.acc_full); PROF_ADD(14); }
-            }
-          }
+      uint32_t wfill = 0, stg_n = 0;
+      uint32_t posts[2] = {0, 0};            // POSTs of each slot already waited for
+      uint32_t jobs[2] = {0, 0};             // jobs of each slot already issued
+      const uint32_t stg_addr = smem_u32(sm.stg), ones_addr = smem_u32(sm.ones);
+      JobIter ji(n_local, kStage);
+      Job j;
+      while (ji.next(j)) {
+        const int s = j.slot, L = j.L;
+        const int n = pgn_layer_n(L), nh = n / 2, ks_total = pgn_layer_ksteps(L), kpf = pgn_ks_per_fill(L);
+        const int ks_act = pgn_layer_kact(L) / 16;
+        const int chunk_ks = pgn_layer_chunk_ks(L);
+        const uint32_t idesc = umma_idesc_bf16(2 * kTM, n);
+        const uint32_t act_addr = smem_u32(sm.act[s]);
+        const uint32_t tmem_acc = tmem_base + (uint32_t)s * 256u;
+        // the previous job of this slot must have been drained (its epilogue wrote act[s] / freed the accumulator)
+        if (jobs[s] > 0) {
+          { PROF_T0(); const bool okw = mbar_wait_cluster(&sm.act_ready[s], posts[s] & 1, status, 201); PROF_ADD(2); if (!okw) goto done; }
+          ++posts[s];
+          tc_fence_after_sync();
         }
+        ++jobs[s];
+        int stage = 0;
+        for (int ks = 0; ks < ks_total; ++ks) {
+          const int kf = ks % kpf;
+          if (kf == 0) {
+            stage = wfill % kWStages;
+            { PROF_T0(); const bool okw = mbar_wait_cluster(&sm.w_full[stage], (wfill / kWStages) & 1, status, 202); PROF_ADD(0); if (!okw) goto done; }
+            tc_fence_after_sync();
+          }
+          uint32_t a_addr;
+          bool chunk_end = false;
+          if (ks == ks_total - 1) {
+            a_addr = ones_addr;                       // bias K-step
+          } else if (ks < ks_act) {
+            a_addr = act_addr + (uint32_t)ks * 2 * kRunBytes;
+          } else {
+            const int e = ks - ks_act, ce = e % chunk_ks;
+            if (ce == 0) {
+              { PROF_T0(); const bool okw = mbar_wait_cluster(&sm.stg_full, stg_n & 1, status, 203); PROF_ADD(1); if (!okw) goto done; }
+              ++stg_n;
+              tc_fence_after_sync();
+            }
+            a_addr = stg_addr + (uint32_t)ce * 2 * kRunBytes;
+            chunk_end = (ce == chunk_ks - 1);
+          }
+          const uint64_t adesc = umma_smem_desc(a_addr, kRunBytes, 128);
+          const uint64_t bdesc = umma_smem_desc(smem_u32(sm.wring[stage]) + (uint32_t)kf * nh * 32u, (uint32_t)nh * 16u, 128);
+          umma_bf16_2cta(tmem_acc, adesc, bdesc, idesc, ks > 0 ? 1u : 0u);
+          if (chunk_end) umma_commit_2cta(&sm.stg_empty);
+          if (kf == kpf - 1 || ks == ks_total - 1) { umma_commit_2cta(&sm.w_empty[stage]); ++wfill; }
+        }
+        umma_commit_2cta(&sm.acc_full[s]);
       }
     }
   } else {
-    // ===================== compute warps (encode, epilogue, composite) =====================
-    uint32_t stg_n = 0, acc_n = 0;
+    // ===================== compute warps (encode, epilogue, compositing) =====================
+    uint32_t stg_n = 0;
+    uint32_t accs[2] = {0, 0};
     const int row = tid & (kTM - 1), half = tid >> 7;
-    for (long long u = cluster_id; u < n_pairs; u += n_clusters) {
-      const long long unit = 2 * u + rank;                 // this CTA's ray group (or stage tile)
-      const long long ray0 = unit * kRPG;
-      const int nr = kStage ? 0 : (int)max(0ll, min((long long)kRPG, rays.n_rays - ray0));
-      if (!kStage) {
-        compute_bar_sync();
-        if (tid < kRPG * 3) {
-          const int rl = tid / 3, a = tid % 3;
-          if (rl < nr) {
-            sm.ray_o[rl][a] = rays.ray_batch[(ray0 + rl) * 11 + a];
-            sm.ray_d[rl][a] = rays.ray_batch[(ray0 + rl) * 11 + 3 + a];
-          } else { sm.ray_o[rl][a] = 0.f; sm.ray_d[rl][a] = (a == 2) ? 1.f : 0.f; }
-        }
-        compute_bar_sync();
-        if (tid < kRPG) {
-          const float* d = sm.ray_d[tid];
-          sm.dnorm[tid] = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
-        }
-        for (int i = tid; i < kRPG * PGN_S; i += kComputeThreads) {
-          const int rl = i / PGN_S, s = i % PGN_S;
-          sm.zc[rl][s] = (rl < nr) ? pgn_coarse_z(near_far[(ray0 + rl) * 2], near_far[(ray0 + rl) * 2 + 1], sc.t_coarse[s]) : 0.f;
-        }
-      }
-      for (int pass = 0; pass < n_pass; ++pass) {
-        const int S = pass == 0 ? PGN_S : PGN_T;
-        const PgnBf16Net& net = pass == 0 ? net_c : net_f;
-        const int total_rows = kStage ? kTM : nr * S;
-        const int ntiles = kStage ? 1 : tiles_in_pass(pass);
-        // epilogue vectors of this net
-        compute_bar_sync();
-        for (int i = tid; i < 9 * 256; i += kComputeThreads) sm.bias[i] = net.bias[i];
-        for (int i = tid; i < 256; i += kComputeThreads) sm.w_alpha[i] = net.w_alpha[i];
-        for (int i = tid; i < 384; i += kComputeThreads) sm.w_rgb[i] = net.w_rgb[i];
-        compute_bar_sync();
 
-        for (int t = 0; t < ntiles; ++t) {
-          TileCtx tc{ray0, S, t * kTM, total_rows};
-          const float* enc_rows = kStage ? enc_global + (size_t)unit * kTM * PGN_ENC : nullptr;
-          const int rows_valid = kStage ? (int)max(0ll, min((long long)kTM, enc_rows_total - unit * kTM)) : kTM;
-          const int tile_ray0 = kStage ? 0 : min(tc.row0 / S, kRPG - 1);
-          if (!kStage) {
-            // PE table of the joint-frame view directions for the <=3 rays of this tile
-            const int tile_ray1 = min((tc.row0 + kTM - 1) / S, nr - 1);
-            for (int i = tid; i < kMaxTileRays * PGN_J; i += kComputeThreads) {
-              const int tr = i / PGN_J, j = i % PGN_J;
-              const int rl = tile_ray0 + tr;
-              if (rl <= tile_ray1) {
-                const float4* m = reinterpret_cast<const float4*>(pgn_ray_skts(rays, ray0 + rl) + j * 16);
-                float dj[3];
-                pgn_joint_dir(__ldg(m), __ldg(m + 1), __ldg(m + 2), sm.ray_d[rl], dj[0], dj[1], dj[2]);
-                float* tab = &sm.dtab[tr][j * 28];
-                for (int k = 0; k < 1 + 2 * PGN_LD; ++k)
-                  for (int a = 0; a < 3; ++a) tab[k * 3 + a] = pgn_pe_term(dj[a], k);
-                tab[27] = 0.f;
-              }
-            }
-            compute_bar_sync();
-          }
-          // ---- L0: x chunks
-          for (int c = 0; c < 3; ++c) {
-            { PROF_T0(); const bool okw = mbar_wait(&sm.stg_empty, (stg_n & 1) ^ 1, status, 301); PROF_ADD(10); if (!okw) goto done; }
-            { PROF_T0(); encode_x_chunk<kStage>(sm, rays, sc, tc, c, row, half, false, enc_rows, rows_valid);
-              compute_arrive(&sm.stg_full); PROF_ADD(6); }
-            ++stg_n;
-          }
-          for (int L = 0; L < 8; ++L) {
-            if (L == 5) {
-              for (int c = 0; c < 3; ++c) {
-                { PROF_T0(); const bool okw = mbar_wait(&sm.stg_empty, (stg_n & 1) ^ 1, status, 302); PROF_ADD(10); if (!okw) goto done; }
-                { PROF_T0(); encode_x_chunk<kStage>(sm, rays, sc, tc, c, row, half, true, enc_rows, rows_valid);
-                  compute_arrive(&sm.stg_full); PROF_ADD(6); }
-                ++stg_n;
-              }
-            }
-            { PROF_T0(); const bool okw = mbar_wait(&sm.acc_full, acc_n & 1, status, 303); PROF_ADD(9); if (!okw) goto done; }
-            ++acc_n;
-            tc_fence_after_sync();
-            { PROF_T0();
-              if (L == 7) epilogue<1>(sm, tmem_base, L, warp, lane);
-              else epilogue<0>(sm, tmem_base, L, warp, lane);
-              compute_arrive(&sm.act_ready); PROF_ADD(8); }
-          }
-          // ---- V: d chunks
-          compute_bar_sync();               // wcache (written during L5's encode) visible to all
-          for (int c = 0; c < 6; ++c) {
-            { PROF_T0(); const bool okw = mbar_wait(&sm.stg_empty, (stg_n & 1) ^ 1, status, 304); PROF_ADD(10); if (!okw) goto done; }
-            { PROF_T0(); encode_d_chunk<kStage>(sm, tc, c, row, half, tile_ray0, enc_rows, rows_valid);
-              compute_arrive(&sm.stg_full); PROF_ADD(7); }
-            ++stg_n;
-          }
-          { PROF_T0(); const bool okw = mbar_wait(&sm.acc_full, acc_n & 1, status, 305); PROF_ADD(9); if (!okw) goto done; }
-          ++acc_n;
-          tc_fence_after_sync();
-          { PROF_T0(); epilogue<2>(sm, tmem_base, 8, warp, lane); PROF_ADD(8); }
-          tc_fence_before_sync();
-          compute_bar_sync();
-          if (tid < kTM) {
-            const float r0 = sm.part[0][tid][0] + sm.part[1][tid][0] + net.b_rgb[0];
-            const float r1 = sm.part[0][tid][1] + sm.part[1][tid][1] + net.b_rgb[1];
-            const float r2 = sm.part[0][tid][2] + sm.part[1][tid][2] + net.b_rgb[2];
-            const float sg = sm.part[0][tid][3] + sm.part[1][tid][3] + net.b_alpha[0];
-            if (kStage) {
-              if (tid < rows_valid) {
-                float* o = raw_global + ((size_t)unit * kTM + tid) * 4;
-                o[0] = r0; o[1] = r1; o[2] = r2; o[3] = sg;
-              }
-            } else {
-              const int grow = tc.row0 + tid;
-              if (grow < total_rows) {
-                const int rl = grow / S, s = grow - rl * S;
-                float* o = &sm.raw[rl][s * 4];
-                o[0] = r0; o[1] = r1; o[2] = r2; o[3] = sg;
-              }
-            }
-          }
-          compute_bar_sync();
-        }
-        if (kStage) continue;
-        // ---- compositing (+ resampling after the coarse pass): one warp per ray
-        {
-          const int rl = warp;
-          if (rl < nr) {
-            const long long ri = ray0 + rl;
-            float rgb3[3], disp, acc;
-            if (pass == 0) {
-              float* a0 = out.alpha0 ? out.alpha0 + ri * PGN_S : nullptr;
-              pgn_composite_warp<PGN_S>(sm.raw[rl], sm.zc[rl], sm.dnorm[rl], sc.density_scale, sc.rgb_eps, lane,
-                                        rgb3, &disp, &acc, sm.wts[rl], a0);
-              if (lane == 0) {
-                if (out.rgb0) { out.rgb0[ri * 3] = rgb3[0]; out.rgb0[ri * 3 + 1] = rgb3[1]; out.rgb0[ri * 3 + 2] = rgb3[2]; }
-                if (out.disp0) out.disp0[ri] = disp;
-                if (out.acc0) out.acc0[ri] = acc;
-              }
-              __syncwarp();
-              if (out.weights0) { out.weights0[ri * PGN_S + lane] = sm.wts[rl][lane]; out.weights0[ri * PGN_S + lane + 32] = sm.wts[rl][lane + 32]; }
-              if (out.raw0) for (int i = lane; i < PGN_S * 4; i += 32) out.raw0[ri * PGN_S * 4 + i] = sm.raw[rl][i];
-              pgn_sample_pdf_warp(sm.zc[rl], sm.wts[rl], sc.u_det, lane, sm.scratch[rl],
-                                  out.z_samples ? out.z_samples + ri * PGN_I : nullptr, sm.zf[rl],
-                                  out.pdf_inds ? out.pdf_inds + ri * PGN_I : nullptr, nullptr);
-              if (out.z_fine) for (int i = lane; i < PGN_T; i += 32) out.z_fine[ri * PGN_T + i] = sm.zf[rl][i];
-            } else {
-              float* a1 = out.alpha ? out.alpha + ri * PGN_T : nullptr;
-              pgn_composite_warp<PGN_T>(sm.raw[rl], sm.zf[rl], sm.dnorm[rl], sc.density_scale, sc.rgb_eps, lane,
-                                        rgb3, &disp, &acc, nullptr, a1);
-              if (lane == 0) {
-                if (out.rgb_map) { out.rgb_map[ri * 3] = rgb3[0]; out.rgb_map[ri * 3 + 1] = rgb3[1]; out.rgb_map[ri * 3 + 2] = rgb3[2]; }
-                if (out.disp_map) out.disp_map[ri] = disp;
-                if (out.acc_map) out.acc_map[ri] = acc;
-              }
-              if (out.raw) for (int i = lane; i < PGN_T * 4; i += 32) out.raw[ri * PGN_T * 4 + i] = sm.raw[rl][i];
-            }
+    auto make_ctx = [&](const Job& j, TileCtx& tc, long long& unit) {
+      const long long u = cluster_id + (long long)j.g * n_clusters;
+      unit = 2 * u + rank;
+      tc.ray0 = unit * kRPG;
+      tc.nr = kStage ? 0 : (int)max(0ll, min((long long)kRPG, rays.n_rays - tc.ray0));
+      tc.pass = j.pass;
+      tc.S = j.pass == 0 ? PGN_S : PGN_T;
+      tc.row0 = j.t * kTM;
+      tc.total_rows = kStage ? kTM : tc.nr * tc.S;
+      tc.buf = j.g & 1;
+      tc.tile_ray0 = min(tc.row0 / tc.S, kRPG - 1);
+    };
+
+    // POST(job): drain the accumulator (epilogue); after the view layer also composite the finished rows
+    auto post = [&](const Job& j) -> bool {
+      const int s = j.slot;
+      const PgnBf16Net& net = j.pass == 0 ? net_c : net_f;
+      { PROF_T0(); const bool okw = mbar_wait(&sm.acc_full[s], accs[s] & 1, status, 303); PROF_ADD(9); if (!okw) return false; }
+      ++accs[s];
+      tc_fence_after_sync();
+      const uint32_t tmem_acc = tmem_base + (uint32_t)s * 256u;
+      { PROF_T0();
+        if (j.L == 8) epilogue<2>(sm, tmem_acc, s, net.w_alpha, net.w_rgb, warp, lane);
+        else if (j.L == 7) epilogue<1>(sm, tmem_acc, s, net.w_alpha, net.w_rgb, warp, lane);
+        else epilogue<0>(sm, tmem_acc, s, net.w_alpha, net.w_rgb, warp, lane);
+        compute_arrive(&sm.act_ready[s], lane); PROF_ADD(8); }
+      if (j.L != 8) return true;
+
+      PROF_T0();
+      TileCtx tc; long long unit;
+      make_ctx(j, tc, unit);
+      compute_bar_sync();
+      if (tid < kTM) {       // head biases -> raw row (rgb_raw, sigma_raw) in part[s]
+        float* p0 = sm.part[s][tid];
+        p0[0] += net.b_rgb[0];
+        p0[1] += net.b_rgb[1];
+        p0[2] += net.b_rgb[2];
+        p0[3] += net.b_alpha[0];
+        if (kStage) {
+          const int rows_valid = (int)max(0ll, min((long long)kTM, enc_rows_total - unit * kTM));
+          if (tid < rows_valid) {
+            float* o = raw_global + ((size_t)unit * kTM + tid) * 4;
+            o[0] = p0[0]; o[1] = p0[1]; o[2] = p0[2]; o[3] = p0[3];
           }
         }
-        compute_bar_sync();
       }
+      compute_bar_sync();
+      if (!kStage) {
+        if (j.pass == 0) {
+          // coarse tile = 2 whole rays: composite, resample, merge -> zf ring; reset the fine carry
+          const int rl = 2 * j.t + warp;
+          if (warp < 2 && rl < tc.nr) {
+            const long long ri = tc.ray0 + rl;
+            float* zc = sm.cscratch[warp];
+            float* wts = zc + 64;
+            float* scr = zc + 128;
+            const float nn = __ldg(near_far + ri * 2), ff = __ldg(near_far + ri * 2 + 1);
+            zc[lane] = pgn_coarse_z(nn, ff, sc.t_coarse[lane]);
+            zc[lane + 32] = pgn_coarse_z(nn, ff, sc.t_coarse[lane + 32]);
+            const float d0 = __ldg(rays.ray_batch + ri * 11 + 3), d1 = __ldg(rays.ray_batch + ri * 11 + 4), d2 = __ldg(rays.ray_batch + ri * 11 + 5);
+            const float dn = sqrtf(d0 * d0 + d1 * d1 + d2 * d2);
+            float* cr = sm.carry[tc.buf][rl];
+            if (lane < 8) cr[lane] = (lane == 0) ? 1.f : 0.f;
+            __syncwarp();
+            const float* rawrows = &sm.part[s][warp * PGN_S][0];
+            pgn_composite_segment_warp<PGN_S>(rawrows, zc, 0, PGN_S, dn, sc.density_scale, sc.rgb_eps, lane, cr, wts,
+                                              out.alpha0 ? out.alpha0 + ri * PGN_S : nullptr);
+            if (lane == 0) {
+              float rgb3[3], disp, acc;
+              pgn_composite_finalize(cr, rgb3, &disp, &acc);
+              if (out.rgb0) { out.rgb0[ri * 3] = rgb3[0]; out.rgb0[ri * 3 + 1] = rgb3[1]; out.rgb0[ri * 3 + 2] = rgb3[2]; }
+              if (out.disp0) out.disp0[ri] = disp;
+              if (out.acc0) out.acc0[ri] = acc;
+            }
+            __syncwarp();
+            if (lane < 8) cr[lane] = (lane == 0) ? 1.f : 0.f;      // carry now belongs to the fine pass of this ray
+            if (out.weights0) { out.weights0[ri * PGN_S + lane] = wts[lane]; out.weights0[ri * PGN_S + lane + 32] = wts[lane + 32]; }
+            if (out.raw0) for (int i = lane; i < PGN_S * 4; i += 32) out.raw0[ri * PGN_S * 4 + i] = rawrows[i];
+            pgn_sample_pdf_warp(zc, wts, sc.u_det, lane, scr, out.z_samples ? out.z_samples + ri * PGN_I : nullptr,
+                                sm.zf[tc.buf][rl], out.pdf_inds ? out.pdf_inds + ri * PGN_I : nullptr, nullptr);
+            if (out.z_fine) for (int i = lane; i < PGN_T; i += 32) out.z_fine[ri * PGN_T + i] = sm.zf[tc.buf][rl][i];
+          }
+        } else {
+          // fine tile: rows [row0, row0+128) cut up to 3 rays; continue each ray's compositing
+          const int rl = tc.tile_ray0 + warp;
+          if (warp < kMaxTileRays && rl < tc.nr && rl * PGN_T < tc.row0 + kTM) {
+            const long long ri = tc.ray0 + rl;
+            const int s0 = max(0, tc.row0 - rl * PGN_T), s1 = min(PGN_T, tc.row0 + kTM - rl * PGN_T);
+            const float d0 = __ldg(rays.ray_batch + ri * 11 + 3), d1 = __ldg(rays.ray_batch + ri * 11 + 4), d2 = __ldg(rays.ray_batch + ri * 11 + 5);
+            const float dn = sqrtf(d0 * d0 + d1 * d1 + d2 * d2);
+            float* cr = sm.carry[tc.buf][rl];
+            const float* rawrows = &sm.part[s][rl * PGN_T + s0 - tc.row0][0];
+            pgn_composite_segment_warp<PGN_T>(rawrows, sm.zf[tc.buf][rl], s0, s1, dn, sc.density_scale, sc.rgb_eps, lane, cr,
+                                              nullptr, out.alpha ? out.alpha + ri * PGN_T : nullptr);
+            if (out.raw) for (int i = lane; i < (s1 - s0) * 4; i += 32) out.raw[(ri * PGN_T + s0) * 4 + i] = rawrows[i];
+            if (s1 == PGN_T && lane == 0) {
+              float rgb3[3], disp, acc;
+              pgn_composite_finalize(cr, rgb3, &disp, &acc);
+              if (out.rgb_map) { out.rgb_map[ri * 3] = rgb3[0]; out.rgb_map[ri * 3 + 1] = rgb3[1]; out.rgb_map[ri * 3 + 2] = rgb3[2]; }
+              if (out.disp_map) out.disp_map[ri] = disp;
+              if (out.acc_map) out.acc_map[ri] = acc;
+            }
+          }
+        }
+      }
+      compute_bar_sync();
+      if (tid < kTM) *reinterpret_cast<float4*>(sm.part[s][tid]) = make_float4(0.f, 0.f, 0.f, 0.f);   // next tile of this slot
+      PROF_ADD(11);
+      return true;
+    };
+
+    // PRE(job): everything the tensor core needs from the CUDA cores before/while it runs the layer
+    auto pre = [&](const Job& j, const Job* drain_after_first) -> bool {
+      const int nchunks = pgn_layer_chunks(j.L);
+      if (nchunks == 0) return drain_after_first ? post(*drain_after_first) : true;
+      TileCtx tc; long long unit;
+      make_ctx(j, tc, unit);
+      const float* enc_rows = kStage ? enc_global + (size_t)unit * kTM * PGN_ENC : nullptr;
+      const int rows_valid = kStage ? (int)max(0ll, min((long long)kTM, enc_rows_total - unit * kTM)) : kTM;
+      if (!kStage && j.L == 0) {
+        // PE table of the joint-frame view directions for the <=3 rays of this tile (used by the V layer)
+        const int tile_ray1 = min((tc.row0 + kTM - 1) / tc.S, tc.nr - 1);
+        for (int i = tid; i < kMaxTileRays * PGN_J; i += kComputeThreads) {
+          const int tr = i / PGN_J, jn = i % PGN_J;
+          const int rl = tc.tile_ray0 + tr;
+          __half* tab = &sm.dtab[j.slot][tr][jn * 32];
+          if (rl <= tile_ray1) {
+            const long long ri = tc.ray0 + rl;
+            const float4* m = reinterpret_cast<const float4*>(pgn_ray_skts(rays, ri) + jn * 16);
+            const float dd[3] = {__ldg(rays.ray_batch + ri * 11 + 3), __ldg(rays.ray_batch + ri * 11 + 4), __ldg(rays.ray_batch + ri * 11 + 5)};
+            float dj[3];
+            pgn_joint_dir(__ldg(m), __ldg(m + 1), __ldg(m + 2), dd, dj[0], dj[1], dj[2]);
+            for (int k = 0; k < 1 + 2 * PGN_LD; ++k)
+              for (int a = 0; a < 3; ++a) tab[k * 3 + a] = __float2half_rn(pgn_pe_term(dj[a], k));
+            for (int e = 27; e < 32; ++e) tab[e] = __float2half_rn(0.f);
+          }
+        }
+      }
+      if (j.L == 8) compute_bar_sync();      // wcache (L5's encode) and dtab (L0's PRE) visible to every thread
+      RowCtx rc;
+      rc.valid = false; rc.px = rc.py = rc.pz = 0.f; rc.skt = rays.skts;
+      if (!kStage && j.L != 8) rc = make_row_ctx(sm, rays, sc, tc, near_far, row);
+      // software pipeline: the values of chunk c+1 are computed while chunk c travels through the
+      // staging buffer / tensor core; only the 16-byte stores wait for the buffer to be released
+      uint32_t packed[20];
+      auto compute_chunk = [&](int c) {
+        if (j.L == 8) { PROF_T0(); encode_d_compute<kStage>(sm, tc, j.slot, c, row, half, enc_rows, rows_valid, packed); PROF_ADD(7); }
+        else { PROF_T0(); encode_x_compute<kStage>(sm, sc, rc, j.slot, c, row, half, j.L == 5, enc_rows, rows_valid, packed); PROF_ADD(6); }
+      };
+      compute_chunk(0);
+      for (int c = 0; c < nchunks; ++c) {
+        { PROF_T0(); const bool okw = mbar_wait(&sm.stg_empty, (stg_n & 1) ^ 1, status, 301); PROF_ADD(10); if (!okw) return false; }
+        { PROF_T0();
+          if (j.L == 8) encode_d_store(sm, row, half, packed); else encode_x_store(sm, row, half, packed);
+          compute_arrive(&sm.stg_full, lane); PROF_ADD(15); }
+        ++stg_n;
+        if (c == 0 && drain_after_first && !post(*drain_after_first)) return false;   // other slot's epilogue, now that this job can start
+        if (c + 1 < nchunks) compute_chunk(c + 1);
+      }
+      return true;
+    };
+
+    JobIter ji(n_local, kStage);
+    Job cur, nxt;
+    bool has_cur = ji.next(cur);
+    if (has_cur && !pre(cur, nullptr)) goto done;
+    while (has_cur) {
+      const bool has_nxt = ji.next(nxt);
+      // other slot next: feed its layer first so the tensor core has work while we drain `cur`;
+      // same slot next (prologue / tail of the schedule): its MMAs wait for our epilogue anyway
+      const bool pre_first = has_nxt && nxt.slot != cur.slot;
+      if (pre_first) { if (!pre(nxt, &cur)) goto done; }
+      else {
+        if (!post(cur)) goto done;
+        if (has_nxt && !pre(nxt, nullptr)) goto done;
+      }
+      cur = nxt;
+      has_cur = has_nxt;
     }
   }
 done:
   if (prof) {
     unsigned long long* pp = prof + (size_t)blockIdx.x * 16;
     const unsigned long long total = (unsigned long long)(clock64() - kernel_t0);
-    if (warp == kIssuerWarp && lane == 0) { pp[0] = pacc[0]; pp[1] = pacc[1]; pp[2] = pacc[2]; pp[3] = total; pp[13] = pacc[13]; pp[14] = pacc[14]; }
+    if (warp == kIssuerWarp && lane == 0) { pp[0] = pacc[0]; pp[1] = pacc[1]; pp[2] = pacc[2]; pp[3] = total; }
     if (warp == kProducerWarp && lane == 0) { pp[4] = pacc[4]; pp[5] = total; }
-    if (tid == 0) { for (int i = 6; i <= 10; ++i) pp[i] = pacc[i]; pp[12] = total; }
+    if (tid == 0) { for (int i = 6; i <= 11; ++i) pp[i] = pacc[i]; pp[12] = total; pp[15] = pacc[15]; }
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -605,8 +735,17 @@ __global__ void pgn_pack_wstream_kernel(PackPtrs p, const float* __restrict__ fo
     const int e = (int)(r & 7);
     const int kp = ks * 16 + kh * 8 + e;
     float v = 0.f;
-    if (L == 0) v = p.w[0][(size_t)n * 432 + pgn_xperm_refcol(kp)];
-    else if (L == 5) v = (kp < 256) ? p.w[5][(size_t)n * 688 + 432 + kp] : p.w[5][(size_t)n * 688 + pgn_xperm_refcol(kp - 256)];
+    if (ks == ks_total - 1) {
+      // bias K-step: k = 0 -> bf16 hi part, k = 1 -> residual (the tensor core adds both in fp32)
+      const float b = (L < 8) ? p.b[L][n] : fold[128 * 256 + n];
+      const float hi = __bfloat162float(__float2bfloat16_rn(b));
+      v = (kh == 0 && e == 0) ? hi : ((kh == 0 && e == 1) ? b - hi : 0.f);
+    } else
+    if (L == 0) { const int rc = pgn_xperm_refcol(kp); v = rc >= 0 ? p.w[0][(size_t)n * 432 + rc] : 0.f; }
+    else if (L == 5) {
+      if (kp < 256) v = p.w[5][(size_t)n * 688 + 432 + kp];
+      else { const int rc = pgn_xperm_refcol(kp - 256); v = rc >= 0 ? p.w[5][(size_t)n * 688 + rc] : 0.f; }
+    }
     else if (L == 8) {
       if (kp < 256) v = fold[n * 256 + kp];
       else { const int rc = pgn_dperm_refcol(kp - 256); v = rc >= 0 ? p.w[10][(size_t)n * 904 + 256 + (rc - 432)] : 0.f; }

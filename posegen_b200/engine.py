@@ -237,8 +237,8 @@ class Engine:
         return img.view(H, W, 3)
 
     PHASES = ["issuer_wait_weights", "issuer_wait_staging", "issuer_wait_act", "issuer_total", "producer_wait_slot",
-              "producer_total", "encode_x", "encode_d", "epilogue", "wait_acc", "wait_stg_free", "-", "compute_total",
-              "issuer_mma_issue", "issuer_commit", "-"]
+              "producer_total", "encode_x", "encode_d", "epilogue", "wait_acc", "wait_stg_free", "composite", "compute_total",
+              "issuer_mma_issue", "issuer_commit", "store_arrive"]
 
     def phase_timers(self, enable=True, read=False):
         """Enable/disable the bf16 kernel's phase timers; read=True returns the last launch's averages (cycles)."""

@@ -62,9 +62,9 @@ def test_bf16_k_permutations_are_bijections():
 #include <cstdio>
 #include "pgn_bf16_layout.h"
 int main() {
-  for (int k = 0; k < 432; ++k) printf("%d ", pgn_xperm_refcol(k));
+  for (int k = 0; k < 480; ++k) printf("%d ", pgn_xperm_refcol(k));
   printf("\n");
-  for (int q = 0; q < 672; ++q) printf("%d ", pgn_dperm_refcol(q));
+  for (int q = 0; q < 768; ++q) printf("%d ", pgn_dperm_refcol(q));
   printf("\n%zu\n", pgn_wstream_elems());
   int ks = 0; for (int L = 0; L < 9; ++L) ks += pgn_layer_ksteps(L);
   printf("%d\n", ks);
@@ -77,10 +77,10 @@ int main() {
         lines = subprocess.run([exe], capture_output=True, text=True, check=True).stdout.strip().split("\n")
     x = [int(v) for v in lines[0].split()]
     d = [int(v) for v in lines[1].split()]
-    assert sorted(x) == list(range(432))
-    assert sorted(v for v in d if v >= 0) == list(range(432, 1080)) and d.count(-1) == 24
-    assert int(lines[2]) == 798720      # bf16 elements per net = tensor MACs per sample
-    assert int(lines[3]) == 224
+    assert sorted(v for v in x if v >= 0) == list(range(432)) and x.count(-1) == 48
+    assert sorted(v for v in d if v >= 0) == list(range(432, 1080)) and d.count(-1) == 120
+    assert int(lines[2]) == 870400      # bf16 elements per net = executed tensor MACs per sample (zero pads + bias K-steps)
+    assert int(lines[3]) == 245
 
 
 def test_raycaster_drop_in_surface():
