@@ -33,20 +33,26 @@ pgn_probe_umma_kernel(const float* __restrict__ A, const float* __restrict__ B, 
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = tmem_slot;
+  const int reps = (variant & 4) ? 8 : 1;     // bit 2: timing mode (same K-steps issued 8x back to back)
+  long long t_issue0 = 0, t_issue1 = 0;
   if (tid == 0) {
     const uint32_t idesc = umma_idesc_bf16(128, N);
+    t_issue0 = clock64();
+    for (int rep = 0; rep < reps; ++rep)
     for (int ks = 0; ks < K / 16; ++ks) {
       const uint32_t a_addr = smem_u32(sA) + ks * 2 * 2048;
       const uint32_t b_addr = smem_u32(sB) + ks * 2 * (N * 16);
       uint64_t ad, bd;
       if (variant & 1) { ad = umma_smem_desc(a_addr, 128, 2048); bd = umma_smem_desc(b_addr, 128, N * 16); }
       else             { ad = umma_smem_desc(a_addr, 2048, 128); bd = umma_smem_desc(b_addr, N * 16, 128); }
-      umma_bf16(tmem, ad, bd, idesc, ks > 0 ? 1u : 0u);
+      umma_bf16(tmem, ad, bd, idesc, (ks > 0 || rep > 0) ? 1u : 0u);
     }
     umma_commit(&bar);
+    t_issue1 = clock64();
   }
   __syncwarp();
   mbar_wait(&bar, 0, status, 901);
+  if (tid == 0 && (variant & 4)) { D[(size_t)128 * N] = (float)(t_issue1 - t_issue0); D[(size_t)128 * N + 1] = (float)(clock64() - t_issue0); }
   tc_fence_after_sync();
   const int row = warp * 32 + lane;
   for (int c0 = 0; c0 < N; c0 += 32) {
@@ -65,7 +71,7 @@ pgn_probe_umma_kernel(const float* __restrict__ A, const float* __restrict__ B, 
 // issues the MMAs and multicasts the commit; each CTA drains its own 128 TMEM lanes.
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
 pgn_probe_umma2_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D, int K, int N,
-                       int* __restrict__ status_g) {
+                       int timing, int* __restrict__ status_g) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int NH = N / 2;
   uint8_t* sA = smem;
@@ -94,19 +100,25 @@ pgn_probe_umma2_kernel(const float* __restrict__ A, const float* __restrict__ B,
   // operands of both CTAs ready -> leader's barrier
   fence_proxy_async_smem();
   mbar_arrive_cluster(&bar_ready, 0);
+  const int reps = timing ? 8 : 1;
+  long long t_issue0 = 0, t_issue1 = 0;
   if (rank == 0 && tid == 0) {
     mbar_wait_cluster(&bar_ready, 0, status, 911);
     tc_fence_after_sync();
     const uint32_t idesc = umma_idesc_bf16(256, N);
+    t_issue0 = clock64();
+    for (int rep = 0; rep < reps; ++rep)
     for (int ks = 0; ks < K / 16; ++ks) {
       const uint64_t ad = umma_smem_desc(smem_u32(sA) + ks * 2 * 2048, 2048, 128);
       const uint64_t bd = umma_smem_desc(smem_u32(sB) + ks * 2 * (NH * 16), NH * 16, 128);
-      umma_bf16_2cta(tmem, ad, bd, idesc, ks > 0 ? 1u : 0u);
+      umma_bf16_2cta(tmem, ad, bd, idesc, (ks > 0 || rep > 0) ? 1u : 0u);
     }
     umma_commit_2cta(&bar_done);
+    t_issue1 = clock64();
   }
   __syncwarp();
   mbar_wait(&bar_done, 0, status, 912);
+  if (rank == 0 && tid == 0 && timing) { D[(size_t)256 * N] = (float)(t_issue1 - t_issue0); D[(size_t)256 * N + 1] = (float)(clock64() - t_issue0); }
   tc_fence_after_sync();
   const int row = warp * 32 + lane;
   for (int c0 = 0; c0 < N; c0 += 32) {
@@ -127,7 +139,7 @@ cudaError_t pgn_launch_probe_umma(const float* A, const float* B, float* D, int 
     const size_t smem2 = (size_t)(K / 8) * 2048 + (size_t)(K / 8) * (N / 2) * 16 + 1024;
     cudaError_t e2 = cudaFuncSetAttribute(pgn_probe_umma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
     if (e2 != cudaSuccess) return e2;
-    pgn_probe_umma2_kernel<<<2, 128, smem2, stream>>>(A, B, D, K, N, status);
+    pgn_probe_umma2_kernel<<<2, 128, smem2, stream>>>(A, B, D, K, N, (variant & 4) ? 1 : 0, status);
     return cudaGetLastError();
   }
   const size_t smem = (size_t)(K / 8) * 2048 + (size_t)(K / 8) * N * 16 + 1024;

@@ -37,10 +37,11 @@ using namespace pgn;
 
 namespace {
 
-constexpr int kComputeThreads = 256;
-constexpr int kThreads = 320;
-constexpr int kProducerWarp = 8;
-constexpr int kIssuerWarp = 9;
+constexpr int kComputeThreads = 256;    // threads per compute group (encode group, epilogue group)
+constexpr int kThreads = 576;
+constexpr int kEpiWarp0 = 8;            // warps 0-7 encode, 8-15 epilogue + compositing
+constexpr int kProducerWarp = 16;
+constexpr int kIssuerWarp = 17;
 constexpr int kRPG = 8;                 // rays per group (per CTA)
 constexpr int kTM = 128;                // rows per CTA tile (UMMA M = 256 over the pair)
 constexpr int kRunBytes = kTM * 16;     // one 8-wide K run of all 128 rows
@@ -96,33 +97,44 @@ struct TileIter {
 struct Job { int slot, g, pass, t, L; };
 
 // Merged layer-job order of the two slots: slot s owns tiles s, s+2, s+4, ... of the sequence; after a
-// prologue of kLag slot-0 jobs the two job streams alternate strictly.
+// prologue of kLag slot-0 jobs the two job streams alternate strictly.  (Scalar state only, so the
+// iterator lives in registers in every role.)
+struct SlotCursor {
+  TileIter it;
+  int g, pass, t, L;
+  bool valid;
+  __device__ void init(int n, bool stage, int skip) {
+    it = TileIter(n, stage);
+    int a, b, c;
+    valid = true;
+    for (int i = 0; i < skip && valid; ++i) valid = it.next(a, b, c);
+    if (valid) valid = it.next(g, pass, t);
+    L = 0;
+  }
+  __device__ void emit(Job& j, int slot) {
+    j.slot = slot; j.g = g; j.pass = pass; j.t = t; j.L = L;
+    if (++L == 9) {
+      L = 0;
+      int a, b, c;
+      valid = it.next(a, b, c) && it.next(g, pass, t);
+    }
+  }
+};
 struct JobIter {
-  TileIter it[2];
-  int g[2], pass[2], t[2], L[2];
-  bool valid[2];
+  SlotCursor c0, c1;
   int emitted0, turn;
   __device__ JobIter(int n, bool stage) {
-    it[0] = TileIter(n, stage); it[1] = TileIter(n, stage);
-    valid[0] = it[0].next(g[0], pass[0], t[0]);
-    int a, b, c;
-    valid[1] = it[1].next(a, b, c) && it[1].next(g[1], pass[1], t[1]);
-    L[0] = L[1] = 0; emitted0 = 0; turn = 1;
+    c0.init(n, stage, 0);
+    c1.init(n, stage, 1);
+    emitted0 = 0; turn = 1;
   }
   __device__ bool next(Job& j) {
-    int s;
-    if (valid[0] && emitted0 < kLag) { s = 0; ++emitted0; }
-    else {
-      s = valid[turn] ? turn : (turn ^ 1);
-      if (!valid[s]) return false;
-      turn = s ^ 1;
-    }
-    j.slot = s; j.g = g[s]; j.pass = pass[s]; j.t = t[s]; j.L = L[s];
-    if (++L[s] == 9) {
-      L[s] = 0;
-      int a, b, c;
-      valid[s] = it[s].next(a, b, c) && it[s].next(g[s], pass[s], t[s]);
-    }
+    if (c0.valid && emitted0 < kLag) { ++emitted0; c0.emit(j, 0); return true; }
+    int s = turn;
+    if (!(s == 0 ? c0.valid : c1.valid)) s ^= 1;
+    if (!(s == 0 ? c0.valid : c1.valid)) return false;
+    turn = s ^ 1;
+    if (s == 0) c0.emit(j, 0); else c1.emit(j, 1);
     return true;
   }
 };
@@ -334,7 +346,8 @@ __device__ __forceinline__ void compute_arrive(uint64_t* bar, int lane) {
   __syncwarp();
   if (lane == 0) mbar_arrive_cluster(bar, 0);
 }
-__device__ __forceinline__ void compute_bar_sync() { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }
+__device__ __forceinline__ void encode_bar_sync() { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 2, 256;\n" ::: "memory"); }
 
 // optional phase timers (cycles, one elected thread per role, accumulated per CTA):
 //  0 issuer wait w_full | 1 issuer wait stg_full | 2 issuer wait act_ready | 3 issuer total
@@ -391,103 +404,124 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
   if (warp == kProducerWarp) {
     // ===================== weight producer (each CTA streams ITS N-half of every fill) =====================
     if (lane == 0) {
-      uint32_t wfill = 0;
+      uint32_t stage = 0, wphase = 1;          // "empty" barriers start released
+      size_t layer_off[9];
+      { size_t o = 0; for (int L = 0; L < 9; ++L) { layer_off[L] = o; o += (size_t)pgn_layer_n(L) * pgn_layer_ksteps(L) * 32; } }
       JobIter ji(n_local, kStage);
       Job j;
-      // byte offset of each layer inside the packed stream
       while (ji.next(j)) {
-        const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(j.pass == 0 ? net_c.wstream : net_f.wstream);
-        size_t off = 0;
-        for (int L = 0; L < j.L; ++L) off += (size_t)pgn_layer_n(L) * pgn_layer_ksteps(L) * 32;
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(j.pass == 0 ? net_c.wstream : net_f.wstream) + layer_off[j.L];
         const int nh = pgn_layer_n(j.L) / 2, ks_total = pgn_layer_ksteps(j.L), kpf = pgn_ks_per_fill(j.L);
         for (int ks = 0; ks < ks_total; ks += kpf) {
           const int nks = min(kpf, ks_total - ks);
           const uint32_t bytes = (uint32_t)nks * nh * 32u;          // this CTA's half of the fill
-          const int stage = wfill % kWStages;
-          { PROF_T0(); const bool okw = mbar_wait(&sm.w_empty[stage], ((wfill / kWStages) & 1) ^ 1, status, 101); PROF_ADD(4); if (!okw) goto done; }
+          { PROF_T0(); const bool okw = mbar_wait(&sm.w_empty[stage], wphase, status, 101); PROF_ADD(4); if (!okw) goto done; }
           mbar_arrive_expect_tx(&sm.w_full[stage], bytes);
-          bulk_g2s(sm.wring[stage], wsrc + off + (size_t)rank * bytes, bytes, &sm.w_full[stage]);
-          off += 2u * bytes;
-          ++wfill;
+          bulk_g2s(sm.wring[stage], src + (size_t)rank * bytes, bytes, &sm.w_full[stage]);
+          src += 2u * bytes;
+          if (++stage == kWStages) { stage = 0; wphase ^= 1; }
         }
       }
     }
   } else if (warp == kIssuerWarp) {
     if (lane == 0 && rank == 1) {
       // ===================== peer relay: "my half of fill f has landed" -> leader's w_full =====================
-      uint32_t wfill = 0;
+      uint32_t stage = 0, wphase = 0;
       JobIter ji(n_local, kStage);
       Job j;
       while (ji.next(j)) {
         const int ks_total = pgn_layer_ksteps(j.L), kpf = pgn_ks_per_fill(j.L);
         for (int ks = 0; ks < ks_total; ks += kpf) {
-          const int stage = wfill % kWStages;
-          if (!mbar_wait(&sm.w_full[stage], (wfill / kWStages) & 1, status, 401)) goto done;
+          if (!mbar_wait(&sm.w_full[stage], wphase, status, 401)) goto done;
           mbar_arrive_cluster(&sm.w_full[stage], 0);
-          ++wfill;
+          if (++stage == kWStages) { stage = 0; wphase ^= 1; }
         }
       }
-    } else if (lane == 0) {
+    } else if (rank == 0) {
       // ===================== MMA issuer (leader CTA): UMMA M=256 over both CTAs =====================
-      uint32_t wfill = 0, stg_n = 0;
-      uint32_t posts[2] = {0, 0};            // POSTs of each slot already waited for
-      uint32_t jobs[2] = {0, 0};             // jobs of each slot already issued
-      const uint32_t stg_addr = smem_u32(sm.stg), ones_addr = smem_u32(sm.ones);
+      // The whole warp runs this loop convergently; one elected lane issues each tcgen05 instruction.
+      // The loop is instruction-count critical (a single warp retires ~1 instruction per 5 cycles):
+      // descriptors advance by adding constants to their low words, ring stage / phases are carried
+      // incrementally, no division in the K loop, no timers.
+      uint32_t stage = 0, wphase = 0;        // weight ring cursor
+      uint32_t stg_phase = 0;                // staging buffer phase
+      uint32_t posts0 = 0, posts1 = 0;       // POSTs of each slot already waited for
+      uint32_t jobs0 = 0, jobs1 = 0;         // jobs of each slot already issued
+      const uint32_t kDescHi = (128u >> 4) | (1u << 14);                 // SBO = 128 B, descriptor version 1
+      const uint32_t a_lbo = (uint32_t)(kRunBytes >> 4) << 16;           // A: LBO = 2048 B
+      const uint32_t stg_lo = (smem_u32(sm.stg) >> 4) | a_lbo;
+      const uint32_t ones_lo = (smem_u32(sm.ones) >> 4) | a_lbo;
+      const uint32_t ring_lo = smem_u32(sm.wring[0]) >> 4;
+      constexpr uint32_t kAStep = (2 * kRunBytes) >> 4;                  // one K-step of A (two runs)
       JobIter ji(n_local, kStage);
       Job j;
       while (ji.next(j)) {
         const int s = j.slot, L = j.L;
-        const int n = pgn_layer_n(L), nh = n / 2, ks_total = pgn_layer_ksteps(L), kpf = pgn_ks_per_fill(L);
+        const uint32_t n = pgn_layer_n(L), nh = n / 2;
+        const int ks_total = pgn_layer_ksteps(L), kpf = pgn_ks_per_fill(L);
         const int ks_act = pgn_layer_kact(L) / 16;
         const int chunk_ks = pgn_layer_chunk_ks(L);
         const uint32_t idesc = umma_idesc_bf16(2 * kTM, n);
-        const uint32_t act_addr = smem_u32(sm.act[s]);
+        const uint32_t act_lo = (smem_u32(sm.act[s]) >> 4) | a_lbo;
+        const uint32_t b_lbo = ((nh * 16u) >> 4) << 16;                  // B: LBO = (N/2)*16 B
+        const uint32_t b_step = (nh * 32u) >> 4;                         // one K-step of this CTA's B half
         const uint32_t tmem_acc = tmem_base + (uint32_t)s * 256u;
         // the previous job of this slot must have been drained (its epilogue wrote act[s] / freed the accumulator)
-        if (jobs[s] > 0) {
-          { PROF_T0(); const bool okw = mbar_wait_cluster(&sm.act_ready[s], posts[s] & 1, status, 201); PROF_ADD(2); if (!okw) goto done; }
-          ++posts[s];
+        const uint32_t njobs = s == 0 ? jobs0 : jobs1;
+        if (njobs > 0) {
+          const uint32_t ph = (s == 0 ? posts0 : posts1) & 1;
+          if (!mbar_wait_cluster(&sm.act_ready[s], ph, status, 201)) goto done;
+          if (s == 0) ++posts0; else ++posts1;
           tc_fence_after_sync();
         }
-        ++jobs[s];
-        int stage = 0;
-        for (int ks = 0; ks < ks_total; ++ks) {
-          const int kf = ks % kpf;
-          if (kf == 0) {
-            stage = wfill % kWStages;
-            { PROF_T0(); const bool okw = mbar_wait_cluster(&sm.w_full[stage], (wfill / kWStages) & 1, status, 202); PROF_ADD(0); if (!okw) goto done; }
-            tc_fence_after_sync();
-          }
-          uint32_t a_addr;
-          bool chunk_end = false;
-          if (ks == ks_total - 1) {
-            a_addr = ones_addr;                       // bias K-step
-          } else if (ks < ks_act) {
-            a_addr = act_addr + (uint32_t)ks * 2 * kRunBytes;
-          } else {
-            const int e = ks - ks_act, ce = e % chunk_ks;
-            if (ce == 0) {
-              { PROF_T0(); const bool okw = mbar_wait_cluster(&sm.stg_full, stg_n & 1, status, 203); PROF_ADD(1); if (!okw) goto done; }
-              ++stg_n;
-              tc_fence_after_sync();
+        if (s == 0) ++jobs0; else ++jobs1;
+        int ks = 0, ce = 0;
+        uint32_t accum = 0;
+        while (ks < ks_total) {
+          // ---- one weight fill (kpf K-steps, fewer at the end of the layer)
+          if (!mbar_wait_cluster(&sm.w_full[stage], wphase, status, 202)) goto done;
+          tc_fence_after_sync();
+          uint32_t b_lo = (ring_lo + stage * (kWStageBytes >> 4)) | b_lbo;
+          const int ks_end = min(ks + kpf, ks_total);
+          for (; ks < ks_end; ++ks, b_lo += b_step) {
+            uint32_t a_lo;
+            bool chunk_end = false;
+            if (ks == ks_total - 1) {
+              a_lo = ones_lo;                                   // bias K-step
+            } else if (ks < ks_act) {
+              a_lo = act_lo + (uint32_t)ks * kAStep;
+            } else {
+              if (ce == 0) {
+                if (!mbar_wait_cluster(&sm.stg_full, stg_phase, status, 203)) goto done;
+                stg_phase ^= 1;
+                tc_fence_after_sync();
+              }
+              a_lo = stg_lo + (uint32_t)ce * kAStep;
+              if (++ce == chunk_ks) { ce = 0; chunk_end = true; }
             }
-            a_addr = stg_addr + (uint32_t)ce * 2 * kRunBytes;
-            chunk_end = (ce == chunk_ks - 1);
+            umma_bf16_2cta_elect(tmem_acc, ((uint64_t)kDescHi << 32) | a_lo, ((uint64_t)kDescHi << 32) | b_lo, idesc, accum);
+            accum = 1;
+            if (chunk_end) umma_commit_2cta_elect(&sm.stg_empty);
           }
-          const uint64_t adesc = umma_smem_desc(a_addr, kRunBytes, 128);
-          const uint64_t bdesc = umma_smem_desc(smem_u32(sm.wring[stage]) + (uint32_t)kf * nh * 32u, (uint32_t)nh * 16u, 128);
-          umma_bf16_2cta(tmem_acc, adesc, bdesc, idesc, ks > 0 ? 1u : 0u);
-          if (chunk_end) umma_commit_2cta(&sm.stg_empty);
-          if (kf == kpf - 1 || ks == ks_total - 1) { umma_commit_2cta(&sm.w_empty[stage]); ++wfill; }
+          umma_commit_2cta_elect(&sm.w_empty[stage]);
+          if (++stage == kWStages) { stage = 0; wphase ^= 1; }
         }
-        umma_commit_2cta(&sm.acc_full[s]);
+        umma_commit_2cta_elect(&sm.acc_full[s]);
       }
     }
   } else {
-    // ===================== compute warps (encode, epilogue, compositing) =====================
+    // ===================== compute groups =====================
+    // warps 0-7: ENCODE group (PRE of every job: generated A-operand chunks)
+    // warps 8-15: EPILOGUE group (POST of every job: accumulator drain, heads, compositing, resampling)
+    // Both walk the same static job order independently; they only meet through the issuer's barriers.
+    // (zf written by POST(V) of a coarse tile is read by PRE of fine tiles >= 3 tiles later in the order,
+    //  while the encode group can run at most ~2 jobs ahead of the epilogue group.)
+    const bool is_epi = warp >= kEpiWarp0;
+    const int gtid = is_epi ? tid - kEpiWarp0 * 32 : tid;     // thread index inside the group
+    const int gwarp = gtid >> 5;
     uint32_t stg_n = 0;
     uint32_t accs[2] = {0, 0};
-    const int row = tid & (kTM - 1), half = tid >> 7;
+    const int row = gtid & (kTM - 1), half = gtid >> 7;
 
     auto make_ctx = [&](const Job& j, TileCtx& tc, long long& unit) {
       const long long u = cluster_id + (long long)j.g * n_clusters;
@@ -511,38 +545,38 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
       tc_fence_after_sync();
       const uint32_t tmem_acc = tmem_base + (uint32_t)s * 256u;
       { PROF_T0();
-        if (j.L == 8) epilogue<2>(sm, tmem_acc, s, net.w_alpha, net.w_rgb, warp, lane);
-        else if (j.L == 7) epilogue<1>(sm, tmem_acc, s, net.w_alpha, net.w_rgb, warp, lane);
-        else epilogue<0>(sm, tmem_acc, s, net.w_alpha, net.w_rgb, warp, lane);
+        if (j.L == 8) epilogue<2>(sm, tmem_acc, s, net.w_alpha, net.w_rgb, gwarp, lane);
+        else if (j.L == 7) epilogue<1>(sm, tmem_acc, s, net.w_alpha, net.w_rgb, gwarp, lane);
+        else epilogue<0>(sm, tmem_acc, s, net.w_alpha, net.w_rgb, gwarp, lane);
         compute_arrive(&sm.act_ready[s], lane); PROF_ADD(8); }
       if (j.L != 8) return true;
 
       PROF_T0();
       TileCtx tc; long long unit;
       make_ctx(j, tc, unit);
-      compute_bar_sync();
-      if (tid < kTM) {       // head biases -> raw row (rgb_raw, sigma_raw) in part[s]
-        float* p0 = sm.part[s][tid];
+      epi_bar_sync();
+      if (gtid < kTM) {       // head biases -> raw row (rgb_raw, sigma_raw) in part[s]
+        float* p0 = sm.part[s][gtid];
         p0[0] += net.b_rgb[0];
         p0[1] += net.b_rgb[1];
         p0[2] += net.b_rgb[2];
         p0[3] += net.b_alpha[0];
         if (kStage) {
           const int rows_valid = (int)max(0ll, min((long long)kTM, enc_rows_total - unit * kTM));
-          if (tid < rows_valid) {
-            float* o = raw_global + ((size_t)unit * kTM + tid) * 4;
+          if (gtid < rows_valid) {
+            float* o = raw_global + ((size_t)unit * kTM + gtid) * 4;
             o[0] = p0[0]; o[1] = p0[1]; o[2] = p0[2]; o[3] = p0[3];
           }
         }
       }
-      compute_bar_sync();
+      epi_bar_sync();
       if (!kStage) {
         if (j.pass == 0) {
           // coarse tile = 2 whole rays: composite, resample, merge -> zf ring; reset the fine carry
-          const int rl = 2 * j.t + warp;
-          if (warp < 2 && rl < tc.nr) {
+          const int rl = 2 * j.t + gwarp;
+          if (gwarp < 2 && rl < tc.nr) {
             const long long ri = tc.ray0 + rl;
-            float* zc = sm.cscratch[warp];
+            float* zc = sm.cscratch[gwarp];
             float* wts = zc + 64;
             float* scr = zc + 128;
             const float nn = __ldg(near_far + ri * 2), ff = __ldg(near_far + ri * 2 + 1);
@@ -553,7 +587,7 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
             float* cr = sm.carry[tc.buf][rl];
             if (lane < 8) cr[lane] = (lane == 0) ? 1.f : 0.f;
             __syncwarp();
-            const float* rawrows = &sm.part[s][warp * PGN_S][0];
+            const float* rawrows = &sm.part[s][gwarp * PGN_S][0];
             pgn_composite_segment_warp<PGN_S>(rawrows, zc, 0, PGN_S, dn, sc.density_scale, sc.rgb_eps, lane, cr, wts,
                                               out.alpha0 ? out.alpha0 + ri * PGN_S : nullptr);
             if (lane == 0) {
@@ -573,8 +607,8 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
           }
         } else {
           // fine tile: rows [row0, row0+128) cut up to 3 rays; continue each ray's compositing
-          const int rl = tc.tile_ray0 + warp;
-          if (warp < kMaxTileRays && rl < tc.nr && rl * PGN_T < tc.row0 + kTM) {
+          const int rl = tc.tile_ray0 + gwarp;
+          if (gwarp < kMaxTileRays && rl < tc.nr && rl * PGN_T < tc.row0 + kTM) {
             const long long ri = tc.ray0 + rl;
             const int s0 = max(0, tc.row0 - rl * PGN_T), s1 = min(PGN_T, tc.row0 + kTM - rl * PGN_T);
             const float d0 = __ldg(rays.ray_batch + ri * 11 + 3), d1 = __ldg(rays.ray_batch + ri * 11 + 4), d2 = __ldg(rays.ray_batch + ri * 11 + 5);
@@ -594,16 +628,16 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
           }
         }
       }
-      compute_bar_sync();
-      if (tid < kTM) *reinterpret_cast<float4*>(sm.part[s][tid]) = make_float4(0.f, 0.f, 0.f, 0.f);   // next tile of this slot
+      epi_bar_sync();
+      if (gtid < kTM) *reinterpret_cast<float4*>(sm.part[s][gtid]) = make_float4(0.f, 0.f, 0.f, 0.f);   // next tile of this slot
       PROF_ADD(11);
       return true;
     };
 
     // PRE(job): everything the tensor core needs from the CUDA cores before/while it runs the layer
-    auto pre = [&](const Job& j, const Job* drain_after_first) -> bool {
+    auto pre = [&](const Job& j) -> bool {
       const int nchunks = pgn_layer_chunks(j.L);
-      if (nchunks == 0) return drain_after_first ? post(*drain_after_first) : true;
+      if (nchunks == 0) return true;
       TileCtx tc; long long unit;
       make_ctx(j, tc, unit);
       const float* enc_rows = kStage ? enc_global + (size_t)unit * kTM * PGN_ENC : nullptr;
@@ -611,7 +645,7 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
       if (!kStage && j.L == 0) {
         // PE table of the joint-frame view directions for the <=3 rays of this tile (used by the V layer)
         const int tile_ray1 = min((tc.row0 + kTM - 1) / tc.S, tc.nr - 1);
-        for (int i = tid; i < kMaxTileRays * PGN_J; i += kComputeThreads) {
+        for (int i = gtid; i < kMaxTileRays * PGN_J; i += kComputeThreads) {
           const int tr = i / PGN_J, jn = i % PGN_J;
           const int rl = tc.tile_ray0 + tr;
           __half* tab = &sm.dtab[j.slot][tr][jn * 32];
@@ -627,7 +661,7 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
           }
         }
       }
-      if (j.L == 8) compute_bar_sync();      // wcache (L5's encode) and dtab (L0's PRE) visible to every thread
+      if (j.L == 8) encode_bar_sync();       // wcache (L5's encode) and dtab (L0's PRE) visible to every thread
       RowCtx rc;
       rc.valid = false; rc.px = rc.py = rc.pz = 0.f; rc.skt = rays.skts;
       if (!kStage && j.L != 8) rc = make_row_ctx(sm, rays, sc, tc, near_far, row);
@@ -645,29 +679,15 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
           if (j.L == 8) encode_d_store(sm, row, half, packed); else encode_x_store(sm, row, half, packed);
           compute_arrive(&sm.stg_full, lane); PROF_ADD(15); }
         ++stg_n;
-        if (c == 0 && drain_after_first && !post(*drain_after_first)) return false;   // other slot's epilogue, now that this job can start
         if (c + 1 < nchunks) compute_chunk(c + 1);
       }
       return true;
     };
 
     JobIter ji(n_local, kStage);
-    Job cur, nxt;
-    bool has_cur = ji.next(cur);
-    if (has_cur && !pre(cur, nullptr)) goto done;
-    while (has_cur) {
-      const bool has_nxt = ji.next(nxt);
-      // other slot next: feed its layer first so the tensor core has work while we drain `cur`;
-      // same slot next (prologue / tail of the schedule): its MMAs wait for our epilogue anyway
-      const bool pre_first = has_nxt && nxt.slot != cur.slot;
-      if (pre_first) { if (!pre(nxt, &cur)) goto done; }
-      else {
-        if (!post(cur)) goto done;
-        if (has_nxt && !pre(nxt, nullptr)) goto done;
-      }
-      cur = nxt;
-      has_cur = has_nxt;
-    }
+    Job j;
+    if (is_epi) { while (ji.next(j)) { if (!post(j)) goto done; } }
+    else { while (ji.next(j)) { if (!pre(j)) goto done; } }
   }
 done:
   if (prof) {
@@ -675,7 +695,8 @@ done:
     const unsigned long long total = (unsigned long long)(clock64() - kernel_t0);
     if (warp == kIssuerWarp && lane == 0) { pp[0] = pacc[0]; pp[1] = pacc[1]; pp[2] = pacc[2]; pp[3] = total; }
     if (warp == kProducerWarp && lane == 0) { pp[4] = pacc[4]; pp[5] = total; }
-    if (tid == 0) { for (int i = 6; i <= 11; ++i) pp[i] = pacc[i]; pp[12] = total; pp[15] = pacc[15]; }
+    if (tid == 0) { pp[6] = pacc[6]; pp[7] = pacc[7]; pp[10] = pacc[10]; pp[12] = total; pp[15] = pacc[15]; }
+    if (tid == kEpiWarp0 * 32) { pp[8] = pacc[8]; pp[9] = pacc[9]; pp[11] = pacc[11]; }
   }
   tc_fence_before_sync();
   __syncthreads();

@@ -151,6 +151,19 @@ __device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
 }
 
 // relu(lo), relu(hi) -> packed bf16x2 in one instruction
+// Warp-uniform issue: the WHOLE warp executes the call convergently and one elected lane issues the
+// instruction (operands are warp-uniform, so they live in uniform registers; no per-lane broadcast loops).
+__device__ __forceinline__ void umma_bf16_2cta_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n .reg .pred p, e;\n elect.sync _|e, 0xffffffff;\n setp.ne.b32 p, %4, 0;\n"
+               " @e tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2cta_elect(uint64_t* bar) {
+  asm volatile("{\n .reg .pred e;\n elect.sync _|e, 0xffffffff;\n"
+               " @e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n}\n"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+
 __device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;\n" : "=r"(r) : "f"(hi), "f"(lo));

@@ -248,7 +248,7 @@ class Engine:
 
     def debug_umma_gemm(self, A, B, variant=0):
         K, N = A.shape[1], B.shape[0]
-        D = torch.empty((256 if variant & 2 else 128, N), dtype=torch.float32, device=A.device)
+        D = torch.empty(((256 if variant & 2 else 128) + (1 if variant & 4 else 0), N), dtype=torch.float32, device=A.device)
         _lib.check(self.lib.pgn_debug_umma_gemm(self.handle, _ptr(A.contiguous()), _ptr(B.contiguous()), _ptr(D), K, N,
                                                 variant, self._stream()))
         return D
