@@ -208,10 +208,11 @@ PGN_API int  pgn_generate_rays(pgn_context* ctx, int32_t H, int32_t W, float foc
 PGN_API int  pgn_compose_frame(pgn_context* ctx, int32_t H, int32_t W, int32_t x0, int32_t y0, int32_t x1, int32_t y1,
                        const float* rgb_map, const float* acc_map, float bg, float* image, void* stream);
 
-/* per-role phase timers of the bf16 render kernel (cycles, averaged over CTAs, of the LAST launch
- * made while enabled): out16 may be NULL.  Slots: 0 issuer-wait-weights, 1 issuer-wait-staging,
- * 2 issuer-wait-activations, 3 issuer total, 4 producer-wait-slot, 5 producer total, 6 encode_x,
- * 7 encode_d, 8 epilogue, 9 compute-wait-accumulator, 10 compute-wait-staging-free, 12 compute total. */
+/* per-role phase timers of the bf16 render kernel (cycles of pipeline slot 0, averaged over CTAs, of
+ * the LAST launch made while enabled): out16 may be NULL.  Slots: 3 issuer total, 4 producer-wait-slot,
+ * 5 producer total, 6 encode_x, 7 encode_d, 8 epilogue, 9 compute-wait-accumulator,
+ * 10 compute-wait-staging-free, 11 compositing, 12 compute total, 13 compute-wait-act-free,
+ * 15 chunk store + arrive. */
 PGN_API int  pgn_debug_phase_timers(pgn_context* ctx, int32_t enable, uint64_t* out16);
 
 /* bring-up probe of the tcgen05 plumbing: D[128,N] = A[128,K] * B[N,K]^T with bf16 inputs

@@ -3,13 +3,18 @@
 // Execution model
 //   * CTA pairs (clusters of 2, cta_group::2): one UMMA covers M=256 rows (128 per CTA), fp32
 //     accumulators in TMEM; the weight (B) operand is split along N between the two CTAs, so each
-//     SM streams only half of every layer from L2 (cp.async.bulk into a 5-deep ring).
-//   * two tiles in flight per CTA ("slots": 2 x 256 TMEM columns, 2 x 64 KB activation buffers):
-//     while the tensor core runs a layer of one slot, the CUDA cores run the epilogue / encoding of
-//     the other.  A static interleaving of the two slots' layer jobs is followed by every role.
-//   * each CTA renders groups of 8 rays: 4 coarse tiles (8x64 samples, network_fn) and 5 fine tiles
-//     (8x80 samples, network_fine); tile order C(g0) | F(g,0) C(g+1,0) F(g,1) C(g+1,1) ... so the
-//     resampling of group g+1 is hidden behind the fine pass of group g.
+//     SM streams only half of every layer from L2 (cp.async.bulk rings).
+//   * every CTA runs TWO independent tile pipelines ("slots"): each slot owns 256 TMEM columns, a
+//     64 KB activation buffer, a weight ring, a weight-producer thread, an MMA-issuer warp and a
+//     compute group of 8 warps that does the slot's encoding, epilogues and compositing.  The two
+//     slots only share the tensor core: while one slot is in an epilogue or is generating operand
+//     chunks, the tensor core runs the other slot's layer (the hardware interleaves the two issue
+//     streams), and the CUDA cores of one slot overlap with the tensor work of the other.
+//   * a slot renders ray groups of 8 rays: 4 coarse tiles (2 rays x 64 samples, network_fn) and 5
+//     fine tiles (8 x 80 samples cut into 128-row tiles, network_fine), in the order
+//     C0 C1 F0 C2 F1 C3 F2 F3 F4.  Compositing / inverse-CDF resampling of a tile is DEFERRED into
+//     the shadow of the next tile's first hidden layer, so it never sits on the tensor core's
+//     critical path; the order guarantees that a fine tile's z values exist before it is encoded.
 //   * per 128-row tile, 9 tensor-core layers (K-steps of 16):
 //       L0   x_p(480)            -> 256 ReLU   A generated on the fly (skeleton-relative encoding +
 //       L1-4 h(256)              -> 256 ReLU     cutoff PE, 4 joints per 20 KB chunk)
@@ -17,13 +22,17 @@
 //       L6-7 h(256)              -> 256 ReLU   (sigma head folded into L7's epilogue, fp32)
 //       V    h7(256) | d(768)    -> 128 ReLU   (feature_linear folded into views_linears[0]; rgb head
 //                                               folded into the epilogue, fp32)
-//   * compositing is incremental (carry per ray), inverse-CDF resampling is a warp per ray; the
-//     samples x joints x embedding tensor only ever exists as 20 KB chunks in shared memory and the
-//     per-sample network outputs never leave the SM.
+//     Generated chunks are staged in a 3-deep ring that lives INSIDE the slot's own activation
+//     buffer: the buffer is dead while L0 runs and, for L5/V, as soon as the 16 activation K-steps
+//     have been consumed (act_free barrier), so operand generation runs up to three chunks ahead
+//     of the tensor core without any dedicated staging memory.
+//   * the samples x joints x embedding tensor only ever exists as 20 KB chunks in shared memory and
+//     the per-sample network outputs never leave the SM.
 //
-// Warp roles (320 threads): warps 0-7 encode + epilogue + compositing (warp w owns TMEM lanes
-// 32*(w%4).., column half w/4), warp 8 = weight producer (one lane issues bulk copies), warp 9 =
-// MMA issuer in the leader CTA / "my half landed" relay in the peer CTA, and TMEM allocator.
+// Warp roles (640 threads): warps 0-7 = compute group of slot 0, 8-15 = compute group of slot 1
+// (warp w owns TMEM lanes 32*(w%4).., column half (w%8)/4), warps 16/17 = weight producers of slot
+// 0/1 (one lane issues bulk copies), warps 18/19 = MMA issuers of slot 0/1 in the leader CTA /
+// "my half landed" relays in the peer CTA; warp 18 also owns the TMEM allocation.
 //
 // Reference semantics: core/raycasters.py:361-474, core/encoders.py:8-37,110-122,181-193,
 // core/cutoff_embedder.py:111-174, core/networks/nerf.py:94-205, core/utils/ray_utils.py:157-289.
@@ -37,129 +46,68 @@ using namespace pgn;
 
 namespace {
 
-constexpr int kComputeThreads = 256;    // threads per compute group (encode group, epilogue group)
-constexpr int kThreads = 576;
-constexpr int kEpiWarp0 = 8;            // warps 0-7 encode, 8-15 epilogue + compositing
-constexpr int kProducerWarp = 16;
-constexpr int kIssuerWarp = 17;
-constexpr int kRPG = 8;                 // rays per group (per CTA)
+constexpr int kGroupThreads = 256;      // threads of one slot's compute group
+constexpr int kGroupWarps = kGroupThreads / 32;
+constexpr int kThreads = 640;
+constexpr int kProducerWarp0 = 16;      // + slot
+constexpr int kIssuerWarp0 = 18;        // + slot
+constexpr int kRPG = 8;                 // rays per group
 constexpr int kTM = 128;                // rows per CTA tile (UMMA M = 256 over the pair)
 constexpr int kRunBytes = kTM * 16;     // one 8-wide K run of all 128 rows
 constexpr int kActBytes = 256 / 8 * kRunBytes;                 // 65536
 constexpr int kStgBytes = (PGN_X_CHUNK_K / 8) * kRunBytes;     // 20480
-constexpr int kWStages = 5;
+constexpr int kStgBufs = 3;             // staging ring inside act[slot]
+constexpr int kWStages = 3;
 constexpr int kWStageBytes = 8192;
 constexpr int kTmemCols = 512;          // two 256-column accumulators
 constexpr int kMaxTileRays = 3;
-constexpr int kLag = 5;                 // slot 1 trails slot 0 by ~half a tile
+constexpr int kTilesPerGroup = 9;
+
+static_assert(kStgBufs * kStgBytes <= kActBytes, "staging ring must fit inside the activation buffer");
 
 struct __align__(128) Smem {
-  uint8_t act[2][kActBytes];
-  uint8_t stg[kStgBytes];
-  uint8_t wring[kWStages][kWStageBytes];
+  uint8_t act[2][kActBytes];                     // per slot: A operand of the hidden layers; first 60 KB double as the staging ring
+  uint8_t wring[2][kWStages][kWStageBytes];      // per slot: weight ring (this CTA's N half)
   __half wcache[2][PGN_J * kTM];                 // d-window per (joint,row), per slot
   __half dtab[2][kMaxTileRays][PGN_J * 32];      // PE of joint-frame view dirs per ray of the tile (27 + 5 zeros)
-  float zf[2][kRPG][PGN_T];                      // merged z of the fine pass, per group parity
+  float zf[2][kRPG][PGN_T];                      // merged z of the fine pass of the slot's current ray group
   float carry[2][kRPG][8];                       // incremental compositing state of the fine rays
   float part[2][kTM][4];                         // per slot: raw rows (rgb_raw, sigma_raw), accumulated by both column halves
   uint8_t ones[2 * kRunBytes];                   // constant A operand of the bias K-step: k = 0,1 -> 1.0, else 0
-  float cscratch[2][256];                        // coarse compositing: z[64] | weights[64] | sample_pdf scratch[128]
-  uint64_t w_full[kWStages], w_empty[kWStages];
-  uint64_t stg_full, stg_empty, act_ready[2], acc_full[2];
+  float cscratch[2][2][256];                     // coarse compositing per slot, per warp: z[64] | weights[64] | sample_pdf scratch[128]
+  uint64_t w_full[2][kWStages], w_empty[2][kWStages];
+  uint64_t stg_full[2][kStgBufs], stg_empty[2][kStgBufs];
+  uint64_t act_ready[2], acc_full[2], act_free[2];
   uint32_t tmem_base;
 };
-
-// ------------------------------------------------------------------ static schedule
-// Tile sequence of one cluster (identical in every role of both CTAs).
-struct TileIter {
-  int n, i, k;
-  bool stage;
-  __device__ TileIter() {}
-  __device__ TileIter(int n_, bool stage_) : n(n_), i(-1), k(0), stage(stage_) {}
-  __device__ bool next(int& g, int& pass, int& t) {
-    if (stage) { if (k >= n) return false; g = k++; pass = 0; t = 0; return true; }
-    for (;;) {
-      if (i < 0) {
-        if (n == 0) return false;
-        if (k < 4) { g = 0; pass = 0; t = k++; return true; }
-        i = 0; k = 0;
-        continue;
-      }
-      if (i >= n) return false;
-      if (k >= 9) { ++i; k = 0; continue; }
-      const int kk = k++;
-      if ((kk & 1) == 0) { g = i; pass = 1; t = kk >> 1; return true; }
-      if (i + 1 < n) { g = i + 1; pass = 0; t = kk >> 1; return true; }
-    }
-  }
-};
-
-struct Job { int slot, g, pass, t, L; };
-
-// Merged layer-job order of the two slots: slot s owns tiles s, s+2, s+4, ... of the sequence; after a
-// prologue of kLag slot-0 jobs the two job streams alternate strictly.  (Scalar state only, so the
-// iterator lives in registers in every role.)
-struct SlotCursor {
-  TileIter it;
-  int g, pass, t, L;
-  bool valid;
-  __device__ void init(int n, bool stage, int skip) {
-    it = TileIter(n, stage);
-    int a, b, c;
-    valid = true;
-    for (int i = 0; i < skip && valid; ++i) valid = it.next(a, b, c);
-    if (valid) valid = it.next(g, pass, t);
-    L = 0;
-  }
-  __device__ void emit(Job& j, int slot) {
-    j.slot = slot; j.g = g; j.pass = pass; j.t = t; j.L = L;
-    if (++L == 9) {
-      L = 0;
-      int a, b, c;
-      valid = it.next(a, b, c) && it.next(g, pass, t);
-    }
-  }
-};
-struct JobIter {
-  SlotCursor c0, c1;
-  int emitted0, turn;
-  __device__ JobIter(int n, bool stage) {
-    c0.init(n, stage, 0);
-    c1.init(n, stage, 1);
-    emitted0 = 0; turn = 1;
-  }
-  __device__ bool next(Job& j) {
-    if (c0.valid && emitted0 < kLag) { ++emitted0; c0.emit(j, 0); return true; }
-    int s = turn;
-    if (!(s == 0 ? c0.valid : c1.valid)) s ^= 1;
-    if (!(s == 0 ? c0.valid : c1.valid)) return false;
-    turn = s ^ 1;
-    if (s == 0) c0.emit(j, 0); else c1.emit(j, 1);
-    return true;
-  }
-};
-
 static_assert(sizeof(Smem) + 1024 <= 232448, "shared memory budget of one CTA exceeded");
+
+// tile k of a ray group: C0 C1 F0 C2 F1 C3 F2 F3 F4
+__device__ __forceinline__ void tile_of(int k, int& pass, int& t) {
+  pass = (0x1D4 >> k) & 1;
+  t = (int)((0x432312010ull >> (4 * k)) & 0xF);
+}
 
 struct TileCtx {
   long long ray0;     // first ray of this CTA's group
+  long long unit;     // work unit (ray group; stage mode: 128-row tile)
   int nr;             // valid rays in the group (0..8)
   int S;              // samples per ray in this pass
   int pass;
+  int t;              // tile index inside the pass
   int row0;           // first row of the tile within the group pass
   int total_rows;     // valid rows in the group pass
-  int buf;            // group parity: zf / carry buffer
   int tile_ray0;      // first ray (local) touched by the tile
 };
 
-// ------------------------------------------------------------------ encode (compute warps)
+// ------------------------------------------------------------------ encode (compute group)
 // x chunk c (joints 4c..4c+3): thread (row, half) produces joints 4c+2*half, +1 -> 36 values + 4 zeros
 // = 5 runs of 8 at run index half*5+r.
 struct RowCtx { bool valid; float px, py, pz; const float* skt; };
 
 // per-row state shared by all chunks of one layer: sample position and the pose's transforms
 __device__ __forceinline__ RowCtx make_row_ctx(const Smem& sm, const PgnRayRefs& rays, const PgnScalars& sc, const TileCtx& tc,
-                                               const float* __restrict__ near_far, int row) {
+                                               const float* __restrict__ near_far, int slot, int row) {
   RowCtx rc;
   const int grow = tc.row0 + row;
   rc.valid = grow < tc.total_rows;
@@ -172,7 +120,7 @@ __device__ __forceinline__ RowCtx make_row_ctx(const Smem& sm, const PgnRayRefs&
     const float o[3] = {__ldg(rb), __ldg(rb + 1), __ldg(rb + 2)};
     const float d[3] = {__ldg(rb + 3), __ldg(rb + 4), __ldg(rb + 5)};
     const float z = (tc.pass == 0) ? pgn_coarse_z(__ldg(near_far + ri * 2), __ldg(near_far + ri * 2 + 1), sc.t_coarse[s])
-                                   : sm.zf[tc.buf][rl][s];
+                                   : sm.zf[slot][rl][s];
     pgn_sample_point(o, d, z, rc.px, rc.py, rc.pz);
     rc.skt = pgn_ray_skts(rays, ri);
   }
@@ -227,11 +175,10 @@ __device__ __forceinline__ void encode_x_compute(Smem& sm, const PgnScalars& sc,
     packed[18] = 0u; packed[19] = 0u;
   }
 }
-__device__ __forceinline__ void encode_x_store(Smem& sm, int row, int half, const uint32_t (&packed)[20]) {
-  uint8_t* base = sm.stg + (size_t)(half * 5) * kRunBytes + row * 16;
+__device__ __forceinline__ void encode_x_store(uint32_t stg, int row, int half, const uint32_t (&packed)[20]) {
+  const uint32_t base = stg + (uint32_t)(half * 5) * kRunBytes + row * 16;
 #pragma unroll
-  for (int r = 0; r < 5; ++r)
-    *reinterpret_cast<uint4*>(base + r * kRunBytes) = make_uint4(packed[4 * r], packed[4 * r + 1], packed[4 * r + 2], packed[4 * r + 3]);
+  for (int r = 0; r < 5; ++r) sts128(base + r * kRunBytes, packed[4 * r], packed[4 * r + 1], packed[4 * r + 2], packed[4 * r + 3]);
 }
 
 // d chunk c (joints 2c, 2c+1): thread (row, half) produces joint 2c+half -> 27 values + 5 zeros
@@ -258,10 +205,10 @@ __device__ __forceinline__ void encode_d_compute(Smem& sm, const TileCtx& tc, in
     const int tr = min(max(rl - tc.tile_ray0, 0), kMaxTileRays - 1);
     const int j = chunk * 2 + half;
     const float wd = valid ? __half2float(sm.wcache[slot][j * kTM + row]) : 0.f;
-    const uint4* tab = reinterpret_cast<const uint4*>(&sm.dtab[slot][tr][j * 32]);   // 32 halfs = 4 x 16 B
+    const uint32_t tab = smem_u32(&sm.dtab[slot][tr][j * 32]);   // 32 halfs = 4 x 16 B
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const uint4 t = tab[i];
+      const uint4 t = lds128(tab + i * 16);
       const uint32_t w4[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -272,38 +219,38 @@ __device__ __forceinline__ void encode_d_compute(Smem& sm, const TileCtx& tc, in
     }
   }
 }
-__device__ __forceinline__ void encode_d_store(Smem& sm, int row, int half, const uint32_t (&packed)[20]) {
-  uint8_t* base = sm.stg + (size_t)(half * 4) * kRunBytes + row * 16;
+__device__ __forceinline__ void encode_d_store(uint32_t stg, int row, int half, const uint32_t (&packed)[20]) {
+  const uint32_t base = stg + (uint32_t)(half * 4) * kRunBytes + row * 16;
 #pragma unroll
-  for (int r = 0; r < 4; ++r)
-    *reinterpret_cast<uint4*>(base + r * kRunBytes) = make_uint4(packed[4 * r], packed[4 * r + 1], packed[4 * r + 2], packed[4 * r + 3]);
+  for (int r = 0; r < 4; ++r) sts128(base + r * kRunBytes, packed[4 * r], packed[4 * r + 1], packed[4 * r + 2], packed[4 * r + 3]);
 }
 
-// ------------------------------------------------------------------ epilogue (compute warps)
+// ------------------------------------------------------------------ epilogue (compute group)
 // The bias is already in the accumulator (bias K-step), so a hidden layer is TMEM -> ReLU+bf16 -> smem.
 // MODE 0: hidden layer -> act.  MODE 1: same + sigma head (fp32).  MODE 2: view layer -> rgb head (fp32).
 // TMEM loads of the next 32-column batch are issued before the current batch is processed.
 template <int MODE>
-__device__ __forceinline__ void epilogue(Smem& sm, uint32_t tmem_acc, int slot, const float* __restrict__ w_alpha,
+__device__ __forceinline__ void epilogue(Smem& sm, uint32_t tmem_acc, uint32_t act_saddr, int slot, const float* __restrict__ w_alpha,
                                          const float* __restrict__ w_rgb, int warp, int lane) {
   const int q = warp & 3, half = warp >> 2;
   const int row = q * 32 + lane;
   constexpr int kCols = (MODE == 2) ? 64 : 128;        // columns per thread
-  constexpr int kBatches = kCols / 32;
+  constexpr int kBatches = kCols / 16;
   const int col0 = half * kCols;
   const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)col0;
+  const uint32_t dst0 = act_saddr + (uint32_t)(col0 >> 3) * kRunBytes + row * 16;
   float sig = 0.f, r0 = 0.f, r1 = 0.f, r2 = 0.f;
-  uint32_t v[2][32];
-  tmem_ld_32x32(taddr, v[0]);
+  uint32_t v[2][16];
+  tmem_ld_32x16(taddr, v[0]);
 #pragma unroll
   for (int b = 0; b < kBatches; ++b) {
     tmem_ld_wait();
-    if (b + 1 < kBatches) tmem_ld_32x32(taddr + (uint32_t)(b + 1) * 32, v[(b + 1) & 1]);
-    const int c0 = col0 + b * 32;
+    if (b + 1 < kBatches) tmem_ld_32x16(taddr + (uint32_t)(b + 1) * 16, v[(b + 1) & 1]);
+    const int c0 = col0 + b * 16;
     const uint32_t* vb = v[b & 1];
     if (MODE == 1) {
 #pragma unroll
-      for (int i4 = 0; i4 < 8; ++i4) {
+      for (int i4 = 0; i4 < 4; ++i4) {
         const float4 wa = __ldg(reinterpret_cast<const float4*>(w_alpha + c0) + i4);
         sig = fmaf(fmaxf(__uint_as_float(vb[4 * i4]), 0.f), wa.x, sig);
         sig = fmaf(fmaxf(__uint_as_float(vb[4 * i4 + 1]), 0.f), wa.y, sig);
@@ -313,7 +260,7 @@ __device__ __forceinline__ void epilogue(Smem& sm, uint32_t tmem_acc, int slot, 
     }
     if (MODE == 2) {
 #pragma unroll
-      for (int i4 = 0; i4 < 8; ++i4) {
+      for (int i4 = 0; i4 < 4; ++i4) {
         const float4 a = __ldg(reinterpret_cast<const float4*>(w_rgb + c0) + i4);
         const float4 g = __ldg(reinterpret_cast<const float4*>(w_rgb + 128 + c0) + i4);
         const float4 c = __ldg(reinterpret_cast<const float4*>(w_rgb + 256 + c0) + i4);
@@ -324,14 +271,13 @@ __device__ __forceinline__ void epilogue(Smem& sm, uint32_t tmem_acc, int slot, 
         r2 = fmaf(x0, c.x, r2); r2 = fmaf(x1, c.y, r2); r2 = fmaf(x2, c.z, r2); r2 = fmaf(x3, c.w, r2);
       }
     } else {
-      uint8_t* dst = sm.act[slot] + (size_t)(c0 >> 3) * kRunBytes + row * 16;
 #pragma unroll
-      for (int g = 0; g < 4; ++g)
-        *reinterpret_cast<uint4*>(dst + g * kRunBytes) =
-            make_uint4(pack_relu_bf16x2(__uint_as_float(vb[8 * g]), __uint_as_float(vb[8 * g + 1])),
-                       pack_relu_bf16x2(__uint_as_float(vb[8 * g + 2]), __uint_as_float(vb[8 * g + 3])),
-                       pack_relu_bf16x2(__uint_as_float(vb[8 * g + 4]), __uint_as_float(vb[8 * g + 5])),
-                       pack_relu_bf16x2(__uint_as_float(vb[8 * g + 6]), __uint_as_float(vb[8 * g + 7])));
+      for (int g = 0; g < 2; ++g)
+        sts128(dst0 + (uint32_t)(2 * b + g) * kRunBytes,
+               pack_relu_bf16x2(__uint_as_float(vb[8 * g]), __uint_as_float(vb[8 * g + 1])),
+               pack_relu_bf16x2(__uint_as_float(vb[8 * g + 2]), __uint_as_float(vb[8 * g + 3])),
+               pack_relu_bf16x2(__uint_as_float(vb[8 * g + 4]), __uint_as_float(vb[8 * g + 5])),
+               pack_relu_bf16x2(__uint_as_float(vb[8 * g + 6]), __uint_as_float(vb[8 * g + 7])));
     }
   }
   if (MODE == 1) atomicAdd(&sm.part[slot][row][3], sig);
@@ -346,13 +292,12 @@ __device__ __forceinline__ void compute_arrive(uint64_t* bar, int lane) {
   __syncwarp();
   if (lane == 0) mbar_arrive_cluster(bar, 0);
 }
-__device__ __forceinline__ void encode_bar_sync() { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 2, 256;\n" ::: "memory"); }
+__device__ __forceinline__ void group_bar_sync(int slot) { asm volatile("bar.sync %0, 256;\n" ::"r"(slot + 1) : "memory"); }
 
-// optional phase timers (cycles, one elected thread per role, accumulated per CTA):
-//  0 issuer wait w_full | 1 issuer wait stg_full | 2 issuer wait act_ready | 3 issuer total
-//  4 producer wait w_empty | 5 producer total
+// optional phase timers (cycles, one elected thread per role of SLOT 0, accumulated per CTA):
+//  3 issuer total | 4 producer wait w_empty | 5 producer total
 //  6 encode_x | 7 encode_d | 8 epilogue | 9 wait acc_full | 10 wait stg_empty | 11 composite | 12 compute total
+//  13 wait act_free | 15 chunk store + arrive
 #define PROF_T0() const long long _pt0 = prof ? clock64() : 0
 #define PROF_ADD(slot) do { if (prof) pacc[slot] += (unsigned long long)(clock64() - _pt0); } while (0)
 
@@ -371,19 +316,24 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
   const PgnScalars& sc = *scp;
   const long long n_clusters = gridDim.x >> 1, cluster_id = blockIdx.x >> 1;
 
-  // work units: ray groups of 8 (stage mode: 128-row tiles); a pair-unit = one unit per CTA of the pair
+  // work units: ray groups of 8 (stage mode: 128-row tiles); a pair-unit = one unit per CTA of the pair.
+  // Pair-units are dealt round-robin to clusters; inside a cluster, alternately to the two slots.
   const long long n_units = kStage ? (enc_rows_total + kTM - 1) / kTM : (rays.n_rays + kRPG - 1) / kRPG;
   const long long n_pairs = (n_units + 1) / 2;
   const int n_local = (int)((n_pairs > cluster_id) ? (n_pairs - cluster_id + n_clusters - 1) / n_clusters : 0);
+  constexpr int kTiles = kStage ? 1 : kTilesPerGroup;
 
   if (tid == 0) {
-    for (int s = 0; s < kWStages; ++s) { mbar_init(&sm.w_full[s], rank == 0 ? 2 : 1); mbar_init(&sm.w_empty[s], 1); }
-    mbar_init(&sm.stg_full, 2 * (kComputeThreads / 32));
-    mbar_init(&sm.stg_empty, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(&sm.act_ready[s], 2 * (kComputeThreads / 32)); mbar_init(&sm.acc_full[s], 1); }
+    for (int s = 0; s < 2; ++s) {
+      for (int i = 0; i < kWStages; ++i) { mbar_init(&sm.w_full[s][i], rank == 0 ? 2 : 1); mbar_init(&sm.w_empty[s][i], 1); }
+      for (int i = 0; i < kStgBufs; ++i) { mbar_init(&sm.stg_full[s][i], 2 * kGroupWarps); mbar_init(&sm.stg_empty[s][i], 1); }
+      mbar_init(&sm.act_ready[s], 2 * kGroupWarps);
+      mbar_init(&sm.acc_full[s], 1);
+      mbar_init(&sm.act_free[s], 1);
+    }
     fence_mbar_init();
   }
-  if (warp == kIssuerWarp) {
+  if (warp == kIssuerWarp0) {
     tmem_alloc_2cta(&sm.tmem_base, kTmemCols);
     tmem_relinquish_2cta();
   }
@@ -401,254 +351,262 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
   unsigned long long pacc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   const long long kernel_t0 = prof ? clock64() : 0;
 
-  if (warp == kProducerWarp) {
-    // ===================== weight producer (each CTA streams ITS N-half of every fill) =====================
+  if (warp >= kProducerWarp0 && warp < kProducerWarp0 + 2) {
+    // ===================== weight producer of slot s (each CTA streams ITS N-half of every fill) =====================
+    const int s = warp - kProducerWarp0;
+    const int n_slot = (n_local + 1 - s) / 2;
     if (lane == 0) {
       uint32_t stage = 0, wphase = 1;          // "empty" barriers start released
-      size_t layer_off[9];
-      { size_t o = 0; for (int L = 0; L < 9; ++L) { layer_off[L] = o; o += (size_t)pgn_layer_n(L) * pgn_layer_ksteps(L) * 32; } }
-      JobIter ji(n_local, kStage);
-      Job j;
-      while (ji.next(j)) {
-        const uint8_t* src = reinterpret_cast<const uint8_t*>(j.pass == 0 ? net_c.wstream : net_f.wstream) + layer_off[j.L];
-        const int nh = pgn_layer_n(j.L) / 2, ks_total = pgn_layer_ksteps(j.L), kpf = pgn_ks_per_fill(j.L);
-        for (int ks = 0; ks < ks_total; ks += kpf) {
-          const int nks = min(kpf, ks_total - ks);
-          const uint32_t bytes = (uint32_t)nks * nh * 32u;          // this CTA's half of the fill
-          { PROF_T0(); const bool okw = mbar_wait(&sm.w_empty[stage], wphase, status, 101); PROF_ADD(4); if (!okw) goto done; }
-          mbar_arrive_expect_tx(&sm.w_full[stage], bytes);
-          bulk_g2s(sm.wring[stage], src + (size_t)rank * bytes, bytes, &sm.w_full[stage]);
-          src += 2u * bytes;
-          if (++stage == kWStages) { stage = 0; wphase ^= 1; }
+      for (int i = 0; i < n_slot; ++i) {
+        for (int k = 0; k < kTiles; ++k) {
+          int pass, t;
+          tile_of(k, pass, t);
+          const uint8_t* wbase = reinterpret_cast<const uint8_t*>((kStage || pass == 0) ? net_c.wstream : net_f.wstream);
+          const uint8_t* src = wbase;          // layers are contiguous in consumption order
+          for (int L = 0; L < 9; ++L) {
+            const int nh = pgn_layer_n(L) / 2, ks_total = pgn_layer_ksteps(L), kpf = pgn_ks_per_fill(L);
+            for (int ks = 0; ks < ks_total; ks += kpf) {
+              const int nks = min(kpf, ks_total - ks);
+              const uint32_t bytes = (uint32_t)nks * nh * 32u;          // this CTA's half of the fill
+              { PROF_T0(); const bool okw = mbar_wait(&sm.w_empty[s][stage], wphase, status, 101); PROF_ADD(4); if (!okw) goto done; }
+              mbar_arrive_expect_tx(&sm.w_full[s][stage], bytes);
+              bulk_g2s(sm.wring[s][stage], src + (size_t)rank * bytes, bytes, &sm.w_full[s][stage]);
+              src += 2u * bytes;
+              if (++stage == kWStages) { stage = 0; wphase ^= 1; }
+            }
+          }
         }
       }
     }
-  } else if (warp == kIssuerWarp) {
-    if (lane == 0 && rank == 1) {
+  } else if (warp >= kIssuerWarp0) {
+    const int s = warp - kIssuerWarp0;
+    const int n_slot = (n_local + 1 - s) / 2;
+    if (rank == 1) {
       // ===================== peer relay: "my half of fill f has landed" -> leader's w_full =====================
-      uint32_t stage = 0, wphase = 0;
-      JobIter ji(n_local, kStage);
-      Job j;
-      while (ji.next(j)) {
-        const int ks_total = pgn_layer_ksteps(j.L), kpf = pgn_ks_per_fill(j.L);
-        for (int ks = 0; ks < ks_total; ks += kpf) {
-          if (!mbar_wait(&sm.w_full[stage], wphase, status, 401)) goto done;
-          mbar_arrive_cluster(&sm.w_full[stage], 0);
-          if (++stage == kWStages) { stage = 0; wphase ^= 1; }
-        }
+      if (lane == 0) {
+        uint32_t stage = 0, wphase = 0;
+        for (int i = 0; i < n_slot; ++i)
+          for (int k = 0; k < kTiles; ++k)
+            for (int L = 0; L < 9; ++L) {
+              const int ks_total = pgn_layer_ksteps(L), kpf = pgn_ks_per_fill(L);
+              for (int ks = 0; ks < ks_total; ks += kpf) {
+                if (!mbar_wait(&sm.w_full[s][stage], wphase, status, 401)) goto done;
+                mbar_arrive_cluster(&sm.w_full[s][stage], 0);
+                if (++stage == kWStages) { stage = 0; wphase ^= 1; }
+              }
+            }
       }
-    } else if (rank == 0) {
-      // ===================== MMA issuer (leader CTA): UMMA M=256 over both CTAs =====================
+    } else {
+      // ===================== MMA issuer of slot s (leader CTA): UMMA M=256 over both CTAs =====================
       // The whole warp runs this loop convergently; one elected lane issues each tcgen05 instruction.
-      // The loop is instruction-count critical (a single warp retires ~1 instruction per 5 cycles):
-      // descriptors advance by adding constants to their low words, ring stage / phases are carried
-      // incrementally, no division in the K loop, no timers.
       uint32_t stage = 0, wphase = 0;        // weight ring cursor
-      uint32_t stg_phase = 0;                // staging buffer phase
-      uint32_t posts0 = 0, posts1 = 0;       // POSTs of each slot already waited for
-      uint32_t jobs0 = 0, jobs1 = 0;         // jobs of each slot already issued
+      uint32_t sbuf = 0, sphase = 0;         // staging ring cursor
+      uint32_t jobs = 0;                     // jobs already issued (act_ready phase)
       const uint32_t kDescHi = (128u >> 4) | (1u << 14);                 // SBO = 128 B, descriptor version 1
       const uint32_t a_lbo = (uint32_t)(kRunBytes >> 4) << 16;           // A: LBO = 2048 B
-      const uint32_t stg_lo = (smem_u32(sm.stg) >> 4) | a_lbo;
+      const uint32_t act_lo = (smem_u32(sm.act[s]) >> 4) | a_lbo;
       const uint32_t ones_lo = (smem_u32(sm.ones) >> 4) | a_lbo;
-      const uint32_t ring_lo = smem_u32(sm.wring[0]) >> 4;
+      const uint32_t ring_lo = smem_u32(sm.wring[s][0]) >> 4;
+      const uint32_t tmem_acc = tmem_base + (uint32_t)s * 256u;
       constexpr uint32_t kAStep = (2 * kRunBytes) >> 4;                  // one K-step of A (two runs)
-      JobIter ji(n_local, kStage);
-      Job j;
-      while (ji.next(j)) {
-        const int s = j.slot, L = j.L;
-        const uint32_t n = pgn_layer_n(L), nh = n / 2;
-        const int ks_total = pgn_layer_ksteps(L), kpf = pgn_ks_per_fill(L);
-        const int ks_act = pgn_layer_kact(L) / 16;
-        const int chunk_ks = pgn_layer_chunk_ks(L);
-        const uint32_t idesc = umma_idesc_bf16(2 * kTM, n);
-        const uint32_t act_lo = (smem_u32(sm.act[s]) >> 4) | a_lbo;
-        const uint32_t b_lbo = ((nh * 16u) >> 4) << 16;                  // B: LBO = (N/2)*16 B
-        const uint32_t b_step = (nh * 32u) >> 4;                         // one K-step of this CTA's B half
-        const uint32_t tmem_acc = tmem_base + (uint32_t)s * 256u;
-        // the previous job of this slot must have been drained (its epilogue wrote act[s] / freed the accumulator)
-        const uint32_t njobs = s == 0 ? jobs0 : jobs1;
-        if (njobs > 0) {
-          const uint32_t ph = (s == 0 ? posts0 : posts1) & 1;
-          if (!mbar_wait_cluster(&sm.act_ready[s], ph, status, 201)) goto done;
-          if (s == 0) ++posts0; else ++posts1;
-          tc_fence_after_sync();
-        }
-        if (s == 0) ++jobs0; else ++jobs1;
-        int ks = 0, ce = 0;
-        uint32_t accum = 0;
-        while (ks < ks_total) {
-          // ---- one weight fill (kpf K-steps, fewer at the end of the layer)
-          if (!mbar_wait_cluster(&sm.w_full[stage], wphase, status, 202)) goto done;
-          tc_fence_after_sync();
-          uint32_t b_lo = (ring_lo + stage * (kWStageBytes >> 4)) | b_lbo;
-          const int ks_end = min(ks + kpf, ks_total);
-          for (; ks < ks_end; ++ks, b_lo += b_step) {
-            uint32_t a_lo;
-            bool chunk_end = false;
-            if (ks == ks_total - 1) {
-              a_lo = ones_lo;                                   // bias K-step
-            } else if (ks < ks_act) {
-              a_lo = act_lo + (uint32_t)ks * kAStep;
-            } else {
-              if (ce == 0) {
-                if (!mbar_wait_cluster(&sm.stg_full, stg_phase, status, 203)) goto done;
-                stg_phase ^= 1;
-                tc_fence_after_sync();
-              }
-              a_lo = stg_lo + (uint32_t)ce * kAStep;
-              if (++ce == chunk_ks) { ce = 0; chunk_end = true; }
+      for (int i = 0; i < n_slot; ++i) {
+        for (int k = 0; k < kTiles; ++k) {
+          for (int L = 0; L < 9; ++L) {
+            const uint32_t n = pgn_layer_n(L), nh = n / 2;
+            const int ks_total = pgn_layer_ksteps(L), kpf = pgn_ks_per_fill(L);
+            const int ks_act = pgn_layer_kact(L) / 16;
+            const int chunk_ks = pgn_layer_chunk_ks(L);
+            const bool has_chunks = pgn_layer_chunks(L) != 0;
+            const uint32_t idesc = umma_idesc_bf16(2 * kTM, n);
+            const uint32_t b_lbo = ((nh * 16u) >> 4) << 16;                  // B: LBO = (N/2)*16 B
+            const uint32_t b_step = (nh * 32u) >> 4;                         // one K-step of this CTA's B half
+            // the previous job of this slot must have been drained (its epilogue wrote act[s] / freed the accumulator)
+            if (jobs > 0) {
+              if (!mbar_wait_cluster(&sm.act_ready[s], (jobs - 1) & 1, status, 201)) goto done;
+              tc_fence_after_sync();
             }
-            umma_bf16_2cta_elect(tmem_acc, ((uint64_t)kDescHi << 32) | a_lo, ((uint64_t)kDescHi << 32) | b_lo, idesc, accum);
-            accum = 1;
-            if (chunk_end) umma_commit_2cta_elect(&sm.stg_empty);
+            ++jobs;
+            int ks = 0, ce = 0;
+            uint32_t accum = 0;
+            while (ks < ks_total) {
+              // ---- one weight fill (kpf K-steps, fewer at the end of the layer)
+              if (!mbar_wait_cluster(&sm.w_full[s][stage], wphase, status, 202)) goto done;
+              tc_fence_after_sync();
+              uint32_t b_lo = (ring_lo + stage * (kWStageBytes >> 4)) | b_lbo;
+              const int ks_end = min(ks + kpf, ks_total);
+              for (; ks < ks_end; ++ks, b_lo += b_step) {
+                uint32_t a_lo;
+                bool chunk_end = false;
+                if (ks == ks_total - 1) {
+                  a_lo = ones_lo;                                   // bias K-step
+                } else if (ks < ks_act) {
+                  a_lo = act_lo + (uint32_t)ks * kAStep;
+                } else {
+                  if (ce == 0) {
+                    if (!mbar_wait_cluster(&sm.stg_full[s][sbuf], sphase, status, 203)) goto done;
+                    tc_fence_after_sync();
+                  }
+                  a_lo = act_lo + sbuf * (uint32_t)(kStgBytes >> 4) + (uint32_t)ce * kAStep;
+                  if (++ce == chunk_ks) { ce = 0; chunk_end = true; }
+                }
+                umma_bf16_2cta_elect(tmem_acc, ((uint64_t)kDescHi << 32) | a_lo, ((uint64_t)kDescHi << 32) | b_lo, idesc, accum);
+                accum = 1;
+                if (chunk_end) {
+                  umma_commit_2cta_elect(&sm.stg_empty[s][sbuf]);
+                  if (++sbuf == kStgBufs) { sbuf = 0; sphase ^= 1; }
+                }
+                if (has_chunks && ks_act > 0 && ks == ks_act - 1) umma_commit_2cta_elect(&sm.act_free[s]);   // act[s] may be overwritten by chunks
+              }
+              umma_commit_2cta_elect(&sm.w_empty[s][stage]);
+              if (++stage == kWStages) { stage = 0; wphase ^= 1; }
+            }
+            umma_commit_2cta_elect(&sm.acc_full[s]);
           }
-          umma_commit_2cta_elect(&sm.w_empty[stage]);
-          if (++stage == kWStages) { stage = 0; wphase ^= 1; }
         }
-        umma_commit_2cta_elect(&sm.acc_full[s]);
       }
     }
   } else {
-    // ===================== compute groups =====================
-    // warps 0-7: ENCODE group (PRE of every job: generated A-operand chunks)
-    // warps 8-15: EPILOGUE group (POST of every job: accumulator drain, heads, compositing, resampling)
-    // Both walk the same static job order independently; they only meet through the issuer's barriers.
-    // (zf written by POST(V) of a coarse tile is read by PRE of fine tiles >= 3 tiles later in the order,
-    //  while the encode group can run at most ~2 jobs ahead of the epilogue group.)
-    const bool is_epi = warp >= kEpiWarp0;
-    const int gtid = is_epi ? tid - kEpiWarp0 * 32 : tid;     // thread index inside the group
+    // ===================== compute group of slot s =====================
+    // Runs the slot's tiles in order; per layer job: PRE (generated A-operand chunks), then POST
+    // (accumulator drain -> next layer's A operand / heads).  The compositing of tile n runs between
+    // POST(L0) and POST(L1) of tile n+1, i.e. while the tensor core works on that tile's first hidden layer.
+    const int s = warp >> 3;
+    const int n_slot = (n_local + 1 - s) / 2;
+    const int gtid = tid - s * kGroupThreads;     // thread index inside the group
     const int gwarp = gtid >> 5;
-    uint32_t stg_n = 0;
-    uint32_t accs[2] = {0, 0};
     const int row = gtid & (kTM - 1), half = gtid >> 7;
+    const uint32_t tmem_acc = tmem_base + (uint32_t)s * 256u;
+    const uint32_t act_saddr = smem_u32(sm.act[s]);
+    const bool timed = prof && s == 0;
+    uint32_t accs = 0, afree = 0;
+    uint32_t sbuf = 0, sphase = 1;                // staging ring cursor ("empty" barriers start released)
 
-    auto make_ctx = [&](const Job& j, TileCtx& tc, long long& unit) {
-      const long long u = cluster_id + (long long)j.g * n_clusters;
-      unit = 2 * u + rank;
-      tc.ray0 = unit * kRPG;
+    auto make_ctx = [&](int i, int k, TileCtx& tc) {
+      const long long q = 2ll * i + s;
+      const long long u = cluster_id + q * n_clusters;
+      tc.unit = 2 * u + rank;
+      tc.ray0 = tc.unit * kRPG;
       tc.nr = kStage ? 0 : (int)max(0ll, min((long long)kRPG, rays.n_rays - tc.ray0));
-      tc.pass = j.pass;
-      tc.S = j.pass == 0 ? PGN_S : PGN_T;
-      tc.row0 = j.t * kTM;
+      if (kStage) { tc.pass = 0; tc.t = 0; } else tile_of(k, tc.pass, tc.t);
+      tc.S = tc.pass == 0 ? PGN_S : PGN_T;
+      tc.row0 = tc.t * kTM;
       tc.total_rows = kStage ? kTM : tc.nr * tc.S;
-      tc.buf = j.g & 1;
       tc.tile_ray0 = min(tc.row0 / tc.S, kRPG - 1);
     };
 
-    // POST(job): drain the accumulator (epilogue); after the view layer also composite the finished rows
-    auto post = [&](const Job& j) -> bool {
-      const int s = j.slot;
-      const PgnBf16Net& net = j.pass == 0 ? net_c : net_f;
-      { PROF_T0(); const bool okw = mbar_wait(&sm.acc_full[s], accs[s] & 1, status, 303); PROF_ADD(9); if (!okw) return false; }
-      ++accs[s];
-      tc_fence_after_sync();
-      const uint32_t tmem_acc = tmem_base + (uint32_t)s * 256u;
-      { PROF_T0();
-        if (j.L == 8) epilogue<2>(sm, tmem_acc, s, net.w_alpha, net.w_rgb, gwarp, lane);
-        else if (j.L == 7) epilogue<1>(sm, tmem_acc, s, net.w_alpha, net.w_rgb, gwarp, lane);
-        else epilogue<0>(sm, tmem_acc, s, net.w_alpha, net.w_rgb, gwarp, lane);
-        compute_arrive(&sm.act_ready[s], lane); PROF_ADD(8); }
-      if (j.L != 8) return true;
-
-      PROF_T0();
-      TileCtx tc; long long unit;
-      make_ctx(j, tc, unit);
-      epi_bar_sync();
-      if (gtid < kTM) {       // head biases -> raw row (rgb_raw, sigma_raw) in part[s]
+    // ---- deferred compositing of a finished tile (raw rows of the tile are in part[s])
+    auto composite_tile = [&](const TileCtx& tc) {
+      const PgnBf16Net& net = tc.pass == 0 ? net_c : net_f;
+      group_bar_sync(s);                                   // every epilogue atomic of the tile has landed
+      if (gtid < kTM) {                                    // head biases -> raw row (rgb_raw, sigma_raw)
         float* p0 = sm.part[s][gtid];
         p0[0] += net.b_rgb[0];
         p0[1] += net.b_rgb[1];
         p0[2] += net.b_rgb[2];
         p0[3] += net.b_alpha[0];
-        if (kStage) {
-          const int rows_valid = (int)max(0ll, min((long long)kTM, enc_rows_total - unit * kTM));
-          if (gtid < rows_valid) {
-            float* o = raw_global + ((size_t)unit * kTM + gtid) * 4;
-            o[0] = p0[0]; o[1] = p0[1]; o[2] = p0[2]; o[3] = p0[3];
+      }
+      group_bar_sync(s);
+      if (tc.pass == 0) {
+        // coarse tile = 2 whole rays: composite, resample, merge -> zf; reset the fine carry
+        const int rl = 2 * tc.t + gwarp;
+        if (gwarp < 2 && rl < tc.nr) {
+          const long long ri = tc.ray0 + rl;
+          float* zc = sm.cscratch[s][gwarp];
+          float* wts = zc + 64;
+          float* scr = zc + 128;
+          const float nn = __ldg(near_far + ri * 2), ff = __ldg(near_far + ri * 2 + 1);
+          zc[lane] = pgn_coarse_z(nn, ff, sc.t_coarse[lane]);
+          zc[lane + 32] = pgn_coarse_z(nn, ff, sc.t_coarse[lane + 32]);
+          const float d0 = __ldg(rays.ray_batch + ri * 11 + 3), d1 = __ldg(rays.ray_batch + ri * 11 + 4), d2 = __ldg(rays.ray_batch + ri * 11 + 5);
+          const float dn = sqrtf(d0 * d0 + d1 * d1 + d2 * d2);
+          float* cr = sm.carry[s][rl];
+          if (lane < 8) cr[lane] = (lane == 0) ? 1.f : 0.f;
+          __syncwarp();
+          const float* rawrows = &sm.part[s][gwarp * PGN_S][0];
+          pgn_composite_segment_warp<PGN_S>(rawrows, zc, 0, PGN_S, dn, sc.density_scale, sc.rgb_eps, lane, cr, wts,
+                                            out.alpha0 ? out.alpha0 + ri * PGN_S : nullptr);
+          if (lane == 0) {
+            float rgb3[3], disp, acc;
+            pgn_composite_finalize(cr, rgb3, &disp, &acc);
+            if (out.rgb0) { out.rgb0[ri * 3] = rgb3[0]; out.rgb0[ri * 3 + 1] = rgb3[1]; out.rgb0[ri * 3 + 2] = rgb3[2]; }
+            if (out.disp0) out.disp0[ri] = disp;
+            if (out.acc0) out.acc0[ri] = acc;
+          }
+          __syncwarp();
+          if (lane < 8) cr[lane] = (lane == 0) ? 1.f : 0.f;      // carry now belongs to the fine pass of this ray
+          if (out.weights0) { out.weights0[ri * PGN_S + lane] = wts[lane]; out.weights0[ri * PGN_S + lane + 32] = wts[lane + 32]; }
+          if (out.raw0) for (int i = lane; i < PGN_S * 4; i += 32) out.raw0[ri * PGN_S * 4 + i] = rawrows[i];
+          pgn_sample_pdf_warp(zc, wts, sc.u_det, lane, scr, out.z_samples ? out.z_samples + ri * PGN_I : nullptr,
+                              sm.zf[s][rl], out.pdf_inds ? out.pdf_inds + ri * PGN_I : nullptr, nullptr);
+          if (out.z_fine) for (int i = lane; i < PGN_T; i += 32) out.z_fine[ri * PGN_T + i] = sm.zf[s][rl][i];
+        }
+      } else {
+        // fine tile: rows [row0, row0+128) cut up to 3 rays; continue each ray's compositing
+        const int rl = tc.tile_ray0 + gwarp;
+        if (gwarp < kMaxTileRays && rl < tc.nr && rl * PGN_T < tc.row0 + kTM) {
+          const long long ri = tc.ray0 + rl;
+          const int s0 = max(0, tc.row0 - rl * PGN_T), s1 = min(PGN_T, tc.row0 + kTM - rl * PGN_T);
+          const float d0 = __ldg(rays.ray_batch + ri * 11 + 3), d1 = __ldg(rays.ray_batch + ri * 11 + 4), d2 = __ldg(rays.ray_batch + ri * 11 + 5);
+          const float dn = sqrtf(d0 * d0 + d1 * d1 + d2 * d2);
+          float* cr = sm.carry[s][rl];
+          const float* rawrows = &sm.part[s][rl * PGN_T + s0 - tc.row0][0];
+          pgn_composite_segment_warp<PGN_T>(rawrows, sm.zf[s][rl], s0, s1, dn, sc.density_scale, sc.rgb_eps, lane, cr,
+                                            nullptr, out.alpha ? out.alpha + ri * PGN_T : nullptr);
+          if (out.raw) for (int i = lane; i < (s1 - s0) * 4; i += 32) out.raw[(ri * PGN_T + s0) * 4 + i] = rawrows[i];
+          if (s1 == PGN_T && lane == 0) {
+            float rgb3[3], disp, acc;
+            pgn_composite_finalize(cr, rgb3, &disp, &acc);
+            if (out.rgb_map) { out.rgb_map[ri * 3] = rgb3[0]; out.rgb_map[ri * 3 + 1] = rgb3[1]; out.rgb_map[ri * 3 + 2] = rgb3[2]; }
+            if (out.disp_map) out.disp_map[ri] = disp;
+            if (out.acc_map) out.acc_map[ri] = acc;
           }
         }
       }
-      epi_bar_sync();
-      if (!kStage) {
-        if (j.pass == 0) {
-          // coarse tile = 2 whole rays: composite, resample, merge -> zf ring; reset the fine carry
-          const int rl = 2 * j.t + gwarp;
-          if (gwarp < 2 && rl < tc.nr) {
-            const long long ri = tc.ray0 + rl;
-            float* zc = sm.cscratch[gwarp];
-            float* wts = zc + 64;
-            float* scr = zc + 128;
-            const float nn = __ldg(near_far + ri * 2), ff = __ldg(near_far + ri * 2 + 1);
-            zc[lane] = pgn_coarse_z(nn, ff, sc.t_coarse[lane]);
-            zc[lane + 32] = pgn_coarse_z(nn, ff, sc.t_coarse[lane + 32]);
-            const float d0 = __ldg(rays.ray_batch + ri * 11 + 3), d1 = __ldg(rays.ray_batch + ri * 11 + 4), d2 = __ldg(rays.ray_batch + ri * 11 + 5);
-            const float dn = sqrtf(d0 * d0 + d1 * d1 + d2 * d2);
-            float* cr = sm.carry[tc.buf][rl];
-            if (lane < 8) cr[lane] = (lane == 0) ? 1.f : 0.f;
-            __syncwarp();
-            const float* rawrows = &sm.part[s][gwarp * PGN_S][0];
-            pgn_composite_segment_warp<PGN_S>(rawrows, zc, 0, PGN_S, dn, sc.density_scale, sc.rgb_eps, lane, cr, wts,
-                                              out.alpha0 ? out.alpha0 + ri * PGN_S : nullptr);
-            if (lane == 0) {
-              float rgb3[3], disp, acc;
-              pgn_composite_finalize(cr, rgb3, &disp, &acc);
-              if (out.rgb0) { out.rgb0[ri * 3] = rgb3[0]; out.rgb0[ri * 3 + 1] = rgb3[1]; out.rgb0[ri * 3 + 2] = rgb3[2]; }
-              if (out.disp0) out.disp0[ri] = disp;
-              if (out.acc0) out.acc0[ri] = acc;
-            }
-            __syncwarp();
-            if (lane < 8) cr[lane] = (lane == 0) ? 1.f : 0.f;      // carry now belongs to the fine pass of this ray
-            if (out.weights0) { out.weights0[ri * PGN_S + lane] = wts[lane]; out.weights0[ri * PGN_S + lane + 32] = wts[lane + 32]; }
-            if (out.raw0) for (int i = lane; i < PGN_S * 4; i += 32) out.raw0[ri * PGN_S * 4 + i] = rawrows[i];
-            pgn_sample_pdf_warp(zc, wts, sc.u_det, lane, scr, out.z_samples ? out.z_samples + ri * PGN_I : nullptr,
-                                sm.zf[tc.buf][rl], out.pdf_inds ? out.pdf_inds + ri * PGN_I : nullptr, nullptr);
-            if (out.z_fine) for (int i = lane; i < PGN_T; i += 32) out.z_fine[ri * PGN_T + i] = sm.zf[tc.buf][rl][i];
-          }
-        } else {
-          // fine tile: rows [row0, row0+128) cut up to 3 rays; continue each ray's compositing
-          const int rl = tc.tile_ray0 + gwarp;
-          if (gwarp < kMaxTileRays && rl < tc.nr && rl * PGN_T < tc.row0 + kTM) {
-            const long long ri = tc.ray0 + rl;
-            const int s0 = max(0, tc.row0 - rl * PGN_T), s1 = min(PGN_T, tc.row0 + kTM - rl * PGN_T);
-            const float d0 = __ldg(rays.ray_batch + ri * 11 + 3), d1 = __ldg(rays.ray_batch + ri * 11 + 4), d2 = __ldg(rays.ray_batch + ri * 11 + 5);
-            const float dn = sqrtf(d0 * d0 + d1 * d1 + d2 * d2);
-            float* cr = sm.carry[tc.buf][rl];
-            const float* rawrows = &sm.part[s][rl * PGN_T + s0 - tc.row0][0];
-            pgn_composite_segment_warp<PGN_T>(rawrows, sm.zf[tc.buf][rl], s0, s1, dn, sc.density_scale, sc.rgb_eps, lane, cr,
-                                              nullptr, out.alpha ? out.alpha + ri * PGN_T : nullptr);
-            if (out.raw) for (int i = lane; i < (s1 - s0) * 4; i += 32) out.raw[(ri * PGN_T + s0) * 4 + i] = rawrows[i];
-            if (s1 == PGN_T && lane == 0) {
-              float rgb3[3], disp, acc;
-              pgn_composite_finalize(cr, rgb3, &disp, &acc);
-              if (out.rgb_map) { out.rgb_map[ri * 3] = rgb3[0]; out.rgb_map[ri * 3 + 1] = rgb3[1]; out.rgb_map[ri * 3 + 2] = rgb3[2]; }
-              if (out.disp_map) out.disp_map[ri] = disp;
-              if (out.acc_map) out.acc_map[ri] = acc;
-            }
-          }
-        }
-      }
-      epi_bar_sync();
+      group_bar_sync(s);
       if (gtid < kTM) *reinterpret_cast<float4*>(sm.part[s][gtid]) = make_float4(0.f, 0.f, 0.f, 0.f);   // next tile of this slot
-      PROF_ADD(11);
+      group_bar_sync(s);
+    };
+
+    // ---- POST(job): drain the accumulator (epilogue)
+    auto post = [&](int L, const TileCtx& tc) -> bool {
+      const PgnBf16Net& net = (kStage || tc.pass == 0) ? net_c : net_f;
+      { PROF_T0(); const bool okw = mbar_wait(&sm.acc_full[s], accs & 1, status, 303); if (timed) PROF_ADD(9); if (!okw) return false; }
+      ++accs;
+      tc_fence_after_sync();
+      { PROF_T0();
+        if (L == 8) epilogue<2>(sm, tmem_acc, act_saddr, s, net.w_alpha, net.w_rgb, gwarp, lane);
+        else if (L == 7) epilogue<1>(sm, tmem_acc, act_saddr, s, net.w_alpha, net.w_rgb, gwarp, lane);
+        else epilogue<0>(sm, tmem_acc, act_saddr, s, net.w_alpha, net.w_rgb, gwarp, lane);
+        compute_arrive(&sm.act_ready[s], lane); if (timed) PROF_ADD(8); }
+      if (kStage && L == 8) {
+        group_bar_sync(s);
+        if (gtid < kTM) {
+          float* p0 = sm.part[s][gtid];
+          const int rows_valid = (int)max(0ll, min((long long)kTM, enc_rows_total - tc.unit * kTM));
+          if (gtid < rows_valid) {
+            float* o = raw_global + ((size_t)tc.unit * kTM + gtid) * 4;
+            o[0] = p0[0] + net.b_rgb[0]; o[1] = p0[1] + net.b_rgb[1]; o[2] = p0[2] + net.b_rgb[2]; o[3] = p0[3] + net.b_alpha[0];
+          }
+          *reinterpret_cast<float4*>(p0) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        group_bar_sync(s);
+      }
       return true;
     };
 
-    // PRE(job): everything the tensor core needs from the CUDA cores before/while it runs the layer
-    auto pre = [&](const Job& j) -> bool {
-      const int nchunks = pgn_layer_chunks(j.L);
+    // ---- PRE(job): everything the tensor core needs from the CUDA cores before/while it runs the layer
+    auto pre = [&](int L, const TileCtx& tc) -> bool {
+      const int nchunks = pgn_layer_chunks(L);
       if (nchunks == 0) return true;
-      TileCtx tc; long long unit;
-      make_ctx(j, tc, unit);
-      const float* enc_rows = kStage ? enc_global + (size_t)unit * kTM * PGN_ENC : nullptr;
-      const int rows_valid = kStage ? (int)max(0ll, min((long long)kTM, enc_rows_total - unit * kTM)) : kTM;
-      if (!kStage && j.L == 0) {
+      const float* enc_rows = kStage ? enc_global + (size_t)tc.unit * kTM * PGN_ENC : nullptr;
+      const int rows_valid = kStage ? (int)max(0ll, min((long long)kTM, enc_rows_total - tc.unit * kTM)) : kTM;
+      if (!kStage && L == 0) {
         // PE table of the joint-frame view directions for the <=3 rays of this tile (used by the V layer)
         const int tile_ray1 = min((tc.row0 + kTM - 1) / tc.S, tc.nr - 1);
-        for (int i = gtid; i < kMaxTileRays * PGN_J; i += kComputeThreads) {
+        for (int i = gtid; i < kMaxTileRays * PGN_J; i += kGroupThreads) {
           const int tr = i / PGN_J, jn = i % PGN_J;
           const int rl = tc.tile_ray0 + tr;
-          __half* tab = &sm.dtab[j.slot][tr][jn * 32];
+          __half* tab = &sm.dtab[s][tr][jn * 32];
           if (rl <= tile_ray1) {
             const long long ri = tc.ray0 + rl;
             const float4* m = reinterpret_cast<const float4*>(pgn_ray_skts(rays, ri) + jn * 16);
@@ -661,48 +619,63 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
           }
         }
       }
-      if (j.L == 8) encode_bar_sync();       // wcache (L5's encode) and dtab (L0's PRE) visible to every thread
+      if (L == 8) group_bar_sync(s);         // wcache (L5's encode) and dtab (L0's PRE) visible to every thread
       RowCtx rc;
       rc.valid = false; rc.px = rc.py = rc.pz = 0.f; rc.skt = rays.skts;
-      if (!kStage && j.L != 8) rc = make_row_ctx(sm, rays, sc, tc, near_far, row);
+      if (!kStage && L != 8) rc = make_row_ctx(sm, rays, sc, tc, near_far, s, row);
       // software pipeline: the values of chunk c+1 are computed while chunk c travels through the
-      // staging buffer / tensor core; only the 16-byte stores wait for the buffer to be released
+      // staging ring / tensor core; only the 16-byte stores wait for a ring buffer to be released
       uint32_t packed[20];
       auto compute_chunk = [&](int c) {
-        if (j.L == 8) { PROF_T0(); encode_d_compute<kStage>(sm, tc, j.slot, c, row, half, enc_rows, rows_valid, packed); PROF_ADD(7); }
-        else { PROF_T0(); encode_x_compute<kStage>(sm, sc, rc, j.slot, c, row, half, j.L == 5, enc_rows, rows_valid, packed); PROF_ADD(6); }
+        if (L == 8) { PROF_T0(); encode_d_compute<kStage>(sm, tc, s, c, row, half, enc_rows, rows_valid, packed); if (timed) PROF_ADD(7); }
+        else { PROF_T0(); encode_x_compute<kStage>(sm, sc, rc, s, c, row, half, L == 5, enc_rows, rows_valid, packed); if (timed) PROF_ADD(6); }
       };
       compute_chunk(0);
+      if (L != 0) {      // the activation K-steps of this layer must have been consumed before act[s] becomes the staging ring
+        PROF_T0(); const bool okw = mbar_wait(&sm.act_free[s], afree & 1, status, 302); if (timed) PROF_ADD(13); if (!okw) return false;
+        ++afree;
+      }
       for (int c = 0; c < nchunks; ++c) {
-        { PROF_T0(); const bool okw = mbar_wait(&sm.stg_empty, (stg_n & 1) ^ 1, status, 301); PROF_ADD(10); if (!okw) return false; }
+        { PROF_T0(); const bool okw = mbar_wait(&sm.stg_empty[s][sbuf], sphase, status, 301); if (timed) PROF_ADD(10); if (!okw) return false; }
         { PROF_T0();
-          if (j.L == 8) encode_d_store(sm, row, half, packed); else encode_x_store(sm, row, half, packed);
-          compute_arrive(&sm.stg_full, lane); PROF_ADD(15); }
-        ++stg_n;
+          const uint32_t stg = act_saddr + sbuf * (uint32_t)kStgBytes;
+          if (L == 8) encode_d_store(stg, row, half, packed); else encode_x_store(stg, row, half, packed);
+          compute_arrive(&sm.stg_full[s][sbuf], lane); if (timed) PROF_ADD(15); }
+        if (++sbuf == kStgBufs) { sbuf = 0; sphase ^= 1; }
         if (c + 1 < nchunks) compute_chunk(c + 1);
       }
       return true;
     };
 
-    JobIter ji(n_local, kStage);
-    Job j;
-    if (is_epi) { while (ji.next(j)) { if (!post(j)) goto done; } }
-    else { while (ji.next(j)) { if (!pre(j)) goto done; } }
+    TileCtx tc, prev;
+    bool pending = false;
+    for (int i = 0; i < n_slot; ++i) {
+      for (int k = 0; k < kTiles; ++k) {
+        make_ctx(i, k, tc);
+        for (int L = 0; L < 9; ++L) {
+          if (!pre(L, tc)) goto done;
+          if (!kStage && L == 1 && pending) { PROF_T0(); composite_tile(prev); if (timed) PROF_ADD(11); pending = false; }
+          if (!post(L, tc)) goto done;
+        }
+        if (!kStage) { prev = tc; pending = true; }
+      }
+    }
+    if (pending) composite_tile(prev);
   }
 done:
   if (prof) {
     unsigned long long* pp = prof + (size_t)blockIdx.x * 16;
     const unsigned long long total = (unsigned long long)(clock64() - kernel_t0);
-    if (warp == kIssuerWarp && lane == 0) { pp[0] = pacc[0]; pp[1] = pacc[1]; pp[2] = pacc[2]; pp[3] = total; }
-    if (warp == kProducerWarp && lane == 0) { pp[4] = pacc[4]; pp[5] = total; }
-    if (tid == 0) { pp[6] = pacc[6]; pp[7] = pacc[7]; pp[10] = pacc[10]; pp[12] = total; pp[15] = pacc[15]; }
-    if (tid == kEpiWarp0 * 32) { pp[8] = pacc[8]; pp[9] = pacc[9]; pp[11] = pacc[11]; }
+    if (warp == kIssuerWarp0 && lane == 0) { pp[0] = 0; pp[1] = 0; pp[2] = 0; pp[3] = total; }
+    if (warp == kProducerWarp0 && lane == 0) { pp[4] = pacc[4]; pp[5] = total; }
+    if (tid == 0) { pp[6] = pacc[6]; pp[7] = pacc[7]; pp[8] = pacc[8]; pp[9] = pacc[9]; pp[10] = pacc[10]; pp[11] = pacc[11];
+                    pp[12] = total; pp[13] = pacc[13]; pp[15] = pacc[15]; }
   }
   tc_fence_before_sync();
   __syncthreads();
   __syncwarp();
   cluster_sync_all();                 // the peer's TMEM/smem must stay alive until every MMA has retired
-  if (warp == kIssuerWarp) {
+  if (warp == kIssuerWarp0) {
     tc_fence_after_sync();
     tmem_dealloc_2cta(tmem_base, kTmemCols);
   }

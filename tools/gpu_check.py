@@ -185,9 +185,9 @@ def step_phases(eng, precisions=("bf16",)):
         torch.cuda.synchronize()
     t = eng.phase_timers(False, read=True)
     n = rb.shape[0]
-    tiles_per_cta = (n / 8) * 9 / 148
-    log("phases", ms=round(e0.elapsed_time(e1), 3), n_rays=n, tiles_per_cta=round(tiles_per_cta, 1),
-        **{k: round(v / tiles_per_cta) for k, v in t.items()})
+    tiles_per_slot = (n / 8) * 9 / 148 / 2          # timers cover pipeline slot 0 of every CTA
+    log("phases", ms=round(e0.elapsed_time(e1), 3), n_rays=n, tiles_per_slot=round(tiles_per_slot, 1),
+        **{k: round(v / tiles_per_slot) for k, v in t.items()})
 
 
 STEPS = {"phases": step_phases, "probe": step_probe, "stages": step_stages, "mlp": step_mlp, "render": step_render, "time": step_time}
