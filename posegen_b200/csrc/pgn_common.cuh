@@ -324,10 +324,9 @@ __device__ __forceinline__ void pgn_composite_finalize(const float* carry, float
 // rounded once to fp32 (torch CPU cumsum accumulates float in double).
 // The search is a warp ballot: ind = #{k : cdf[k] <= u}.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void pgn_sample_pdf_warp(const float* __restrict__ z, const float* __restrict__ weights,
-                                                    const float* __restrict__ u_det, int lane, float* scratch,
-                                                    float* z_samples, float* z_sorted,
-                                                    int* pdf_inds, int* sorted_idxs) {
+// part 1: pdf -> cdf[63] | bins[63] in scratch (2 x 64 floats)
+__device__ __forceinline__ void pgn_sample_pdf_cdf_warp(const float* __restrict__ z, const float* __restrict__ weights,
+                                                        int lane, float* scratch) {
   float* cdf = scratch;        // [63] (+1 pad)
   float* bins = scratch + 64;  // [63]
   // pdf over the 62 interior weights; lane handles k = lane and lane+32
@@ -361,6 +360,14 @@ __device__ __forceinline__ void pgn_sample_pdf_warp(const float* __restrict__ z,
   bins[lane] = __fmul_rn(0.5f, __fadd_rn(z[lane + 1], z[lane]));
   if (lane + 32 < 63) bins[lane + 32] = __fmul_rn(0.5f, __fadd_rn(z[lane + 33], z[lane + 32]));
   __syncwarp();
+}
+
+// part 2: inverse-CDF draw at u_det, merge with the coarse z (scratch as left by part 1)
+__device__ __forceinline__ void pgn_sample_pdf_draw_warp(const float* __restrict__ z, const float* __restrict__ u_det, int lane,
+                                                         float* scratch, float* z_samples, float* z_sorted,
+                                                         int* pdf_inds, int* sorted_idxs) {
+  float* cdf = scratch;
+  float* bins = scratch + 64;
   const float ca = cdf[lane];
   const float cb = (lane + 32 < 63) ? cdf[lane + 32] : INFINITY;
   float my_sample = 0.0f;
@@ -402,4 +409,12 @@ __device__ __forceinline__ void pgn_sample_pdf_warp(const float* __restrict__ z,
     if (sorted_idxs) sorted_idxs[r] = PGN_S + lane;
   }
   __syncwarp();
+}
+
+__device__ __forceinline__ void pgn_sample_pdf_warp(const float* __restrict__ z, const float* __restrict__ weights,
+                                                    const float* __restrict__ u_det, int lane, float* scratch,
+                                                    float* z_samples, float* z_sorted,
+                                                    int* pdf_inds, int* sorted_idxs) {
+  pgn_sample_pdf_cdf_warp(z, weights, lane, scratch);
+  pgn_sample_pdf_draw_warp(z, u_det, lane, scratch, z_samples, z_sorted, pdf_inds, sorted_idxs);
 }

@@ -70,6 +70,7 @@ struct __align__(128) Smem {
   uint8_t wring[2][kWStages][kWStageBytes];      // per slot: weight ring (this CTA's N half)
   __half wcache[2][PGN_J * kTM];                 // d-window per (joint,row), per slot
   __half dtab[2][kMaxTileRays][PGN_J * 32];      // PE of joint-frame view dirs per ray of the tile (27 + 5 zeros)
+  float jtab[2][kMaxTileRays][PGN_J][8];         // per (tile ray, joint): a = R o + t, b = R d, window offsets (see encode)
   float zf[2][kRPG][PGN_T];                      // merged z of the fine pass of the slot's current ray group
   float carry[2][kRPG][8];                       // incremental compositing state of the fine rays
   float part[2][kTM][4];                         // per slot: raw rows (rgb_raw, sigma_raw), accumulated by both column halves
@@ -101,78 +102,94 @@ struct TileCtx {
 };
 
 // ------------------------------------------------------------------ encode (compute group)
-// x chunk c (joints 4c..4c+3): thread (row, half) produces joints 4c+2*half, +1 -> 36 values + 4 zeros
-// = 5 runs of 8 at run index half*5+r.
-struct RowCtx { bool valid; float px, py, pz; const float* skt; };
+// Per tile, PRE(L0) builds two small tables for the <=3 rays the tile touches:
+//   jtab[ray][joint] = { a = R_j o + t_j, b = R_j d, -tau_v c_j log2e, -tau_d c_j log2e }   (8 floats)
+//       so that a sample's joint-local position is a + z b (3 FMAs) instead of a 3x4 transform of o + z d;
+//   dtab[ray][joint] = PE of the normalised joint-frame view direction (27 halfs + 5 zeros).
+// Row state (valid, z, tile-ray index) is computed once per tile and reused by L0, L5 and V.
+struct RowCtx { bool valid; int tr; float z; };
 
-// per-row state shared by all chunks of one layer: sample position and the pose's transforms
-__device__ __forceinline__ RowCtx make_row_ctx(const Smem& sm, const PgnRayRefs& rays, const PgnScalars& sc, const TileCtx& tc,
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__device__ __forceinline__ RowCtx make_row_ctx(const Smem& sm, const PgnScalars& sc, const TileCtx& tc,
                                                const float* __restrict__ near_far, int slot, int row) {
   RowCtx rc;
   const int grow = tc.row0 + row;
   rc.valid = grow < tc.total_rows;
-  rc.px = rc.py = rc.pz = 0.f;
-  rc.skt = rays.skts;
+  rc.tr = 0;
+  rc.z = 0.f;
   if (rc.valid) {
     const int rl = grow / tc.S, s = grow - rl * tc.S;
     const long long ri = tc.ray0 + rl;
-    const float* rb = rays.ray_batch + ri * 11;
-    const float o[3] = {__ldg(rb), __ldg(rb + 1), __ldg(rb + 2)};
-    const float d[3] = {__ldg(rb + 3), __ldg(rb + 4), __ldg(rb + 5)};
-    const float z = (tc.pass == 0) ? pgn_coarse_z(__ldg(near_far + ri * 2), __ldg(near_far + ri * 2 + 1), sc.t_coarse[s])
-                                   : sm.zf[slot][rl][s];
-    pgn_sample_point(o, d, z, rc.px, rc.py, rc.pz);
-    rc.skt = pgn_ray_skts(rays, ri);
+    rc.tr = rl - tc.tile_ray0;
+    rc.z = (tc.pass == 0) ? pgn_coarse_z(__ldg(near_far + ri * 2), __ldg(near_far + ri * 2 + 1), sc.t_coarse[s])
+                          : sm.zf[slot][rl][s];
   }
   return rc;
 }
 
-template <bool kStage>
-__device__ __forceinline__ void encode_x_compute(Smem& sm, const PgnScalars& sc, const RowCtx& rc, int slot, int chunk, int row, int half,
-                                                 bool write_wcache, const float* __restrict__ enc_rows, int rows_valid,
-                                                 uint32_t (&packed)[20]) {
-  if (kStage) {
-#pragma unroll
-    for (int i = 0; i < 20; ++i) {
-      const int kp = chunk * PGN_X_CHUNK_K + half * 40 + 2 * i;
-      const int ca = pgn_xperm_refcol(kp), cb = pgn_xperm_refcol(kp + 1);
-      float a = 0.f, b = 0.f;
-      if (row < rows_valid) {
-        if (ca >= 0) a = enc_rows[(size_t)row * PGN_ENC + ca];
-        if (cb >= 0) b = enc_rows[(size_t)row * PGN_ENC + cb];
-      }
-      packed[i] = pack_bf16x2(a, b);
-    }
-  } else {
+// x chunk c (joints 4c..4c+3): thread (row, half) produces joints 4c+2*half, +1 -> 36 values + 4 zeros
+// = 5 runs of 8 at run index half*5+r.  The valid path is one basic block so the two joints interleave.
+template <bool kWriteW>
+__device__ __forceinline__ void encode_x_fast(Smem& sm, uint32_t jtab_saddr, const RowCtx& rc, float tau_v2, float tau_d2,
+                                              int slot, int chunk, int row, int half, uint32_t (&packed)[20]) {
+  const int j0 = chunk * 4 + half * 2;
+  if (rc.valid) {
+    const uint32_t jt = jtab_saddr + (uint32_t)(rc.tr * PGN_J + j0) * 32u;
 #pragma unroll
     for (int jj = 0; jj < 2; ++jj) {
-      const int j = chunk * 4 + half * 2 + jj;
-      float vals[18];
-      if (rc.valid) {
-        const float4* m = reinterpret_cast<const float4*>(rc.skt + j * 16);
-        const PgnJointGeom g = pgn_joint_geom<true>(__ldg(m), __ldg(m + 1), __ldg(m + 2), rc.px, rc.py, rc.pz, sc.tau_v, sc.cutoff_v[j]);
-        if (write_wcache) sm.wcache[slot][j * kTM + row] = __float2half_rn(pgn_window<true>(g.v, sc.tau_d, sc.cutoff_d[j]));
-        float sn, cs;
-        __sincosf(g.v, &sn, &cs);
-        vals[0] = g.v * g.w;
-#pragma unroll
-        for (int f = 0; f < PGN_LV; ++f) {
-          vals[1 + 2 * f] = sn * g.w;
-          vals[2 + 2 * f] = cs * g.w;
-          const float s2 = 2.f * sn * cs;
-          const float c2 = fmaf(cs, cs, -sn * sn);
-          sn = s2; cs = c2;
-        }
-        vals[15] = g.rx; vals[16] = g.ry; vals[17] = g.rz;
-      } else {
-        if (write_wcache) sm.wcache[slot][j * kTM + row] = __float2half_rn(0.f);
-#pragma unroll
-        for (int i = 0; i < 18; ++i) vals[i] = 0.f;
+      const uint4 qa = lds128(jt + jj * 32), qb = lds128(jt + jj * 32 + 16);
+      const float x = fmaf(rc.z, __uint_as_float(qa.w), __uint_as_float(qa.x));
+      const float y = fmaf(rc.z, __uint_as_float(qb.x), __uint_as_float(qa.y));
+      const float z = fmaf(rc.z, __uint_as_float(qb.y), __uint_as_float(qa.z));
+      const float n2 = fmaf(z, z, fmaf(y, y, x * x));
+      const float rsq = rsqrtf(fmaxf(n2, 1e-24f));
+      const float v = n2 * rsq;
+      const float w = __fdividef(1.0f, 1.0f + ex2_approx(fmaf(tau_v2, v, __uint_as_float(qb.z))));   // 1 - sigmoid(tau (v - c))
+      if (kWriteW) {
+        const float wd = __fdividef(1.0f, 1.0f + ex2_approx(fmaf(tau_d2, v, __uint_as_float(qb.w))));
+        sm.wcache[slot][(j0 + jj) * kTM + row] = __float2half_rn(wd);
       }
+      float sn, cs;
+      __sincosf(v, &sn, &cs);
+      float vals[18];
+      vals[0] = v * w;
+#pragma unroll
+      for (int f = 0; f < PGN_LV; ++f) {
+        vals[1 + 2 * f] = sn * w;
+        vals[2 + 2 * f] = cs * w;
+        const float s2 = 2.f * sn * cs;
+        const float c2 = fmaf(cs, cs, -sn * sn);
+        sn = s2; cs = c2;
+      }
+      vals[15] = x * rsq; vals[16] = y * rsq; vals[17] = z * rsq;
 #pragma unroll
       for (int i = 0; i < 9; ++i) packed[jj * 9 + i] = pack_bf16x2(vals[2 * i], vals[2 * i + 1]);
     }
-    packed[18] = 0u; packed[19] = 0u;
+  } else {
+    if (kWriteW) { sm.wcache[slot][j0 * kTM + row] = __float2half_rn(0.f); sm.wcache[slot][(j0 + 1) * kTM + row] = __float2half_rn(0.f); }
+#pragma unroll
+    for (int i = 0; i < 18; ++i) packed[i] = 0u;
+  }
+  packed[18] = 0u; packed[19] = 0u;
+}
+// stage mode (pgn_mlp): the A operand comes from explicit encodings in global memory
+__device__ __forceinline__ void encode_x_stage(int chunk, int row, int half, const float* __restrict__ enc_rows, int rows_valid,
+                                               uint32_t (&packed)[20]) {
+#pragma unroll
+  for (int i = 0; i < 20; ++i) {
+    const int kp = chunk * PGN_X_CHUNK_K + half * 40 + 2 * i;
+    const int ca = pgn_xperm_refcol(kp), cb = pgn_xperm_refcol(kp + 1);
+    float a = 0.f, b = 0.f;
+    if (row < rows_valid) {
+      if (ca >= 0) a = enc_rows[(size_t)row * PGN_ENC + ca];
+      if (cb >= 0) b = enc_rows[(size_t)row * PGN_ENC + cb];
+    }
+    packed[i] = pack_bf16x2(a, b);
   }
 }
 __device__ __forceinline__ void encode_x_store(uint32_t stg, int row, int half, const uint32_t (&packed)[20]) {
@@ -183,40 +200,35 @@ __device__ __forceinline__ void encode_x_store(uint32_t stg, int row, int half, 
 
 // d chunk c (joints 2c, 2c+1): thread (row, half) produces joint 2c+half -> 27 values + 5 zeros
 // = 4 runs at run index half*4+r.
-template <bool kStage>
-__device__ __forceinline__ void encode_d_compute(Smem& sm, const TileCtx& tc, int slot, int chunk, int row, int half,
-                                                 const float* __restrict__ enc_rows, int rows_valid, uint32_t (&packed)[20]) {
-  if (kStage) {
+__device__ __forceinline__ void encode_d_fast(Smem& sm, uint32_t dtab_saddr, const RowCtx& rc, int slot, int chunk, int row, int half,
+                                              uint32_t (&packed)[20]) {
+  const int j = chunk * 2 + half;
+  const float wd = rc.valid ? __half2float(sm.wcache[slot][j * kTM + row]) : 0.f;
+  const uint32_t tab = dtab_saddr + (uint32_t)(rc.tr * PGN_J + j) * 64u;   // 32 halfs = 4 x 16 B
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const int q = chunk * PGN_D_CHUNK_K + half * 32 + 2 * i;
-      const int ca = pgn_dperm_refcol(q), cb = pgn_dperm_refcol(q + 1);
-      float a = 0.f, b = 0.f;
-      if (row < rows_valid) {
-        if (ca >= 0) a = enc_rows[(size_t)row * PGN_ENC + ca];
-        if (cb >= 0) b = enc_rows[(size_t)row * PGN_ENC + cb];
-      }
-      packed[i] = pack_bf16x2(a, b);
+  for (int i = 0; i < 4; ++i) {
+    const uint4 t = lds128(tab + i * 16);
+    const uint32_t w4[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const __half2 h2 = *reinterpret_cast<const __half2*>(&w4[e]);
+      const float2 f2 = __half22float2(h2);
+      packed[i * 4 + e] = pack_bf16x2(f2.x * wd, f2.y * wd);
     }
-  } else {
-    const int grow = tc.row0 + row;
-    const bool valid = grow < tc.total_rows;
-    const int rl = valid ? grow / tc.S : tc.tile_ray0;
-    const int tr = min(max(rl - tc.tile_ray0, 0), kMaxTileRays - 1);
-    const int j = chunk * 2 + half;
-    const float wd = valid ? __half2float(sm.wcache[slot][j * kTM + row]) : 0.f;
-    const uint32_t tab = smem_u32(&sm.dtab[slot][tr][j * 32]);   // 32 halfs = 4 x 16 B
+  }
+}
+__device__ __forceinline__ void encode_d_stage(int chunk, int row, int half, const float* __restrict__ enc_rows, int rows_valid,
+                                               uint32_t (&packed)[20]) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const uint4 t = lds128(tab + i * 16);
-      const uint32_t w4[4] = {t.x, t.y, t.z, t.w};
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const __half2 h2 = *reinterpret_cast<const __half2*>(&w4[e]);
-        const float2 f2 = __half22float2(h2);
-        packed[i * 4 + e] = pack_bf16x2(f2.x * wd, f2.y * wd);
-      }
+  for (int i = 0; i < 16; ++i) {
+    const int q = chunk * PGN_D_CHUNK_K + half * 32 + 2 * i;
+    const int ca = pgn_dperm_refcol(q), cb = pgn_dperm_refcol(q + 1);
+    float a = 0.f, b = 0.f;
+    if (row < rows_valid) {
+      if (ca >= 0) a = enc_rows[(size_t)row * PGN_ENC + ca];
+      if (cb >= 0) b = enc_rows[(size_t)row * PGN_ENC + cb];
     }
+    packed[i] = pack_bf16x2(a, b);
   }
 }
 __device__ __forceinline__ void encode_d_store(uint32_t stg, int row, int half, const uint32_t (&packed)[20]) {
@@ -297,7 +309,7 @@ __device__ __forceinline__ void group_bar_sync(int slot) { asm volatile("bar.syn
 // optional phase timers (cycles, one elected thread per role of SLOT 0, accumulated per CTA):
 //  3 issuer total | 4 producer wait w_empty | 5 producer total
 //  6 encode_x | 7 encode_d | 8 epilogue | 9 wait acc_full | 10 wait stg_empty | 11 composite | 12 compute total
-//  13 wait act_free | 15 chunk store + arrive
+//  13 wait act_free | 14 per-tile tables | 15 chunk store + arrive
 #define PROF_T0() const long long _pt0 = prof ? clock64() : 0
 #define PROF_ADD(slot) do { if (prof) pacc[slot] += (unsigned long long)(clock64() - _pt0); } while (0)
 
@@ -468,8 +480,9 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
   } else {
     // ===================== compute group of slot s =====================
     // Runs the slot's tiles in order; per layer job: PRE (generated A-operand chunks), then POST
-    // (accumulator drain -> next layer's A operand / heads).  The compositing of tile n runs between
-    // POST(L0) and POST(L1) of tile n+1, i.e. while the tensor core works on that tile's first hidden layer.
+    // (accumulator drain -> next layer's A operand / heads).  The compositing of tile n is cut into four
+    // stages that run between PRE and POST of layers 1..4 of tile n+1, i.e. while the tensor core works on
+    // that tile's hidden layers.
     const int s = warp >> 3;
     const int n_slot = (n_local + 1 - s) / 2;
     const int gtid = tid - s * kGroupThreads;     // thread index inside the group
@@ -477,7 +490,11 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
     const int row = gtid & (kTM - 1), half = gtid >> 7;
     const uint32_t tmem_acc = tmem_base + (uint32_t)s * 256u;
     const uint32_t act_saddr = smem_u32(sm.act[s]);
+    const uint32_t jtab_saddr = smem_u32(sm.jtab[s]);
+    const uint32_t dtab_saddr = smem_u32(sm.dtab[s]);
     const bool timed = prof && s == 0;
+    const float kLog2e = 1.4426950408889634f;
+    const float tau_v2 = sc.tau_v * kLog2e, tau_d2 = sc.tau_d * kLog2e;
     uint32_t accs = 0, afree = 0;
     uint32_t sbuf = 0, sphase = 1;                // staging ring cursor ("empty" barriers start released)
 
@@ -494,77 +511,146 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
       tc.tile_ray0 = min(tc.row0 / tc.S, kRPG - 1);
     };
 
-    // ---- deferred compositing of a finished tile (raw rows of the tile are in part[s])
-    auto composite_tile = [&](const TileCtx& tc) {
-      const PgnBf16Net& net = tc.pass == 0 ? net_c : net_f;
-      group_bar_sync(s);                                   // every epilogue atomic of the tile has landed
-      if (gtid < kTM) {                                    // head biases -> raw row (rgb_raw, sigma_raw)
-        float* p0 = sm.part[s][gtid];
-        p0[0] += net.b_rgb[0];
-        p0[1] += net.b_rgb[1];
-        p0[2] += net.b_rgb[2];
-        p0[3] += net.b_alpha[0];
+    // ---- per-tile tables (jtab, dtab) for the <=3 rays of the tile: one (ray, joint, axis) item per thread
+    auto build_tables = [&](const TileCtx& tc) {
+      const int tile_ray1 = min((tc.row0 + kTM - 1) / tc.S, tc.nr - 1);
+      if (gtid < kMaxTileRays * PGN_J * 3) {
+        const int tr = gtid / (PGN_J * 3), rem = gtid - tr * (PGN_J * 3);
+        const int jn = rem / 3, axis = rem - jn * 3;
+        const int rl = tc.tile_ray0 + tr;
+        if (rl <= tile_ray1) {
+          const long long ri = tc.ray0 + rl;
+          const float* rb = rays.ray_batch + ri * 11;
+          const float4* m = reinterpret_cast<const float4*>(pgn_ray_skts(rays, ri) + jn * 16);
+          const float4 m0 = __ldg(m), m1 = __ldg(m + 1), m2 = __ldg(m + 2);
+          const float o0 = __ldg(rb), o1 = __ldg(rb + 1), o2 = __ldg(rb + 2);
+          const float dd[3] = {__ldg(rb + 3), __ldg(rb + 4), __ldg(rb + 5)};
+          const float b0 = fmaf(m0.z, dd[2], fmaf(m0.y, dd[1], m0.x * dd[0]));
+          const float b1 = fmaf(m1.z, dd[2], fmaf(m1.y, dd[1], m1.x * dd[0]));
+          const float b2 = fmaf(m2.z, dd[2], fmaf(m2.y, dd[1], m2.x * dd[0]));
+          if (axis == 0) {
+            const float a0 = fmaf(m0.z, o2, fmaf(m0.y, o1, m0.x * o0)) + m0.w;
+            const float a1 = fmaf(m1.z, o2, fmaf(m1.y, o1, m1.x * o0)) + m1.w;
+            const float a2 = fmaf(m2.z, o2, fmaf(m2.y, o1, m2.x * o0)) + m2.w;
+            const uint32_t jt = jtab_saddr + (uint32_t)(tr * PGN_J + jn) * 32u;
+            sts128(jt, __float_as_uint(a0), __float_as_uint(a1), __float_as_uint(a2), __float_as_uint(b0));
+            sts128(jt + 16, __float_as_uint(b1), __float_as_uint(b2), __float_as_uint(-tau_v2 * sc.cutoff_v[jn]),
+                   __float_as_uint(-tau_d2 * sc.cutoff_d[jn]));
+          }
+          // normalised joint-frame view direction (core/encoders.py:25-37,181-193), component `axis`
+          const float den = fmaxf(sqrtf(fmaf(b2, b2, fmaf(b1, b1, b0 * b0))), 1e-12f);
+          const float x = (axis == 0 ? b0 : (axis == 1 ? b1 : b2)) / den;
+          __half* tab = &sm.dtab[s][tr][jn * 32];
+          float sn, cs;
+          __sincosf(x, &sn, &cs);            // |x| <= 1
+          tab[axis] = __float2half_rn(x);
+#pragma unroll
+          for (int f = 0; f < PGN_LD; ++f) {
+            tab[(1 + 2 * f) * 3 + axis] = __float2half_rn(sn);
+            tab[(2 + 2 * f) * 3 + axis] = __float2half_rn(cs);
+            const float s2 = 2.f * sn * cs;
+            const float c2 = fmaf(cs, cs, -sn * sn);
+            sn = s2; cs = c2;
+          }
+          if (axis == 0) for (int e = 27; e < 32; ++e) tab[e] = __float2half_rn(0.f);
+        }
       }
-      group_bar_sync(s);
-      if (tc.pass == 0) {
-        // coarse tile = 2 whole rays: composite, resample, merge -> zf; reset the fine carry
+    };
+
+    // ---- deferred compositing of a finished tile (raw rows of the tile are in part[s]), in four stages
+    auto composite_stage = [&](const TileCtx& tc, int stage) {
+      const PgnBf16Net& net = tc.pass == 0 ? net_c : net_f;
+      if (stage == 1) {
+        group_bar_sync(s);                                   // every epilogue atomic of the tile has landed
+        const float br = net.b_rgb[0], bg = net.b_rgb[1], bb = net.b_rgb[2], ba = net.b_alpha[0];
+        if (tc.pass == 0) {
+          // coarse tile = 2 whole rays: head biases, composite, outputs, weights for the resampling
+          const int rl = 2 * tc.t + gwarp;
+          if (gwarp < 2 && rl < tc.nr) {
+            const long long ri = tc.ray0 + rl;
+            float* zc = sm.cscratch[s][gwarp];
+            float* wts = zc + 64;
+            float* rawrows = &sm.part[s][gwarp * PGN_S][0];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              float4* p = reinterpret_cast<float4*>(rawrows + (lane + 32 * h) * 4);
+              float4 v = *p;
+              v.x += br; v.y += bg; v.z += bb; v.w += ba;
+              *p = v;
+            }
+            const float nn = __ldg(near_far + ri * 2), ff = __ldg(near_far + ri * 2 + 1);
+            zc[lane] = pgn_coarse_z(nn, ff, sc.t_coarse[lane]);
+            zc[lane + 32] = pgn_coarse_z(nn, ff, sc.t_coarse[lane + 32]);
+            const float d0 = __ldg(rays.ray_batch + ri * 11 + 3), d1 = __ldg(rays.ray_batch + ri * 11 + 4), d2 = __ldg(rays.ray_batch + ri * 11 + 5);
+            const float dn = sqrtf(d0 * d0 + d1 * d1 + d2 * d2);
+            float* cr = sm.carry[s][rl];
+            if (lane < 8) cr[lane] = (lane == 0) ? 1.f : 0.f;
+            __syncwarp();
+            pgn_composite_segment_warp<PGN_S>(rawrows, zc, 0, PGN_S, dn, sc.density_scale, sc.rgb_eps, lane, cr, wts,
+                                              out.alpha0 ? out.alpha0 + ri * PGN_S : nullptr);
+            if (lane == 0) {
+              float rgb3[3], disp, acc;
+              pgn_composite_finalize(cr, rgb3, &disp, &acc);
+              if (out.rgb0) { out.rgb0[ri * 3] = rgb3[0]; out.rgb0[ri * 3 + 1] = rgb3[1]; out.rgb0[ri * 3 + 2] = rgb3[2]; }
+              if (out.disp0) out.disp0[ri] = disp;
+              if (out.acc0) out.acc0[ri] = acc;
+            }
+            __syncwarp();
+            if (lane < 8) cr[lane] = (lane == 0) ? 1.f : 0.f;      // carry now belongs to the fine pass of this ray
+            if (out.weights0) { out.weights0[ri * PGN_S + lane] = wts[lane]; out.weights0[ri * PGN_S + lane + 32] = wts[lane + 32]; }
+            if (out.raw0) for (int i = lane; i < PGN_S * 4; i += 32) out.raw0[ri * PGN_S * 4 + i] = rawrows[i];
+            __syncwarp();
+          }
+        } else {
+          // fine tile: rows [row0, row0+128) cut up to 3 rays; continue each ray's compositing
+          const int rl = tc.tile_ray0 + gwarp;
+          if (gwarp < kMaxTileRays && rl < tc.nr && rl * PGN_T < tc.row0 + kTM) {
+            const long long ri = tc.ray0 + rl;
+            const int s0 = max(0, tc.row0 - rl * PGN_T), s1 = min(PGN_T, tc.row0 + kTM - rl * PGN_T);
+            float* rawrows = &sm.part[s][rl * PGN_T + s0 - tc.row0][0];
+            for (int i = lane; i < s1 - s0; i += 32) {
+              float4* p = reinterpret_cast<float4*>(rawrows + i * 4);
+              float4 v = *p;
+              v.x += br; v.y += bg; v.z += bb; v.w += ba;
+              *p = v;
+            }
+            __syncwarp();
+            const float d0 = __ldg(rays.ray_batch + ri * 11 + 3), d1 = __ldg(rays.ray_batch + ri * 11 + 4), d2 = __ldg(rays.ray_batch + ri * 11 + 5);
+            const float dn = sqrtf(d0 * d0 + d1 * d1 + d2 * d2);
+            float* cr = sm.carry[s][rl];
+            pgn_composite_segment_warp<PGN_T>(rawrows, sm.zf[s][rl], s0, s1, dn, sc.density_scale, sc.rgb_eps, lane, cr,
+                                              nullptr, out.alpha ? out.alpha + ri * PGN_T : nullptr);
+            if (out.raw) for (int i = lane; i < (s1 - s0) * 4; i += 32) out.raw[(ri * PGN_T + s0) * 4 + i] = rawrows[i];
+            if (s1 == PGN_T && lane == 0) {
+              float rgb3[3], disp, acc;
+              pgn_composite_finalize(cr, rgb3, &disp, &acc);
+              if (out.rgb_map) { out.rgb_map[ri * 3] = rgb3[0]; out.rgb_map[ri * 3 + 1] = rgb3[1]; out.rgb_map[ri * 3 + 2] = rgb3[2]; }
+              if (out.disp_map) out.disp_map[ri] = disp;
+              if (out.acc_map) out.acc_map[ri] = acc;
+            }
+          }
+        }
+      } else if (stage == 2 || stage == 3) {
+        // coarse tile: inverse-CDF resampling of the two rays (cdf, then draw + merge -> zf)
         const int rl = 2 * tc.t + gwarp;
-        if (gwarp < 2 && rl < tc.nr) {
+        if (tc.pass == 0 && gwarp < 2 && rl < tc.nr) {
           const long long ri = tc.ray0 + rl;
           float* zc = sm.cscratch[s][gwarp];
           float* wts = zc + 64;
           float* scr = zc + 128;
-          const float nn = __ldg(near_far + ri * 2), ff = __ldg(near_far + ri * 2 + 1);
-          zc[lane] = pgn_coarse_z(nn, ff, sc.t_coarse[lane]);
-          zc[lane + 32] = pgn_coarse_z(nn, ff, sc.t_coarse[lane + 32]);
-          const float d0 = __ldg(rays.ray_batch + ri * 11 + 3), d1 = __ldg(rays.ray_batch + ri * 11 + 4), d2 = __ldg(rays.ray_batch + ri * 11 + 5);
-          const float dn = sqrtf(d0 * d0 + d1 * d1 + d2 * d2);
-          float* cr = sm.carry[s][rl];
-          if (lane < 8) cr[lane] = (lane == 0) ? 1.f : 0.f;
-          __syncwarp();
-          const float* rawrows = &sm.part[s][gwarp * PGN_S][0];
-          pgn_composite_segment_warp<PGN_S>(rawrows, zc, 0, PGN_S, dn, sc.density_scale, sc.rgb_eps, lane, cr, wts,
-                                            out.alpha0 ? out.alpha0 + ri * PGN_S : nullptr);
-          if (lane == 0) {
-            float rgb3[3], disp, acc;
-            pgn_composite_finalize(cr, rgb3, &disp, &acc);
-            if (out.rgb0) { out.rgb0[ri * 3] = rgb3[0]; out.rgb0[ri * 3 + 1] = rgb3[1]; out.rgb0[ri * 3 + 2] = rgb3[2]; }
-            if (out.disp0) out.disp0[ri] = disp;
-            if (out.acc0) out.acc0[ri] = acc;
+          if (stage == 2) {
+            pgn_sample_pdf_cdf_warp(zc, wts, lane, scr);
+          } else {
+            pgn_sample_pdf_draw_warp(zc, sc.u_det, lane, scr, out.z_samples ? out.z_samples + ri * PGN_I : nullptr,
+                                     sm.zf[s][rl], out.pdf_inds ? out.pdf_inds + ri * PGN_I : nullptr, nullptr);
+            if (out.z_fine) for (int i = lane; i < PGN_T; i += 32) out.z_fine[ri * PGN_T + i] = sm.zf[s][rl][i];
           }
-          __syncwarp();
-          if (lane < 8) cr[lane] = (lane == 0) ? 1.f : 0.f;      // carry now belongs to the fine pass of this ray
-          if (out.weights0) { out.weights0[ri * PGN_S + lane] = wts[lane]; out.weights0[ri * PGN_S + lane + 32] = wts[lane + 32]; }
-          if (out.raw0) for (int i = lane; i < PGN_S * 4; i += 32) out.raw0[ri * PGN_S * 4 + i] = rawrows[i];
-          pgn_sample_pdf_warp(zc, wts, sc.u_det, lane, scr, out.z_samples ? out.z_samples + ri * PGN_I : nullptr,
-                              sm.zf[s][rl], out.pdf_inds ? out.pdf_inds + ri * PGN_I : nullptr, nullptr);
-          if (out.z_fine) for (int i = lane; i < PGN_T; i += 32) out.z_fine[ri * PGN_T + i] = sm.zf[s][rl][i];
         }
       } else {
-        // fine tile: rows [row0, row0+128) cut up to 3 rays; continue each ray's compositing
-        const int rl = tc.tile_ray0 + gwarp;
-        if (gwarp < kMaxTileRays && rl < tc.nr && rl * PGN_T < tc.row0 + kTM) {
-          const long long ri = tc.ray0 + rl;
-          const int s0 = max(0, tc.row0 - rl * PGN_T), s1 = min(PGN_T, tc.row0 + kTM - rl * PGN_T);
-          const float d0 = __ldg(rays.ray_batch + ri * 11 + 3), d1 = __ldg(rays.ray_batch + ri * 11 + 4), d2 = __ldg(rays.ray_batch + ri * 11 + 5);
-          const float dn = sqrtf(d0 * d0 + d1 * d1 + d2 * d2);
-          float* cr = sm.carry[s][rl];
-          const float* rawrows = &sm.part[s][rl * PGN_T + s0 - tc.row0][0];
-          pgn_composite_segment_warp<PGN_T>(rawrows, sm.zf[s][rl], s0, s1, dn, sc.density_scale, sc.rgb_eps, lane, cr,
-                                            nullptr, out.alpha ? out.alpha + ri * PGN_T : nullptr);
-          if (out.raw) for (int i = lane; i < (s1 - s0) * 4; i += 32) out.raw[(ri * PGN_T + s0) * 4 + i] = rawrows[i];
-          if (s1 == PGN_T && lane == 0) {
-            float rgb3[3], disp, acc;
-            pgn_composite_finalize(cr, rgb3, &disp, &acc);
-            if (out.rgb_map) { out.rgb_map[ri * 3] = rgb3[0]; out.rgb_map[ri * 3 + 1] = rgb3[1]; out.rgb_map[ri * 3 + 2] = rgb3[2]; }
-            if (out.disp_map) out.disp_map[ri] = disp;
-            if (out.acc_map) out.acc_map[ri] = acc;
-          }
-        }
+        group_bar_sync(s);                                   // every reader of part[s] / writer of zf[s] is done
+        if (gtid < kTM) *reinterpret_cast<float4*>(sm.part[s][gtid]) = make_float4(0.f, 0.f, 0.f, 0.f);   // next tile of this slot
+        group_bar_sync(s);
       }
-      group_bar_sync(s);
-      if (gtid < kTM) *reinterpret_cast<float4*>(sm.part[s][gtid]) = make_float4(0.f, 0.f, 0.f, 0.f);   // next tile of this slot
-      group_bar_sync(s);
     };
 
     // ---- POST(job): drain the accumulator (epilogue)
@@ -595,41 +681,38 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
     };
 
     // ---- PRE(job): everything the tensor core needs from the CUDA cores before/while it runs the layer
+    RowCtx rc;
+    rc.valid = false; rc.tr = 0; rc.z = 0.f;
     auto pre = [&](int L, const TileCtx& tc) -> bool {
       const int nchunks = pgn_layer_chunks(L);
       if (nchunks == 0) return true;
       const float* enc_rows = kStage ? enc_global + (size_t)tc.unit * kTM * PGN_ENC : nullptr;
       const int rows_valid = kStage ? (int)max(0ll, min((long long)kTM, enc_rows_total - tc.unit * kTM)) : kTM;
       if (!kStage && L == 0) {
-        // PE table of the joint-frame view directions for the <=3 rays of this tile (used by the V layer)
-        const int tile_ray1 = min((tc.row0 + kTM - 1) / tc.S, tc.nr - 1);
-        for (int i = gtid; i < kMaxTileRays * PGN_J; i += kGroupThreads) {
-          const int tr = i / PGN_J, jn = i % PGN_J;
-          const int rl = tc.tile_ray0 + tr;
-          __half* tab = &sm.dtab[s][tr][jn * 32];
-          if (rl <= tile_ray1) {
-            const long long ri = tc.ray0 + rl;
-            const float4* m = reinterpret_cast<const float4*>(pgn_ray_skts(rays, ri) + jn * 16);
-            const float dd[3] = {__ldg(rays.ray_batch + ri * 11 + 3), __ldg(rays.ray_batch + ri * 11 + 4), __ldg(rays.ray_batch + ri * 11 + 5)};
-            float dj[3];
-            pgn_joint_dir(__ldg(m), __ldg(m + 1), __ldg(m + 2), dd, dj[0], dj[1], dj[2]);
-            for (int k = 0; k < 1 + 2 * PGN_LD; ++k)
-              for (int a = 0; a < 3; ++a) tab[k * 3 + a] = __float2half_rn(pgn_pe_term(dj[a], k));
-            for (int e = 27; e < 32; ++e) tab[e] = __float2half_rn(0.f);
-          }
-        }
+        PROF_T0();
+        build_tables(tc);
+        rc = make_row_ctx(sm, sc, tc, near_far, s, row);
+        group_bar_sync(s);                 // tables visible to every thread of the group
+        if (timed) PROF_ADD(14);
       }
-      if (L == 8) group_bar_sync(s);         // wcache (L5's encode) and dtab (L0's PRE) visible to every thread
-      RowCtx rc;
-      rc.valid = false; rc.px = rc.py = rc.pz = 0.f; rc.skt = rays.skts;
-      if (!kStage && L != 8) rc = make_row_ctx(sm, rays, sc, tc, near_far, s, row);
       // software pipeline: the values of chunk c+1 are computed while chunk c travels through the
       // staging ring / tensor core; only the 16-byte stores wait for a ring buffer to be released
       uint32_t packed[20];
       auto compute_chunk = [&](int c) {
-        if (L == 8) { PROF_T0(); encode_d_compute<kStage>(sm, tc, s, c, row, half, enc_rows, rows_valid, packed); if (timed) PROF_ADD(7); }
-        else { PROF_T0(); encode_x_compute<kStage>(sm, sc, rc, s, c, row, half, L == 5, enc_rows, rows_valid, packed); if (timed) PROF_ADD(6); }
+        if (L == 8) {
+          PROF_T0();
+          if (kStage) encode_d_stage(c, row, half, enc_rows, rows_valid, packed);
+          else encode_d_fast(sm, dtab_saddr, rc, s, c, row, half, packed);
+          if (timed) PROF_ADD(7);
+        } else {
+          PROF_T0();
+          if (kStage) encode_x_stage(c, row, half, enc_rows, rows_valid, packed);
+          else if (L == 5) encode_x_fast<true>(sm, jtab_saddr, rc, tau_v2, tau_d2, s, c, row, half, packed);
+          else encode_x_fast<false>(sm, jtab_saddr, rc, tau_v2, tau_d2, s, c, row, half, packed);
+          if (timed) PROF_ADD(6);
+        }
       };
+      if (L == 8) group_bar_sync(s);       // wcache (written by L5's encode) visible to every thread
       compute_chunk(0);
       if (L != 0) {      // the activation K-steps of this layer must have been consumed before act[s] becomes the staging ring
         PROF_T0(); const bool okw = mbar_wait(&sm.act_free[s], afree & 1, status, 302); if (timed) PROF_ADD(13); if (!okw) return false;
@@ -654,13 +737,13 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
         make_ctx(i, k, tc);
         for (int L = 0; L < 9; ++L) {
           if (!pre(L, tc)) goto done;
-          if (!kStage && L == 1 && pending) { PROF_T0(); composite_tile(prev); if (timed) PROF_ADD(11); pending = false; }
+          if (!kStage && pending && L >= 1 && L <= 4) { PROF_T0(); composite_stage(prev, L); if (timed) PROF_ADD(11); }
           if (!post(L, tc)) goto done;
         }
         if (!kStage) { prev = tc; pending = true; }
       }
     }
-    if (pending) composite_tile(prev);
+    if (pending) for (int st = 1; st <= 4; ++st) composite_stage(prev, st);
   }
 done:
   if (prof) {
@@ -669,7 +752,7 @@ done:
     if (warp == kIssuerWarp0 && lane == 0) { pp[0] = 0; pp[1] = 0; pp[2] = 0; pp[3] = total; }
     if (warp == kProducerWarp0 && lane == 0) { pp[4] = pacc[4]; pp[5] = total; }
     if (tid == 0) { pp[6] = pacc[6]; pp[7] = pacc[7]; pp[8] = pacc[8]; pp[9] = pacc[9]; pp[10] = pacc[10]; pp[11] = pacc[11];
-                    pp[12] = total; pp[13] = pacc[13]; pp[15] = pacc[15]; }
+                    pp[12] = total; pp[13] = pacc[13]; pp[14] = pacc[14]; pp[15] = pacc[15]; }
   }
   tc_fence_before_sync();
   __syncthreads();

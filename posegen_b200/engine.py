@@ -238,7 +238,7 @@ class Engine:
 
     PHASES = ["issuer_wait_weights", "issuer_wait_staging", "issuer_wait_act", "issuer_total", "producer_wait_slot",
               "producer_total", "encode_x", "encode_d", "epilogue", "wait_acc", "wait_stg_free", "composite", "compute_total",
-              "wait_act_free", "-", "store_arrive"]
+              "wait_act_free", "tables", "store_arrive"]
 
     def phase_timers(self, enable=True, read=False):
         """Enable/disable the bf16 kernel's phase timers; read=True returns the last launch's averages (cycles)."""
