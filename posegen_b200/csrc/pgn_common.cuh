@@ -240,11 +240,11 @@ __device__ __forceinline__ void pgn_composite_warp(const float* __restrict__ raw
 //   raw_seg: rows of samples s0..s1-1 ([i - s0][4]);  z: the ray's full z array [S].
 // All lanes of the warp must call it; carry is updated by lane 0 (then __syncwarp()).
 // ---------------------------------------------------------------------------
-template <int S>
+// kFast (bf16 tensor-core tier only): ex2/rcp approximations instead of expf and IEEE division.
+template <int S, bool kFast = false, int CH = 3>       // CH samples per lane: up to 32*CH samples per call
 __device__ __forceinline__ void pgn_composite_segment_warp(const float* __restrict__ raw_seg, const float* __restrict__ z,
                                                            int s0, int s1, float dnorm, float density_scale, float rgb_eps,
                                                            int lane, float* carry, float* weights_out, float* alpha_out) {
-  constexpr int CH = 3;                                  // up to 96 samples per call
   float a[CH], p[CH];
   float lane_prod = 1.0f;
 #pragma unroll
@@ -254,8 +254,8 @@ __device__ __forceinline__ void pgn_composite_segment_warp(const float* __restri
     if (i < s1) {
       float dist = (i + 1 < S) ? __fsub_rn(z[i + 1], z[i]) : 1e10f;
       dist = __fmul_rn(dist, dnorm);
-      const float sig = fmaxf(raw_seg[(i - s0) * 4 + 3] / density_scale, 0.0f);
-      al = 1.0f - expf(-__fmul_rn(sig, dist));
+      const float sig = fmaxf(kFast ? __fdividef(raw_seg[(i - s0) * 4 + 3], density_scale) : raw_seg[(i - s0) * 4 + 3] / density_scale, 0.0f);
+      al = 1.0f - (kFast ? __expf(-__fmul_rn(sig, dist)) : expf(-__fmul_rn(sig, dist)));
     }
     a[c] = al;
     p[c] = lane_prod;
@@ -281,9 +281,9 @@ __device__ __forceinline__ void pgn_composite_segment_warp(const float* __restri
       if (alpha_out) alpha_out[i] = a[c];
       const float k = 1.0f + 2.0f * rgb_eps;
       const float* rw = raw_seg + (i - s0) * 4;
-      const float r = (1.0f / (1.0f + expf(-rw[0]))) * k - rgb_eps;
-      const float g = (1.0f / (1.0f + expf(-rw[1]))) * k - rgb_eps;
-      const float b = (1.0f / (1.0f + expf(-rw[2]))) * k - rgb_eps;
+      const float r = (kFast ? __fdividef(1.0f, 1.0f + __expf(-rw[0])) : 1.0f / (1.0f + expf(-rw[0]))) * k - rgb_eps;
+      const float g = (kFast ? __fdividef(1.0f, 1.0f + __expf(-rw[1])) : 1.0f / (1.0f + expf(-rw[1]))) * k - rgb_eps;
+      const float b = (kFast ? __fdividef(1.0f, 1.0f + __expf(-rw[2])) : 1.0f / (1.0f + expf(-rw[2]))) * k - rgb_eps;
       sr = fmaf(w, r, sr); sg = fmaf(w, g, sg); sb = fmaf(w, b, sb);
       sw += w; sd = fmaf(w, z[i], sd);
     }

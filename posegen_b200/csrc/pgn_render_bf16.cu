@@ -298,11 +298,17 @@ __device__ __forceinline__ void epilogue(Smem& sm, uint32_t tmem_acc, uint32_t a
 
 // "my part of the A operand is written / my TMEM reads are done" -> the LEADER CTA's barrier
 // (one elected arrive per warp: every lane fences its own writes, __syncwarp orders them before lane 0's release)
-__device__ __forceinline__ void compute_arrive(uint64_t* bar, int lane) {
+__device__ __forceinline__ void compute_arrive(uint32_t bar, int lane) {
   tc_fence_before_sync();
   fence_proxy_async_smem();
   __syncwarp();
-  if (lane == 0) mbar_arrive_cluster(bar, 0);
+  if (lane == 0) mbar_arrive_cluster_s(bar, 0);
+}
+// chunk hand-off: plain shared-memory writes only (no tcgen05 operation of this thread to order)
+__device__ __forceinline__ void chunk_arrive(uint32_t bar, int lane) {
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) mbar_arrive_cluster_s(bar, 0);
 }
 __device__ __forceinline__ void group_bar_sync(int slot) { asm volatile("bar.sync %0, 256;\n" ::"r"(slot + 1) : "memory"); }
 
@@ -310,11 +316,11 @@ __device__ __forceinline__ void group_bar_sync(int slot) { asm volatile("bar.syn
 //  3 issuer total | 4 producer wait w_empty | 5 producer total
 //  6 encode_x | 7 encode_d | 8 epilogue | 9 wait acc_full | 10 wait stg_empty | 11 composite | 12 compute total
 //  13 wait act_free | 14 per-tile tables | 15 chunk store + arrive
-#define PROF_T0() const long long _pt0 = prof ? clock64() : 0
-#define PROF_ADD(slot) do { if (prof) pacc[slot] += (unsigned long long)(clock64() - _pt0); } while (0)
+#define PROF_T0() const long long _pt0 = kProf ? clock64() : 0
+#define PROF_ADD(slot) do { if (kProf) pacc[slot] += (unsigned long long)(clock64() - _pt0); } while (0)
 
 // ------------------------------------------------------------------ the kernel
-template <bool kStage>
+template <bool kStage, bool kProf>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf16Net net_f,
                        const PgnScalars* __restrict__ scp, const float* __restrict__ near_far,
@@ -323,7 +329,13 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   volatile int* status = status_g;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // volatile reads: keeps tid / lane in registers instead of re-reading the special registers (S2R) in hot loops
+  int tid, lane;
+  asm volatile("mov.u32 %0, %%tid.x;\n" : "=r"(tid));
+  asm volatile("mov.u32 %0, %%laneid;\n" : "=r"(lane));
+  const int warp = tid >> 5;
+  const uint32_t sm_base = smem_u32(&sm);
+#define SADDR(field) (sm_base + (uint32_t)offsetof(Smem, field))
   const uint32_t rank = cluster_ctarank();
   const PgnScalars& sc = *scp;
   const long long n_clusters = gridDim.x >> 1, cluster_id = blockIdx.x >> 1;
@@ -361,13 +373,15 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
   tc_fence_after_sync();
   const uint32_t tmem_base = sm.tmem_base;
   unsigned long long pacc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-  const long long kernel_t0 = prof ? clock64() : 0;
+  const long long kernel_t0 = kProf ? clock64() : 0;
 
   if (warp >= kProducerWarp0 && warp < kProducerWarp0 + 2) {
     // ===================== weight producer of slot s (each CTA streams ITS N-half of every fill) =====================
     const int s = warp - kProducerWarp0;
     const int n_slot = (n_local + 1 - s) / 2;
     if (lane == 0) {
+      const uint32_t w_full0 = SADDR(w_full) + s * kWStages * 8, w_empty0 = SADDR(w_empty) + s * kWStages * 8;
+      const uint32_t ring0 = SADDR(wring) + s * kWStages * kWStageBytes;
       uint32_t stage = 0, wphase = 1;          // "empty" barriers start released
       for (int i = 0; i < n_slot; ++i) {
         for (int k = 0; k < kTiles; ++k) {
@@ -380,9 +394,9 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
             for (int ks = 0; ks < ks_total; ks += kpf) {
               const int nks = min(kpf, ks_total - ks);
               const uint32_t bytes = (uint32_t)nks * nh * 32u;          // this CTA's half of the fill
-              { PROF_T0(); const bool okw = mbar_wait(&sm.w_empty[s][stage], wphase, status, 101); PROF_ADD(4); if (!okw) goto done; }
-              mbar_arrive_expect_tx(&sm.w_full[s][stage], bytes);
-              bulk_g2s(sm.wring[s][stage], src + (size_t)rank * bytes, bytes, &sm.w_full[s][stage]);
+              { PROF_T0(); const bool okw = mbar_wait_s(w_empty0 + stage * 8, wphase, status, 101); PROF_ADD(4); if (!okw) goto done; }
+              mbar_arrive_expect_tx_s(w_full0 + stage * 8, bytes);
+              bulk_g2s_s(ring0 + stage * kWStageBytes, src + (size_t)rank * bytes, bytes, w_full0 + stage * 8);
               src += 2u * bytes;
               if (++stage == kWStages) { stage = 0; wphase ^= 1; }
             }
@@ -396,14 +410,15 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
     if (rank == 1) {
       // ===================== peer relay: "my half of fill f has landed" -> leader's w_full =====================
       if (lane == 0) {
+        const uint32_t w_full0 = SADDR(w_full) + s * kWStages * 8;
         uint32_t stage = 0, wphase = 0;
         for (int i = 0; i < n_slot; ++i)
           for (int k = 0; k < kTiles; ++k)
             for (int L = 0; L < 9; ++L) {
               const int ks_total = pgn_layer_ksteps(L), kpf = pgn_ks_per_fill(L);
               for (int ks = 0; ks < ks_total; ks += kpf) {
-                if (!mbar_wait(&sm.w_full[s][stage], wphase, status, 401)) goto done;
-                mbar_arrive_cluster(&sm.w_full[s][stage], 0);
+                if (!mbar_wait_s(w_full0 + stage * 8, wphase, status, 401)) goto done;
+                mbar_arrive_cluster_s(w_full0 + stage * 8, 0);
                 if (++stage == kWStages) { stage = 0; wphase ^= 1; }
               }
             }
@@ -414,11 +429,14 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
       uint32_t stage = 0, wphase = 0;        // weight ring cursor
       uint32_t sbuf = 0, sphase = 0;         // staging ring cursor
       uint32_t jobs = 0;                     // jobs already issued (act_ready phase)
+      const uint32_t w_full0 = SADDR(w_full) + s * kWStages * 8, w_empty0 = SADDR(w_empty) + s * kWStages * 8;
+      const uint32_t stg_full0 = SADDR(stg_full) + s * kStgBufs * 8, stg_empty0 = SADDR(stg_empty) + s * kStgBufs * 8;
+      const uint32_t act_ready_a = SADDR(act_ready) + s * 8, acc_full_a = SADDR(acc_full) + s * 8, act_free_a = SADDR(act_free) + s * 8;
       const uint32_t kDescHi = (128u >> 4) | (1u << 14);                 // SBO = 128 B, descriptor version 1
       const uint32_t a_lbo = (uint32_t)(kRunBytes >> 4) << 16;           // A: LBO = 2048 B
-      const uint32_t act_lo = (smem_u32(sm.act[s]) >> 4) | a_lbo;
-      const uint32_t ones_lo = (smem_u32(sm.ones) >> 4) | a_lbo;
-      const uint32_t ring_lo = smem_u32(sm.wring[s][0]) >> 4;
+      const uint32_t act_lo = ((SADDR(act) + s * kActBytes) >> 4) | a_lbo;
+      const uint32_t ones_lo = (SADDR(ones) >> 4) | a_lbo;
+      const uint32_t ring_lo = (SADDR(wring) + s * kWStages * kWStageBytes) >> 4;
       const uint32_t tmem_acc = tmem_base + (uint32_t)s * 256u;
       constexpr uint32_t kAStep = (2 * kRunBytes) >> 4;                  // one K-step of A (two runs)
       for (int i = 0; i < n_slot; ++i) {
@@ -434,7 +452,7 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
             const uint32_t b_step = (nh * 32u) >> 4;                         // one K-step of this CTA's B half
             // the previous job of this slot must have been drained (its epilogue wrote act[s] / freed the accumulator)
             if (jobs > 0) {
-              if (!mbar_wait_cluster(&sm.act_ready[s], (jobs - 1) & 1, status, 201)) goto done;
+              if (!mbar_wait_s(act_ready_a, (jobs - 1) & 1, status, 201)) goto done;
               tc_fence_after_sync();
             }
             ++jobs;
@@ -442,7 +460,7 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
             uint32_t accum = 0;
             while (ks < ks_total) {
               // ---- one weight fill (kpf K-steps, fewer at the end of the layer)
-              if (!mbar_wait_cluster(&sm.w_full[s][stage], wphase, status, 202)) goto done;
+              if (!mbar_wait_s(w_full0 + stage * 8, wphase, status, 202)) goto done;
               tc_fence_after_sync();
               uint32_t b_lo = (ring_lo + stage * (kWStageBytes >> 4)) | b_lbo;
               const int ks_end = min(ks + kpf, ks_total);
@@ -455,7 +473,7 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
                   a_lo = act_lo + (uint32_t)ks * kAStep;
                 } else {
                   if (ce == 0) {
-                    if (!mbar_wait_cluster(&sm.stg_full[s][sbuf], sphase, status, 203)) goto done;
+                    if (!mbar_wait_s(stg_full0 + sbuf * 8, sphase, status, 203)) goto done;
                     tc_fence_after_sync();
                   }
                   a_lo = act_lo + sbuf * (uint32_t)(kStgBytes >> 4) + (uint32_t)ce * kAStep;
@@ -464,15 +482,15 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
                 umma_bf16_2cta_elect(tmem_acc, ((uint64_t)kDescHi << 32) | a_lo, ((uint64_t)kDescHi << 32) | b_lo, idesc, accum);
                 accum = 1;
                 if (chunk_end) {
-                  umma_commit_2cta_elect(&sm.stg_empty[s][sbuf]);
+                  umma_commit_2cta_elect_s(stg_empty0 + sbuf * 8);
                   if (++sbuf == kStgBufs) { sbuf = 0; sphase ^= 1; }
                 }
-                if (has_chunks && ks_act > 0 && ks == ks_act - 1) umma_commit_2cta_elect(&sm.act_free[s]);   // act[s] may be overwritten by chunks
+                if (has_chunks && ks_act > 0 && ks == ks_act - 1) umma_commit_2cta_elect_s(act_free_a);   // act[s] may be overwritten by chunks
               }
-              umma_commit_2cta_elect(&sm.w_empty[s][stage]);
+              umma_commit_2cta_elect_s(w_empty0 + stage * 8);
               if (++stage == kWStages) { stage = 0; wphase ^= 1; }
             }
-            umma_commit_2cta_elect(&sm.acc_full[s]);
+            umma_commit_2cta_elect_s(acc_full_a);
           }
         }
       }
@@ -489,10 +507,12 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
     const int gwarp = gtid >> 5;
     const int row = gtid & (kTM - 1), half = gtid >> 7;
     const uint32_t tmem_acc = tmem_base + (uint32_t)s * 256u;
-    const uint32_t act_saddr = smem_u32(sm.act[s]);
-    const uint32_t jtab_saddr = smem_u32(sm.jtab[s]);
-    const uint32_t dtab_saddr = smem_u32(sm.dtab[s]);
-    const bool timed = prof && s == 0;
+    const uint32_t act_saddr = SADDR(act) + s * kActBytes;
+    const uint32_t jtab_saddr = SADDR(jtab) + s * (uint32_t)sizeof(sm.jtab[0]);
+    const uint32_t dtab_saddr = SADDR(dtab) + s * (uint32_t)sizeof(sm.dtab[0]);
+    const uint32_t stg_full0 = SADDR(stg_full) + s * kStgBufs * 8, stg_empty0 = SADDR(stg_empty) + s * kStgBufs * 8;
+    const uint32_t act_ready_a = SADDR(act_ready) + s * 8, acc_full_a = SADDR(acc_full) + s * 8, act_free_a = SADDR(act_free) + s * 8;
+    const bool timed = kProf && s == 0;
     const float kLog2e = 1.4426950408889634f;
     const float tau_v2 = sc.tau_v * kLog2e, tau_d2 = sc.tau_d * kLog2e;
     uint32_t accs = 0, afree = 0;
@@ -586,7 +606,7 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
             float* cr = sm.carry[s][rl];
             if (lane < 8) cr[lane] = (lane == 0) ? 1.f : 0.f;
             __syncwarp();
-            pgn_composite_segment_warp<PGN_S>(rawrows, zc, 0, PGN_S, dn, sc.density_scale, sc.rgb_eps, lane, cr, wts,
+            pgn_composite_segment_warp<PGN_S, true, 2>(rawrows, zc, 0, PGN_S, dn, sc.density_scale, sc.rgb_eps, lane, cr, wts,
                                               out.alpha0 ? out.alpha0 + ri * PGN_S : nullptr);
             if (lane == 0) {
               float rgb3[3], disp, acc;
@@ -618,7 +638,7 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
             const float d0 = __ldg(rays.ray_batch + ri * 11 + 3), d1 = __ldg(rays.ray_batch + ri * 11 + 4), d2 = __ldg(rays.ray_batch + ri * 11 + 5);
             const float dn = sqrtf(d0 * d0 + d1 * d1 + d2 * d2);
             float* cr = sm.carry[s][rl];
-            pgn_composite_segment_warp<PGN_T>(rawrows, sm.zf[s][rl], s0, s1, dn, sc.density_scale, sc.rgb_eps, lane, cr,
+            pgn_composite_segment_warp<PGN_T, true, 3>(rawrows, sm.zf[s][rl], s0, s1, dn, sc.density_scale, sc.rgb_eps, lane, cr,
                                               nullptr, out.alpha ? out.alpha + ri * PGN_T : nullptr);
             if (out.raw) for (int i = lane; i < (s1 - s0) * 4; i += 32) out.raw[(ri * PGN_T + s0) * 4 + i] = rawrows[i];
             if (s1 == PGN_T && lane == 0) {
@@ -656,14 +676,14 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
     // ---- POST(job): drain the accumulator (epilogue)
     auto post = [&](int L, const TileCtx& tc) -> bool {
       const PgnBf16Net& net = (kStage || tc.pass == 0) ? net_c : net_f;
-      { PROF_T0(); const bool okw = mbar_wait(&sm.acc_full[s], accs & 1, status, 303); if (timed) PROF_ADD(9); if (!okw) return false; }
+      { PROF_T0(); const bool okw = mbar_wait_s(acc_full_a, accs & 1, status, 303); if (timed) PROF_ADD(9); if (!okw) return false; }
       ++accs;
       tc_fence_after_sync();
       { PROF_T0();
         if (L == 8) epilogue<2>(sm, tmem_acc, act_saddr, s, net.w_alpha, net.w_rgb, gwarp, lane);
         else if (L == 7) epilogue<1>(sm, tmem_acc, act_saddr, s, net.w_alpha, net.w_rgb, gwarp, lane);
         else epilogue<0>(sm, tmem_acc, act_saddr, s, net.w_alpha, net.w_rgb, gwarp, lane);
-        compute_arrive(&sm.act_ready[s], lane); if (timed) PROF_ADD(8); }
+        compute_arrive(act_ready_a, lane); if (timed) PROF_ADD(8); }
       if (kStage && L == 8) {
         group_bar_sync(s);
         if (gtid < kTM) {
@@ -715,15 +735,15 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
       if (L == 8) group_bar_sync(s);       // wcache (written by L5's encode) visible to every thread
       compute_chunk(0);
       if (L != 0) {      // the activation K-steps of this layer must have been consumed before act[s] becomes the staging ring
-        PROF_T0(); const bool okw = mbar_wait(&sm.act_free[s], afree & 1, status, 302); if (timed) PROF_ADD(13); if (!okw) return false;
+        PROF_T0(); const bool okw = mbar_wait_s(act_free_a, afree & 1, status, 302); if (timed) PROF_ADD(13); if (!okw) return false;
         ++afree;
       }
       for (int c = 0; c < nchunks; ++c) {
-        { PROF_T0(); const bool okw = mbar_wait(&sm.stg_empty[s][sbuf], sphase, status, 301); if (timed) PROF_ADD(10); if (!okw) return false; }
+        { PROF_T0(); const bool okw = mbar_wait_s(stg_empty0 + sbuf * 8, sphase, status, 301); if (timed) PROF_ADD(10); if (!okw) return false; }
         { PROF_T0();
           const uint32_t stg = act_saddr + sbuf * (uint32_t)kStgBytes;
           if (L == 8) encode_d_store(stg, row, half, packed); else encode_x_store(stg, row, half, packed);
-          compute_arrive(&sm.stg_full[s][sbuf], lane); if (timed) PROF_ADD(15); }
+          chunk_arrive(stg_full0 + sbuf * 8, lane); if (timed) PROF_ADD(15); }
         if (++sbuf == kStgBufs) { sbuf = 0; sphase ^= 1; }
         if (c + 1 < nchunks) compute_chunk(c + 1);
       }
@@ -746,7 +766,7 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
     if (pending) for (int st = 1; st <= 4; ++st) composite_stage(prev, st);
   }
 done:
-  if (prof) {
+  if (kProf) {
     unsigned long long* pp = prof + (size_t)blockIdx.x * 16;
     const unsigned long long total = (unsigned long long)(clock64() - kernel_t0);
     if (warp == kIssuerWarp0 && lane == 0) { pp[0] = 0; pp[1] = 0; pp[2] = 0; pp[3] = total; }
@@ -856,9 +876,11 @@ cudaError_t pgn_pack_bf16_net(const float* const* w_dev, const float* const* b_d
 static cudaError_t configure_bf16() {
   static bool done = false;
   if (done) return cudaSuccess;
-  cudaError_t e = cudaFuncSetAttribute(pgn_render_bf16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem) + 1024);
+  cudaError_t e = cudaFuncSetAttribute(pgn_render_bf16_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem) + 1024);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(pgn_render_bf16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem) + 1024);
+  e = cudaFuncSetAttribute(pgn_render_bf16_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem) + 1024);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(pgn_render_bf16_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem) + 1024);
   if (e != cudaSuccess) return e;
   done = true;
   return cudaSuccess;
@@ -873,8 +895,12 @@ cudaError_t pgn_launch_render_bf16(const PgnRayRefs& rays, const PgnOutputs& out
   if (n_groups == 0) return cudaSuccess;
   const long long n_pairs = (n_groups + 1) / 2;
   const int grid = 2 * (int)min((long long)(num_sms / 2), n_pairs);      // clusters of 2 CTAs
-  pgn_render_bf16_kernel<false><<<grid, kThreads, sizeof(Smem) + 1024, stream>>>(rays, out, nc, nf, sc_dev, near_far,
-                                                                                 nullptr, 0, nullptr, status, prof);
+  if (prof)
+    pgn_render_bf16_kernel<false, true><<<grid, kThreads, sizeof(Smem) + 1024, stream>>>(rays, out, nc, nf, sc_dev, near_far,
+                                                                                         nullptr, 0, nullptr, status, prof);
+  else
+    pgn_render_bf16_kernel<false, false><<<grid, kThreads, sizeof(Smem) + 1024, stream>>>(rays, out, nc, nf, sc_dev, near_far,
+                                                                                          nullptr, 0, nullptr, status, nullptr);
   return cudaGetLastError();
 }
 
@@ -887,7 +913,7 @@ cudaError_t pgn_launch_mlp_bf16(const PgnBf16Net& net, const float* enc, long lo
   const int grid = 2 * (int)min((long long)(num_sms / 2), (n_tiles + 1) / 2);
   PgnRayRefs rays{};
   PgnOutputs out{};
-  pgn_render_bf16_kernel<true><<<grid, kThreads, sizeof(Smem) + 1024, stream>>>(rays, out, net, net, sc_dev, nullptr,
-                                                                                enc, m, raw, status, nullptr);
+  pgn_render_bf16_kernel<true, false><<<grid, kThreads, sizeof(Smem) + 1024, stream>>>(rays, out, net, net, sc_dev, nullptr,
+                                                                                       enc, m, raw, status, nullptr);
   return cudaGetLastError();
 }

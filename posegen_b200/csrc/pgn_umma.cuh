@@ -72,6 +72,34 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
 }
 
+// ---- the same primitives on 32-bit shared-window addresses (no generic->shared conversion per call;
+// the render kernel computes every barrier address once as smem base + offset)
+__device__ __forceinline__ void mbar_arrive_expect_tx_s(uint32_t bar, uint32_t bytes) {
+  asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_s(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ bool mbar_wait_s(uint32_t bar, uint32_t parity, volatile int* status, int code) {
+  if (mbar_try_wait_s(bar, parity)) return true;
+  const long long t0 = clock64();
+  int spins = 0;
+  while (!mbar_try_wait_s(bar, parity)) {
+    if ((++spins & 255) == 0) {
+      if (*status != 0) return false;
+      if (clock64() - t0 > (1ll << 31)) { *status = code; return false; }
+    }
+  }
+  return true;
+}
+__device__ __forceinline__ void mbar_arrive_cluster_s(uint32_t bar, uint32_t cta) {
+  asm volatile("{\n .reg .b32 ra;\n mapa.shared::cluster.u32 ra, %0, %1;\n"
+               " mbarrier.arrive.shared::cluster.b64 _, [ra];\n}\n" ::"r"(bar), "r"(cta) : "memory");
+}
+
 // ------------------------------------------------------------ proxies/fences
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
@@ -81,6 +109,11 @@ __device__ __forceinline__ void tc_fence_after_sync() { asm volatile("tcgen05.fe
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
                ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void bulk_g2s_s(uint32_t smem_dst, const void* gmem_src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+               ::"r"(smem_dst), "l"(gmem_src), "r"(bytes), "r"(bar) : "memory");
 }
 
 // ------------------------------------------------------------ TMEM
@@ -184,6 +217,12 @@ __device__ __forceinline__ void umma_commit_2cta_elect(uint64_t* bar) {
   asm volatile("{\n .reg .pred e;\n elect.sync _|e, 0xffffffff;\n"
                " @e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n}\n"
                ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+
+__device__ __forceinline__ void umma_commit_2cta_elect_s(uint32_t bar) {
+  asm volatile("{\n .reg .pred e;\n elect.sync _|e, 0xffffffff;\n"
+               " @e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n}\n"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
 
 __device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) {
