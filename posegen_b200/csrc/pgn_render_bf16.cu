@@ -73,7 +73,7 @@ struct __align__(128) Smem {
   float jtab[2][kMaxTileRays][PGN_J][8];         // per (tile ray, joint): a = R o + t, b = R d, window offsets (see encode)
   float zf[2][kRPG][PGN_T];                      // merged z of the fine pass of the slot's current ray group
   float carry[2][kRPG][8];                       // incremental compositing state of the fine rays
-  float part[2][kTM][4];                         // per slot: raw rows (rgb_raw, sigma_raw), accumulated by both column halves
+  float part[2][2][kTM][4];                      // per slot, per column half: partial raw rows (rgb_raw, sigma_raw) of the heads
   uint8_t ones[2 * kRunBytes];                   // constant A operand of the bias K-step: k = 0,1 -> 1.0, else 0
   float cscratch[2][2][256];                     // coarse compositing per slot, per warp: z[64] | weights[64] | sample_pdf scratch[128]
   uint64_t w_full[2][kWStages], w_empty[2][kWStages];
@@ -243,7 +243,7 @@ __device__ __forceinline__ void encode_d_store(uint32_t stg, int row, int half, 
 // TMEM loads of the next 32-column batch are issued before the current batch is processed.
 template <int MODE>
 __device__ __forceinline__ void epilogue(Smem& sm, uint32_t tmem_acc, uint32_t act_saddr, int slot, const float* __restrict__ w_alpha,
-                                         const float* __restrict__ w_rgb, int warp, int lane) {
+                                         const float* __restrict__ w_rgb, int warp, int lane, float& sig_keep) {
   const int q = warp & 3, half = warp >> 2;
   const int row = q * 32 + lane;
   constexpr int kCols = (MODE == 2) ? 64 : 128;        // columns per thread
@@ -292,8 +292,9 @@ __device__ __forceinline__ void epilogue(Smem& sm, uint32_t tmem_acc, uint32_t a
                pack_relu_bf16x2(__uint_as_float(vb[8 * g + 6]), __uint_as_float(vb[8 * g + 7])));
     }
   }
-  if (MODE == 1) atomicAdd(&sm.part[slot][row][3], sig);
-  if (MODE == 2) { atomicAdd(&sm.part[slot][row][0], r0); atomicAdd(&sm.part[slot][row][1], r1); atomicAdd(&sm.part[slot][row][2], r2); }
+  // heads: this thread's column half of (rgb_raw, sigma_raw) -> one conflict-free 16-byte store per tile
+  if (MODE == 1) sig_keep = sig;
+  if (MODE == 2) sts128(smem_u32(&sm.part[slot][half][row][0]), __float_as_uint(r0), __float_as_uint(r1), __float_as_uint(r2), __float_as_uint(sig_keep));
 }
 
 // "my part of the A operand is written / my TMEM reads are done" -> the LEADER CTA's barrier
@@ -361,10 +362,9 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
     tmem_alloc_2cta(&sm.tmem_base, kTmemCols);
     tmem_relinquish_2cta();
   }
-  if (tid < kTM) {     // constant A operand of the bias K-step; zeroed head accumulators
+  if (tid < kTM) {     // constant A operand of the bias K-step
     *reinterpret_cast<uint4*>(sm.ones + tid * 16) = make_uint4(0x3F803F80u, 0u, 0u, 0u);      // bf16 (1.0, 1.0, 0...)
     *reinterpret_cast<uint4*>(sm.ones + kRunBytes + tid * 16) = make_uint4(0u, 0u, 0u, 0u);
-    for (int s = 0; s < 2; ++s) *reinterpret_cast<float4*>(sm.part[s][tid]) = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   fence_proxy_async_smem();
   tc_fence_before_sync();
@@ -498,8 +498,8 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
   } else {
     // ===================== compute group of slot s =====================
     // Runs the slot's tiles in order; per layer job: PRE (generated A-operand chunks), then POST
-    // (accumulator drain -> next layer's A operand / heads).  The compositing of tile n is cut into four
-    // stages that run between PRE and POST of layers 1..4 of tile n+1, i.e. while the tensor core works on
+    // (accumulator drain -> next layer's A operand / heads).  The compositing of tile n is cut into three
+    // stages that run between PRE and POST of layers 1..3 of tile n+1, i.e. while the tensor core works on
     // that tile's hidden layers.
     const int s = warp >> 3;
     const int n_slot = (n_local + 1 - s) / 2;
@@ -577,11 +577,11 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
       }
     };
 
-    // ---- deferred compositing of a finished tile (raw rows of the tile are in part[s]), in four stages
+    // ---- deferred compositing of a finished tile (raw rows of the tile are in part[s]), in three stages
     auto composite_stage = [&](const TileCtx& tc, int stage) {
       const PgnBf16Net& net = tc.pass == 0 ? net_c : net_f;
       if (stage == 1) {
-        group_bar_sync(s);                                   // every epilogue atomic of the tile has landed
+        group_bar_sync(s);                                   // every head partial of the tile has been stored
         const float br = net.b_rgb[0], bg = net.b_rgb[1], bb = net.b_rgb[2], ba = net.b_alpha[0];
         if (tc.pass == 0) {
           // coarse tile = 2 whole rays: head biases, composite, outputs, weights for the resampling
@@ -590,12 +590,13 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
             const long long ri = tc.ray0 + rl;
             float* zc = sm.cscratch[s][gwarp];
             float* wts = zc + 64;
-            float* rawrows = &sm.part[s][gwarp * PGN_S][0];
+            float* rawrows = &sm.part[s][0][gwarp * PGN_S][0];           // summed in place into the half-0 rows
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               float4* p = reinterpret_cast<float4*>(rawrows + (lane + 32 * h) * 4);
+              const float4 u = *reinterpret_cast<const float4*>(&sm.part[s][1][gwarp * PGN_S + lane + 32 * h][0]);
               float4 v = *p;
-              v.x += br; v.y += bg; v.z += bb; v.w += ba;
+              v.x += u.x + br; v.y += u.y + bg; v.z += u.z + bb; v.w += u.w + ba;
               *p = v;
             }
             const float nn = __ldg(near_far + ri * 2), ff = __ldg(near_far + ri * 2 + 1);
@@ -627,11 +628,12 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
           if (gwarp < kMaxTileRays && rl < tc.nr && rl * PGN_T < tc.row0 + kTM) {
             const long long ri = tc.ray0 + rl;
             const int s0 = max(0, tc.row0 - rl * PGN_T), s1 = min(PGN_T, tc.row0 + kTM - rl * PGN_T);
-            float* rawrows = &sm.part[s][rl * PGN_T + s0 - tc.row0][0];
+            float* rawrows = &sm.part[s][0][rl * PGN_T + s0 - tc.row0][0];
             for (int i = lane; i < s1 - s0; i += 32) {
               float4* p = reinterpret_cast<float4*>(rawrows + i * 4);
+              const float4 u = *reinterpret_cast<const float4*>(&sm.part[s][1][rl * PGN_T + s0 - tc.row0 + i][0]);
               float4 v = *p;
-              v.x += br; v.y += bg; v.z += bb; v.w += ba;
+              v.x += u.x + br; v.y += u.y + bg; v.z += u.z + bb; v.w += u.w + ba;
               *p = v;
             }
             __syncwarp();
@@ -666,34 +668,32 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
             if (out.z_fine) for (int i = lane; i < PGN_T; i += 32) out.z_fine[ri * PGN_T + i] = sm.zf[s][rl][i];
           }
         }
-      } else {
-        group_bar_sync(s);                                   // every reader of part[s] / writer of zf[s] is done
-        if (gtid < kTM) *reinterpret_cast<float4*>(sm.part[s][gtid]) = make_float4(0.f, 0.f, 0.f, 0.f);   // next tile of this slot
-        group_bar_sync(s);
       }
     };
 
     // ---- POST(job): drain the accumulator (epilogue)
+    float sig_keep = 0.f;             // this thread's sigma-head partial, carried from L7's epilogue to V's
     auto post = [&](int L, const TileCtx& tc) -> bool {
       const PgnBf16Net& net = (kStage || tc.pass == 0) ? net_c : net_f;
       { PROF_T0(); const bool okw = mbar_wait_s(acc_full_a, accs & 1, status, 303); if (timed) PROF_ADD(9); if (!okw) return false; }
       ++accs;
       tc_fence_after_sync();
       { PROF_T0();
-        if (L == 8) epilogue<2>(sm, tmem_acc, act_saddr, s, net.w_alpha, net.w_rgb, gwarp, lane);
-        else if (L == 7) epilogue<1>(sm, tmem_acc, act_saddr, s, net.w_alpha, net.w_rgb, gwarp, lane);
-        else epilogue<0>(sm, tmem_acc, act_saddr, s, net.w_alpha, net.w_rgb, gwarp, lane);
+        if (L == 8) epilogue<2>(sm, tmem_acc, act_saddr, s, net.w_alpha, net.w_rgb, gwarp, lane, sig_keep);
+        else if (L == 7) epilogue<1>(sm, tmem_acc, act_saddr, s, net.w_alpha, net.w_rgb, gwarp, lane, sig_keep);
+        else epilogue<0>(sm, tmem_acc, act_saddr, s, net.w_alpha, net.w_rgb, gwarp, lane, sig_keep);
         compute_arrive(act_ready_a, lane); if (timed) PROF_ADD(8); }
       if (kStage && L == 8) {
         group_bar_sync(s);
         if (gtid < kTM) {
-          float* p0 = sm.part[s][gtid];
+          const float* p0 = sm.part[s][0][gtid];
+          const float* p1 = sm.part[s][1][gtid];
           const int rows_valid = (int)max(0ll, min((long long)kTM, enc_rows_total - tc.unit * kTM));
           if (gtid < rows_valid) {
             float* o = raw_global + ((size_t)tc.unit * kTM + gtid) * 4;
-            o[0] = p0[0] + net.b_rgb[0]; o[1] = p0[1] + net.b_rgb[1]; o[2] = p0[2] + net.b_rgb[2]; o[3] = p0[3] + net.b_alpha[0];
+            o[0] = p0[0] + p1[0] + net.b_rgb[0]; o[1] = p0[1] + p1[1] + net.b_rgb[1];
+            o[2] = p0[2] + p1[2] + net.b_rgb[2]; o[3] = p0[3] + p1[3] + net.b_alpha[0];
           }
-          *reinterpret_cast<float4*>(p0) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         group_bar_sync(s);
       }
@@ -757,13 +757,13 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
         make_ctx(i, k, tc);
         for (int L = 0; L < 9; ++L) {
           if (!pre(L, tc)) goto done;
-          if (!kStage && pending && L >= 1 && L <= 4) { PROF_T0(); composite_stage(prev, L); if (timed) PROF_ADD(11); }
+          if (!kStage && pending && L >= 1 && L <= 3) { PROF_T0(); composite_stage(prev, L); if (timed) PROF_ADD(11); }
           if (!post(L, tc)) goto done;
         }
         if (!kStage) { prev = tc; pending = true; }
       }
     }
-    if (pending) for (int st = 1; st <= 4; ++st) composite_stage(prev, st);
+    if (pending) for (int st = 1; st <= 3; ++st) composite_stage(prev, st);
   }
 done:
   if (kProf) {
