@@ -29,7 +29,21 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FLOP_PER_RAY = 248_205_312          # 144 samples x 1,723,648 FLOP (un-padded nn.Linear MACs x 2)
-N_POSES = 8                          # distinct synthetic poses cycled through the steps
+N_POSES = 5                          # distinct synthetic poses cycled through the steps (rank r starts at pose r:
+                                     # every rank renders the same pool, different images at any one time)
+
+
+def ncu_traffic():
+    """DRAM bytes of one launch of the dominant kernel from the committed ncu capture (profiles/)."""
+    path = os.path.join(ROOT, "profiles", "r1_bf16_render_512.json")
+    try:
+        prof = json.load(open(path))
+        m = prof["kernels"][0]["metrics"]
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        rd, wr = m["dram__bytes_read.sum"], m["dram__bytes_write.sum"]
+        return float(rd["value"]) * scale[rd["unit"]] + float(wr["value"]) * scale[wr["unit"]]
+    except Exception:  # noqa: BLE001
+        return None
 
 
 def measured_peaks():
@@ -74,7 +88,7 @@ def make_jobs(res, rank, world):
     from posegen_b200 import synthetic as syn
     jobs = []
     for i in range(N_POSES):
-        frame = syn.synthetic_frame(100 + rank * N_POSES + i, res, res)
+        frame = syn.synthetic_frame(100 + (rank + i) % N_POSES, res, res)
         jobs.append((frame, syn.ray_batch(frame.rays_o, frame.rays_d)))
     return jobs
 
@@ -144,6 +158,7 @@ def run_ours(args, rank, world, local):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     n_max = max(rb.shape[0] for _, rb in jobs)
     gather_buf = torch.empty((world, n_max, 3), device=dev) if world > 1 else None
+    pad_buf = torch.zeros((n_max, 3), device=dev) if world > 1 else None
 
     def barrier():
         if world > 1:
@@ -154,9 +169,8 @@ def run_ours(args, rank, world, local):
         rb, sk, cy = dev_in[i % N_POSES]
         ret = eng.render(rb, sk, cy, nanfill_chunk=4096, precision=args.precision, return_alpha=False)
         if world > 1:
-            pad = torch.zeros((n_max, 3), device=dev)
-            pad[:rb.shape[0]] = ret["rgb_map"]
-            dist.all_gather_into_tensor(gather_buf.view(-1, 3), pad)
+            pad_buf[:rb.shape[0]] = ret["rgb_map"]          # rows beyond this pose's ray count are stale padding
+            dist.all_gather_into_tensor(gather_buf.view(-1, 3), pad_buf)
         return rb.shape[0]
 
     def e2e_step(i):
@@ -234,7 +248,10 @@ def run_ours(args, rank, world, local):
                 "api": "posegen_b200.RayCaster.forward (pinned host ray_batch/skts/cyls -> device, result rows -> host)"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "achieved": per_gpu_tflops, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                     "frac": per_gpu_tflops / peaks["bf16_sustained"], "traffic": None,
+                     "frac": per_gpu_tflops / peaks["bf16_sustained"],
+                     "traffic": ncu_traffic() if args.precision == "bf16" else None,
+                     "traffic_note": "DRAM bytes read+written by one launch (239,148-ray frame), ncu --set full, profiles/r1_bf16_render_512.json; "
+                                     "algorithmic bytes per launch = 84 B/ray + 2 x 1.83 MB weights = 23.7 MB (HBM is not the bound)",
                      "peak_source": f"{peaks['src']} bf16 sustained (kernel runs >100 ms per launch); burst {peaks['bf16_burst']}",
                      "flop_per_ray": FLOP_PER_RAY, "kernel": "pgn_render_bf16_kernel" if args.precision == "bf16" else "pgn_render_fp32_kernel",
                      "note": "algorithmic FLOPs (reference nn.Linear MACs x2); whole-step device time (near/far pre-pass included)"},

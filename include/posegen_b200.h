@@ -209,11 +209,11 @@ PGN_API int  pgn_compose_frame(pgn_context* ctx, int32_t H, int32_t W, int32_t x
                        const float* rgb_map, const float* acc_map, float bg, float* image, void* stream);
 
 /* per-role phase timers of the bf16 render kernel (cycles of pipeline slot 0, averaged over CTAs, of
- * the LAST launch made while enabled): out16 may be NULL.  Slots: 3 issuer total, 4 producer-wait-slot,
+ * the LAST launch made while enabled): out32 (32 values) may be NULL.  Slots: 3 issuer total, 4 producer-wait-slot,
  * 5 producer total, 6 encode_x, 7 encode_d, 8 epilogue, 9 compute-wait-accumulator,
  * 10 compute-wait-staging-free, 11 compositing, 12 compute total, 13 compute-wait-act-free,
- * 15 chunk store + arrive. */
-PGN_API int  pgn_debug_phase_timers(pgn_context* ctx, int32_t enable, uint64_t* out16);
+ * 15 chunk store + arrive, 16..24 compute-wait-accumulator per layer L0..L7,V, 25..27 PRE elapsed of L0, L5, V. */
+PGN_API int  pgn_debug_phase_timers(pgn_context* ctx, int32_t enable, uint64_t* out32);
 
 /* bring-up probe of the tcgen05 plumbing: D[128,N] = A[128,K] * B[N,K]^T with bf16 inputs
  * and fp32 accumulation, one CTA.  variant bit 1 selects the CTA-pair form (cta_group::2, UMMA M=256):

@@ -55,7 +55,7 @@ struct pgn_context {
   float* d_fold;
   PgnBf16Net bf16[2];
   int* d_status;
-  unsigned long long* d_prof;   // optional phase timers [num_sms][16]
+  unsigned long long* d_prof;   // optional phase timers [num_sms][32]
   bool prof_on;
   float* d_c2w;
   int64_t launches;
@@ -92,8 +92,8 @@ int pgn_create(const pgn_config* cfg, pgn_context** out) {
   PGN_CUDA(cudaMalloc(&c->d_sc, sizeof(PgnScalars)));
   PGN_CUDA(cudaMalloc(&c->d_status, sizeof(int)));
   PGN_CUDA(cudaMemset(c->d_status, 0, sizeof(int)));
-  PGN_CUDA(cudaMalloc(&c->d_prof, (size_t)c->num_sms * 16 * sizeof(unsigned long long)));
-  PGN_CUDA(cudaMemset(c->d_prof, 0, (size_t)c->num_sms * 16 * sizeof(unsigned long long)));
+  PGN_CUDA(cudaMalloc(&c->d_prof, (size_t)c->num_sms * 32 * sizeof(unsigned long long)));
+  PGN_CUDA(cudaMemset(c->d_prof, 0, (size_t)c->num_sms * 32 * sizeof(unsigned long long)));
   PGN_CUDA(cudaMalloc(&c->d_c2w, 12 * sizeof(float)));
   PGN_CUDA(cudaMalloc(&c->d_fold, (128 * 256 + 128) * sizeof(float)));
   for (int n = 0; n < 2; ++n) {
@@ -318,14 +318,14 @@ int pgn_compose_frame(pgn_context* c, int32_t H, int32_t W, int32_t x0, int32_t 
   return PGN_OK;
 }
 
-int pgn_debug_phase_timers(pgn_context* c, int32_t enable, uint64_t* out16) {
+int pgn_debug_phase_timers(pgn_context* c, int32_t enable, uint64_t* out32) {
   if (!c) return fail(PGN_E_INVALID, "pgn_debug_phase_timers: null context");
   PGN_CUDA(cudaSetDevice(c->cfg.device));
-  if (out16) {
-    const size_t n = (size_t)c->num_sms * 16;
+  if (out32) {
+    const size_t n = (size_t)c->num_sms * 32;
     unsigned long long* h = new unsigned long long[n];
     PGN_CUDA(cudaMemcpy(h, c->d_prof, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-    for (int k = 0; k < 16; ++k) { unsigned long long s = 0; for (int b = 0; b < c->num_sms; ++b) s += h[(size_t)b * 16 + k]; out16[k] = s / (unsigned long long)c->num_sms; }
+    for (int k = 0; k < 32; ++k) { unsigned long long s = 0; for (int b = 0; b < c->num_sms; ++b) s += h[(size_t)b * 32 + k]; out32[k] = s / (unsigned long long)c->num_sms; }
     delete[] h;
   }
   c->prof_on = enable != 0;

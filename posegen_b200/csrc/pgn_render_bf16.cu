@@ -313,6 +313,73 @@ __device__ __forceinline__ void chunk_arrive(uint32_t bar, int lane) {
 }
 __device__ __forceinline__ void group_bar_sync(int slot) { asm volatile("bar.sync %0, 256;\n" ::"r"(slot + 1) : "memory"); }
 
+// ------------------------------------------------------------------ MMA issue (one warp per slot, leader CTA)
+// Layer kinds and their static structure (pgn_bf16_layout.h): K-steps, activation K-steps, chunk size, fill size,
+// and the weight-ring stage the layer starts on (fills per tile: L0 16 | H 9 | L5 24 | V 17; 111 = 0 mod 3, so every
+// layer kind always starts on the same ring stage; chunks per layer are multiples of 3, so chunk c always
+// uses staging buffer c % 3).
+constexpr int kKindL0 = 0, kKindH = 1, kKindL5 = 2, kKindV = 3;
+static_assert(kWStages == 3 && kStgBufs == 3, "issue_layer's static ring schedule assumes 3-deep rings");
+static_assert((pgn_layer_ksteps(0) + 1) / 2 == 16 && (pgn_layer_ksteps(1) + 1) / 2 == 9 && (pgn_layer_ksteps(5) + 1) / 2 == 24 &&
+              (pgn_layer_ksteps(8) + 3) / 4 == 17, "fills per layer changed: recompute the static ring stages");
+
+struct IssuerCtx {
+  uint32_t w_full0, w_empty0, stg_full0, stg_empty0, acc_full, act_free;
+  uint32_t act_lo, ones_lo, ring_lo, tmem_acc;
+  uint32_t wph, sph;            // per-stage / per-buffer phase bits
+  volatile int* status;
+};
+
+template <int KIND>
+__device__ __forceinline__ bool issue_layer(IssuerCtx& ic) {
+  constexpr int L = KIND == kKindL0 ? 0 : (KIND == kKindH ? 1 : (KIND == kKindL5 ? 5 : 8));
+  constexpr int n = pgn_layer_n(L), nh = n / 2;
+  constexpr int ks_total = pgn_layer_ksteps(L), kpf = pgn_ks_per_fill(L);
+  constexpr int ks_act = pgn_layer_kact(L) / 16;
+  constexpr int chunk_ks = pgn_layer_chunk_ks(L);
+  constexpr bool has_chunks = pgn_layer_chunks(L) != 0;
+  constexpr int stage0 = KIND == kKindL0 ? 0 : 1;
+  constexpr uint32_t idesc = umma_idesc_bf16(2 * kTM, n);
+  constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);                 // SBO = 128 B, descriptor version 1
+  constexpr uint32_t b_lbo = ((nh * 16u) >> 4) << 16;                    // B: LBO = (N/2)*16 B
+  constexpr uint32_t b_step = (nh * 32u) >> 4;                           // one K-step of this CTA's B half
+  constexpr uint32_t kAStep = (2 * kRunBytes) >> 4;                      // one K-step of A (two runs)
+#pragma unroll
+  for (int ks = 0; ks < ks_total; ++ks) {
+    const int f = ks / kpf, st = (stage0 + f) % kWStages;
+    if (ks % kpf == 0) {                                                  // ---- next weight fill
+      if (!mbar_wait_s(ic.w_full0 + st * 8, (ic.wph >> st) & 1u, ic.status, 202)) return false;
+      ic.wph ^= 1u << st;
+      tc_fence_after_sync();
+    }
+    uint32_t a_lo;
+    bool chunk_end = false;
+    int sb = 0;
+    if (ks == ks_total - 1) {
+      a_lo = ic.ones_lo;                                                  // bias K-step
+    } else if (ks < ks_act) {
+      a_lo = ic.act_lo + (uint32_t)ks * kAStep;
+    } else {
+      const int cs = ks - ks_act, c = cs / chunk_ks, ce = cs % chunk_ks;
+      sb = c % kStgBufs;
+      if (ce == 0) {
+        if (!mbar_wait_s(ic.stg_full0 + sb * 8, (ic.sph >> sb) & 1u, ic.status, 203)) return false;
+        ic.sph ^= 1u << sb;
+        tc_fence_after_sync();
+      }
+      a_lo = ic.act_lo + (uint32_t)sb * (uint32_t)(kStgBytes >> 4) + (uint32_t)ce * kAStep;
+      chunk_end = ce == chunk_ks - 1;
+    }
+    const uint32_t b_lo = (ic.ring_lo + (uint32_t)st * (kWStageBytes >> 4) + (uint32_t)(ks % kpf) * b_step) | b_lbo;
+    umma_bf16_2cta_elect(ic.tmem_acc, ((uint64_t)kDescHi << 32) | a_lo, ((uint64_t)kDescHi << 32) | b_lo, idesc, ks > 0 ? 1u : 0u);
+    if (chunk_end) umma_commit_2cta_elect_s(ic.stg_empty0 + sb * 8);
+    if (has_chunks && ks_act > 0 && ks == ks_act - 1) umma_commit_2cta_elect_s(ic.act_free);   // act[s] may be overwritten by chunks
+    if (ks % kpf == kpf - 1 || ks == ks_total - 1) umma_commit_2cta_elect_s(ic.w_empty0 + st * 8);
+  }
+  umma_commit_2cta_elect_s(ic.acc_full);
+  return true;
+}
+
 // optional phase timers (cycles, one elected thread per role of SLOT 0, accumulated per CTA):
 //  3 issuer total | 4 producer wait w_empty | 5 producer total
 //  6 encode_x | 7 encode_d | 8 epilogue | 9 wait acc_full | 10 wait stg_empty | 11 composite | 12 compute total
@@ -372,7 +439,7 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
   cluster_sync_all();
   tc_fence_after_sync();
   const uint32_t tmem_base = sm.tmem_base;
-  unsigned long long pacc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  unsigned long long pacc[32] = {};
   const long long kernel_t0 = kProf ? clock64() : 0;
 
   if (warp >= kProducerWarp0 && warp < kProducerWarp0 + 2) {
@@ -425,72 +492,47 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
       }
     } else {
       // ===================== MMA issuer of slot s (leader CTA): UMMA M=256 over both CTAs =====================
-      // The whole warp runs this loop convergently; one elected lane issues each tcgen05 instruction.
-      uint32_t stage = 0, wphase = 0;        // weight ring cursor
-      uint32_t sbuf = 0, sphase = 0;         // staging ring cursor
-      uint32_t jobs = 0;                     // jobs already issued (act_ready phase)
-      const uint32_t w_full0 = SADDR(w_full) + s * kWStages * 8, w_empty0 = SADDR(w_empty) + s * kWStages * 8;
-      const uint32_t stg_full0 = SADDR(stg_full) + s * kStgBufs * 8, stg_empty0 = SADDR(stg_empty) + s * kStgBufs * 8;
-      const uint32_t act_ready_a = SADDR(act_ready) + s * 8, acc_full_a = SADDR(acc_full) + s * 8, act_free_a = SADDR(act_free) + s * 8;
-      const uint32_t kDescHi = (128u >> 4) | (1u << 14);                 // SBO = 128 B, descriptor version 1
+      // The whole warp runs this code convergently; one elected lane issues each tcgen05 instruction.
+      // A single warp retires roughly one instruction per 5-6 cycles, so a K-step (131 cycles of tensor
+      // time at N=256) leaves room for ~20 instructions: every layer kind is fully unrolled
+      // (issue_layer<KIND>) so that operand descriptors and barrier addresses are base + immediate.
+      IssuerCtx ic;
+      ic.w_full0 = SADDR(w_full) + s * kWStages * 8; ic.w_empty0 = SADDR(w_empty) + s * kWStages * 8;
+      ic.stg_full0 = SADDR(stg_full) + s * kStgBufs * 8; ic.stg_empty0 = SADDR(stg_empty) + s * kStgBufs * 8;
+      ic.acc_full = SADDR(acc_full) + s * 8; ic.act_free = SADDR(act_free) + s * 8;
       const uint32_t a_lbo = (uint32_t)(kRunBytes >> 4) << 16;           // A: LBO = 2048 B
-      const uint32_t act_lo = ((SADDR(act) + s * kActBytes) >> 4) | a_lbo;
-      const uint32_t ones_lo = (SADDR(ones) >> 4) | a_lbo;
-      const uint32_t ring_lo = (SADDR(wring) + s * kWStages * kWStageBytes) >> 4;
-      const uint32_t tmem_acc = tmem_base + (uint32_t)s * 256u;
-      constexpr uint32_t kAStep = (2 * kRunBytes) >> 4;                  // one K-step of A (two runs)
+      ic.act_lo = ((SADDR(act) + s * kActBytes) >> 4) | a_lbo;
+      ic.ones_lo = (SADDR(ones) >> 4) | a_lbo;
+      ic.ring_lo = (SADDR(wring) + s * kWStages * kWStageBytes) >> 4;
+      ic.tmem_acc = tmem_base + (uint32_t)s * 256u;
+      ic.wph = 0; ic.sph = 0;
+      ic.status = status;
+      const uint32_t act_ready_a = SADDR(act_ready) + s * 8;
+      uint32_t jobs = 0;                     // jobs already issued (act_ready phase)
       for (int i = 0; i < n_slot; ++i) {
         for (int k = 0; k < kTiles; ++k) {
+#pragma unroll 1
           for (int L = 0; L < 9; ++L) {
-            const uint32_t n = pgn_layer_n(L), nh = n / 2;
-            const int ks_total = pgn_layer_ksteps(L), kpf = pgn_ks_per_fill(L);
-            const int ks_act = pgn_layer_kact(L) / 16;
-            const int chunk_ks = pgn_layer_chunk_ks(L);
-            const bool has_chunks = pgn_layer_chunks(L) != 0;
-            const uint32_t idesc = umma_idesc_bf16(2 * kTM, n);
-            const uint32_t b_lbo = ((nh * 16u) >> 4) << 16;                  // B: LBO = (N/2)*16 B
-            const uint32_t b_step = (nh * 32u) >> 4;                         // one K-step of this CTA's B half
             // the previous job of this slot must have been drained (its epilogue wrote act[s] / freed the accumulator)
             if (jobs > 0) {
+              PROF_T0();
               if (!mbar_wait_s(act_ready_a, (jobs - 1) & 1, status, 201)) goto done;
               tc_fence_after_sync();
+              PROF_ADD(2);
             }
             ++jobs;
-            int ks = 0, ce = 0;
-            uint32_t accum = 0;
-            while (ks < ks_total) {
-              // ---- one weight fill (kpf K-steps, fewer at the end of the layer)
-              if (!mbar_wait_s(w_full0 + stage * 8, wphase, status, 202)) goto done;
-              tc_fence_after_sync();
-              uint32_t b_lo = (ring_lo + stage * (kWStageBytes >> 4)) | b_lbo;
-              const int ks_end = min(ks + kpf, ks_total);
-              for (; ks < ks_end; ++ks, b_lo += b_step) {
-                uint32_t a_lo;
-                bool chunk_end = false;
-                if (ks == ks_total - 1) {
-                  a_lo = ones_lo;                                   // bias K-step
-                } else if (ks < ks_act) {
-                  a_lo = act_lo + (uint32_t)ks * kAStep;
-                } else {
-                  if (ce == 0) {
-                    if (!mbar_wait_s(stg_full0 + sbuf * 8, sphase, status, 203)) goto done;
-                    tc_fence_after_sync();
-                  }
-                  a_lo = act_lo + sbuf * (uint32_t)(kStgBytes >> 4) + (uint32_t)ce * kAStep;
-                  if (++ce == chunk_ks) { ce = 0; chunk_end = true; }
-                }
-                umma_bf16_2cta_elect(tmem_acc, ((uint64_t)kDescHi << 32) | a_lo, ((uint64_t)kDescHi << 32) | b_lo, idesc, accum);
-                accum = 1;
-                if (chunk_end) {
-                  umma_commit_2cta_elect_s(stg_empty0 + sbuf * 8);
-                  if (++sbuf == kStgBufs) { sbuf = 0; sphase ^= 1; }
-                }
-                if (has_chunks && ks_act > 0 && ks == ks_act - 1) umma_commit_2cta_elect_s(act_free_a);   // act[s] may be overwritten by chunks
-              }
-              umma_commit_2cta_elect_s(w_empty0 + stage * 8);
-              if (++stage == kWStages) { stage = 0; wphase ^= 1; }
+            const long long t_job0 = kProf ? clock64() : 0;
+            bool ok;
+            if (L == 0) ok = issue_layer<kKindL0>(ic);
+            else if (L == 5) ok = issue_layer<kKindL5>(ic);
+            else if (L == 8) ok = issue_layer<kKindV>(ic);
+            else ok = issue_layer<kKindH>(ic);
+            if (!ok) goto done;
+            if (kProf && s == 0 && L != 0 && L != 5 && L != 8) {      // hidden layers: issue time and time until the accumulator is complete
+              pacc[28] += (unsigned long long)(clock64() - t_job0);
+              mbar_wait_s(ic.acc_full, (jobs - 1) & 1, status, 204);
+              pacc[29] += (unsigned long long)(clock64() - t_job0);
             }
-            umma_commit_2cta_elect_s(acc_full_a);
           }
         }
       }
@@ -675,7 +717,7 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
     float sig_keep = 0.f;             // this thread's sigma-head partial, carried from L7's epilogue to V's
     auto post = [&](int L, const TileCtx& tc) -> bool {
       const PgnBf16Net& net = (kStage || tc.pass == 0) ? net_c : net_f;
-      { PROF_T0(); const bool okw = mbar_wait_s(acc_full_a, accs & 1, status, 303); if (timed) PROF_ADD(9); if (!okw) return false; }
+      { PROF_T0(); const bool okw = mbar_wait_s(acc_full_a, accs & 1, status, 303); if (timed) { PROF_ADD(9); PROF_ADD(16 + L); } if (!okw) return false; }
       ++accs;
       tc_fence_after_sync();
       { PROF_T0();
@@ -756,7 +798,7 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
       for (int k = 0; k < kTiles; ++k) {
         make_ctx(i, k, tc);
         for (int L = 0; L < 9; ++L) {
-          if (!pre(L, tc)) goto done;
+          { PROF_T0(); const bool okp = pre(L, tc); if (timed && (L == 0 || L == 5 || L == 8)) PROF_ADD(L == 0 ? 25 : (L == 5 ? 26 : 27)); if (!okp) goto done; }
           if (!kStage && pending && L >= 1 && L <= 3) { PROF_T0(); composite_stage(prev, L); if (timed) PROF_ADD(11); }
           if (!post(L, tc)) goto done;
         }
@@ -767,12 +809,14 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
   }
 done:
   if (kProf) {
-    unsigned long long* pp = prof + (size_t)blockIdx.x * 16;
+    unsigned long long* pp = prof + (size_t)blockIdx.x * 32;
     const unsigned long long total = (unsigned long long)(clock64() - kernel_t0);
-    if (warp == kIssuerWarp0 && lane == 0) { pp[0] = 0; pp[1] = 0; pp[2] = 0; pp[3] = total; }
+    if (warp == kIssuerWarp0 && lane == 0 && rank == 0) { pp[0] = pacc[0]; pp[1] = pacc[1]; pp[2] = pacc[2]; pp[3] = total; pp[28] = pacc[28]; pp[29] = pacc[29]; }
+    if (warp == kIssuerWarp0 && lane == 0 && rank == 1) { pp[0] = 0; pp[1] = 0; pp[2] = 0; pp[3] = total; pp[28] = 0; pp[29] = 0; }
     if (warp == kProducerWarp0 && lane == 0) { pp[4] = pacc[4]; pp[5] = total; }
     if (tid == 0) { pp[6] = pacc[6]; pp[7] = pacc[7]; pp[8] = pacc[8]; pp[9] = pacc[9]; pp[10] = pacc[10]; pp[11] = pacc[11];
-                    pp[12] = total; pp[13] = pacc[13]; pp[14] = pacc[14]; pp[15] = pacc[15]; }
+                    pp[12] = total; pp[13] = pacc[13]; pp[14] = pacc[14]; pp[15] = pacc[15];
+                    for (int k = 16; k < 28; ++k) pp[k] = pacc[k]; }
   }
   tc_fence_before_sync();
   __syncthreads();

@@ -238,11 +238,13 @@ class Engine:
 
     PHASES = ["issuer_wait_weights", "issuer_wait_staging", "issuer_wait_act", "issuer_total", "producer_wait_slot",
               "producer_total", "encode_x", "encode_d", "epilogue", "wait_acc", "wait_stg_free", "composite", "compute_total",
-              "wait_act_free", "tables", "store_arrive"]
+              "wait_act_free", "tables", "store_arrive",
+              "wacc_L0", "wacc_L1", "wacc_L2", "wacc_L3", "wacc_L4", "wacc_L5", "wacc_L6", "wacc_L7", "wacc_V",
+              "pre_L0", "pre_L5", "pre_V", "hidden_issue", "hidden_complete", "-", "-"]
 
     def phase_timers(self, enable=True, read=False):
         """Enable/disable the bf16 kernel's phase timers; read=True returns the last launch's averages (cycles)."""
-        buf = (C.c_uint64 * 16)()
+        buf = (C.c_uint64 * 32)()
         _lib.check(self.lib.pgn_debug_phase_timers(self.handle, 1 if enable else 0, buf if read else None))
         return {n: int(buf[i]) for i, n in enumerate(self.PHASES) if n != "-"} if read else None
 
