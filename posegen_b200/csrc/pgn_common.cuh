@@ -411,6 +411,88 @@ __device__ __forceinline__ void pgn_sample_pdf_draw_warp(const float* __restrict
   __syncwarp();
 }
 
+// ---------------------------------------------------------------------------
+// bf16-tier variants of the two parts (same algorithm, cheaper arithmetic): the pdf sum / cumsum run in
+// fp32, and the 16 draws are independent per-lane binary searches instead of 16 warp-wide ballots; the
+// merge ranks use binary searches over the (sorted) coarse z and the (non-decreasing) samples, which give
+// the same counts as the exhaustive comparisons above.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void pgn_sample_pdf_cdf_warp_fast(const float* __restrict__ z, const float* __restrict__ weights,
+                                                             int lane, float* scratch) {
+  float* cdf = scratch;        // [63] (+1 pad)
+  float* bins = scratch + 64;  // [63]
+  const float w0 = (lane < 62) ? weights[1 + lane] + 1e-5f : 0.0f;
+  const float w1 = (lane + 32 < 62) ? weights[1 + lane + 32] + 1e-5f : 0.0f;
+  float s = w0 + w1;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  const float inv = __fdividef(1.0f, s);
+  float c0 = w0 * inv, c1 = w1 * inv;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const float u0 = __shfl_up_sync(0xffffffffu, c0, off), u1 = __shfl_up_sync(0xffffffffu, c1, off);
+    if (lane >= off) { c0 += u0; c1 += u1; }
+  }
+  c1 += __shfl_sync(0xffffffffu, c0, 31);
+  if (lane == 0) cdf[0] = 0.0f;
+  cdf[1 + lane] = c0;
+  if (lane + 32 < 62) cdf[33 + lane] = c1;
+  bins[lane] = 0.5f * (z[lane + 1] + z[lane]);
+  if (lane + 32 < 63) bins[lane + 32] = 0.5f * (z[lane + 33] + z[lane + 32]);
+  __syncwarp();
+}
+
+__device__ __forceinline__ void pgn_sample_pdf_draw_warp_fast(const float* __restrict__ z, const float* __restrict__ u_det, int lane,
+                                                              float* scratch, float* z_samples, float* z_sorted, int* pdf_inds) {
+  float* cdf = scratch;
+  float* bins = scratch + 64;
+  float my_sample = 0.0f;
+  if (lane < PGN_I) {
+    const float u = u_det[lane];
+    int lo = 0, hi = 63;                                // ind = #{k in [0,63) : cdf[k] <= u}  (cdf is non-decreasing)
+#pragma unroll
+    for (int it = 0; it < 6; ++it) {
+      const int mid = (lo + hi) >> 1;
+      if (cdf[mid] <= u) lo = mid + 1; else hi = mid;
+    }
+    const int ind = lo;
+    const int below = max(ind - 1, 0), above = min(ind, 62);
+    const float cdb = cdf[below], cda = cdf[above];
+    float denom = cda - cdb;
+    if (denom < 1e-5f) denom = 1.0f;
+    const float t = __fdividef(u - cdb, denom);
+    my_sample = fmaf(t, bins[above] - bins[below], bins[below]);
+    if (pdf_inds) pdf_inds[lane] = ind;
+    if (z_samples) z_samples[lane] = my_sample;
+  }
+  __syncwarp();
+  float* samp = scratch;        // reuse (cdf no longer needed): samples in scratch[0..15]
+  if (lane < PGN_I) samp[lane] = my_sample;
+  __syncwarp();
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int i = lane + 32 * h;
+    const float zi = z[i];
+    int lo = 0, hi = PGN_I;                             // #{k : samp[k] < zi}
+#pragma unroll
+    for (int it = 0; it < 5; ++it) {
+      const int mid = (lo + hi) >> 1;
+      if (lo < hi) { if (samp[mid] < zi) lo = mid + 1; else hi = mid; }
+    }
+    z_sorted[i + lo] = zi;
+  }
+  if (lane < PGN_I) {
+    int lo = 0, hi = PGN_S;                             // #{i : z[i] <= my_sample}
+#pragma unroll
+    for (int it = 0; it < 7; ++it) {
+      const int mid = (lo + hi) >> 1;
+      if (lo < hi) { if (z[mid] <= my_sample) lo = mid + 1; else hi = mid; }
+    }
+    z_sorted[lane + lo] = my_sample;
+  }
+  __syncwarp();
+}
+
 __device__ __forceinline__ void pgn_sample_pdf_warp(const float* __restrict__ z, const float* __restrict__ weights,
                                                     const float* __restrict__ u_det, int lane, float* scratch,
                                                     float* z_samples, float* z_sorted,

@@ -135,8 +135,8 @@ __device__ __forceinline__ RowCtx make_row_ctx(const Smem& sm, const PgnScalars&
 // x chunk c (joints 4c..4c+3): thread (row, half) produces joints 4c+2*half, +1 -> 36 values + 4 zeros
 // = 5 runs of 8 at run index half*5+r.  The valid path is one basic block so the two joints interleave.
 template <bool kWriteW>
-__device__ __forceinline__ void encode_x_fast(Smem& sm, uint32_t jtab_saddr, const RowCtx& rc, float tau_v2, float tau_d2,
-                                              int slot, int chunk, int row, int half, uint32_t (&packed)[20]) {
+__device__ __forceinline__ void encode_x_fast(uint32_t wcache_saddr, uint32_t jtab_saddr, const RowCtx& rc, float tau_v2, float tau_d2,
+                                              int chunk, int row, int half, uint32_t (&packed)[20]) {
   const int j0 = chunk * 4 + half * 2;
   if (rc.valid) {
     const uint32_t jt = jtab_saddr + (uint32_t)(rc.tr * PGN_J + j0) * 32u;
@@ -152,7 +152,7 @@ __device__ __forceinline__ void encode_x_fast(Smem& sm, uint32_t jtab_saddr, con
       const float w = __fdividef(1.0f, 1.0f + ex2_approx(fmaf(tau_v2, v, __uint_as_float(qb.z))));   // 1 - sigmoid(tau (v - c))
       if (kWriteW) {
         const float wd = __fdividef(1.0f, 1.0f + ex2_approx(fmaf(tau_d2, v, __uint_as_float(qb.w))));
-        sm.wcache[slot][(j0 + jj) * kTM + row] = __float2half_rn(wd);
+        sts16(wcache_saddr + (uint32_t)((j0 + jj) * kTM + row) * 2u, __half_as_ushort(__float2half_rn(wd)));
       }
       float sn, cs;
       __sincosf(v, &sn, &cs);
@@ -171,7 +171,7 @@ __device__ __forceinline__ void encode_x_fast(Smem& sm, uint32_t jtab_saddr, con
       for (int i = 0; i < 9; ++i) packed[jj * 9 + i] = pack_bf16x2(vals[2 * i], vals[2 * i + 1]);
     }
   } else {
-    if (kWriteW) { sm.wcache[slot][j0 * kTM + row] = __float2half_rn(0.f); sm.wcache[slot][(j0 + 1) * kTM + row] = __float2half_rn(0.f); }
+    if (kWriteW) { sts16(wcache_saddr + (uint32_t)(j0 * kTM + row) * 2u, 0); sts16(wcache_saddr + (uint32_t)((j0 + 1) * kTM + row) * 2u, 0); }
 #pragma unroll
     for (int i = 0; i < 18; ++i) packed[i] = 0u;
   }
@@ -200,10 +200,10 @@ __device__ __forceinline__ void encode_x_store(uint32_t stg, int row, int half, 
 
 // d chunk c (joints 2c, 2c+1): thread (row, half) produces joint 2c+half -> 27 values + 5 zeros
 // = 4 runs at run index half*4+r.
-__device__ __forceinline__ void encode_d_fast(Smem& sm, uint32_t dtab_saddr, const RowCtx& rc, int slot, int chunk, int row, int half,
+__device__ __forceinline__ void encode_d_fast(uint32_t wcache_saddr, uint32_t dtab_saddr, const RowCtx& rc, int chunk, int row, int half,
                                               uint32_t (&packed)[20]) {
   const int j = chunk * 2 + half;
-  const float wd = rc.valid ? __half2float(sm.wcache[slot][j * kTM + row]) : 0.f;
+  const float wd = rc.valid ? __half2float(__ushort_as_half(lds16(wcache_saddr + (uint32_t)(j * kTM + row) * 2u))) : 0.f;
   const uint32_t tab = dtab_saddr + (uint32_t)(rc.tr * PGN_J + j) * 64u;   // 32 halfs = 4 x 16 B
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -528,11 +528,7 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
             else if (L == 8) ok = issue_layer<kKindV>(ic);
             else ok = issue_layer<kKindH>(ic);
             if (!ok) goto done;
-            if (kProf && s == 0 && L != 0 && L != 5 && L != 8) {      // hidden layers: issue time and time until the accumulator is complete
-              pacc[28] += (unsigned long long)(clock64() - t_job0);
-              mbar_wait_s(ic.acc_full, (jobs - 1) & 1, status, 204);
-              pacc[29] += (unsigned long long)(clock64() - t_job0);
-            }
+            if (kProf && s == 0 && L != 0 && L != 5 && L != 8) pacc[28] += (unsigned long long)(clock64() - t_job0);   // hidden layers: issue time
           }
         }
       }
@@ -552,6 +548,7 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
     const uint32_t act_saddr = SADDR(act) + s * kActBytes;
     const uint32_t jtab_saddr = SADDR(jtab) + s * (uint32_t)sizeof(sm.jtab[0]);
     const uint32_t dtab_saddr = SADDR(dtab) + s * (uint32_t)sizeof(sm.dtab[0]);
+    const uint32_t wcache_saddr = SADDR(wcache) + s * (uint32_t)sizeof(sm.wcache[0]);
     const uint32_t stg_full0 = SADDR(stg_full) + s * kStgBufs * 8, stg_empty0 = SADDR(stg_empty) + s * kStgBufs * 8;
     const uint32_t act_ready_a = SADDR(act_ready) + s * 8, acc_full_a = SADDR(acc_full) + s * 8, act_free_a = SADDR(act_free) + s * 8;
     const bool timed = kProf && s == 0;
@@ -703,10 +700,10 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
           float* wts = zc + 64;
           float* scr = zc + 128;
           if (stage == 2) {
-            pgn_sample_pdf_cdf_warp(zc, wts, lane, scr);
+            pgn_sample_pdf_cdf_warp_fast(zc, wts, lane, scr);
           } else {
-            pgn_sample_pdf_draw_warp(zc, sc.u_det, lane, scr, out.z_samples ? out.z_samples + ri * PGN_I : nullptr,
-                                     sm.zf[s][rl], out.pdf_inds ? out.pdf_inds + ri * PGN_I : nullptr, nullptr);
+            pgn_sample_pdf_draw_warp_fast(zc, sc.u_det, lane, scr, out.z_samples ? out.z_samples + ri * PGN_I : nullptr,
+                                          sm.zf[s][rl], out.pdf_inds ? out.pdf_inds + ri * PGN_I : nullptr);
             if (out.z_fine) for (int i = lane; i < PGN_T; i += 32) out.z_fine[ri * PGN_T + i] = sm.zf[s][rl][i];
           }
         }
@@ -764,13 +761,13 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
         if (L == 8) {
           PROF_T0();
           if (kStage) encode_d_stage(c, row, half, enc_rows, rows_valid, packed);
-          else encode_d_fast(sm, dtab_saddr, rc, s, c, row, half, packed);
+          else encode_d_fast(wcache_saddr, dtab_saddr, rc, c, row, half, packed);
           if (timed) PROF_ADD(7);
         } else {
           PROF_T0();
           if (kStage) encode_x_stage(c, row, half, enc_rows, rows_valid, packed);
-          else if (L == 5) encode_x_fast<true>(sm, jtab_saddr, rc, tau_v2, tau_d2, s, c, row, half, packed);
-          else encode_x_fast<false>(sm, jtab_saddr, rc, tau_v2, tau_d2, s, c, row, half, packed);
+          else if (L == 5) encode_x_fast<true>(wcache_saddr, jtab_saddr, rc, tau_v2, tau_d2, c, row, half, packed);
+          else encode_x_fast<false>(wcache_saddr, jtab_saddr, rc, tau_v2, tau_d2, c, row, half, packed);
           if (timed) PROF_ADD(6);
         }
       };

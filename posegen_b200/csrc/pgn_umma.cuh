@@ -155,6 +155,14 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16])
 __device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+__device__ __forceinline__ void sts16(uint32_t saddr, uint16_t v) {
+  asm volatile("st.shared.b16 [%0], %1;\n" ::"r"(saddr), "h"(v) : "memory");
+}
+__device__ __forceinline__ uint16_t lds16(uint32_t saddr) {
+  uint16_t v;
+  asm volatile("ld.shared.b16 %0, [%1];\n" : "=h"(v) : "r"(saddr));
+  return v;
+}
 __device__ __forceinline__ uint4 lds128(uint32_t saddr) {
   uint4 r;
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];\n" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(saddr));
