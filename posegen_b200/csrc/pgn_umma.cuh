@@ -77,10 +77,13 @@ __device__ __forceinline__ void cluster_sync_all() {
 __device__ __forceinline__ void mbar_arrive_expect_tx_s(uint32_t bar, uint32_t bytes) {
   asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}\n" ::"r"(bar), "r"(bytes) : "memory");
 }
+// try_wait with a suspend-time hint: the waiting warp is parked by the hardware until the phase completes
+// (or the hint expires) instead of spinning through the issue slots -- the render kernel has up to 20 warps
+// waiting on barriers at any time and runs at the board's power cap.
 __device__ __forceinline__ bool mbar_try_wait_s(uint32_t bar, uint32_t parity) {
   uint32_t ok;
-  asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
-               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}\n"
+               : "=r"(ok) : "r"(bar), "r"(parity), "r"(0x989680u) : "memory");
   return ok != 0;
 }
 __device__ __forceinline__ bool mbar_wait_s(uint32_t bar, uint32_t parity, volatile int* status, int code) {
