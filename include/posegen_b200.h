@@ -208,6 +208,24 @@ PGN_API int  pgn_generate_rays(pgn_context* ctx, int32_t H, int32_t W, float foc
 PGN_API int  pgn_compose_frame(pgn_context* ctx, int32_t H, int32_t W, int32_t x0, int32_t y0, int32_t x1, int32_t y1,
                        const float* rgb_map, const float* acc_map, float bg, float* image, void* stream);
 
+/* "next" row 2: forward kinematics on the device.  bones: device [n_poses,24,3] axis-angle,
+ * rest_pose: HOST [24,3] (already scaled, e.g. smpl_rest_pose * 0.4, run_gan.py:2032).  Replaces
+ * get_smpl_l2ws (core/utils/skeleton_utils.py:334-377), skts = inv(l2ws) / kps = l2ws[..., :3, 3]
+ * (run_gan.py:447-449) and get_kp_bounding_cylinder (skeleton_utils.py:635-685; cyl_extend = extend_mm * ext_scale,
+ * ratios 1.6 / 1.1 in the reference).  Outputs (device): skts [n,24,4,4], kps [n,24,3] (may be NULL),
+ * cyls [n,5] (may be NULL), l2ws [n,24,4,4] (may be NULL). */
+PGN_API int  pgn_pose_to_skts(pgn_context* ctx, const float* bones, const float* rest_pose, int32_t n_poses,
+                              float cyl_extend, float top_expand_ratio, float bot_expand_ratio,
+                              float* skts, float* kps, float* cyls, float* l2ws, void* stream);
+
+/* "next" row 4: rendered frame -> HMR input without the PNG round trip
+ * (run_gan.py:2057-2071, 2326, 2433-2445): optional uint8 quantisation, crop [y0:y1, x0:x1], /255,
+ * Normalize(mean, std), skimage.transform.resize(..., (3,R,R), anti_aliasing=True).
+ * image: device [H,W,3] in [0,1]; mean3/std3: HOST [3]; out: device [3,R,R]. */
+PGN_API int  pgn_frame_to_hmr_input(pgn_context* ctx, const float* image, int32_t H, int32_t W, int32_t x0, int32_t y0,
+                                    int32_t x1, int32_t y1, int32_t out_res, const float* mean3, const float* std3,
+                                    int32_t quantize_u8, float* out, void* stream);
+
 /* per-role phase timers of the bf16 render kernel (cycles of pipeline slot 0, averaged over CTAs, of
  * the LAST launch made while enabled): out32 (32 values) may be NULL.  Slots: 3 issuer total, 4 producer-wait-slot,
  * 5 producer total, 6 encode_x, 7 encode_d, 8 epilogue, 9 compute-wait-accumulator,

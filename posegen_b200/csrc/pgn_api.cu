@@ -58,6 +58,7 @@ struct pgn_context {
   unsigned long long* d_prof;   // optional phase timers [num_sms][32]
   bool prof_on;
   float* d_c2w;
+  float* d_rest;            // rest pose [24,3] of the last pgn_pose_to_skts call
   int64_t launches;
 };
 
@@ -95,6 +96,7 @@ int pgn_create(const pgn_config* cfg, pgn_context** out) {
   PGN_CUDA(cudaMalloc(&c->d_prof, (size_t)c->num_sms * 32 * sizeof(unsigned long long)));
   PGN_CUDA(cudaMemset(c->d_prof, 0, (size_t)c->num_sms * 32 * sizeof(unsigned long long)));
   PGN_CUDA(cudaMalloc(&c->d_c2w, 12 * sizeof(float)));
+  PGN_CUDA(cudaMalloc(&c->d_rest, PGN_J * 3 * sizeof(float)));
   PGN_CUDA(cudaMalloc(&c->d_fold, (128 * 256 + 128) * sizeof(float)));
   for (int n = 0; n < 2; ++n) {
     PGN_CUDA(cudaMalloc(&c->d_w[n], weight_floats() * sizeof(float)));
@@ -129,7 +131,7 @@ int pgn_create(const pgn_config* cfg, pgn_context** out) {
 void pgn_destroy(pgn_context* c) {
   if (!c) return;
   cudaSetDevice(c->cfg.device);
-  cudaFree(c->d_sc); cudaFree(c->d_status); cudaFree(c->d_c2w); cudaFree(c->d_fold);
+  cudaFree(c->d_sc); cudaFree(c->d_status); cudaFree(c->d_c2w); cudaFree(c->d_rest); cudaFree(c->d_fold);
   for (int n = 0; n < 2; ++n) {
     cudaFree(c->d_w[n]); cudaFree(c->d_b[n]); cudaFree(c->d_wt[n]); cudaFree(c->d_wstream[n]); cudaFree(c->d_bf16_aux[n]);
   }
@@ -314,6 +316,29 @@ int pgn_compose_frame(pgn_context* c, int32_t H, int32_t W, int32_t x0, int32_t 
   if (!c || !image || ((x1 > x0 && y1 > y0) && (!rgb_map || !acc_map))) return fail(PGN_E_INVALID, "pgn_compose_frame: bad argument");
   PGN_CUDA(cudaSetDevice(c->cfg.device));
   PGN_CUDA(pgn_launch_compose_frame(H, W, x0, y0, x1, y1, rgb_map, acc_map, bg, image, (cudaStream_t)stream));
+  c->launches++;
+  return PGN_OK;
+}
+
+int pgn_pose_to_skts(pgn_context* c, const float* bones, const float* rest_pose, int32_t n_poses, float cyl_extend,
+                     float top_expand_ratio, float bot_expand_ratio, float* skts, float* kps, float* cyls, float* l2ws,
+                     void* stream_) {
+  if (!c || !bones || !rest_pose || !skts || n_poses < 0) return fail(PGN_E_INVALID, "pgn_pose_to_skts: bad argument");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  PGN_CUDA(cudaSetDevice(c->cfg.device));
+  PGN_CUDA(cudaMemcpyAsync(c->d_rest, rest_pose, PGN_J * 3 * sizeof(float), cudaMemcpyHostToDevice, stream));
+  PGN_CUDA(pgn_launch_pose_fk(bones, c->d_rest, n_poses, cyl_extend, top_expand_ratio, bot_expand_ratio, skts, kps, cyls, l2ws, stream));
+  c->launches++;
+  return PGN_OK;
+}
+
+int pgn_frame_to_hmr_input(pgn_context* c, const float* image, int32_t H, int32_t W, int32_t x0, int32_t y0, int32_t x1,
+                           int32_t y1, int32_t out_res, const float* mean3, const float* std3, int32_t quantize_u8,
+                           float* out, void* stream) {
+  if (!c || !image || !out || !mean3 || !std3 || x0 < 0 || y0 < 0 || x1 > W || y1 > H || x1 <= x0 || y1 <= y0 || out_res <= 0)
+    return fail(PGN_E_INVALID, "pgn_frame_to_hmr_input: bad argument");
+  PGN_CUDA(cudaSetDevice(c->cfg.device));
+  PGN_CUDA(pgn_launch_hmr_input(image, H, W, x0, y0, x1, y1, out_res, mean3, std3, quantize_u8, out, (cudaStream_t)stream));
   c->launches++;
   return PGN_OK;
 }

@@ -62,6 +62,11 @@ cudaError_t pgn_launch_generate_rays(int H, int W, float focal, const float* c2w
 cudaError_t pgn_launch_compose_frame(int H, int W, int x0, int y0, int x1, int y1, const float* rgb, const float* acc,
                                      float bg, float* image, cudaStream_t stream);
 
+cudaError_t pgn_launch_pose_fk(const float* bones, const float* rest, int n_poses, float ext, float top_ratio, float bot_ratio,
+                               float* skts, float* kps, float* cyls, float* l2ws, cudaStream_t stream);
+cudaError_t pgn_launch_hmr_input(const float* image, int H, int W, int x0, int y0, int x1, int y1, int R,
+                                 const float* mean3, const float* std3, int quantize, float* out, cudaStream_t stream);
+
 // bring-up probe (pgn_probe.cu)
 cudaError_t pgn_launch_probe_umma(const float* A, const float* B, float* D, int K, int N, int variant, int* status,
                                   cudaStream_t stream);

@@ -273,3 +273,146 @@ cudaError_t pgn_launch_compose_frame(int H, int W, int x0, int y0, int x1, int y
   pgn_compose_frame_kernel<<<(unsigned)grid, block, 0, stream>>>(H, W, x0, y0, x1, y1, rgb, acc, bg, image);
   return cudaGetLastError();
 }
+
+// ---------------------------------------------------------------------------
+// forward kinematics on the device.
+//   axis-angle -> rotation (scipy Rotation.from_rotvec = Rodrigues)      core/utils/skeleton_utils.py:352
+//   kinematic chain l2w[i] = l2w[parent] @ [R_i | rest_i - rest_parent]  core/utils/skeleton_utils.py:334-377
+//   skts = inverse(l2ws) (closed-form rigid inverse), kps = l2ws[:, :3, 3]      run_gan.py:447-449
+//   cylinder (cx, cz, R, top, bot), head '-y'                             core/utils/skeleton_utils.py:635-685
+// One thread per pose; the chain is evaluated in fp64 like the numpy reference and rounded once.
+// ---------------------------------------------------------------------------
+__constant__ int c_smpl_parents[PGN_J] = {0, 0, 0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 9, 9, 12, 13, 14, 16, 17, 18, 19, 20, 21};
+
+__global__ void pgn_pose_fk_kernel(const float* __restrict__ bones, const float* __restrict__ rest, int n_poses,
+                                   float ext, float top_ratio, float bot_ratio,
+                                   float* __restrict__ skts, float* __restrict__ kps, float* __restrict__ cyls,
+                                   float* __restrict__ l2ws_out) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_poses) return;
+  double R[PGN_J][9], T[PGN_J][3];
+  for (int i = 0; i < PGN_J; ++i) {
+    const double rx = bones[(p * PGN_J + i) * 3], ry = bones[(p * PGN_J + i) * 3 + 1], rz = bones[(p * PGN_J + i) * 3 + 2];
+    const double th = sqrt(rx * rx + ry * ry + rz * rz);
+    double r[9];
+    if (th < 1e-12) {
+      r[0] = 1; r[1] = 0; r[2] = 0; r[3] = 0; r[4] = 1; r[5] = 0; r[6] = 0; r[7] = 0; r[8] = 1;
+    } else {
+      const double kx = rx / th, ky = ry / th, kz = rz / th, s = sin(th), c = cos(th), v = 1.0 - c;
+      r[0] = c + kx * kx * v;      r[1] = kx * ky * v - kz * s; r[2] = kx * kz * v + ky * s;
+      r[3] = ky * kx * v + kz * s; r[4] = c + ky * ky * v;      r[5] = ky * kz * v - kx * s;
+      r[6] = kz * kx * v - ky * s; r[7] = kz * ky * v + kx * s; r[8] = c + kz * kz * v;
+    }
+    if (i == 0) {
+      for (int k = 0; k < 9; ++k) R[0][k] = r[k];
+      for (int k = 0; k < 3; ++k) T[0][k] = rest[k];
+    } else {
+      const int pa = c_smpl_parents[i];
+      const double d[3] = {(double)rest[i * 3] - (double)rest[pa * 3], (double)rest[i * 3 + 1] - (double)rest[pa * 3 + 1],
+                           (double)rest[i * 3 + 2] - (double)rest[pa * 3 + 2]};
+      for (int a = 0; a < 3; ++a) {
+        for (int b = 0; b < 3; ++b)
+          R[i][a * 3 + b] = R[pa][a * 3] * r[b] + R[pa][a * 3 + 1] * r[3 + b] + R[pa][a * 3 + 2] * r[6 + b];
+        T[i][a] = R[pa][a * 3] * d[0] + R[pa][a * 3 + 1] * d[1] + R[pa][a * 3 + 2] * d[2] + T[pa][a];
+      }
+    }
+  }
+  double rad = 0.0, hmax = -1e300, hmin = 1e300;
+  for (int i = 0; i < PGN_J; ++i) {
+    float* s = skts + ((size_t)p * PGN_J + i) * 16;
+    for (int a = 0; a < 3; ++a) {           // [R^T | -R^T t]
+      for (int b = 0; b < 3; ++b) s[a * 4 + b] = (float)R[i][b * 3 + a];
+      s[a * 4 + 3] = (float)(-(R[i][a] * T[i][0] + R[i][3 + a] * T[i][1] + R[i][6 + a] * T[i][2]));
+    }
+    s[12] = 0.f; s[13] = 0.f; s[14] = 0.f; s[15] = 1.f;
+    if (l2ws_out) {
+      float* l = l2ws_out + ((size_t)p * PGN_J + i) * 16;
+      for (int a = 0; a < 3; ++a) { for (int b = 0; b < 3; ++b) l[a * 4 + b] = (float)R[i][a * 3 + b]; l[a * 4 + 3] = (float)T[i][a]; }
+      l[12] = 0.f; l[13] = 0.f; l[14] = 0.f; l[15] = 1.f;
+    }
+    if (kps) { kps[(p * PGN_J + i) * 3] = (float)T[i][0]; kps[(p * PGN_J + i) * 3 + 1] = (float)T[i][1]; kps[(p * PGN_J + i) * 3 + 2] = (float)T[i][2]; }
+    // the cylinder is computed from the fp32 key points like the reference (skeleton_utils.py:635-685 on kps arrays)
+    const float kx = (float)T[i][0] - (float)T[0][0], kz = (float)T[i][2] - (float)T[0][2];
+    rad = fmax(rad, (double)sqrtf(kx * kx + kz * kz));
+    const double h = -(double)(float)T[i][1];
+    hmax = fmax(hmax, h); hmin = fmin(hmin, h);
+  }
+  if (cyls) {
+    float* c = cyls + (size_t)p * 5;
+    c[0] = (float)T[0][0]; c[1] = (float)T[0][2]; c[2] = (float)rad + ext;
+    c[3] = -((float)hmax + ext * top_ratio); c[4] = -((float)hmin - ext * bot_ratio);
+  }
+}
+
+cudaError_t pgn_launch_pose_fk(const float* bones, const float* rest, int n_poses, float ext, float top_ratio, float bot_ratio,
+                               float* skts, float* kps, float* cyls, float* l2ws, cudaStream_t stream) {
+  if (n_poses <= 0) return cudaSuccess;
+  pgn_pose_fk_kernel<<<(n_poses + 63) / 64, 64, 0, stream>>>(bones, rest, n_poses, ext, top_ratio, bot_ratio, skts, kps, cyls, l2ws);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// rendered frame -> HMR input on the device (run_gan.py:2057-2071,2433-2445):
+//   uint8 quantisation of the saved PNG ((rgb*255).astype(uint8), run_gan.py:2326) -> crop [y0:y1, x0:x1] -> /255 ->
+//   Normalize(mean, std) -> skimage.transform.resize(img, (3, R, R), anti_aliasing=True) -> [3,R,R] fp32.
+// skimage's resize (>= 0.19) = scipy.ndimage.gaussian_filter(sigma = (scale-1)/2 per axis, truncate 4, mode 'mirror')
+// followed by scipy.ndimage.zoom(order=1, mode='mirror', grid_mode=True): x_in = (x_out + 0.5) * scale - 0.5.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int pgn_mirror(int i, int n) {        // scipy 'mirror': d c b | a b c d | c b a
+  if (n == 1) return 0;
+  const int period = 2 * (n - 1);
+  i = i % period;
+  if (i < 0) i += period;
+  return i < n ? i : period - i;
+}
+
+__global__ void pgn_hmr_input_kernel(const float* __restrict__ image, int H, int W, int x0, int y0, int cw, int ch, int R,
+                                     float m0, float m1, float m2, float s0, float s1, float s2, int quantize,
+                                     float* __restrict__ out) {
+  const int n = 3 * R * R;
+  const double sy = (double)ch / R, sx = (double)cw / R;
+  const double sig_y = fmax(0.0, (sy - 1.0) * 0.5), sig_x = fmax(0.0, (sx - 1.0) * 0.5);
+  const int ry = (int)(4.0 * sig_y + 0.5), rx = (int)(4.0 * sig_x + 0.5);
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
+    const int c = idx / (R * R), oy = (idx / R) % R, ox = idx % R;
+    const float mean = c == 0 ? m0 : (c == 1 ? m1 : m2), stdv = c == 0 ? s0 : (c == 1 ? s1 : s2);
+    auto pix = [&](int yy, int xx) -> double {            // normalised crop pixel with mirror extension
+      const int y = y0 + pgn_mirror(yy, ch), x = x0 + pgn_mirror(xx, cw);
+      float v = image[((size_t)y * W + x) * 3 + c];
+      if (quantize) v = floorf(fminf(fmaxf(v * 255.0f, 0.0f), 255.0f));      // astype(uint8) truncates
+      else v = v * 255.0f;
+      return (double)((v / 255.0f - mean) / stdv);
+    };
+    auto blurred = [&](int yy, int xx) -> double {        // separable Gaussian, evaluated at one (mirrored) location
+      yy = pgn_mirror(yy, ch); xx = pgn_mirror(xx, cw);
+      double acc = 0.0, wsum_y = 0.0;
+      for (int dy = -ry; dy <= ry; ++dy) {
+        const double wy = sig_y > 0.0 ? exp(-0.5 * dy * dy / (sig_y * sig_y)) : 1.0;
+        double row = 0.0, wsum_x = 0.0;
+        for (int dx = -rx; dx <= rx; ++dx) {
+          const double wx = sig_x > 0.0 ? exp(-0.5 * dx * dx / (sig_x * sig_x)) : 1.0;
+          row += wx * pix(yy + dy, xx + dx);
+          wsum_x += wx;
+        }
+        acc += wy * row / wsum_x;
+        wsum_y += wy;
+      }
+      return acc / wsum_y;
+    };
+    const double fy = (oy + 0.5) * sy - 0.5, fx = (ox + 0.5) * sx - 0.5;
+    const int iy = (int)floor(fy), ix = (int)floor(fx);
+    const double ty = fy - iy, tx = fx - ix;
+    const double v = (1.0 - ty) * ((1.0 - tx) * blurred(iy, ix) + tx * blurred(iy, ix + 1)) +
+                     ty * ((1.0 - tx) * blurred(iy + 1, ix) + tx * blurred(iy + 1, ix + 1));
+    out[idx] = (float)v;
+  }
+}
+
+cudaError_t pgn_launch_hmr_input(const float* image, int H, int W, int x0, int y0, int x1, int y1, int R,
+                                 const float* mean3, const float* std3, int quantize, float* out, cudaStream_t stream) {
+  const int n = 3 * R * R;
+  if (n <= 0) return cudaSuccess;
+  pgn_hmr_input_kernel<<<(n + 255) / 256, 256, 0, stream>>>(image, H, W, x0, y0, x1 - x0, y1 - y0, R, mean3[0], mean3[1], mean3[2],
+                                                            std3[0], std3[1], std3[2], quantize, out);
+  return cudaGetLastError();
+}

@@ -242,6 +242,34 @@ class Engine:
               "wacc_L0", "wacc_L1", "wacc_L2", "wacc_L3", "wacc_L4", "wacc_L5", "wacc_L6", "wacc_L7", "wacc_V",
               "pre_L0", "pre_L5", "pre_V", "hidden_issue", "hidden_complete", "-", "-"]
 
+    def pose_to_skts(self, bones, rest_pose, ext_scale=0.001, extend_mm=250., top_expand_ratio=1.6, bot_expand_ratio=1.1,
+                     return_l2ws=False):
+        """Device FK: bones [B,24,3] axis-angle (CUDA) -> skts [B,24,4,4], kps [B,24,3], cyls [B,5]."""
+        _check_f32_cuda(bones, "bones")
+        b = bones.contiguous()
+        n = b.shape[0]
+        rest = (C.c_float * 72)(*[float(v) for v in torch.as_tensor(rest_pose, dtype=torch.float32).reshape(-1).tolist()])
+        skts = torch.empty((n, 24, 4, 4), dtype=torch.float32, device=b.device)
+        kps = torch.empty((n, 24, 3), dtype=torch.float32, device=b.device)
+        cyls = torch.empty((n, 5), dtype=torch.float32, device=b.device)
+        l2ws = torch.empty((n, 24, 4, 4), dtype=torch.float32, device=b.device) if return_l2ws else None
+        _lib.check(self.lib.pgn_pose_to_skts(self.handle, _ptr(b), rest, n, float(extend_mm * ext_scale), float(top_expand_ratio),
+                                             float(bot_expand_ratio), _ptr(skts), _ptr(kps), _ptr(cyls), _ptr(l2ws), self._stream()))
+        return (skts, kps, cyls, l2ws) if return_l2ws else (skts, kps, cyls)
+
+    def frame_to_hmr_input(self, image, crop=(100, 100, 412, 412), out_res=224, mean=(0.485, 0.456, 0.406),
+                           std=(0.485, 0.456, 0.406), quantize_u8=True):
+        """Rendered frame [H,W,3] in [0,1] (CUDA) -> HMR input [3,out_res,out_res].
+        crop = (x0, y0, x1, y1); the reference normalises with std = mean (run_gan.py:2343)."""
+        _check_f32_cuda(image, "image")
+        img = image.contiguous()
+        H, W = img.shape[0], img.shape[1]
+        out = torch.empty((3, out_res, out_res), dtype=torch.float32, device=img.device)
+        m3, s3 = (C.c_float * 3)(*mean), (C.c_float * 3)(*std)
+        _lib.check(self.lib.pgn_frame_to_hmr_input(self.handle, _ptr(img), H, W, crop[0], crop[1], crop[2], crop[3], out_res,
+                                                   m3, s3, 1 if quantize_u8 else 0, _ptr(out), self._stream()))
+        return out
+
     def phase_timers(self, enable=True, read=False):
         """Enable/disable the bf16 kernel's phase timers; read=True returns the last launch's averages (cycles)."""
         buf = (C.c_uint64 * 32)()

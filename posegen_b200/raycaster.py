@@ -151,10 +151,72 @@ class RayCaster(nn.Module):
 
     # -- forward -------------------------------------------------------------------
     def forward(self, *args, fwd_type="", **kwargs):
-        if fwd_type in ("density", "density_color", "mesh"):
-            raise NotImplementedError(f"fwd_type={fwd_type!r} (density-only queries, core/raycasters.py:579-648) "
-                                      "is a later scope row (SURVEY.md §8f-5)")
+        # routing of core/raycasters.py:349-355
+        if fwd_type == "density":
+            return self.render_pts_density(*args, **kwargs)
+        if fwd_type == "mesh":
+            return self.render_mesh_density(*args, **kwargs)
+        if fwd_type == "density_color":
+            raise NotImplementedError("fwd_type='density_color' needs texture_linears, which no shipped config has "
+                                      "(core/raycasters.py:624-625)")
         return self.render_rays(*args, **kwargs)
+
+    # -- density-only queries ---------------------------------------
+    @torch.no_grad()
+    def render_pts_density(self, pts, kps=None, skts=None, bones=None, render_kwargs=None, subject_idxs=None,
+                           netchunk=1024 * 64, network=None, color=False, v=None, precision=None):
+        """core/raycasters.py:597-648: raw density (alpha_linear output, before the ReLU) of arbitrary points.
+
+        pts [N,S,3] (CUDA), skts [N,24,4,4] or [1,24,4,4] / [24,4,4] (one pose for all points).  Uses
+        network_fine like the reference (`network` may be 'coarse'/'fine' or one of the two modules).
+        The points run through the stage entry points pgn_encode (z = 0 along a zero direction, i.e. the
+        point itself) and pgn_mlp; only the sigma channel is returned, shape [N,S,1]."""
+        if color or v is not None:
+            raise NotImplementedError("color / precomputed v are not part of the surreal.txt density query")
+        if skts is None:
+            raise ValueError("skts is required")
+        if not pts.is_cuda:
+            raise RuntimeError("posegen_b200.RayCaster needs CUDA tensors; there is no CPU fallback")
+        dev = pts.device
+        eng = self.engine(dev)
+        net_id = 1
+        if network is not None:
+            net_id = 0 if (network is self.network or network == "coarse") else 1
+        n, s = pts.shape[0], pts.shape[1]
+        flat = pts.reshape(-1, 3).float().contiguous()
+        sk = torch.as_tensor(skts, dtype=torch.float32, device=dev)
+        shared = sk.dim() == 3 or sk.shape[0] == 1
+        if shared:
+            sk = sk.reshape(24, 4, 4)
+        else:
+            sk = sk[:, None].expand(n, s, 24, 4, 4).reshape(-1, 24, 4, 4)
+        out = torch.empty((flat.shape[0], 1), dtype=torch.float32, device=dev)
+        cyl = torch.zeros(5, dtype=torch.float32, device=dev)
+        for i in range(0, flat.shape[0], netchunk):
+            p = flat[i:i + netchunk]
+            m = p.shape[0]
+            rb = torch.zeros((m, 11), dtype=torch.float32, device=dev)
+            rb[:, :3] = p
+            rb[:, 7] = 1.0
+            z = torch.zeros((m, 1), dtype=torch.float32, device=dev)
+            enc = eng.encode(rb, sk if shared else sk[i:i + netchunk].contiguous(), cyl, z)
+            out[i:i + netchunk] = eng.mlp(net_id, enc, precision=precision or self.precision).reshape(m, 4)[:, 3:4]
+        return out.reshape(n, s, 1)
+
+    @torch.no_grad()
+    def render_mesh_density(self, kps, skts, bones=None, subject_idxs=None, radius=1.0, res=64,
+                            render_kwargs=None, netchunk=1024 * 64, v=None, precision=None):
+        """core/raycasters.py:579-595: raw density on a (res+1)^3 grid of half-width `radius` around the root joint."""
+        import numpy as np
+        kps = torch.as_tensor(kps)
+        dev = next(self.parameters()).device
+        t = np.linspace(-radius, radius, res + 1)
+        grid = np.stack(np.meshgrid(t, t, t), axis=-1).astype(np.float32)
+        sh = grid.shape
+        pts = torch.tensor(grid.reshape(-1, 3)) + kps[0, 0].detach().cpu().float()
+        raw = self.render_pts_density(pts.reshape(-1, 1, 3).to(dev), kps, skts, bones, render_kwargs, subject_idxs,
+                                      netchunk, v=v, precision=precision)[..., :1]
+        return raw.reshape(*sh[:-1]).transpose(1, 0)
 
     @torch.no_grad()
     def render_rays(self, ray_batch, N_samples, kp_batch=None, skts=None, cyls=None, bones=None, cams=None,

@@ -121,3 +121,19 @@ def test_synthetic_geometry_properties():
     assert 0.5 < len(frame.valid_idx) / (64 * 64) <= 1.0
     full = syn.synthetic_frame(7, 64, 64, full_frame=True)
     assert len(full.valid_idx) == 64 * 64
+
+
+def test_hmr_input_oracle_properties():
+    """The skimage.resize restatement: identity when the crop already has the output size, constants stay constant."""
+    import numpy as np
+    from oracle import next_oracle as nxt
+    rng = np.random.RandomState(0)
+    img = rng.rand(64, 64, 3).astype(np.float32)
+    out = nxt.hmr_input(img, crop=(8, 8, 40, 40), out_res=32, quantize_u8=False)
+    want = (np.transpose(img[8:40, 8:40], (2, 0, 1)) - np.array([0.485, 0.456, 0.406], np.float32)[:, None, None]) / \
+        np.array([0.485, 0.456, 0.406], np.float32)[:, None, None]
+    assert np.abs(out - want).max() <= 1e-6
+    flat = np.full((80, 80, 3), 1.0, np.float32)                      # white background frame
+    out = nxt.hmr_input(flat, crop=(0, 0, 80, 80), out_res=24)
+    assert np.abs(out - (1.0 - np.array([0.485, 0.456, 0.406], np.float32))[:, None, None] /
+                  np.array([0.485, 0.456, 0.406], np.float32)[:, None, None]).max() <= 1e-5
