@@ -78,7 +78,8 @@ struct __align__(128) Smem {
   float cscratch[2][2][256];                     // coarse compositing per slot, per warp: z[64] | weights[64] | sample_pdf scratch[128]
   uint64_t w_full[2][kWStages], w_empty[2][kWStages];
   uint64_t stg_full[2][kStgBufs], stg_empty[2][kStgBufs];
-  uint64_t act_ready[2], acc_full[2], act_free[2];
+  uint64_t act_ready[2], acc_full[2];
+  uint64_t act_free[2][kStgBufs];                // activation K-steps under staging buffer b consumed (skip / view layer)
   uint32_t tmem_base;
 };
 static_assert(sizeof(Smem) + 1024 <= 232448, "shared memory budget of one CTA exceeded");
@@ -373,7 +374,8 @@ __device__ __forceinline__ bool issue_layer(IssuerCtx& ic) {
     const uint32_t b_lo = (ic.ring_lo + (uint32_t)st * (kWStageBytes >> 4) + (uint32_t)(ks % kpf) * b_step) | b_lbo;
     umma_bf16_2cta_elect(ic.tmem_acc, ((uint64_t)kDescHi << 32) | a_lo, ((uint64_t)kDescHi << 32) | b_lo, idesc, ks > 0 ? 1u : 0u);
     if (chunk_end) umma_commit_2cta_elect_s(ic.stg_empty0 + sb * 8);
-    if (has_chunks && ks_act > 0 && ks == ks_act - 1) umma_commit_2cta_elect_s(ic.act_free);   // act[s] may be overwritten by chunks
+    // activation K-steps 0-4 / 5-9 / 10-14 consumed -> staging buffer 0 / 1 / 2 (20 KB = 5 K-steps each) may be overwritten
+    if (has_chunks && ks_act > 0 && (ks == 4 || ks == 9 || ks == 14)) umma_commit_2cta_elect_s(ic.act_free + (ks / 5) * 8);
     if (ks % kpf == kpf - 1 || ks == ks_total - 1) umma_commit_2cta_elect_s(ic.w_empty0 + st * 8);
   }
   umma_commit_2cta_elect_s(ic.acc_full);
@@ -421,7 +423,7 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
       for (int i = 0; i < kStgBufs; ++i) { mbar_init(&sm.stg_full[s][i], 2 * kGroupWarps); mbar_init(&sm.stg_empty[s][i], 1); }
       mbar_init(&sm.act_ready[s], 2 * kGroupWarps);
       mbar_init(&sm.acc_full[s], 1);
-      mbar_init(&sm.act_free[s], 1);
+      for (int i = 0; i < kStgBufs; ++i) mbar_init(&sm.act_free[s][i], 1);
     }
     fence_mbar_init();
   }
@@ -499,7 +501,7 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
       IssuerCtx ic;
       ic.w_full0 = SADDR(w_full) + s * kWStages * 8; ic.w_empty0 = SADDR(w_empty) + s * kWStages * 8;
       ic.stg_full0 = SADDR(stg_full) + s * kStgBufs * 8; ic.stg_empty0 = SADDR(stg_empty) + s * kStgBufs * 8;
-      ic.acc_full = SADDR(acc_full) + s * 8; ic.act_free = SADDR(act_free) + s * 8;
+      ic.acc_full = SADDR(acc_full) + s * 8; ic.act_free = SADDR(act_free) + s * kStgBufs * 8;
       const uint32_t a_lbo = (uint32_t)(kRunBytes >> 4) << 16;           // A: LBO = 2048 B
       ic.act_lo = ((SADDR(act) + s * kActBytes) >> 4) | a_lbo;
       ic.ones_lo = (SADDR(ones) >> 4) | a_lbo;
@@ -550,7 +552,7 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
     const uint32_t dtab_saddr = SADDR(dtab) + s * (uint32_t)sizeof(sm.dtab[0]);
     const uint32_t wcache_saddr = SADDR(wcache) + s * (uint32_t)sizeof(sm.wcache[0]);
     const uint32_t stg_full0 = SADDR(stg_full) + s * kStgBufs * 8, stg_empty0 = SADDR(stg_empty) + s * kStgBufs * 8;
-    const uint32_t act_ready_a = SADDR(act_ready) + s * 8, acc_full_a = SADDR(acc_full) + s * 8, act_free_a = SADDR(act_free) + s * 8;
+    const uint32_t act_ready_a = SADDR(act_ready) + s * 8, acc_full_a = SADDR(acc_full) + s * 8, act_free_a = SADDR(act_free) + s * kStgBufs * 8;
     const bool timed = kProf && s == 0;
     const float kLog2e = 1.4426950408889634f;
     const float tau_v2 = sc.tau_v * kLog2e, tau_d2 = sc.tau_d * kLog2e;
@@ -773,11 +775,11 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
       };
       if (L == 8) group_bar_sync(s);       // wcache (written by L5's encode) visible to every thread
       compute_chunk(0);
-      if (L != 0) {      // the activation K-steps of this layer must have been consumed before act[s] becomes the staging ring
-        PROF_T0(); const bool okw = mbar_wait_s(act_free_a, afree & 1, status, 302); if (timed) PROF_ADD(13); if (!okw) return false;
-        ++afree;
-      }
       for (int c = 0; c < nchunks; ++c) {
+        if (L != 0 && c < kStgBufs) {   // the activation K-steps of this layer that lie under ring buffer c must have been consumed
+          PROF_T0(); const bool okw = mbar_wait_s(act_free_a + c * 8, afree & 1, status, 302); if (timed) PROF_ADD(13); if (!okw) return false;
+          if (c == kStgBufs - 1) ++afree;
+        }
         { PROF_T0(); const bool okw = mbar_wait_s(stg_empty0 + sbuf * 8, sphase, status, 301); if (timed) PROF_ADD(10); if (!okw) return false; }
         { PROF_T0();
           const uint32_t stg = act_saddr + sbuf * (uint32_t)kStgBytes;
