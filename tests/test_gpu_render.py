@@ -106,6 +106,29 @@ def test_512_bf16_agrees_with_fp32_path(engine, frame512):
         assert pu.psnr(h[k].cpu().numpy(), f[k].cpu().numpy()) >= BF16_PSNR
 
 
+def test_512_full_frame_matches_oracle_on_device(engine, frame512):
+    """BASELINE.json configs[1] at full size: every bbox ray of a 512x512 frame against the oracle (the op-for-op
+    restatement of the reference, fp32, run with torch on the same GPU so that it finishes in seconds)."""
+    frame, ckpt, rb, sk, cy = frame512
+    assert not torch.backends.cuda.matmul.allow_tf32            # the oracle's nn.Linear layers stay fp32
+    ref = pu.oracle_render(rb, sk, cy, ckpt, chunk=4096, device="cuda")
+    engine.load_checkpoint(ckpt)
+    h = engine.render(rb, sk, cy, nanfill_chunk=4096, precision="bf16", return_alpha=False)
+    torch.cuda.synchronize()
+    engine.check_status()
+    for k in ("rgb_map", "acc_map", "rgb0", "acc0"):
+        assert pu.max_abs(h[k].cpu().numpy(), ref[k]) <= BF16_TOL, k
+    assert pu.psnr(h["rgb_map"].cpu().numpy(), ref["rgb_map"]) >= BF16_PSNR
+    assert pu.psnr(h["acc_map"].cpu().numpy(), ref["acc_map"]) >= BF16_PSNR
+    # fp32 tier on every 8th chunk-aligned block of 4096 rays (the NaN fill is per chunk, so blocks stay comparable)
+    n = rb.shape[0]
+    blocks = [slice(i, min(i + 4096, n)) for i in range(0, n, 8 * 4096)]
+    for bl in blocks:
+        f = engine.render(rb[bl].contiguous(), sk, cy, nanfill_chunk=4096, precision="fp32", return_alpha=False)
+        for k in ("rgb_map", "acc_map", "rgb0", "acc0"):
+            assert pu.max_abs(f[k].cpu().numpy(), ref[k][bl]) <= FP32_TOL, k
+
+
 def test_raycaster_dropin_forward(engine):
     g = pu.load_golden("a_32_boost_taps")
     frame, ckpt, rb, cyl = pu.case_from_golden(g)
