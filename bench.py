@@ -9,7 +9,9 @@ Workload (BASELINE.json configs[1]; configs[2] for N>1): one "step" = one synthe
 rendered at 512x512, coarse+fine (64+16 samples, two 8x256 A-NeRF MLPs), rays restricted to the
 cylinder bbox exactly like the reference's kp_to_valid_rays (run_gan camera, focal 1000).
 N>1: every rank renders its own pose per step (images shard across GPUs, weights replicated,
-no data-path collective; a final all_gather of the finished frames is inside the timed region).
+no data-path collective); the frames of all K steps are exchanged by ONE final all_gather, which is
+timed (CUDA events) and added to the rank's step time (BASELINE.json configs[2]: "no communication
+except a final gather").
 Metric: rays/s over all ranks (max-over-ranks device time, CUDA events).
 """
 from __future__ import annotations
@@ -134,7 +136,7 @@ def workload_config(args, rays_per_frame):
                         "(64+16 samples, 2x 8x256 MLP), cylinder-bbox rays, white_bkgd, random-init weights (x400 alpha head)",
             "rays_per_frame": int(rays_per_frame), "res": args.res, "precision": args.precision,
             "poses_cycled": N_POSES, "l2": "256 MiB buffer written between timed steps (L2 flush)",
-            "parallelism": f"dp{args.gpus} (images sharded by rank, no data-path collective)"}
+            "parallelism": f"dp{args.gpus} (images sharded by rank, no data-path collective; one final all_gather of the frames)"}
 
 
 # ------------------------------------------------------------------------------ our arm
@@ -157,8 +159,8 @@ def run_ours(args, rank, world, local):
                 torch.from_numpy(f.pose.cyl).pin_memory()) for f, rb in jobs]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     n_max = max(rb.shape[0] for _, rb in jobs)
-    gather_buf = torch.empty((world, n_max, 3), device=dev) if world > 1 else None
-    pad_buf = torch.zeros((n_max, 3), device=dev) if world > 1 else None
+    stash = torch.zeros((args.steps, n_max, 3), device=dev) if world > 1 else None            # this rank's finished frames
+    gather_buf = torch.empty((world, args.steps, n_max, 3), device=dev) if world > 1 else None
 
     def barrier():
         if world > 1:
@@ -168,9 +170,8 @@ def run_ours(args, rank, world, local):
     def resident_step(i):
         rb, sk, cy = dev_in[i % N_POSES]
         ret = eng.render(rb, sk, cy, nanfill_chunk=4096, precision=args.precision, return_alpha=False)
-        if world > 1:
-            pad_buf[:rb.shape[0]] = ret["rgb_map"]          # rows beyond this pose's ray count are stale padding
-            dist.all_gather_into_tensor(gather_buf.view(-1, 3), pad_buf)
+        if world > 1 and i >= args.warmup:
+            stash[i - args.warmup, :rb.shape[0]] = ret["rgb_map"]       # rows beyond this pose's ray count stay zero padding
         return rb.shape[0]
 
     def e2e_step(i):
@@ -216,6 +217,15 @@ def run_ours(args, rank, world, local):
     launches0 = eng.launch_count
     ms, rays, _ = timed(resident_step, args.steps, args.warmup)
     launches = eng.launch_count - launches0 - 2 * args.warmup          # 2 kernels per render call
+    if world > 1:                                                      # the final gather of every rank's frames
+        dist.all_gather_into_tensor(gather_buf.view(-1, 3), stash.view(-1, 3))      # warm-up (NCCL channel setup)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        dist.all_gather_into_tensor(gather_buf.view(-1, 3), stash.view(-1, 3))
+        g1.record()
+        torch.cuda.synchronize()
+        ms += g0.elapsed_time(g1)
     eng.check_status()
     ms_e2e, rays_e2e, io = timed(e2e_step, args.steps, min(args.warmup, 3))
     if rank == 0:

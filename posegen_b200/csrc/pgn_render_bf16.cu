@@ -37,6 +37,7 @@
 // Reference semantics: core/raycasters.py:361-474, core/encoders.py:8-37,110-122,181-193,
 // core/cutoff_embedder.py:111-174, core/networks/nerf.py:94-205, core/utils/ray_utils.py:157-289.
 #include <cuda_fp16.h>
+#include <cuda_bf16.h>
 #include "pgn_common.cuh"
 #include "pgn_kernels.h"
 #include "pgn_umma.cuh"
@@ -68,8 +69,8 @@ static_assert(kStgBufs * kStgBytes <= kActBytes, "staging ring must fit inside t
 struct __align__(128) Smem {
   uint8_t act[2][kActBytes];                     // per slot: A operand of the hidden layers; first 60 KB double as the staging ring
   uint8_t wring[2][kWStages][kWStageBytes];      // per slot: weight ring (this CTA's N half)
-  __half wcache[2][PGN_J * kTM];                 // d-window per (joint,row), per slot
-  __half dtab[2][kMaxTileRays][PGN_J * 32];      // PE of joint-frame view dirs per ray of the tile (27 + 5 zeros)
+  __nv_bfloat16 wcache[2][PGN_J * kTM];          // d-window per (joint,row), per slot (bf16)
+  __nv_bfloat16 dtab[2][kMaxTileRays][PGN_J * 32];   // PE of joint-frame view dirs per ray of the tile (27 + 5 zeros), bf16
   float jtab[2][kMaxTileRays][PGN_J][8];         // per (tile ray, joint): a = R o + t, b = R d, window offsets (see encode)
   float zf[2][kRPG][PGN_T];                      // merged z of the fine pass of the slot's current ray group
   float carry[2][kRPG][8];                       // incremental compositing state of the fine rays
@@ -153,7 +154,7 @@ __device__ __forceinline__ void encode_x_fast(uint32_t wcache_saddr, uint32_t jt
       const float w = __fdividef(1.0f, 1.0f + ex2_approx(fmaf(tau_v2, v, __uint_as_float(qb.z))));   // 1 - sigmoid(tau (v - c))
       if (kWriteW) {
         const float wd = __fdividef(1.0f, 1.0f + ex2_approx(fmaf(tau_d2, v, __uint_as_float(qb.w))));
-        sts16(wcache_saddr + (uint32_t)((j0 + jj) * kTM + row) * 2u, __half_as_ushort(__float2half_rn(wd)));
+        sts16(wcache_saddr + (uint32_t)((j0 + jj) * kTM + row) * 2u, __bfloat16_as_ushort(__float2bfloat16_rn(wd)));
       }
       float sn, cs;
       __sincosf(v, &sn, &cs);
@@ -203,18 +204,21 @@ __device__ __forceinline__ void encode_x_store(uint32_t stg, int row, int half, 
 // = 4 runs at run index half*4+r.
 __device__ __forceinline__ void encode_d_fast(uint32_t wcache_saddr, uint32_t dtab_saddr, const RowCtx& rc, int chunk, int row, int half,
                                               uint32_t (&packed)[20]) {
+  // d_emb[row, (j, t)] = w_d[row, j] * PE(dir_j)[t]: both factors are kept in bf16 and multiplied pairwise
+  // (one HMUL2.BF16 per two operand values; the product is the bf16 A-operand element)
   const int j = chunk * 2 + half;
-  const float wd = rc.valid ? __half2float(__ushort_as_half(lds16(wcache_saddr + (uint32_t)(j * kTM + row) * 2u))) : 0.f;
-  const uint32_t tab = dtab_saddr + (uint32_t)(rc.tr * PGN_J + j) * 64u;   // 32 halfs = 4 x 16 B
+  const uint32_t wbits = rc.valid ? (uint32_t)lds16(wcache_saddr + (uint32_t)(j * kTM + row) * 2u) : 0u;
+  const uint32_t w2u = wbits | (wbits << 16);
+  const __nv_bfloat162 w2 = *reinterpret_cast<const __nv_bfloat162*>(&w2u);
+  const uint32_t tab = dtab_saddr + (uint32_t)(rc.tr * PGN_J + j) * 64u;   // 32 bf16 = 4 x 16 B
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const uint4 t = lds128(tab + i * 16);
     const uint32_t w4[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const __half2 h2 = *reinterpret_cast<const __half2*>(&w4[e]);
-      const float2 f2 = __half22float2(h2);
-      packed[i * 4 + e] = pack_bf16x2(f2.x * wd, f2.y * wd);
+      const __nv_bfloat162 p = __hmul2(*reinterpret_cast<const __nv_bfloat162*>(&w4[e]), w2);
+      packed[i * 4 + e] = *reinterpret_cast<const uint32_t*>(&p);
     }
   }
 }
@@ -601,19 +605,19 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
           // normalised joint-frame view direction (core/encoders.py:25-37,181-193), component `axis`
           const float den = fmaxf(sqrtf(fmaf(b2, b2, fmaf(b1, b1, b0 * b0))), 1e-12f);
           const float x = (axis == 0 ? b0 : (axis == 1 ? b1 : b2)) / den;
-          __half* tab = &sm.dtab[s][tr][jn * 32];
+          __nv_bfloat16* tab = &sm.dtab[s][tr][jn * 32];
           float sn, cs;
           __sincosf(x, &sn, &cs);            // |x| <= 1
-          tab[axis] = __float2half_rn(x);
+          tab[axis] = __float2bfloat16_rn(x);
 #pragma unroll
           for (int f = 0; f < PGN_LD; ++f) {
-            tab[(1 + 2 * f) * 3 + axis] = __float2half_rn(sn);
-            tab[(2 + 2 * f) * 3 + axis] = __float2half_rn(cs);
+            tab[(1 + 2 * f) * 3 + axis] = __float2bfloat16_rn(sn);
+            tab[(2 + 2 * f) * 3 + axis] = __float2bfloat16_rn(cs);
             const float s2 = 2.f * sn * cs;
             const float c2 = fmaf(cs, cs, -sn * sn);
             sn = s2; cs = c2;
           }
-          if (axis == 0) for (int e = 27; e < 32; ++e) tab[e] = __float2half_rn(0.f);
+          if (axis == 0) for (int e = 27; e < 32; ++e) tab[e] = __float2bfloat16_rn(0.f);
         }
       }
     };
