@@ -164,9 +164,9 @@ __device__ __forceinline__ void encode_x_fast(uint32_t wcache_saddr, uint32_t jt
       for (int f = 0; f < PGN_LV; ++f) {
         vals[1 + 2 * f] = sn * w;
         vals[2 + 2 * f] = cs * w;
-        const float s2 = 2.f * sn * cs;
-        const float c2 = fmaf(cs, cs, -sn * sn);
-        sn = s2; cs = c2;
+        const float t2 = cs + cs;                 // double angle: sin 2a = (2 cos a) sin a, cos 2a = (2 cos a) cos a - 1
+        sn = t2 * sn;
+        cs = fmaf(t2, cs, -1.0f);
       }
       vals[15] = x * rsq; vals[16] = y * rsq; vals[17] = z * rsq;
 #pragma unroll
@@ -748,18 +748,20 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
     // ---- PRE(job): everything the tensor core needs from the CUDA cores before/while it runs the layer
     RowCtx rc;
     rc.valid = false; rc.tr = 0; rc.z = 0.f;
+    bool tables_ready = false;
     auto pre = [&](int L, const TileCtx& tc) -> bool {
       const int nchunks = pgn_layer_chunks(L);
       if (nchunks == 0) return true;
       const float* enc_rows = kStage ? enc_global + (size_t)tc.unit * kTM * PGN_ENC : nullptr;
       const int rows_valid = kStage ? (int)max(0ll, min((long long)kTM, enc_rows_total - tc.unit * kTM)) : kTM;
-      if (!kStage && L == 0) {
+      if (!kStage && L == 0 && !tables_ready) {      // (normally built ahead, in the shadow of the previous tile's view layer)
         PROF_T0();
         build_tables(tc);
         rc = make_row_ctx(sm, sc, tc, near_far, s, row);
         group_bar_sync(s);                 // tables visible to every thread of the group
         if (timed) PROF_ADD(14);
       }
+      if (L == 0) tables_ready = false;
       // software pipeline: the values of chunk c+1 are computed while chunk c travels through the
       // staging ring / tensor core; only the 16-byte stores wait for a ring buffer to be released
       uint32_t packed[20];
@@ -803,6 +805,18 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
         for (int L = 0; L < 9; ++L) {
           { PROF_T0(); const bool okp = pre(L, tc); if (timed && (L == 0 || L == 5 || L == 8)) PROF_ADD(L == 0 ? 25 : (L == 5 ? 26 : 27)); if (!okp) goto done; }
           if (!kStage && pending && L >= 1 && L <= 3) { PROF_T0(); composite_stage(prev, L); if (timed) PROF_ADD(11); }
+          if (!kStage && L == 8 && (k + 1 < kTiles || i + 1 < n_slot)) {
+            // the view layer's last chunks are still in the tensor core: build the next tile's tables now
+            PROF_T0();
+            TileCtx nx;
+            if (k + 1 < kTiles) make_ctx(i, k + 1, nx); else make_ctx(i + 1, 0, nx);
+            group_bar_sync(s);               // every thread is done reading this tile's tables
+            build_tables(nx);
+            rc = make_row_ctx(sm, sc, nx, near_far, s, row);
+            group_bar_sync(s);               // tables visible to every thread of the group
+            tables_ready = true;
+            if (timed) PROF_ADD(14);
+          }
           if (!post(L, tc)) goto done;
         }
         if (!kStage) { prev = tc; pending = true; }
