@@ -187,6 +187,8 @@ def run_ours(args, rank, world, local):
         host = out.to("cpu", non_blocking=False)          # device->host read of the step's result
         return n, rb_h.numel() * 4 + sk_h.numel() * 4 + cy_h.numel() * 4, host.numel() * 4
 
+    step_ms = []
+
     def timed(step_fn, steps, warmup):
         for i in range(warmup):
             step_fn(i)
@@ -194,6 +196,7 @@ def run_ours(args, rank, world, local):
         barrier()
         total_ms, rays = 0.0, 0
         extras = None
+        step_ms.clear()
         for i in range(steps):
             flush.fill_(i & 0xFF)                      # L2 flush between timed iterations (not timed)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -203,6 +206,7 @@ def run_ours(args, rank, world, local):
             e1.record()
             torch.cuda.synchronize()
             total_ms += e0.elapsed_time(e1)
+            step_ms.append(e0.elapsed_time(e1))
             if isinstance(r, tuple):
                 rays += r[0]
                 extras = r[1:]
@@ -216,6 +220,7 @@ def run_ours(args, rank, world, local):
         sampler.start()
     launches0 = eng.launch_count
     ms, rays, _ = timed(resident_step, args.steps, args.warmup)
+    resident_step_ms = list(step_ms)
     launches = eng.launch_count - launches0 - 2 * args.warmup          # 2 kernels per render call
     if world > 1:                                                      # the final gather of every rank's frames
         dist.all_gather_into_tensor(gather_buf.view(-1, 3), stash.view(-1, 3))      # warm-up (NCCL channel setup)
@@ -253,6 +258,7 @@ def run_ours(args, rank, world, local):
         "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
         "config": workload_config(args, rays_per_frame),
         "frames_per_sec_512": value / rays_per_frame,
+        "step_ms_min_max": [round(min(resident_step_ms), 3), round(max(resident_step_ms), 3)],
         "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": int(io[0]), "d2h_bytes_per_step": int(io[1]),
                 "frames_per_sec_512": e2e_value / rays_per_frame,
                 "api": "posegen_b200.RayCaster.forward (pinned host ray_batch/skts/cyls -> device, result rows -> host)"},

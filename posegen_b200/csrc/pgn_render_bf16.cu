@@ -13,7 +13,7 @@
 //   * a slot renders ray groups of 8 rays: 4 coarse tiles (2 rays x 64 samples, network_fn) and 5
 //     fine tiles (8 x 80 samples cut into 128-row tiles, network_fine), in the order
 //     C0 C1 F0 C2 F1 C3 F2 F3 F4.  Compositing / inverse-CDF resampling of a tile is DEFERRED into
-//     the shadow of the next tile's first hidden layer, so it never sits on the tensor core's
+//     the shadow of the next tile's hidden layers 1-3, so it never sits on the tensor core's
 //     critical path; the order guarantees that a fine tile's z values exist before it is encoded.
 //   * per 128-row tile, 9 tensor-core layers (K-steps of 16):
 //       L0   x_p(480)            -> 256 ReLU   A generated on the fly (skeleton-relative encoding +
@@ -23,9 +23,9 @@
 //       V    h7(256) | d(768)    -> 128 ReLU   (feature_linear folded into views_linears[0]; rgb head
 //                                               folded into the epilogue, fp32)
 //     Generated chunks are staged in a 3-deep ring that lives INSIDE the slot's own activation
-//     buffer: the buffer is dead while L0 runs and, for L5/V, as soon as the 16 activation K-steps
-//     have been consumed (act_free barrier), so operand generation runs up to three chunks ahead
-//     of the tensor core without any dedicated staging memory.
+//     buffer: the buffer is dead while L0 runs and, for L5/V, ring buffer b is free as soon as the
+//     activation K-steps under it have been consumed (act_free[b] barriers), so operand generation
+//     runs up to three chunks ahead of the tensor core without any dedicated staging memory.
 //   * the samples x joints x embedding tensor only ever exists as 20 KB chunks in shared memory and
 //     the per-sample network outputs never leave the SM.
 //
