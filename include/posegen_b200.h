@@ -158,6 +158,17 @@ PGN_API int  pgn_render_forward(pgn_context* ctx, const pgn_render_inputs* in,
                         const pgn_render_outputs* out,
                         void* workspace, size_t workspace_bytes, void* stream);
 
+/* Training-step forward (reference core/trainer.py:232-275, eval-style sampling: perturb = 0, no noise): the same
+ * fused bf16 pipeline as pgn_render_forward that additionally stores the post-ReLU activations of every MLP layer
+ * (bf16) so that the weight gradients can be formed by plain GEMMs.  Per pass the dump is laid out
+ * [layer 0..8][run][row][8]: run = 8 consecutive columns, layers 0-7 (pts_linears) have 32 runs, layer 8
+ * (views_linears.0, 128 columns) has 16 and starts 8*32 runs in; rows are samples in (ray, sample) order, padded
+ * to pgn_activation_dump_bytes(n, pass) / 4352 rows.  act_coarse / act_fine: device buffers of
+ * pgn_activation_dump_bytes(n_rays, 0 / 1) bytes.  Request out->raw0 / raw / z_fine / near_far for the backward. */
+PGN_API size_t pgn_activation_dump_bytes(int64_t n_rays, int32_t pass);
+PGN_API int  pgn_render_forward_train(pgn_context* ctx, const pgn_render_inputs* in, const pgn_render_outputs* out,
+                                      void* act_coarse, void* act_fine, void* workspace, size_t workspace_bytes, void* stream);
+
 /* number of kernel launches issued by this context since creation
  * (bench.py reports it as gpu_launches) */
 PGN_API int64_t pgn_launch_count(const pgn_context* ctx);
@@ -188,6 +199,12 @@ PGN_API int  pgn_mlp(pgn_context* ctx, int net_id, const float* enc, int64_t m, 
 PGN_API int  pgn_composite(pgn_context* ctx, const pgn_render_inputs* in, const float* raw, const float* z,
                    int32_t s, float* rgb_map, float* disp_map, float* acc_map,
                    float* weights, float* alpha, void* stream);
+
+/* backward of NeRF.raw2outputs for the training step (core/trainer.py:321-370 reads rgb_map and acc_map):
+ * g_rgb [n,3] = dL/d rgb_map, g_acc [n] = dL/d acc_map (may be NULL) -> d_raw [n,s,4] = dL/d raw.
+ * No gradient flows through z (the importance samples are detached, core/utils/ray_utils.py:286). */
+PGN_API int  pgn_composite_backward(pgn_context* ctx, const pgn_render_inputs* in, const float* raw, const float* z,
+                                    int32_t s, const float* g_rgb, const float* g_acc, float* d_raw, void* stream);
 
 /* isample_from_lineseg + sample_pdf, det=True (core/utils/ray_utils.py:157-201,255-289):
  * z [n,64], weights [n,64] -> z_samples [n,16], z_sorted [n,80], pdf_inds [n,16],

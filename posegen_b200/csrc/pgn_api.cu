@@ -198,8 +198,31 @@ static PgnRayRefs make_refs(const pgn_render_inputs* in) {
   return r;
 }
 
+static int render_forward_impl(pgn_context* c, const pgn_render_inputs* in, const pgn_render_outputs* out,
+                               void* workspace, size_t workspace_bytes, void* stream_, const PgnActDump* dump);
+
 int pgn_render_forward(pgn_context* c, const pgn_render_inputs* in, const pgn_render_outputs* out,
                        void* workspace, size_t workspace_bytes, void* stream_) {
+  return render_forward_impl(c, in, out, workspace, workspace_bytes, stream_, nullptr);
+}
+
+size_t pgn_activation_dump_bytes(int64_t n_rays, int32_t pass) {
+  if (n_rays < 0 || (pass != 0 && pass != 1)) return 0;
+  return (size_t)pgn_bf16_dump_rows(n_rays, pass == 0 ? PGN_S : PGN_T) * (8 * 256 + 128) * sizeof(__nv_bfloat16);
+}
+
+int pgn_render_forward_train(pgn_context* c, const pgn_render_inputs* in, const pgn_render_outputs* out,
+                             void* act_coarse, void* act_fine, void* workspace, size_t workspace_bytes, void* stream_) {
+  if (!in || in->precision != PGN_PRECISION_BF16) return fail(PGN_E_INVALID, "pgn_render_forward_train: the bf16 tensor-core path only");
+  if (!act_coarse || !act_fine) return fail(PGN_E_INVALID, "pgn_render_forward_train: null activation dump");
+  PgnActDump d;
+  d.c = (__nv_bfloat16*)act_coarse; d.f = (__nv_bfloat16*)act_fine;
+  d.rows_c = pgn_bf16_dump_rows(in->n_rays, PGN_S); d.rows_f = pgn_bf16_dump_rows(in->n_rays, PGN_T);
+  return render_forward_impl(c, in, out, workspace, workspace_bytes, stream_, &d);
+}
+
+static int render_forward_impl(pgn_context* c, const pgn_render_inputs* in, const pgn_render_outputs* out,
+                               void* workspace, size_t workspace_bytes, void* stream_, const PgnActDump* dump) {
   int rc = check_inputs(c, in, "pgn_render_forward");
   if (rc) return rc;
   if (!out) return fail(PGN_E_INVALID, "pgn_render_forward: null outputs");
@@ -223,7 +246,7 @@ int pgn_render_forward(pgn_context* c, const pgn_render_inputs* in, const pgn_re
   if (in->precision == PGN_PRECISION_FP32)
     PGN_CUDA(pgn_launch_render_fp32(refs, o, c->fp32[0], c->fp32[1], c->d_sc, near_far, c->num_sms, stream));
   else
-    PGN_CUDA(pgn_launch_render_bf16(refs, o, c->bf16[0], c->bf16[1], c->d_sc, near_far, c->d_status, c->prof_on ? c->d_prof : nullptr, c->num_sms, stream));
+    PGN_CUDA(pgn_launch_render_bf16(refs, o, c->bf16[0], c->bf16[1], c->d_sc, near_far, c->d_status, c->prof_on ? c->d_prof : nullptr, dump, c->num_sms, stream));
   c->launches++;
   return PGN_OK;
 }
@@ -284,6 +307,18 @@ int pgn_composite(pgn_context* c, const pgn_render_inputs* in, const float* raw,
   if (!c->have_sc) return fail(PGN_E_STATE, "pgn_composite: scalars not set");
   PGN_CUDA(cudaSetDevice(c->cfg.device));
   PGN_CUDA(pgn_launch_composite(make_refs(in), c->d_sc, raw, z, s, rgb_map, disp_map, acc_map, weights, alpha, (cudaStream_t)stream));
+  c->launches++;
+  return PGN_OK;
+}
+
+int pgn_composite_backward(pgn_context* c, const pgn_render_inputs* in, const float* raw, const float* z, int32_t s,
+                           const float* g_rgb, const float* g_acc, float* d_raw, void* stream) {
+  int rc = check_inputs(c, in, "pgn_composite_backward");
+  if (rc) return rc;
+  if (!raw || !z || !g_rgb || !d_raw || (s != PGN_S && s != PGN_T)) return fail(PGN_E_INVALID, "pgn_composite_backward: bad argument");
+  if (!c->have_sc) return fail(PGN_E_STATE, "pgn_composite_backward: scalars not set");
+  PGN_CUDA(cudaSetDevice(c->cfg.device));
+  PGN_CUDA(pgn_launch_composite_backward(make_refs(in), c->d_sc, raw, z, s, g_rgb, g_acc, d_raw, (cudaStream_t)stream));
   c->launches++;
   return PGN_OK;
 }

@@ -36,13 +36,23 @@ struct PgnBf16Net {
   const float* b_rgb;             // [3]
 };
 
+// Training forward: post-ReLU activations of the 8 trunk layers (256 columns) and of the view layer (128), bf16,
+// per pass laid out [layer 0..8][run][row][8] (run = 8 consecutive columns; layers 0-7 have 32 runs, layer 8 has 16
+// and starts at layer offset 8 * 32 runs), rows in (ray, sample) order, pgn_bf16_dump_rows() rows per pass.
+struct PgnActDump {
+  __nv_bfloat16* c;     // coarse pass
+  __nv_bfloat16* f;     // fine pass
+  long long rows_c, rows_f;
+};
+long long pgn_bf16_dump_rows(long long n_rays, int samples_per_ray);
+
 size_t pgn_bf16_wstream_elems();
 // pack one net (device fp32 nn.Linear tensors) into wstream/bias; runs on `stream`
 cudaError_t pgn_pack_bf16_net(const float* const* w_dev, const float* const* b_dev, __nv_bfloat16* wstream,
                               float* bias, float* w_alpha, float* w_rgb, float* fold_tmp, cudaStream_t stream);
 cudaError_t pgn_launch_render_bf16(const PgnRayRefs& rays, const PgnOutputs& out, const PgnBf16Net& nc,
                                    const PgnBf16Net& nf, const PgnScalars* sc_dev, const float* near_far,
-                                   int* status, unsigned long long* prof, int num_sms, cudaStream_t stream);
+                                   int* status, unsigned long long* prof, const PgnActDump* dump, int num_sms, cudaStream_t stream);
 cudaError_t pgn_launch_mlp_bf16(const PgnBf16Net& net, const float* enc, long long m, float* raw,
                                 const PgnScalars* sc_dev, int* status, int num_sms, cudaStream_t stream);
 
@@ -62,6 +72,8 @@ cudaError_t pgn_launch_generate_rays(int H, int W, float focal, const float* c2w
 cudaError_t pgn_launch_compose_frame(int H, int W, int x0, int y0, int x1, int y1, const float* rgb, const float* acc,
                                      float bg, float* image, cudaStream_t stream);
 
+cudaError_t pgn_launch_composite_backward(const PgnRayRefs& rays, const PgnScalars* sc_dev, const float* raw, const float* z,
+                                          int s, const float* g_rgb, const float* g_acc, float* d_raw, cudaStream_t stream);
 cudaError_t pgn_launch_pose_fk(const float* bones, const float* rest, int n_poses, float ext, float top_ratio, float bot_ratio,
                                float* skts, float* kps, float* cyls, float* l2ws, cudaStream_t stream);
 cudaError_t pgn_launch_hmr_input(const float* image, int H, int W, int x0, int y0, int x1, int y1, int R,

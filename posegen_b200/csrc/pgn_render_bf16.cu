@@ -248,7 +248,10 @@ __device__ __forceinline__ void encode_d_store(uint32_t stg, int row, int half, 
 // TMEM loads of the next 32-column batch are issued before the current batch is processed.
 template <int MODE>
 __device__ __forceinline__ void epilogue(Smem& sm, uint32_t tmem_acc, uint32_t act_saddr, int slot, const float* __restrict__ w_alpha,
-                                         const float* __restrict__ w_rgb, int warp, int lane, float& sig_keep) {
+                                         const float* __restrict__ w_rgb, int warp, int lane, float& sig_keep,
+                                         uint4* dump = nullptr, size_t dump_run_stride = 0) {
+  // dump (training forward only): this thread's row in run 0 of the layer's activation dump; run r of the layer
+  // (8 consecutive columns of every row, the UMMA run layout) lives dump_run_stride uint4's further per run
   const int q = warp & 3, half = warp >> 2;
   const int row = q * 32 + lane;
   constexpr int kCols = (MODE == 2) ? 64 : 128;        // columns per thread
@@ -289,12 +292,23 @@ __device__ __forceinline__ void epilogue(Smem& sm, uint32_t tmem_acc, uint32_t a
       }
     } else {
 #pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        const uint32_t p0 = pack_relu_bf16x2(__uint_as_float(vb[8 * g]), __uint_as_float(vb[8 * g + 1]));
+        const uint32_t p1 = pack_relu_bf16x2(__uint_as_float(vb[8 * g + 2]), __uint_as_float(vb[8 * g + 3]));
+        const uint32_t p2 = pack_relu_bf16x2(__uint_as_float(vb[8 * g + 4]), __uint_as_float(vb[8 * g + 5]));
+        const uint32_t p3 = pack_relu_bf16x2(__uint_as_float(vb[8 * g + 6]), __uint_as_float(vb[8 * g + 7]));
+        sts128(dst0 + (uint32_t)(2 * b + g) * kRunBytes, p0, p1, p2, p3);
+        if (dump) dump[(size_t)((col0 >> 3) + 2 * b + g) * dump_run_stride] = make_uint4(p0, p1, p2, p3);
+      }
+    }
+    if (MODE == 2 && dump) {      // view layer: relu(g) of this thread's 16 columns
+#pragma unroll
       for (int g = 0; g < 2; ++g)
-        sts128(dst0 + (uint32_t)(2 * b + g) * kRunBytes,
-               pack_relu_bf16x2(__uint_as_float(vb[8 * g]), __uint_as_float(vb[8 * g + 1])),
-               pack_relu_bf16x2(__uint_as_float(vb[8 * g + 2]), __uint_as_float(vb[8 * g + 3])),
-               pack_relu_bf16x2(__uint_as_float(vb[8 * g + 4]), __uint_as_float(vb[8 * g + 5])),
-               pack_relu_bf16x2(__uint_as_float(vb[8 * g + 6]), __uint_as_float(vb[8 * g + 7])));
+        dump[(size_t)((col0 >> 3) + 2 * b + g) * dump_run_stride] =
+            make_uint4(pack_relu_bf16x2(__uint_as_float(vb[8 * g]), __uint_as_float(vb[8 * g + 1])),
+                       pack_relu_bf16x2(__uint_as_float(vb[8 * g + 2]), __uint_as_float(vb[8 * g + 3])),
+                       pack_relu_bf16x2(__uint_as_float(vb[8 * g + 4]), __uint_as_float(vb[8 * g + 5])),
+                       pack_relu_bf16x2(__uint_as_float(vb[8 * g + 6]), __uint_as_float(vb[8 * g + 7])));
     }
   }
   // heads: this thread's column half of (rgb_raw, sigma_raw) -> one conflict-free 16-byte store per tile
@@ -394,12 +408,12 @@ __device__ __forceinline__ bool issue_layer(IssuerCtx& ic) {
 #define PROF_ADD(slot) do { if (kProf) pacc[slot] += (unsigned long long)(clock64() - _pt0); } while (0)
 
 // ------------------------------------------------------------------ the kernel
-template <bool kStage, bool kProf>
+template <bool kStage, bool kProf, bool kDump>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf16Net net_f,
                        const PgnScalars* __restrict__ scp, const float* __restrict__ near_far,
                        const float* __restrict__ enc_global, long long enc_rows_total, float* __restrict__ raw_global,
-                       int* __restrict__ status_g, unsigned long long* __restrict__ prof) {
+                       int* __restrict__ status_g, unsigned long long* __restrict__ prof, PgnActDump dump) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   volatile int* status = status_g;
@@ -723,10 +737,20 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
       { PROF_T0(); const bool okw = mbar_wait_s(acc_full_a, accs & 1, status, 303); if (timed) { PROF_ADD(9); PROF_ADD(16 + L); } if (!okw) return false; }
       ++accs;
       tc_fence_after_sync();
+      uint4* dptr = nullptr;
+      size_t dstride = 0;
+      if (kDump) {
+        // training forward: post-ReLU activations of every layer, bf16, per pass [layer][run][row][8]; rows in
+        // (ray, sample) order: row = unit * rows_per_group + tile * 128 + row_in_tile (units padded to pairs)
+        const long long m = tc.pass == 0 ? dump.rows_c : dump.rows_f;
+        const long long grow = tc.unit * (long long)(kRPG * tc.S) + tc.row0 + ((gwarp & 3) * 32 + lane);
+        dstride = (size_t)m;
+        dptr = reinterpret_cast<uint4*>(tc.pass == 0 ? dump.c : dump.f) + (size_t)L * 32 * (size_t)m + (size_t)grow;
+      }
       { PROF_T0();
-        if (L == 8) epilogue<2>(sm, tmem_acc, act_saddr, s, net.w_alpha, net.w_rgb, gwarp, lane, sig_keep);
-        else if (L == 7) epilogue<1>(sm, tmem_acc, act_saddr, s, net.w_alpha, net.w_rgb, gwarp, lane, sig_keep);
-        else epilogue<0>(sm, tmem_acc, act_saddr, s, net.w_alpha, net.w_rgb, gwarp, lane, sig_keep);
+        if (L == 8) epilogue<2>(sm, tmem_acc, act_saddr, s, net.w_alpha, net.w_rgb, gwarp, lane, sig_keep, dptr, dstride);
+        else if (L == 7) epilogue<1>(sm, tmem_acc, act_saddr, s, net.w_alpha, net.w_rgb, gwarp, lane, sig_keep, dptr, dstride);
+        else epilogue<0>(sm, tmem_acc, act_saddr, s, net.w_alpha, net.w_rgb, gwarp, lane, sig_keep, dptr, dstride);
         compute_arrive(act_ready_a, lane); if (timed) PROF_ADD(8); }
       if (kStage && L == 8) {
         group_bar_sync(s);
@@ -925,6 +949,12 @@ __global__ void pgn_pack_wstream_kernel(PackPtrs p, const float* __restrict__ fo
 
 size_t pgn_bf16_wstream_elems() { return pgn_wstream_elems(); }
 
+// rows of the activation dump of one pass (units are padded to CTA pairs): samples_per_ray = 64 | 80
+long long pgn_bf16_dump_rows(long long n_rays, int samples_per_ray) {
+  const long long n_groups = (n_rays + kRPG - 1) / kRPG;
+  return ((n_groups + 1) / 2) * 2 * (long long)kRPG * samples_per_ray;
+}
+
 cudaError_t pgn_pack_bf16_net(const float* const* w_dev, const float* const* b_dev, __nv_bfloat16* wstream,
                               float* bias, float* w_alpha, float* w_rgb, float* fold_tmp, cudaStream_t stream) {
   PackPtrs p;
@@ -937,11 +967,13 @@ cudaError_t pgn_pack_bf16_net(const float* const* w_dev, const float* const* b_d
 static cudaError_t configure_bf16() {
   static bool done = false;
   if (done) return cudaSuccess;
-  cudaError_t e = cudaFuncSetAttribute(pgn_render_bf16_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem) + 1024);
+  cudaError_t e = cudaFuncSetAttribute(pgn_render_bf16_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem) + 1024);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(pgn_render_bf16_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem) + 1024);
+  e = cudaFuncSetAttribute(pgn_render_bf16_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem) + 1024);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(pgn_render_bf16_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem) + 1024);
+  e = cudaFuncSetAttribute(pgn_render_bf16_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem) + 1024);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(pgn_render_bf16_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem) + 1024);
   if (e != cudaSuccess) return e;
   done = true;
   return cudaSuccess;
@@ -949,19 +981,23 @@ static cudaError_t configure_bf16() {
 
 cudaError_t pgn_launch_render_bf16(const PgnRayRefs& rays, const PgnOutputs& out, const PgnBf16Net& nc,
                                    const PgnBf16Net& nf, const PgnScalars* sc_dev, const float* near_far,
-                                   int* status, unsigned long long* prof, int num_sms, cudaStream_t stream) {
+                                   int* status, unsigned long long* prof, const PgnActDump* dump, int num_sms, cudaStream_t stream) {
   cudaError_t e = configure_bf16();
   if (e != cudaSuccess) return e;
   const long long n_groups = (rays.n_rays + kRPG - 1) / kRPG;
   if (n_groups == 0) return cudaSuccess;
   const long long n_pairs = (n_groups + 1) / 2;
   const int grid = 2 * (int)min((long long)(num_sms / 2), n_pairs);      // clusters of 2 CTAs
-  if (prof)
-    pgn_render_bf16_kernel<false, true><<<grid, kThreads, sizeof(Smem) + 1024, stream>>>(rays, out, nc, nf, sc_dev, near_far,
-                                                                                         nullptr, 0, nullptr, status, prof);
+  const PgnActDump nodump{};
+  if (dump)
+    pgn_render_bf16_kernel<false, false, true><<<grid, kThreads, sizeof(Smem) + 1024, stream>>>(rays, out, nc, nf, sc_dev, near_far,
+                                                                                                nullptr, 0, nullptr, status, nullptr, *dump);
+  else if (prof)
+    pgn_render_bf16_kernel<false, true, false><<<grid, kThreads, sizeof(Smem) + 1024, stream>>>(rays, out, nc, nf, sc_dev, near_far,
+                                                                                                nullptr, 0, nullptr, status, prof, nodump);
   else
-    pgn_render_bf16_kernel<false, false><<<grid, kThreads, sizeof(Smem) + 1024, stream>>>(rays, out, nc, nf, sc_dev, near_far,
-                                                                                          nullptr, 0, nullptr, status, nullptr);
+    pgn_render_bf16_kernel<false, false, false><<<grid, kThreads, sizeof(Smem) + 1024, stream>>>(rays, out, nc, nf, sc_dev, near_far,
+                                                                                                 nullptr, 0, nullptr, status, nullptr, nodump);
   return cudaGetLastError();
 }
 
@@ -974,7 +1010,7 @@ cudaError_t pgn_launch_mlp_bf16(const PgnBf16Net& net, const float* enc, long lo
   const int grid = 2 * (int)min((long long)(num_sms / 2), (n_tiles + 1) / 2);
   PgnRayRefs rays{};
   PgnOutputs out{};
-  pgn_render_bf16_kernel<true, false><<<grid, kThreads, sizeof(Smem) + 1024, stream>>>(rays, out, net, net, sc_dev, nullptr,
-                                                                                       enc, m, raw, status, nullptr);
+  pgn_render_bf16_kernel<true, false, false><<<grid, kThreads, sizeof(Smem) + 1024, stream>>>(rays, out, net, net, sc_dev, nullptr,
+                                                                                              enc, m, raw, status, nullptr, PgnActDump{});
   return cudaGetLastError();
 }

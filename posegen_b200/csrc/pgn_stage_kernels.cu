@@ -416,3 +416,105 @@ cudaError_t pgn_launch_hmr_input(const float* image, int H, int W, int x0, int y
                                                             std3[0], std3[1], std3[2], quantize, out);
   return cudaGetLastError();
 }
+
+// ---------------------------------------------------------------------------
+// Backward of NeRF.raw2outputs (core/networks/nerf.py:150-205) for the training step
+// (core/trainer.py:321-370: the loss reads rgb_map and acc_map of both passes): one warp per ray.
+//   w_i = a_i T_i,  T_i = prod_{k<i} (1 - a_k + 1e-10),  a_i = 1 - exp(-relu(raw_s / B) d_i)
+//   dL/da_i = T_i G_i - (sum_{j>i} w_j G_j) / (1 - a_i + 1e-10),   G_i = g_rgb . c_i + g_acc [acc < 1]
+//   dL/draw_s = dL/da_i d_i exp(-s_i d_i) [raw_s > 0] / B ;  dL/draw_c = w_i g_rgb (1 + 2 eps) sig (1 - sig)
+// (no gradient flows through z: the importance samples are detached, ray_utils.py:286.)
+// ---------------------------------------------------------------------------
+template <int S>
+__global__ void pgn_composite_backward_kernel(PgnRayRefs rays, const PgnScalars* __restrict__ scp, const float* __restrict__ raw,
+                                              const float* __restrict__ z, const float* __restrict__ g_rgb,
+                                              const float* __restrict__ g_acc, float* __restrict__ d_raw) {
+  constexpr int CH = (S + 31) / 32;
+  const PgnScalars& sc = *scp;
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const float keps = 1.0f + 2.0f * sc.rgb_eps;
+  for (long long r = warp; r < rays.n_rays; r += nwarps) {
+    const float* d = rays.ray_batch + r * 11 + 3;
+    const float dn = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+    const float* rw = raw + r * S * 4;
+    const float* zz = z + r * S;
+    const float gr = g_rgb[r * 3], gg = g_rgb[r * 3 + 1], gb = g_rgb[r * 3 + 2];
+    float al[CH], om[CH], dist[CH], p[CH], c0[CH], c1[CH], c2[CH], s0[CH], s1[CH], s2[CH];
+    float lane_prod = 1.0f;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      const int i = lane * CH + c;
+      al[c] = 0.f; om[c] = 1.f; dist[c] = 0.f; c0[c] = c1[c] = c2[c] = 0.f; s0[c] = s1[c] = s2[c] = 0.f;
+      p[c] = lane_prod;
+      if (i < S) {
+        float di = (i + 1 < S) ? __fsub_rn(zz[i + 1], zz[i]) : 1e10f;
+        di = __fmul_rn(di, dn);
+        const float sig = fmaxf(rw[i * 4 + 3] / sc.density_scale, 0.0f);
+        al[c] = 1.0f - expf(-__fmul_rn(sig, di));
+        om[c] = __fadd_rn(__fsub_rn(1.0f, al[c]), 1e-10f);
+        dist[c] = di;
+        s0[c] = 1.0f / (1.0f + expf(-rw[i * 4 + 0])); s1[c] = 1.0f / (1.0f + expf(-rw[i * 4 + 1])); s2[c] = 1.0f / (1.0f + expf(-rw[i * 4 + 2]));
+        c0[c] = s0[c] * keps - sc.rgb_eps; c1[c] = s1[c] * keps - sc.rgb_eps; c2[c] = s2[c] * keps - sc.rgb_eps;
+        lane_prod *= om[c];
+      }
+    }
+    float incl = lane_prod;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const float up = __shfl_up_sync(0xffffffffu, incl, off);
+      if (lane >= off) incl *= up;
+    }
+    float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) excl = 1.0f;
+    float w[CH], G[CH], T[CH];
+    float sw = 0.f;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) { T[c] = excl * p[c]; w[c] = al[c] * T[c]; sw += w[c]; }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) sw += __shfl_xor_sync(0xffffffffu, sw, off);
+    const float ga = (g_acc && sw < 1.0f) ? g_acc[r] : 0.0f;          // acc_map = min(sum w, 1)
+    float lane_sum = 0.f, pre[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      G[c] = gr * c0[c] + gg * c1[c] + gb * c2[c] + ga;
+      lane_sum += w[c] * G[c];
+      pre[c] = lane_sum;                                               // inclusive within the lane
+    }
+    float incl_s = lane_sum;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const float up = __shfl_up_sync(0xffffffffu, incl_s, off);
+      if (lane >= off) incl_s += up;
+    }
+    const float total = __shfl_sync(0xffffffffu, incl_s, 31);
+    const float before = incl_s - lane_sum;                            // sum over earlier lanes
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      const int i = lane * CH + c;
+      if (i < S) {
+        const float after = total - (before + pre[c]);                 // sum_{j>i} w_j G_j
+        const float dalpha = T[c] * G[c] - after / om[c];
+        const float rs = rw[i * 4 + 3];
+        const float dsig = dalpha * dist[c] * (1.0f - al[c]);
+        float* o = d_raw + (r * S + i) * 4;
+        o[0] = w[c] * gr * keps * s0[c] * (1.0f - s0[c]);
+        o[1] = w[c] * gg * keps * s1[c] * (1.0f - s1[c]);
+        o[2] = w[c] * gb * keps * s2[c] * (1.0f - s2[c]);
+        o[3] = rs > 0.0f ? dsig / sc.density_scale : 0.0f;
+      }
+    }
+  }
+}
+
+cudaError_t pgn_launch_composite_backward(const PgnRayRefs& rays, const PgnScalars* sc_dev, const float* raw, const float* z,
+                                          int s, const float* g_rgb, const float* g_acc, float* d_raw, cudaStream_t stream) {
+  if (rays.n_rays == 0) return cudaSuccess;
+  const int block = 256;
+  const long long grid = min((rays.n_rays * 32 + block - 1) / block, (long long)148 * 8);
+  if (s == PGN_S) pgn_composite_backward_kernel<PGN_S><<<(unsigned)grid, block, 0, stream>>>(rays, sc_dev, raw, z, g_rgb, g_acc, d_raw);
+  else if (s == PGN_T) pgn_composite_backward_kernel<PGN_T><<<(unsigned)grid, block, 0, stream>>>(rays, sc_dev, raw, z, g_rgb, g_acc, d_raw);
+  else return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}

@@ -178,6 +178,32 @@ class Engine:
                                                    self._stream()))
         return ret
 
+    def render_train(self, ray_batch, skts, cyls, pose_idx=None, nanfill_chunk=0):
+        """pgn_render_forward_train: the fused bf16 forward + per-layer activation dump for the weight gradients.
+        Returns (outputs incl. the taps the backward needs, {"c": dump, "f": dump}); dump[p] is a bf16 tensor
+        [272 runs, rows, 8] (layers 0-7: 32 runs each, view layer: 16), rows in (ray, sample) order."""
+        inp, keep = self._inputs(ray_batch, skts, cyls, pose_idx, nanfill_chunk, "bf16")
+        n, dev = inp.n_rays, ray_batch.device
+        f = lambda *sh: torch.empty(sh, dtype=torch.float32, device=dev)  # noqa: E731
+        ret = {"rgb_map": f(n, 3), "disp_map": f(n), "acc_map": f(n), "rgb0": f(n, 3), "disp0": f(n), "acc0": f(n),
+               "z_fine": f(n, T), "raw0": f(n, S, 4), "raw": f(n, T, 4), "near_far": f(n, 2)}
+        out = _lib.RenderOutputs()
+        for k, v in ret.items():
+            setattr(out, k, v.data_ptr())
+        acts = {}
+        for key, p in (("c", 0), ("f", 1)):
+            nbytes = self.lib.pgn_activation_dump_bytes(n, p)
+            rows = nbytes // (272 * 16)
+            acts[key] = torch.empty((272, rows, 8), dtype=torch.bfloat16, device=dev)
+        need = self.lib.pgn_workspace_bytes(self.handle, n)
+        if self._workspace is None or self._workspace.numel() < need or self._workspace.device != dev:
+            self._workspace = torch.empty(max(need, 1 << 20), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(self.lib.pgn_render_forward_train(self.handle, C.byref(inp), C.byref(out), _ptr(acts["c"]), _ptr(acts["f"]),
+                                                         C.c_void_p(self._workspace.data_ptr()), self._workspace.numel(),
+                                                         self._stream()))
+        return ret, acts
+
     # ------------------------------------------------------ stage entry points
     def near_far(self, ray_batch, skts, cyls, nanfill_chunk=0):
         inp, keep = self._inputs(ray_batch, skts, cyls, None, nanfill_chunk)
@@ -210,6 +236,15 @@ class Engine:
                                           _ptr(ret["rgb_map"]), _ptr(ret["disp_map"]), _ptr(ret["acc_map"]),
                                           _ptr(ret["weights"]), _ptr(ret["alpha"]), self._stream()))
         return ret
+
+    def composite_backward(self, ray_batch, skts, cyls, raw, z, g_rgb, g_acc=None):
+        """dL/d raw [n,s,4] of raw2outputs given dL/d rgb_map [n,3] and dL/d acc_map [n]."""
+        inp, keep = self._inputs(ray_batch, skts, cyls)
+        d_raw = torch.empty_like(raw, memory_format=torch.contiguous_format)
+        _lib.check(self.lib.pgn_composite_backward(self.handle, C.byref(inp), _ptr(raw.contiguous()), _ptr(z.contiguous()), z.shape[1],
+                                                   _ptr(g_rgb.contiguous()), _ptr(g_acc.contiguous()) if g_acc is not None else None,
+                                                   _ptr(d_raw), self._stream()))
+        return d_raw
 
     def sample_pdf(self, z, weights):
         _check_f32_cuda(z, "z")

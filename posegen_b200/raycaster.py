@@ -218,15 +218,14 @@ class RayCaster(nn.Module):
                                       netchunk, v=v, precision=precision)[..., :1]
         return raw.reshape(*sh[:-1]).transpose(1, 0)
 
-    @torch.no_grad()
     def render_rays(self, ray_batch, N_samples, kp_batch=None, skts=None, cyls=None, bones=None, cams=None,
                     subject_idxs=None, retraw=False, lindisp=False, perturb=0., N_importance=0,
                     network_fine=None, raw_noise_std=0., ray_noise_std=0., verbose=False, ext_scale=0.001,
                     pytest=False, preproc_kwargs=None, nerf_type="nerf", use_viewdirs=True,
                     precision=None, nanfill_chunk=None, **_ignored):
         if self.training and (perturb or raw_noise_std or ray_noise_std):
-            raise NotImplementedError("training-time sampling noise (perturb / raw_noise_std / ray_noise_std) and the "
-                                      "backward pass are not implemented yet; call .eval() for rendering")
+            raise NotImplementedError("training-time sampling noise (perturb / raw_noise_std / ray_noise_std) is not "
+                                      "implemented yet; train with perturb=0, raw_noise_std=0 or call .eval() for rendering")
         if perturb or raw_noise_std or ray_noise_std or lindisp:
             raise NotImplementedError("perturb / raw_noise_std / ray_noise_std / lindisp must be 0/False on the render path")
         if N_samples != 64 or N_importance != 16:
@@ -238,6 +237,12 @@ class RayCaster(nn.Module):
         if not ray_batch.is_cuda:
             raise RuntimeError("posegen_b200.RayCaster needs CUDA tensors (the reference moves each chunk with "
                                ".to('cuda') in batchify_rays, core/trainer.py:70-74); there is no CPU fallback")
+        if self.training and torch.is_grad_enabled():
+            # training step (core/trainer.py:232-275): differentiable w.r.t. the two MLPs (posegen_b200/train.py)
+            from .train import render_train
+            if (precision or self.precision) != "bf16":
+                raise NotImplementedError("the training step runs on the bf16 tensor-core path only")
+            return render_train(self, ray_batch, skts.to(ray_batch.device), cyls.to(ray_batch.device), nanfill_chunk)
         eng = self.engine(ray_batch.device)
         n = ray_batch.shape[0]
         ret = eng.render(ray_batch.float(), skts.to(ray_batch.device).float(), cyls.to(ray_batch.device).float(),

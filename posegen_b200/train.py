@@ -1,0 +1,143 @@
+"""Training step of the A-NeRF renderer (BASELINE.json configs[3]; reference core/trainer.py:232-275).
+
+Forward: the fused bf16 tensor-core kernel (`pgn_render_forward_train`) with the post-ReLU activations of
+every MLP layer dumped in bf16.  Backward: `pgn_composite_backward` (hand-written) turns dL/d(rgb_map, acc_map)
+of both passes into dL/d raw; the weight gradients of the two MLPs are then plain dense GEMMs over all samples
+of the batch (activations^T x deltas, deltas x weights) and go through cuBLAS (`torch.mm`, bf16 inputs, fp32
+accumulation); the network inputs x_p / d_emb are regenerated with `pgn_encode`.  No gradient flows through the
+sample positions (the importance samples are detached in the reference, core/utils/ray_utils.py:286) and, in
+this round, none to `skts` (pose optimisation, config 5).
+
+Sampling is the eval-style deterministic one (perturb = 0, raw_noise_std = 0: the reference's parity setting,
+SURVEY.md §8d config 4); stratified jitter and density noise are not implemented yet.
+
+Multi-GPU: data-parallel over rays; `allreduce_gradients` is one NCCL all-reduce of the flattened 1.73 M-element
+gradient bucket.
+"""
+from __future__ import annotations
+
+from typing import Dict, List
+
+import torch
+import torch.distributed as dist
+
+S, T = 64, 80
+PARAM_ORDER = [f"pts_linears.{i}.{k}" for i in range(8) for k in ("weight", "bias")] + \
+    [f"{m}.{k}" for m in ("alpha_linear", "feature_linear", "views_linears.0", "rgb_linear") for k in ("weight", "bias")]
+
+
+def _mm32(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """a [m,k] @ b [k,n] with bf16 inputs and an fp32 result (cuBLAS accumulates in fp32)."""
+    try:
+        return torch.mm(a, b, out_dtype=torch.float32)
+    except TypeError:                                      # older torch: no out_dtype
+        return torch.mm(a.float(), b.float())
+
+
+def _layer(acts: torch.Tensor, l: int, m: int) -> torch.Tensor:
+    """Activation matrix of layer l (0..7: 256 columns, 8: view layer, 128) for the first m rows, [m, cols] bf16."""
+    runs = acts[l * 32:(l + 1) * 32] if l < 8 else acts[256:272]
+    return runs[:, :m].permute(1, 0, 2).reshape(m, -1)
+
+
+def mlp_backward(params: Dict[str, torch.Tensor], enc: torch.Tensor, acts: torch.Tensor, d_raw: torch.Tensor) -> Dict[str, torch.Tensor]:
+    """Weight gradients of one NeRF MLP (core/networks/nerf.py:94-148).
+
+    params: fp32 nn.Linear tensors; enc [m,1080] fp32 network input; acts: the kernel's activation dump of this
+    pass; d_raw [m,4] = dL/d(rgb_raw, sigma_raw).  Returns {name: fp32 gradient}."""
+    m = enc.shape[0]
+    bf = torch.bfloat16
+    x_p, d_emb = enc[:, :432].to(bf), enc[:, 432:].to(bf)
+    H = [_layer(acts, l, m) for l in range(8)]
+    G = _layer(acts, 8, m)
+    W = {k: v.detach().to(bf) for k, v in params.items() if k.endswith("weight")}
+    g: Dict[str, torch.Tensor] = {}
+    d_rgb, d_sig = d_raw[:, :3].to(bf), d_raw[:, 3:4].to(bf)
+    # rgb head and view layer:  g = relu(W_v [f | d_emb] + b_v),  f = W_f h7 + b_f,  rgb_raw = W_rgb g + b_rgb
+    g["rgb_linear.weight"] = _mm32(d_rgb.t(), G)
+    g["rgb_linear.bias"] = d_raw[:, :3].sum(0)
+    dG = (torch.mm(d_rgb, W["rgb_linear.weight"]) * (G > 0)).to(bf)
+    f = (torch.mm(H[7], W["feature_linear.weight"].t()).float() + params["feature_linear.bias"].detach()).to(bf)
+    g["views_linears.0.weight"] = torch.cat([_mm32(dG.t(), f), _mm32(dG.t(), d_emb)], 1)
+    g["views_linears.0.bias"] = dG.float().sum(0)
+    df = torch.mm(dG, W["views_linears.0.weight"][:, :256])
+    g["feature_linear.weight"] = _mm32(df.t(), H[7])
+    g["feature_linear.bias"] = df.float().sum(0)
+    # sigma head
+    g["alpha_linear.weight"] = _mm32(d_sig.t(), H[7])
+    g["alpha_linear.bias"] = d_raw[:, 3:4].sum(0)
+    dH = torch.mm(df, W["feature_linear.weight"]).float() + d_raw[:, 3:4] * params["alpha_linear.weight"].detach()
+    # trunk, last layer first; layer 5 reads [x_p | h4] (skip after layer index 4, nerf.py:100-101)
+    for l in range(7, -1, -1):
+        dZ = (dH * (H[l] > 0)).to(bf)
+        if l == 0:
+            g["pts_linears.0.weight"] = _mm32(dZ.t(), x_p)
+        elif l == 5:
+            g["pts_linears.5.weight"] = torch.cat([_mm32(dZ.t(), x_p), _mm32(dZ.t(), H[4])], 1)
+        else:
+            g[f"pts_linears.{l}.weight"] = _mm32(dZ.t(), H[l - 1])
+        g[f"pts_linears.{l}.bias"] = dZ.float().sum(0)
+        if l > 0:
+            Wl = W[f"pts_linears.{l}.weight"]
+            dH = torch.mm(dZ, Wl[:, 432:] if l == 5 else Wl).float()
+    return g
+
+
+class _RenderTrainFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, rc, ray_batch, skts, cyls, nanfill_chunk, *params):
+        eng = rc.engine(ray_batch.device)
+        ret, acts = eng.render_train(ray_batch, skts, cyls, nanfill_chunk=nanfill_chunk)
+        ctx.rc, ctx.acts = rc, acts
+        ctx.save_for_backward(ray_batch, skts, cyls, ret["raw0"], ret["raw"], ret["z_fine"], ret["near_far"])
+        ctx.mark_non_differentiable(ret["disp_map"], ret["disp0"])
+        return ret["rgb_map"], ret["acc_map"], ret["rgb0"], ret["acc0"], ret["disp_map"], ret["disp0"]
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_acc, g_rgb0, g_acc0, _gd, _gd0):
+        rb, sk, cy, raw0, raw, z_fine, near_far = ctx.saved_tensors
+        rc = ctx.rc
+        eng = rc.engine(rb.device)
+        n = rb.shape[0]
+        zero3, zero1 = torch.zeros((n, 3), device=rb.device), torch.zeros(n, device=rb.device)
+        t = torch.linspace(0., 1., S, device=rb.device)                       # sample_from_lineseg, ray_utils.py:204-251
+        z_c = near_far[:, :1] * (1. - t) + near_far[:, 1:2] * t
+        grads: List[torch.Tensor] = []
+        for net, acts, z, raw_p, gr, ga in ((rc.network, ctx.acts["c"], z_c, raw0, g_rgb0, g_acc0),
+                                            (rc.network_fine, ctx.acts["f"], z_fine, raw, g_rgb, g_acc)):
+            gr = zero3 if gr is None else gr.contiguous().float()
+            ga = zero1 if ga is None else ga.contiguous().float()
+            d_raw = eng.composite_backward(rb, sk, cy, raw_p, z.contiguous(), gr, ga)
+            enc = eng.encode(rb, sk, cy, z.contiguous())
+            pd = dict(net.named_parameters())
+            gd = mlp_backward(pd, enc.reshape(-1, 1080), acts, d_raw.reshape(-1, 4))
+            grads += [gd[k].reshape(pd[k].shape).to(pd[k].dtype) for k in PARAM_ORDER]
+        ctx.acts = None
+        return (None, None, None, None, None) + tuple(grads)
+
+
+def render_train(rc, ray_batch, skts, cyls, nanfill_chunk=None) -> Dict[str, torch.Tensor]:
+    """Differentiable (w.r.t. the two MLPs' parameters) render of a ray batch: the train-mode body of
+    RayCaster.forward.  Returns the reference's dict (core/raycasters.py:711-724) without alpha/alpha0."""
+    params = [dict(net.named_parameters())[k] for net in (rc.network, rc.network_fine) for k in PARAM_ORDER]
+    n = ray_batch.shape[0]
+    out = _RenderTrainFn.apply(rc, ray_batch.float().contiguous(), skts.float(), cyls.float(),
+                               n if nanfill_chunk is None else nanfill_chunk, *params)
+    return {"rgb_map": out[0], "acc_map": out[1], "rgb0": out[2], "acc0": out[3], "disp_map": out[4], "disp0": out[5],
+            "alpha": None, "alpha0": None}
+
+
+def allreduce_gradients(parameters, average: bool = True):
+    """One all-reduce of the flattened gradient bucket (NCCL on GPUs, gloo in the CPU tests)."""
+    ps = [p for p in parameters if p.grad is not None]
+    if not ps or not dist.is_initialized() or dist.get_world_size() == 1:
+        return
+    flat = torch.cat([p.grad.reshape(-1) for p in ps])
+    dist.all_reduce(flat)
+    if average:
+        flat /= dist.get_world_size()
+    o = 0
+    for p in ps:
+        k = p.grad.numel()
+        p.grad.copy_(flat[o:o + k].view_as(p.grad))
+        o += k

@@ -41,3 +41,28 @@ def test_gather_frames_world2_gloo():
     ok = mp.get_context("spawn").Array("i", [0, 0])
     mp.spawn(_worker, args=(2, port, 5, ok), nprocs=2, join=True)
     assert list(ok) == [1, 1]
+
+
+def _grad_worker(rank, world, port, ok):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    pdist.init_process_group("gloo")
+    from posegen_b200.train import allreduce_gradients
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.Linear(7, 3))
+    for i, p in enumerate(net.parameters()):
+        p.grad = torch.full_like(p, float(rank + 1) * (i + 1))
+    net[1].bias.grad = None                                   # parameters without a gradient are skipped
+    allreduce_gradients(net.parameters(), average=True)
+    good = net[1].bias.grad is None
+    for i, p in enumerate(list(net.parameters())[:3]):
+        good &= bool(torch.allclose(p.grad, torch.full_like(p, 1.5 * (i + 1))))     # mean of ranks' (1, 2) * (i + 1)
+    ok[rank] = int(good)
+    dist.destroy_process_group()
+
+
+def test_allreduce_gradients_world2_gloo():
+    """The training step's only collective: one all-reduce of the flattened gradient bucket."""
+    port = _free_port()
+    ok = mp.get_context("spawn").Array("i", [0, 0])
+    mp.spawn(_grad_worker, args=(2, port, ok), nprocs=2, join=True)
+    assert list(ok) == [1, 1]

@@ -150,3 +150,31 @@ def test_empty_and_ragged_inputs(engine, case_a):
             tol = 1e-4 if prec == "fp32" else 2e-2
             assert pu.max_abs(out["rgb_map"].cpu().numpy(), case_a["g"]["rgb_map"][:n]) <= tol, (n, prec)
             assert pu.max_abs(out["acc_map"].cpu().numpy(), case_a["g"]["acc_map"][:n]) <= tol, (n, prec)
+
+
+@pytest.mark.parametrize("s", [64, 80])
+def test_composite_backward_matches_autograd(engine, case_a, s):
+    """pgn_composite_backward vs torch autograd through the oracle's raw2outputs (fp64), on random raw / z and
+    random upstream gradients for rgb_map and acc_map (the two outputs the training loss reads)."""
+    g, dev = case_a["g"], engine.device
+    rng = np.random.RandomState(11 + s)
+    n = 257
+    rb = np.asarray(case_a["rb"].cpu().numpy()[:n], dtype=np.float32)
+    z = np.sort(rng.rand(n, s).astype(np.float32) * 2.0 + 3.0, axis=1)
+    raw = rng.randn(n, s, 4).astype(np.float32)
+    raw[..., 3] *= 8.0                                      # dense and empty samples, saturated rays (acc clamps at 1)
+    raw[5, :, 3] = -1.0                                     # an empty ray
+    g_rgb = rng.randn(n, 3).astype(np.float32)
+    g_acc = rng.randn(n).astype(np.float32)
+    t = lambda a: torch.as_tensor(a, device=dev)           # noqa: E731
+    d_raw = engine.composite_backward(t(rb), case_a["sk"], case_a["cy"], t(raw), t(z), t(g_rgb), t(g_acc))
+    torch.cuda.synchronize()
+    rawd = torch.tensor(raw, dtype=torch.float64, requires_grad=True)
+    out = orc.raw2outputs(rawd, torch.tensor(z, dtype=torch.float64), torch.tensor(rb[:, 3:6], dtype=torch.float64))
+    loss = (out["rgb_map"] * torch.tensor(g_rgb, dtype=torch.float64)).sum() + (out["acc_map"] * torch.tensor(g_acc, dtype=torch.float64)).sum()
+    loss.backward()
+    ref = rawd.grad.numpy()
+    got = d_raw.cpu().numpy()
+    scale = np.abs(ref).max()
+    assert np.isfinite(got).all()
+    assert pu.max_abs(got, ref) <= 2e-5 * max(1.0, scale)

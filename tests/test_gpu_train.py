@@ -1,0 +1,107 @@
+"""GPU: the training step (BASELINE.json configs[3], reference core/trainer.py:232-370) — fused bf16 forward with
+activation dump, hand-written compositing backward, GEMM weight gradients — against torch autograd through the
+oracle (the op-for-op restatement of the reference) on the same rays, weights and loss."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import render_oracle as orc
+from posegen_b200 import synthetic as syn
+from posegen_b200.raycaster import raycaster_from_checkpoint
+from posegen_b200.train import PARAM_ORDER, allreduce_gradients
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_loss(rb, sk, cy, nets, emb, tgt, bg=1.0):
+    """render_rays with the reference's detach of the importance samples (core/utils/ray_utils.py:286) and the
+    trainer's loss: MSE(rgb_map + (1 - acc) bg, tgt) + MSE(rgb0 + (1 - acc0) bg, tgt)  (core/trainer.py:355-370)."""
+    rays_o, rays_d = rb[:, 0:3], rb[:, 3:6]
+    near, far = orc.near_far_in_cylinder(rays_o, rays_d, cy, rb[:, 6:7], rb[:, 7:8])
+    z = orc.coarse_z_vals(near, far, 64)
+    enc = orc.encode(rays_o[:, None] + rays_d[:, None] * z[:, :, None], rays_d, sk, emb)
+    raw0 = orc.nerf_forward(enc.reshape(-1, 1080), nets[0]).reshape(-1, 64, 4)
+    r0 = orc.raw2outputs(raw0, z, rays_d)
+    z_all, _, _, _, _ = orc.importance_z_vals(z, r0["weights"].detach(), 16)
+    enc_f = orc.encode(rays_o[:, None] + rays_d[:, None] * z_all[:, :, None], rays_d, sk, emb)
+    raw = orc.nerf_forward(enc_f.reshape(-1, 1080), nets[1]).reshape(-1, 80, 4)
+    r = orc.raw2outputs(raw, z_all, rays_d)
+    loss = ((r["rgb_map"] + (1 - r["acc_map"][:, None]) * bg - tgt) ** 2).mean() + \
+        ((r0["rgb_map"] + (1 - r0["acc_map"][:, None]) * bg - tgt) ** 2).mean()
+    return loss, r, r0
+
+
+@pytest.fixture(scope="module")
+def train_case():
+    frame = syn.synthetic_frame(3, 64, 64)
+    ckpt = syn.synthetic_raycaster_state(4, alpha_gain=40.0)           # semi-transparent volume: smooth gradients
+    n = 1536
+    rb = syn.ray_batch(frame.rays_o, frame.rays_d)[:n]
+    rng = np.random.RandomState(0)
+    tgt = rng.rand(n, 3).astype(np.float32)
+    return frame, ckpt, rb, tgt
+
+
+def test_training_step_gradients_match_oracle_autograd(engine, train_case):
+    frame, ckpt, rb, tgt = train_case
+    n = rb.shape[0]
+    dev = torch.device("cuda")
+    # ---- oracle: fp32 autograd on the host
+    nets = orc.nets_from_ckpt(ckpt)
+    emb = orc.embed_params_from_ckpt(ckpt)
+    for net in nets:
+        for v in net.values():
+            v.requires_grad_(True)
+    sk = torch.as_tensor(frame.pose.skts)[None].expand(n, -1, -1, -1)
+    cy = torch.as_tensor(frame.pose.cyl)[None].expand(n, -1)
+    loss_ref, r_ref, r0_ref = _oracle_loss(torch.as_tensor(rb), sk, cy, nets, emb, torch.as_tensor(tgt))
+    loss_ref.backward()
+    # ---- ours: RayCaster in train mode
+    rc = raycaster_from_checkpoint(ckpt, device="cuda", precision="bf16")
+    rc.train()
+    ret = rc(torch.as_tensor(rb, device=dev), N_samples=64, N_importance=16, kp_batch=None, skts=sk.to(dev).contiguous(),
+             cyls=cy.to(dev).contiguous(), bones=None, cams=None, subject_idxs=None, perturb=0., raw_noise_std=0.)
+    t = torch.as_tensor(tgt, device=dev)
+    loss = ((ret["rgb_map"] + (1 - ret["acc_map"][:, None]) - t) ** 2).mean() + ((ret["rgb0"] + (1 - ret["acc0"][:, None]) - t) ** 2).mean()
+    loss.backward()
+    torch.cuda.synchronize()
+    engine.check_status()
+    assert abs(float(loss.detach()) - float(loss_ref.detach())) <= 2e-3 * max(1.0, abs(float(loss_ref.detach())))
+    flat, flat_ref = [], []
+    for net, ref in ((rc.network, nets[0]), (rc.network_fine, nets[1])):
+        pd = dict(net.named_parameters())
+        for k in PARAM_ORDER:
+            g, gr = pd[k].grad.detach().cpu().double(), ref[k].grad.double()
+            assert g.shape == gr.shape and torch.isfinite(g).all(), k
+            flat.append(g.reshape(-1)); flat_ref.append(gr.reshape(-1))
+            if float(gr.norm()) > 1e-7:
+                rel = float((g - gr).norm() / gr.norm())
+                assert rel <= 6e-2, (k, rel)                     # bf16 forward activations and deltas
+    g, gr = torch.cat(flat), torch.cat(flat_ref)
+    cos = float((g @ gr) / (g.norm() * gr.norm()))
+    assert cos >= 0.999, cos
+    assert float((g - gr).norm() / gr.norm()) <= 3e-2
+
+
+def test_training_step_reduces_the_loss(engine, train_case):
+    """A few Adam steps through the drop-in RayCaster (weights are re-packed after every optimizer.step)."""
+    frame, ckpt, rb, tgt = train_case
+    n = 1024
+    dev = torch.device("cuda")
+    rc = raycaster_from_checkpoint(ckpt, device="cuda", precision="bf16")
+    rc.train()
+    opt = torch.optim.Adam([p for p in rc.parameters() if p.requires_grad], lr=5e-4)
+    rbt = torch.as_tensor(rb[:n], device=dev)
+    sk = torch.as_tensor(frame.pose.skts, device=dev)
+    cy = torch.as_tensor(frame.pose.cyl, device=dev)
+    t = torch.full((n, 3), 0.25, device=dev)
+    losses = []
+    for _ in range(8):
+        opt.zero_grad()
+        ret = rc(rbt, N_samples=64, N_importance=16, kp_batch=None, skts=sk, cyls=cy, bones=None, cams=None, perturb=0., raw_noise_std=0.)
+        loss = ((ret["rgb_map"] + (1 - ret["acc_map"][:, None]) - t) ** 2).mean() + ((ret["rgb0"] + (1 - ret["acc0"][:, None]) - t) ** 2).mean()
+        loss.backward()
+        allreduce_gradients(rc.parameters())          # no-op for world size 1
+        opt.step()
+        losses.append(float(loss))
+    assert losses[-1] < 0.7 * losses[0], losses
