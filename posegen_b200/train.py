@@ -40,46 +40,55 @@ def _layer(acts: torch.Tensor, l: int, m: int) -> torch.Tensor:
     return runs[:, :m].permute(1, 0, 2).reshape(m, -1)
 
 
+def _relu_bwd(grad: torch.Tensor, act: torch.Tensor) -> torch.Tensor:
+    """grad * [act > 0] in one pass (act is the post-ReLU activation)."""
+    return torch.ops.aten.threshold_backward(grad, act, 0.0)
+
+
 def mlp_backward(params: Dict[str, torch.Tensor], enc: torch.Tensor, acts: torch.Tensor, d_raw: torch.Tensor) -> Dict[str, torch.Tensor]:
     """Weight gradients of one NeRF MLP (core/networks/nerf.py:94-148).
 
     params: fp32 nn.Linear tensors; enc [m,1080] fp32 network input; acts: the kernel's activation dump of this
-    pass; d_raw [m,4] = dL/d(rgb_raw, sigma_raw).  Returns {name: fp32 gradient}."""
+    pass; d_raw [m,4] = dL/d(rgb_raw, sigma_raw).  Deltas and activations are bf16, every GEMM accumulates in fp32
+    and the weight gradients are produced in fp32.  Returns {name: fp32 gradient}."""
     m = enc.shape[0]
     bf = torch.bfloat16
-    x_p, d_emb = enc[:, :432].to(bf), enc[:, 432:].to(bf)
+    encb = enc.to(bf)
+    x_p, d_emb = encb[:, :432], encb[:, 432:]
     H = [_layer(acts, l, m) for l in range(8)]
     G = _layer(acts, 8, m)
     W = {k: v.detach().to(bf) for k, v in params.items() if k.endswith("weight")}
     g: Dict[str, torch.Tensor] = {}
-    d_rgb, d_sig = d_raw[:, :3].to(bf), d_raw[:, 3:4].to(bf)
+    d_rawb = d_raw.to(bf)
+    d_rgb, d_sig = d_rawb[:, :3], d_rawb[:, 3:4]
     # rgb head and view layer:  g = relu(W_v [f | d_emb] + b_v),  f = W_f h7 + b_f,  rgb_raw = W_rgb g + b_rgb
     g["rgb_linear.weight"] = _mm32(d_rgb.t(), G)
     g["rgb_linear.bias"] = d_raw[:, :3].sum(0)
-    dG = (torch.mm(d_rgb, W["rgb_linear.weight"]) * (G > 0)).to(bf)
-    f = (torch.mm(H[7], W["feature_linear.weight"].t()).float() + params["feature_linear.bias"].detach()).to(bf)
+    dG = _relu_bwd(torch.mm(d_rgb, W["rgb_linear.weight"]), G)
+    f = torch.addmm(params["feature_linear.bias"].detach().to(bf), H[7], W["feature_linear.weight"].t())
     g["views_linears.0.weight"] = torch.cat([_mm32(dG.t(), f), _mm32(dG.t(), d_emb)], 1)
-    g["views_linears.0.bias"] = dG.float().sum(0)
+    g["views_linears.0.bias"] = dG.sum(0, dtype=torch.float32)
     df = torch.mm(dG, W["views_linears.0.weight"][:, :256])
     g["feature_linear.weight"] = _mm32(df.t(), H[7])
-    g["feature_linear.bias"] = df.float().sum(0)
+    g["feature_linear.bias"] = df.sum(0, dtype=torch.float32)
     # sigma head
     g["alpha_linear.weight"] = _mm32(d_sig.t(), H[7])
     g["alpha_linear.bias"] = d_raw[:, 3:4].sum(0)
-    dH = torch.mm(df, W["feature_linear.weight"]).float() + d_raw[:, 3:4] * params["alpha_linear.weight"].detach()
+    dH = torch.addmm(d_sig * W["alpha_linear.weight"], df, W["feature_linear.weight"])
     # trunk, last layer first; layer 5 reads [x_p | h4] (skip after layer index 4, nerf.py:100-101)
     for l in range(7, -1, -1):
-        dZ = (dH * (H[l] > 0)).to(bf)
+        dZ = _relu_bwd(dH, H[l])
+        dZt = dZ.t()
         if l == 0:
-            g["pts_linears.0.weight"] = _mm32(dZ.t(), x_p)
+            g["pts_linears.0.weight"] = _mm32(dZt, x_p)
         elif l == 5:
-            g["pts_linears.5.weight"] = torch.cat([_mm32(dZ.t(), x_p), _mm32(dZ.t(), H[4])], 1)
+            g["pts_linears.5.weight"] = torch.cat([_mm32(dZt, x_p), _mm32(dZt, H[4])], 1)
         else:
-            g[f"pts_linears.{l}.weight"] = _mm32(dZ.t(), H[l - 1])
-        g[f"pts_linears.{l}.bias"] = dZ.float().sum(0)
+            g[f"pts_linears.{l}.weight"] = _mm32(dZt, H[l - 1])
+        g[f"pts_linears.{l}.bias"] = dZ.sum(0, dtype=torch.float32)
         if l > 0:
             Wl = W[f"pts_linears.{l}.weight"]
-            dH = torch.mm(dZ, Wl[:, 432:] if l == 5 else Wl).float()
+            dH = torch.mm(dZ, Wl[:, 432:] if l == 5 else Wl)
     return g
 
 

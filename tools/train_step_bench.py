@@ -1,0 +1,101 @@
+#!/usr/bin/env python
+"""Training-step benchmark (BASELINE.json configs[3] / SURVEY.md §8d config 4): 3072-ray batches drawn from 256
+synthetic poses x 12 rays (per-ray skts, like configs/h36m/h36m_prot2.txt:34-35), forward + backward through
+posegen_b200.RayCaster in train mode, one NCCL all-reduce of the gradients, Adam step.  Eval-style sampling
+(perturb = 0, raw_noise_std = 0: the parity setting).  Auxiliary to bench.py; prints one JSON line on rank 0.
+
+    python tools/train_step_bench.py [--steps 20] [--cpu-baseline]
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/train_step_bench.py
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from posegen_b200 import dist as pdist, synthetic as syn                         # noqa: E402
+from posegen_b200.raycaster import raycaster_from_checkpoint                     # noqa: E402
+from posegen_b200.train import allreduce_gradients                               # noqa: E402
+
+
+def make_batch(seed, n_poses=256, rays_per_pose=12, res=512):
+    rng = np.random.RandomState(seed)
+    rb, sk, cy = [], [], []
+    for p in range(n_poses):
+        frame = syn.synthetic_frame(1000 + (seed * n_poses + p) % 64, res, res)      # 64 distinct poses are enough
+        b = syn.ray_batch(frame.rays_o, frame.rays_d)
+        sel = rng.randint(0, b.shape[0], rays_per_pose)
+        rb.append(b[sel]); sk.append(np.repeat(frame.pose.skts[None], rays_per_pose, 0)); cy.append(np.repeat(frame.pose.cyl[None], rays_per_pose, 0))
+    return np.concatenate(rb).astype(np.float32), np.concatenate(sk).astype(np.float32), np.concatenate(cy).astype(np.float32)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    rank, world, local = pdist.env_rank_world()
+    pdist.init_process_group("nccl" if world > 1 else None)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    ckpt = syn.synthetic_raycaster_state(4, alpha_gain=40.0)
+    rc = raycaster_from_checkpoint(ckpt, device=dev, precision="bf16")
+    rc.train()
+    opt = torch.optim.Adam([p for p in rc.parameters() if p.requires_grad], lr=5e-4)
+    rb, sk, cy = make_batch(rank)
+    n = rb.shape[0]
+    rbt, skt, cyt = (torch.as_tensor(x, device=dev) for x in (rb, sk, cy))
+    tgt = torch.rand(n, 3, device=dev)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        ret = rc(rbt, N_samples=64, N_importance=16, kp_batch=None, skts=skt, cyls=cyt, bones=None, cams=None, perturb=0., raw_noise_std=0.)
+        loss = ((ret["rgb_map"] + (1 - ret["acc_map"][:, None]) - tgt) ** 2).mean() + ((ret["rgb0"] + (1 - ret["acc0"][:, None]) - tgt) ** 2).mean()
+        loss.backward()
+        allreduce_gradients(rc.parameters())
+        opt.step()
+        return loss
+
+    for _ in range(a.warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = pdist.max_over_ranks(e0.elapsed_time(e1), dev) / a.steps
+    line = {"metric": "train_steps_per_sec", "value": 1e3 / ms, "ms_per_step": ms, "n_gpus": world, "rays_per_step": n * world,
+            "rays_per_sec": n * world / ms * 1e3, "final_loss": float(loss.detach()),
+            "config": "3072 rays/GPU from 256 poses x 12 rays, coarse+fine, fwd+bwd+allreduce+Adam, perturb=0, raw_noise_std=0, bf16 tensor-core forward"}
+    if a.cpu_baseline and rank == 0:
+        from oracle import render_oracle as orc
+        torch.set_num_threads(os.cpu_count() or 1)
+        nets, emb = orc.nets_from_ckpt(ckpt), orc.embed_params_from_ckpt(ckpt)
+        for net in nets:
+            for v in net.values():
+                v.requires_grad_(True)
+        m = 768                                          # bounded sample of the batch
+        t0 = time.perf_counter()
+        r = orc.render_rays(torch.as_tensor(rb[:m]), torch.as_tensor(sk[:m]), torch.as_tensor(cy[:m]), nets, emb)
+        l = ((r["rgb_map"] + (1 - r["acc_map"][:, None]) - tgt[:m].cpu()) ** 2).mean() + ((r["rgb0"] + (1 - r["acc0"][:, None]) - tgt[:m].cpu()) ** 2).mean()
+        l.backward()
+        sec = time.perf_counter() - t0
+        line["cpu_baseline"] = {"rays_per_sec": m / sec, "cores": os.cpu_count(), "kind": "port", "sample": f"{m} rays of the batch, fwd+bwd (autograd through the oracle), {sec:.1f} s"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
