@@ -200,6 +200,12 @@ PGN_API int  pgn_composite(pgn_context* ctx, const pgn_render_inputs* in, const 
                    int32_t s, float* rgb_map, float* disp_map, float* acc_map,
                    float* weights, float* alpha, void* stream);
 
+/* backward of encode_inputs (core/raycasters.py:476-555) w.r.t. the world->joint transforms, the gradient the pose
+ * generator / pose optimisation receives (run_gan.py GAN step; core/pose_opt.py): g_enc [n, n_z, 1080] = dL/d(network
+ * input) in the reference channel order, z [n, n_z] -> d_skts [n,24,4,4] (per-ray gradient, bottom rows zero). */
+PGN_API int  pgn_encode_backward(pgn_context* ctx, const pgn_render_inputs* in, const float* z, int32_t n_z,
+                                 const float* g_enc, float* d_skts, void* stream);
+
 /* backward of NeRF.raw2outputs for the training step (core/trainer.py:321-370 reads rgb_map and acc_map):
  * g_rgb [n,3] = dL/d rgb_map, g_acc [n] = dL/d acc_map (may be NULL) -> d_raw [n,s,4] = dL/d raw.
  * No gradient flows through z (the importance samples are detached, core/utils/ray_utils.py:286). */

@@ -311,6 +311,18 @@ int pgn_composite(pgn_context* c, const pgn_render_inputs* in, const float* raw,
   return PGN_OK;
 }
 
+int pgn_encode_backward(pgn_context* c, const pgn_render_inputs* in, const float* z, int32_t n_z, const float* g_enc,
+                        float* d_skts, void* stream) {
+  int rc = check_inputs(c, in, "pgn_encode_backward");
+  if (rc) return rc;
+  if (!z || !g_enc || !d_skts || n_z <= 0) return fail(PGN_E_INVALID, "pgn_encode_backward: bad argument");
+  if (!c->have_sc) return fail(PGN_E_STATE, "pgn_encode_backward: scalars not set");
+  PGN_CUDA(cudaSetDevice(c->cfg.device));
+  PGN_CUDA(pgn_launch_encode_backward(make_refs(in), c->d_sc, z, n_z, g_enc, d_skts, (cudaStream_t)stream));
+  c->launches++;
+  return PGN_OK;
+}
+
 int pgn_composite_backward(pgn_context* c, const pgn_render_inputs* in, const float* raw, const float* z, int32_t s,
                            const float* g_rgb, const float* g_acc, float* d_raw, void* stream) {
   int rc = check_inputs(c, in, "pgn_composite_backward");

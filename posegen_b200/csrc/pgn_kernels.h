@@ -74,6 +74,8 @@ cudaError_t pgn_launch_compose_frame(int H, int W, int x0, int y0, int x1, int y
 
 cudaError_t pgn_launch_composite_backward(const PgnRayRefs& rays, const PgnScalars* sc_dev, const float* raw, const float* z,
                                           int s, const float* g_rgb, const float* g_acc, float* d_raw, cudaStream_t stream);
+cudaError_t pgn_launch_encode_backward(const PgnRayRefs& rays, const PgnScalars* sc_dev, const float* z, int n_z,
+                                       const float* g_enc, float* d_skts, cudaStream_t stream);
 cudaError_t pgn_launch_pose_fk(const float* bones, const float* rest, int n_poses, float ext, float top_ratio, float bot_ratio,
                                float* skts, float* kps, float* cyls, float* l2ws, cudaStream_t stream);
 cudaError_t pgn_launch_hmr_input(const float* image, int H, int W, int x0, int y0, int x1, int y1, int R,

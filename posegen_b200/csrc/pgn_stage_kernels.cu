@@ -518,3 +518,118 @@ cudaError_t pgn_launch_composite_backward(const PgnRayRefs& rays, const PgnScala
   else return cudaErrorInvalidValue;
   return cudaGetLastError();
 }
+
+// ---------------------------------------------------------------------------
+// Backward of encode_inputs (core/raycasters.py:476-555; encoders.py:8-37,110-122,181-193;
+// cutoff_embedder.py:111-174) w.r.t. the world->joint transforms: the gradient the pose generator / pose
+// optimisation receives (BASELINE.json configs[4]: "differentiable render, grad w.r.t. pose/bone transforms").
+// One thread per (ray, joint) loops over the ray's samples; g_enc [n, n_z, 1080] = dL/d(network input) in the
+// reference channel order; d_skts [n, 24, 4, 4] receives the per-ray gradient (bottom row 0).  Sample positions
+// carry no gradient (rays are inputs, importance samples are detached).
+//   pts_t = R p + t, v = |pts_t|, r = pts_t / v, w = 1 - sigmoid(tau (v - c)),  w' = -tau w (1 - w)
+//   e_k = phi_k(v) w (v-embed), q_k,a = psi_k(u_a) w_d(v) with u = R d / |R d| (view embed)
+// ---------------------------------------------------------------------------
+__global__ void pgn_encode_backward_kernel(PgnRayRefs rays, const PgnScalars* __restrict__ scp, const float* __restrict__ z,
+                                           int n_z, const float* __restrict__ g_enc, float* __restrict__ d_skts) {
+  const PgnScalars& sc = *scp;
+  const long long total = rays.n_rays * PGN_J;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(idx % PGN_J);
+    const long long ray = idx / PGN_J;
+    const float* rb = rays.ray_batch + ray * 11;
+    const float4* m = reinterpret_cast<const float4*>(pgn_ray_skts(rays, ray) + j * 16);
+    const float4 m0 = __ldg(m), m1 = __ldg(m + 1), m2 = __ldg(m + 2);
+    const float dd[3] = {rb[3], rb[4], rb[5]};
+    // joint-frame view direction (per ray)
+    float dj[3] = {fmaf(m0.z, dd[2], fmaf(m0.y, dd[1], m0.x * dd[0])), fmaf(m1.z, dd[2], fmaf(m1.y, dd[1], m1.x * dd[0])),
+                   fmaf(m2.z, dd[2], fmaf(m2.y, dd[1], m2.x * dd[0]))};
+    const float nd = sqrtf(dj[0] * dj[0] + dj[1] * dj[1] + dj[2] * dj[2]);
+    const float ndc = fmaxf(nd, 1e-12f);
+    const float u[3] = {dj[0] / ndc, dj[1] / ndc, dj[2] / ndc};
+    float gR[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, gt[3] = {0, 0, 0}, gu[3] = {0, 0, 0};
+    for (int s = 0; s < n_z; ++s) {
+      const long long rs = ray * n_z + s;
+      float p[3];
+      pgn_sample_point(rb, rb + 3, z[rs], p[0], p[1], p[2]);
+      const float x = fmaf(m0.z, p[2], fmaf(m0.y, p[1], m0.x * p[0])) + m0.w;
+      const float y = fmaf(m1.z, p[2], fmaf(m1.y, p[1], m1.x * p[0])) + m1.w;
+      const float zz = fmaf(m2.z, p[2], fmaf(m2.y, p[1], m2.x * p[0])) + m2.w;
+      const float v = sqrtf(x * x + y * y + zz * zz);
+      const float vc = fmaxf(v, 1e-12f);
+      const float r[3] = {x / vc, y / vc, zz / vc};
+      const float w = pgn_window<false>(v, sc.tau_v, sc.cutoff_v[j]);
+      const float wd = pgn_window<false>(v, sc.tau_d, sc.cutoff_d[j]);
+      const float dw = -sc.tau_v * w * (1.0f - w), dwd = -sc.tau_d * wd * (1.0f - wd);
+      const float* ge = g_enc + rs * PGN_ENC;
+      // v-embed: k = 0 -> v, k = 1 + 2f -> sin(2^f v), 2 + 2f -> cos(2^f v)
+      float gv = ge[j] * (w + v * dw);
+#pragma unroll
+      for (int f = 0; f < PGN_LV; ++f) {
+        const float fr = (float)(1 << f), a = v * fr;
+        const float sn = sinf(a), cs = cosf(a);
+        gv += ge[(1 + 2 * f) * PGN_J + j] * (fr * cs * w + sn * dw);
+        gv += ge[(2 + 2 * f) * PGN_J + j] * (-fr * sn * w + cs * dw);
+      }
+      // view embed: every channel is psi(u_a) * wd(v)
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const float* gq = ge + PGN_ENC_P + j * 3 + a;
+        gv += gq[0] * u[a] * dwd;
+        gu[a] += gq[0] * wd;
+#pragma unroll
+        for (int f = 0; f < PGN_LD; ++f) {
+          const float fr = (float)(1 << f), ang = u[a] * fr;
+          const float sn = sinf(ang), cs = cosf(ang);
+          const float g1 = gq[(1 + 2 * f) * 72], g2 = gq[(2 + 2 * f) * 72];
+          gv += (g1 * sn + g2 * cs) * dwd;
+          gu[a] += (g1 * cs - g2 * sn) * fr * wd;
+        }
+      }
+      // r = pts_t / v
+      const float gr[3] = {ge[360 + j * 3], ge[360 + j * 3 + 1], ge[360 + j * 3 + 2]};
+      float gp[3];
+      if (v > 1e-12f) {
+        const float rg = r[0] * gr[0] + r[1] * gr[1] + r[2] * gr[2];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) gp[a] = gv * r[a] + (gr[a] - r[a] * rg) / v;
+      } else {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) gp[a] = gr[a] / 1e-12f;
+      }
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        gR[a * 3 + 0] += gp[a] * p[0]; gR[a * 3 + 1] += gp[a] * p[1]; gR[a * 3 + 2] += gp[a] * p[2];
+        gt[a] += gp[a];
+      }
+    }
+    // u = R d / |R d|
+    float gdj[3];
+    if (nd > 1e-12f) {
+      const float ug = u[0] * gu[0] + u[1] * gu[1] + u[2] * gu[2];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) gdj[a] = (gu[a] - u[a] * ug) / nd;
+    } else {
+#pragma unroll
+      for (int a = 0; a < 3; ++a) gdj[a] = gu[a] / 1e-12f;
+    }
+    float* o = d_skts + (ray * PGN_J + j) * 16;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      o[a * 4 + 0] = gR[a * 3 + 0] + gdj[a] * dd[0];
+      o[a * 4 + 1] = gR[a * 3 + 1] + gdj[a] * dd[1];
+      o[a * 4 + 2] = gR[a * 3 + 2] + gdj[a] * dd[2];
+      o[a * 4 + 3] = gt[a];
+    }
+    o[12] = 0.f; o[13] = 0.f; o[14] = 0.f; o[15] = 0.f;
+  }
+}
+
+cudaError_t pgn_launch_encode_backward(const PgnRayRefs& rays, const PgnScalars* sc_dev, const float* z, int n_z,
+                                       const float* g_enc, float* d_skts, cudaStream_t stream) {
+  const long long total = rays.n_rays * PGN_J;
+  if (total == 0) return cudaSuccess;
+  const int block = 96;                                   // 4 rays x 24 joints: the 24 threads of a ray read contiguous channels
+  const long long grid = min((total + block - 1) / block, (long long)148 * 32);
+  pgn_encode_backward_kernel<<<(unsigned)grid, block, 0, stream>>>(rays, sc_dev, z, n_z, g_enc, d_skts);
+  return cudaGetLastError();
+}

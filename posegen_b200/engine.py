@@ -246,6 +246,15 @@ class Engine:
                                                    _ptr(d_raw), self._stream()))
         return d_raw
 
+    def encode_backward(self, ray_batch, skts, cyls, z, g_enc):
+        """dL/d skts [n,24,4,4] (per ray) given dL/d(network input) [n, n_z, 1080]."""
+        inp, keep = self._inputs(ray_batch, skts, cyls)
+        z = z.contiguous()
+        d = torch.empty((inp.n_rays, 24, 4, 4), dtype=torch.float32, device=z.device)
+        _lib.check(self.lib.pgn_encode_backward(self.handle, C.byref(inp), _ptr(z), z.shape[1], _ptr(g_enc.contiguous()), _ptr(d),
+                                                self._stream()))
+        return d
+
     def sample_pdf(self, z, weights):
         _check_f32_cuda(z, "z")
         n, dev = z.shape[0], z.device

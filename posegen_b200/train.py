@@ -4,9 +4,10 @@ Forward: the fused bf16 tensor-core kernel (`pgn_render_forward_train`) with the
 every MLP layer dumped in bf16.  Backward: `pgn_composite_backward` (hand-written) turns dL/d(rgb_map, acc_map)
 of both passes into dL/d raw; the weight gradients of the two MLPs are then plain dense GEMMs over all samples
 of the batch (activations^T x deltas, deltas x weights) and go through cuBLAS (`torch.mm`, bf16 inputs, fp32
-accumulation); the network inputs x_p / d_emb are regenerated with `pgn_encode`.  No gradient flows through the
-sample positions (the importance samples are detached in the reference, core/utils/ray_utils.py:286) and, in
-this round, none to `skts` (pose optimisation, config 5).
+accumulation); the network inputs x_p / d_emb are regenerated with `pgn_encode`.  When `skts` requires grad (the
+pose generator / pose optimisation, configs[4]) dL/d(network input) is formed by three more GEMMs and
+`pgn_encode_backward` (hand-written) turns it into dL/d skts.  No gradient flows through the sample positions
+(the importance samples are detached in the reference, core/utils/ray_utils.py:286).
 
 Sampling is the eval-style deterministic one (perturb = 0, raw_noise_std = 0: the reference's parity setting,
 SURVEY.md §8d config 4); stratified jitter and density noise are not implemented yet.
@@ -45,12 +46,14 @@ def _relu_bwd(grad: torch.Tensor, act: torch.Tensor) -> torch.Tensor:
     return torch.ops.aten.threshold_backward(grad, act, 0.0)
 
 
-def mlp_backward(params: Dict[str, torch.Tensor], enc: torch.Tensor, acts: torch.Tensor, d_raw: torch.Tensor) -> Dict[str, torch.Tensor]:
+def mlp_backward(params: Dict[str, torch.Tensor], enc: torch.Tensor, acts: torch.Tensor, d_raw: torch.Tensor,
+                 want_input_grad: bool = False) -> Dict[str, torch.Tensor]:
     """Weight gradients of one NeRF MLP (core/networks/nerf.py:94-148).
 
     params: fp32 nn.Linear tensors; enc [m,1080] fp32 network input; acts: the kernel's activation dump of this
     pass; d_raw [m,4] = dL/d(rgb_raw, sigma_raw).  Deltas and activations are bf16, every GEMM accumulates in fp32
-    and the weight gradients are produced in fp32.  Returns {name: fp32 gradient}."""
+    and the weight gradients are produced in fp32.  Returns {name: fp32 gradient}; with want_input_grad also
+    "_g_enc" [m,1080] = dL/d(network input) (for the gradient w.r.t. the pose transforms)."""
     m = enc.shape[0]
     bf = torch.bfloat16
     encb = enc.to(bf)
@@ -68,6 +71,9 @@ def mlp_backward(params: Dict[str, torch.Tensor], enc: torch.Tensor, acts: torch
     f = torch.addmm(params["feature_linear.bias"].detach().to(bf), H[7], W["feature_linear.weight"].t())
     g["views_linears.0.weight"] = torch.cat([_mm32(dG.t(), f), _mm32(dG.t(), d_emb)], 1)
     g["views_linears.0.bias"] = dG.sum(0, dtype=torch.float32)
+    g_in = torch.zeros((m, 1080), dtype=torch.float32, device=enc.device) if want_input_grad else None
+    if want_input_grad:
+        g_in[:, 432:] = torch.mm(dG, W["views_linears.0.weight"][:, 256:])
     df = torch.mm(dG, W["views_linears.0.weight"][:, :256])
     g["feature_linear.weight"] = _mm32(df.t(), H[7])
     g["feature_linear.bias"] = df.sum(0, dtype=torch.float32)
@@ -86,9 +92,13 @@ def mlp_backward(params: Dict[str, torch.Tensor], enc: torch.Tensor, acts: torch
         else:
             g[f"pts_linears.{l}.weight"] = _mm32(dZt, H[l - 1])
         g[f"pts_linears.{l}.bias"] = dZ.sum(0, dtype=torch.float32)
+        Wl = W[f"pts_linears.{l}.weight"]
+        if want_input_grad and l in (0, 5):
+            g_in[:, :432] += torch.mm(dZ, Wl[:, :432])
         if l > 0:
-            Wl = W[f"pts_linears.{l}.weight"]
             dH = torch.mm(dZ, Wl[:, 432:] if l == 5 else Wl)
+    if want_input_grad:
+        g["_g_enc"] = g_in
     return g
 
 
@@ -112,6 +122,8 @@ class _RenderTrainFn(torch.autograd.Function):
         t = torch.linspace(0., 1., S, device=rb.device)                       # sample_from_lineseg, ray_utils.py:204-251
         z_c = near_far[:, :1] * (1. - t) + near_far[:, 1:2] * t
         grads: List[torch.Tensor] = []
+        want_sk = ctx.needs_input_grad[2]
+        d_skts = None
         for net, acts, z, raw_p, gr, ga in ((rc.network, ctx.acts["c"], z_c, raw0, g_rgb0, g_acc0),
                                             (rc.network_fine, ctx.acts["f"], z_fine, raw, g_rgb, g_acc)):
             gr = zero3 if gr is None else gr.contiguous().float()
@@ -119,18 +131,23 @@ class _RenderTrainFn(torch.autograd.Function):
             d_raw = eng.composite_backward(rb, sk, cy, raw_p, z.contiguous(), gr, ga)
             enc = eng.encode(rb, sk, cy, z.contiguous())
             pd = dict(net.named_parameters())
-            gd = mlp_backward(pd, enc.reshape(-1, 1080), acts, d_raw.reshape(-1, 4))
+            gd = mlp_backward(pd, enc.reshape(-1, 1080), acts, d_raw.reshape(-1, 4), want_input_grad=want_sk)
             grads += [gd[k].reshape(pd[k].shape).to(pd[k].dtype) for k in PARAM_ORDER]
+            if want_sk:          # pose gradient: dL/d(network input) -> dL/d skts (per ray), both passes add up
+                d = eng.encode_backward(rb, sk, cy, z.contiguous(), gd["_g_enc"].reshape(n, -1, 1080))
+                d_skts = d if d_skts is None else d_skts + d
         ctx.acts = None
-        return (None, None, None, None, None) + tuple(grads)
+        if want_sk and sk.dim() == 3:
+            d_skts = d_skts.sum(0)                     # one pose shared by every ray of the batch
+        return (None, None, d_skts, None, None) + tuple(grads)
 
 
 def render_train(rc, ray_batch, skts, cyls, nanfill_chunk=None) -> Dict[str, torch.Tensor]:
-    """Differentiable (w.r.t. the two MLPs' parameters) render of a ray batch: the train-mode body of
+    """Differentiable (w.r.t. the two MLPs' parameters and `skts`) render of a ray batch: the train-mode body of
     RayCaster.forward.  Returns the reference's dict (core/raycasters.py:711-724) without alpha/alpha0."""
     params = [dict(net.named_parameters())[k] for net in (rc.network, rc.network_fine) for k in PARAM_ORDER]
     n = ray_batch.shape[0]
-    out = _RenderTrainFn.apply(rc, ray_batch.float().contiguous(), skts.float(), cyls.float(),
+    out = _RenderTrainFn.apply(rc, ray_batch.float().contiguous(), skts if skts.dtype == torch.float32 else skts.float(), cyls.float(),
                                n if nanfill_chunk is None else nanfill_chunk, *params)
     return {"rgb_map": out[0], "acc_map": out[1], "rgb0": out[2], "acc0": out[3], "disp_map": out[4], "disp0": out[5],
             "alpha": None, "alpha0": None}

@@ -103,5 +103,40 @@ def test_training_step_reduces_the_loss(engine, train_case):
         loss.backward()
         allreduce_gradients(rc.parameters())          # no-op for world size 1
         opt.step()
-        losses.append(float(loss))
+        losses.append(float(loss.detach()))
     assert losses[-1] < 0.7 * losses[0], losses
+
+
+def test_pose_gradient_matches_oracle_autograd(engine, train_case):
+    """BASELINE.json configs[4]: differentiable render, gradient w.r.t. the pose / bone transforms (skts)."""
+    frame, ckpt, rb, tgt = train_case
+    n = 768
+    dev = torch.device("cuda")
+    nets, emb = orc.nets_from_ckpt(ckpt), orc.embed_params_from_ckpt(ckpt)
+    sk_ref = torch.as_tensor(frame.pose.skts)[None].repeat(n, 1, 1, 1).requires_grad_(True)       # per-ray leaf, like the reference
+    cy = torch.as_tensor(frame.pose.cyl)[None].expand(n, -1)
+    loss_ref, _, _ = _oracle_loss(torch.as_tensor(rb[:n]), sk_ref, cy, nets, emb, torch.as_tensor(tgt[:n]))
+    loss_ref.backward()
+    rc = raycaster_from_checkpoint(ckpt, device="cuda", precision="bf16")
+    rc.train()
+    sk = torch.as_tensor(frame.pose.skts, device=dev)[None].repeat(n, 1, 1, 1).requires_grad_(True)
+    ret = rc(torch.as_tensor(rb[:n], device=dev), N_samples=64, N_importance=16, kp_batch=None, skts=sk, cyls=cy.to(dev).contiguous(),
+             bones=None, cams=None, perturb=0., raw_noise_std=0.)
+    t = torch.as_tensor(tgt[:n], device=dev)
+    loss = ((ret["rgb_map"] + (1 - ret["acc_map"][:, None]) - t) ** 2).mean() + ((ret["rgb0"] + (1 - ret["acc0"][:, None]) - t) ** 2).mean()
+    loss.backward()
+    torch.cuda.synchronize()
+    engine.check_status()
+    g, gr = sk.grad.cpu().double(), sk_ref.grad.double()
+    assert g.shape == gr.shape and torch.isfinite(g).all()
+    assert float(g[:, :, 3].abs().max()) == 0.0                       # the homogeneous row carries no gradient
+    rel = float((g - gr).norm() / gr.norm())
+    cos = float((g.reshape(-1) @ gr.reshape(-1)) / (g.norm() * gr.norm()))
+    assert cos >= 0.995 and rel <= 0.1, (cos, rel)
+    # a pose shared by all rays ([24,4,4]) receives the sum over rays
+    sk1 = torch.as_tensor(frame.pose.skts, device=dev).clone().requires_grad_(True)
+    ret = rc(torch.as_tensor(rb[:n], device=dev), N_samples=64, N_importance=16, kp_batch=None, skts=sk1, cyls=torch.as_tensor(frame.pose.cyl, device=dev),
+             bones=None, cams=None, perturb=0., raw_noise_std=0.)
+    loss = ((ret["rgb_map"] + (1 - ret["acc_map"][:, None]) - t) ** 2).mean() + ((ret["rgb0"] + (1 - ret["acc0"][:, None]) - t) ** 2).mean()
+    loss.backward()
+    assert float((sk1.grad.cpu().double() - gr.sum(0)).norm() / gr.sum(0).norm()) <= 0.1
