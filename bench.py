@@ -268,7 +268,7 @@ def run_ours(args, rank, world, local):
                      "traffic": ncu_traffic() if args.precision == "bf16" else None,
                      "traffic_note": "DRAM bytes read+written by one launch (239,148-ray frame), ncu --set full, profiles/r1_bf16_render_512.json; "
                                      "algorithmic bytes per launch = 84 B/ray + 2 x 1.83 MB weights = 23.7 MB (HBM is not the bound)",
-                     "peak_source": f"{peaks['src']} bf16 sustained (kernel runs >100 ms per launch); burst {peaks['bf16_burst']}",
+                     "peak_source": f"{peaks['src']} bf16 sustained (40-55 ms launches back to back inside a seconds-long step loop at the power cap); burst {peaks['bf16_burst']}",
                      "flop_per_ray": FLOP_PER_RAY, "kernel": "pgn_render_bf16_kernel" if args.precision == "bf16" else "pgn_render_fp32_kernel",
                      "note": "algorithmic FLOPs (reference nn.Linear MACs x2); whole-step device time (near/far pre-pass included)"},
         "clocks": sampler.summary(),
