@@ -29,10 +29,12 @@ PARAM_ORDER = [f"pts_linears.{i}.{k}" for i in range(8) for k in ("weight", "bia
 
 def _mm32(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     """a [m,k] @ b [k,n] with bf16 inputs and an fp32 result (cuBLAS accumulates in fp32)."""
-    try:
-        return torch.mm(a, b, out_dtype=torch.float32)
-    except TypeError:                                      # older torch: no out_dtype
-        return torch.mm(a.float(), b.float())
+    if a.is_cuda:
+        try:
+            return torch.mm(a, b, out_dtype=torch.float32)
+        except (TypeError, RuntimeError):                  # older torch: no out_dtype
+            pass
+    return torch.mm(a.float(), b.float())
 
 
 def _layer(acts: torch.Tensor, l: int, m: int) -> torch.Tensor:

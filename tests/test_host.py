@@ -137,3 +137,49 @@ def test_hmr_input_oracle_properties():
     out = nxt.hmr_input(flat, crop=(0, 0, 80, 80), out_res=24)
     assert np.abs(out - (1.0 - np.array([0.485, 0.456, 0.406], np.float32))[:, None, None] /
                   np.array([0.485, 0.456, 0.406], np.float32)[:, None, None]).max() <= 1e-5
+
+
+def test_mlp_backward_matches_autograd_on_cpu():
+    """Host logic of the training step (posegen_b200/train.py): the GEMM weight / input gradients of one NeRF MLP,
+    fed with an activation dump in the kernel's layout ([layer][run][row][8]) built from a torch forward, against
+    autograd through the oracle's nerf_forward."""
+    import numpy as np
+    import torch
+    from oracle import render_oracle as orc
+    from posegen_b200 import synthetic as syn
+    from posegen_b200.train import mlp_backward, PARAM_ORDER
+    torch.manual_seed(0)
+    m = 192
+    net = {k: torch.as_tensor(v) for k, v in syn.synthetic_nerf_state(5).items()}
+    for v in net.values():
+        v.requires_grad_(True)
+    enc = (torch.randn(m, 1080) * 0.5).requires_grad_(True)
+    raw = orc.nerf_forward(enc, net)
+    d_raw = torch.randn(m, 4)
+    (raw * d_raw).sum().backward()
+    # activation dump: post-ReLU activations per layer, bf16, [272 runs, rows (padded), 8]
+    with torch.no_grad():
+        x_p, x_v = enc[:, :432], enc[:, 432:]
+        h, acts = x_p, []
+        for l in range(8):
+            h = torch.relu(torch.nn.functional.linear(h, net[f"pts_linears.{l}.weight"], net[f"pts_linears.{l}.bias"]))
+            acts.append(h)
+            if l == 4:
+                h = torch.cat([x_p, h], -1)
+        feat = torch.nn.functional.linear(acts[7], net["feature_linear.weight"], net["feature_linear.bias"])
+        g = torch.relu(torch.nn.functional.linear(torch.cat([feat, x_v], -1), net["views_linears.0.weight"], net["views_linears.0.bias"]))
+        rows = 256
+        dump = torch.zeros((272, rows, 8), dtype=torch.bfloat16)
+        for l in range(8):
+            dump[l * 32:(l + 1) * 32, :m] = acts[l].reshape(m, 32, 8).permute(1, 0, 2).to(torch.bfloat16)
+        dump[256:272, :m] = g.reshape(m, 16, 8).permute(1, 0, 2).to(torch.bfloat16)
+    params = {k: v.detach() for k, v in net.items()}
+    got = mlp_backward(params, enc.detach(), dump, d_raw, want_input_grad=True)
+    flat, ref = [], []
+    for k in PARAM_ORDER:
+        assert got[k].reshape(net[k].shape).shape == net[k].grad.shape
+        flat.append(got[k].reshape(-1).double()); ref.append(net[k].grad.reshape(-1).double())
+    a, b = torch.cat(flat), torch.cat(ref)
+    assert float((a - b).norm() / b.norm()) <= 2e-2                      # bf16 activations / deltas / weights
+    ge, gr = got["_g_enc"].double(), enc.grad.double()
+    assert float((ge - gr).norm() / gr.norm()) <= 2e-2
