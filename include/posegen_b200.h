@@ -164,10 +164,19 @@ PGN_API int  pgn_render_forward(pgn_context* ctx, const pgn_render_inputs* in,
  * [layer 0..8][run][row][8]: run = 8 consecutive columns, layers 0-7 (pts_linears) have 32 runs, layer 8
  * (views_linears.0, 128 columns) has 16 and starts 8*32 runs in; rows are samples in (ray, sample) order, padded
  * to pgn_activation_dump_bytes(n, pass) / 4352 rows.  act_coarse / act_fine: device buffers of
- * pgn_activation_dump_bytes(n_rays, 0 / 1) bytes.  Request out->raw0 / raw / z_fine / near_far for the backward. */
+ * pgn_activation_dump_bytes(n_rays, 0 / 1) bytes.  Request out->raw0 / raw / z_fine / near_far for the backward.
+ * rnd (may be NULL = deterministic eval sampling) carries the training-time randomness as explicit device arrays so
+ * that a run is reproducible and checkable: the caller draws them with its own generator. */
+typedef struct pgn_train_random {
+  const float* t_rand;   /* [n,64] U(0,1): stratified jitter of the coarse samples, perturb > 0 (ray_utils.py:236-246) */
+  const float* u_is;     /* [n,16] U(0,1): importance-sampling quantiles, det = False (ray_utils.py:169-170)          */
+  const float* noise0;   /* [n,64] N(0,1) * raw_noise_std * B: density noise of the coarse pass (nerf.py:176-186)     */
+  const float* noise;    /* [n,80] same for the fine pass                                                              */
+} pgn_train_random;
 PGN_API size_t pgn_activation_dump_bytes(int64_t n_rays, int32_t pass);
 PGN_API int  pgn_render_forward_train(pgn_context* ctx, const pgn_render_inputs* in, const pgn_render_outputs* out,
-                                      void* act_coarse, void* act_fine, void* workspace, size_t workspace_bytes, void* stream);
+                                      void* act_coarse, void* act_fine, const pgn_train_random* rnd,
+                                      void* workspace, size_t workspace_bytes, void* stream);
 
 /* number of kernel launches issued by this context since creation
  * (bench.py reports it as gpu_launches) */
@@ -210,7 +219,8 @@ PGN_API int  pgn_encode_backward(pgn_context* ctx, const pgn_render_inputs* in, 
  * g_rgb [n,3] = dL/d rgb_map, g_acc [n] = dL/d acc_map (may be NULL) -> d_raw [n,s,4] = dL/d raw.
  * No gradient flows through z (the importance samples are detached, core/utils/ray_utils.py:286). */
 PGN_API int  pgn_composite_backward(pgn_context* ctx, const pgn_render_inputs* in, const float* raw, const float* z,
-                                    int32_t s, const float* g_rgb, const float* g_acc, float* d_raw, void* stream);
+                                    int32_t s, const float* g_rgb, const float* g_acc, const float* noise /* [n,s] or NULL */,
+                                    float* d_raw, void* stream);
 
 /* isample_from_lineseg + sample_pdf, det=True (core/utils/ray_utils.py:157-201,255-289):
  * z [n,64], weights [n,64] -> z_samples [n,16], z_sorted [n,80], pdf_inds [n,16],

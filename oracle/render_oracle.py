@@ -61,12 +61,19 @@ def _nanmean32(x):
 
 
 # ----------------------------------------------------------------------------
-# core/utils/ray_utils.py:204-251  sample_from_lineseg (perturb == 0, lindisp False)
+# core/utils/ray_utils.py:204-251  sample_from_lineseg (lindisp False).  perturb > 0 (training): the
+# stratified jitter takes its uniform numbers from `t_rand` [N,n_samples] (the reference draws torch.rand).
 # ----------------------------------------------------------------------------
-def coarse_z_vals(near, far, n_samples):
+def coarse_z_vals(near, far, n_samples, t_rand=None):
     t = torch.linspace(0., 1., steps=n_samples, dtype=near.dtype, device=near.device)
     t = t.expand(near.shape[0], n_samples)
-    return near * (1. - t) + far * t
+    z_vals = near * (1. - t) + far * t
+    if t_rand is not None:
+        mids = .5 * (z_vals[..., 1:] + z_vals[..., :-1])
+        upper = torch.cat([mids, z_vals[..., -1:]], -1)
+        lower = torch.cat([z_vals[..., :1], mids], -1)
+        z_vals = lower + (upper - lower) * t_rand
+    return z_vals
 
 
 # ----------------------------------------------------------------------------
@@ -149,15 +156,16 @@ def nerf_forward(x, net, chunk=1024 * 64):
 
 
 # ----------------------------------------------------------------------------
-# core/networks/nerf.py:150-205  raw2outputs (act=relu, B=density_scale, no noise)
+# core/networks/nerf.py:150-205  raw2outputs (act=relu, B=density_scale).  `noise` [N,S] (training,
+# raw_noise_std > 0) = randn * raw_noise_std * B, added to raw_sigma / B before the ReLU (nerf.py:165,176-186).
 # ----------------------------------------------------------------------------
-def raw2outputs(raw, z_vals, rays_d, density_scale=1.0, rgb_eps=0.001):
+def raw2outputs(raw, z_vals, rays_d, density_scale=1.0, rgb_eps=0.001, noise=None):
     dists = z_vals[..., 1:] - z_vals[..., :-1]
     big = torch.full_like(dists[..., :1], 1e10)
     dists = torch.cat([dists, big], -1)
     dists = dists * torch.norm(rays_d[..., None, :], dim=-1)
     rgb = torch.sigmoid(raw[..., :3]) * (1 + 2 * rgb_eps) - rgb_eps
-    alpha = 1. - torch.exp(-F.relu(raw[..., 3] / density_scale) * dists)
+    alpha = 1. - torch.exp(-F.relu(raw[..., 3] / density_scale + (0. if noise is None else noise)) * dists)
     ones = torch.ones((alpha.shape[0], 1), dtype=alpha.dtype, device=alpha.device)
     weights = alpha * torch.cumprod(torch.cat([ones, 1. - alpha + 1e-10], -1), -1)[:, :-1]
     rgb_map = torch.sum(weights[..., None] * rgb, -2)
@@ -171,15 +179,18 @@ def raw2outputs(raw, z_vals, rays_d, density_scale=1.0, rgb_eps=0.001):
 
 
 # ----------------------------------------------------------------------------
-# core/utils/ray_utils.py:157-201  sample_pdf (det=True)
+# core/utils/ray_utils.py:157-201  sample_pdf (det=True; det=False when `u` [N,n_samples] is given: the
+# reference then draws torch.rand)
 # ----------------------------------------------------------------------------
-def sample_pdf_det(bins, weights, n_samples):
+def sample_pdf_det(bins, weights, n_samples, u=None):
     weights = weights + 1e-5
     pdf = weights / torch.sum(weights, -1, keepdim=True)
     cdf = torch.cumsum(pdf, -1)
     cdf = torch.cat([torch.zeros_like(cdf[..., :1]), cdf], -1)
-    u = torch.linspace(0., 1., steps=n_samples, dtype=cdf.dtype, device=cdf.device)
-    u = u.expand(list(cdf.shape[:-1]) + [n_samples]).contiguous()
+    if u is None:
+        u = torch.linspace(0., 1., steps=n_samples, dtype=cdf.dtype, device=cdf.device)
+        u = u.expand(list(cdf.shape[:-1]) + [n_samples])
+    u = u.contiguous()
     inds = torch.searchsorted(cdf, u, right=True)
     below = torch.clamp(inds - 1, min=0)
     above = torch.clamp(inds, max=cdf.shape[-1] - 1)
@@ -194,9 +205,9 @@ def sample_pdf_det(bins, weights, n_samples):
 # ----------------------------------------------------------------------------
 # core/utils/ray_utils.py:255-289  isample_from_lineseg (is_only False)
 # ----------------------------------------------------------------------------
-def importance_z_vals(z_vals, weights, n_importance):
+def importance_z_vals(z_vals, weights, n_importance, u=None):
     mids = .5 * (z_vals[..., 1:] + z_vals[..., :-1])
-    z_samples, inds, cdf = sample_pdf_det(mids, weights[..., 1:-1], n_importance)
+    z_samples, inds, cdf = sample_pdf_det(mids, weights[..., 1:-1], n_importance, u=u)
     z_all, sorted_idxs = torch.sort(torch.cat([z_vals, z_samples], -1), -1)
     return z_all, z_samples, sorted_idxs, inds, cdf
 

@@ -47,6 +47,10 @@ class RenderOutputs(C.Structure):
                                           "z_samples", "z_fine", "pdf_inds", "weights0", "raw0", "raw", "near_far")]
 
 
+class TrainRandom(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("t_rand", "u_is", "noise0", "noise")]
+
+
 class PosegenError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"posegen_b200 error {code}: {msg}")
@@ -78,7 +82,7 @@ def load() -> C.CDLL:
     lib.pgn_render_forward.argtypes = [vp, C.POINTER(RenderInputs), C.POINTER(RenderOutputs), vp, C.c_size_t, vp]
     lib.pgn_activation_dump_bytes.argtypes = [i64, i32]
     lib.pgn_activation_dump_bytes.restype = C.c_size_t
-    lib.pgn_render_forward_train.argtypes = [vp, C.POINTER(RenderInputs), C.POINTER(RenderOutputs), vp, vp, vp, C.c_size_t, vp]
+    lib.pgn_render_forward_train.argtypes = [vp, C.POINTER(RenderInputs), C.POINTER(RenderOutputs), vp, vp, C.POINTER(TrainRandom), vp, C.c_size_t, vp]
     lib.pgn_launch_count.argtypes = [vp]
     lib.pgn_launch_count.restype = i64
     lib.pgn_check_device_status.argtypes = [vp]
@@ -86,7 +90,7 @@ def load() -> C.CDLL:
     lib.pgn_encode.argtypes = [vp, C.POINTER(RenderInputs), vp, i32, vp, vp]
     lib.pgn_mlp.argtypes = [vp, C.c_int, vp, i64, vp, i32, vp]
     lib.pgn_composite.argtypes = [vp, C.POINTER(RenderInputs), vp, vp, i32, vp, vp, vp, vp, vp, vp]
-    lib.pgn_composite_backward.argtypes = [vp, C.POINTER(RenderInputs), vp, vp, i32, vp, vp, vp, vp]
+    lib.pgn_composite_backward.argtypes = [vp, C.POINTER(RenderInputs), vp, vp, i32, vp, vp, vp, vp, vp]
     lib.pgn_encode_backward.argtypes = [vp, C.POINTER(RenderInputs), vp, i32, vp, vp, vp]
     lib.pgn_sample_pdf.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp, vp]
     lib.pgn_generate_rays.argtypes = [vp, i32, i32, f32, C.POINTER(f32), i32, i32, i32, i32, vp, vp]

@@ -212,12 +212,15 @@ size_t pgn_activation_dump_bytes(int64_t n_rays, int32_t pass) {
 }
 
 int pgn_render_forward_train(pgn_context* c, const pgn_render_inputs* in, const pgn_render_outputs* out,
-                             void* act_coarse, void* act_fine, void* workspace, size_t workspace_bytes, void* stream_) {
+                             void* act_coarse, void* act_fine, const pgn_train_random* rnd,
+                             void* workspace, size_t workspace_bytes, void* stream_) {
   if (!in || in->precision != PGN_PRECISION_BF16) return fail(PGN_E_INVALID, "pgn_render_forward_train: the bf16 tensor-core path only");
   if (!act_coarse || !act_fine) return fail(PGN_E_INVALID, "pgn_render_forward_train: null activation dump");
   PgnActDump d;
   d.c = (__nv_bfloat16*)act_coarse; d.f = (__nv_bfloat16*)act_fine;
   d.rows_c = pgn_bf16_dump_rows(in->n_rays, PGN_S); d.rows_f = pgn_bf16_dump_rows(in->n_rays, PGN_T);
+  d.t_rand = rnd ? rnd->t_rand : nullptr; d.u_is = rnd ? rnd->u_is : nullptr;
+  d.noise0 = rnd ? rnd->noise0 : nullptr; d.noise = rnd ? rnd->noise : nullptr;
   return render_forward_impl(c, in, out, workspace, workspace_bytes, stream_, &d);
 }
 
@@ -324,13 +327,13 @@ int pgn_encode_backward(pgn_context* c, const pgn_render_inputs* in, const float
 }
 
 int pgn_composite_backward(pgn_context* c, const pgn_render_inputs* in, const float* raw, const float* z, int32_t s,
-                           const float* g_rgb, const float* g_acc, float* d_raw, void* stream) {
+                           const float* g_rgb, const float* g_acc, const float* noise, float* d_raw, void* stream) {
   int rc = check_inputs(c, in, "pgn_composite_backward");
   if (rc) return rc;
   if (!raw || !z || !g_rgb || !d_raw || (s != PGN_S && s != PGN_T)) return fail(PGN_E_INVALID, "pgn_composite_backward: bad argument");
   if (!c->have_sc) return fail(PGN_E_STATE, "pgn_composite_backward: scalars not set");
   PGN_CUDA(cudaSetDevice(c->cfg.device));
-  PGN_CUDA(pgn_launch_composite_backward(make_refs(in), c->d_sc, raw, z, s, g_rgb, g_acc, d_raw, (cudaStream_t)stream));
+  PGN_CUDA(pgn_launch_composite_backward(make_refs(in), c->d_sc, raw, z, s, g_rgb, g_acc, noise, d_raw, (cudaStream_t)stream));
   c->launches++;
   return PGN_OK;
 }

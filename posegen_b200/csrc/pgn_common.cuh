@@ -89,6 +89,15 @@ __device__ __forceinline__ float pgn_coarse_z(float near, float far, float t) {
   return __fadd_rn(__fmul_rn(near, __fsub_rn(1.0f, t)), __fmul_rn(far, t));
 }
 
+// stratified jitter of the coarse samples (training, perturb > 0; ray_utils.py:236-246):
+//   mids = .5 (z[1:] + z[:-1]); upper = [mids, z[-1]]; lower = [z[0], mids]; z = lower + (upper - lower) t_rand
+__device__ __forceinline__ float pgn_coarse_z_jitter(float near, float far, const float* __restrict__ t, int i, float t_rand) {
+  const float zi = pgn_coarse_z(near, far, t[i]);
+  const float lower = i > 0 ? __fmul_rn(0.5f, __fadd_rn(zi, pgn_coarse_z(near, far, t[i - 1]))) : zi;
+  const float upper = i + 1 < PGN_S ? __fmul_rn(0.5f, __fadd_rn(pgn_coarse_z(near, far, t[i + 1]), zi)) : zi;
+  return __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), t_rand));
+}
+
 // ---------------------------------------------------------------------------
 // Joint-frame geometry of one (sample, joint):
 //   pts = o + d*z                                   core/raycasters.py:658
@@ -244,7 +253,9 @@ __device__ __forceinline__ void pgn_composite_warp(const float* __restrict__ raw
 template <int S, bool kFast = false, int CH = 3>       // CH samples per lane: up to 32*CH samples per call
 __device__ __forceinline__ void pgn_composite_segment_warp(const float* __restrict__ raw_seg, const float* __restrict__ z,
                                                            int s0, int s1, float dnorm, float density_scale, float rgb_eps,
-                                                           int lane, float* carry, float* weights_out, float* alpha_out) {
+                                                           int lane, float* carry, float* weights_out, float* alpha_out,
+                                                           const float* __restrict__ noise = nullptr) {
+  // noise (training, nerf.py:176-186): per-sample additive term on raw_sigma / B before the ReLU, indexed by sample
   float a[CH], p[CH];
   float lane_prod = 1.0f;
 #pragma unroll
@@ -254,7 +265,8 @@ __device__ __forceinline__ void pgn_composite_segment_warp(const float* __restri
     if (i < s1) {
       float dist = (i + 1 < S) ? __fsub_rn(z[i + 1], z[i]) : 1e10f;
       dist = __fmul_rn(dist, dnorm);
-      const float sig = fmaxf(kFast ? __fdividef(raw_seg[(i - s0) * 4 + 3], density_scale) : raw_seg[(i - s0) * 4 + 3] / density_scale, 0.0f);
+      const float sig = fmaxf((kFast ? __fdividef(raw_seg[(i - s0) * 4 + 3], density_scale) : raw_seg[(i - s0) * 4 + 3] / density_scale) +
+                              (noise ? noise[i] : 0.0f), 0.0f);
       al = 1.0f - (kFast ? __expf(-__fmul_rn(sig, dist)) : expf(-__fmul_rn(sig, dist)));
     }
     a[c] = al;
@@ -489,6 +501,54 @@ __device__ __forceinline__ void pgn_sample_pdf_draw_warp_fast(const float* __res
       if (lo < hi) { if (z[mid] <= my_sample) lo = mid + 1; else hi = mid; }
     }
     z_sorted[lane + lo] = my_sample;
+  }
+  __syncwarp();
+}
+
+// training variant of the draw (det = False, ray_utils.py:169-170): 16 arbitrary, unsorted u per ray; the merge is
+// a full rank computation over the 80 values (ties: coarse samples first, then importance samples in index order)
+__device__ __forceinline__ void pgn_sample_pdf_draw_warp_rand(const float* __restrict__ z, const float* __restrict__ u_ray, int lane,
+                                                              float* scratch, float* z_samples, float* z_sorted, int* pdf_inds) {
+  float* cdf = scratch;
+  float* bins = scratch + 64;
+  float my_sample = 0.0f;
+  if (lane < PGN_I) {
+    const float u = u_ray[lane];
+    int lo = 0, hi = 63;                                // ind = #{k in [0,63) : cdf[k] <= u}
+#pragma unroll
+    for (int it = 0; it < 6; ++it) {
+      const int mid = (lo + hi) >> 1;
+      if (cdf[mid] <= u) lo = mid + 1; else hi = mid;
+    }
+    const int ind = lo;
+    const int below = max(ind - 1, 0), above = min(ind, 62);
+    const float cdb = cdf[below], cda = cdf[above];
+    float denom = cda - cdb;
+    if (denom < 1e-5f) denom = 1.0f;
+    const float t = __fdividef(u - cdb, denom);
+    my_sample = fmaf(t, bins[above] - bins[below], bins[below]);
+    if (pdf_inds) pdf_inds[lane] = ind;
+    if (z_samples) z_samples[lane] = my_sample;
+  }
+  __syncwarp();
+  float* samp = scratch;
+  if (lane < PGN_I) samp[lane] = my_sample;
+  __syncwarp();
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int i = lane + 32 * h;
+    const float zi = z[i];
+    int r = i;
+#pragma unroll
+    for (int k = 0; k < PGN_I; ++k) r += (samp[k] < zi) ? 1 : 0;
+    z_sorted[r] = zi;
+  }
+  if (lane < PGN_I) {
+    int r = 0;
+    for (int i = 0; i < PGN_S; ++i) r += (z[i] <= my_sample) ? 1 : 0;
+#pragma unroll
+    for (int k = 0; k < PGN_I; ++k) r += (samp[k] < my_sample || (samp[k] == my_sample && k < lane)) ? 1 : 0;
+    z_sorted[r] = my_sample;
   }
   __syncwarp();
 }

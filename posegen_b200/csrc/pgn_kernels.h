@@ -43,6 +43,11 @@ struct PgnActDump {
   __nv_bfloat16* c;     // coarse pass
   __nv_bfloat16* f;     // fine pass
   long long rows_c, rows_f;
+  // training-time randomness, all optional (device pointers, NULL = the deterministic eval sampling):
+  const float* t_rand;   // [n,64] U(0,1): stratified jitter of the coarse samples (perturb > 0)
+  const float* u_is;     // [n,16] U(0,1): importance-sampling quantiles (det = False)
+  const float* noise0;   // [n,64] raw-density noise of the coarse pass, already scaled by raw_noise_std * B
+  const float* noise;    // [n,80] same for the fine pass
 };
 long long pgn_bf16_dump_rows(long long n_rays, int samples_per_ray);
 
@@ -73,7 +78,8 @@ cudaError_t pgn_launch_compose_frame(int H, int W, int x0, int y0, int x1, int y
                                      float bg, float* image, cudaStream_t stream);
 
 cudaError_t pgn_launch_composite_backward(const PgnRayRefs& rays, const PgnScalars* sc_dev, const float* raw, const float* z,
-                                          int s, const float* g_rgb, const float* g_acc, float* d_raw, cudaStream_t stream);
+                                          int s, const float* g_rgb, const float* g_acc, const float* noise, float* d_raw,
+                                          cudaStream_t stream);
 cudaError_t pgn_launch_encode_backward(const PgnRayRefs& rays, const PgnScalars* sc_dev, const float* z, int n_z,
                                        const float* g_enc, float* d_skts, cudaStream_t stream);
 cudaError_t pgn_launch_pose_fk(const float* bones, const float* rest, int n_poses, float ext, float top_ratio, float bot_ratio,

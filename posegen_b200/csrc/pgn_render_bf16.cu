@@ -118,7 +118,8 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 
 __device__ __forceinline__ RowCtx make_row_ctx(const Smem& sm, const PgnScalars& sc, const TileCtx& tc,
-                                               const float* __restrict__ near_far, int slot, int row) {
+                                               const float* __restrict__ near_far, int slot, int row,
+                                               const float* __restrict__ t_rand = nullptr) {
   RowCtx rc;
   const int grow = tc.row0 + row;
   rc.valid = grow < tc.total_rows;
@@ -128,8 +129,9 @@ __device__ __forceinline__ RowCtx make_row_ctx(const Smem& sm, const PgnScalars&
     const int rl = grow / tc.S, s = grow - rl * tc.S;
     const long long ri = tc.ray0 + rl;
     rc.tr = rl - tc.tile_ray0;
-    rc.z = (tc.pass == 0) ? pgn_coarse_z(__ldg(near_far + ri * 2), __ldg(near_far + ri * 2 + 1), sc.t_coarse[s])
-                          : sm.zf[slot][rl][s];
+    if (tc.pass != 0) rc.z = sm.zf[slot][rl][s];
+    else if (t_rand) rc.z = pgn_coarse_z_jitter(__ldg(near_far + ri * 2), __ldg(near_far + ri * 2 + 1), sc.t_coarse, s, __ldg(t_rand + ri * PGN_S + s));
+    else rc.z = pgn_coarse_z(__ldg(near_far + ri * 2), __ldg(near_far + ri * 2 + 1), sc.t_coarse[s]);
   }
   return rc;
 }
@@ -659,15 +661,21 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
               *p = v;
             }
             const float nn = __ldg(near_far + ri * 2), ff = __ldg(near_far + ri * 2 + 1);
-            zc[lane] = pgn_coarse_z(nn, ff, sc.t_coarse[lane]);
-            zc[lane + 32] = pgn_coarse_z(nn, ff, sc.t_coarse[lane + 32]);
+            if (kDump && dump.t_rand) {
+              zc[lane] = pgn_coarse_z_jitter(nn, ff, sc.t_coarse, lane, __ldg(dump.t_rand + ri * PGN_S + lane));
+              zc[lane + 32] = pgn_coarse_z_jitter(nn, ff, sc.t_coarse, lane + 32, __ldg(dump.t_rand + ri * PGN_S + lane + 32));
+            } else {
+              zc[lane] = pgn_coarse_z(nn, ff, sc.t_coarse[lane]);
+              zc[lane + 32] = pgn_coarse_z(nn, ff, sc.t_coarse[lane + 32]);
+            }
             const float d0 = __ldg(rays.ray_batch + ri * 11 + 3), d1 = __ldg(rays.ray_batch + ri * 11 + 4), d2 = __ldg(rays.ray_batch + ri * 11 + 5);
             const float dn = sqrtf(d0 * d0 + d1 * d1 + d2 * d2);
             float* cr = sm.carry[s][rl];
             if (lane < 8) cr[lane] = (lane == 0) ? 1.f : 0.f;
             __syncwarp();
             pgn_composite_segment_warp<PGN_S, true, 2>(rawrows, zc, 0, PGN_S, dn, sc.density_scale, sc.rgb_eps, lane, cr, wts,
-                                              out.alpha0 ? out.alpha0 + ri * PGN_S : nullptr);
+                                                       out.alpha0 ? out.alpha0 + ri * PGN_S : nullptr,
+                                                       (kDump && dump.noise0) ? dump.noise0 + ri * PGN_S : nullptr);
             if (lane == 0) {
               float rgb3[3], disp, acc;
               pgn_composite_finalize(cr, rgb3, &disp, &acc);
@@ -700,7 +708,8 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
             const float dn = sqrtf(d0 * d0 + d1 * d1 + d2 * d2);
             float* cr = sm.carry[s][rl];
             pgn_composite_segment_warp<PGN_T, true, 3>(rawrows, sm.zf[s][rl], s0, s1, dn, sc.density_scale, sc.rgb_eps, lane, cr,
-                                              nullptr, out.alpha ? out.alpha + ri * PGN_T : nullptr);
+                                                       nullptr, out.alpha ? out.alpha + ri * PGN_T : nullptr,
+                                                       (kDump && dump.noise) ? dump.noise + ri * PGN_T : nullptr);
             if (out.raw) for (int i = lane; i < (s1 - s0) * 4; i += 32) out.raw[(ri * PGN_T + s0) * 4 + i] = rawrows[i];
             if (s1 == PGN_T && lane == 0) {
               float rgb3[3], disp, acc;
@@ -722,8 +731,12 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
           if (stage == 2) {
             pgn_sample_pdf_cdf_warp_fast(zc, wts, lane, scr);
           } else {
-            pgn_sample_pdf_draw_warp_fast(zc, sc.u_det, lane, scr, out.z_samples ? out.z_samples + ri * PGN_I : nullptr,
-                                          sm.zf[s][rl], out.pdf_inds ? out.pdf_inds + ri * PGN_I : nullptr);
+            if (kDump && dump.u_is)
+              pgn_sample_pdf_draw_warp_rand(zc, dump.u_is + ri * PGN_I, lane, scr, out.z_samples ? out.z_samples + ri * PGN_I : nullptr,
+                                            sm.zf[s][rl], out.pdf_inds ? out.pdf_inds + ri * PGN_I : nullptr);
+            else
+              pgn_sample_pdf_draw_warp_fast(zc, sc.u_det, lane, scr, out.z_samples ? out.z_samples + ri * PGN_I : nullptr,
+                                            sm.zf[s][rl], out.pdf_inds ? out.pdf_inds + ri * PGN_I : nullptr);
             if (out.z_fine) for (int i = lane; i < PGN_T; i += 32) out.z_fine[ri * PGN_T + i] = sm.zf[s][rl][i];
           }
         }
@@ -781,7 +794,7 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
       if (!kStage && L == 0 && !tables_ready) {      // (normally built ahead, in the shadow of the previous tile's view layer)
         PROF_T0();
         build_tables(tc);
-        rc = make_row_ctx(sm, sc, tc, near_far, s, row);
+        rc = make_row_ctx(sm, sc, tc, near_far, s, row, kDump ? dump.t_rand : nullptr);
         group_bar_sync(s);                 // tables visible to every thread of the group
         if (timed) PROF_ADD(14);
       }
@@ -836,7 +849,7 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
             if (k + 1 < kTiles) make_ctx(i, k + 1, nx); else make_ctx(i + 1, 0, nx);
             group_bar_sync(s);               // every thread is done reading this tile's tables
             build_tables(nx);
-            rc = make_row_ctx(sm, sc, nx, near_far, s, row);
+            rc = make_row_ctx(sm, sc, nx, near_far, s, row, kDump ? dump.t_rand : nullptr);
             group_bar_sync(s);               // tables visible to every thread of the group
             tables_ready = true;
             if (timed) PROF_ADD(14);

@@ -428,7 +428,8 @@ cudaError_t pgn_launch_hmr_input(const float* image, int H, int W, int x0, int y
 template <int S>
 __global__ void pgn_composite_backward_kernel(PgnRayRefs rays, const PgnScalars* __restrict__ scp, const float* __restrict__ raw,
                                               const float* __restrict__ z, const float* __restrict__ g_rgb,
-                                              const float* __restrict__ g_acc, float* __restrict__ d_raw) {
+                                              const float* __restrict__ g_acc, const float* __restrict__ noise,
+                                              float* __restrict__ d_raw) {
   constexpr int CH = (S + 31) / 32;
   const PgnScalars& sc = *scp;
   const int lane = threadIdx.x & 31;
@@ -451,10 +452,11 @@ __global__ void pgn_composite_backward_kernel(PgnRayRefs rays, const PgnScalars*
       if (i < S) {
         float di = (i + 1 < S) ? __fsub_rn(zz[i + 1], zz[i]) : 1e10f;
         di = __fmul_rn(di, dn);
-        const float sig = fmaxf(rw[i * 4 + 3] / sc.density_scale, 0.0f);
+        const float pre = rw[i * 4 + 3] / sc.density_scale + (noise ? noise[r * S + i] : 0.0f);     // nerf.py:165: act(raw / B + noise)
+        const float sig = fmaxf(pre, 0.0f);
         al[c] = 1.0f - expf(-__fmul_rn(sig, di));
         om[c] = __fadd_rn(__fsub_rn(1.0f, al[c]), 1e-10f);
-        dist[c] = di;
+        dist[c] = pre > 0.0f ? di : 0.0f;                  // ReLU mask folded into the distance factor
         s0[c] = 1.0f / (1.0f + expf(-rw[i * 4 + 0])); s1[c] = 1.0f / (1.0f + expf(-rw[i * 4 + 1])); s2[c] = 1.0f / (1.0f + expf(-rw[i * 4 + 2]));
         c0[c] = s0[c] * keps - sc.rgb_eps; c1[c] = s1[c] * keps - sc.rgb_eps; c2[c] = s2[c] * keps - sc.rgb_eps;
         lane_prod *= om[c];
@@ -496,25 +498,25 @@ __global__ void pgn_composite_backward_kernel(PgnRayRefs rays, const PgnScalars*
       if (i < S) {
         const float after = total - (before + pre[c]);                 // sum_{j>i} w_j G_j
         const float dalpha = T[c] * G[c] - after / om[c];
-        const float rs = rw[i * 4 + 3];
         const float dsig = dalpha * dist[c] * (1.0f - al[c]);
         float* o = d_raw + (r * S + i) * 4;
         o[0] = w[c] * gr * keps * s0[c] * (1.0f - s0[c]);
         o[1] = w[c] * gg * keps * s1[c] * (1.0f - s1[c]);
         o[2] = w[c] * gb * keps * s2[c] * (1.0f - s2[c]);
-        o[3] = rs > 0.0f ? dsig / sc.density_scale : 0.0f;
+        o[3] = dsig / sc.density_scale;
       }
     }
   }
 }
 
 cudaError_t pgn_launch_composite_backward(const PgnRayRefs& rays, const PgnScalars* sc_dev, const float* raw, const float* z,
-                                          int s, const float* g_rgb, const float* g_acc, float* d_raw, cudaStream_t stream) {
+                                          int s, const float* g_rgb, const float* g_acc, const float* noise, float* d_raw,
+                                          cudaStream_t stream) {
   if (rays.n_rays == 0) return cudaSuccess;
   const int block = 256;
   const long long grid = min((rays.n_rays * 32 + block - 1) / block, (long long)148 * 8);
-  if (s == PGN_S) pgn_composite_backward_kernel<PGN_S><<<(unsigned)grid, block, 0, stream>>>(rays, sc_dev, raw, z, g_rgb, g_acc, d_raw);
-  else if (s == PGN_T) pgn_composite_backward_kernel<PGN_T><<<(unsigned)grid, block, 0, stream>>>(rays, sc_dev, raw, z, g_rgb, g_acc, d_raw);
+  if (s == PGN_S) pgn_composite_backward_kernel<PGN_S><<<(unsigned)grid, block, 0, stream>>>(rays, sc_dev, raw, z, g_rgb, g_acc, noise, d_raw);
+  else if (s == PGN_T) pgn_composite_backward_kernel<PGN_T><<<(unsigned)grid, block, 0, stream>>>(rays, sc_dev, raw, z, g_rgb, g_acc, noise, d_raw);
   else return cudaErrorInvalidValue;
   return cudaGetLastError();
 }

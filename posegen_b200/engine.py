@@ -178,10 +178,12 @@ class Engine:
                                                    self._stream()))
         return ret
 
-    def render_train(self, ray_batch, skts, cyls, pose_idx=None, nanfill_chunk=0):
+    def render_train(self, ray_batch, skts, cyls, pose_idx=None, nanfill_chunk=0, rand=None):
         """pgn_render_forward_train: the fused bf16 forward + per-layer activation dump for the weight gradients.
         Returns (outputs incl. the taps the backward needs, {"c": dump, "f": dump}); dump[p] is a bf16 tensor
-        [272 runs, rows, 8] (layers 0-7: 32 runs each, view layer: 16), rows in (ray, sample) order."""
+        [272 runs, rows, 8] (layers 0-7: 32 runs each, view layer: 16), rows in (ray, sample) order.
+        rand: optional dict of CUDA fp32 tensors t_rand [n,64], u_is [n,16], noise0 [n,64], noise [n,80] (training-time
+        randomness drawn by the caller; missing keys = deterministic)."""
         inp, keep = self._inputs(ray_batch, skts, cyls, pose_idx, nanfill_chunk, "bf16")
         n, dev = inp.n_rays, ray_batch.device
         f = lambda *sh: torch.empty(sh, dtype=torch.float32, device=dev)  # noqa: E731
@@ -199,7 +201,18 @@ class Engine:
         if self._workspace is None or self._workspace.numel() < need or self._workspace.device != dev:
             self._workspace = torch.empty(max(need, 1 << 20), dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
+            rnd = None
+            if rand:
+                rnd = _lib.TrainRandom()
+                for k, cols in (("t_rand", S), ("u_is", I), ("noise0", S), ("noise", T)):
+                    v = rand.get(k)
+                    if v is not None:
+                        _check_f32_cuda(v, k)
+                        if tuple(v.shape) != (n, cols) or not v.is_contiguous():
+                            raise ValueError(f"rand[{k!r}] must be a contiguous [{n},{cols}] tensor")
+                        setattr(rnd, k, v.data_ptr())
             _lib.check(self.lib.pgn_render_forward_train(self.handle, C.byref(inp), C.byref(out), _ptr(acts["c"]), _ptr(acts["f"]),
+                                                         C.byref(rnd) if rnd is not None else None,
                                                          C.c_void_p(self._workspace.data_ptr()), self._workspace.numel(),
                                                          self._stream()))
         return ret, acts
@@ -237,12 +250,13 @@ class Engine:
                                           _ptr(ret["weights"]), _ptr(ret["alpha"]), self._stream()))
         return ret
 
-    def composite_backward(self, ray_batch, skts, cyls, raw, z, g_rgb, g_acc=None):
+    def composite_backward(self, ray_batch, skts, cyls, raw, z, g_rgb, g_acc=None, noise=None):
         """dL/d raw [n,s,4] of raw2outputs given dL/d rgb_map [n,3] and dL/d acc_map [n]."""
         inp, keep = self._inputs(ray_batch, skts, cyls)
         d_raw = torch.empty_like(raw, memory_format=torch.contiguous_format)
         _lib.check(self.lib.pgn_composite_backward(self.handle, C.byref(inp), _ptr(raw.contiguous()), _ptr(z.contiguous()), z.shape[1],
                                                    _ptr(g_rgb.contiguous()), _ptr(g_acc.contiguous()) if g_acc is not None else None,
+                                                   _ptr(noise.contiguous()) if noise is not None else None,
                                                    _ptr(d_raw), self._stream()))
         return d_raw
 

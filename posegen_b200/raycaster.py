@@ -223,11 +223,12 @@ class RayCaster(nn.Module):
                     network_fine=None, raw_noise_std=0., ray_noise_std=0., verbose=False, ext_scale=0.001,
                     pytest=False, preproc_kwargs=None, nerf_type="nerf", use_viewdirs=True,
                     precision=None, nanfill_chunk=None, **_ignored):
-        if self.training and (perturb or raw_noise_std or ray_noise_std):
-            raise NotImplementedError("training-time sampling noise (perturb / raw_noise_std / ray_noise_std) is not "
-                                      "implemented yet; train with perturb=0, raw_noise_std=0 or call .eval() for rendering")
-        if perturb or raw_noise_std or ray_noise_std or lindisp:
-            raise NotImplementedError("perturb / raw_noise_std / ray_noise_std / lindisp must be 0/False on the render path")
+        train_step = self.training and torch.is_grad_enabled()
+        if ray_noise_std or lindisp:
+            raise NotImplementedError("ray_noise_std / lindisp are not part of the surreal.txt path")
+        if (perturb or raw_noise_std) and not train_step:
+            raise NotImplementedError("perturb / raw_noise_std (training-time sampling noise) need .train() and grad mode; "
+                                      "the render path is deterministic (render_kwargs_test, core/raycasters.py:176-178)")
         if N_samples != 64 or N_importance != 16:
             raise NotImplementedError("only N_samples=64, N_importance=16 (surreal.txt) is implemented")
         if cams is not None:
@@ -237,12 +238,13 @@ class RayCaster(nn.Module):
         if not ray_batch.is_cuda:
             raise RuntimeError("posegen_b200.RayCaster needs CUDA tensors (the reference moves each chunk with "
                                ".to('cuda') in batchify_rays, core/trainer.py:70-74); there is no CPU fallback")
-        if self.training and torch.is_grad_enabled():
+        if train_step:
             # training step (core/trainer.py:232-275): differentiable w.r.t. the two MLPs (posegen_b200/train.py)
             from .train import render_train
             if (precision or self.precision) != "bf16":
                 raise NotImplementedError("the training step runs on the bf16 tensor-core path only")
-            return render_train(self, ray_batch, skts.to(ray_batch.device), cyls.to(ray_batch.device), nanfill_chunk)
+            return render_train(self, ray_batch, skts.to(ray_batch.device), cyls.to(ray_batch.device), nanfill_chunk,
+                                perturb=float(perturb), raw_noise_std=float(raw_noise_std), rand=_ignored.get("train_random"))
         eng = self.engine(ray_batch.device)
         n = ray_batch.shape[0]
         ret = eng.render(ray_batch.float(), skts.to(ray_batch.device).float(), cyls.to(ray_batch.device).float(),

@@ -9,8 +9,10 @@ pose generator / pose optimisation, configs[4]) dL/d(network input) is formed by
 `pgn_encode_backward` (hand-written) turns it into dL/d skts.  No gradient flows through the sample positions
 (the importance samples are detached in the reference, core/utils/ray_utils.py:286).
 
-Sampling is the eval-style deterministic one (perturb = 0, raw_noise_std = 0: the reference's parity setting,
-SURVEY.md §8d config 4); stratified jitter and density noise are not implemented yet.
+Sampling: deterministic (perturb = 0, raw_noise_std = 0: the reference's parity setting)
+or the reference's training-time randomness (perturb > 0: stratified jitter of the coarse samples and random
+importance quantiles, ray_utils.py:169-170,236-246; raw_noise_std > 0: density noise, nerf.py:176-186).  The
+random numbers are drawn here with torch's CUDA generator and handed to the kernel as explicit arrays.
 
 Multi-GPU: data-parallel over rays; `allreduce_gradients` is one NCCL all-reduce of the flattened 1.73 M-element
 gradient bucket.
@@ -106,10 +108,10 @@ def mlp_backward(params: Dict[str, torch.Tensor], enc: torch.Tensor, acts: torch
 
 class _RenderTrainFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, rc, ray_batch, skts, cyls, nanfill_chunk, *params):
+    def forward(ctx, rc, ray_batch, skts, cyls, nanfill_chunk, rand, *params):
         eng = rc.engine(ray_batch.device)
-        ret, acts = eng.render_train(ray_batch, skts, cyls, nanfill_chunk=nanfill_chunk)
-        ctx.rc, ctx.acts = rc, acts
+        ret, acts = eng.render_train(ray_batch, skts, cyls, nanfill_chunk=nanfill_chunk, rand=rand)
+        ctx.rc, ctx.acts, ctx.rand = rc, acts, (rand or {})
         ctx.save_for_backward(ray_batch, skts, cyls, ret["raw0"], ret["raw"], ret["z_fine"], ret["near_far"])
         ctx.mark_non_differentiable(ret["disp_map"], ret["disp0"])
         return ret["rgb_map"], ret["acc_map"], ret["rgb0"], ret["acc0"], ret["disp_map"], ret["disp0"]
@@ -123,14 +125,19 @@ class _RenderTrainFn(torch.autograd.Function):
         zero3, zero1 = torch.zeros((n, 3), device=rb.device), torch.zeros(n, device=rb.device)
         t = torch.linspace(0., 1., S, device=rb.device)                       # sample_from_lineseg, ray_utils.py:204-251
         z_c = near_far[:, :1] * (1. - t) + near_far[:, 1:2] * t
+        rand = ctx.rand
+        if rand.get("t_rand") is not None:                                    # stratified jitter, ray_utils.py:236-246
+            mids = .5 * (z_c[:, 1:] + z_c[:, :-1])
+            upper, lower = torch.cat([mids, z_c[:, -1:]], -1), torch.cat([z_c[:, :1], mids], -1)
+            z_c = lower + (upper - lower) * rand["t_rand"]
         grads: List[torch.Tensor] = []
         want_sk = ctx.needs_input_grad[2]
         d_skts = None
-        for net, acts, z, raw_p, gr, ga in ((rc.network, ctx.acts["c"], z_c, raw0, g_rgb0, g_acc0),
-                                            (rc.network_fine, ctx.acts["f"], z_fine, raw, g_rgb, g_acc)):
+        for net, acts, z, raw_p, gr, ga, nz in ((rc.network, ctx.acts["c"], z_c, raw0, g_rgb0, g_acc0, rand.get("noise0")),
+                                                (rc.network_fine, ctx.acts["f"], z_fine, raw, g_rgb, g_acc, rand.get("noise"))):
             gr = zero3 if gr is None else gr.contiguous().float()
             ga = zero1 if ga is None else ga.contiguous().float()
-            d_raw = eng.composite_backward(rb, sk, cy, raw_p, z.contiguous(), gr, ga)
+            d_raw = eng.composite_backward(rb, sk, cy, raw_p, z.contiguous(), gr, ga, noise=nz)
             enc = eng.encode(rb, sk, cy, z.contiguous())
             pd = dict(net.named_parameters())
             gd = mlp_backward(pd, enc.reshape(-1, 1080), acts, d_raw.reshape(-1, 4), want_input_grad=want_sk)
@@ -141,16 +148,31 @@ class _RenderTrainFn(torch.autograd.Function):
         ctx.acts = None
         if want_sk and sk.dim() == 3:
             d_skts = d_skts.sum(0)                     # one pose shared by every ray of the batch
-        return (None, None, d_skts, None, None) + tuple(grads)
+        return (None, None, d_skts, None, None, None) + tuple(grads)
 
 
-def render_train(rc, ray_batch, skts, cyls, nanfill_chunk=None) -> Dict[str, torch.Tensor]:
+def draw_train_random(n: int, device, perturb: float = 0., raw_noise_std: float = 0., density_scale: float = 1.0) -> Dict[str, torch.Tensor]:
+    """The random numbers one training forward consumes (what the reference draws with torch.rand / torch.randn)."""
+    rand: Dict[str, torch.Tensor] = {}
+    if perturb > 0.:
+        rand["t_rand"] = torch.rand((n, S), device=device)
+        rand["u_is"] = torch.rand((n, 16), device=device)
+    if raw_noise_std > 0.:
+        rand["noise0"] = torch.randn((n, S), device=device) * (raw_noise_std * density_scale)
+        rand["noise"] = torch.randn((n, T), device=device) * (raw_noise_std * density_scale)
+    return rand
+
+
+def render_train(rc, ray_batch, skts, cyls, nanfill_chunk=None, perturb: float = 0., raw_noise_std: float = 0.,
+                 rand: Dict[str, torch.Tensor] | None = None) -> Dict[str, torch.Tensor]:
     """Differentiable (w.r.t. the two MLPs' parameters and `skts`) render of a ray batch: the train-mode body of
     RayCaster.forward.  Returns the reference's dict (core/raycasters.py:711-724) without alpha/alpha0."""
     params = [dict(net.named_parameters())[k] for net in (rc.network, rc.network_fine) for k in PARAM_ORDER]
     n = ray_batch.shape[0]
+    if rand is None:
+        rand = draw_train_random(n, ray_batch.device, perturb, raw_noise_std, float(rc.network.density_scale))
     out = _RenderTrainFn.apply(rc, ray_batch.float().contiguous(), skts if skts.dtype == torch.float32 else skts.float(), cyls.float(),
-                               n if nanfill_chunk is None else nanfill_chunk, *params)
+                               n if nanfill_chunk is None else nanfill_chunk, rand or None, *params)
     return {"rgb_map": out[0], "acc_map": out[1], "rgb0": out[2], "acc0": out[3], "disp_map": out[4], "disp0": out[5],
             "alpha": None, "alpha0": None}
 

@@ -13,19 +13,20 @@ from posegen_b200.train import PARAM_ORDER, allreduce_gradients
 pytestmark = pytest.mark.gpu
 
 
-def _oracle_loss(rb, sk, cy, nets, emb, tgt, bg=1.0):
+def _oracle_loss(rb, sk, cy, nets, emb, tgt, bg=1.0, rand=None):
     """render_rays with the reference's detach of the importance samples (core/utils/ray_utils.py:286) and the
     trainer's loss: MSE(rgb_map + (1 - acc) bg, tgt) + MSE(rgb0 + (1 - acc0) bg, tgt)  (core/trainer.py:355-370)."""
     rays_o, rays_d = rb[:, 0:3], rb[:, 3:6]
     near, far = orc.near_far_in_cylinder(rays_o, rays_d, cy, rb[:, 6:7], rb[:, 7:8])
-    z = orc.coarse_z_vals(near, far, 64)
+    rand = rand or {}
+    z = orc.coarse_z_vals(near, far, 64, t_rand=rand.get("t_rand"))
     enc = orc.encode(rays_o[:, None] + rays_d[:, None] * z[:, :, None], rays_d, sk, emb)
     raw0 = orc.nerf_forward(enc.reshape(-1, 1080), nets[0]).reshape(-1, 64, 4)
-    r0 = orc.raw2outputs(raw0, z, rays_d)
-    z_all, _, _, _, _ = orc.importance_z_vals(z, r0["weights"].detach(), 16)
+    r0 = orc.raw2outputs(raw0, z, rays_d, noise=rand.get("noise0"))
+    z_all, _, _, _, _ = orc.importance_z_vals(z, r0["weights"].detach(), 16, u=rand.get("u_is"))
     enc_f = orc.encode(rays_o[:, None] + rays_d[:, None] * z_all[:, :, None], rays_d, sk, emb)
     raw = orc.nerf_forward(enc_f.reshape(-1, 1080), nets[1]).reshape(-1, 80, 4)
-    r = orc.raw2outputs(raw, z_all, rays_d)
+    r = orc.raw2outputs(raw, z_all, rays_d, noise=rand.get("noise"))
     loss = ((r["rgb_map"] + (1 - r["acc_map"][:, None]) * bg - tgt) ** 2).mean() + \
         ((r0["rgb_map"] + (1 - r0["acc_map"][:, None]) * bg - tgt) ** 2).mean()
     return loss, r, r0
@@ -140,3 +141,52 @@ def test_pose_gradient_matches_oracle_autograd(engine, train_case):
     loss = ((ret["rgb_map"] + (1 - ret["acc_map"][:, None]) - t) ** 2).mean() + ((ret["rgb0"] + (1 - ret["acc0"][:, None]) - t) ** 2).mean()
     loss.backward()
     assert float((sk1.grad.cpu().double() - gr.sum(0)).norm() / gr.sum(0).norm()) <= 0.1
+
+
+def test_training_step_with_sampling_noise_matches_oracle(engine, train_case):
+    """The reference's training-time randomness (perturb = 1: stratified jitter + random importance quantiles;
+    raw_noise_std: density noise) with the SAME random numbers fed to the oracle and to the kernel."""
+    frame, ckpt, rb, tgt = train_case
+    n = 1024
+    dev = torch.device("cuda")
+    g = torch.Generator().manual_seed(123)
+    rand = {"t_rand": torch.rand((n, 64), generator=g), "u_is": torch.rand((n, 16), generator=g),
+            "noise0": torch.randn((n, 64), generator=g) * 0.3, "noise": torch.randn((n, 80), generator=g) * 0.3}
+    nets, emb = orc.nets_from_ckpt(ckpt), orc.embed_params_from_ckpt(ckpt)
+    for net in nets:
+        for v in net.values():
+            v.requires_grad_(True)
+    sk = torch.as_tensor(frame.pose.skts)[None].expand(n, -1, -1, -1)
+    cy = torch.as_tensor(frame.pose.cyl)[None].expand(n, -1)
+    loss_ref, r_ref, r0_ref = _oracle_loss(torch.as_tensor(rb[:n]), sk, cy, nets, emb, torch.as_tensor(tgt[:n]), rand=rand)
+    loss_ref.backward()
+    rc = raycaster_from_checkpoint(ckpt, device="cuda", precision="bf16")
+    rc.train()
+    ret = rc(torch.as_tensor(rb[:n], device=dev), N_samples=64, N_importance=16, kp_batch=None, skts=sk.to(dev).contiguous(),
+             cyls=cy.to(dev).contiguous(), bones=None, cams=None, perturb=1.0, raw_noise_std=1.0,
+             train_random={k: v.to(dev).contiguous() for k, v in rand.items()})
+    t = torch.as_tensor(tgt[:n], device=dev)
+    loss = ((ret["rgb_map"] + (1 - ret["acc_map"][:, None]) - t) ** 2).mean() + ((ret["rgb0"] + (1 - ret["acc0"][:, None]) - t) ** 2).mean()
+    loss.backward()
+    torch.cuda.synchronize()
+    engine.check_status()
+    # forward: the rays whose last (delta = 1e10) sample sits on the ReLU edge can flip between the bf16 and fp32 nets
+    for k, ref in (("rgb0", r0_ref["rgb_map"]), ("acc0", r0_ref["acc_map"]), ("rgb_map", r_ref["rgb_map"]), ("acc_map", r_ref["acc_map"])):
+        err = (ret[k].detach().cpu() - ref.detach()).abs()
+        err = err.reshape(n, -1).max(1).values
+        assert float((err <= 2e-2).float().mean()) >= 0.97, k
+    flat, flat_ref = [], []
+    for net, ref in ((rc.network, nets[0]), (rc.network_fine, nets[1])):
+        pd = dict(net.named_parameters())
+        for k in PARAM_ORDER:
+            flat.append(pd[k].grad.detach().cpu().double().reshape(-1)); flat_ref.append(ref[k].grad.double().reshape(-1))
+    a, b = torch.cat(flat), torch.cat(flat_ref)
+    assert torch.isfinite(a).all()
+    cos = float((a @ b) / (a.norm() * b.norm()))
+    assert cos >= 0.99, cos
+    # without explicit numbers the drop-in draws its own: two calls differ, the result is finite
+    r1 = rc(torch.as_tensor(rb[:256], device=dev), N_samples=64, N_importance=16, kp_batch=None, skts=sk[:256].to(dev).contiguous(),
+            cyls=cy[:256].to(dev).contiguous(), perturb=1.0, raw_noise_std=1.0)
+    r2 = rc(torch.as_tensor(rb[:256], device=dev), N_samples=64, N_importance=16, kp_batch=None, skts=sk[:256].to(dev).contiguous(),
+            cyls=cy[:256].to(dev).contiguous(), perturb=1.0, raw_noise_std=1.0)
+    assert torch.isfinite(r1["rgb_map"]).all() and not torch.equal(r1["rgb_map"], r2["rgb_map"])

@@ -1,8 +1,9 @@
 #!/usr/bin/env python
 """Training-step benchmark (BASELINE.json configs[3] / SURVEY.md §8d config 4): 3072-ray batches drawn from 256
 synthetic poses x 12 rays (per-ray skts, like configs/h36m/h36m_prot2.txt:34-35), forward + backward through
-posegen_b200.RayCaster in train mode, one NCCL all-reduce of the gradients, Adam step.  Eval-style sampling
-(perturb = 0, raw_noise_std = 0: the parity setting).  Auxiliary to bench.py; prints one JSON line on rank 0.
+posegen_b200.RayCaster in train mode, one NCCL all-reduce of the gradients, Adam step, with the config's
+training-time randomness (perturb = 1, raw_noise_std = 1, configs/surreal/surreal.txt; `--deterministic` for the
+parity setting).  Auxiliary to bench.py; prints one JSON line on rank 0.
 
     python tools/train_step_bench.py [--steps 20] [--cpu-baseline]
     python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/train_step_bench.py
@@ -39,6 +40,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--cpu-baseline", action="store_true")
+    ap.add_argument("--deterministic", action="store_true", help="perturb = 0, raw_noise_std = 0")
     a = ap.parse_args()
     rank, world, local = pdist.env_rank_world()
     pdist.init_process_group("nccl" if world > 1 else None)
@@ -55,7 +57,8 @@ def main():
 
     def step():
         opt.zero_grad(set_to_none=True)
-        ret = rc(rbt, N_samples=64, N_importance=16, kp_batch=None, skts=skt, cyls=cyt, bones=None, cams=None, perturb=0., raw_noise_std=0.)
+        ret = rc(rbt, N_samples=64, N_importance=16, kp_batch=None, skts=skt, cyls=cyt, bones=None, cams=None,
+                 perturb=0. if a.deterministic else 1., raw_noise_std=0. if a.deterministic else 1.)
         loss = ((ret["rgb_map"] + (1 - ret["acc_map"][:, None]) - tgt) ** 2).mean() + ((ret["rgb0"] + (1 - ret["acc0"][:, None]) - tgt) ** 2).mean()
         loss.backward()
         allreduce_gradients(rc.parameters())
@@ -76,7 +79,8 @@ def main():
     ms = pdist.max_over_ranks(e0.elapsed_time(e1), dev) / a.steps
     line = {"metric": "train_steps_per_sec", "value": 1e3 / ms, "ms_per_step": ms, "n_gpus": world, "rays_per_step": n * world,
             "rays_per_sec": n * world / ms * 1e3, "final_loss": float(loss.detach()),
-            "config": "3072 rays/GPU from 256 poses x 12 rays, coarse+fine, fwd+bwd+allreduce+Adam, perturb=0, raw_noise_std=0, bf16 tensor-core forward"}
+            "config": "3072 rays/GPU from 256 poses x 12 rays, coarse+fine, fwd+bwd+allreduce+Adam, "
+                      + ("perturb=0, raw_noise_std=0" if a.deterministic else "perturb=1, raw_noise_std=1") + ", bf16 tensor-core forward"}
     if a.cpu_baseline and rank == 0:
         from oracle import render_oracle as orc
         torch.set_num_threads(os.cpu_count() or 1)
