@@ -183,3 +183,20 @@ def test_mlp_backward_matches_autograd_on_cpu():
     assert float((a - b).norm() / b.norm()) <= 2e-2                      # bf16 activations / deltas / weights
     ge, gr = got["_g_enc"].double(), enc.grad.double()
     assert float((ge - gr).norm() / gr.norm()) <= 2e-2
+
+
+def test_torch_fk_matches_numpy_helpers_and_is_differentiable():
+    import numpy as np
+    import torch
+    from posegen_b200 import fk, synthetic as syn
+    rng = np.random.RandomState(1)
+    bones = (rng.randn(5, 24, 3) * 0.3).astype(np.float64)
+    rest = (syn.SMPL_REST_POSE * syn.BODY_SCALE).astype(np.float64)
+    b = torch.tensor(bones, requires_grad=True)
+    skts, kps = fk.smpl_skts(b, torch.tensor(rest))
+    ref = np.stack([syn.smpl_local_to_world(x, rest) for x in bones])
+    assert np.abs(skts.detach().numpy() - syn.rigid_inverse(ref)).max() <= 1e-10
+    assert np.abs(kps.detach().numpy() - ref[:, :, :3, 3]).max() <= 1e-10
+    (skts[..., :3, :] ** 2).sum().backward()
+    assert torch.isfinite(b.grad).all() and float(b.grad.abs().max()) > 0
+    assert torch.autograd.gradcheck(lambda x: fk.smpl_skts(x, torch.tensor(rest))[0][..., :3, :], (b[:1].detach().requires_grad_(True),), atol=1e-6)
