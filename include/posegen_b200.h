@@ -160,10 +160,9 @@ PGN_API int  pgn_render_forward(pgn_context* ctx, const pgn_render_inputs* in,
 
 /* Training-step forward (reference core/trainer.py:232-275, eval-style sampling: perturb = 0, no noise): the same
  * fused bf16 pipeline as pgn_render_forward that additionally stores the post-ReLU activations of every MLP layer
- * (bf16) so that the weight gradients can be formed by plain GEMMs.  Per pass the dump is laid out
- * [layer 0..8][run][row][8]: run = 8 consecutive columns, layers 0-7 (pts_linears) have 32 runs, layer 8
- * (views_linears.0, 128 columns) has 16 and starts 8*32 runs in; rows are samples in (ray, sample) order, padded
- * to pgn_activation_dump_bytes(n, pass) / 4352 rows.  act_coarse / act_fine: device buffers of
+ * (bf16) so that the weight gradients can be formed by plain GEMMs.  Per pass the dump is row-major per layer:
+ * layers 0-7 (pts_linears) [rows,256] each, then layer 8 (views_linears.0) [rows,128]; rows are samples in
+ * (ray, sample) order, padded to rows = pgn_activation_dump_bytes(n, pass) / 4352.  act_coarse / act_fine: device buffers of
  * pgn_activation_dump_bytes(n_rays, 0 / 1) bytes.  Request out->raw0 / raw / z_fine / near_far for the backward.
  * rnd (may be NULL = deterministic eval sampling) carries the training-time randomness as explicit device arrays so
  * that a run is reproducible and checkable: the caller draws them with its own generator. */
@@ -197,6 +196,23 @@ PGN_API int  pgn_near_far(pgn_context* ctx, const pgn_render_inputs* in, float* 
  * ([0,360) v_emb k*24+j | [360,432) r j*3+c | [432,1080) d_emb k*72+j*3+c). */
 PGN_API int  pgn_encode(pgn_context* ctx, const pgn_render_inputs* in, const float* z, int32_t n_z,
                 float* enc, void* stream);
+
+/* the same encoding rounded to bf16, [n, n_z, 1080] row-major: the operand the weight-gradient GEMMs of the training
+ * step read (enc: device bf16 buffer of n * n_z * 1080 * 2 bytes). */
+PGN_API int  pgn_encode_bf16(pgn_context* ctx, const pgn_render_inputs* in, const float* z, int32_t n_z,
+                             void* enc, void* stream);
+
+/* One fused pass over a layer's delta matrix in the MLP backward of the training step (what autograd does with
+ * threshold_backward + sum + an outer product + a skinny GEMM; core/networks/nerf.py:94-148):
+ *   dh[m, n_cols] (bf16, in/out)  <-  [act > 0] * ((has_input ? dh : 0) + rs @ wr)
+ *   colsum[n_cols]                <-  column sums of the new dh            (bias gradient of the layer)
+ *   wsum[nrs, n_cols]             <-  rs^T @ act                           (weight gradient of the head reading act)
+ * act: bf16 [m, n_cols] post-ReLU activations of the layer (NULL = no mask); rs: fp32 per-row head deltas, row r at
+ * rs + r * rs_stride, nrs values (0: no head; 1: alpha_linear on h7; 3: rgb_linear on the view layer);
+ * wr: fp32 [nrs, n_cols] head weights; wsum may be NULL.  n_cols is 256 (nrs 0|1) or 128 (nrs 0|3). */
+PGN_API int  pgn_mlp_delta(pgn_context* ctx, void* dh, int32_t has_input, const void* act, int64_t m, int32_t n_cols,
+                           const float* rs, int32_t rs_stride, int32_t nrs, const float* wr,
+                           float* colsum, float* wsum, void* stream);
 
 /* NeRF.forward (core/networks/nerf.py:133-148) on explicit encodings:
  * enc [m,1080] -> raw [m,4].  precision selects the MLP engine. */

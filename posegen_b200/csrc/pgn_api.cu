@@ -289,6 +289,30 @@ int pgn_encode(pgn_context* c, const pgn_render_inputs* in, const float* z, int3
   return PGN_OK;
 }
 
+int pgn_encode_bf16(pgn_context* c, const pgn_render_inputs* in, const float* z, int32_t n_z, void* enc, void* stream) {
+  int rc = check_inputs(c, in, "pgn_encode_bf16");
+  if (rc) return rc;
+  if (!z || !enc || n_z <= 0) return fail(PGN_E_INVALID, "pgn_encode_bf16: bad argument");
+  if (!c->have_sc) return fail(PGN_E_STATE, "pgn_encode_bf16: scalars not set");
+  PGN_CUDA(cudaSetDevice(c->cfg.device));
+  PGN_CUDA(pgn_launch_encode_bf16(make_refs(in), c->d_sc, z, n_z, reinterpret_cast<__nv_bfloat16*>(enc), (cudaStream_t)stream));
+  c->launches++;
+  return PGN_OK;
+}
+
+int pgn_mlp_delta(pgn_context* c, void* dh, int32_t has_input, const void* act, int64_t m, int32_t n_cols, const float* rs,
+                  int32_t rs_stride, int32_t nrs, const float* wr, float* colsum, float* wsum, void* stream) {
+  if (!c || !dh || !colsum || m < 0) return fail(PGN_E_INVALID, "pgn_mlp_delta: bad argument");
+  if (!((n_cols == 256 && (nrs == 0 || nrs == 1)) || (n_cols == 128 && (nrs == 0 || nrs == 3))))
+    return fail(PGN_E_INVALID, "pgn_mlp_delta: supported shapes are 256 columns with 0/1 head rows, 128 columns with 0/3");
+  if (nrs > 0 && (!rs || !wr || rs_stride < nrs)) return fail(PGN_E_INVALID, "pgn_mlp_delta: head deltas / weights missing");
+  if (!has_input && nrs == 0) return fail(PGN_E_INVALID, "pgn_mlp_delta: nothing to do");
+  PGN_CUDA(cudaSetDevice(c->cfg.device));
+  PGN_CUDA(pgn_launch_mlp_delta(dh, has_input, act, m, n_cols, rs, rs_stride, nrs, wr, colsum, wsum, c->num_sms, (cudaStream_t)stream));
+  c->launches++;
+  return PGN_OK;
+}
+
 int pgn_mlp(pgn_context* c, int net_id, const float* enc, int64_t m, float* raw, int32_t precision, void* stream) {
   if (!c || !enc || !raw || net_id < 0 || net_id > 1 || m < 0) return fail(PGN_E_INVALID, "pgn_mlp: bad argument");
   if (!c->have_w[net_id]) return fail(PGN_E_STATE, "pgn_mlp: weights not uploaded");

@@ -37,8 +37,8 @@ struct PgnBf16Net {
 };
 
 // Training forward: post-ReLU activations of the 8 trunk layers (256 columns) and of the view layer (128), bf16,
-// per pass laid out [layer 0..8][run][row][8] (run = 8 consecutive columns; layers 0-7 have 32 runs, layer 8 has 16
-// and starts at layer offset 8 * 32 runs), rows in (ray, sample) order, pgn_bf16_dump_rows() rows per pass.
+// per pass laid out row-major per layer: layers 0-7 [rows,256] each, then layer 8 [rows,128]; rows in (ray, sample)
+// order, pgn_bf16_dump_rows() rows per pass.
 struct PgnActDump {
   __nv_bfloat16* c;     // coarse pass
   __nv_bfloat16* f;     // fine pass
@@ -82,6 +82,10 @@ cudaError_t pgn_launch_composite_backward(const PgnRayRefs& rays, const PgnScala
                                           cudaStream_t stream);
 cudaError_t pgn_launch_encode_backward(const PgnRayRefs& rays, const PgnScalars* sc_dev, const float* z, int n_z,
                                        const float* g_enc, float* d_skts, cudaStream_t stream);
+cudaError_t pgn_launch_encode_bf16(const PgnRayRefs& rays, const PgnScalars* sc_dev, const float* z, int n_z,
+                                   __nv_bfloat16* enc, cudaStream_t stream);
+cudaError_t pgn_launch_mlp_delta(void* dh, int has_in, const void* act, long long m, int C, const float* rs, int rs_stride,
+                                 int nrs, const float* wr, float* colsum, float* wsum, int num_sms, cudaStream_t stream);
 cudaError_t pgn_launch_pose_fk(const float* bones, const float* rest, int n_poses, float ext, float top_ratio, float bot_ratio,
                                float* skts, float* kps, float* cyls, float* l2ws, cudaStream_t stream);
 cudaError_t pgn_launch_hmr_input(const float* image, int H, int W, int x0, int y0, int x1, int y1, int R,

@@ -244,6 +244,13 @@ __device__ __forceinline__ void encode_d_store(uint32_t stg, int row, int half, 
   for (int r = 0; r < 4; ++r) sts128(base + r * kRunBytes, packed[4 * r], packed[4 * r + 1], packed[4 * r + 2], packed[4 * r + 3]);
 }
 
+// 256-bit global store (sm_100: STG.E.256): one full sector per thread, 32-byte aligned address
+__device__ __forceinline__ void stg256(void* p, const uint32_t (&v)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]),
+               "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+
 // ------------------------------------------------------------------ epilogue (compute group)
 // The bias is already in the accumulator (bias K-step), so a hidden layer is TMEM -> ReLU+bf16 -> smem.
 // MODE 0: hidden layer -> act.  MODE 1: same + sigma head (fp32).  MODE 2: view layer -> rgb head (fp32).
@@ -251,9 +258,9 @@ __device__ __forceinline__ void encode_d_store(uint32_t stg, int row, int half, 
 template <int MODE>
 __device__ __forceinline__ void epilogue(Smem& sm, uint32_t tmem_acc, uint32_t act_saddr, int slot, const float* __restrict__ w_alpha,
                                          const float* __restrict__ w_rgb, int warp, int lane, float& sig_keep,
-                                         uint4* dump = nullptr, size_t dump_run_stride = 0) {
-  // dump (training forward only): this thread's row in run 0 of the layer's activation dump; run r of the layer
-  // (8 consecutive columns of every row, the UMMA run layout) lives dump_run_stride uint4's further per run
+                                         uint4* dump = nullptr) {
+  // dump (training forward only): this thread's row of the layer's row-major activation dump ([rows, 256 | 128] bf16);
+  // a thread owns 128 (view layer: 64) consecutive columns, i.e. 256 (128) contiguous bytes of its row
   const int q = warp & 3, half = warp >> 2;
   const int row = q * 32 + lane;
   constexpr int kCols = (MODE == 2) ? 64 : 128;        // columns per thread
@@ -293,24 +300,21 @@ __device__ __forceinline__ void epilogue(Smem& sm, uint32_t tmem_acc, uint32_t a
         r2 = fmaf(x0, c.x, r2); r2 = fmaf(x1, c.y, r2); r2 = fmaf(x2, c.z, r2); r2 = fmaf(x3, c.w, r2);
       }
     } else {
+      uint32_t pk[8];
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
-        const uint32_t p0 = pack_relu_bf16x2(__uint_as_float(vb[8 * g]), __uint_as_float(vb[8 * g + 1]));
-        const uint32_t p1 = pack_relu_bf16x2(__uint_as_float(vb[8 * g + 2]), __uint_as_float(vb[8 * g + 3]));
-        const uint32_t p2 = pack_relu_bf16x2(__uint_as_float(vb[8 * g + 4]), __uint_as_float(vb[8 * g + 5]));
-        const uint32_t p3 = pack_relu_bf16x2(__uint_as_float(vb[8 * g + 6]), __uint_as_float(vb[8 * g + 7]));
-        sts128(dst0 + (uint32_t)(2 * b + g) * kRunBytes, p0, p1, p2, p3);
-        if (dump) dump[(size_t)((col0 >> 3) + 2 * b + g) * dump_run_stride] = make_uint4(p0, p1, p2, p3);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          pk[4 * g + i] = pack_relu_bf16x2(__uint_as_float(vb[8 * g + 2 * i]), __uint_as_float(vb[8 * g + 2 * i + 1]));
+        sts128(dst0 + (uint32_t)(2 * b + g) * kRunBytes, pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
       }
+      if (dump) stg256(dump + (col0 >> 3) + 2 * b, pk);                  // 16 columns = one full 32-byte sector
     }
     if (MODE == 2 && dump) {      // view layer: relu(g) of this thread's 16 columns
+      uint32_t pk[8];
 #pragma unroll
-      for (int g = 0; g < 2; ++g)
-        dump[(size_t)((col0 >> 3) + 2 * b + g) * dump_run_stride] =
-            make_uint4(pack_relu_bf16x2(__uint_as_float(vb[8 * g]), __uint_as_float(vb[8 * g + 1])),
-                       pack_relu_bf16x2(__uint_as_float(vb[8 * g + 2]), __uint_as_float(vb[8 * g + 3])),
-                       pack_relu_bf16x2(__uint_as_float(vb[8 * g + 4]), __uint_as_float(vb[8 * g + 5])),
-                       pack_relu_bf16x2(__uint_as_float(vb[8 * g + 6]), __uint_as_float(vb[8 * g + 7])));
+      for (int i = 0; i < 8; ++i) pk[i] = pack_relu_bf16x2(__uint_as_float(vb[2 * i]), __uint_as_float(vb[2 * i + 1]));
+      stg256(dump + (col0 >> 3) + 2 * b, pk);
     }
   }
   // heads: this thread's column half of (rgb_raw, sigma_raw) -> one conflict-free 16-byte store per tile
@@ -751,19 +755,18 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
       ++accs;
       tc_fence_after_sync();
       uint4* dptr = nullptr;
-      size_t dstride = 0;
       if (kDump) {
-        // training forward: post-ReLU activations of every layer, bf16, per pass [layer][run][row][8]; rows in
-        // (ray, sample) order: row = unit * rows_per_group + tile * 128 + row_in_tile (units padded to pairs)
+        // training forward: post-ReLU activations of every layer, bf16, per pass [layer][row][256] row-major (view
+        // layer: [row][128], after the eight trunk layers); rows in (ray, sample) order:
+        // row = unit * rows_per_group + tile * 128 + row_in_tile (units padded to pairs)
         const long long m = tc.pass == 0 ? dump.rows_c : dump.rows_f;
         const long long grow = tc.unit * (long long)(kRPG * tc.S) + tc.row0 + ((gwarp & 3) * 32 + lane);
-        dstride = (size_t)m;
-        dptr = reinterpret_cast<uint4*>(tc.pass == 0 ? dump.c : dump.f) + (size_t)L * 32 * (size_t)m + (size_t)grow;
+        dptr = reinterpret_cast<uint4*>(tc.pass == 0 ? dump.c : dump.f) + (size_t)L * 32 * (size_t)m + (size_t)grow * (L == 8 ? 16 : 32);
       }
       { PROF_T0();
-        if (L == 8) epilogue<2>(sm, tmem_acc, act_saddr, s, net.w_alpha, net.w_rgb, gwarp, lane, sig_keep, dptr, dstride);
-        else if (L == 7) epilogue<1>(sm, tmem_acc, act_saddr, s, net.w_alpha, net.w_rgb, gwarp, lane, sig_keep, dptr, dstride);
-        else epilogue<0>(sm, tmem_acc, act_saddr, s, net.w_alpha, net.w_rgb, gwarp, lane, sig_keep, dptr, dstride);
+        if (L == 8) epilogue<2>(sm, tmem_acc, act_saddr, s, net.w_alpha, net.w_rgb, gwarp, lane, sig_keep, dptr);
+        else if (L == 7) epilogue<1>(sm, tmem_acc, act_saddr, s, net.w_alpha, net.w_rgb, gwarp, lane, sig_keep, dptr);
+        else epilogue<0>(sm, tmem_acc, act_saddr, s, net.w_alpha, net.w_rgb, gwarp, lane, sig_keep, dptr);
         compute_arrive(act_ready_a, lane); if (timed) PROF_ADD(8); }
       if (kStage && L == 8) {
         group_bar_sync(s);

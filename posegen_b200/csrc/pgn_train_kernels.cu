@@ -1,0 +1,189 @@
+// Training-step glue kernels of the A-NeRF MLP backward (HBM-bound, CUDA cores).
+//
+//   pgn_encode_bf16_kernel   encode_inputs (core/raycasters.py:476-555) straight to the bf16 operand the weight-gradient
+//                            GEMMs read (x_p | d_emb, reference channel order), rows staged in shared memory and stored
+//                            with 16-byte coalesced writes.
+//   pgn_mlp_delta_kernel     one pass over a layer's delta matrix that fuses what autograd does in four:
+//                            dZ = [act > 0] * (dH + rs @ wr)        ReLU backward (core/networks/nerf.py:96-99,129)
+//                            colsum += sum_rows dZ                   bias gradient of the layer
+//                            wsum   += rs^T @ act                    weight gradient of a 1- or 3-row head that reads `act`
+//                            (alpha_linear on h7, rgb_linear on the view layer; nerf.py:102,131)
+//                            with `rs @ wr` the head's contribution to dL/d act (outer product of the per-row head deltas
+//                            and the head weights).
+#include "pgn_common.cuh"
+#include "pgn_kernels.h"
+
+namespace {
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
+
+constexpr int kEncRows = 8;                                  // rows (samples) per block iteration
+constexpr int kEncThreads = kEncRows * PGN_J;                // one thread per (row, joint)
+
+__global__ void __launch_bounds__(kEncThreads) pgn_encode_bf16_kernel(PgnRayRefs rays, const PgnScalars* __restrict__ scp,
+                                                                      const float* __restrict__ z, int n_z,
+                                                                      __nv_bfloat16* __restrict__ enc) {
+  __shared__ __align__(16) __nv_bfloat16 tile[kEncRows][PGN_ENC];
+  const PgnScalars& sc = *scp;
+  const long long rows = rays.n_rays * n_z;
+  const int j = threadIdx.x % PGN_J, rl = threadIdx.x / PGN_J;
+  for (long long row0 = (long long)blockIdx.x * kEncRows; row0 < rows; row0 += (long long)gridDim.x * kEncRows) {
+    const long long rs = row0 + rl;
+    if (rs < rows) {
+      const long long ray = rs / n_z;
+      const float* rb = rays.ray_batch + ray * 11;
+      const float4* m = reinterpret_cast<const float4*>(pgn_ray_skts(rays, ray) + j * 16);
+      const float4 m0 = __ldg(m), m1 = __ldg(m + 1), m2 = __ldg(m + 2);
+      float px, py, pz;
+      pgn_sample_point(rb, rb + 3, z[rs], px, py, pz);
+      // same arithmetic as the operand generator of the fused forward kernel (pgn_render_bf16.cu encode_x): fast
+      // window, one __sincosf + double-angle steps; the values are rounded to bf16 anyway
+      const PgnJointGeom g = pgn_joint_geom<true>(m0, m1, m2, px, py, pz, sc.tau_v, sc.cutoff_v[j]);
+      const float wd = pgn_window<true>(g.v, sc.tau_d, sc.cutoff_d[j]);
+      __nv_bfloat16* e = tile[rl];
+      float sn, cs;
+      __sincosf(g.v, &sn, &cs);
+      e[j] = __float2bfloat16_rn(g.v * g.w);
+#pragma unroll
+      for (int f = 0; f < PGN_LV; ++f) {
+        e[(1 + 2 * f) * PGN_J + j] = __float2bfloat16_rn(sn * g.w);
+        e[(2 + 2 * f) * PGN_J + j] = __float2bfloat16_rn(cs * g.w);
+        const float t2 = cs + cs;
+        sn = t2 * sn;
+        cs = fmaf(t2, cs, -1.0f);
+      }
+      e[360 + j * 3 + 0] = __float2bfloat16_rn(g.rx);
+      e[360 + j * 3 + 1] = __float2bfloat16_rn(g.ry);
+      e[360 + j * 3 + 2] = __float2bfloat16_rn(g.rz);
+      float dj[3];
+      pgn_joint_dir(m0, m1, m2, rb + 3, dj[0], dj[1], dj[2]);
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        __sincosf(dj[a], &sn, &cs);                 // |dj| <= 1
+        e[PGN_ENC_P + j * 3 + a] = __float2bfloat16_rn(wd * dj[a]);
+#pragma unroll
+        for (int f = 0; f < PGN_LD; ++f) {
+          e[PGN_ENC_P + (1 + 2 * f) * 72 + j * 3 + a] = __float2bfloat16_rn(wd * sn);
+          e[PGN_ENC_P + (2 + 2 * f) * 72 + j * 3 + a] = __float2bfloat16_rn(wd * cs);
+          const float t2 = cs + cs;
+          sn = t2 * sn;
+          cs = fmaf(t2, cs, -1.0f);
+        }
+      }
+    }
+    __syncthreads();
+    // 8 consecutive rows are one contiguous 17,280-byte block of the output
+    const long long nrow = min((long long)kEncRows, rows - row0);
+    const int n16 = (int)(nrow * (PGN_ENC * 2 / 16));
+    uint4* dst = reinterpret_cast<uint4*>(enc + row0 * PGN_ENC);
+    const uint4* src = reinterpret_cast<const uint4*>(&tile[0][0]);
+    for (int i = threadIdx.x; i < n16; i += kEncThreads) dst[i] = src[i];
+    __syncthreads();
+  }
+}
+
+template <int C, int NRS>
+__global__ void __launch_bounds__(256) pgn_mlp_delta_kernel(uint4* __restrict__ dh, int has_in, const uint4* __restrict__ act,
+                                                            long long m, const float* __restrict__ rs, int rs_stride,
+                                                            const float* __restrict__ wr, float* __restrict__ colsum,
+                                                            float* __restrict__ wsum) {
+  constexpr int TPR = C / 8;            // threads per row (8 columns = one 16-byte word each)
+  constexpr int RPB = 256 / TPR;        // rows per block iteration
+  constexpr int NR = NRS > 0 ? NRS : 1;
+  __shared__ float red[RPB][C + 1];
+  const int cg = threadIdx.x % TPR, rl = threadIdx.x / TPR;
+  float cs[8], ws[NR][8], wv[NR][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    cs[i] = 0.f;
+#pragma unroll
+    for (int k = 0; k < NR; ++k) { ws[k][i] = 0.f; wv[k][i] = NRS > 0 ? __ldg(wr + k * C + cg * 8 + i) : 0.f; }
+  }
+  for (long long row = (long long)blockIdx.x * RPB + rl; row < m; row += (long long)gridDim.x * RPB) {
+    const size_t off = (size_t)row * TPR + cg;
+    uint4 a = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);      // no mask: every column "active"
+    if (act) a = __ldg(act + off);
+    uint4 d = make_uint4(0u, 0u, 0u, 0u);
+    if (has_in) d = dh[off];
+    float r[NR];
+#pragma unroll
+    for (int k = 0; k < NR; ++k) r[k] = NRS > 0 ? __ldg(rs + (size_t)row * rs_stride + k) : 0.f;
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, dw[4] = {d.x, d.y, d.z, d.w};
+    uint32_t ow[4];
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const float a0 = bf16_lo(aw[w]), a1 = bf16_hi(aw[w]);
+      float p0 = bf16_lo(dw[w]), p1 = bf16_hi(dw[w]);
+#pragma unroll
+      for (int k = 0; k < NRS; ++k) {
+        p0 = fmaf(r[k], wv[k][2 * w], p0);
+        p1 = fmaf(r[k], wv[k][2 * w + 1], p1);
+        ws[k][2 * w] = fmaf(r[k], a0, ws[k][2 * w]);
+        ws[k][2 * w + 1] = fmaf(r[k], a1, ws[k][2 * w + 1]);
+      }
+      p0 = a0 > 0.f ? p0 : 0.f;
+      p1 = a1 > 0.f ? p1 : 0.f;
+      cs[2 * w] += p0;
+      cs[2 * w + 1] += p1;
+      ow[w] = pack_bf16x2(p0, p1);
+    }
+    dh[off] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+  }
+  // block reduction over the row lanes, then one atomic per column per block
+  for (int q = 0; q < 1 + NRS; ++q) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[rl][cg * 8 + i] = q == 0 ? cs[i] : ws[q > 0 ? q - 1 : 0][i];
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += 256) {
+      float s = 0.f;
+#pragma unroll 4
+      for (int r2 = 0; r2 < RPB; ++r2) s += red[r2][c];
+      if (q == 0) atomicAdd(colsum + c, s);
+      else if (wsum) atomicAdd(wsum + (q - 1) * C + c, s);
+    }
+  }
+}
+
+template <int C, int NRS>
+cudaError_t launch_delta(void* dh, int has_in, const void* act, long long m, const float* rs, int rs_stride, const float* wr,
+                         float* colsum, float* wsum, int num_sms, cudaStream_t stream) {
+  constexpr int RPB = 256 / (C / 8);
+  const long long grid = min((m + RPB - 1) / RPB, (long long)num_sms * 8);
+  pgn_mlp_delta_kernel<C, NRS><<<(unsigned)grid, 256, 0, stream>>>(reinterpret_cast<uint4*>(dh), has_in,
+                                                                    reinterpret_cast<const uint4*>(act), m, rs, rs_stride, wr,
+                                                                    colsum, wsum);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t pgn_launch_encode_bf16(const PgnRayRefs& rays, const PgnScalars* sc_dev, const float* z, int n_z,
+                                   __nv_bfloat16* enc, cudaStream_t stream) {
+  const long long rows = rays.n_rays * n_z;
+  if (rows == 0) return cudaSuccess;
+  const long long grid = min((rows + kEncRows - 1) / kEncRows, (long long)148 * 10);
+  pgn_encode_bf16_kernel<<<(unsigned)grid, kEncThreads, 0, stream>>>(rays, sc_dev, z, n_z, enc);
+  return cudaGetLastError();
+}
+
+cudaError_t pgn_launch_mlp_delta(void* dh, int has_in, const void* act, long long m, int C, const float* rs, int rs_stride,
+                                 int nrs, const float* wr, float* colsum, float* wsum, int num_sms, cudaStream_t stream) {
+  cudaError_t e = cudaMemsetAsync(colsum, 0, sizeof(float) * C, stream);
+  if (e != cudaSuccess) return e;
+  if (wsum && nrs > 0) {
+    e = cudaMemsetAsync(wsum, 0, sizeof(float) * C * nrs, stream);
+    if (e != cudaSuccess) return e;
+  }
+  if (m == 0) return cudaSuccess;
+  if (C == 256 && nrs == 0) return launch_delta<256, 0>(dh, has_in, act, m, rs, rs_stride, wr, colsum, wsum, num_sms, stream);
+  if (C == 256 && nrs == 1) return launch_delta<256, 1>(dh, has_in, act, m, rs, rs_stride, wr, colsum, wsum, num_sms, stream);
+  if (C == 128 && nrs == 0) return launch_delta<128, 0>(dh, has_in, act, m, rs, rs_stride, wr, colsum, wsum, num_sms, stream);
+  if (C == 128 && nrs == 3) return launch_delta<128, 3>(dh, has_in, act, m, rs, rs_stride, wr, colsum, wsum, num_sms, stream);
+  return cudaErrorInvalidValue;
+}

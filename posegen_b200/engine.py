@@ -180,8 +180,9 @@ class Engine:
 
     def render_train(self, ray_batch, skts, cyls, pose_idx=None, nanfill_chunk=0, rand=None):
         """pgn_render_forward_train: the fused bf16 forward + per-layer activation dump for the weight gradients.
-        Returns (outputs incl. the taps the backward needs, {"c": dump, "f": dump}); dump[p] is a bf16 tensor
-        [272 runs, rows, 8] (layers 0-7: 32 runs each, view layer: 16), rows in (ray, sample) order.
+        Returns (outputs incl. the taps the backward needs, {"c": dump, "f": dump}); dump[p] is a flat bf16 buffer of
+        rows * 2176 elements: layers 0-7 row-major [rows,256] each, then the view layer [rows,128] (`act_layer`
+        returns the views), rows in (ray, sample) order.
         rand: optional dict of CUDA fp32 tensors t_rand [n,64], u_is [n,16], noise0 [n,64], noise [n,80] (training-time
         randomness drawn by the caller; missing keys = deterministic)."""
         inp, keep = self._inputs(ray_batch, skts, cyls, pose_idx, nanfill_chunk, "bf16")
@@ -195,8 +196,7 @@ class Engine:
         acts = {}
         for key, p in (("c", 0), ("f", 1)):
             nbytes = self.lib.pgn_activation_dump_bytes(n, p)
-            rows = nbytes // (272 * 16)
-            acts[key] = torch.empty((272, rows, 8), dtype=torch.bfloat16, device=dev)
+            acts[key] = torch.empty((nbytes // 2,), dtype=torch.bfloat16, device=dev)
         need = self.lib.pgn_workspace_bytes(self.handle, n)
         if self._workspace is None or self._workspace.numel() < need or self._workspace.device != dev:
             self._workspace = torch.empty(max(need, 1 << 20), dtype=torch.uint8, device=dev)
@@ -230,6 +230,38 @@ class Engine:
         enc = torch.empty((inp.n_rays, z.shape[1], 1080), dtype=torch.float32, device=z.device)
         _lib.check(self.lib.pgn_encode(self.handle, C.byref(inp), _ptr(z), z.shape[1], _ptr(enc), self._stream()))
         return enc
+
+    def encode_bf16(self, ray_batch, skts, cyls, z):
+        """The same encoding rounded to bf16 [n, n_z, 1080] (operand of the weight-gradient GEMMs)."""
+        inp, keep = self._inputs(ray_batch, skts, cyls)
+        z = z.contiguous()
+        enc = torch.empty((inp.n_rays, z.shape[1], 1080), dtype=torch.bfloat16, device=z.device)
+        _lib.check(self.lib.pgn_encode_bf16(self.handle, C.byref(inp), _ptr(z), z.shape[1], _ptr(enc), self._stream()))
+        return enc
+
+    def mlp_delta(self, dh, act, rs=None, wr=None, has_input=True, want_wsum=False):
+        """pgn_mlp_delta: in place dh <- [act > 0] * ((has_input ? dh : 0) + rs @ wr); returns (column sums of the new dh,
+        rs^T @ act or None).  dh / act: bf16 [m, 256 | 128] contiguous; rs: fp32 [m, nrs] view with unit inner stride
+        (row stride arbitrary); wr: fp32 [nrs, cols] contiguous."""
+        m, cols = dh.shape
+        if dh.dtype != torch.bfloat16 or not dh.is_contiguous() or not dh.is_cuda:
+            raise ValueError("dh must be a contiguous CUDA bf16 matrix")
+        if act is not None and (act.dtype != torch.bfloat16 or not act.is_contiguous() or act.shape != dh.shape):
+            raise ValueError("act must be a contiguous bf16 matrix of dh's shape")
+        nrs = 0 if rs is None else rs.shape[1]
+        if nrs:
+            if rs.dtype != torch.float32 or rs.stride(1) != 1 or rs.shape[0] != m:
+                raise ValueError("rs must be fp32 [m, nrs] with unit inner stride")
+            wr = wr.detach().float().contiguous()
+            if wr.shape != (nrs, cols):
+                raise ValueError("wr must be [nrs, cols]")
+        colsum = torch.empty((cols,), dtype=torch.float32, device=dh.device)
+        wsum = torch.empty((nrs, cols), dtype=torch.float32, device=dh.device) if (want_wsum and nrs) else None
+        with torch.cuda.device(dh.device):
+            _lib.check(self.lib.pgn_mlp_delta(self.handle, _ptr(dh), 1 if has_input else 0, _ptr(act), m, cols,
+                                              _ptr(rs) if nrs else None, rs.stride(0) if nrs else 0, nrs, _ptr(wr) if nrs else None,
+                                              _ptr(colsum), _ptr(wsum), self._stream()))
+        return colsum, wsum
 
     def mlp(self, net_id, enc, precision="bf16"):
         _check_f32_cuda(enc, "enc")

@@ -126,27 +126,46 @@ class RayCaster(nn.Module):
         self.return_alpha = True
         self._engines = {}
         self._uploaded = {}
+        self._dirty = {}
 
     # -- engine / weight sync ---------------------------------------------------
     def _param_signature(self):
-        taus = (self.embed_fn.tau, self.embeddirs_fn.tau)
-        return tuple([p._version for p in self.parameters()] + [t._version for t in taus] + [t.data_ptr() for t in taus])
+        ps = list(self.parameters())
+        return tuple(p._version for p in ps) + tuple(p.data_ptr() for p in ps)
+
+    def _scalar_signature(self):
+        ts = (self.embed_fn.tau, self.embeddirs_fn.tau, self.embed_fn.cutoff_dist, self.embeddirs_fn.cutoff_dist)
+        return tuple(t._version for t in ts) + tuple(t.data_ptr() for t in ts) + (float(self.network.density_scale),)
+
+    def mark_weights_dirty(self):
+        """Force a re-pack of the kernel-side weight copies on the next call (after in-place parameter edits that
+        bypass autograd's version counters, e.g. `p.data.copy_()`)."""
+        for key in self._engines:
+            self._dirty[key] = True
 
     def engine(self, device) -> Engine:
+        """The per-device C-ABI context with this module's current weights.  Weights are re-packed (device to device, on
+        the current stream, no host sync) when a parameter's version counter moved (optimizer.step); the embedder
+        scalars are read back to the host only when their buffers changed (update_embed_fns), so a training loop
+        never blocks on the device here.  Version counters are not bumped by every optimizer (torch's fused Adam
+        updates parameters without touching them), so a differentiable train-mode forward also marks the packed copy
+        stale (`mark_weights_dirty`): the call after it always re-packs."""
         device = torch.device(device)
         key = device.index if device.index is not None else torch.cuda.current_device()
         if key not in self._engines:
             self._engines[key] = Engine(torch.device("cuda", key))
         eng = self._engines[key]
-        sig = (self._param_signature(), tuple(p.data_ptr() for p in self.parameters()))
-        if self._uploaded.get(key) != sig:
+        sig_w, sig_s = self._param_signature(), self._scalar_signature()
+        up = self._uploaded.get(key, (None, None))
+        if up[0] != sig_w or self._dirty.pop(key, False):
             eng.upload_net(0, self.network.state_dict())
             eng.upload_net(1, self.network_fine.state_dict())
+        if up[1] != sig_s:
             eng.set_scalars(float(self.embed_fn.tau), float(self.embeddirs_fn.tau),
                             self.embed_fn.cutoff_dist.detach().flatten().tolist(),
                             self.embeddirs_fn.cutoff_dist.detach().flatten().tolist(),
                             float(self.network.density_scale))
-            self._uploaded[key] = sig
+        self._uploaded[key] = (sig_w, sig_s)
         return eng
 
     # -- forward -------------------------------------------------------------------

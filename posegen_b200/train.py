@@ -19,7 +19,7 @@ gradient bucket.
 """
 from __future__ import annotations
 
-from typing import Dict, List
+from typing import Callable, Dict, List
 
 import torch
 import torch.distributed as dist
@@ -39,55 +39,59 @@ def _mm32(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     return torch.mm(a.float(), b.float())
 
 
-def _layer(acts: torch.Tensor, l: int, m: int) -> torch.Tensor:
-    """Activation matrix of layer l (0..7: 256 columns, 8: view layer, 128) for the first m rows, [m, cols] bf16."""
-    runs = acts[l * 32:(l + 1) * 32] if l < 8 else acts[256:272]
-    return runs[:, :m].permute(1, 0, 2).reshape(m, -1)
-
-
-def _relu_bwd(grad: torch.Tensor, act: torch.Tensor) -> torch.Tensor:
-    """grad * [act > 0] in one pass (act is the post-ReLU activation)."""
-    return torch.ops.aten.threshold_backward(grad, act, 0.0)
+def act_layer(acts: torch.Tensor, l: int, m: int) -> torch.Tensor:
+    """Activation matrix of layer l (0..7: 256 columns, 8: view layer, 128) for the first m rows of the kernel's
+    row-major dump (a view, no copy): [m, cols] bf16."""
+    rows = acts.numel() // 2176
+    if l < 8:
+        return acts[l * rows * 256:(l + 1) * rows * 256].view(rows, 256)[:m]
+    return acts[8 * rows * 256:].view(rows, 128)[:m]
 
 
 def mlp_backward(params: Dict[str, torch.Tensor], enc: torch.Tensor, acts: torch.Tensor, d_raw: torch.Tensor,
-                 want_input_grad: bool = False) -> Dict[str, torch.Tensor]:
+                 fuse: Callable, want_input_grad: bool = False) -> Dict[str, torch.Tensor]:
     """Weight gradients of one NeRF MLP (core/networks/nerf.py:94-148).
 
-    params: fp32 nn.Linear tensors; enc [m,1080] fp32 network input; acts: the kernel's activation dump of this
-    pass; d_raw [m,4] = dL/d(rgb_raw, sigma_raw).  Deltas and activations are bf16, every GEMM accumulates in fp32
-    and the weight gradients are produced in fp32.  Returns {name: fp32 gradient}; with want_input_grad also
-    "_g_enc" [m,1080] = dL/d(network input) (for the gradient w.r.t. the pose transforms)."""
+    params: fp32 nn.Linear tensors; enc [m,1080] bf16 network input (`pgn_encode_bf16`); acts: the kernel's activation
+    dump of this pass; d_raw [m,4] fp32 = dL/d(rgb_raw, sigma_raw).  `fuse(dh, act, rs, wr, has_input, want_wsum)` is
+    `Engine.mlp_delta` (`pgn_mlp_delta`): the ReLU backward, the bias gradient and the two skinny heads in one pass
+    over each delta matrix.  Deltas and activations are bf16, every GEMM accumulates in fp32 and the weight
+    gradients are produced in fp32.  `feature_linear` has no activation (nerf.py:125-128), so it never shows up at
+    batch size: with T = dG^T h7 its gradients and those of the feature block of `views_linears.0` are
+    [128,256]-sized products, and dL/d h7 reads the folded weight W_v[:, :256] @ W_f.
+    Returns {name: fp32 gradient}; with want_input_grad also "_g_enc" [m,1080] = dL/d(network input)."""
     m = enc.shape[0]
     bf = torch.bfloat16
-    encb = enc.to(bf)
-    x_p, d_emb = encb[:, :432], encb[:, 432:]
-    H = [_layer(acts, l, m) for l in range(8)]
-    G = _layer(acts, 8, m)
-    W = {k: v.detach().to(bf) for k, v in params.items() if k.endswith("weight")}
+    x_p, d_emb = enc[:, :432], enc[:, 432:]
+    H = [act_layer(acts, l, m) for l in range(8)]
+    G = act_layer(acts, 8, m)
+    P = {k: v.detach() for k, v in params.items()}
+    W = {k: v.to(bf) for k, v in P.items() if k.startswith("pts_linears") and k.endswith("weight")}
     g: Dict[str, torch.Tensor] = {}
-    d_rawb = d_raw.to(bf)
-    d_rgb, d_sig = d_rawb[:, :3], d_rawb[:, 3:4]
-    # rgb head and view layer:  g = relu(W_v [f | d_emb] + b_v),  f = W_f h7 + b_f,  rgb_raw = W_rgb g + b_rgb
-    g["rgb_linear.weight"] = _mm32(d_rgb.t(), G)
+    # rgb head + view layer:  g = relu(W_v [f | d_emb] + b_v),  f = W_f h7 + b_f,  rgb_raw = W_rgb g + b_rgb
+    dG = torch.empty((m, 128), dtype=bf, device=enc.device)
+    bias_v, g_rgb = fuse(dG, G, d_raw[:, :3], P["rgb_linear.weight"], False, True)
+    g["rgb_linear.weight"] = g_rgb
     g["rgb_linear.bias"] = d_raw[:, :3].sum(0)
-    dG = _relu_bwd(torch.mm(d_rgb, W["rgb_linear.weight"]), G)
-    f = torch.addmm(params["feature_linear.bias"].detach().to(bf), H[7], W["feature_linear.weight"].t())
-    g["views_linears.0.weight"] = torch.cat([_mm32(dG.t(), f), _mm32(dG.t(), d_emb)], 1)
-    g["views_linears.0.bias"] = dG.sum(0, dtype=torch.float32)
-    g_in = torch.zeros((m, 1080), dtype=torch.float32, device=enc.device) if want_input_grad else None
+    dGt = dG.t()
+    Tm = _mm32(dGt, H[7])                                                    # [128,256] = dG^T h7
+    W_v, W_f, b_f = P["views_linears.0.weight"], P["feature_linear.weight"], P["feature_linear.bias"]
+    W_vf = W_v[:, :256]
+    g["views_linears.0.weight"] = torch.cat([Tm @ W_f.t() + bias_v[:, None] * b_f[None, :], _mm32(dGt, d_emb)], 1)
+    g["views_linears.0.bias"] = bias_v
+    g["feature_linear.weight"] = W_vf.t() @ Tm
+    g["feature_linear.bias"] = W_vf.t() @ bias_v
+    g_in = torch.empty((m, 1080), dtype=torch.float32, device=enc.device) if want_input_grad else None
     if want_input_grad:
-        g_in[:, 432:] = torch.mm(dG, W["views_linears.0.weight"][:, 256:])
-    df = torch.mm(dG, W["views_linears.0.weight"][:, :256])
-    g["feature_linear.weight"] = _mm32(df.t(), H[7])
-    g["feature_linear.bias"] = df.sum(0, dtype=torch.float32)
-    # sigma head
-    g["alpha_linear.weight"] = _mm32(d_sig.t(), H[7])
+        g_in[:, 432:] = torch.mm(dG, W_v[:, 256:].to(bf))
+    # sigma head + last trunk layer: dL/d h7 = dG (W_vf W_f) + d_sigma w_alpha
+    dH = torch.mm(dG, (W_vf @ W_f).to(bf))
+    bias, g_alpha = fuse(dH, H[7], d_raw[:, 3:4], P["alpha_linear.weight"], True, True)
+    g["alpha_linear.weight"] = g_alpha
     g["alpha_linear.bias"] = d_raw[:, 3:4].sum(0)
-    dH = torch.addmm(d_sig * W["alpha_linear.weight"], df, W["feature_linear.weight"])
     # trunk, last layer first; layer 5 reads [x_p | h4] (skip after layer index 4, nerf.py:100-101)
     for l in range(7, -1, -1):
-        dZ = _relu_bwd(dH, H[l])
+        dZ = dH                                                              # masked in place by `fuse`
         dZt = dZ.t()
         if l == 0:
             g["pts_linears.0.weight"] = _mm32(dZt, x_p)
@@ -95,12 +99,17 @@ def mlp_backward(params: Dict[str, torch.Tensor], enc: torch.Tensor, acts: torch
             g["pts_linears.5.weight"] = torch.cat([_mm32(dZt, x_p), _mm32(dZt, H[4])], 1)
         else:
             g[f"pts_linears.{l}.weight"] = _mm32(dZt, H[l - 1])
-        g[f"pts_linears.{l}.bias"] = dZ.sum(0, dtype=torch.float32)
+        g[f"pts_linears.{l}.bias"] = bias
         Wl = W[f"pts_linears.{l}.weight"]
         if want_input_grad and l in (0, 5):
-            g_in[:, :432] += torch.mm(dZ, Wl[:, :432])
+            gx = torch.mm(dZ, Wl[:, :432])
+            if l == 5:
+                g_in[:, :432] = gx
+            else:
+                g_in[:, :432] += gx
         if l > 0:
             dH = torch.mm(dZ, Wl[:, 432:] if l == 5 else Wl)
+            bias, _ = fuse(dH, H[l - 1], None, None, True, False)
     if want_input_grad:
         g["_g_enc"] = g_in
     return g
@@ -111,6 +120,7 @@ class _RenderTrainFn(torch.autograd.Function):
     def forward(ctx, rc, ray_batch, skts, cyls, nanfill_chunk, rand, *params):
         eng = rc.engine(ray_batch.device)
         ret, acts = eng.render_train(ray_batch, skts, cyls, nanfill_chunk=nanfill_chunk, rand=rand)
+        rc.mark_weights_dirty()            # an optimizer step follows; not every optimizer bumps the version counters
         ctx.rc, ctx.acts, ctx.rand = rc, acts, (rand or {})
         ctx.save_for_backward(ray_batch, skts, cyls, ret["raw0"], ret["raw"], ret["z_fine"], ret["near_far"])
         ctx.mark_non_differentiable(ret["disp_map"], ret["disp0"])
@@ -138,9 +148,9 @@ class _RenderTrainFn(torch.autograd.Function):
             gr = zero3 if gr is None else gr.contiguous().float()
             ga = zero1 if ga is None else ga.contiguous().float()
             d_raw = eng.composite_backward(rb, sk, cy, raw_p, z.contiguous(), gr, ga, noise=nz)
-            enc = eng.encode(rb, sk, cy, z.contiguous())
+            enc = eng.encode_bf16(rb, sk, cy, z.contiguous())
             pd = dict(net.named_parameters())
-            gd = mlp_backward(pd, enc.reshape(-1, 1080), acts, d_raw.reshape(-1, 4), want_input_grad=want_sk)
+            gd = mlp_backward(pd, enc.reshape(-1, 1080), acts, d_raw.reshape(-1, 4), eng.mlp_delta, want_input_grad=want_sk)
             grads += [gd[k].reshape(pd[k].shape).to(pd[k].dtype) for k in PARAM_ORDER]
             if want_sk:          # pose gradient: dL/d(network input) -> dL/d skts (per ray), both passes add up
                 d = eng.encode_backward(rb, sk, cy, z.contiguous(), gd["_g_enc"].reshape(n, -1, 1080))

@@ -84,14 +84,16 @@ def test_training_step_gradients_match_oracle_autograd(engine, train_case):
     assert float((g - gr).norm() / gr.norm()) <= 3e-2
 
 
-def test_training_step_reduces_the_loss(engine, train_case):
-    """A few Adam steps through the drop-in RayCaster (weights are re-packed after every optimizer.step)."""
+@pytest.mark.parametrize("fused", [False, True])
+def test_training_step_reduces_the_loss(engine, train_case, fused):
+    """A few Adam steps through the drop-in RayCaster (weights are re-packed after every optimizer.step; torch's fused
+    Adam updates parameters without bumping their version counters, which must not leave the packed copy stale)."""
     frame, ckpt, rb, tgt = train_case
     n = 1024
     dev = torch.device("cuda")
     rc = raycaster_from_checkpoint(ckpt, device="cuda", precision="bf16")
     rc.train()
-    opt = torch.optim.Adam([p for p in rc.parameters() if p.requires_grad], lr=5e-4)
+    opt = torch.optim.Adam([p for p in rc.parameters() if p.requires_grad], lr=5e-4, fused=fused)
     rbt = torch.as_tensor(rb[:n], device=dev)
     sk = torch.as_tensor(frame.pose.skts, device=dev)
     cy = torch.as_tensor(frame.pose.cyl, device=dev)
@@ -190,3 +192,51 @@ def test_training_step_with_sampling_noise_matches_oracle(engine, train_case):
     r2 = rc(torch.as_tensor(rb[:256], device=dev), N_samples=64, N_importance=16, kp_batch=None, skts=sk[:256].to(dev).contiguous(),
             cyls=cy[:256].to(dev).contiguous(), perturb=1.0, raw_noise_std=1.0)
     assert torch.isfinite(r1["rgb_map"]).all() and not torch.equal(r1["rgb_map"], r2["rgb_map"])
+
+
+def test_mlp_delta_kernel_matches_torch(engine):
+    """pgn_mlp_delta (ReLU backward + bias gradient + skinny heads in one pass) against the same arithmetic in torch,
+    every supported shape, ragged row counts (incl. rows that are no multiple of the block tile)."""
+    dev = torch.device("cuda")
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for m, cols, nrs, has_in, masked in ((1000, 256, 0, True, True), (4097, 256, 1, True, True), (777, 128, 3, False, True),
+                                         (513, 128, 0, True, False), (1, 256, 1, True, True)):
+        dh = torch.randn((m, cols), device=dev, generator=g).to(torch.bfloat16)
+        act = torch.relu(torch.randn((m, cols), device=dev, generator=g)).to(torch.bfloat16) if masked else None
+        raw = torch.randn((m, 4), device=dev, generator=g)
+        rs = {0: None, 1: raw[:, 3:4], 3: raw[:, :3]}[nrs]
+        wr = torch.randn((nrs, cols), device=dev, generator=g) if nrs else None
+        pre = dh.float() if has_in else torch.zeros((m, cols), device=dev)
+        if nrs:
+            pre = pre + rs @ wr
+        want = torch.where(act > 0, pre, torch.zeros((), device=dev)) if masked else pre
+        got = dh.clone()
+        colsum, wsum = engine.mlp_delta(got, act, rs, wr, has_input=has_in, want_wsum=nrs > 0)
+        engine.check_status()
+        if nrs == 0:
+            assert torch.equal(got, want.to(torch.bfloat16)), (m, cols, nrs)
+        else:       # the kernel forms dh + rs @ wr with FMAs: within one bf16 rounding of the two-step torch result
+            assert bool(((got.float() - want).abs() <= 2.0 ** -7 * want.abs() + 1e-6).all()), (m, cols, nrs)
+            assert torch.equal(got == 0, want.to(torch.bfloat16) == 0) or masked
+        ref = want.double().sum(0)
+        assert float((colsum.double() - ref).abs().max()) <= 1e-4 * max(1.0, float(ref.abs().max())) + 1e-3
+        if nrs:
+            wref = rs.double().t() @ act.double()
+            assert float((wsum.double() - wref).abs().max()) <= 1e-4 * max(1.0, float(wref.abs().max())) + 1e-3
+
+
+def test_encode_bf16_is_the_rounded_fp32_encoding(engine, train_case):
+    """pgn_encode_bf16 against pgn_encode (the parity-checked fp32 encoding) within one bf16 rounding plus the fast-math
+    error of the double-angle recurrences the tensor-core tier uses (<= 2e-4), incl. a ragged last row block."""
+    frame, ckpt, rb, tgt = train_case
+    engine.load_checkpoint(ckpt)
+    dev = torch.device("cuda")
+    n = 37
+    rbt = torch.as_tensor(rb[:n], device=dev)
+    sk = torch.as_tensor(frame.pose.skts, device=dev)
+    cy = torch.as_tensor(frame.pose.cyl, device=dev)
+    z = torch.rand((n, 5), device=dev).sort(-1).values * 2 + 3
+    a = engine.encode(rbt, sk, cy, z)
+    b = engine.encode_bf16(rbt, sk, cy, z)
+    assert b.dtype == torch.bfloat16 and b.shape == a.shape
+    assert bool(((a - b.float()).abs() <= 2.0 ** -8 * a.abs() + 3e-4).all())

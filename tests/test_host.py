@@ -141,8 +141,8 @@ def test_hmr_input_oracle_properties():
 
 def test_mlp_backward_matches_autograd_on_cpu():
     """Host logic of the training step (posegen_b200/train.py): the GEMM weight / input gradients of one NeRF MLP,
-    fed with an activation dump in the kernel's layout ([layer][run][row][8]) built from a torch forward, against
-    autograd through the oracle's nerf_forward."""
+    fed with an activation dump in the kernel's layout (row-major per layer) built from a torch forward and a torch
+    restatement of the fused delta pass (`pgn_mlp_delta`), against autograd through the oracle's nerf_forward."""
     import numpy as np
     import torch
     from oracle import render_oracle as orc
@@ -157,7 +157,7 @@ def test_mlp_backward_matches_autograd_on_cpu():
     raw = orc.nerf_forward(enc, net)
     d_raw = torch.randn(m, 4)
     (raw * d_raw).sum().backward()
-    # activation dump: post-ReLU activations per layer, bf16, [272 runs, rows (padded), 8]
+    # activation dump: post-ReLU activations per layer, bf16, layers 0-7 [rows (padded), 256] then the view layer [rows, 128]
     with torch.no_grad():
         x_p, x_v = enc[:, :432], enc[:, 432:]
         h, acts = x_p, []
@@ -169,12 +169,21 @@ def test_mlp_backward_matches_autograd_on_cpu():
         feat = torch.nn.functional.linear(acts[7], net["feature_linear.weight"], net["feature_linear.bias"])
         g = torch.relu(torch.nn.functional.linear(torch.cat([feat, x_v], -1), net["views_linears.0.weight"], net["views_linears.0.bias"]))
         rows = 256
-        dump = torch.zeros((272, rows, 8), dtype=torch.bfloat16)
+        dump = torch.zeros((rows * 2176,), dtype=torch.bfloat16)
         for l in range(8):
-            dump[l * 32:(l + 1) * 32, :m] = acts[l].reshape(m, 32, 8).permute(1, 0, 2).to(torch.bfloat16)
-        dump[256:272, :m] = g.reshape(m, 16, 8).permute(1, 0, 2).to(torch.bfloat16)
+            dump[l * rows * 256:(l + 1) * rows * 256].view(rows, 256)[:m] = acts[l].to(torch.bfloat16)
+        dump[8 * rows * 256:].view(rows, 128)[:m] = g.to(torch.bfloat16)
+
+    def fuse(dh, act, rs, wr, has_input, want_wsum):          # what pgn_mlp_delta computes, in torch
+        pre = dh.float() if has_input else torch.zeros(dh.shape)
+        if rs is not None:
+            pre = pre + rs @ wr.float()
+        z = torch.where(act > 0, pre, torch.zeros(())) if act is not None else pre
+        dh.copy_(z.to(torch.bfloat16))
+        return z.sum(0), (rs.t() @ act.float() if (want_wsum and rs is not None) else None)
+
     params = {k: v.detach() for k, v in net.items()}
-    got = mlp_backward(params, enc.detach(), dump, d_raw, want_input_grad=True)
+    got = mlp_backward(params, enc.detach().to(torch.bfloat16), dump, d_raw, fuse, want_input_grad=True)
     flat, ref = [], []
     for k in PARAM_ORDER:
         assert got[k].reshape(net[k].shape).shape == net[k].grad.shape

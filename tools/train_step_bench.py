@@ -41,6 +41,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--cpu-baseline", action="store_true")
     ap.add_argument("--deterministic", action="store_true", help="perturb = 0, raw_noise_std = 0")
+    ap.add_argument("--profile", default=None, help="write a torch.profiler kernel table of 3 steps to this file (after the timed run)")
     a = ap.parse_args()
     rank, world, local = pdist.env_rank_world()
     pdist.init_process_group("nccl" if world > 1 else None)
@@ -49,7 +50,7 @@ def main():
     ckpt = syn.synthetic_raycaster_state(4, alpha_gain=40.0)
     rc = raycaster_from_checkpoint(ckpt, device=dev, precision="bf16")
     rc.train()
-    opt = torch.optim.Adam([p for p in rc.parameters() if p.requires_grad], lr=5e-4)
+    opt = torch.optim.Adam([p for p in rc.parameters() if p.requires_grad], lr=5e-4, fused=True)
     rb, sk, cy = make_batch(rank)
     n = rb.shape[0]
     rbt, skt, cyt = (torch.as_tensor(x, device=dev) for x in (rb, sk, cy))
@@ -97,6 +98,14 @@ def main():
         line["cpu_baseline"] = {"rays_per_sec": m / sec, "cores": os.cpu_count(), "kind": "port", "sample": f"{m} rays of the batch, fwd+bwd (autograd through the oracle), {sec:.1f} s"}
     if rank == 0:
         print(json.dumps(line), flush=True)
+    if a.profile and rank == 0:
+        from torch.profiler import profile, ProfilerActivity
+        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+            for _ in range(3):
+                step()
+            torch.cuda.synchronize()
+        with open(a.profile, "w") as f:
+            f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=70))
     if world > 1:
         torch.distributed.destroy_process_group()
 
