@@ -163,7 +163,8 @@ PGN_API int  pgn_render_forward(pgn_context* ctx, const pgn_render_inputs* in,
  * (bf16) so that the weight gradients can be formed by plain GEMMs.  Per pass the dump is row-major per layer:
  * layers 0-7 (pts_linears) [rows,256] each, then layer 8 (views_linears.0) [rows,128]; rows are samples in
  * (ray, sample) order, padded to rows = pgn_activation_dump_bytes(n, pass) / 4352.  act_coarse / act_fine: device buffers of
- * pgn_activation_dump_bytes(n_rays, 0 / 1) bytes.  Request out->raw0 / raw / z_fine / near_far for the backward.
+ * pgn_activation_dump_bytes(n_rays, 0 / 1) bytes; one of them may be NULL (that pass is not dumped: a loss that reads
+ * only the fine outputs sends no gradient into the coarse network).  Request out->raw0 / raw / z_fine / near_far for the backward.
  * rnd (may be NULL = deterministic eval sampling) carries the training-time randomness as explicit device arrays so
  * that a run is reproducible and checkable: the caller draws them with its own generator. */
 typedef struct pgn_train_random {

@@ -215,7 +215,7 @@ int pgn_render_forward_train(pgn_context* c, const pgn_render_inputs* in, const 
                              void* act_coarse, void* act_fine, const pgn_train_random* rnd,
                              void* workspace, size_t workspace_bytes, void* stream_) {
   if (!in || in->precision != PGN_PRECISION_BF16) return fail(PGN_E_INVALID, "pgn_render_forward_train: the bf16 tensor-core path only");
-  if (!act_coarse || !act_fine) return fail(PGN_E_INVALID, "pgn_render_forward_train: null activation dump");
+  if (!act_coarse && !act_fine) return fail(PGN_E_INVALID, "pgn_render_forward_train: null activation dump");
   PgnActDump d;
   d.c = (__nv_bfloat16*)act_coarse; d.f = (__nv_bfloat16*)act_fine;
   d.rows_c = pgn_bf16_dump_rows(in->n_rays, PGN_S); d.rows_f = pgn_bf16_dump_rows(in->n_rays, PGN_T);

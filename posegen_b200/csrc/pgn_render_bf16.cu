@@ -755,7 +755,7 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
       ++accs;
       tc_fence_after_sync();
       uint4* dptr = nullptr;
-      if (kDump) {
+      if (kDump && (tc.pass == 0 ? dump.c : dump.f) != nullptr) {       // a pass without a buffer is not dumped
         // training forward: post-ReLU activations of every layer, bf16, per pass [layer][row][256] row-major (view
         // layer: [row][128], after the eight trunk layers); rows in (ray, sample) order:
         // row = unit * rows_per_group + tile * 128 + row_in_tile (units padded to pairs)

@@ -178,7 +178,7 @@ class Engine:
                                                    self._stream()))
         return ret
 
-    def render_train(self, ray_batch, skts, cyls, pose_idx=None, nanfill_chunk=0, rand=None):
+    def render_train(self, ray_batch, skts, cyls, pose_idx=None, nanfill_chunk=0, rand=None, dump_coarse=True):
         """pgn_render_forward_train: the fused bf16 forward + per-layer activation dump for the weight gradients.
         Returns (outputs incl. the taps the backward needs, {"c": dump, "f": dump}); dump[p] is a flat bf16 buffer of
         rows * 2176 elements: layers 0-7 row-major [rows,256] each, then the view layer [rows,128] (`act_layer`
@@ -195,6 +195,9 @@ class Engine:
             setattr(out, k, v.data_ptr())
         acts = {}
         for key, p in (("c", 0), ("f", 1)):
+            if key == "c" and not dump_coarse:
+                acts[key] = None
+                continue
             nbytes = self.lib.pgn_activation_dump_bytes(n, p)
             acts[key] = torch.empty((nbytes // 2,), dtype=torch.bfloat16, device=dev)
         need = self.lib.pgn_workspace_bytes(self.handle, n)

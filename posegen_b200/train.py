@@ -49,10 +49,11 @@ def act_layer(acts: torch.Tensor, l: int, m: int) -> torch.Tensor:
 
 
 def mlp_backward(params: Dict[str, torch.Tensor], enc: torch.Tensor, acts: torch.Tensor, d_raw: torch.Tensor,
-                 fuse: Callable, want_input_grad: bool = False) -> Dict[str, torch.Tensor]:
+                 fuse: Callable, want_input_grad: bool = False, want_weight_grad: bool = True) -> Dict[str, torch.Tensor]:
     """Weight gradients of one NeRF MLP (core/networks/nerf.py:94-148).
 
-    params: fp32 nn.Linear tensors; enc [m,1080] bf16 network input (`pgn_encode_bf16`); acts: the kernel's activation
+    params: fp32 nn.Linear tensors; enc [m,1080] bf16 network input (`pgn_encode_bf16`; may be None when
+    want_weight_grad is False: a frozen network, the GAN step, only passes dL/d(network input) on); acts: the kernel's activation
     dump of this pass; d_raw [m,4] fp32 = dL/d(rgb_raw, sigma_raw).  `fuse(dh, act, rs, wr, has_input, want_wsum)` is
     `Engine.mlp_delta` (`pgn_mlp_delta`): the ReLU backward, the bias gradient and the two skinny heads in one pass
     over each delta matrix.  Deltas and activations are bf16, every GEMM accumulates in fp32 and the weight
@@ -60,46 +61,51 @@ def mlp_backward(params: Dict[str, torch.Tensor], enc: torch.Tensor, acts: torch
     batch size: with T = dG^T h7 its gradients and those of the feature block of `views_linears.0` are
     [128,256]-sized products, and dL/d h7 reads the folded weight W_v[:, :256] @ W_f.
     Returns {name: fp32 gradient}; with want_input_grad also "_g_enc" [m,1080] = dL/d(network input)."""
-    m = enc.shape[0]
+    m = d_raw.shape[0]
     bf = torch.bfloat16
-    x_p, d_emb = enc[:, :432], enc[:, 432:]
+    if want_weight_grad:
+        x_p, d_emb = enc[:, :432], enc[:, 432:]
     H = [act_layer(acts, l, m) for l in range(8)]
     G = act_layer(acts, 8, m)
     P = {k: v.detach() for k, v in params.items()}
     W = {k: v.to(bf) for k, v in P.items() if k.startswith("pts_linears") and k.endswith("weight")}
     g: Dict[str, torch.Tensor] = {}
     # rgb head + view layer:  g = relu(W_v [f | d_emb] + b_v),  f = W_f h7 + b_f,  rgb_raw = W_rgb g + b_rgb
-    dG = torch.empty((m, 128), dtype=bf, device=enc.device)
-    bias_v, g_rgb = fuse(dG, G, d_raw[:, :3], P["rgb_linear.weight"], False, True)
-    g["rgb_linear.weight"] = g_rgb
-    g["rgb_linear.bias"] = d_raw[:, :3].sum(0)
-    dGt = dG.t()
-    Tm = _mm32(dGt, H[7])                                                    # [128,256] = dG^T h7
+    wg = want_weight_grad
+    dG = torch.empty((m, 128), dtype=bf, device=d_raw.device)
+    bias_v, g_rgb = fuse(dG, G, d_raw[:, :3], P["rgb_linear.weight"], False, wg)
     W_v, W_f, b_f = P["views_linears.0.weight"], P["feature_linear.weight"], P["feature_linear.bias"]
     W_vf = W_v[:, :256]
-    g["views_linears.0.weight"] = torch.cat([Tm @ W_f.t() + bias_v[:, None] * b_f[None, :], _mm32(dGt, d_emb)], 1)
-    g["views_linears.0.bias"] = bias_v
-    g["feature_linear.weight"] = W_vf.t() @ Tm
-    g["feature_linear.bias"] = W_vf.t() @ bias_v
-    g_in = torch.empty((m, 1080), dtype=torch.float32, device=enc.device) if want_input_grad else None
+    if wg:
+        g["rgb_linear.weight"] = g_rgb
+        g["rgb_linear.bias"] = d_raw[:, :3].sum(0)
+        dGt = dG.t()
+        Tm = _mm32(dGt, H[7])                                                # [128,256] = dG^T h7
+        g["views_linears.0.weight"] = torch.cat([Tm @ W_f.t() + bias_v[:, None] * b_f[None, :], _mm32(dGt, d_emb)], 1)
+        g["views_linears.0.bias"] = bias_v
+        g["feature_linear.weight"] = W_vf.t() @ Tm
+        g["feature_linear.bias"] = W_vf.t() @ bias_v
+    g_in = torch.empty((m, 1080), dtype=torch.float32, device=d_raw.device) if want_input_grad else None
     if want_input_grad:
         g_in[:, 432:] = torch.mm(dG, W_v[:, 256:].to(bf))
     # sigma head + last trunk layer: dL/d h7 = dG (W_vf W_f) + d_sigma w_alpha
     dH = torch.mm(dG, (W_vf @ W_f).to(bf))
-    bias, g_alpha = fuse(dH, H[7], d_raw[:, 3:4], P["alpha_linear.weight"], True, True)
-    g["alpha_linear.weight"] = g_alpha
-    g["alpha_linear.bias"] = d_raw[:, 3:4].sum(0)
+    bias, g_alpha = fuse(dH, H[7], d_raw[:, 3:4], P["alpha_linear.weight"], True, wg)
+    if wg:
+        g["alpha_linear.weight"] = g_alpha
+        g["alpha_linear.bias"] = d_raw[:, 3:4].sum(0)
     # trunk, last layer first; layer 5 reads [x_p | h4] (skip after layer index 4, nerf.py:100-101)
     for l in range(7, -1, -1):
         dZ = dH                                                              # masked in place by `fuse`
-        dZt = dZ.t()
-        if l == 0:
-            g["pts_linears.0.weight"] = _mm32(dZt, x_p)
-        elif l == 5:
-            g["pts_linears.5.weight"] = torch.cat([_mm32(dZt, x_p), _mm32(dZt, H[4])], 1)
-        else:
-            g[f"pts_linears.{l}.weight"] = _mm32(dZt, H[l - 1])
-        g[f"pts_linears.{l}.bias"] = bias
+        if wg:
+            dZt = dZ.t()
+            if l == 0:
+                g["pts_linears.0.weight"] = _mm32(dZt, x_p)
+            elif l == 5:
+                g["pts_linears.5.weight"] = torch.cat([_mm32(dZt, x_p), _mm32(dZt, H[4])], 1)
+            else:
+                g[f"pts_linears.{l}.weight"] = _mm32(dZt, H[l - 1])
+            g[f"pts_linears.{l}.bias"] = bias
         Wl = W[f"pts_linears.{l}.weight"]
         if want_input_grad and l in (0, 5):
             gx = torch.mm(dZ, Wl[:, :432])
@@ -121,7 +127,8 @@ class _RenderTrainFn(torch.autograd.Function):
         eng = rc.engine(ray_batch.device)
         ret, acts = eng.render_train(ray_batch, skts, cyls, nanfill_chunk=nanfill_chunk, rand=rand)
         rc.mark_weights_dirty()            # an optimizer step follows; not every optimizer bumps the version counters
-        ctx.rc, ctx.acts, ctx.rand = rc, acts, (rand or {})
+        ctx.rc, ctx.eng, ctx.acts, ctx.rand = rc, eng, acts, (rand or {})
+        ctx.set_materialize_grads(False)   # outputs the loss does not read arrive as None: their pass is skipped
         ctx.save_for_backward(ray_batch, skts, cyls, ret["raw0"], ret["raw"], ret["z_fine"], ret["near_far"])
         ctx.mark_non_differentiable(ret["disp_map"], ret["disp0"])
         return ret["rgb_map"], ret["acc_map"], ret["rgb0"], ret["acc0"], ret["disp_map"], ret["disp0"]
@@ -129,8 +136,7 @@ class _RenderTrainFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_rgb, g_acc, g_rgb0, g_acc0, _gd, _gd0):
         rb, sk, cy, raw0, raw, z_fine, near_far = ctx.saved_tensors
-        rc = ctx.rc
-        eng = rc.engine(rb.device)
+        rc, eng = ctx.rc, ctx.eng      # the context as the forward left it (rc.engine() would re-pack the weights here)
         n = rb.shape[0]
         zero3, zero1 = torch.zeros((n, 3), device=rb.device), torch.zeros(n, device=rb.device)
         t = torch.linspace(0., 1., S, device=rb.device)                       # sample_from_lineseg, ray_utils.py:204-251
@@ -142,21 +148,26 @@ class _RenderTrainFn(torch.autograd.Function):
             z_c = lower + (upper - lower) * rand["t_rand"]
         grads: List[torch.Tensor] = []
         want_sk = ctx.needs_input_grad[2]
+        want_w = any(ctx.needs_input_grad[6:])               # False for a frozen NeRF (the GAN step)
         d_skts = None
         for net, acts, z, raw_p, gr, ga, nz in ((rc.network, ctx.acts["c"], z_c, raw0, g_rgb0, g_acc0, rand.get("noise0")),
                                                 (rc.network_fine, ctx.acts["f"], z_fine, raw, g_rgb, g_acc, rand.get("noise"))):
+            if (gr is None and ga is None) or not (want_w or want_sk):      # the loss does not read this pass
+                grads += [None] * len(PARAM_ORDER)
+                continue
             gr = zero3 if gr is None else gr.contiguous().float()
             ga = zero1 if ga is None else ga.contiguous().float()
-            d_raw = eng.composite_backward(rb, sk, cy, raw_p, z.contiguous(), gr, ga, noise=nz)
-            enc = eng.encode_bf16(rb, sk, cy, z.contiguous())
+            z = z.contiguous()
+            d_raw = eng.composite_backward(rb, sk, cy, raw_p, z, gr, ga, noise=nz)
+            enc = eng.encode_bf16(rb, sk, cy, z).reshape(-1, 1080) if want_w else None
             pd = dict(net.named_parameters())
-            gd = mlp_backward(pd, enc.reshape(-1, 1080), acts, d_raw.reshape(-1, 4), eng.mlp_delta, want_input_grad=want_sk)
-            grads += [gd[k].reshape(pd[k].shape).to(pd[k].dtype) for k in PARAM_ORDER]
+            gd = mlp_backward(pd, enc, acts, d_raw.reshape(-1, 4), eng.mlp_delta, want_input_grad=want_sk, want_weight_grad=want_w)
+            grads += [gd[k].reshape(pd[k].shape).to(pd[k].dtype) for k in PARAM_ORDER] if want_w else [None] * len(PARAM_ORDER)
             if want_sk:          # pose gradient: dL/d(network input) -> dL/d skts (per ray), both passes add up
-                d = eng.encode_backward(rb, sk, cy, z.contiguous(), gd["_g_enc"].reshape(n, -1, 1080))
+                d = eng.encode_backward(rb, sk, cy, z, gd["_g_enc"].reshape(n, -1, 1080))
                 d_skts = d if d_skts is None else d_skts + d
         ctx.acts = None
-        if want_sk and sk.dim() == 3:
+        if want_sk and d_skts is not None and sk.dim() == 3:
             d_skts = d_skts.sum(0)                     # one pose shared by every ray of the batch
         return (None, None, d_skts, None, None, None) + tuple(grads)
 

@@ -108,6 +108,15 @@ def test_training_step_reduces_the_loss(engine, train_case, fused):
         opt.step()
         losses.append(float(loss.detach()))
     assert losses[-1] < 0.7 * losses[0], losses
+    # the packed copy is the parameters as the last optimizer.step left them: same render as a fresh module
+    rc.eval()
+    with torch.no_grad():
+        a = rc(rbt, N_samples=64, N_importance=16, kp_batch=None, skts=sk, cyls=cy, bones=None, cams=None, perturb=0., raw_noise_std=0.)
+        rc2 = raycaster_from_checkpoint({k: ({kk: vv.detach().cpu() for kk, vv in v.items()} if isinstance(v, dict) else v)
+                                         for k, v in rc.state_dict().items()}, device="cuda", precision="bf16")
+        rc2.eval()
+        b = rc2(rbt, N_samples=64, N_importance=16, kp_batch=None, skts=sk, cyls=cy, bones=None, cams=None, perturb=0., raw_noise_std=0.)
+    assert torch.equal(a["rgb_map"], b["rgb_map"]) and torch.equal(a["acc_map"], b["acc_map"])
 
 
 def test_pose_gradient_matches_oracle_autograd(engine, train_case):
