@@ -93,7 +93,9 @@ def render_path(render_poses, hwf, chunk, render_kwargs, kp=None, skts=None, cyl
             img = eng.compose_frame(H, W, x0, y0, x1, y1, ret["rgb_map"], ret["acc_map"], bg)
             disp = torch.zeros(H * W, device=dev)
             acc = torch.zeros(H * W, device=dev)
-            idx = torch.as_tensor(valid_idxs[-1], device=dev)
+            # flat pixel indices of the bbox formed on the device (a pageable H2D copy of valid_idxs would stall the
+            # launch queue behind the render)
+            idx = ((torch.arange(y0, y1, device=dev) * W)[:, None] + torch.arange(x0, x1, device=dev)[None, :]).reshape(-1)
             disp[idx] = ret["disp_map"]
             acc[idx] = ret["acc_map"]
         else:

@@ -1,0 +1,84 @@
+#!/usr/bin/env python
+"""PoseGen generation loop (BASELINE.json configs[2] / SURVEY.md §8d config 3): a batch of synthetic poses
+(axis-angle bones, seeds 0..P-1) -> device FK (`pgn_pose_to_skts`) -> cylinder bbox -> device rays -> fused render ->
+white-background frame -> HMR input (crop / resize 224 / normalise), sharded by image over the GPUs
+(`pose_idx % world_size`), weights replicated, one final all_gather of the frames.  This is the reference's
+`run_render` + the image hand-off of `train_gan` (run_gan.py:2299-2347, 2057-2071) without the PNG round trip.
+Time = max over ranks (CUDA events), gather included.  Prints one JSON line on rank 0.
+
+    python tools/generation_loop_bench.py [--poses 256]
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/generation_loop_bench.py --poses 256
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from posegen_b200 import dist as pdist, synthetic as syn                         # noqa: E402
+from posegen_b200.raycaster import raycaster_from_checkpoint                     # noqa: E402
+from posegen_b200.render import render_path                                      # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--poses", type=int, default=256)
+    ap.add_argument("--res", type=int, default=512)
+    a = ap.parse_args()
+    rank, world, local = pdist.env_rank_world()
+    pdist.init_process_group("nccl" if world > 1 else None)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    rc = raycaster_from_checkpoint(syn.synthetic_raycaster_state(0, alpha_gain=400.), device=dev, precision="bf16")
+    rc.eval()
+    eng = rc.engine(dev)
+    mine = pdist.shard_indices(a.poses, rank, world)
+    bones = np.stack([syn.synthetic_pose(s).bones for s in mine]).astype(np.float32)
+    rest = (syn.SMPL_REST_POSE * syn.BODY_SCALE).astype(np.float32)
+    c2w = syn.run_gan_c2w()
+    focal = 1000.0 * a.res / 512
+    crop = tuple(int(round(v * a.res / 512)) for v in (100, 100, 412, 412))
+    kwargs = {"ray_caster": rc}
+
+    def run(bones_np):
+        b = torch.as_tensor(bones_np, device=dev)
+        skts, kps, cyls = eng.pose_to_skts(b, rest)
+        poses = np.repeat(c2w[None], len(bones_np), 0)
+        rgbs, _, _, valid, _ = render_path(poses, (a.res, a.res, focal), 4096, kwargs, kp=kps, skts=skts, cyls=cyls,
+                                           white_bkgd=True, to_numpy=False)
+        hmr = torch.stack([eng.frame_to_hmr_input(f, crop=crop) for f in rgbs])
+        return rgbs, hmr, sum(len(v) for v in valid)
+
+    run(bones[:2])                                                     # warm-up
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    rgbs, hmr, n_rays = run(bones)
+    frames_u8 = (rgbs.clamp(0, 1) * 255).to(torch.uint8)               # what the reference writes to PNG (run_nerf.py to8b)
+    all_frames = pdist.gather_frames(frames_u8, a.poses, rank, world)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = pdist.max_over_ranks(e0.elapsed_time(e1), dev)
+    tot = torch.tensor([float(n_rays)], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(tot)
+    if rank == 0:
+        assert all_frames.shape[0] == a.poses
+        print(json.dumps({"metric": "frames_per_sec_512", "value": a.poses / ms * 1e3, "unit": "frames/s", "n_gpus": world,
+                          "poses": a.poses, "seconds": ms * 1e-3, "rays_per_sec": float(tot[0]) / ms * 1e3,
+                          "hmr_inputs": list(hmr.shape), "finite": bool(torch.isfinite(hmr).all()),
+                          "config": f"{a.poses} synthetic poses x {a.res}x{a.res} bbox renders sharded pose_idx % {world}; device FK, "
+                                    "device rays, fused bf16 render, white-bg frame, HMR input 224; one final all_gather of the uint8 frames"}),
+              flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
