@@ -161,8 +161,9 @@ PGN_API int  pgn_render_forward(pgn_context* ctx, const pgn_render_inputs* in,
 /* Training-step forward (reference core/trainer.py:232-275, eval-style sampling: perturb = 0, no noise): the same
  * fused bf16 pipeline as pgn_render_forward that additionally stores the post-ReLU activations of every MLP layer
  * (bf16) so that the weight gradients can be formed by plain GEMMs.  Per pass the dump is row-major per layer:
- * layers 0-7 (pts_linears) [rows,256] each, then layer 8 (views_linears.0) [rows,128]; rows are samples in
- * (ray, sample) order, padded to rows = pgn_activation_dump_bytes(n, pass) / 4352.  act_coarse / act_fine: device buffers of
+ * layers 0-7 (pts_linears) [rows,256] each, then layer 8 (views_linears.0) [rows,128], then the ReLU masks of
+ * layers 0-7 as bits ([layer][row][256 bits], bit c = [activation c > 0]); rows are samples in (ray, sample) order,
+ * padded to rows = pgn_activation_dump_bytes(n, pass) / 4608.  act_coarse / act_fine: device buffers of
  * pgn_activation_dump_bytes(n_rays, 0 / 1) bytes; one of them may be NULL (that pass is not dumped: a loss that reads
  * only the fine outputs sends no gradient into the coarse network).  Request out->raw0 / raw / z_fine / near_far for the backward.
  * rnd (may be NULL = deterministic eval sampling) carries the training-time randomness as explicit device arrays so
@@ -214,6 +215,19 @@ PGN_API int  pgn_encode_bf16(pgn_context* ctx, const pgn_render_inputs* in, cons
 PGN_API int  pgn_mlp_delta(pgn_context* ctx, void* dh, int32_t has_input, const void* act, int64_t m, int32_t n_cols,
                            const float* rs, int32_t rs_stride, int32_t nrs, const float* wr,
                            float* colsum, float* wsum, void* stream);
+
+/* The delta chain of the trunk backward as ONE tcgen05 kernel (what autograd runs as 8 x (GEMM + threshold_backward +
+ * sum) through HBM; core/networks/nerf.py:94-102 backwards):
+ *   dL/dh7 = dG W_fold + d_sigma w_alpha;  dZ_l = [h_l > 0] * dL/dh_l;  dL/dh_{l-1} = dZ_l W_l   (l = 7..1)
+ * dG: bf16 [m,128] = dL/d(pre-activation of views_linears.0) (from pgn_mlp_delta); d_raw: fp32 [m,4] (column 3 =
+ * d_sigma); mask: the ReLU-mask area of the activation dump of pgn_render_forward_train (starts
+ * rows * 4352 bytes into the pass's buffer, rows = mask_rows = pgn_activation_dump_bytes / 4608); w_alpha fp32 [256].
+ * wstream: the eight weights W'_j [256, K_j] bf16 (W'_0 = (W_v[:, :256] W_f)^T with K = 128; W'_j = W_l^T for
+ * l = 8 - j, K = 256, the skip layer l = 5 without its 432 input columns), each cut into K = 16 slabs laid out
+ * [K/16][2][256][8] (UMMA K-major core matrices), concatenated: 120 slabs of 8 KB.
+ * Outputs: dz bf16 [8][m][256] (dz[l] = dZ_l, row-major) and colsum fp32 [8][256] (bias gradients). */
+PGN_API int  pgn_mlp_delta_chain(pgn_context* ctx, const void* dG, const float* d_raw, const void* mask, int64_t mask_rows,
+                                 int64_t m, const void* wstream, const float* w_alpha, void* dz, float* colsum, void* stream);
 
 /* NeRF.forward (core/networks/nerf.py:133-148) on explicit encodings:
  * enc [m,1080] -> raw [m,4].  precision selects the MLP engine. */

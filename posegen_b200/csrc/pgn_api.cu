@@ -208,7 +208,8 @@ int pgn_render_forward(pgn_context* c, const pgn_render_inputs* in, const pgn_re
 
 size_t pgn_activation_dump_bytes(int64_t n_rays, int32_t pass) {
   if (n_rays < 0 || (pass != 0 && pass != 1)) return 0;
-  return (size_t)pgn_bf16_dump_rows(n_rays, pass == 0 ? PGN_S : PGN_T) * (8 * 256 + 128) * sizeof(__nv_bfloat16);
+  // activations (8 x 256 + 128 bf16 per row) followed by the ReLU masks of the 8 trunk layers (256 bits per row each)
+  return (size_t)pgn_bf16_dump_rows(n_rays, pass == 0 ? PGN_S : PGN_T) * ((8 * 256 + 128) * sizeof(__nv_bfloat16) + 8 * 32);
 }
 
 int pgn_render_forward_train(pgn_context* c, const pgn_render_inputs* in, const pgn_render_outputs* out,
@@ -309,6 +310,16 @@ int pgn_mlp_delta(pgn_context* c, void* dh, int32_t has_input, const void* act, 
   if (!has_input && nrs == 0) return fail(PGN_E_INVALID, "pgn_mlp_delta: nothing to do");
   PGN_CUDA(cudaSetDevice(c->cfg.device));
   PGN_CUDA(pgn_launch_mlp_delta(dh, has_input, act, m, n_cols, rs, rs_stride, nrs, wr, colsum, wsum, c->num_sms, (cudaStream_t)stream));
+  c->launches++;
+  return PGN_OK;
+}
+
+int pgn_mlp_delta_chain(pgn_context* c, const void* dG, const float* d_raw, const void* mask, int64_t mask_rows, int64_t m,
+                        const void* wstream, const float* w_alpha, void* dz, float* colsum, void* stream) {
+  if (!c || !dG || !d_raw || !mask || !wstream || !w_alpha || !dz || !colsum || m < 0 || mask_rows < m)
+    return fail(PGN_E_INVALID, "pgn_mlp_delta_chain: bad argument");
+  PGN_CUDA(cudaSetDevice(c->cfg.device));
+  PGN_CUDA(pgn_launch_delta_chain(dG, d_raw, mask, mask_rows, m, wstream, w_alpha, dz, colsum, c->d_status, c->num_sms, (cudaStream_t)stream));
   c->launches++;
   return PGN_OK;
 }

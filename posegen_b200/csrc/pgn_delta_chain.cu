@@ -1,0 +1,294 @@
+// Fused delta chain of the A-NeRF trunk backward (training step / GAN step) on tcgen05.
+//
+// What autograd does per trunk layer (core/networks/nerf.py:94-102 backwards) is a GEMM dL/dh_{l-1} = dZ_l W_l followed
+// by a ReLU mask; done layer by layer through HBM that is 5 passes over a [rows,256] matrix per layer.  Here one CTA
+// keeps a 256-row block of deltas in shared memory for the whole chain:
+//
+//     dG [rows,128]  --W_fold-->  dL/dh7 (+ d_sigma w_alpha)  --mask h7-->  dZ7  --W_7--> ... --W_1--> dZ0
+//
+// Eight tensor-core layers per block (K = 128 once, K = 256 seven times, N = 256, fp32 accumulators in TMEM); every
+// dZ_l is written to HBM exactly once (row-major bf16, the operand of the weight-gradient GEMMs) and nothing is read
+// back: the ReLU masks come from the 1-bit-per-activation dump of the forward kernel (32 B per row and layer).
+// Algorithmic bytes per row: 8 x 512 B written + 8 x 32 B masks + 256 B dG + 4 B d_sigma = 4.6 KB (HBM-bound:
+// 0.47 TFLOP over 2.0 GB for a 3,072-ray batch).
+//
+// Roles (512 threads, 1 CTA per SM, persistent over row blocks): warp 0 lane 0 streams the weights of all eight layers
+// in consumption order through a 10 x 8 KB ring with cp.async.bulk (one K-step slab = [2][256][8] bf16, UMMA K-major
+// SWIZZLE_NONE); warp 1 lane 0 issues the MMAs (UMMA M = 128, two row tiles share every weight slab, cta_group::1);
+// warps 4-11 drain the accumulators (tcgen05.ld 32x32b), add the sigma head's outer product on the first layer, mask,
+// pack to bf16 and store the next layer's A operand into shared memory ([k/8][row][8]); warps 12-15 then read that
+// tile back from shared memory - while the tensor core already runs the next layer on it - and write the dZ rows to
+// HBM (4 rows x 128 B per warp store: full lines) and accumulate the bias gradients (column sums; every column has
+// one owner thread, no atomics).  Draining and storing from the accumulator-owning threads directly costs 2x: a
+// thread owns one row, so each of its stores touches 32 different lines and the column sums need 128 shuffles.
+#include <cstdlib>
+#include "pgn_common.cuh"
+#include "pgn_kernels.h"
+#include "pgn_umma.cuh"
+
+using namespace pgn;
+
+namespace {
+
+constexpr int kTile = 128;                       // rows per UMMA tile
+constexpr int kTiles = 2;                        // row tiles per CTA block (share the weight slabs)
+constexpr int kBlockRows = kTile * kTiles;
+constexpr int kRun = kTile * 16;                 // bytes of one 8-wide K run of a tile
+constexpr int kABytes = 32 * kRun;               // 64 KB: [256/8 runs][128 rows][8] bf16
+constexpr int kSlabBytes = 2 * 256 * 16;         // one K = 16 step of a [256 x K] weight: [2][256][8] bf16
+constexpr int kStages = 10;                     // 80 KB of weight slabs in flight (a 16-slab layer is 128 KB)
+constexpr int kLayers = 8;                       // fold layer (K = 128) + W_7 .. W_1 (K = 256)
+constexpr int kSlabsPerBlock = 8 + 7 * 16;       // 120
+constexpr int kThreads = 512;
+
+struct __align__(1024) ChainSmem {
+  uint8_t a[kTiles][kABytes];
+  uint8_t w[kStages][kSlabBytes];
+  float colsum[kLayers][256];
+  float w_alpha[256];
+  uint64_t w_full[kStages], w_empty[kStages], acc_full, act_ready[kTiles], cs_ready[kTiles], cs_done[kTiles];
+  uint32_t tmem_slot;
+};
+
+__device__ __forceinline__ void mbar_arrive_local(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__global__ void __launch_bounds__(kThreads, 1)
+pgn_delta_chain_kernel(const uint4* __restrict__ dG, const float* __restrict__ d_raw, const uint4* __restrict__ mask,
+                       long long mask_rows, long long m, const uint8_t* __restrict__ wstream,
+                       const float* __restrict__ w_alpha, uint4* __restrict__ dz, float* __restrict__ colsum_g,
+                       int* __restrict__ status_g, int dbg) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  ChainSmem& sm = *reinterpret_cast<ChainSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  volatile int* status = status_g;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long n_blocks = (m + kBlockRows - 1) / kBlockRows;
+
+  if (tid == 0) {
+    for (int i = 0; i < kStages; ++i) { mbar_init(&sm.w_full[i], 1); mbar_init(&sm.w_empty[i], 1); }
+    mbar_init(&sm.acc_full, 1);
+    for (int t = 0; t < kTiles; ++t) { mbar_init(&sm.act_ready[t], 8); mbar_init(&sm.cs_ready[t], 8); mbar_init(&sm.cs_done[t], 4); }
+    fence_mbar_init();
+  }
+  for (int i = tid; i < kLayers * 256; i += kThreads) (&sm.colsum[0][0])[i] = 0.f;
+  for (int i = tid; i < 256; i += kThreads) sm.w_alpha[i] = w_alpha[i];
+  if (warp == 0) { tmem_alloc(&sm.tmem_slot, 512); tmem_relinquish(); }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = sm.tmem_slot;
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- weight producer
+    if (lane == 0) {
+      uint32_t slab = 0;
+      for (long long blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+        for (int i = 0; i < kSlabsPerBlock; ++i, ++slab) {
+          const uint32_t st = slab % kStages, use = slab / kStages;
+          if (use > 0 && !mbar_wait(&sm.w_empty[st], (use - 1) & 1, status, 701)) return;
+          mbar_expect_tx(&sm.w_full[st], kSlabBytes);
+          bulk_g2s_s(smem_u32(sm.w[st]), wstream + (size_t)i * kSlabBytes, kSlabBytes, smem_u32(&sm.w_full[st]));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(kTile, 256);
+      uint32_t slab = 0, ready_phase = 0;
+      for (long long blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+        for (int j = 0; j < kLayers; ++j, ++ready_phase) {
+          for (int t = 0; t < kTiles; ++t)
+            if (!mbar_wait(&sm.act_ready[t], ready_phase & 1, status, 702)) return;
+          tc_fence_after_sync();
+          const int nks = j == 0 ? 8 : 16;
+          for (int ks = 0; ks < nks; ++ks, ++slab) {
+            const uint32_t st = slab % kStages, use = slab / kStages;
+            if (!mbar_wait(&sm.w_full[st], use & 1, status, 703)) return;
+            tc_fence_after_sync();
+            const uint64_t bd = umma_smem_desc(smem_u32(sm.w[st]), 256 * 16, 128);
+#pragma unroll
+            for (int t = 0; t < kTiles; ++t) {
+              const uint64_t ad = umma_smem_desc(smem_u32(sm.a[t]) + (uint32_t)ks * 2 * kRun, kRun, 128);
+              umma_bf16(tmem + (uint32_t)t * 256, ad, bd, idesc, ks > 0 ? 1u : 0u);
+            }
+            umma_commit(&sm.w_empty[st]);
+          }
+          umma_commit(&sm.acc_full);
+        }
+      }
+    }
+  } else if (warp >= 12) {
+    // ---------------------------------------------------------------- dZ store + bias-gradient group (128 threads)
+    // warp w owns the 8 runs (64 columns) 8w .. 8w+7 of a tile; lane = (row & 3) + 4 * (run & 7)
+    const int dw = warp - 12, rr = lane & 3, run = dw * 8 + (lane >> 2);
+    uint32_t phase = 0;
+    for (long long blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+      const long long r0 = blk * kBlockRows;
+      for (int j = 0; j < kLayers; ++j, ++phase) {
+        const int L = 7 - j;
+        for (int t = 0; t < kTiles; ++t) {
+          if (!mbar_wait(&sm.cs_ready[t], phase & 1, status, 705)) return;
+          const uint32_t src = smem_u32(sm.a[t]) + (uint32_t)run * kRun + rr * 16;
+          const long long g0 = r0 + t * kTile + rr;
+          uint4* out = dz + ((size_t)L * m + (size_t)g0) * 32 + run;
+          float acc[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+#pragma unroll 8
+          for (int i = 0; i < 32; ++i) {
+            const uint4 v = lds128(src + (uint32_t)i * 64);
+            if (g0 + 4 * i < m && !(dbg & 2)) out[(size_t)i * 128] = v;
+            const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              acc[2 * e] += __uint_as_float(w4[e] << 16);
+              acc[2 * e + 1] += __uint_as_float(w4[e] & 0xffff0000u);
+            }
+          }
+          if (!(dbg & 1)) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 1);
+              acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 2);
+            }
+            if (rr == 0) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) sm.colsum[L][run * 8 + e] += acc[e];
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive_local(&sm.cs_done[t]);
+        }
+      }
+    }
+    // this thread's columns of the CTA's bias partials -> global
+    if (rr == 0) {
+      for (int L = 0; L < kLayers; ++L)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) atomicAdd(colsum_g + L * 256 + run * 8 + e, sm.colsum[L][run * 8 + e]);
+    }
+  } else if (warp >= 4) {
+    // ---------------------------------------------------------------- epilogue / staging group (256 threads)
+    const int ew = warp - 4, q = ew & 3, half = ew >> 2;
+    const int et = tid - 128;                       // 0..255
+    const int row = q * 32 + lane;                  // TMEM lane = row of the tile
+    const int col0 = half * 128;
+    uint32_t acc_phase = 0, csd_phase = 0;          // csd_phase: completed store/sum passes over an A tile waited for so far
+    bool first = true;
+    for (long long blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+      const long long r0 = blk * kBlockRows;
+      // stage in dG: [256 rows x 128 columns] -> the first 16 runs of both A tiles (once the store group has read the
+      // previous block's last deltas out of them)
+      {
+        const int srow = et & 127, sh = et >> 7;    // row of a tile, 64-column half
+        if (!first) {
+          for (int t = 0; t < kTiles; ++t)
+            if (!mbar_wait(&sm.cs_done[t], csd_phase & 1, status, 706)) return;
+          ++csd_phase;
+        }
+        first = false;
+#pragma unroll
+        for (int t = 0; t < kTiles; ++t) {
+          const long long gr = r0 + t * kTile + srow;
+          const uint32_t dst = smem_u32(sm.a[t]) + (uint32_t)(sh * 8) * kRun + srow * 16;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (gr < m) v = __ldg(dG + (size_t)gr * 16 + sh * 8 + i);
+            sts128(dst + (uint32_t)i * kRun, v.x, v.y, v.z, v.w);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_local(&sm.act_ready[t]);
+        }
+      }
+      float dsig[kTiles];
+#pragma unroll
+      for (int t = 0; t < kTiles; ++t) {
+        const long long gr = r0 + t * kTile + row;
+        dsig[t] = gr < m ? __ldg(d_raw + (size_t)gr * 4 + 3) : 0.f;
+      }
+      for (int j = 0; j < kLayers; ++j, ++acc_phase) {
+        const int L = 7 - j;                        // this layer's output is dL/dh_L; its mask is [h_L > 0]
+        uint4 mk[kTiles];
+#pragma unroll
+        for (int t = 0; t < kTiles; ++t) {
+          const long long gr = r0 + t * kTile + row;
+          mk[t] = gr < m ? __ldg(mask + ((size_t)L * mask_rows + gr) * 2 + half) : make_uint4(0u, 0u, 0u, 0u);
+        }
+        if (!mbar_wait(&sm.acc_full, acc_phase & 1, status, 704)) return;
+        tc_fence_after_sync();
+        if (j > 0) {                                 // the previous deltas have been stored / summed out of the A tiles
+          for (int t = 0; t < kTiles; ++t)
+            if (!mbar_wait(&sm.cs_done[t], csd_phase & 1, status, 707)) return;
+          ++csd_phase;
+        }
+#pragma unroll
+        for (int t = 0; t < kTiles; ++t) {
+          const uint32_t taddr = tmem + (uint32_t)t * 256 + ((uint32_t)(q * 32) << 16) + (uint32_t)col0;
+          const uint32_t dst0 = smem_u32(sm.a[t]) + (uint32_t)(col0 >> 3) * kRun + row * 16;
+          const uint32_t mw[4] = {mk[t].x, mk[t].y, mk[t].z, mk[t].w};
+          uint32_t v[2][16];
+          tmem_ld_32x16(taddr, v[0]);
+#pragma unroll
+          for (int b = 0; b < 8; ++b) {
+            tmem_ld_wait();
+            if (b + 1 < 8) tmem_ld_32x16(taddr + (uint32_t)(b + 1) * 16, v[(b + 1) & 1]);
+            const uint32_t* vb = v[b & 1];
+            const uint32_t bits = mw[b >> 1] >> ((b & 1) * 16);
+            float x[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float p = __uint_as_float(vb[i]);
+              if (j == 0) p = fmaf(dsig[t], sm.w_alpha[col0 + b * 16 + i], p);
+              x[i] = ((bits >> i) & 1u) ? p : 0.f;
+            }
+            uint32_t pk[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) pk[i] = pack_bf16x2(x[2 * i], x[2 * i + 1]);
+            sts128(dst0 + (uint32_t)(2 * b) * kRun, pk[0], pk[1], pk[2], pk[3]);
+            sts128(dst0 + (uint32_t)(2 * b + 1) * kRun, pk[4], pk[5], pk[6], pk[7]);
+          }
+          tc_fence_before_sync();
+          if (j + 1 < kLayers) fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (j + 1 < kLayers) mbar_arrive_local(&sm.act_ready[t]);      // next layer's A operand (and a free accumulator)
+            mbar_arrive_local(&sm.cs_ready[t]);                            // dZ_L of this tile is in shared memory
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after_sync(); tmem_dealloc(tmem, 512); }
+}
+
+}  // namespace
+
+cudaError_t pgn_launch_delta_chain(const void* dG, const float* d_raw, const void* mask, long long mask_rows, long long m,
+                                   const void* wstream, const float* w_alpha, void* dz, float* colsum, int* status,
+                                   int num_sms, cudaStream_t stream) {
+  cudaError_t e = cudaMemsetAsync(colsum, 0, sizeof(float) * kLayers * 256, stream);
+  if (e != cudaSuccess || m == 0) return e;
+  const size_t smem = sizeof(ChainSmem) + 1024;
+  static bool configured = false;
+  if (!configured) {
+    e = cudaFuncSetAttribute(pgn_delta_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  static const int dbg = getenv("PGN_CHAIN_DEBUG") ? atoi(getenv("PGN_CHAIN_DEBUG")) : 0;   // bring-up only: 1 no column sums, 2 no dZ stores
+  const long long n_blocks = (m + kBlockRows - 1) / kBlockRows;
+  const unsigned grid = (unsigned)(n_blocks < num_sms ? n_blocks : num_sms);
+  pgn_delta_chain_kernel<<<grid, kThreads, smem, stream>>>(reinterpret_cast<const uint4*>(dG), d_raw,
+                                                           reinterpret_cast<const uint4*>(mask), mask_rows, m,
+                                                           reinterpret_cast<const uint8_t*>(wstream), w_alpha,
+                                                           reinterpret_cast<uint4*>(dz), colsum, status, dbg);
+  return cudaGetLastError();
+}

@@ -181,8 +181,8 @@ class Engine:
     def render_train(self, ray_batch, skts, cyls, pose_idx=None, nanfill_chunk=0, rand=None, dump_coarse=True):
         """pgn_render_forward_train: the fused bf16 forward + per-layer activation dump for the weight gradients.
         Returns (outputs incl. the taps the backward needs, {"c": dump, "f": dump}); dump[p] is a flat bf16 buffer of
-        rows * 2176 elements: layers 0-7 row-major [rows,256] each, then the view layer [rows,128] (`act_layer`
-        returns the views), rows in (ray, sample) order.
+        rows * 2304 elements: layers 0-7 row-major [rows,256] each, then the view layer [rows,128], then the ReLU mask
+        bits of layers 0-7 (`train.act_layer` / `train.act_masks` return the views), rows in (ray, sample) order.
         rand: optional dict of CUDA fp32 tensors t_rand [n,64], u_is [n,16], noise0 [n,64], noise [n,80] (training-time
         randomness drawn by the caller; missing keys = deterministic)."""
         inp, keep = self._inputs(ray_batch, skts, cyls, pose_idx, nanfill_chunk, "bf16")
@@ -265,6 +265,25 @@ class Engine:
                                               _ptr(rs) if nrs else None, rs.stride(0) if nrs else 0, nrs, _ptr(wr) if nrs else None,
                                               _ptr(colsum), _ptr(wsum), self._stream()))
         return colsum, wsum
+
+    def mlp_delta_chain(self, dG, d_raw, mask, mask_rows, wstream, w_alpha):
+        """pgn_mlp_delta_chain: dG bf16 [m,128], d_raw fp32 [m,4], mask = the mask area of the activation dump ->
+        (dz bf16 [8,m,256] with dz[l] = dZ_l, colsum fp32 [8,256] = the trunk's bias gradients)."""
+        m = dG.shape[0]
+        if dG.dtype != torch.bfloat16 or not dG.is_contiguous() or dG.shape[1] != 128 or not dG.is_cuda:
+            raise ValueError("dG must be a contiguous CUDA bf16 [m,128] matrix")
+        if d_raw.dtype != torch.float32 or not d_raw.is_contiguous() or tuple(d_raw.shape) != (m, 4):
+            raise ValueError("d_raw must be contiguous fp32 [m,4]")
+        if wstream.dtype != torch.bfloat16 or wstream.numel() != 120 * 4096 or not wstream.is_contiguous():
+            raise ValueError("wstream must be the 120-slab bf16 weight stream (train.chain_wstream)")
+        if mask.numel() * mask.element_size() < mask_rows * 256 or mask_rows < m:
+            raise ValueError("mask area too small")
+        dz = torch.empty((8, m, 256), dtype=torch.bfloat16, device=dG.device)
+        colsum = torch.empty((8, 256), dtype=torch.float32, device=dG.device)
+        with torch.cuda.device(dG.device):
+            _lib.check(self.lib.pgn_mlp_delta_chain(self.handle, _ptr(dG), _ptr(d_raw), _ptr(mask), mask_rows, m, _ptr(wstream),
+                                                    _ptr(w_alpha), _ptr(dz), _ptr(colsum), self._stream()))
+        return dz, colsum
 
     def mlp(self, net_id, enc, precision="bf16"):
         _check_f32_cuda(enc, "enc")

@@ -27,7 +27,8 @@ import numpy as np
 import torch
 
 from . import synthetic as syn
-from .train import S, T, mlp_backward
+from . import train
+from .train import T, mlp_backward
 
 
 class _FrameRenderFn(torch.autograd.Function):
@@ -58,7 +59,7 @@ class _FrameRenderFn(torch.autograd.Function):
             d_raw = eng.composite_backward(rb, sk, cy, ret["raw"], z, g_rgb.index_select(0, idx).contiguous(),
                                            g_acc.index_select(0, idx).contiguous())
             gd = mlp_backward(pd, None, acts["f"], d_raw.reshape(-1, 4), eng.mlp_delta, want_input_grad=True,
-                              want_weight_grad=False)
+                              want_weight_grad=False, chain=eng.mlp_delta_chain if train.USE_DELTA_CHAIN else None)
             d = eng.encode_backward(rb, sk, cy, z, gd["_g_enc"].reshape(rb.shape[0], T, 1080))
             d_skts += d.sum(0)
             del acts, gd, d

@@ -25,6 +25,7 @@ import torch
 import torch.distributed as dist
 
 S, T = 64, 80
+USE_DELTA_CHAIN = True        # trunk backward through pgn_mlp_delta_chain (False: layer by layer, for A/B runs)
 PARAM_ORDER = [f"pts_linears.{i}.{k}" for i in range(8) for k in ("weight", "bias")] + \
     [f"{m}.{k}" for m in ("alpha_linear", "feature_linear", "views_linears.0", "rgb_linear") for k in ("weight", "bias")]
 
@@ -39,17 +40,37 @@ def _mm32(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     return torch.mm(a.float(), b.float())
 
 
+ACT_ROW_ELEMS = 2304          # bf16 elements per dump row: 8 x 256 + 128 activations + 8 x 16 (the ReLU mask bits)
+
+
 def act_layer(acts: torch.Tensor, l: int, m: int) -> torch.Tensor:
     """Activation matrix of layer l (0..7: 256 columns, 8: view layer, 128) for the first m rows of the kernel's
     row-major dump (a view, no copy): [m, cols] bf16."""
-    rows = acts.numel() // 2176
+    rows = acts.numel() // ACT_ROW_ELEMS
     if l < 8:
         return acts[l * rows * 256:(l + 1) * rows * 256].view(rows, 256)[:m]
-    return acts[8 * rows * 256:].view(rows, 128)[:m]
+    return acts[8 * rows * 256:rows * 2176].view(rows, 128)[:m]
+
+
+def act_masks(acts: torch.Tensor):
+    """(mask area of the dump, rows): [8 layers][rows][256 bits], the operand of `pgn_mlp_delta_chain`."""
+    rows = acts.numel() // ACT_ROW_ELEMS
+    return acts[rows * 2176:], rows
+
+
+def chain_wstream(P: Dict[str, torch.Tensor]) -> torch.Tensor:
+    """The eight weights of the delta chain in the slab layout `pgn_mlp_delta_chain` streams (include/posegen_b200.h):
+    W'_0 = (W_v[:, :256] W_f)^T [256,128], W'_j = W_l^T [256,256] for l = 7..1 (layer 5 without its 432 skip columns),
+    each as [K/16][2][256][8] bf16."""
+    fold = P["views_linears.0.weight"][:, :256] @ P["feature_linear.weight"]
+    mats = [fold.t()] + [(P[f"pts_linears.{l}.weight"][:, 432:] if l == 5 else P[f"pts_linears.{l}.weight"]).t()
+                         for l in range(7, 0, -1)]
+    return torch.cat([w.to(torch.bfloat16).reshape(256, -1, 2, 8).permute(1, 2, 0, 3).reshape(-1) for w in mats])
 
 
 def mlp_backward(params: Dict[str, torch.Tensor], enc: torch.Tensor, acts: torch.Tensor, d_raw: torch.Tensor,
-                 fuse: Callable, want_input_grad: bool = False, want_weight_grad: bool = True) -> Dict[str, torch.Tensor]:
+                 fuse: Callable, want_input_grad: bool = False, want_weight_grad: bool = True,
+                 chain: Callable | None = None) -> Dict[str, torch.Tensor]:
     """Weight gradients of one NeRF MLP (core/networks/nerf.py:94-148).
 
     params: fp32 nn.Linear tensors; enc [m,1080] bf16 network input (`pgn_encode_bf16`; may be None when
@@ -60,6 +81,9 @@ def mlp_backward(params: Dict[str, torch.Tensor], enc: torch.Tensor, acts: torch
     gradients are produced in fp32.  `feature_linear` has no activation (nerf.py:125-128), so it never shows up at
     batch size: with T = dG^T h7 its gradients and those of the feature block of `views_linears.0` are
     [128,256]-sized products, and dL/d h7 reads the folded weight W_v[:, :256] @ W_f.
+    `chain(dG, d_raw, mask, mask_rows, wstream, w_alpha)` is `Engine.mlp_delta_chain` (`pgn_mlp_delta_chain`): the
+    whole trunk chain dG -> dZ_7 .. dZ_0 (+ bias gradients) as one tcgen05 kernel; without it the chain runs layer by
+    layer (a cuBLAS GEMM and a `fuse` pass per layer), which is also what the host-logic test exercises.
     Returns {name: fp32 gradient}; with want_input_grad also "_g_enc" [m,1080] = dL/d(network input)."""
     m = d_raw.shape[0]
     bf = torch.bfloat16
@@ -88,6 +112,27 @@ def mlp_backward(params: Dict[str, torch.Tensor], enc: torch.Tensor, acts: torch
     g_in = torch.empty((m, 1080), dtype=torch.float32, device=d_raw.device) if want_input_grad else None
     if want_input_grad:
         g_in[:, 432:] = torch.mm(dG, W_v[:, 256:].to(bf))
+    if chain is not None:
+        # trunk: one fused kernel for the eight deltas; the weight gradients are GEMMs over (dZ_l, h_{l-1})
+        mask, mask_rows = act_masks(acts)
+        dz, colsum = chain(dG, d_raw, mask, mask_rows, chain_wstream(P), P["alpha_linear.weight"].reshape(-1).float().contiguous())
+        if wg:
+            g["alpha_linear.weight"] = _mm32(d_raw[:, 3:4].to(bf).t(), H[7])
+            g["alpha_linear.bias"] = d_raw[:, 3:4].sum(0)
+            for l in range(8):
+                dZt = dz[l].t()
+                if l == 0:
+                    g["pts_linears.0.weight"] = _mm32(dZt, x_p)
+                elif l == 5:
+                    g["pts_linears.5.weight"] = torch.cat([_mm32(dZt, x_p), _mm32(dZt, H[4])], 1)
+                else:
+                    g[f"pts_linears.{l}.weight"] = _mm32(dZt, H[l - 1])
+                g[f"pts_linears.{l}.bias"] = colsum[l]
+        if want_input_grad:
+            g_in[:, :432] = torch.mm(dz[5], W["pts_linears.5.weight"][:, :432])
+            g_in[:, :432] += torch.mm(dz[0], W["pts_linears.0.weight"])
+            g["_g_enc"] = g_in
+        return g
     # sigma head + last trunk layer: dL/d h7 = dG (W_vf W_f) + d_sigma w_alpha
     dH = torch.mm(dG, (W_vf @ W_f).to(bf))
     bias, g_alpha = fuse(dH, H[7], d_raw[:, 3:4], P["alpha_linear.weight"], True, wg)
@@ -161,7 +206,8 @@ class _RenderTrainFn(torch.autograd.Function):
             d_raw = eng.composite_backward(rb, sk, cy, raw_p, z, gr, ga, noise=nz)
             enc = eng.encode_bf16(rb, sk, cy, z).reshape(-1, 1080) if want_w else None
             pd = dict(net.named_parameters())
-            gd = mlp_backward(pd, enc, acts, d_raw.reshape(-1, 4), eng.mlp_delta, want_input_grad=want_sk, want_weight_grad=want_w)
+            gd = mlp_backward(pd, enc, acts, d_raw.reshape(-1, 4), eng.mlp_delta, want_input_grad=want_sk, want_weight_grad=want_w,
+                              chain=eng.mlp_delta_chain if USE_DELTA_CHAIN else None)
             grads += [gd[k].reshape(pd[k].shape).to(pd[k].dtype) for k in PARAM_ORDER] if want_w else [None] * len(PARAM_ORDER)
             if want_sk:          # pose gradient: dL/d(network input) -> dL/d skts (per ray), both passes add up
                 d = eng.encode_backward(rb, sk, cy, z, gd["_g_enc"].reshape(n, -1, 1080))

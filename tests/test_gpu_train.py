@@ -249,3 +249,57 @@ def test_encode_bf16_is_the_rounded_fp32_encoding(engine, train_case):
     b = engine.encode_bf16(rbt, sk, cy, z)
     assert b.dtype == torch.bfloat16 and b.shape == a.shape
     assert bool(((a - b.float()).abs() <= 2.0 ** -8 * a.abs() + 3e-4).all())
+
+
+def test_forward_dump_masks_match_the_activations(engine, train_case):
+    """The 1-bit ReLU masks the training forward dumps behind the activations are [activation > 0] of the same dump."""
+    from posegen_b200.train import act_layer, act_masks
+    frame, ckpt, rb, tgt = train_case
+    engine.load_checkpoint(ckpt)
+    dev = torch.device("cuda")
+    n = 100                                                        # ragged: not a multiple of the 8-ray groups
+    ret, acts = engine.render_train(torch.as_tensor(rb[:n], device=dev), torch.as_tensor(frame.pose.skts, device=dev),
+                                    torch.as_tensor(frame.pose.cyl, device=dev))
+    engine.check_status()
+    for key, s in (("c", 64), ("f", 80)):
+        m = n * s
+        mask, rows = act_masks(acts[key])
+        bits = mask.view(torch.int32).view(8, rows, 8)[:, :m]                       # 8 words of 32 columns per row
+        got = ((bits[..., None] >> torch.arange(32, device=dev, dtype=torch.int32)) & 1).reshape(8, m, 256).bool()
+        for l in range(8):
+            assert torch.equal(got[l], act_layer(acts[key], l, m) > 0), (key, l)
+
+
+def test_delta_chain_kernel_matches_layerwise_reference(engine):
+    """pgn_mlp_delta_chain (eight tcgen05 layers per 256-row block, masks from bits, bias column sums) against the same
+    chain in torch with bf16 rounding at the same places (fp32 accumulation, bf16 deltas), ragged row counts."""
+    from posegen_b200.train import chain_wstream
+    dev = torch.device("cuda")
+    g = torch.Generator(device="cuda").manual_seed(3)
+    P = {k: torch.as_tensor(v, device=dev) for k, v in syn.synthetic_nerf_state(7).items()}
+    for m in (256, 1000, 37 * 1024 + 5):
+        rows = ((m + 1279) // 1280) * 1280
+        dG = (torch.randn((m, 128), device=dev, generator=g) * 0.1).to(torch.bfloat16)
+        d_raw = torch.randn((m, 4), device=dev, generator=g) * 0.1
+        act = torch.rand((8, rows, 256), device=dev, generator=g) > 0.4
+        words = (act.view(8, rows, 8, 32).to(torch.int64) << torch.arange(32, device=dev)).sum(-1)
+        mask = words.to(torch.int32)                                                   # wraps bit 31 into the sign
+        mask = torch.where(words >= 2 ** 31, words - 2 ** 32, words).to(torch.int32).contiguous()
+        dz, colsum = engine.mlp_delta_chain(dG, d_raw.contiguous(), mask, rows, chain_wstream(P),
+                                            P["alpha_linear.weight"].reshape(-1).float().contiguous())
+        engine.check_status()
+        bf = torch.bfloat16
+        fold = (P["views_linears.0.weight"][:, :256] @ P["feature_linear.weight"]).to(bf).float()
+        pre = dG.float() @ fold + d_raw[:, 3:4] * P["alpha_linear.weight"].float()
+        for l in range(7, -1, -1):
+            z = torch.where(act[l, :m], pre, torch.zeros((), device=dev))
+            zb = z.to(bf)
+            err = (dz[l].float() - zb.float()).abs()
+            tol = 2.0 ** -7 * zb.float().abs() + 1e-5                                   # one bf16 rounding (accumulation order)
+            assert bool((err <= tol).all()), (m, l, float(err.max()))
+            ref = dz[l].double().sum(0)                # the bias gradient is the column sum of the bf16 deltas it wrote
+            assert float((colsum[l].double() - ref).abs().max()) <= 2e-4 * max(1.0, float(ref.abs().max())), (m, l)
+            assert float((colsum[l].double() - z.double().sum(0)).abs().max()) <= 1e-2 * max(1.0, float(ref.abs().max())), (m, l)
+            if l > 0:
+                W = P[f"pts_linears.{l}.weight"][:, 432:] if l == 5 else P[f"pts_linears.{l}.weight"]
+                pre = dz[l].float() @ W.to(bf).float()                                  # continue from the kernel's own bf16 deltas

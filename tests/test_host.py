@@ -169,10 +169,10 @@ def test_mlp_backward_matches_autograd_on_cpu():
         feat = torch.nn.functional.linear(acts[7], net["feature_linear.weight"], net["feature_linear.bias"])
         g = torch.relu(torch.nn.functional.linear(torch.cat([feat, x_v], -1), net["views_linears.0.weight"], net["views_linears.0.bias"]))
         rows = 256
-        dump = torch.zeros((rows * 2176,), dtype=torch.bfloat16)
+        dump = torch.zeros((rows * 2304,), dtype=torch.bfloat16)            # 2176 activations + 128 (mask bits, unused here) per row
         for l in range(8):
             dump[l * rows * 256:(l + 1) * rows * 256].view(rows, 256)[:m] = acts[l].to(torch.bfloat16)
-        dump[8 * rows * 256:].view(rows, 128)[:m] = g.to(torch.bfloat16)
+        dump[8 * rows * 256:rows * 2176].view(rows, 128)[:m] = g.to(torch.bfloat16)
 
     def fuse(dh, act, rs, wr, has_input, want_wsum):          # what pgn_mlp_delta computes, in torch
         pre = dh.float() if has_input else torch.zeros(dh.shape)

@@ -1,0 +1,20 @@
+import sys, torch
+sys.path.insert(0, '/root/repo')
+from posegen_b200 import synthetic as syn
+from posegen_b200.engine import Engine
+from posegen_b200.train import chain_wstream
+eng = Engine(); dev = torch.device('cuda')
+P = {k: torch.as_tensor(v, device=dev) for k, v in syn.synthetic_nerf_state(7).items()}
+m = 3072 * 80; rows = m
+dG = (torch.randn((m, 128), device=dev) * 0.1).to(torch.bfloat16)
+d_raw = torch.randn((m, 4), device=dev)
+mask = torch.randint(-2**31, 2**31 - 1, (8, rows, 8), device=dev, dtype=torch.int32)
+ws = chain_wstream(P); wa = P["alpha_linear.weight"].reshape(-1).float().contiguous()
+for _ in range(3): eng.mlp_delta_chain(dG, d_raw, mask, rows, ws, wa)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(10): eng.mlp_delta_chain(dG, d_raw, mask, rows, ws, wa)
+e1.record(); torch.cuda.synchronize()
+print(sys.argv[1:], "chain us per call:", e0.elapsed_time(e1) * 100, "rows", m)
+eng.check_status()
