@@ -246,6 +246,11 @@ PGN_API int  pgn_composite(pgn_context* ctx, const pgn_render_inputs* in, const 
 PGN_API int  pgn_encode_backward(pgn_context* ctx, const pgn_render_inputs* in, const float* z, int32_t n_z,
                                  const float* g_enc, float* d_skts, void* stream);
 
+/* the same with dL/d(network input) as the training backward produces it: two bf16 GEMM outputs, g_xp [n * n_z, 432]
+ * (channels [0,432): v-embed | r) and g_d [n * n_z, 648] (view embed), no fp32 [.,1080] matrix in between. */
+PGN_API int  pgn_encode_backward_bf16(pgn_context* ctx, const pgn_render_inputs* in, const float* z, int32_t n_z,
+                                      const void* g_xp, const void* g_d, float* d_skts, void* stream);
+
 /* backward of NeRF.raw2outputs for the training step (core/trainer.py:321-370 reads rgb_map and acc_map):
  * g_rgb [n,3] = dL/d rgb_map, g_acc [n] = dL/d acc_map (may be NULL) -> d_raw [n,s,4] = dL/d raw.
  * No gradient flows through z (the importance samples are detached, core/utils/ray_utils.py:286). */

@@ -361,6 +361,19 @@ int pgn_encode_backward(pgn_context* c, const pgn_render_inputs* in, const float
   return PGN_OK;
 }
 
+int pgn_encode_backward_bf16(pgn_context* c, const pgn_render_inputs* in, const float* z, int32_t n_z, const void* g_xp,
+                             const void* g_d, float* d_skts, void* stream) {
+  int rc = check_inputs(c, in, "pgn_encode_backward_bf16");
+  if (rc) return rc;
+  if (!z || !g_xp || !g_d || !d_skts || n_z <= 0) return fail(PGN_E_INVALID, "pgn_encode_backward_bf16: bad argument");
+  if (!c->have_sc) return fail(PGN_E_STATE, "pgn_encode_backward_bf16: scalars not set");
+  PGN_CUDA(cudaSetDevice(c->cfg.device));
+  PGN_CUDA(pgn_launch_encode_backward_bf16(make_refs(in), c->d_sc, z, n_z, reinterpret_cast<const __nv_bfloat16*>(g_xp),
+                                           reinterpret_cast<const __nv_bfloat16*>(g_d), d_skts, (cudaStream_t)stream));
+  c->launches++;
+  return PGN_OK;
+}
+
 int pgn_composite_backward(pgn_context* c, const pgn_render_inputs* in, const float* raw, const float* z, int32_t s,
                            const float* g_rgb, const float* g_acc, const float* noise, float* d_raw, void* stream) {
   int rc = check_inputs(c, in, "pgn_composite_backward");

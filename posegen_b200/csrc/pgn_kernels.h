@@ -82,6 +82,8 @@ cudaError_t pgn_launch_composite_backward(const PgnRayRefs& rays, const PgnScala
                                           cudaStream_t stream);
 cudaError_t pgn_launch_encode_backward(const PgnRayRefs& rays, const PgnScalars* sc_dev, const float* z, int n_z,
                                        const float* g_enc, float* d_skts, cudaStream_t stream);
+cudaError_t pgn_launch_encode_backward_bf16(const PgnRayRefs& rays, const PgnScalars* sc_dev, const float* z, int n_z,
+                                            const __nv_bfloat16* g_xp, const __nv_bfloat16* g_d, float* d_skts, cudaStream_t stream);
 cudaError_t pgn_launch_encode_bf16(const PgnRayRefs& rays, const PgnScalars* sc_dev, const float* z, int n_z,
                                    __nv_bfloat16* enc, cudaStream_t stream);
 cudaError_t pgn_launch_mlp_delta(void* dh, int has_in, const void* act, long long m, int C, const float* rs, int rs_stride,

@@ -531,8 +531,17 @@ cudaError_t pgn_launch_composite_backward(const PgnRayRefs& rays, const PgnScala
 //   pts_t = R p + t, v = |pts_t|, r = pts_t / v, w = 1 - sigmoid(tau (v - c)),  w' = -tau w (1 - w)
 //   e_k = phi_k(v) w (v-embed), q_k,a = psi_k(u_a) w_d(v) with u = R d / |R d| (view embed)
 // ---------------------------------------------------------------------------
+__device__ __forceinline__ float pgn_ldg_f(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float pgn_ldg_f(const __nv_bfloat16* p) {
+  return __uint_as_float((uint32_t)__ldg(reinterpret_cast<const unsigned short*>(p)) << 16);
+}
+
+// G = float: one [rows,1080] matrix (g_xp = g_enc, g_d = g_enc + 432, both row strides 1080);
+// G = __nv_bfloat16: the two GEMM outputs of the training backward as they are, [rows,432] and [rows,648].
+template <typename G>
 __global__ void pgn_encode_backward_kernel(PgnRayRefs rays, const PgnScalars* __restrict__ scp, const float* __restrict__ z,
-                                           int n_z, const float* __restrict__ g_enc, float* __restrict__ d_skts) {
+                                           int n_z, const G* __restrict__ g_xp, int stride_xp, const G* __restrict__ g_d,
+                                           int stride_d, float* __restrict__ d_skts) {
   const PgnScalars& sc = *scp;
   const long long total = rays.n_rays * PGN_J;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -549,6 +558,20 @@ __global__ void pgn_encode_backward_kernel(PgnRayRefs rays, const PgnScalars* __
     const float ndc = fmaxf(nd, 1e-12f);
     const float u[3] = {dj[0] / ndc, dj[1] / ndc, dj[2] / ndc};
     float gR[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, gt[3] = {0, 0, 0}, gu[3] = {0, 0, 0};
+    // sin / cos of the view-direction frequencies (per ray): one sincosf + double-angle steps
+    float usn[3][PGN_LD], ucs[3][PGN_LD];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      float sn, cs;
+      sincosf(u[a], &sn, &cs);
+#pragma unroll
+      for (int f = 0; f < PGN_LD; ++f) {
+        usn[a][f] = sn; ucs[a][f] = cs;
+        const float t2 = cs + cs;
+        sn = t2 * sn;
+        cs = fmaf(t2, cs, -1.0f);
+      }
+    }
     for (int s = 0; s < n_z; ++s) {
       const long long rs = ray * n_z + s;
       float p[3];
@@ -562,33 +585,37 @@ __global__ void pgn_encode_backward_kernel(PgnRayRefs rays, const PgnScalars* __
       const float w = pgn_window<false>(v, sc.tau_v, sc.cutoff_v[j]);
       const float wd = pgn_window<false>(v, sc.tau_d, sc.cutoff_d[j]);
       const float dw = -sc.tau_v * w * (1.0f - w), dwd = -sc.tau_d * wd * (1.0f - wd);
-      const float* ge = g_enc + rs * PGN_ENC;
+      const G* ge = g_xp + rs * stride_xp;
       // v-embed: k = 0 -> v, k = 1 + 2f -> sin(2^f v), 2 + 2f -> cos(2^f v)
-      float gv = ge[j] * (w + v * dw);
+      float gv = pgn_ldg_f(ge + j) * (w + v * dw);
+      float sn, cs;
+      sincosf(v, &sn, &cs);
 #pragma unroll
       for (int f = 0; f < PGN_LV; ++f) {
-        const float fr = (float)(1 << f), a = v * fr;
-        const float sn = sinf(a), cs = cosf(a);
-        gv += ge[(1 + 2 * f) * PGN_J + j] * (fr * cs * w + sn * dw);
-        gv += ge[(2 + 2 * f) * PGN_J + j] * (-fr * sn * w + cs * dw);
+        const float fr = (float)(1 << f);
+        gv += pgn_ldg_f(ge + (1 + 2 * f) * PGN_J + j) * (fr * cs * w + sn * dw);
+        gv += pgn_ldg_f(ge + (2 + 2 * f) * PGN_J + j) * (-fr * sn * w + cs * dw);
+        const float t2 = cs + cs;                 // double angle
+        sn = t2 * sn;
+        cs = fmaf(t2, cs, -1.0f);
       }
       // view embed: every channel is psi(u_a) * wd(v)
 #pragma unroll
       for (int a = 0; a < 3; ++a) {
-        const float* gq = ge + PGN_ENC_P + j * 3 + a;
-        gv += gq[0] * u[a] * dwd;
-        gu[a] += gq[0] * wd;
+        const G* gq = g_d + rs * stride_d + j * 3 + a;
+        const float g0 = pgn_ldg_f(gq);
+        gv += g0 * u[a] * dwd;
+        gu[a] += g0 * wd;
 #pragma unroll
         for (int f = 0; f < PGN_LD; ++f) {
-          const float fr = (float)(1 << f), ang = u[a] * fr;
-          const float sn = sinf(ang), cs = cosf(ang);
-          const float g1 = gq[(1 + 2 * f) * 72], g2 = gq[(2 + 2 * f) * 72];
-          gv += (g1 * sn + g2 * cs) * dwd;
-          gu[a] += (g1 * cs - g2 * sn) * fr * wd;
+          const float fr = (float)(1 << f);
+          const float g1 = pgn_ldg_f(gq + (1 + 2 * f) * 72), g2 = pgn_ldg_f(gq + (2 + 2 * f) * 72);
+          gv += (g1 * usn[a][f] + g2 * ucs[a][f]) * dwd;
+          gu[a] += (g1 * ucs[a][f] - g2 * usn[a][f]) * fr * wd;
         }
       }
       // r = pts_t / v
-      const float gr[3] = {ge[360 + j * 3], ge[360 + j * 3 + 1], ge[360 + j * 3 + 2]};
+      const float gr[3] = {pgn_ldg_f(ge + 360 + j * 3), pgn_ldg_f(ge + 360 + j * 3 + 1), pgn_ldg_f(ge + 360 + j * 3 + 2)};
       float gp[3];
       if (v > 1e-12f) {
         const float rg = r[0] * gr[0] + r[1] * gr[1] + r[2] * gr[2];
@@ -632,6 +659,18 @@ cudaError_t pgn_launch_encode_backward(const PgnRayRefs& rays, const PgnScalars*
   if (total == 0) return cudaSuccess;
   const int block = 96;                                   // 4 rays x 24 joints: the 24 threads of a ray read contiguous channels
   const long long grid = min((total + block - 1) / block, (long long)148 * 32);
-  pgn_encode_backward_kernel<<<(unsigned)grid, block, 0, stream>>>(rays, sc_dev, z, n_z, g_enc, d_skts);
+  pgn_encode_backward_kernel<float><<<(unsigned)grid, block, 0, stream>>>(rays, sc_dev, z, n_z, g_enc, PGN_ENC, g_enc + PGN_ENC_P,
+                                                                          PGN_ENC, d_skts);
+  return cudaGetLastError();
+}
+
+cudaError_t pgn_launch_encode_backward_bf16(const PgnRayRefs& rays, const PgnScalars* sc_dev, const float* z, int n_z,
+                                            const __nv_bfloat16* g_xp, const __nv_bfloat16* g_d, float* d_skts, cudaStream_t stream) {
+  const long long total = rays.n_rays * PGN_J;
+  if (total == 0) return cudaSuccess;
+  const int block = 96;
+  const long long grid = min((total + block - 1) / block, (long long)148 * 32);
+  pgn_encode_backward_kernel<__nv_bfloat16><<<(unsigned)grid, block, 0, stream>>>(rays, sc_dev, z, n_z, g_xp, PGN_ENC_P, g_d,
+                                                                                  PGN_ENC - PGN_ENC_P, d_skts);
   return cudaGetLastError();
 }

@@ -323,6 +323,19 @@ class Engine:
                                                 self._stream()))
         return d
 
+    def encode_backward_bf16(self, ray_batch, skts, cyls, z, g_xp, g_d):
+        """dL/d skts [n,24,4,4] (per ray) given dL/d(network input) as two bf16 matrices [n * n_z, 432] and [n * n_z, 648]."""
+        inp, keep = self._inputs(ray_batch, skts, cyls)
+        z = z.contiguous()
+        rows = inp.n_rays * z.shape[1]
+        for t, cols in ((g_xp, 432), (g_d, 648)):
+            if t.dtype != torch.bfloat16 or not t.is_contiguous() or tuple(t.shape) != (rows, cols):
+                raise ValueError(f"expected a contiguous bf16 [{rows},{cols}] matrix, got {tuple(t.shape)} {t.dtype}")
+        d = torch.empty((inp.n_rays, 24, 4, 4), dtype=torch.float32, device=z.device)
+        _lib.check(self.lib.pgn_encode_backward_bf16(self.handle, C.byref(inp), _ptr(z), z.shape[1], _ptr(g_xp), _ptr(g_d), _ptr(d),
+                                                     self._stream()))
+        return d
+
     def sample_pdf(self, z, weights):
         _check_f32_cuda(z, "z")
         n, dev = z.shape[0], z.device

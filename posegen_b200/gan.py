@@ -28,7 +28,7 @@ import torch
 
 from . import synthetic as syn
 from . import train
-from .train import T, mlp_backward
+from .train import mlp_backward
 
 
 class _FrameRenderFn(torch.autograd.Function):
@@ -60,7 +60,7 @@ class _FrameRenderFn(torch.autograd.Function):
                                            g_acc.index_select(0, idx).contiguous())
             gd = mlp_backward(pd, None, acts["f"], d_raw.reshape(-1, 4), eng.mlp_delta, want_input_grad=True,
                               want_weight_grad=False, chain=eng.mlp_delta_chain if train.USE_DELTA_CHAIN else None)
-            d = eng.encode_backward(rb, sk, cy, z, gd["_g_enc"].reshape(rb.shape[0], T, 1080))
+            d = eng.encode_backward_bf16(rb, sk, cy, z, gd["_g_xp"], gd["_g_d"])
             d_skts += d.sum(0)
             del acts, gd, d
         return None, None, d_skts, None, None

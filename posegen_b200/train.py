@@ -84,7 +84,8 @@ def mlp_backward(params: Dict[str, torch.Tensor], enc: torch.Tensor, acts: torch
     `chain(dG, d_raw, mask, mask_rows, wstream, w_alpha)` is `Engine.mlp_delta_chain` (`pgn_mlp_delta_chain`): the
     whole trunk chain dG -> dZ_7 .. dZ_0 (+ bias gradients) as one tcgen05 kernel; without it the chain runs layer by
     layer (a cuBLAS GEMM and a `fuse` pass per layer), which is also what the host-logic test exercises.
-    Returns {name: fp32 gradient}; with want_input_grad also "_g_enc" [m,1080] = dL/d(network input)."""
+    Returns {name: fp32 gradient}; with want_input_grad also dL/d(network input) as "_g_xp" [m,432] (v-embed | r
+    channels) and "_g_d" [m,648] (view embed), bf16 (the operands of `pgn_encode_backward_bf16`)."""
     m = d_raw.shape[0]
     bf = torch.bfloat16
     if want_weight_grad:
@@ -109,9 +110,8 @@ def mlp_backward(params: Dict[str, torch.Tensor], enc: torch.Tensor, acts: torch
         g["views_linears.0.bias"] = bias_v
         g["feature_linear.weight"] = W_vf.t() @ Tm
         g["feature_linear.bias"] = W_vf.t() @ bias_v
-    g_in = torch.empty((m, 1080), dtype=torch.float32, device=d_raw.device) if want_input_grad else None
-    if want_input_grad:
-        g_in[:, 432:] = torch.mm(dG, W_v[:, 256:].to(bf))
+    if want_input_grad:                         # dL/d(network input) stays two bf16 GEMM outputs: x_p part and view part
+        g["_g_d"] = torch.mm(dG, W_v[:, 256:].to(bf))
     if chain is not None:
         # trunk: one fused kernel for the eight deltas; the weight gradients are GEMMs over (dZ_l, h_{l-1})
         mask, mask_rows = act_masks(acts)
@@ -129,9 +129,7 @@ def mlp_backward(params: Dict[str, torch.Tensor], enc: torch.Tensor, acts: torch
                     g[f"pts_linears.{l}.weight"] = _mm32(dZt, H[l - 1])
                 g[f"pts_linears.{l}.bias"] = colsum[l]
         if want_input_grad:
-            g_in[:, :432] = torch.mm(dz[5], W["pts_linears.5.weight"][:, :432])
-            g_in[:, :432] += torch.mm(dz[0], W["pts_linears.0.weight"])
-            g["_g_enc"] = g_in
+            g["_g_xp"] = torch.mm(dz[5], W["pts_linears.5.weight"][:, :432]).addmm_(dz[0], W["pts_linears.0.weight"])
         return g
     # sigma head + last trunk layer: dL/d h7 = dG (W_vf W_f) + d_sigma w_alpha
     dH = torch.mm(dG, (W_vf @ W_f).to(bf))
@@ -153,16 +151,10 @@ def mlp_backward(params: Dict[str, torch.Tensor], enc: torch.Tensor, acts: torch
             g[f"pts_linears.{l}.bias"] = bias
         Wl = W[f"pts_linears.{l}.weight"]
         if want_input_grad and l in (0, 5):
-            gx = torch.mm(dZ, Wl[:, :432])
-            if l == 5:
-                g_in[:, :432] = gx
-            else:
-                g_in[:, :432] += gx
+            g["_g_xp"] = torch.mm(dZ, Wl[:, :432]) if l == 5 else g["_g_xp"].addmm_(dZ, Wl)
         if l > 0:
             dH = torch.mm(dZ, Wl[:, 432:] if l == 5 else Wl)
             bias, _ = fuse(dH, H[l - 1], None, None, True, False)
-    if want_input_grad:
-        g["_g_enc"] = g_in
     return g
 
 
@@ -210,7 +202,7 @@ class _RenderTrainFn(torch.autograd.Function):
                               chain=eng.mlp_delta_chain if USE_DELTA_CHAIN else None)
             grads += [gd[k].reshape(pd[k].shape).to(pd[k].dtype) for k in PARAM_ORDER] if want_w else [None] * len(PARAM_ORDER)
             if want_sk:          # pose gradient: dL/d(network input) -> dL/d skts (per ray), both passes add up
-                d = eng.encode_backward(rb, sk, cy, z, gd["_g_enc"].reshape(n, -1, 1080))
+                d = eng.encode_backward_bf16(rb, sk, cy, z, gd["_g_xp"], gd["_g_d"])
                 d_skts = d if d_skts is None else d_skts + d
         ctx.acts = None
         if want_sk and d_skts is not None and sk.dim() == 3:

@@ -190,7 +190,7 @@ def test_mlp_backward_matches_autograd_on_cpu():
         flat.append(got[k].reshape(-1).double()); ref.append(net[k].grad.reshape(-1).double())
     a, b = torch.cat(flat), torch.cat(ref)
     assert float((a - b).norm() / b.norm()) <= 2e-2                      # bf16 activations / deltas / weights
-    ge, gr = got["_g_enc"].double(), enc.grad.double()
+    ge, gr = torch.cat([got["_g_xp"], got["_g_d"]], 1).double(), enc.grad.double()
     assert float((ge - gr).norm() / gr.norm()) <= 2e-2
 
 

@@ -106,6 +106,7 @@ def main():
     ap.add_argument("--poses-per-gpu", type=int, default=2)
     ap.add_argument("--res", type=int, default=512)
     ap.add_argument("--chunk", type=int, default=16384)
+    ap.add_argument("--profile", default=None, help="write a torch.profiler kernel table of one step to this file")
     a = ap.parse_args()
     rank, world, local = pdist.env_rank_world()
     pdist.init_process_group("nccl" if world > 1 else None)
@@ -165,6 +166,13 @@ def main():
                       f"recompute backward to skts (chunk {a.chunk} rays), crop/resize 224, ResNet-50 HMR stand-in, MPJPE, Adam on the generator"}
     if rank == 0:
         print(json.dumps(line), flush=True)
+    if a.profile and rank == 0:
+        from torch.profiler import profile, ProfilerActivity
+        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+            step()
+            torch.cuda.synchronize()
+        with open(a.profile, "w") as f:
+            f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=50, max_name_column_width=70))
     if world > 1:
         torch.distributed.destroy_process_group()
 
