@@ -41,6 +41,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--cpu-baseline", action="store_true")
     ap.add_argument("--deterministic", action="store_true", help="perturb = 0, raw_noise_std = 0")
+    ap.add_argument("--graph", action="store_true", help="capture the step into a CUDA graph (posegen_b200.train.GraphedTrainStep)")
     ap.add_argument("--profile", default=None, help="write a torch.profiler kernel table of 3 steps to this file (after the timed run)")
     a = ap.parse_args()
     rank, world, local = pdist.env_rank_world()
@@ -50,7 +51,7 @@ def main():
     ckpt = syn.synthetic_raycaster_state(4, alpha_gain=40.0)
     rc = raycaster_from_checkpoint(ckpt, device=dev, precision="bf16")
     rc.train()
-    opt = torch.optim.Adam([p for p in rc.parameters() if p.requires_grad], lr=5e-4, fused=True)
+    opt = torch.optim.Adam([p for p in rc.parameters() if p.requires_grad], lr=5e-4, fused=True, capturable=a.graph)
     rb, sk, cy = make_batch(rank)
     n = rb.shape[0]
     rbt, skt, cyt = (torch.as_tensor(x, device=dev) for x in (rb, sk, cy))
@@ -66,6 +67,16 @@ def main():
         opt.step()
         return loss
 
+    if a.graph:
+        from posegen_b200.train import GraphedTrainStep
+
+        def loss_fn(ret, t):
+            return ((ret["rgb_map"] + (1 - ret["acc_map"][:, None]) - t) ** 2).mean() + ((ret["rgb0"] + (1 - ret["acc0"][:, None]) - t) ** 2).mean()
+        graphed = GraphedTrainStep(rc, opt, loss_fn, {"ray_batch": rbt, "skts": skt, "cyls": cyt, "target": tgt},
+                                   perturb=0. if a.deterministic else 1., raw_noise_std=0. if a.deterministic else 1.)
+
+        def step():                                       # a new batch is copied into the static inputs every step
+            return graphed(ray_batch=rbt, skts=skt, cyls=cyt, target=tgt)
     for _ in range(a.warmup):
         step()
     torch.cuda.synchronize()
@@ -81,7 +92,7 @@ def main():
     line = {"metric": "train_steps_per_sec", "value": 1e3 / ms, "ms_per_step": ms, "n_gpus": world, "rays_per_step": n * world,
             "rays_per_sec": n * world / ms * 1e3, "final_loss": float(loss.detach()),
             "config": "3072 rays/GPU from 256 poses x 12 rays, coarse+fine, fwd+bwd+allreduce+Adam, "
-                      + ("perturb=0, raw_noise_std=0" if a.deterministic else "perturb=1, raw_noise_std=1") + ", bf16 tensor-core forward"}
+                      + ("perturb=0, raw_noise_std=0" if a.deterministic else "perturb=1, raw_noise_std=1") + ", bf16 tensor-core forward" + (", CUDA graph" if a.graph else "")}
     if a.cpu_baseline and rank == 0:
         from oracle import render_oracle as orc
         torch.set_num_threads(os.cpu_count() or 1)
