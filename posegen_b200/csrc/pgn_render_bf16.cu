@@ -312,14 +312,12 @@ __device__ __forceinline__ void epilogue(Smem& sm, uint32_t tmem_acc, uint32_t a
       if (dump) {
         stg256(dump + (col0 >> 3) + 2 * b, pk);                  // 16 columns = one full 32-byte sector
         // ReLU mask of the 16 columns (what the fused delta chain of the backward reads instead of the activations):
-        // a packed bf16 is positive iff it is non-zero (cvt.relu clamps negatives to +0)
+        // one compare + one predicated OR per column (a positive fp32 stays positive in bf16)
         uint32_t mb = 0;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          mb |= ((pk[i] & 0xffffu) != 0u ? 1u : 0u) << (2 * i);
-          mb |= ((pk[i] >> 16) != 0u ? 1u : 0u) << (2 * i + 1);
-        }
-        mask_w[b >> 1] |= mb << ((b & 1) * 16);
+        for (int i = 0; i < 16; ++i)
+          if (__uint_as_float(vb[i]) > 0.f) mb |= 1u << (i + (b & 1) * 16);
+        mask_w[b >> 1] |= mb;
       }
     }
     if (MODE == 2 && dump) {      // view layer: relu(g) of this thread's 16 columns

@@ -303,3 +303,39 @@ def test_delta_chain_kernel_matches_layerwise_reference(engine):
             if l > 0:
                 W = P[f"pts_linears.{l}.weight"][:, 432:] if l == 5 else P[f"pts_linears.{l}.weight"]
                 pre = dz[l].float() @ W.to(bf).float()                                  # continue from the kernel's own bf16 deltas
+
+
+def test_graphed_training_step_follows_the_eager_one(engine, train_case):
+    """GraphedTrainStep (whole step captured into a CUDA graph, weights re-packed inside the graph) against the same
+    steps issued eagerly from the same initial weights: same loss trajectory."""
+    from posegen_b200.train import GraphedTrainStep
+    frame, ckpt, rb, tgt = train_case
+    n, dev = 1024, torch.device("cuda")
+    rbt = torch.as_tensor(rb[:n], device=dev)
+    sk = torch.as_tensor(np.repeat(frame.pose.skts[None], n, 0), device=dev)
+    cy = torch.as_tensor(np.repeat(frame.pose.cyl[None], n, 0), device=dev)
+    t = torch.full((n, 3), 0.25, device=dev)
+
+    def loss_fn(ret, tg):
+        return ((ret["rgb_map"] + (1 - ret["acc_map"][:, None]) - tg) ** 2).mean() + ((ret["rgb0"] + (1 - ret["acc0"][:, None]) - tg) ** 2).mean()
+
+    losses = {}
+    for mode in ("eager", "graph"):
+        rc = raycaster_from_checkpoint(ckpt, device="cuda", precision="bf16")
+        rc.train()
+        opt = torch.optim.Adam([p for p in rc.parameters() if p.requires_grad], lr=5e-4, fused=True, capturable=True)
+        if mode == "eager":
+            for _ in range(6):
+                opt.zero_grad(set_to_none=True)
+                ret = rc(rbt, N_samples=64, N_importance=16, kp_batch=None, skts=sk, cyls=cy, bones=None, cams=None, perturb=0., raw_noise_std=0.)
+                loss = loss_fn(ret, t)
+                loss.backward()
+                opt.step()
+            losses[mode] = float(loss.detach())
+        else:
+            g = GraphedTrainStep(rc, opt, loss_fn, {"ray_batch": rbt, "skts": sk, "cyls": cy, "target": t}, warmup=3,
+                                 perturb=0., raw_noise_std=0.)
+            for _ in range(3):
+                loss = g(ray_batch=rbt, skts=sk, cyls=cy, target=t)
+            losses[mode] = float(loss)
+    assert abs(losses["eager"] - losses["graph"]) <= 2e-3 * max(1.0, abs(losses["eager"])), losses
