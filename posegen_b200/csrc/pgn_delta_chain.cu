@@ -21,7 +21,6 @@
 // HBM (4 rows x 128 B per warp store: full lines) and accumulate the bias gradients (column sums; every column has
 // one owner thread, no atomics).  Draining and storing from the accumulator-owning threads directly costs 2x: a
 // thread owns one row, so each of its stores touches 32 different lines and the column sums need 128 shuffles.
-#include <cstdlib>
 #include "pgn_common.cuh"
 #include "pgn_kernels.h"
 #include "pgn_umma.cuh"
@@ -60,7 +59,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 pgn_delta_chain_kernel(const uint4* __restrict__ dG, const float* __restrict__ d_raw, const uint4* __restrict__ mask,
                        long long mask_rows, long long m, const uint8_t* __restrict__ wstream,
                        const float* __restrict__ w_alpha, uint4* __restrict__ dz, float* __restrict__ colsum_g,
-                       int* __restrict__ status_g, int dbg) {
+                       int* __restrict__ status_g) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   ChainSmem& sm = *reinterpret_cast<ChainSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   volatile int* status = status_g;
@@ -141,7 +140,7 @@ pgn_delta_chain_kernel(const uint4* __restrict__ dG, const float* __restrict__ d
 #pragma unroll 8
           for (int i = 0; i < 32; ++i) {
             const uint4 v = lds128(src + (uint32_t)i * 64);
-            if (g0 + 4 * i < m && !(dbg & 2)) out[(size_t)i * 128] = v;
+            if (g0 + 4 * i < m) out[(size_t)i * 128] = v;
             const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -149,16 +148,14 @@ pgn_delta_chain_kernel(const uint4* __restrict__ dG, const float* __restrict__ d
               acc[2 * e + 1] += __uint_as_float(w4[e] & 0xffff0000u);
             }
           }
-          if (!(dbg & 1)) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 1);
-              acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 2);
-            }
-            if (rr == 0) {
+          for (int e = 0; e < 8; ++e) {
+            acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 1);
+            acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 2);
+          }
+          if (rr == 0) {
 #pragma unroll
-              for (int e = 0; e < 8; ++e) sm.colsum[L][run * 8 + e] += acc[e];
-            }
+            for (int e = 0; e < 8; ++e) sm.colsum[L][run * 8 + e] += acc[e];
           }
           __syncwarp();
           if (lane == 0) mbar_arrive_local(&sm.cs_done[t]);
@@ -283,12 +280,11 @@ cudaError_t pgn_launch_delta_chain(const void* dG, const float* d_raw, const voi
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  static const int dbg = getenv("PGN_CHAIN_DEBUG") ? atoi(getenv("PGN_CHAIN_DEBUG")) : 0;   // bring-up only: 1 no column sums, 2 no dZ stores
   const long long n_blocks = (m + kBlockRows - 1) / kBlockRows;
   const unsigned grid = (unsigned)(n_blocks < num_sms ? n_blocks : num_sms);
   pgn_delta_chain_kernel<<<grid, kThreads, smem, stream>>>(reinterpret_cast<const uint4*>(dG), d_raw,
                                                            reinterpret_cast<const uint4*>(mask), mask_rows, m,
                                                            reinterpret_cast<const uint8_t*>(wstream), w_alpha,
-                                                           reinterpret_cast<uint4*>(dz), colsum, status, dbg);
+                                                           reinterpret_cast<uint4*>(dz), colsum, status);
   return cudaGetLastError();
 }

@@ -1,13 +1,14 @@
 """Training step of the A-NeRF renderer (BASELINE.json configs[3]; reference core/trainer.py:232-275).
 
-Forward: the fused bf16 tensor-core kernel (`pgn_render_forward_train`) with the post-ReLU activations of
-every MLP layer dumped in bf16.  Backward: `pgn_composite_backward` (hand-written) turns dL/d(rgb_map, acc_map)
-of both passes into dL/d raw; the weight gradients of the two MLPs are then plain dense GEMMs over all samples
-of the batch (activations^T x deltas, deltas x weights) and go through cuBLAS (`torch.mm`, bf16 inputs, fp32
-accumulation); the network inputs x_p / d_emb are regenerated with `pgn_encode`.  When `skts` requires grad (the
-pose generator / pose optimisation, configs[4]) dL/d(network input) is formed by three more GEMMs and
-`pgn_encode_backward` (hand-written) turns it into dL/d skts.  No gradient flows through the sample positions
-(the importance samples are detached in the reference, core/utils/ray_utils.py:286).
+Forward: the fused bf16 tensor-core kernel (`pgn_render_forward_train`) with the post-ReLU activations of every MLP
+layer dumped row-major in bf16 plus their 1-bit ReLU masks.  Backward, per pass: `pgn_composite_backward` turns
+dL/d(rgb_map, acc_map) into dL/d raw; `pgn_mlp_delta` forms the view layer's delta (+ bias and rgb-head gradients);
+`pgn_mlp_delta_chain` runs the trunk's delta chain dG -> dZ_7 .. dZ_0 as one tcgen05 kernel (bias gradients included);
+the weight gradients are plain dense GEMMs over all samples of the batch (deltas^T x activations; `pgn_encode_bf16`
+regenerates x_p / d_emb) and go through cuBLAS (`torch.mm`, bf16 inputs, fp32 accumulation).  When `skts` requires grad
+(the pose generator / pose optimisation, configs[4]) dL/d(network input) is formed by three more GEMMs and
+`pgn_encode_backward_bf16` turns it into dL/d skts.  No gradient flows through the sample positions (the importance
+samples are detached in the reference, core/utils/ray_utils.py:286).
 
 Sampling: deterministic (perturb = 0, raw_noise_std = 0: the reference's parity setting)
 or the reference's training-time randomness (perturb > 0: stratified jitter of the coarse samples and random

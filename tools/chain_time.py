@@ -1,3 +1,4 @@
+"""Time pgn_mlp_delta_chain alone on a fine-pass-sized batch (245,760 rows): python tools/chain_time.py"""
 import sys, torch
 sys.path.insert(0, '/root/repo')
 from posegen_b200 import synthetic as syn
