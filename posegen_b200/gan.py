@@ -33,12 +33,38 @@ from .train import mlp_backward
 
 class _FrameRenderFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, rc, ray_batch, skts, cyl, chunk):
+    def forward(ctx, rc, ray_batch, skts, cyl, chunk, live, dump_budget):
         eng = rc.engine(ray_batch.device)
-        ret = eng.render(ray_batch, skts, cyl, nanfill_chunk=0, precision="bf16", return_alpha=False)
         ctx.rc, ctx.eng, ctx.chunk = rc, eng, int(chunk)
+        ctx.kept = None
+        if live is None:
+            ret = eng.render(ray_batch, skts, cyl, nanfill_chunk=0, precision="bf16", return_alpha=False)
+            ctx.save_for_backward(ray_batch, skts, cyl)
+            return ret["rgb_map"], ret["acc_map"]
+        # the caller names the rays the loss can reach: the others take the plain kernel, the live ones the dumping
+        # kernel, and their fine-pass dumps are kept for the backward while they fit the budget (no recompute)
+        n, dev = ray_batch.shape[0], ray_batch.device
+        rgb, acc = torch.empty((n, 3), device=dev), torch.empty((n,), device=dev)
+        idx_dead = (~live).nonzero().squeeze(-1)
+        idx_live = live.nonzero().squeeze(-1)
+        if idx_dead.numel():
+            ret = eng.render(ray_batch.index_select(0, idx_dead), skts, cyl, nanfill_chunk=0, precision="bf16", return_alpha=False)
+            rgb[idx_dead], acc[idx_dead] = ret["rgb_map"], ret["acc_map"]
+        kept, used = [], 0
+        for i in range(0, idx_live.numel(), ctx.chunk):
+            idx = idx_live[i:i + ctx.chunk]
+            rb = ray_batch.index_select(0, idx)
+            ret, acts = eng.render_train(rb, skts, cyl, nanfill_chunk=0, dump_coarse=False)
+            rgb[idx], acc[idx] = ret["rgb_map"], ret["acc_map"]
+            nbytes = acts["f"].numel() * 2
+            if used + nbytes <= dump_budget:
+                kept.append((idx, rb, acts["f"], ret["raw"], ret["z_fine"]))
+                used += nbytes
+            else:
+                kept.append((idx, rb, None, None, None))
+        ctx.kept = kept
         ctx.save_for_backward(ray_batch, skts, cyl)
-        return ret["rgb_map"], ret["acc_map"]
+        return rgb, acc
 
     @staticmethod
     def backward(ctx, g_rgb, g_acc):
@@ -48,29 +74,42 @@ class _FrameRenderFn(torch.autograd.Function):
         n = rb_all.shape[0]
         g_rgb = torch.zeros((n, 3), device=dev) if g_rgb is None else g_rgb.float()
         g_acc = torch.zeros((n,), device=dev) if g_acc is None else g_acc.float()
-        live = ((g_rgb.abs().sum(-1) + g_acc.abs()) > 0).nonzero().squeeze(-1)
+        if ctx.kept is None:
+            live = ((g_rgb.abs().sum(-1) + g_acc.abs()) > 0).nonzero().squeeze(-1)
+            work = [(live[i:i + ctx.chunk], None, None, None, None) for i in range(0, live.numel(), ctx.chunk)]
+        else:
+            work, ctx.kept = ctx.kept, None
         d_skts = torch.zeros((24, 4, 4), dtype=torch.float32, device=dev)
         pd = dict(rc.network_fine.named_parameters())
-        for i in range(0, live.numel(), ctx.chunk):
-            idx = live[i:i + ctx.chunk]
-            rb = rb_all.index_select(0, idx)
-            ret, acts = eng.render_train(rb, sk, cy, nanfill_chunk=0, dump_coarse=False)
-            z = ret["z_fine"]
-            d_raw = eng.composite_backward(rb, sk, cy, ret["raw"], z, g_rgb.index_select(0, idx).contiguous(),
+        while work:
+            idx, rb, acts_f, raw, z = work.pop(0)                      # popped: a chunk's dump is freed as soon as it is used
+            if rb is None:
+                rb = rb_all.index_select(0, idx)
+            if acts_f is None:                                           # recompute this chunk with the fine-pass dump
+                ret, acts = eng.render_train(rb, sk, cy, nanfill_chunk=0, dump_coarse=False)
+                acts_f, raw, z = acts["f"], ret["raw"], ret["z_fine"]
+            d_raw = eng.composite_backward(rb, sk, cy, raw, z, g_rgb.index_select(0, idx).contiguous(),
                                            g_acc.index_select(0, idx).contiguous())
-            gd = mlp_backward(pd, None, acts["f"], d_raw.reshape(-1, 4), eng.mlp_delta, want_input_grad=True,
+            gd = mlp_backward(pd, None, acts_f, d_raw.reshape(-1, 4), eng.mlp_delta, want_input_grad=True,
                               want_weight_grad=False, chain=eng.mlp_delta_chain if train.USE_DELTA_CHAIN else None)
             d = eng.encode_backward_bf16(rb, sk, cy, z, gd["_g_xp"], gd["_g_d"])
             d_skts += d.sum(0)
-            del acts, gd, d
-        return None, None, d_skts, None, None
+            del acts_f, gd, d, raw, z
+        return None, None, d_skts, None, None, None, None
 
 
-def render_frame(rc, ray_batch: torch.Tensor, skts: torch.Tensor, cyl: torch.Tensor, chunk: int = 16384) -> Tuple[torch.Tensor, torch.Tensor]:
-    """(rgb_map [n,3], acc_map [n]) of all rays of one frame, differentiable w.r.t. skts [24,4,4] (one pose)."""
+def render_frame(rc, ray_batch: torch.Tensor, skts: torch.Tensor, cyl: torch.Tensor, chunk: int = 16384,
+                 live: torch.Tensor | None = None, dump_budget_bytes: int = 48 << 30) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(rgb_map [n,3], acc_map [n]) of all rays of one frame, differentiable w.r.t. skts [24,4,4] (one pose).
+
+    live (optional bool [n]): a promise that the loss only reads the rays marked True (e.g. those inside the HMR crop);
+    the others are rendered as constants.  With it the live rays go through the dumping kernel in the forward and
+    their fine-pass dumps (369 KB per ray) are kept for the backward while they fit dump_budget_bytes, which removes
+    the recompute; without it the backward finds the rays with a non-zero upstream gradient and re-renders them."""
     if skts.shape != (24, 4, 4):
         raise ValueError("render_frame renders one pose: skts must be [24,4,4]")
-    return _FrameRenderFn.apply(rc, ray_batch.float().contiguous(), skts.float(), cyl.float().contiguous(), chunk)
+    return _FrameRenderFn.apply(rc, ray_batch.float().contiguous(), skts.float(), cyl.float().contiguous(), chunk, live,
+                                int(dump_budget_bytes))
 
 
 def compose_white(rgb_map, acc_map, H, W, x0, y0, x1, y1, bg: float = 1.0) -> torch.Tensor:
@@ -130,10 +169,13 @@ def hmr_input(eng, image: torch.Tensor, crop=(100, 100, 412, 412), out_res: int 
 
 
 def render_pose_images(rc, bones: torch.Tensor, rest_pose: torch.Tensor, c2w: np.ndarray, H: int = 512, W: int = 512,
-                       focal: float = 1000.0, ext_scale: float = 0.001, chunk: int = 16384, bg: float = 1.0):
+                       focal: float = 1000.0, ext_scale: float = 0.001, chunk: int = 16384, bg: float = 1.0,
+                       live_crop=None, dump_budget_bytes: int = 48 << 30):
     """bones [B,24,3] axis-angle (requires grad) -> frames [B,H,W,3] with autograd back to `bones`.
 
-    FK with autograd (`fk.smpl_skts`), bbox from the detached key points (`kp_to_valid_rays`), rays on the device."""
+    FK with autograd (`fk.smpl_skts`), bbox from the detached key points (`kp_to_valid_rays`), rays on the device.
+    live_crop = (x0, y0, x1, y1): only pixels inside it will be read by the loss (the HMR crop, run_gan.py:2059):
+    `render_frame(live=...)`."""
     from . import fk
     dev = bones.device
     eng = rc.engine(dev)
@@ -147,6 +189,12 @@ def render_pose_images(rc, bones: torch.Tensor, rest_pose: torch.Tensor, c2w: np
         x0, y0, x1, y1 = int(tl[0]), int(tl[1]), int(br[0]), int(br[1])
         rb = eng.generate_rays(H, W, float(focal), c2w, x0, y0, x1, y1)
         cyl = torch.as_tensor(cyl_np, dtype=torch.float32, device=dev)
-        rgb, acc = render_frame(rc, rb, skts[b], cyl, chunk)
+        live = None
+        if live_crop is not None:
+            cx0, cy0, cx1, cy1 = live_crop
+            ys = torch.arange(y0, y1, device=dev)[:, None]
+            xs = torch.arange(x0, x1, device=dev)[None, :]
+            live = ((ys >= cy0) & (ys < cy1) & (xs >= cx0) & (xs < cx1)).reshape(-1)
+        rgb, acc = render_frame(rc, rb, skts[b], cyl, chunk, live=live, dump_budget_bytes=dump_budget_bytes // max(1, bones.shape[0]))
         frames.append(compose_white(rgb, acc, H, W, x0, y0, x1, y1, bg))
     return torch.stack(frames), kps

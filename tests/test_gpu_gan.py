@@ -47,6 +47,16 @@ def test_frame_render_pose_gradient_matches_training_path(rc):
     assert torch.isfinite(ga).all() and float(ga.abs().max()) > 0
     assert float((ga - gb).norm() / gb.norm()) <= 2e-3, float((ga - gb).norm() / gb.norm())
     assert float(ga[:, 3].abs().max()) == 0.0                            # bottom rows carry no gradient
+    # (c) frame path with the live-ray hint: dumps kept in the forward (the budget holds one of the three chunks, the
+    # others fall back to the recompute), same image, same gradient
+    rc.eval()
+    sk_c = torch.as_tensor(frame.pose.skts, dtype=torch.float32, device=dev).requires_grad_(True)
+    one_chunk = 1000 * 80 * 4608
+    rgb_c, acc_c = gan.render_frame(rc, rb, sk_c, cy, chunk=1000, live=~dead, dump_budget_bytes=one_chunk + 1024)
+    ((rgb_c * w_rgb).sum() + (acc_c * w_acc).sum()).backward()
+    assert torch.equal(rgb_c.detach(), rgb.detach()) and torch.equal(acc_c.detach(), acc.detach())
+    gc = sk_c.grad.double()
+    assert float((gc - ga).norm() / ga.norm()) <= 1e-4, float((gc - ga).norm() / ga.norm())
 
 
 def test_compose_white_matches_the_device_composite(rc):
