@@ -229,26 +229,35 @@ pgn_delta_chain_kernel(const uint4* __restrict__ dG, const float* __restrict__ d
           const uint32_t taddr = tmem + (uint32_t)t * 256 + ((uint32_t)(q * 32) << 16) + (uint32_t)col0;
           const uint32_t dst0 = smem_u32(sm.a[t]) + (uint32_t)(col0 >> 3) * kRun + row * 16;
           const uint32_t mw[4] = {mk[t].x, mk[t].y, mk[t].z, mk[t].w};
-          uint32_t v[2][16];
-          tmem_ld_32x16(taddr, v[0]);
+          // 32 columns per tcgen05.ld, double-buffered: the drain of one tile is bound by the TMEM load latency (only
+          // this tile's 8 warps read at a time), so each wait should cover as many columns as the registers allow
+          uint32_t v[2][32];
+          tmem_ld_32x32(taddr, v[0]);
 #pragma unroll
-          for (int b = 0; b < 8; ++b) {
+          for (int b2 = 0; b2 < 4; ++b2) {
             tmem_ld_wait();
-            if (b + 1 < 8) tmem_ld_32x16(taddr + (uint32_t)(b + 1) * 16, v[(b + 1) & 1]);
-            const uint32_t* vb = v[b & 1];
-            const uint32_t bits = mw[b >> 1] >> ((b & 1) * 16);
-            float x[16];
+            if (b2 + 1 < 4) tmem_ld_32x32(taddr + (uint32_t)(b2 + 1) * 32, v[(b2 + 1) & 1]);
+            const uint32_t bits32 = mw[b2];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              float p = __uint_as_float(vb[i]);
-              if (j == 0) p = fmaf(dsig[t], sm.w_alpha[col0 + b * 16 + i], p);
-              x[i] = ((bits >> i) & 1u) ? p : 0.f;
+            for (int h = 0; h < 2; ++h) {
+              const int b = 2 * b2 + h;                       // 16-column batch
+              const uint32_t* vb = v[b2 & 1] + 16 * h;
+              const uint32_t bits = bits32 >> (16 * h);
+              uint32_t pk[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                float p0 = __uint_as_float(vb[2 * i]), p1 = __uint_as_float(vb[2 * i + 1]);
+                if (j == 0) {
+                  p0 = fmaf(dsig[t], sm.w_alpha[col0 + b * 16 + 2 * i], p0);
+                  p1 = fmaf(dsig[t], sm.w_alpha[col0 + b * 16 + 2 * i + 1], p1);
+                }
+                if (!(bits & (1u << (2 * i)))) p0 = 0.f;
+                if (!(bits & (1u << (2 * i + 1)))) p1 = 0.f;
+                pk[i] = pack_bf16x2(p0, p1);
+              }
+              sts128(dst0 + (uint32_t)(2 * b) * kRun, pk[0], pk[1], pk[2], pk[3]);
+              sts128(dst0 + (uint32_t)(2 * b + 1) * kRun, pk[4], pk[5], pk[6], pk[7]);
             }
-            uint32_t pk[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) pk[i] = pack_bf16x2(x[2 * i], x[2 * i + 1]);
-            sts128(dst0 + (uint32_t)(2 * b) * kRun, pk[0], pk[1], pk[2], pk[3]);
-            sts128(dst0 + (uint32_t)(2 * b + 1) * kRun, pk[4], pk[5], pk[6], pk[7]);
           }
           tc_fence_before_sync();
           if (j + 1 < kLayers) fence_proxy_async_smem();

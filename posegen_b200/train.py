@@ -254,7 +254,7 @@ def allreduce_gradients(parameters, average: bool = True):
 
 
 class GraphedTrainStep:
-    """One training step (forward, loss, backward, gradient all-reduce, optimizer step) captured into a CUDA graph.
+    """One training step (forward, loss, backward, optimizer step) captured into a CUDA graph.
 
     The step is ~150 kernel launches of 10-400 us; issued from Python the launch queue runs dry between them (about
     1 ms of a 5.5 ms step).  `GraphedTrainStep(rc, optimizer, loss_fn, inputs)` warms the step up on a side stream,
@@ -268,30 +268,46 @@ class GraphedTrainStep:
     def __init__(self, rc, optimizer, loss_fn, inputs: Dict[str, torch.Tensor], warmup: int = 3, **render_kwargs):
         self.rc, self.opt, self.loss_fn, self.kw = rc, optimizer, loss_fn, render_kwargs
         self.static = {k: v.clone() for k, v in inputs.items()}
+        # data-parallel runs keep the gradient all-reduce out of the capture (NCCL's watchdog and a capturing stream do
+        # not mix): graph A = forward + backward, eager all-reduce, graph B = optimizer step
+        self.split = dist.is_initialized() and dist.get_world_size() > 1
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(warmup):
-                self._step()
+                self._fwd_bwd()
+                allreduce_gradients(self.rc.parameters())
+                self.opt.step()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.loss = self._step()
+        self.graph_opt = None
+        if not self.split:
+            with torch.cuda.graph(self.graph):
+                self.loss = self._fwd_bwd()
+                self.opt.step()
+        else:
+            with torch.cuda.graph(self.graph):
+                self.loss = self._fwd_bwd()
+            self.graph_opt = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_opt, pool=self.graph.pool()):
+                self.opt.step()
 
-    def _step(self):
+    def _fwd_bwd(self):
+        # gradients are re-created by every backward of the captured graph at the same addresses
         self.opt.zero_grad(set_to_none=True)
         s = self.static
         ret = self.rc(s["ray_batch"], N_samples=S, N_importance=T - S, kp_batch=None, skts=s["skts"], cyls=s["cyls"], bones=None,
                       cams=None, **self.kw)
         loss = self.loss_fn(ret, s["target"])
         loss.backward()
-        allreduce_gradients(self.rc.parameters())
-        self.opt.step()
         return loss.detach()
 
     def __call__(self, **inputs):
         for k, v in inputs.items():
             self.static[k].copy_(v, non_blocking=True)
         self.graph.replay()
+        if self.split:
+            allreduce_gradients(self.rc.parameters())
+            self.graph_opt.replay()
         return self.loss
