@@ -12,11 +12,11 @@
 // Algorithmic bytes per row: 8 x 512 B written + 8 x 32 B masks + 256 B dG + 4 B d_sigma = 4.6 KB (HBM-bound:
 // 0.47 TFLOP over 2.0 GB for a 3,072-ray batch).
 //
-// Roles (512 threads, 1 CTA per SM, persistent over row blocks): warp 0 lane 0 streams the weights of all eight layers
+// Roles (768 threads, 1 CTA per SM, persistent over row blocks): warp 0 lane 0 streams the weights of all eight layers
 // in consumption order through a 10 x 8 KB ring with cp.async.bulk (one K-step slab = [2][256][8] bf16, UMMA K-major
 // SWIZZLE_NONE); warp 1 lane 0 issues the MMAs (UMMA M = 128, two row tiles share every weight slab, cta_group::1);
-// warps 4-11 drain the accumulators (tcgen05.ld 32x32b), add the sigma head's outer product on the first layer, mask,
-// pack to bf16 and store the next layer's A operand into shared memory ([k/8][row][8]); warps 12-15 then read that
+// warps 4-19 drain the two accumulators (8 warps each; tcgen05.ld 32x32b), add the sigma head's outer product on the
+// first layer, mask, pack to bf16 and store the next layer's A operand into shared memory ([k/8][row][8]); warps 20-23 then read that
 // tile back from shared memory - while the tensor core already runs the next layer on it - and write the dZ rows to
 // HBM (4 rows x 128 B per warp store: full lines) and accumulate the bias gradients (column sums; every column has
 // one owner thread, no atomics).  Draining and storing from the accumulator-owning threads directly costs 2x: a
@@ -38,7 +38,7 @@ constexpr int kSlabBytes = 2 * 256 * 16;         // one K = 16 step of a [256 x 
 constexpr int kStages = 10;                     // 80 KB of weight slabs in flight (a 16-slab layer is 128 KB)
 constexpr int kLayers = 8;                       // fold layer (K = 128) + W_7 .. W_1 (K = 256)
 constexpr int kSlabsPerBlock = 8 + 7 * 16;       // 120
-constexpr int kThreads = 512;
+constexpr int kThreads = 768;
 
 struct __align__(1024) ChainSmem {
   uint8_t a[kTiles][kABytes];
@@ -120,10 +120,10 @@ pgn_delta_chain_kernel(const uint4* __restrict__ dG, const float* __restrict__ d
         }
       }
     }
-  } else if (warp >= 12) {
+  } else if (warp >= 20) {
     // ---------------------------------------------------------------- dZ store + bias-gradient group (128 threads)
     // warp w owns the 8 runs (64 columns) 8w .. 8w+7 of a tile; lane = (row & 3) + 4 * (run & 7)
-    const int dw = warp - 12, rr = lane & 3, run = dw * 8 + (lane >> 2);
+    const int dw = warp - 20, rr = lane & 3, run = dw * 8 + (lane >> 2);
     uint32_t phase = 0;
     for (long long blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
       const long long r0 = blk * kBlockRows;
@@ -169,103 +169,82 @@ pgn_delta_chain_kernel(const uint4* __restrict__ dG, const float* __restrict__ d
         for (int e = 0; e < 8; ++e) atomicAdd(colsum_g + L * 256 + run * 8 + e, sm.colsum[L][run * 8 + e]);
     }
   } else if (warp >= 4) {
-    // ---------------------------------------------------------------- epilogue / staging group (256 threads)
-    const int ew = warp - 4, q = ew & 3, half = ew >> 2;
-    const int et = tid - 128;                       // 0..255
+    // ---------------------------------------------------------------- epilogue / staging groups (2 x 256 threads)
+    // warps 4-11 own tile 0, warps 12-19 tile 1: both accumulators are drained at the same time (a drain is a long
+    // dependent chain per thread, so its rate grows with the number of warps on it)
+    const int ew = warp - 4, t = ew >> 3, q = ew & 3, half = (ew >> 2) & 1;
+    const int et = (tid - 128) & 255;               // thread of the tile's group
     const int row = q * 32 + lane;                  // TMEM lane = row of the tile
     const int col0 = half * 128;
-    uint32_t acc_phase = 0, csd_phase = 0;          // csd_phase: completed store/sum passes over an A tile waited for so far
+    const uint32_t a_base = smem_u32(sm.a[t]);
+    const uint32_t taddr = tmem + (uint32_t)t * 256 + ((uint32_t)(q * 32) << 16) + (uint32_t)col0;
+    const uint32_t dst0 = a_base + (uint32_t)(col0 >> 3) * kRun + row * 16;
+    uint32_t acc_phase = 0, csd_phase = 0;          // csd_phase: completed store/sum passes over the A tile waited for so far
     bool first = true;
     for (long long blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
-      const long long r0 = blk * kBlockRows;
-      // stage in dG: [256 rows x 128 columns] -> the first 16 runs of both A tiles (once the store group has read the
-      // previous block's last deltas out of them)
+      const long long r0 = blk * kBlockRows + t * kTile;
+      // stage in dG: [128 rows x 128 columns] -> the first 16 runs of the A tile (once the store group has read the
+      // previous block's last deltas out of it)
       {
-        const int srow = et & 127, sh = et >> 7;    // row of a tile, 64-column half
+        const int srow = et & 127, sh = et >> 7;    // row of the tile, 64-column half
         if (!first) {
-          for (int t = 0; t < kTiles; ++t)
-            if (!mbar_wait(&sm.cs_done[t], csd_phase & 1, status, 706)) return;
+          if (!mbar_wait(&sm.cs_done[t], csd_phase & 1, status, 706)) return;
           ++csd_phase;
         }
         first = false;
+        const long long gr = r0 + srow;
+        const uint32_t dst = a_base + (uint32_t)(sh * 8) * kRun + srow * 16;
 #pragma unroll
-        for (int t = 0; t < kTiles; ++t) {
-          const long long gr = r0 + t * kTile + srow;
-          const uint32_t dst = smem_u32(sm.a[t]) + (uint32_t)(sh * 8) * kRun + srow * 16;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (gr < m) v = __ldg(dG + (size_t)gr * 16 + sh * 8 + i);
-            sts128(dst + (uint32_t)i * kRun, v.x, v.y, v.z, v.w);
-          }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_local(&sm.act_ready[t]);
+        for (int i = 0; i < 8; ++i) {
+          uint4 v = make_uint4(0u, 0u, 0u, 0u);
+          if (gr < m) v = __ldg(dG + (size_t)gr * 16 + sh * 8 + i);
+          sts128(dst + (uint32_t)i * kRun, v.x, v.y, v.z, v.w);
         }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_local(&sm.act_ready[t]);
       }
-      float dsig[kTiles];
-#pragma unroll
-      for (int t = 0; t < kTiles; ++t) {
-        const long long gr = r0 + t * kTile + row;
-        dsig[t] = gr < m ? __ldg(d_raw + (size_t)gr * 4 + 3) : 0.f;
-      }
+      const long long gr = r0 + row;
+      const float dsig = gr < m ? __ldg(d_raw + (size_t)gr * 4 + 3) : 0.f;
       for (int j = 0; j < kLayers; ++j, ++acc_phase) {
         const int L = 7 - j;                        // this layer's output is dL/dh_L; its mask is [h_L > 0]
-        uint4 mk[kTiles];
-#pragma unroll
-        for (int t = 0; t < kTiles; ++t) {
-          const long long gr = r0 + t * kTile + row;
-          mk[t] = gr < m ? __ldg(mask + ((size_t)L * mask_rows + gr) * 2 + half) : make_uint4(0u, 0u, 0u, 0u);
-        }
+        const uint4 mk = gr < m ? __ldg(mask + ((size_t)L * mask_rows + gr) * 2 + half) : make_uint4(0u, 0u, 0u, 0u);
         if (!mbar_wait(&sm.acc_full, acc_phase & 1, status, 704)) return;
         tc_fence_after_sync();
-        if (j > 0) {                                 // the previous deltas have been stored / summed out of the A tiles
-          for (int t = 0; t < kTiles; ++t)
-            if (!mbar_wait(&sm.cs_done[t], csd_phase & 1, status, 707)) return;
+        if (j > 0) {                                 // the previous deltas have been stored / summed out of the A tile
+          if (!mbar_wait(&sm.cs_done[t], csd_phase & 1, status, 707)) return;
           ++csd_phase;
         }
+        const uint32_t mw[4] = {mk.x, mk.y, mk.z, mk.w};
+        uint32_t v[2][16];
+        tmem_ld_32x16(taddr, v[0]);
 #pragma unroll
-        for (int t = 0; t < kTiles; ++t) {
-          const uint32_t taddr = tmem + (uint32_t)t * 256 + ((uint32_t)(q * 32) << 16) + (uint32_t)col0;
-          const uint32_t dst0 = smem_u32(sm.a[t]) + (uint32_t)(col0 >> 3) * kRun + row * 16;
-          const uint32_t mw[4] = {mk[t].x, mk[t].y, mk[t].z, mk[t].w};
-          // 32 columns per tcgen05.ld, double-buffered: the drain of one tile is bound by the TMEM load latency (only
-          // this tile's 8 warps read at a time), so each wait should cover as many columns as the registers allow
-          uint32_t v[2][32];
-          tmem_ld_32x32(taddr, v[0]);
+        for (int b = 0; b < 8; ++b) {
+          tmem_ld_wait();
+          if (b + 1 < 8) tmem_ld_32x16(taddr + (uint32_t)(b + 1) * 16, v[(b + 1) & 1]);
+          const uint32_t* vb = v[b & 1];
+          const uint32_t bits = mw[b >> 1] >> ((b & 1) * 16);
+          uint32_t pk[8];
 #pragma unroll
-          for (int b2 = 0; b2 < 4; ++b2) {
-            tmem_ld_wait();
-            if (b2 + 1 < 4) tmem_ld_32x32(taddr + (uint32_t)(b2 + 1) * 32, v[(b2 + 1) & 1]);
-            const uint32_t bits32 = mw[b2];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const int b = 2 * b2 + h;                       // 16-column batch
-              const uint32_t* vb = v[b2 & 1] + 16 * h;
-              const uint32_t bits = bits32 >> (16 * h);
-              uint32_t pk[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                float p0 = __uint_as_float(vb[2 * i]), p1 = __uint_as_float(vb[2 * i + 1]);
-                if (j == 0) {
-                  p0 = fmaf(dsig[t], sm.w_alpha[col0 + b * 16 + 2 * i], p0);
-                  p1 = fmaf(dsig[t], sm.w_alpha[col0 + b * 16 + 2 * i + 1], p1);
-                }
-                if (!(bits & (1u << (2 * i)))) p0 = 0.f;
-                if (!(bits & (1u << (2 * i + 1)))) p1 = 0.f;
-                pk[i] = pack_bf16x2(p0, p1);
-              }
-              sts128(dst0 + (uint32_t)(2 * b) * kRun, pk[0], pk[1], pk[2], pk[3]);
-              sts128(dst0 + (uint32_t)(2 * b + 1) * kRun, pk[4], pk[5], pk[6], pk[7]);
+          for (int i = 0; i < 8; ++i) {
+            float p0 = __uint_as_float(vb[2 * i]), p1 = __uint_as_float(vb[2 * i + 1]);
+            if (j == 0) {
+              p0 = fmaf(dsig, sm.w_alpha[col0 + b * 16 + 2 * i], p0);
+              p1 = fmaf(dsig, sm.w_alpha[col0 + b * 16 + 2 * i + 1], p1);
             }
+            if (!(bits & (1u << (2 * i)))) p0 = 0.f;
+            if (!(bits & (1u << (2 * i + 1)))) p1 = 0.f;
+            pk[i] = pack_bf16x2(p0, p1);
           }
-          tc_fence_before_sync();
-          if (j + 1 < kLayers) fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            if (j + 1 < kLayers) mbar_arrive_local(&sm.act_ready[t]);      // next layer's A operand (and a free accumulator)
-            mbar_arrive_local(&sm.cs_ready[t]);                            // dZ_L of this tile is in shared memory
-          }
+          sts128(dst0 + (uint32_t)(2 * b) * kRun, pk[0], pk[1], pk[2], pk[3]);
+          sts128(dst0 + (uint32_t)(2 * b + 1) * kRun, pk[4], pk[5], pk[6], pk[7]);
+        }
+        tc_fence_before_sync();
+        if (j + 1 < kLayers) fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (j + 1 < kLayers) mbar_arrive_local(&sm.act_ready[t]);      // next layer's A operand (and a free accumulator)
+          mbar_arrive_local(&sm.cs_ready[t]);                            // dZ_L of this tile is in shared memory
         }
       }
     }
