@@ -287,7 +287,7 @@ def cpu_baseline(args, job):
     torch.set_num_threads(threads)
     ckpt = syn.synthetic_raycaster_state(0, alpha_gain=400.)
     nets, emb = orc.nets_from_ckpt(ckpt), orc.embed_params_from_ckpt(ckpt)
-    n_sample = min(args.cpu_rays, rb.shape[0])
+    n_sample = min(3 * args.cpu_rays, rb.shape[0])                 # ~10 s of host work (one measurement, not K steps)
     sel = np.linspace(0, rb.shape[0] - 1, n_sample).astype(np.int64)
     rbt, sk, cy = torch.from_numpy(rb[sel]), torch.from_numpy(frame.pose.skts), torch.from_numpy(frame.pose.cyl)
     orc.render(rbt[:512], sk, cy, nets, emb, chunk=4096)          # warm-up
