@@ -179,6 +179,20 @@ PGN_API int  pgn_render_forward_train(pgn_context* ctx, const pgn_render_inputs*
                                       void* act_coarse, void* act_fine, const pgn_train_random* rnd,
                                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same forward for a FROZEN network whose pose gradient is wanted (GAN step, run_gan.py:159-160): only the ReLU
+ * masks of the fine pass are kept - 272 B per sample instead of 4,608 B - which is all the input-gradient backward
+ * needs (pgn_view_delta_from_mask, pgn_mlp_delta_chain).  masks_fine: device buffer of pgn_mask_dump_bytes(n_rays)
+ * bytes laid out [layer 0..7][rows][256 bits] then [rows][128 bits] (views_linears.0), rows = bytes / 272, samples in
+ * (ray, sample) order.  Sampling is the deterministic eval sampling; request out->raw / z_fine for the backward. */
+PGN_API size_t pgn_mask_dump_bytes(int64_t n_rays);
+PGN_API int  pgn_render_forward_masks(pgn_context* ctx, const pgn_render_inputs* in, const pgn_render_outputs* out,
+                                      void* masks_fine, void* workspace, size_t workspace_bytes, void* stream);
+
+/* dG [m,128] (bf16) = [g > 0] * (d_rgb W_rgb): the view layer's delta from its mask bits (vmask: [m][128 bits]),
+ * d_raw fp32 [m,4] (columns 0-2 = d_rgb), w_rgb fp32 [3,128] (rgb_linear.weight; core/networks/nerf.py:129-131). */
+PGN_API int  pgn_view_delta_from_mask(pgn_context* ctx, void* dG, const float* d_raw, const float* w_rgb, const void* vmask,
+                                      int64_t m, void* stream);
+
 /* number of kernel launches issued by this context since creation
  * (bench.py reports it as gpu_launches) */
 PGN_API int64_t pgn_launch_count(const pgn_context* ctx);

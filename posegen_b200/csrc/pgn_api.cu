@@ -219,9 +219,27 @@ int pgn_render_forward_train(pgn_context* c, const pgn_render_inputs* in, const 
   if (!act_coarse && !act_fine) return fail(PGN_E_INVALID, "pgn_render_forward_train: null activation dump");
   PgnActDump d;
   d.c = (__nv_bfloat16*)act_coarse; d.f = (__nv_bfloat16*)act_fine;
+  d.masks_only = 0;
   d.rows_c = pgn_bf16_dump_rows(in->n_rays, PGN_S); d.rows_f = pgn_bf16_dump_rows(in->n_rays, PGN_T);
   d.t_rand = rnd ? rnd->t_rand : nullptr; d.u_is = rnd ? rnd->u_is : nullptr;
   d.noise0 = rnd ? rnd->noise0 : nullptr; d.noise = rnd ? rnd->noise : nullptr;
+  return render_forward_impl(c, in, out, workspace, workspace_bytes, stream_, &d);
+}
+
+size_t pgn_mask_dump_bytes(int64_t n_rays) {
+  if (n_rays < 0) return 0;
+  return (size_t)pgn_bf16_dump_rows(n_rays, PGN_T) * (8 * 32 + 16);
+}
+
+int pgn_render_forward_masks(pgn_context* c, const pgn_render_inputs* in, const pgn_render_outputs* out, void* masks_fine,
+                             void* workspace, size_t workspace_bytes, void* stream_) {
+  if (!in || in->precision != PGN_PRECISION_BF16) return fail(PGN_E_INVALID, "pgn_render_forward_masks: the bf16 tensor-core path only");
+  if (!masks_fine) return fail(PGN_E_INVALID, "pgn_render_forward_masks: null mask buffer");
+  PgnActDump d;
+  d.c = nullptr; d.f = (__nv_bfloat16*)masks_fine;
+  d.rows_c = pgn_bf16_dump_rows(in->n_rays, PGN_S); d.rows_f = pgn_bf16_dump_rows(in->n_rays, PGN_T);
+  d.masks_only = 1;
+  d.t_rand = nullptr; d.u_is = nullptr; d.noise0 = nullptr; d.noise = nullptr;
   return render_forward_impl(c, in, out, workspace, workspace_bytes, stream_, &d);
 }
 
@@ -310,6 +328,15 @@ int pgn_mlp_delta(pgn_context* c, void* dh, int32_t has_input, const void* act, 
   if (!has_input && nrs == 0) return fail(PGN_E_INVALID, "pgn_mlp_delta: nothing to do");
   PGN_CUDA(cudaSetDevice(c->cfg.device));
   PGN_CUDA(pgn_launch_mlp_delta(dh, has_input, act, m, n_cols, rs, rs_stride, nrs, wr, colsum, wsum, c->num_sms, (cudaStream_t)stream));
+  c->launches++;
+  return PGN_OK;
+}
+
+int pgn_view_delta_from_mask(pgn_context* c, void* dG, const float* d_raw, const float* w_rgb, const void* vmask, int64_t m,
+                             void* stream) {
+  if (!c || !dG || !d_raw || !w_rgb || !vmask || m < 0) return fail(PGN_E_INVALID, "pgn_view_delta_from_mask: bad argument");
+  PGN_CUDA(cudaSetDevice(c->cfg.device));
+  PGN_CUDA(pgn_launch_view_delta_bits(dG, d_raw, w_rgb, vmask, m, c->num_sms, (cudaStream_t)stream));
   c->launches++;
   return PGN_OK;
 }

@@ -43,6 +43,7 @@ struct PgnActDump {
   __nv_bfloat16* c;     // coarse pass
   __nv_bfloat16* f;     // fine pass
   long long rows_c, rows_f;
+  int masks_only;       // 1: c / f receive only ReLU masks: [8][rows][256 bits] (trunk) then [rows][128 bits] (view layer)
   // training-time randomness, all optional (device pointers, NULL = the deterministic eval sampling):
   const float* t_rand;   // [n,64] U(0,1): stratified jitter of the coarse samples (perturb > 0)
   const float* u_is;     // [n,16] U(0,1): importance-sampling quantiles (det = False)
@@ -88,6 +89,8 @@ cudaError_t pgn_launch_encode_bf16(const PgnRayRefs& rays, const PgnScalars* sc_
                                    __nv_bfloat16* enc, cudaStream_t stream);
 cudaError_t pgn_launch_mlp_delta(void* dh, int has_in, const void* act, long long m, int C, const float* rs, int rs_stride,
                                  int nrs, const float* wr, float* colsum, float* wsum, int num_sms, cudaStream_t stream);
+cudaError_t pgn_launch_view_delta_bits(void* dG, const float* d_raw, const float* w_rgb, const void* vmask, long long m,
+                                       int num_sms, cudaStream_t stream);
 cudaError_t pgn_launch_delta_chain(const void* dG, const float* d_raw, const void* mask, long long mask_rows, long long m,
                                    const void* wstream, const float* w_alpha, void* dz, float* colsum, int* status,
                                    int num_sms, cudaStream_t stream);

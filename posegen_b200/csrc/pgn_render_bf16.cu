@@ -258,7 +258,7 @@ __device__ __forceinline__ void stg256(void* p, const uint32_t (&v)[8]) {
 template <int MODE>
 __device__ __forceinline__ void epilogue(Smem& sm, uint32_t tmem_acc, uint32_t act_saddr, int slot, const float* __restrict__ w_alpha,
                                          const float* __restrict__ w_rgb, int warp, int lane, float& sig_keep,
-                                         uint4* dump = nullptr, uint4* dump_mask = nullptr) {
+                                         uint4* dump = nullptr, uint4* dump_mask = nullptr, uint2* dump_vmask = nullptr) {
   // dump (training forward only): this thread's row of the layer's row-major activation dump ([rows, 256 | 128] bf16);
   // a thread owns 128 (view layer: 64) consecutive columns, i.e. 256 (128) contiguous bytes of its row
   const int q = warp & 3, half = warp >> 2;
@@ -309,8 +309,8 @@ __device__ __forceinline__ void epilogue(Smem& sm, uint32_t tmem_acc, uint32_t a
           pk[4 * g + i] = pack_relu_bf16x2(__uint_as_float(vb[8 * g + 2 * i]), __uint_as_float(vb[8 * g + 2 * i + 1]));
         sts128(dst0 + (uint32_t)(2 * b + g) * kRunBytes, pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
       }
-      if (dump) {
-        stg256(dump + (col0 >> 3) + 2 * b, pk);                  // 16 columns = one full 32-byte sector
+      if (dump) stg256(dump + (col0 >> 3) + 2 * b, pk);          // 16 columns = one full 32-byte sector
+      if (dump_mask) {
         // ReLU mask of the 16 columns (what the fused delta chain of the backward reads instead of the activations):
         // one compare + one predicated OR per column (a positive fp32 stays positive in bf16)
         uint32_t mb = 0;
@@ -326,8 +326,16 @@ __device__ __forceinline__ void epilogue(Smem& sm, uint32_t tmem_acc, uint32_t a
       for (int i = 0; i < 8; ++i) pk[i] = pack_relu_bf16x2(__uint_as_float(vb[2 * i]), __uint_as_float(vb[2 * i + 1]));
       stg256(dump + (col0 >> 3) + 2 * b, pk);
     }
+    if (MODE == 2 && dump_vmask) {   // masks-only dump: [g > 0] of this thread's 64 view-layer columns as bits
+      uint32_t mb = 0;
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (__uint_as_float(vb[i]) > 0.f) mb |= 1u << (i + (b & 1) * 16);
+      mask_w[b >> 1] |= mb;
+    }
   }
   if (MODE != 2 && dump_mask) *dump_mask = make_uint4(mask_w[0], mask_w[1], mask_w[2], mask_w[3]);
+  if (MODE == 2 && dump_vmask) *dump_vmask = make_uint2(mask_w[0], mask_w[1]);
   // heads: this thread's column half of (rgb_raw, sigma_raw) -> one conflict-free 16-byte store per tile
   if (MODE == 1) sig_keep = sig;
   if (MODE == 2) sts128(smem_u32(&sm.part[slot][half][row][0]), __float_as_uint(r0), __float_as_uint(r1), __float_as_uint(r2), __float_as_uint(sig_keep));
@@ -767,6 +775,7 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
       tc_fence_after_sync();
       uint4* dptr = nullptr;
       uint4* mptr = nullptr;
+      uint2* vptr = nullptr;
       if (kDump && (tc.pass == 0 ? dump.c : dump.f) != nullptr) {       // a pass without a buffer is not dumped
         // training forward: post-ReLU activations of every layer, bf16, per pass [layer][row][256] row-major (view
         // layer: [row][128], after the eight trunk layers); rows in (ray, sample) order:
@@ -774,14 +783,21 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
         const long long m = tc.pass == 0 ? dump.rows_c : dump.rows_f;
         const long long grow = tc.unit * (long long)(kRPG * tc.S) + tc.row0 + ((gwarp & 3) * 32 + lane);
         uint4* base = reinterpret_cast<uint4*>(tc.pass == 0 ? dump.c : dump.f);
-        dptr = base + (size_t)L * 32 * (size_t)m + (size_t)grow * (L == 8 ? 16 : 32);
-        // ReLU masks of the trunk layers behind the activations: [layer 0..7][row][column half] x 128 bits
-        if (L < 8) mptr = base + (size_t)272 * (size_t)m + ((size_t)L * (size_t)m + (size_t)grow) * 2 + (gwarp >> 2);
+        if (!dump.masks_only) {
+          dptr = base + (size_t)L * 32 * (size_t)m + (size_t)grow * (L == 8 ? 16 : 32);
+          // ReLU masks of the trunk layers behind the activations: [layer 0..7][row][column half] x 128 bits
+          if (L < 8) mptr = base + (size_t)272 * (size_t)m + ((size_t)L * (size_t)m + (size_t)grow) * 2 + (gwarp >> 2);
+        } else {
+          // masks only (frozen network, pose gradient): trunk masks [layer 0..7][row][half] x 128 bits, then the view
+          // layer's [row][half] x 64 bits
+          if (L < 8) mptr = base + ((size_t)L * (size_t)m + (size_t)grow) * 2 + (gwarp >> 2);
+          else vptr = reinterpret_cast<uint2*>(base + (size_t)16 * (size_t)m) + (size_t)grow * 2 + (gwarp >> 2);
+        }
       }
       { PROF_T0();
-        if (L == 8) epilogue<2>(sm, tmem_acc, act_saddr, s, net.w_alpha, net.w_rgb, gwarp, lane, sig_keep, dptr, mptr);
-        else if (L == 7) epilogue<1>(sm, tmem_acc, act_saddr, s, net.w_alpha, net.w_rgb, gwarp, lane, sig_keep, dptr, mptr);
-        else epilogue<0>(sm, tmem_acc, act_saddr, s, net.w_alpha, net.w_rgb, gwarp, lane, sig_keep, dptr, mptr);
+        if (L == 8) epilogue<2>(sm, tmem_acc, act_saddr, s, net.w_alpha, net.w_rgb, gwarp, lane, sig_keep, dptr, mptr, vptr);
+        else if (L == 7) epilogue<1>(sm, tmem_acc, act_saddr, s, net.w_alpha, net.w_rgb, gwarp, lane, sig_keep, dptr, mptr, vptr);
+        else epilogue<0>(sm, tmem_acc, act_saddr, s, net.w_alpha, net.w_rgb, gwarp, lane, sig_keep, dptr, mptr, vptr);
         compute_arrive(act_ready_a, lane); if (timed) PROF_ADD(8); }
       if (kStage && L == 8) {
         group_bar_sync(s);

@@ -150,6 +150,33 @@ __global__ void __launch_bounds__(256) pgn_mlp_delta_kernel(uint4* __restrict__ 
   }
 }
 
+// dG[m,128] = [g > 0] * (d_rgb W_rgb) with the view layer's ReLU mask given as bits (masks-only dump of the forward):
+// one thread per (row, 8 columns)
+__global__ void __launch_bounds__(256) pgn_view_delta_bits_kernel(uint4* __restrict__ dG, const float* __restrict__ d_raw,
+                                                                  const float* __restrict__ w_rgb,
+                                                                  const uint32_t* __restrict__ vmask, long long m) {
+  const int cg = threadIdx.x & 15;
+  float wv[3][8];
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) wv[k][i] = __ldg(w_rgb + k * 128 + cg * 8 + i);
+  for (long long row = (long long)blockIdx.x * 16 + (threadIdx.x >> 4); row < m; row += (long long)gridDim.x * 16) {
+    const float r0 = __ldg(d_raw + row * 4), r1 = __ldg(d_raw + row * 4 + 1), r2 = __ldg(d_raw + row * 4 + 2);
+    const uint32_t bits = __ldg(vmask + row * 4 + (cg >> 2)) >> ((cg & 3) * 8);
+    uint32_t ow[4];
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      float p0 = fmaf(r2, wv[2][2 * w], fmaf(r1, wv[1][2 * w], r0 * wv[0][2 * w]));
+      float p1 = fmaf(r2, wv[2][2 * w + 1], fmaf(r1, wv[1][2 * w + 1], r0 * wv[0][2 * w + 1]));
+      if (!(bits & (1u << (2 * w)))) p0 = 0.f;
+      if (!(bits & (1u << (2 * w + 1)))) p1 = 0.f;
+      ow[w] = pack_bf16x2(p0, p1);
+    }
+    dG[(size_t)row * 16 + cg] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+  }
+}
+
 template <int C, int NRS>
 cudaError_t launch_delta(void* dh, int has_in, const void* act, long long m, const float* rs, int rs_stride, const float* wr,
                          float* colsum, float* wsum, int num_sms, cudaStream_t stream) {
@@ -169,6 +196,15 @@ cudaError_t pgn_launch_encode_bf16(const PgnRayRefs& rays, const PgnScalars* sc_
   if (rows == 0) return cudaSuccess;
   const long long grid = min((rows + kEncRows - 1) / kEncRows, (long long)148 * 10);
   pgn_encode_bf16_kernel<<<(unsigned)grid, kEncThreads, 0, stream>>>(rays, sc_dev, z, n_z, enc);
+  return cudaGetLastError();
+}
+
+cudaError_t pgn_launch_view_delta_bits(void* dG, const float* d_raw, const float* w_rgb, const void* vmask, long long m,
+                                       int num_sms, cudaStream_t stream) {
+  if (m == 0) return cudaSuccess;
+  const long long grid = min((m + 15) / 16, (long long)num_sms * 8);
+  pgn_view_delta_bits_kernel<<<(unsigned)grid, 256, 0, stream>>>(reinterpret_cast<uint4*>(dG), d_raw, w_rgb,
+                                                                reinterpret_cast<const uint32_t*>(vmask), m);
   return cudaGetLastError();
 }
 

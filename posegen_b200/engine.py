@@ -220,6 +220,44 @@ class Engine:
                                                          self._stream()))
         return ret, acts
 
+    def render_masks(self, ray_batch, skts, cyls, pose_idx=None, nanfill_chunk=0):
+        """pgn_render_forward_masks: the fused bf16 forward that keeps only the fine pass's ReLU masks (272 B per sample),
+        for the pose gradient through a frozen network.  Returns (outputs incl. raw / z_fine, (trunk_mask, view_mask)):
+        trunk_mask int32 [8, rows, 8] (256 bits per row and trunk layer), view_mask int32 [rows, 4]; rows >= n * 80,
+        samples in (ray, sample) order."""
+        inp, keep = self._inputs(ray_batch, skts, cyls, pose_idx, nanfill_chunk, "bf16")
+        n, dev = inp.n_rays, ray_batch.device
+        f = lambda *sh: torch.empty(sh, dtype=torch.float32, device=dev)  # noqa: E731
+        ret = {"rgb_map": f(n, 3), "disp_map": f(n), "acc_map": f(n), "rgb0": f(n, 3), "disp0": f(n), "acc0": f(n),
+               "z_fine": f(n, T), "raw": f(n, T, 4)}
+        out = _lib.RenderOutputs()
+        for k, v in ret.items():
+            setattr(out, k, v.data_ptr())
+        nbytes = self.lib.pgn_mask_dump_bytes(n)
+        rows = nbytes // 272
+        buf = torch.empty((nbytes // 4,), dtype=torch.int32, device=dev)
+        need = self.lib.pgn_workspace_bytes(self.handle, n)
+        if self._workspace is None or self._workspace.numel() < need or self._workspace.device != dev:
+            self._workspace = torch.empty(max(need, 1 << 20), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(self.lib.pgn_render_forward_masks(self.handle, C.byref(inp), C.byref(out), _ptr(buf),
+                                                         C.c_void_p(self._workspace.data_ptr()), self._workspace.numel(),
+                                                         self._stream()))
+        return ret, (buf[:rows * 64].view(8, rows, 8), buf[rows * 64:].view(rows, 4))
+
+    def view_delta_from_mask(self, d_raw, w_rgb, view_mask):
+        """pgn_view_delta_from_mask: dG bf16 [m,128] = [g > 0] * (d_rgb W_rgb) from the view layer's mask bits."""
+        m = d_raw.shape[0]
+        if d_raw.dtype != torch.float32 or not d_raw.is_contiguous() or tuple(d_raw.shape) != (m, 4) or not d_raw.is_cuda:
+            raise ValueError("d_raw must be contiguous CUDA fp32 [m,4]")
+        if view_mask.dtype != torch.int32 or not view_mask.is_contiguous() or tuple(view_mask.shape) != (m, 4):
+            raise ValueError("view_mask must be contiguous int32 [m,4]")
+        w = w_rgb.detach().float().contiguous()
+        dG = torch.empty((m, 128), dtype=torch.bfloat16, device=d_raw.device)
+        with torch.cuda.device(d_raw.device):
+            _lib.check(self.lib.pgn_view_delta_from_mask(self.handle, _ptr(dG), _ptr(d_raw), _ptr(w), _ptr(view_mask), m, self._stream()))
+        return dG
+
     # ------------------------------------------------------ stage entry points
     def near_far(self, ray_batch, skts, cyls, nanfill_chunk=0):
         inp, keep = self._inputs(ray_batch, skts, cyls, None, nanfill_chunk)

@@ -71,7 +71,7 @@ def chain_wstream(P: Dict[str, torch.Tensor]) -> torch.Tensor:
 
 def mlp_backward(params: Dict[str, torch.Tensor], enc: torch.Tensor, acts: torch.Tensor, d_raw: torch.Tensor,
                  fuse: Callable, want_input_grad: bool = False, want_weight_grad: bool = True,
-                 chain: Callable | None = None) -> Dict[str, torch.Tensor]:
+                 chain: Callable | None = None, mask_dump=None, view_delta: Callable | None = None) -> Dict[str, torch.Tensor]:
     """Weight gradients of one NeRF MLP (core/networks/nerf.py:94-148).
 
     params: fp32 nn.Linear tensors; enc [m,1080] bf16 network input (`pgn_encode_bf16`; may be None when
@@ -85,21 +85,30 @@ def mlp_backward(params: Dict[str, torch.Tensor], enc: torch.Tensor, acts: torch
     `chain(dG, d_raw, mask, mask_rows, wstream, w_alpha)` is `Engine.mlp_delta_chain` (`pgn_mlp_delta_chain`): the
     whole trunk chain dG -> dZ_7 .. dZ_0 (+ bias gradients) as one tcgen05 kernel; without it the chain runs layer by
     layer (a cuBLAS GEMM and a `fuse` pass per layer), which is also what the host-logic test exercises.
+    mask_dump = (trunk_mask int32 [8,m,8], view_mask int32 [m,4]) with `view_delta` = `Engine.view_delta_from_mask`
+    replaces `acts` for a frozen network (want_weight_grad False, `chain` required): the masks-only dump of
+    `pgn_render_forward_masks` is all the input-gradient chain reads.
     Returns {name: fp32 gradient}; with want_input_grad also dL/d(network input) as "_g_xp" [m,432] (v-embed | r
     channels) and "_g_d" [m,648] (view embed), bf16 (the operands of `pgn_encode_backward_bf16`)."""
     m = d_raw.shape[0]
     bf = torch.bfloat16
     if want_weight_grad:
         x_p, d_emb = enc[:, :432], enc[:, 432:]
-    H = [act_layer(acts, l, m) for l in range(8)]
-    G = act_layer(acts, 8, m)
+    if mask_dump is not None and (want_weight_grad or chain is None or view_delta is None):
+        raise ValueError("a masks-only dump serves the input-gradient chain only (want_weight_grad=False, chain, view_delta)")
+    if mask_dump is None:
+        H = [act_layer(acts, l, m) for l in range(8)]
+        G = act_layer(acts, 8, m)
     P = {k: v.detach() for k, v in params.items()}
     W = {k: v.to(bf) for k, v in P.items() if k.startswith("pts_linears") and k.endswith("weight")}
     g: Dict[str, torch.Tensor] = {}
     # rgb head + view layer:  g = relu(W_v [f | d_emb] + b_v),  f = W_f h7 + b_f,  rgb_raw = W_rgb g + b_rgb
     wg = want_weight_grad
-    dG = torch.empty((m, 128), dtype=bf, device=d_raw.device)
-    bias_v, g_rgb = fuse(dG, G, d_raw[:, :3], P["rgb_linear.weight"], False, wg)
+    if mask_dump is not None:
+        dG = view_delta(d_raw, P["rgb_linear.weight"], mask_dump[1])
+    else:
+        dG = torch.empty((m, 128), dtype=bf, device=d_raw.device)
+        bias_v, g_rgb = fuse(dG, G, d_raw[:, :3], P["rgb_linear.weight"], False, wg)
     W_v, W_f, b_f = P["views_linears.0.weight"], P["feature_linear.weight"], P["feature_linear.bias"]
     W_vf = W_v[:, :256]
     if wg:
@@ -115,7 +124,7 @@ def mlp_backward(params: Dict[str, torch.Tensor], enc: torch.Tensor, acts: torch
         g["_g_d"] = torch.mm(dG, W_v[:, 256:].to(bf))
     if chain is not None:
         # trunk: one fused kernel for the eight deltas; the weight gradients are GEMMs over (dZ_l, h_{l-1})
-        mask, mask_rows = act_masks(acts)
+        mask, mask_rows = (mask_dump[0], m) if mask_dump is not None else act_masks(acts)
         dz, colsum = chain(dG, d_raw, mask, mask_rows, chain_wstream(P), P["alpha_linear.weight"].reshape(-1).float().contiguous())
         if wg:
             g["alpha_linear.weight"] = _mm32(d_raw[:, 3:4].to(bf).t(), H[7])

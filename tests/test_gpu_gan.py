@@ -1,5 +1,5 @@
-"""GPU: the differentiable frame render of the GAN step (BASELINE.json configs[4], posegen_b200/gan.py): chunked
-recompute backward to the bone transforms against the training path (itself checked against oracle autograd in
+"""GPU: the differentiable frame render of the GAN step (BASELINE.json configs[4], posegen_b200/gan.py): masks-only
+forward and input-gradient backward to the bone transforms against the training path (itself checked against oracle autograd in
 test_gpu_train.py), the white-background composite against pgn_compose_frame, and the adjoint of the HMR hand-off."""
 import numpy as np
 import pytest
@@ -31,7 +31,7 @@ def test_frame_render_pose_gradient_matches_training_path(rc):
     dead = torch.rand((n,), device=dev, generator=g) < 0.3            # rays without upstream gradient are skipped
     w_rgb[dead] = 0
     w_acc[dead] = 0
-    # (a) frame path: eval-mode forward, chunked recompute in the backward
+    # (a) frame path: eval-mode forward that keeps the ReLU masks, chunked input-gradient backward over the live rays
     rc.eval()
     sk_a = torch.as_tensor(frame.pose.skts, dtype=torch.float32, device=dev).requires_grad_(True)
     rgb, acc = gan.render_frame(rc, rb, sk_a, cy, chunk=1000)
@@ -45,29 +45,31 @@ def test_frame_render_pose_gradient_matches_training_path(rc):
     assert torch.equal(rgb.detach(), ret["rgb_map"].detach()) and torch.equal(acc.detach(), ret["acc_map"].detach())
     ga, gb = sk_a.grad.double(), sk_b.grad.double()
     assert torch.isfinite(ga).all() and float(ga.abs().max()) > 0
-    assert float((ga - gb).norm() / gb.norm()) <= 2e-3, float((ga - gb).norm() / gb.norm())
+    assert float((ga - gb).norm() / gb.norm()) <= 5e-3, float((ga - gb).norm() / gb.norm())
     assert float(ga[:, 3].abs().max()) == 0.0                            # bottom rows carry no gradient
-    # (c) frame path with the live-ray hint: dumps kept in the forward (the budget holds one of the three chunks, the
-    # others fall back to the recompute), same image, same gradient
-    rc.eval()
-    sk_c = torch.as_tensor(frame.pose.skts, dtype=torch.float32, device=dev).requires_grad_(True)
-    one_chunk = 1000 * 80 * 4608
-    rgb_c, acc_c = gan.render_frame(rc, rb, sk_c, cy, chunk=1000, live=~dead, dump_budget_bytes=one_chunk + 1024)
-    ((rgb_c * w_rgb).sum() + (acc_c * w_acc).sum()).backward()
-    # a ray that hits the cylinder renders to the same value whatever batch it is in, up to the association order of its
-    # fine-pass compositing (a ray's 80 samples straddle 128-row tiles differently at another position in its group of 8);
-    # the bbox corners that miss the cylinder take the mean near/far of their batch (the reference's chunk-level
-    # nan-mean, ray_utils.py:328-342), which depends on how the frame is split
-    o_xz, d_xz = rb[:, [0, 2]], rb[:, [3, 5]]
-    to_c = cy[None, :2] - o_xz
-    dist = (to_c[:, 0] * d_xz[:, 1] - to_c[:, 1] * d_xz[:, 0]).abs() / d_xz.norm(dim=-1)
-    hit = dist < cy[2] * (1 - 1e-4)
-    assert float(hit.float().mean()) > 0.3
-    assert float((rgb_c.detach() - rgb.detach())[hit].abs().max()) <= 1e-5
-    assert float((acc_c.detach() - acc.detach())[hit].abs().max()) <= 1e-5
-    assert float((rgb_c.detach() - rgb.detach()).abs().max()) <= 1e-1
-    gc = sk_c.grad.double()
-    assert float((gc - ga).norm() / ga.norm()) <= 5e-2, float((gc - ga).norm() / ga.norm())
+
+
+def test_masks_only_forward_matches_the_full_dump(rc):
+    """pgn_render_forward_masks keeps exactly the ReLU masks of the full activation dump (trunk bits, view layer = [g > 0])
+    and renders the same values."""
+    from posegen_b200.train import act_layer, act_masks
+    frame = syn.synthetic_frame(3, 64, 64)
+    dev = torch.device("cuda")
+    n = 203
+    rb = torch.as_tensor(syn.ray_batch(frame.rays_o, frame.rays_d)[:n], device=dev)
+    sk = torch.as_tensor(frame.pose.skts, dtype=torch.float32, device=dev)
+    cy = torch.as_tensor(frame.pose.cyl, dtype=torch.float32, device=dev)
+    eng = rc.engine(dev)
+    ret_m, (trunk, view) = eng.render_masks(rb, sk, cy)
+    ret_d, acts = eng.render_train(rb, sk, cy, dump_coarse=False)
+    eng.check_status()
+    m = n * 80
+    for k in ("rgb_map", "acc_map", "raw", "z_fine"):
+        assert torch.equal(ret_m[k], ret_d[k]), k
+    full, rows = act_masks(acts["f"])
+    assert torch.equal(trunk[:, :m], full.view(torch.int32).view(8, rows, 8)[:, :m])
+    bits = ((view[:m, :, None] >> torch.arange(32, device=dev, dtype=torch.int32)) & 1).reshape(m, 128).bool()
+    assert torch.equal(bits, act_layer(acts["f"], 8, m) > 0)
 
 
 def test_compose_white_matches_the_device_composite(rc):

@@ -106,7 +106,6 @@ def main():
     ap.add_argument("--poses-per-gpu", type=int, default=2)
     ap.add_argument("--res", type=int, default=512)
     ap.add_argument("--chunk", type=int, default=16384)
-    ap.add_argument("--no-live-hint", action="store_true", help="do not tell the renderer which rays the HMR crop reads (recompute backward)")
     ap.add_argument("--profile", default=None, help="write a torch.profiler kernel table of one step to this file")
     a = ap.parse_args()
     rank, world, local = pdist.env_rank_world()
@@ -135,8 +134,7 @@ def main():
     def step():
         opt.zero_grad(set_to_none=True)
         bones = gen(a.poses_per_gpu, dev)
-        frames, kps = gan.render_pose_images(rc, bones, rest, c2w, H, W, focal, chunk=a.chunk,
-                                             live_crop=None if a.no_live_hint else crop)
+        frames, kps = gan.render_pose_images(rc, bones, rest, c2w, H, W, focal, chunk=a.chunk)
         x = torch.stack([gan.hmr_input(eng, f, crop=crop) for f in frames])
         pred = joints_from_rotmats(hmr(x), rest)
         tgt = kps.float()
@@ -164,8 +162,8 @@ def main():
     n_img = a.poses_per_gpu * world
     line = {"metric": "gan_steps_per_sec", "value": 1e3 / ms, "ms_per_step": ms, "n_gpus": world, "images_per_step": n_img,
             "images_per_sec": n_img / ms * 1e3, "loss": float(stats["loss"]), "generator_grad_norm": float(stats["gnorm"]),
-            "config": f"{a.poses_per_gpu} poses/GPU, {a.res}x{a.res} bbox rays, frozen A-NeRF (bf16 tcgen05) forward + chunked "
-                      f"{'recompute' if a.no_live_hint else 'kept-dump (HMR-crop rays)'} backward to skts (chunk {a.chunk} rays), crop/resize 224, ResNet-50 HMR stand-in, MPJPE, Adam on the generator"}
+            "config": f"{a.poses_per_gpu} poses/GPU, {a.res}x{a.res} bbox rays, frozen A-NeRF (bf16 tcgen05) forward + "
+                      f"masks-only dump, backward to skts over the rays the crop reads (chunk {a.chunk} rays), crop/resize 224, ResNet-50 HMR stand-in, MPJPE, Adam on the generator"}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if a.profile and rank == 0:
