@@ -209,3 +209,38 @@ def test_torch_fk_matches_numpy_helpers_and_is_differentiable():
     (skts[..., :3, :] ** 2).sum().backward()
     assert torch.isfinite(b.grad).all() and float(b.grad.abs().max()) > 0
     assert torch.autograd.gradcheck(lambda x: fk.smpl_skts(x, torch.tensor(rest))[0][..., :3, :], (b[:1].detach().requires_grad_(True),), atol=1e-6)
+
+
+def test_chain_weight_stream_layout():
+    """train.chain_wstream: the 120 K=16 slabs pgn_mlp_delta_chain streams, [K/16][2][256][8] per weight, in the order
+    fold layer, W_7 .. W_1 (include/posegen_b200.h)."""
+    import torch
+    from posegen_b200 import synthetic as syn
+    from posegen_b200.train import chain_wstream
+    P = {k: torch.as_tensor(v) for k, v in syn.synthetic_nerf_state(3).items()}
+    ws = chain_wstream(P)
+    assert ws.dtype == torch.bfloat16 and ws.numel() == 120 * 4096
+    fold = (P["views_linears.0.weight"][:, :256] @ P["feature_linear.weight"]).t().to(torch.bfloat16)      # [256,128]
+    mats = [fold] + [(P[f"pts_linears.{l}.weight"][:, 432:] if l == 5 else P[f"pts_linears.{l}.weight"]).t().to(torch.bfloat16)
+                     for l in range(7, 0, -1)]
+    off = 0
+    for w in mats:
+        K = w.shape[1]
+        slabs = ws[off:off + 256 * K].view(K // 16, 2, 256, 8)
+        for (ks, kc, n, e) in ((0, 0, 0, 0), (K // 16 - 1, 1, 255, 7), (1, 0, 17, 3), (2, 1, 200, 5)):
+            assert slabs[ks, kc, n, e] == w[n, ks * 16 + kc * 8 + e]
+        off += 256 * K
+    assert off == ws.numel()
+
+
+def test_activation_dump_views():
+    """train.act_layer / act_masks address the flat dump buffer of pgn_render_forward_train as documented."""
+    import torch
+    from posegen_b200.train import ACT_ROW_ELEMS, act_layer, act_masks
+    rows, m = 1024, 1000
+    buf = torch.arange(rows * ACT_ROW_ELEMS, dtype=torch.float32).to(torch.bfloat16)
+    assert act_layer(buf, 0, m).shape == (m, 256) and act_layer(buf, 8, m).shape == (m, 128)
+    assert act_layer(buf, 3, m).data_ptr() == buf.data_ptr() + 3 * rows * 256 * 2
+    assert act_layer(buf, 8, m).data_ptr() == buf.data_ptr() + 8 * rows * 256 * 2
+    mask, r = act_masks(buf)
+    assert r == rows and mask.data_ptr() == buf.data_ptr() + rows * 4352 and mask.numel() * 2 == rows * 256
