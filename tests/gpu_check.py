@@ -1,6 +1,6 @@
 """GPU bring-up / parity report (run on the B200 box):
 
-    python tools/gpu_check.py <step> [<step> ...]     steps: probe stages mlp render time
+    python tests/gpu_check.py <step> [<step> ...]     steps: probe stages mlp render time
 
 Prints error metrics of every stage against the oracle / golden fixtures and appends them
 to gpurun_out/gpu_check.jsonl.  Each step is independent so a fault in one does not hide

@@ -5,7 +5,7 @@ posegen_b200.RayCaster in train mode, one NCCL all-reduce of the gradients, Adam
 training-time randomness (perturb = 1, raw_noise_std = 1, configs/surreal/surreal.txt; `--deterministic` for the
 parity setting).  Auxiliary to bench.py; prints one JSON line on rank 0.
 
-    python tools/train_step_bench.py [--steps 20] [--cpu-baseline]
+    python tools/train_step_bench.py [--steps 20] [--graph] [--deterministic]
     python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/train_step_bench.py
 """
 import argparse
@@ -39,7 +39,6 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--cpu-baseline", action="store_true")
     ap.add_argument("--deterministic", action="store_true", help="perturb = 0, raw_noise_std = 0")
     ap.add_argument("--graph", action="store_true", help="capture the step into a CUDA graph (posegen_b200.train.GraphedTrainStep)")
     ap.add_argument("--profile", default=None, help="write a torch.profiler kernel table of 3 steps to this file (after the timed run)")
@@ -93,20 +92,6 @@ def main():
             "rays_per_sec": n * world / ms * 1e3, "final_loss": float(loss.detach()),
             "config": "3072 rays/GPU from 256 poses x 12 rays, coarse+fine, fwd+bwd+allreduce+Adam, "
                       + ("perturb=0, raw_noise_std=0" if a.deterministic else "perturb=1, raw_noise_std=1") + ", bf16 tensor-core forward" + (", CUDA graph" if a.graph else "")}
-    if a.cpu_baseline and rank == 0:
-        from oracle import render_oracle as orc
-        torch.set_num_threads(os.cpu_count() or 1)
-        nets, emb = orc.nets_from_ckpt(ckpt), orc.embed_params_from_ckpt(ckpt)
-        for net in nets:
-            for v in net.values():
-                v.requires_grad_(True)
-        m = 768                                          # bounded sample of the batch
-        t0 = time.perf_counter()
-        r = orc.render_rays(torch.as_tensor(rb[:m]), torch.as_tensor(sk[:m]), torch.as_tensor(cy[:m]), nets, emb)
-        l = ((r["rgb_map"] + (1 - r["acc_map"][:, None]) - tgt[:m].cpu()) ** 2).mean() + ((r["rgb0"] + (1 - r["acc0"][:, None]) - tgt[:m].cpu()) ** 2).mean()
-        l.backward()
-        sec = time.perf_counter() - t0
-        line["cpu_baseline"] = {"rays_per_sec": m / sec, "cores": os.cpu_count(), "kind": "port", "sample": f"{m} rays of the batch, fwd+bwd (autograd through the oracle), {sec:.1f} s"}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if a.profile and rank == 0:
