@@ -312,12 +312,13 @@ __device__ __forceinline__ void epilogue(Smem& sm, uint32_t tmem_acc, uint32_t a
       if (dump) stg256(dump + (col0 >> 3) + 2 * b, pk);          // 16 columns = one full 32-byte sector
       if (dump_mask) {
         // ReLU mask of the 16 columns (what the fused delta chain of the backward reads instead of the activations):
-        // one compare + one predicated OR per column (a positive fp32 stays positive in bf16)
+        // one funnel shift per column collects the accumulators' sign bits (last column first, so column 0 ends up in
+        // bit 0); active = not negative (a positive fp32 stays positive in bf16; an exact +0 counts as active, its
+        // activation and hence its delta's effect are zero anyway)
         uint32_t mb = 0;
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (__uint_as_float(vb[i]) > 0.f) mb |= 1u << (i + (b & 1) * 16);
-        mask_w[b >> 1] |= mb;
+        for (int i = 15; i >= 0; --i) mb = __funnelshift_l(vb[i], mb, 1);
+        mask_w[b >> 1] |= (~mb & 0xffffu) << ((b & 1) * 16);
       }
     }
     if (MODE == 2 && dump) {      // view layer: relu(g) of this thread's 16 columns
@@ -329,9 +330,8 @@ __device__ __forceinline__ void epilogue(Smem& sm, uint32_t tmem_acc, uint32_t a
     if (MODE == 2 && dump_vmask) {   // masks-only dump: [g > 0] of this thread's 64 view-layer columns as bits
       uint32_t mb = 0;
 #pragma unroll
-      for (int i = 0; i < 16; ++i)
-        if (__uint_as_float(vb[i]) > 0.f) mb |= 1u << (i + (b & 1) * 16);
-      mask_w[b >> 1] |= mb;
+      for (int i = 15; i >= 0; --i) mb = __funnelshift_l(vb[i], mb, 1);
+      mask_w[b >> 1] |= (~mb & 0xffffu) << ((b & 1) * 16);
     }
   }
   if (MODE != 2 && dump_mask) *dump_mask = make_uint4(mask_w[0], mask_w[1], mask_w[2], mask_w[3]);
