@@ -433,7 +433,9 @@ __device__ __forceinline__ bool issue_layer(IssuerCtx& ic) {
 #define PROF_ADD(slot) do { if (kProf) pacc[slot] += (unsigned long long)(clock64() - _pt0); } while (0)
 
 // ------------------------------------------------------------------ the kernel
-template <bool kStage, bool kProf, bool kDump>
+// kDump: 0 = inference, 1 = training forward (activation + mask dump, training-time randomness), 2 = masks only
+// (deterministic sampling; the fine pass's ReLU masks for the pose gradient through a frozen network)
+template <bool kStage, bool kProf, int kDump>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf16Net net_f,
                        const PgnScalars* __restrict__ scp, const float* __restrict__ near_far,
@@ -684,7 +686,7 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
               *p = v;
             }
             const float nn = __ldg(near_far + ri * 2), ff = __ldg(near_far + ri * 2 + 1);
-            if (kDump && dump.t_rand) {
+            if (kDump == 1 && dump.t_rand) {
               zc[lane] = pgn_coarse_z_jitter(nn, ff, sc.t_coarse, lane, __ldg(dump.t_rand + ri * PGN_S + lane));
               zc[lane + 32] = pgn_coarse_z_jitter(nn, ff, sc.t_coarse, lane + 32, __ldg(dump.t_rand + ri * PGN_S + lane + 32));
             } else {
@@ -698,7 +700,7 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
             __syncwarp();
             pgn_composite_segment_warp<PGN_S, true, 2>(rawrows, zc, 0, PGN_S, dn, sc.density_scale, sc.rgb_eps, lane, cr, wts,
                                                        out.alpha0 ? out.alpha0 + ri * PGN_S : nullptr,
-                                                       (kDump && dump.noise0) ? dump.noise0 + ri * PGN_S : nullptr);
+                                                       (kDump == 1 && dump.noise0) ? dump.noise0 + ri * PGN_S : nullptr);
             if (lane == 0) {
               float rgb3[3], disp, acc;
               pgn_composite_finalize(cr, rgb3, &disp, &acc);
@@ -732,7 +734,7 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
             float* cr = sm.carry[s][rl];
             pgn_composite_segment_warp<PGN_T, true, 3>(rawrows, sm.zf[s][rl], s0, s1, dn, sc.density_scale, sc.rgb_eps, lane, cr,
                                                        nullptr, out.alpha ? out.alpha + ri * PGN_T : nullptr,
-                                                       (kDump && dump.noise) ? dump.noise + ri * PGN_T : nullptr);
+                                                       (kDump == 1 && dump.noise) ? dump.noise + ri * PGN_T : nullptr);
             if (out.raw) for (int i = lane; i < (s1 - s0) * 4; i += 32) out.raw[(ri * PGN_T + s0) * 4 + i] = rawrows[i];
             if (s1 == PGN_T && lane == 0) {
               float rgb3[3], disp, acc;
@@ -754,7 +756,7 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
           if (stage == 2) {
             pgn_sample_pdf_cdf_warp_fast(zc, wts, lane, scr);
           } else {
-            if (kDump && dump.u_is)
+            if (kDump == 1 && dump.u_is)
               pgn_sample_pdf_draw_warp_rand(zc, dump.u_is + ri * PGN_I, lane, scr, out.z_samples ? out.z_samples + ri * PGN_I : nullptr,
                                             sm.zf[s][rl], out.pdf_inds ? out.pdf_inds + ri * PGN_I : nullptr);
             else
@@ -776,23 +778,25 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
       uint4* dptr = nullptr;
       uint4* mptr = nullptr;
       uint2* vptr = nullptr;
-      if (kDump && (tc.pass == 0 ? dump.c : dump.f) != nullptr) {       // a pass without a buffer is not dumped
+      if (kDump == 2 && tc.pass == 1) {
+        // masks only (frozen network, pose gradient): trunk masks [layer 0..7][row][half] x 128 bits of the fine pass,
+        // then the view layer's [row][half] x 64 bits
+        const long long m = dump.rows_f;
+        const long long grow = tc.unit * (long long)(kRPG * tc.S) + tc.row0 + ((gwarp & 3) * 32 + lane);
+        uint4* base = reinterpret_cast<uint4*>(dump.f);
+        if (L < 8) mptr = base + ((size_t)L * (size_t)m + (size_t)grow) * 2 + (gwarp >> 2);
+        else vptr = reinterpret_cast<uint2*>(base + (size_t)16 * (size_t)m) + (size_t)grow * 2 + (gwarp >> 2);
+      }
+      if (kDump == 1 && (tc.pass == 0 ? dump.c : dump.f) != nullptr) {       // a pass without a buffer is not dumped
         // training forward: post-ReLU activations of every layer, bf16, per pass [layer][row][256] row-major (view
         // layer: [row][128], after the eight trunk layers); rows in (ray, sample) order:
         // row = unit * rows_per_group + tile * 128 + row_in_tile (units padded to pairs)
         const long long m = tc.pass == 0 ? dump.rows_c : dump.rows_f;
         const long long grow = tc.unit * (long long)(kRPG * tc.S) + tc.row0 + ((gwarp & 3) * 32 + lane);
         uint4* base = reinterpret_cast<uint4*>(tc.pass == 0 ? dump.c : dump.f);
-        if (!dump.masks_only) {
-          dptr = base + (size_t)L * 32 * (size_t)m + (size_t)grow * (L == 8 ? 16 : 32);
-          // ReLU masks of the trunk layers behind the activations: [layer 0..7][row][column half] x 128 bits
-          if (L < 8) mptr = base + (size_t)272 * (size_t)m + ((size_t)L * (size_t)m + (size_t)grow) * 2 + (gwarp >> 2);
-        } else {
-          // masks only (frozen network, pose gradient): trunk masks [layer 0..7][row][half] x 128 bits, then the view
-          // layer's [row][half] x 64 bits
-          if (L < 8) mptr = base + ((size_t)L * (size_t)m + (size_t)grow) * 2 + (gwarp >> 2);
-          else vptr = reinterpret_cast<uint2*>(base + (size_t)16 * (size_t)m) + (size_t)grow * 2 + (gwarp >> 2);
-        }
+        dptr = base + (size_t)L * 32 * (size_t)m + (size_t)grow * (L == 8 ? 16 : 32);
+        // ReLU masks of the trunk layers behind the activations: [layer 0..7][row][column half] x 128 bits
+        if (L < 8) mptr = base + (size_t)272 * (size_t)m + ((size_t)L * (size_t)m + (size_t)grow) * 2 + (gwarp >> 2);
       }
       { PROF_T0();
         if (L == 8) epilogue<2>(sm, tmem_acc, act_saddr, s, net.w_alpha, net.w_rgb, gwarp, lane, sig_keep, dptr, mptr, vptr);
@@ -828,7 +832,7 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
       if (!kStage && L == 0 && !tables_ready) {      // (normally built ahead, in the shadow of the previous tile's view layer)
         PROF_T0();
         build_tables(tc);
-        rc = make_row_ctx(sm, sc, tc, near_far, s, row, kDump ? dump.t_rand : nullptr);
+        rc = make_row_ctx(sm, sc, tc, near_far, s, row, kDump == 1 ? dump.t_rand : nullptr);
         group_bar_sync(s);                 // tables visible to every thread of the group
         if (timed) PROF_ADD(14);
       }
@@ -883,7 +887,7 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
             if (k + 1 < kTiles) make_ctx(i, k + 1, nx); else make_ctx(i + 1, 0, nx);
             group_bar_sync(s);               // every thread is done reading this tile's tables
             build_tables(nx);
-            rc = make_row_ctx(sm, sc, nx, near_far, s, row, kDump ? dump.t_rand : nullptr);
+            rc = make_row_ctx(sm, sc, nx, near_far, s, row, kDump == 1 ? dump.t_rand : nullptr);
             group_bar_sync(s);               // tables visible to every thread of the group
             tables_ready = true;
             if (timed) PROF_ADD(14);
@@ -1014,13 +1018,15 @@ cudaError_t pgn_pack_bf16_net(const float* const* w_dev, const float* const* b_d
 static cudaError_t configure_bf16() {
   static bool done = false;
   if (done) return cudaSuccess;
-  cudaError_t e = cudaFuncSetAttribute(pgn_render_bf16_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem) + 1024);
+  cudaError_t e = cudaFuncSetAttribute(pgn_render_bf16_kernel<false, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem) + 1024);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(pgn_render_bf16_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem) + 1024);
+  e = cudaFuncSetAttribute(pgn_render_bf16_kernel<false, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem) + 1024);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(pgn_render_bf16_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem) + 1024);
+  e = cudaFuncSetAttribute(pgn_render_bf16_kernel<true, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem) + 1024);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(pgn_render_bf16_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem) + 1024);
+  e = cudaFuncSetAttribute(pgn_render_bf16_kernel<false, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem) + 1024);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(pgn_render_bf16_kernel<false, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem) + 1024);
   if (e != cudaSuccess) return e;
   done = true;
   return cudaSuccess;
@@ -1036,14 +1042,17 @@ cudaError_t pgn_launch_render_bf16(const PgnRayRefs& rays, const PgnOutputs& out
   const long long n_pairs = (n_groups + 1) / 2;
   const int grid = 2 * (int)min((long long)(num_sms / 2), n_pairs);      // clusters of 2 CTAs
   const PgnActDump nodump{};
-  if (dump)
-    pgn_render_bf16_kernel<false, false, true><<<grid, kThreads, sizeof(Smem) + 1024, stream>>>(rays, out, nc, nf, sc_dev, near_far,
-                                                                                                nullptr, 0, nullptr, status, nullptr, *dump);
+  if (dump && dump->masks_only)
+    pgn_render_bf16_kernel<false, false, 2><<<grid, kThreads, sizeof(Smem) + 1024, stream>>>(rays, out, nc, nf, sc_dev, near_far,
+                                                                                             nullptr, 0, nullptr, status, nullptr, *dump);
+  else if (dump)
+    pgn_render_bf16_kernel<false, false, 1><<<grid, kThreads, sizeof(Smem) + 1024, stream>>>(rays, out, nc, nf, sc_dev, near_far,
+                                                                                             nullptr, 0, nullptr, status, nullptr, *dump);
   else if (prof)
-    pgn_render_bf16_kernel<false, true, false><<<grid, kThreads, sizeof(Smem) + 1024, stream>>>(rays, out, nc, nf, sc_dev, near_far,
+    pgn_render_bf16_kernel<false, true, 0><<<grid, kThreads, sizeof(Smem) + 1024, stream>>>(rays, out, nc, nf, sc_dev, near_far,
                                                                                                 nullptr, 0, nullptr, status, prof, nodump);
   else
-    pgn_render_bf16_kernel<false, false, false><<<grid, kThreads, sizeof(Smem) + 1024, stream>>>(rays, out, nc, nf, sc_dev, near_far,
+    pgn_render_bf16_kernel<false, false, 0><<<grid, kThreads, sizeof(Smem) + 1024, stream>>>(rays, out, nc, nf, sc_dev, near_far,
                                                                                                  nullptr, 0, nullptr, status, nullptr, nodump);
   return cudaGetLastError();
 }
@@ -1057,7 +1066,7 @@ cudaError_t pgn_launch_mlp_bf16(const PgnBf16Net& net, const float* enc, long lo
   const int grid = 2 * (int)min((long long)(num_sms / 2), (n_tiles + 1) / 2);
   PgnRayRefs rays{};
   PgnOutputs out{};
-  pgn_render_bf16_kernel<true, false, false><<<grid, kThreads, sizeof(Smem) + 1024, stream>>>(rays, out, net, net, sc_dev, nullptr,
+  pgn_render_bf16_kernel<true, false, 0><<<grid, kThreads, sizeof(Smem) + 1024, stream>>>(rays, out, net, net, sc_dev, nullptr,
                                                                                               enc, m, raw, status, nullptr, PgnActDump{});
   return cudaGetLastError();
 }
