@@ -27,6 +27,16 @@
 
 using namespace pgn;
 
+// -DPGN_CHAIN_PROF: per-role wait / work cycle counters of CTA 0 (tools/chain_prof.py reads them); off in the product build
+#ifdef PGN_CHAIN_PROF
+__device__ unsigned long long g_chain_prof[16];
+#define CP_T0() const long long cp_t0 = clock64()
+#define CP_ADD(slot) do { if (blockIdx.x == 0) atomicAdd(&g_chain_prof[slot], (unsigned long long)(clock64() - cp_t0)); } while (0)
+#else
+#define CP_T0()
+#define CP_ADD(slot)
+#endif
+
 namespace {
 
 constexpr int kTile = 128;                       // rows per UMMA tile
@@ -39,6 +49,7 @@ constexpr int kStages = 10;                     // 80 KB of weight slabs in flig
 constexpr int kLayers = 8;                       // fold layer (K = 128) + W_7 .. W_1 (K = 256)
 constexpr int kSlabsPerBlock = 8 + 7 * 16;       // 120
 constexpr int kThreads = 768;
+constexpr int kGroup = 4;                       // weight slabs (K-steps) issued per tile before switching accumulators
 
 struct __align__(1024) ChainSmem {
   uint8_t a[kTiles][kABytes];
@@ -100,21 +111,36 @@ pgn_delta_chain_kernel(const uint4* __restrict__ dG, const float* __restrict__ d
       uint32_t slab = 0, ready_phase = 0;
       for (long long blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
         for (int j = 0; j < kLayers; ++j, ++ready_phase) {
+          { CP_T0();
           for (int t = 0; t < kTiles; ++t)
             if (!mbar_wait(&sm.act_ready[t], ready_phase & 1, status, 702)) return;
+          CP_ADD(0); }
           tc_fence_after_sync();
+          // K-steps are issued in groups of kGroup slabs per tile: consecutive MMAs that accumulate into the SAME TMEM
+          // tile pipeline back to back (131 cycles each); alternating the two accumulators every instruction costs 2x
           const int nks = j == 0 ? 8 : 16;
-          for (int ks = 0; ks < nks; ++ks, ++slab) {
-            const uint32_t st = slab % kStages, use = slab / kStages;
-            if (!mbar_wait(&sm.w_full[st], use & 1, status, 703)) return;
+          for (int ks0 = 0; ks0 < nks; ks0 += kGroup) {
+#pragma unroll
+            for (int g = 0; g < kGroup; ++g) {
+              const uint32_t sl = slab + g, st = sl % kStages, use = sl / kStages;
+              CP_T0();
+              if (!mbar_wait(&sm.w_full[st], use & 1, status, 703)) return;
+              CP_ADD(1);
+            }
             tc_fence_after_sync();
-            const uint64_t bd = umma_smem_desc(smem_u32(sm.w[st]), 256 * 16, 128);
 #pragma unroll
             for (int t = 0; t < kTiles; ++t) {
-              const uint64_t ad = umma_smem_desc(smem_u32(sm.a[t]) + (uint32_t)ks * 2 * kRun, kRun, 128);
-              umma_bf16(tmem + (uint32_t)t * 256, ad, bd, idesc, ks > 0 ? 1u : 0u);
+#pragma unroll
+              for (int g = 0; g < kGroup; ++g) {
+                const uint32_t st = (slab + g) % kStages;
+                const uint64_t bd = umma_smem_desc(smem_u32(sm.w[st]), 256 * 16, 128);
+                const uint64_t ad = umma_smem_desc(smem_u32(sm.a[t]) + (uint32_t)(ks0 + g) * 2 * kRun, kRun, 128);
+                umma_bf16(tmem + (uint32_t)t * 256, ad, bd, idesc, (ks0 + g) > 0 ? 1u : 0u);
+              }
             }
-            umma_commit(&sm.w_empty[st]);
+#pragma unroll
+            for (int g = 0; g < kGroup; ++g) umma_commit(&sm.w_empty[(slab + g) % kStages]);
+            slab += kGroup;
           }
           umma_commit(&sm.acc_full);
         }
@@ -122,7 +148,9 @@ pgn_delta_chain_kernel(const uint4* __restrict__ dG, const float* __restrict__ d
     }
   } else if (warp >= 20) {
     // ---------------------------------------------------------------- dZ store + bias-gradient group (128 threads)
-    // warp w owns the 8 runs (64 columns) 8w .. 8w+7 of a tile; lane = (row & 3) + 4 * (run & 7)
+    // warp w owns the 8 runs (64 columns) 8w .. 8w+7 of a tile; lane = (row & 3) + 4 * (run & 7): a warp store covers
+    // 4 rows x 128 contiguous bytes (full lines).  (8 rows x 4 runs would make the LDS.128 conflict-free, but its
+    // 64-byte row pieces made this group 1.6x slower: it is bound by its global stores, all SMs storing at once.)
     const int dw = warp - 20, rr = lane & 3, run = dw * 8 + (lane >> 2);
     uint32_t phase = 0;
     for (long long blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
@@ -130,7 +158,8 @@ pgn_delta_chain_kernel(const uint4* __restrict__ dG, const float* __restrict__ d
       for (int j = 0; j < kLayers; ++j, ++phase) {
         const int L = 7 - j;
         for (int t = 0; t < kTiles; ++t) {
-          if (!mbar_wait(&sm.cs_ready[t], phase & 1, status, 705)) return;
+          { CP_T0(); if (!mbar_wait(&sm.cs_ready[t], phase & 1, status, 705)) return; if (warp == 20 && lane == 0) CP_ADD(2); }
+          CP_T0();
           const uint32_t src = smem_u32(sm.a[t]) + (uint32_t)run * kRun + rr * 16;
           const long long g0 = r0 + t * kTile + rr;
           uint4* out = dz + ((size_t)L * m + (size_t)g0) * 32 + run;
@@ -158,6 +187,7 @@ pgn_delta_chain_kernel(const uint4* __restrict__ dG, const float* __restrict__ d
             for (int e = 0; e < 8; ++e) sm.colsum[L][run * 8 + e] += acc[e];
           }
           __syncwarp();
+          if (warp == 20 && lane == 0) CP_ADD(3);
           if (lane == 0) mbar_arrive_local(&sm.cs_done[t]);
         }
       }
@@ -209,12 +239,15 @@ pgn_delta_chain_kernel(const uint4* __restrict__ dG, const float* __restrict__ d
       for (int j = 0; j < kLayers; ++j, ++acc_phase) {
         const int L = 7 - j;                        // this layer's output is dL/dh_L; its mask is [h_L > 0]
         const uint4 mk = gr < m ? __ldg(mask + ((size_t)L * mask_rows + gr) * 2 + half) : make_uint4(0u, 0u, 0u, 0u);
-        if (!mbar_wait(&sm.acc_full, acc_phase & 1, status, 704)) return;
+        { CP_T0(); if (!mbar_wait(&sm.acc_full, acc_phase & 1, status, 704)) return; if (tid == 128) CP_ADD(4); }
         tc_fence_after_sync();
         if (j > 0) {                                 // the previous deltas have been stored / summed out of the A tile
+          CP_T0();
           if (!mbar_wait(&sm.cs_done[t], csd_phase & 1, status, 707)) return;
+          if (tid == 128) CP_ADD(5);
           ++csd_phase;
         }
+        CP_T0();
         const uint32_t mw[4] = {mk.x, mk.y, mk.z, mk.w};
         uint32_t v[2][16];
         tmem_ld_32x16(taddr, v[0]);
@@ -242,6 +275,7 @@ pgn_delta_chain_kernel(const uint4* __restrict__ dG, const float* __restrict__ d
         tc_fence_before_sync();
         if (j + 1 < kLayers) fence_proxy_async_smem();
         __syncwarp();
+        if (tid == 128) CP_ADD(6);
         if (lane == 0) {
           if (j + 1 < kLayers) mbar_arrive_local(&sm.act_ready[t]);      // next layer's A operand (and a free accumulator)
           mbar_arrive_local(&sm.cs_ready[t]);                            // dZ_L of this tile is in shared memory
@@ -276,3 +310,12 @@ cudaError_t pgn_launch_delta_chain(const void* dG, const float* d_raw, const voi
                                                            reinterpret_cast<uint4*>(dz), colsum, status);
   return cudaGetLastError();
 }
+
+#ifdef PGN_CHAIN_PROF
+extern "C" __attribute__((visibility("default"))) int pgn_debug_chain_prof(unsigned long long* out16, int reset) {
+  unsigned long long z[16] = {0};
+  if (cudaMemcpyFromSymbol(out16, g_chain_prof, sizeof(z)) != cudaSuccess) return -1;
+  if (reset && cudaMemcpyToSymbol(g_chain_prof, z, sizeof(z)) != cudaSuccess) return -1;
+  return 0;
+}
+#endif
