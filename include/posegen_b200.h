@@ -239,9 +239,11 @@ PGN_API int  pgn_mlp_delta(pgn_context* ctx, void* dh, int32_t has_input, const 
  * wstream: the eight weights W'_j [256, K_j] bf16 (W'_0 = (W_v[:, :256] W_f)^T with K = 128; W'_j = W_l^T for
  * l = 8 - j, K = 256, the skip layer l = 5 without its 432 input columns), each cut into K = 16 slabs laid out
  * [K/16][2][256][8] (UMMA K-major core matrices), concatenated: 120 slabs of 8 KB.
- * Outputs: dz bf16 [8][m][256] (dz[l] = dZ_l, row-major) and colsum fp32 [8][256] (bias gradients). */
+ * Outputs: dz bf16 [8][m][256] (dz[l] = dZ_l, row-major) and colsum fp32 [8][256] (bias gradients), for the layers
+ * whose bit is set in layer_mask (0xFF: all; a frozen network's pose gradient reads only dZ_0 and dZ_5: 0x21). */
 PGN_API int  pgn_mlp_delta_chain(pgn_context* ctx, const void* dG, const float* d_raw, const void* mask, int64_t mask_rows,
-                                 int64_t m, const void* wstream, const float* w_alpha, void* dz, float* colsum, void* stream);
+                                 int64_t m, const void* wstream, const float* w_alpha, void* dz, float* colsum,
+                                 uint32_t layer_mask, void* stream);
 
 /* NeRF.forward (core/networks/nerf.py:133-148) on explicit encodings:
  * enc [m,1080] -> raw [m,4].  precision selects the MLP engine. */

@@ -96,7 +96,7 @@ def load() -> C.CDLL:
     lib.pgn_mask_dump_bytes.restype = C.c_size_t
     lib.pgn_render_forward_masks.argtypes = [vp, C.POINTER(RenderInputs), C.POINTER(RenderOutputs), vp, vp, C.c_size_t, vp]
     lib.pgn_view_delta_from_mask.argtypes = [vp, vp, vp, vp, vp, i64, vp]
-    lib.pgn_mlp_delta_chain.argtypes = [vp, vp, vp, vp, i64, i64, vp, vp, vp, vp, vp]
+    lib.pgn_mlp_delta_chain.argtypes = [vp, vp, vp, vp, i64, i64, vp, vp, vp, vp, C.c_uint32, vp]
     lib.pgn_composite.argtypes = [vp, C.POINTER(RenderInputs), vp, vp, i32, vp, vp, vp, vp, vp, vp]
     lib.pgn_composite_backward.argtypes = [vp, C.POINTER(RenderInputs), vp, vp, i32, vp, vp, vp, vp, vp]
     lib.pgn_encode_backward.argtypes = [vp, C.POINTER(RenderInputs), vp, i32, vp, vp, vp]

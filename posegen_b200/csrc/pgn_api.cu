@@ -342,11 +342,11 @@ int pgn_view_delta_from_mask(pgn_context* c, void* dG, const float* d_raw, const
 }
 
 int pgn_mlp_delta_chain(pgn_context* c, const void* dG, const float* d_raw, const void* mask, int64_t mask_rows, int64_t m,
-                        const void* wstream, const float* w_alpha, void* dz, float* colsum, void* stream) {
+                        const void* wstream, const float* w_alpha, void* dz, float* colsum, uint32_t layer_mask, void* stream) {
   if (!c || !dG || !d_raw || !mask || !wstream || !w_alpha || !dz || !colsum || m < 0 || mask_rows < m)
     return fail(PGN_E_INVALID, "pgn_mlp_delta_chain: bad argument");
   PGN_CUDA(cudaSetDevice(c->cfg.device));
-  PGN_CUDA(pgn_launch_delta_chain(dG, d_raw, mask, mask_rows, m, wstream, w_alpha, dz, colsum, c->d_status, c->num_sms, (cudaStream_t)stream));
+  PGN_CUDA(pgn_launch_delta_chain(dG, d_raw, mask, mask_rows, m, wstream, w_alpha, dz, colsum, layer_mask, c->d_status, c->num_sms, (cudaStream_t)stream));
   c->launches++;
   return PGN_OK;
 }

@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 pgn_delta_chain_kernel(const uint4* __restrict__ dG, const float* __restrict__ d_raw, const uint4* __restrict__ mask,
                        long long mask_rows, long long m, const uint8_t* __restrict__ wstream,
                        const float* __restrict__ w_alpha, uint4* __restrict__ dz, float* __restrict__ colsum_g,
-                       int* __restrict__ status_g) {
+                       int* __restrict__ status_g, unsigned layer_mask) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   ChainSmem& sm = *reinterpret_cast<ChainSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   volatile int* status = status_g;
@@ -166,6 +166,7 @@ pgn_delta_chain_kernel(const uint4* __restrict__ dG, const float* __restrict__ d
           float acc[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+          if ((layer_mask >> L) & 1u)                     // layers nobody reads (frozen network) are neither stored nor summed
 #pragma unroll 8
           for (int i = 0; i < 32; ++i) {
             const uint4 v = lds128(src + (uint32_t)i * 64);
@@ -291,8 +292,8 @@ pgn_delta_chain_kernel(const uint4* __restrict__ dG, const float* __restrict__ d
 }  // namespace
 
 cudaError_t pgn_launch_delta_chain(const void* dG, const float* d_raw, const void* mask, long long mask_rows, long long m,
-                                   const void* wstream, const float* w_alpha, void* dz, float* colsum, int* status,
-                                   int num_sms, cudaStream_t stream) {
+                                   const void* wstream, const float* w_alpha, void* dz, float* colsum, unsigned layer_mask,
+                                   int* status, int num_sms, cudaStream_t stream) {
   cudaError_t e = cudaMemsetAsync(colsum, 0, sizeof(float) * kLayers * 256, stream);
   if (e != cudaSuccess || m == 0) return e;
   const size_t smem = sizeof(ChainSmem) + 1024;
@@ -307,7 +308,7 @@ cudaError_t pgn_launch_delta_chain(const void* dG, const float* d_raw, const voi
   pgn_delta_chain_kernel<<<grid, kThreads, smem, stream>>>(reinterpret_cast<const uint4*>(dG), d_raw,
                                                            reinterpret_cast<const uint4*>(mask), mask_rows, m,
                                                            reinterpret_cast<const uint8_t*>(wstream), w_alpha,
-                                                           reinterpret_cast<uint4*>(dz), colsum, status);
+                                                           reinterpret_cast<uint4*>(dz), colsum, status, layer_mask);
   return cudaGetLastError();
 }
 

@@ -92,8 +92,8 @@ cudaError_t pgn_launch_mlp_delta(void* dh, int has_in, const void* act, long lon
 cudaError_t pgn_launch_view_delta_bits(void* dG, const float* d_raw, const float* w_rgb, const void* vmask, long long m,
                                        int num_sms, cudaStream_t stream);
 cudaError_t pgn_launch_delta_chain(const void* dG, const float* d_raw, const void* mask, long long mask_rows, long long m,
-                                   const void* wstream, const float* w_alpha, void* dz, float* colsum, int* status,
-                                   int num_sms, cudaStream_t stream);
+                                   const void* wstream, const float* w_alpha, void* dz, float* colsum, unsigned layer_mask,
+                                   int* status, int num_sms, cudaStream_t stream);
 cudaError_t pgn_launch_pose_fk(const float* bones, const float* rest, int n_poses, float ext, float top_ratio, float bot_ratio,
                                float* skts, float* kps, float* cyls, float* l2ws, cudaStream_t stream);
 cudaError_t pgn_launch_hmr_input(const float* image, int H, int W, int x0, int y0, int x1, int y1, int R,

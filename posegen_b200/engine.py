@@ -304,9 +304,10 @@ class Engine:
                                               _ptr(colsum), _ptr(wsum), self._stream()))
         return colsum, wsum
 
-    def mlp_delta_chain(self, dG, d_raw, mask, mask_rows, wstream, w_alpha):
+    def mlp_delta_chain(self, dG, d_raw, mask, mask_rows, wstream, w_alpha, layer_mask=0xFF):
         """pgn_mlp_delta_chain: dG bf16 [m,128], d_raw fp32 [m,4], mask = the mask area of the activation dump ->
-        (dz bf16 [8,m,256] with dz[l] = dZ_l, colsum fp32 [8,256] = the trunk's bias gradients)."""
+        (dz bf16 [8,m,256] with dz[l] = dZ_l, colsum fp32 [8,256] = the trunk's bias gradients); only the layers in
+        layer_mask (bit l) are written / summed."""
         m = dG.shape[0]
         if dG.dtype != torch.bfloat16 or not dG.is_contiguous() or dG.shape[1] != 128 or not dG.is_cuda:
             raise ValueError("dG must be a contiguous CUDA bf16 [m,128] matrix")
@@ -320,7 +321,7 @@ class Engine:
         colsum = torch.empty((8, 256), dtype=torch.float32, device=dG.device)
         with torch.cuda.device(dG.device):
             _lib.check(self.lib.pgn_mlp_delta_chain(self.handle, _ptr(dG), _ptr(d_raw), _ptr(mask), mask_rows, m, _ptr(wstream),
-                                                    _ptr(w_alpha), _ptr(dz), _ptr(colsum), self._stream()))
+                                                    _ptr(w_alpha), _ptr(dz), _ptr(colsum), int(layer_mask), self._stream()))
         return dz, colsum
 
     def mlp(self, net_id, enc, precision="bf16"):

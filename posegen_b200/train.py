@@ -125,7 +125,8 @@ def mlp_backward(params: Dict[str, torch.Tensor], enc: torch.Tensor, acts: torch
     if chain is not None:
         # trunk: one fused kernel for the eight deltas; the weight gradients are GEMMs over (dZ_l, h_{l-1})
         mask, mask_rows = (mask_dump[0], m) if mask_dump is not None else act_masks(acts)
-        dz, colsum = chain(dG, d_raw, mask, mask_rows, chain_wstream(P), P["alpha_linear.weight"].reshape(-1).float().contiguous())
+        dz, colsum = chain(dG, d_raw, mask, mask_rows, chain_wstream(P), P["alpha_linear.weight"].reshape(-1).float().contiguous(),
+                           0xFF if wg else 0x21)               # a frozen network's pose gradient reads only dZ_0 and dZ_5
         if wg:
             g["alpha_linear.weight"] = _mm32(d_raw[:, 3:4].to(bf).t(), H[7])
             g["alpha_linear.bias"] = d_raw[:, 3:4].sum(0)

@@ -303,6 +303,12 @@ def test_delta_chain_kernel_matches_layerwise_reference(engine):
             if l > 0:
                 W = P[f"pts_linears.{l}.weight"][:, 432:] if l == 5 else P[f"pts_linears.{l}.weight"]
                 pre = dz[l].float() @ W.to(bf).float()                                  # continue from the kernel's own bf16 deltas
+        # layer mask: only the requested deltas / sums are produced, bit-identical to the full run
+        dz2, cs2 = engine.mlp_delta_chain(dG, d_raw.contiguous(), mask, rows, chain_wstream(P),
+                                          P["alpha_linear.weight"].reshape(-1).float().contiguous(), layer_mask=0x21)
+        engine.check_status()
+        assert torch.equal(dz2[0], dz[0]) and torch.equal(dz2[5], dz[5])
+        assert float(cs2[[1, 2, 3, 4, 6, 7]].abs().max()) == 0.0 and float((cs2[0] - colsum[0]).abs().max()) <= 1e-3 * max(1.0, float(colsum[0].abs().max()))
 
 
 def test_graphed_training_step_follows_the_eager_one(engine, train_case):
