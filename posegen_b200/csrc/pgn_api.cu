@@ -55,6 +55,7 @@ struct pgn_context {
   float* d_fold;
   PgnBf16Net bf16[2];
   int* d_status;
+  bool fp32_stale[2] = {false, false};   // fp32-tier transposes pending since the last pgn_upload_weights
   unsigned long long* d_prof;   // optional phase timers [num_sms][32]
   bool prof_on;
   float* d_c2w;
@@ -148,15 +149,28 @@ int pgn_upload_weights(pgn_context* c, int net_id, const pgn_net_weights* w, int
     PGN_CUDA(cudaMemcpyAsync((void*)c->w_ptr[net_id][l], w->weight[l], (size_t)kOut[l] * kIn[l] * sizeof(float), kind, stream));
     PGN_CUDA(cudaMemcpyAsync((void*)c->b_ptr[net_id][l], w->bias[l], (size_t)kOut[l] * sizeof(float), kind, stream));
   }
-  for (int l = 0; l < PGN_N_LINEAR; ++l) {
-    if (l == 8 || l == 11) continue;   // small heads keep nn.Linear layout
-    PGN_CUDA(pgn_launch_transpose(c->w_ptr[net_id][l], kOut[l], kIn[l], (float*)c->fp32[net_id].wt[l], stream));
-    c->launches++;
-  }
+  // the fp32 CUDA-core tier's transposed copies are rebuilt lazily, by the first fp32 call after an upload
+  // (ensure_fp32_tier): a bf16 training loop re-packs every step and never reads them
+  c->fp32_stale[net_id] = true;
   PGN_CUDA(pgn_pack_bf16_net(c->w_ptr[net_id], c->b_ptr[net_id], c->d_wstream[net_id], c->d_bf16_aux[net_id],
                              c->d_bf16_aux[net_id] + 9 * 256, c->d_bf16_aux[net_id] + 9 * 256 + 256, c->d_fold, stream));
   c->launches += 2;
   c->have_w[net_id] = true;
+  return PGN_OK;
+}
+
+// fp32 tier: transposed weights from the context's fp32 copies, on the calling stream (which must be ordered after the
+// upload's stream; both are the caller's current stream in the Python binding)
+static int ensure_fp32_tier(pgn_context* c, cudaStream_t stream) {
+  for (int n = 0; n < 2; ++n) {
+    if (!c->fp32_stale[n] || !c->have_w[n]) continue;
+    for (int l = 0; l < PGN_N_LINEAR; ++l) {
+      if (l == 8 || l == 11) continue;   // small heads keep nn.Linear layout
+      PGN_CUDA(pgn_launch_transpose(c->w_ptr[n][l], kOut[l], kIn[l], (float*)c->fp32[n].wt[l], stream));
+      c->launches++;
+    }
+    c->fp32_stale[n] = false;
+  }
   return PGN_OK;
 }
 
@@ -265,6 +279,10 @@ static int render_forward_impl(pgn_context* c, const pgn_render_inputs* in, cons
   o.raw0 = out->raw0; o.raw = out->raw; o.near_far = out->near_far;
   if (out->near_far)
     PGN_CUDA(cudaMemcpyAsync(out->near_far, near_far, (size_t)in->n_rays * 2 * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+  if (in->precision == PGN_PRECISION_FP32) {
+    int rc2 = ensure_fp32_tier(c, stream);
+    if (rc2) return rc2;
+  }
   if (in->precision == PGN_PRECISION_FP32)
     PGN_CUDA(pgn_launch_render_fp32(refs, o, c->fp32[0], c->fp32[1], c->d_sc, near_far, c->num_sms, stream));
   else
@@ -355,6 +373,10 @@ int pgn_mlp(pgn_context* c, int net_id, const float* enc, int64_t m, float* raw,
   if (!c || !enc || !raw || net_id < 0 || net_id > 1 || m < 0) return fail(PGN_E_INVALID, "pgn_mlp: bad argument");
   if (!c->have_w[net_id]) return fail(PGN_E_STATE, "pgn_mlp: weights not uploaded");
   PGN_CUDA(cudaSetDevice(c->cfg.device));
+  if (precision == PGN_PRECISION_FP32) {
+    int rc2 = ensure_fp32_tier(c, (cudaStream_t)stream);
+    if (rc2) return rc2;
+  }
   if (precision == PGN_PRECISION_FP32)
     PGN_CUDA(pgn_launch_mlp_fp32(c->fp32[net_id], enc, m, raw, c->num_sms, (cudaStream_t)stream));
   else if (precision == PGN_PRECISION_BF16)
