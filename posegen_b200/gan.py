@@ -74,6 +74,9 @@ def render_frame(rc, ray_batch: torch.Tensor, skts: torch.Tensor, cyl: torch.Ten
     """(rgb_map [n,3], acc_map [n]) of all rays of one frame, differentiable w.r.t. skts [24,4,4] (one pose)."""
     if skts.shape != (24, 4, 4):
         raise ValueError("render_frame renders one pose: skts must be [24,4,4]")
+    if torch.is_grad_enabled() and any(p.requires_grad for net in (rc.network, rc.network_fine) for p in net.parameters()):
+        raise RuntimeError("render_frame back-propagates to the pose only and keeps no activations: freeze the NeRF "
+                           "(run_gan.py:159-160) or use RayCaster.forward in train mode for weight gradients")
     return _FrameRenderFn.apply(rc, ray_batch.float().contiguous(), skts.float(), cyl.float().contiguous(), chunk)
 
 
