@@ -170,7 +170,7 @@ pgn_delta_chain_kernel(const uint4* __restrict__ dG, const float* __restrict__ d
 #pragma unroll 8
           for (int i = 0; i < 32; ++i) {
             const uint4 v = lds128(src + (uint32_t)i * 64);
-            if (g0 + 4 * i < m) out[(size_t)i * 128] = v;
+            if (g0 + 4 * i < m) __stcs(out + (size_t)i * 128, v);      // written once, read by a later kernel: streaming store
             const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {

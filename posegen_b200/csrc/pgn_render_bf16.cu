@@ -246,7 +246,7 @@ __device__ __forceinline__ void encode_d_store(uint32_t stg, int row, int half, 
 
 // 256-bit global store (sm_100: STG.E.256): one full sector per thread, 32-byte aligned address
 __device__ __forceinline__ void stg256(void* p, const uint32_t (&v)[8]) {
-  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]),
+  asm volatile("st.global.cs.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]),
                "r"(v[5]), "r"(v[6]), "r"(v[7])
                : "memory");
 }
