@@ -269,7 +269,8 @@ __device__ __forceinline__ void epilogue(Smem& sm, uint32_t tmem_acc, uint32_t a
   const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)col0;
   const uint32_t dst0 = act_saddr + (uint32_t)(col0 >> 3) * kRunBytes + row * 16;
   float sig = 0.f, r0 = 0.f, r1 = 0.f, r2 = 0.f;
-  uint32_t mask_w[4] = {0u, 0u, 0u, 0u};       // training forward: [column > 0] bits of this thread's 128 columns
+  uint32_t mask_w = 0u;                        // training forward: [column > 0] bits of the current 32 columns (stored per word:
+                                               // one live register instead of four across the drain loop)
   uint32_t v[2][16];
   tmem_ld_32x16(taddr, v[0]);
 #pragma unroll
@@ -318,7 +319,8 @@ __device__ __forceinline__ void epilogue(Smem& sm, uint32_t tmem_acc, uint32_t a
         uint32_t mb = 0;
 #pragma unroll
         for (int i = 15; i >= 0; --i) mb = __funnelshift_l(vb[i], mb, 1);
-        mask_w[b >> 1] |= (~mb & 0xffffu) << ((b & 1) * 16);
+        if (b & 1) reinterpret_cast<uint32_t*>(dump_mask)[b >> 1] = mask_w | ((~mb & 0xffffu) << 16);
+        else mask_w = ~mb & 0xffffu;
       }
     }
     if (MODE == 2 && dump) {      // view layer: relu(g) of this thread's 16 columns
@@ -331,11 +333,10 @@ __device__ __forceinline__ void epilogue(Smem& sm, uint32_t tmem_acc, uint32_t a
       uint32_t mb = 0;
 #pragma unroll
       for (int i = 15; i >= 0; --i) mb = __funnelshift_l(vb[i], mb, 1);
-      mask_w[b >> 1] |= (~mb & 0xffffu) << ((b & 1) * 16);
+      if (b & 1) reinterpret_cast<uint32_t*>(dump_vmask)[b >> 1] = mask_w | ((~mb & 0xffffu) << 16);
+      else mask_w = ~mb & 0xffffu;
     }
   }
-  if (MODE != 2 && dump_mask) *dump_mask = make_uint4(mask_w[0], mask_w[1], mask_w[2], mask_w[3]);
-  if (MODE == 2 && dump_vmask) *dump_vmask = make_uint2(mask_w[0], mask_w[1]);
   // heads: this thread's column half of (rgb_raw, sigma_raw) -> one conflict-free 16-byte store per tile
   if (MODE == 1) sig_keep = sig;
   if (MODE == 2) sts128(smem_u32(&sm.part[slot][half][row][0]), __float_as_uint(r0), __float_as_uint(r1), __float_as_uint(r2), __float_as_uint(sig_keep));
