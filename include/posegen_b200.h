@@ -245,6 +245,11 @@ PGN_API int  pgn_mlp_delta_chain(pgn_context* ctx, const void* dG, const float* 
                                  int64_t m, const void* wstream, const float* w_alpha, void* dz, float* colsum,
                                  uint32_t layer_mask, void* stream);
 
+/* the same with the weights of an uploaded net (pgn_upload_weights also packs the chain's weight stream from its fp32
+ * copies): what the training / GAN step call, no per-step packing on the host side */
+PGN_API int  pgn_mlp_delta_chain_net(pgn_context* ctx, int32_t net_id, const void* dG, const float* d_raw, const void* mask,
+                                     int64_t mask_rows, int64_t m, void* dz, float* colsum, uint32_t layer_mask, void* stream);
+
 /* NeRF.forward (core/networks/nerf.py:133-148) on explicit encodings:
  * enc [m,1080] -> raw [m,4].  precision selects the MLP engine. */
 PGN_API int  pgn_mlp(pgn_context* ctx, int net_id, const float* enc, int64_t m, float* raw,

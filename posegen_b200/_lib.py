@@ -21,7 +21,7 @@ EXPORTED = [
     "pgn_abi_version", "pgn_last_error", "pgn_create", "pgn_destroy", "pgn_upload_weights",
     "pgn_set_embed_scalars", "pgn_workspace_bytes", "pgn_render_forward", "pgn_activation_dump_bytes",
     "pgn_render_forward_train", "pgn_launch_count",
-    "pgn_check_device_status", "pgn_near_far", "pgn_encode", "pgn_mlp", "pgn_composite", "pgn_composite_backward", "pgn_encode_backward", "pgn_encode_bf16", "pgn_encode_backward_bf16", "pgn_mlp_delta", "pgn_mlp_delta_chain", "pgn_mask_dump_bytes", "pgn_render_forward_masks", "pgn_view_delta_from_mask",
+    "pgn_check_device_status", "pgn_near_far", "pgn_encode", "pgn_mlp", "pgn_composite", "pgn_composite_backward", "pgn_encode_backward", "pgn_encode_bf16", "pgn_encode_backward_bf16", "pgn_mlp_delta", "pgn_mlp_delta_chain", "pgn_mlp_delta_chain_net", "pgn_mask_dump_bytes", "pgn_render_forward_masks", "pgn_view_delta_from_mask",
     "pgn_sample_pdf", "pgn_generate_rays", "pgn_compose_frame", "pgn_pose_to_skts", "pgn_frame_to_hmr_input",
     "pgn_debug_umma_gemm", "pgn_debug_phase_timers",
 ]
@@ -92,6 +92,7 @@ def load() -> C.CDLL:
     lib.pgn_encode_backward_bf16.argtypes = [vp, C.POINTER(RenderInputs), vp, i32, vp, vp, vp, vp]
     lib.pgn_encode_bf16.argtypes = [vp, C.POINTER(RenderInputs), vp, i32, vp, vp]
     lib.pgn_mlp_delta.argtypes = [vp, vp, i32, vp, i64, i32, vp, i32, i32, vp, vp, vp, vp]
+    lib.pgn_mlp_delta_chain_net.argtypes = [vp, i32, vp, vp, vp, i64, i64, vp, vp, C.c_uint32, vp]
     lib.pgn_mask_dump_bytes.argtypes = [i64]
     lib.pgn_mask_dump_bytes.restype = C.c_size_t
     lib.pgn_render_forward_masks.argtypes = [vp, C.POINTER(RenderInputs), C.POINTER(RenderOutputs), vp, vp, C.c_size_t, vp]

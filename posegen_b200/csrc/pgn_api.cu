@@ -53,6 +53,7 @@ struct pgn_context {
   __nv_bfloat16* d_wstream[2];
   float* d_bf16_aux[2];     // bias[9*256] | w_alpha[256] | w_rgb[384]
   float* d_fold;
+  __nv_bfloat16* d_chain_w[2] = {nullptr, nullptr};   // per net: the delta chain's weight stream (120 slabs of 8 KB)
   PgnBf16Net bf16[2];
   int* d_status;
   bool fp32_stale[2] = {false, false};   // fp32-tier transposes pending since the last pgn_upload_weights
@@ -99,6 +100,7 @@ int pgn_create(const pgn_config* cfg, pgn_context** out) {
   PGN_CUDA(cudaMalloc(&c->d_c2w, 12 * sizeof(float)));
   PGN_CUDA(cudaMalloc(&c->d_rest, PGN_J * 3 * sizeof(float)));
   PGN_CUDA(cudaMalloc(&c->d_fold, (128 * 256 + 128) * sizeof(float)));
+  for (int n = 0; n < 2; ++n) PGN_CUDA(cudaMalloc(&c->d_chain_w[n], (size_t)120 * 4096 * sizeof(__nv_bfloat16)));
   for (int n = 0; n < 2; ++n) {
     PGN_CUDA(cudaMalloc(&c->d_w[n], weight_floats() * sizeof(float)));
     PGN_CUDA(cudaMalloc(&c->d_b[n], bias_floats() * sizeof(float)));
@@ -132,7 +134,7 @@ int pgn_create(const pgn_config* cfg, pgn_context** out) {
 void pgn_destroy(pgn_context* c) {
   if (!c) return;
   cudaSetDevice(c->cfg.device);
-  cudaFree(c->d_sc); cudaFree(c->d_status); cudaFree(c->d_c2w); cudaFree(c->d_rest); cudaFree(c->d_fold);
+  cudaFree(c->d_sc); cudaFree(c->d_status); cudaFree(c->d_c2w); cudaFree(c->d_rest); cudaFree(c->d_fold); cudaFree(c->d_chain_w[0]); cudaFree(c->d_chain_w[1]);
   for (int n = 0; n < 2; ++n) {
     cudaFree(c->d_w[n]); cudaFree(c->d_b[n]); cudaFree(c->d_wt[n]); cudaFree(c->d_wstream[n]); cudaFree(c->d_bf16_aux[n]);
   }
@@ -154,7 +156,9 @@ int pgn_upload_weights(pgn_context* c, int net_id, const pgn_net_weights* w, int
   c->fp32_stale[net_id] = true;
   PGN_CUDA(pgn_pack_bf16_net(c->w_ptr[net_id], c->b_ptr[net_id], c->d_wstream[net_id], c->d_bf16_aux[net_id],
                              c->d_bf16_aux[net_id] + 9 * 256, c->d_bf16_aux[net_id] + 9 * 256 + 256, c->d_fold, stream));
-  c->launches += 2;
+  // the backward's delta-chain weight stream (reads the fold the pack above left in d_fold)
+  PGN_CUDA(pgn_launch_pack_chain_weights(c->w_ptr[net_id], c->d_fold, c->d_chain_w[net_id], stream));
+  c->launches += 3;
   c->have_w[net_id] = true;
   return PGN_OK;
 }
@@ -367,6 +371,13 @@ int pgn_mlp_delta_chain(pgn_context* c, const void* dG, const float* d_raw, cons
   PGN_CUDA(pgn_launch_delta_chain(dG, d_raw, mask, mask_rows, m, wstream, w_alpha, dz, colsum, layer_mask, c->d_status, c->num_sms, (cudaStream_t)stream));
   c->launches++;
   return PGN_OK;
+}
+
+int pgn_mlp_delta_chain_net(pgn_context* c, int32_t net_id, const void* dG, const float* d_raw, const void* mask,
+                            int64_t mask_rows, int64_t m, void* dz, float* colsum, uint32_t layer_mask, void* stream) {
+  if (!c || net_id < 0 || net_id > 1) return fail(PGN_E_INVALID, "pgn_mlp_delta_chain_net: bad argument");
+  if (!c->have_w[net_id]) return fail(PGN_E_STATE, "pgn_mlp_delta_chain_net: weights not uploaded");
+  return pgn_mlp_delta_chain(c, dG, d_raw, mask, mask_rows, m, c->d_chain_w[net_id], c->w_ptr[net_id][8], dz, colsum, layer_mask, stream);
 }
 
 int pgn_mlp(pgn_context* c, int net_id, const float* enc, int64_t m, float* raw, int32_t precision, void* stream) {

@@ -289,7 +289,36 @@ pgn_delta_chain_kernel(const uint4* __restrict__ dG, const float* __restrict__ d
   if (warp == 0) { tc_fence_after_sync(); tmem_dealloc(tmem, 512); }
 }
 
+// the chain's weight stream from the context's fp32 copies (include/posegen_b200.h: pgn_mlp_delta_chain): slab element
+// (j, ks, kc, n, e) = W'_j[n][ks * 16 + kc * 8 + e];  W'_0 = fold^T (fold = W_v[:, :256] W_f, [128][256]),
+// W'_j = W_l^T for l = 8 - j (nn.Linear layout [out][in]; the skip layer l = 5 without its first 432 input columns)
+struct ChainPackPtrs { const float* w[8]; };       // pts_linears.0 .. 7
+__global__ void pgn_pack_chain_kernel(ChainPackPtrs p, const float* __restrict__ fold, __nv_bfloat16* __restrict__ out) {
+  const int total = kSlabsPerBlock * 4096;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int slab = idx >> 12, r = idx & 4095;
+    const int kc = r >> 11, n = (r >> 3) & 255, e = r & 7;
+    float v;
+    if (slab < 8) {
+      const int k = slab * 16 + kc * 8 + e;
+      v = fold[k * 256 + n];
+    } else {
+      const int j = 1 + (slab - 8) / 16, ks = (slab - 8) % 16, l = 8 - j;
+      const int k = ks * 16 + kc * 8 + e;
+      v = (l == 5) ? p.w[5][k * 688 + 432 + n] : p.w[l][k * 256 + n];
+    }
+    out[idx] = __float2bfloat16_rn(v);
+  }
+}
+
 }  // namespace
+
+cudaError_t pgn_launch_pack_chain_weights(const float* const* w_dev, const float* fold, __nv_bfloat16* out, cudaStream_t stream) {
+  ChainPackPtrs p;
+  for (int l = 0; l < 8; ++l) p.w[l] = w_dev[l];
+  pgn_pack_chain_kernel<<<148 * 2, 256, 0, stream>>>(p, fold, out);
+  return cudaGetLastError();
+}
 
 cudaError_t pgn_launch_delta_chain(const void* dG, const float* d_raw, const void* mask, long long mask_rows, long long m,
                                    const void* wstream, const float* w_alpha, void* dz, float* colsum, unsigned layer_mask,

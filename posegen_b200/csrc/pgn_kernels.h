@@ -91,6 +91,7 @@ cudaError_t pgn_launch_mlp_delta(void* dh, int has_in, const void* act, long lon
                                  int nrs, const float* wr, float* colsum, float* wsum, int num_sms, cudaStream_t stream);
 cudaError_t pgn_launch_view_delta_bits(void* dG, const float* d_raw, const float* w_rgb, const void* vmask, long long m,
                                        int num_sms, cudaStream_t stream);
+cudaError_t pgn_launch_pack_chain_weights(const float* const* w_dev, const float* fold, __nv_bfloat16* out, cudaStream_t stream);
 cudaError_t pgn_launch_delta_chain(const void* dG, const float* d_raw, const void* mask, long long mask_rows, long long m,
                                    const void* wstream, const float* w_alpha, void* dz, float* colsum, unsigned layer_mask,
                                    int* status, int num_sms, cudaStream_t stream);

@@ -324,6 +324,22 @@ class Engine:
                                                     _ptr(w_alpha), _ptr(dz), _ptr(colsum), int(layer_mask), self._stream()))
         return dz, colsum
 
+    def mlp_delta_chain_net(self, net_id, dG, d_raw, mask, mask_rows, layer_mask=0xFF):
+        """pgn_mlp_delta_chain_net: the delta chain with the weights of uploaded net `net_id` (0 coarse, 1 fine)."""
+        m = dG.shape[0]
+        if dG.dtype != torch.bfloat16 or not dG.is_contiguous() or dG.shape[1] != 128 or not dG.is_cuda:
+            raise ValueError("dG must be a contiguous CUDA bf16 [m,128] matrix")
+        if d_raw.dtype != torch.float32 or not d_raw.is_contiguous() or tuple(d_raw.shape) != (m, 4):
+            raise ValueError("d_raw must be contiguous fp32 [m,4]")
+        if mask.numel() * mask.element_size() < mask_rows * 256 or mask_rows < m or not mask.is_contiguous():
+            raise ValueError("mask area too small")
+        dz = torch.empty((8, m, 256), dtype=torch.bfloat16, device=dG.device)
+        colsum = torch.empty((8, 256), dtype=torch.float32, device=dG.device)
+        with torch.cuda.device(dG.device):
+            _lib.check(self.lib.pgn_mlp_delta_chain_net(self.handle, int(net_id), _ptr(dG), _ptr(d_raw), _ptr(mask), mask_rows, m,
+                                                        _ptr(dz), _ptr(colsum), int(layer_mask), self._stream()))
+        return dz, colsum
+
     def mlp(self, net_id, enc, precision="bf16"):
         _check_f32_cuda(enc, "enc")
         enc2 = enc.reshape(-1, 1080).contiguous()

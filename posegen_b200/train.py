@@ -20,6 +20,7 @@ gradient bucket.
 """
 from __future__ import annotations
 
+import functools
 from typing import Callable, Dict, List
 
 import torch
@@ -82,7 +83,8 @@ def mlp_backward(params: Dict[str, torch.Tensor], enc: torch.Tensor, acts: torch
     gradients are produced in fp32.  `feature_linear` has no activation (nerf.py:125-128), so it never shows up at
     batch size: with T = dG^T h7 its gradients and those of the feature block of `views_linears.0` are
     [128,256]-sized products, and dL/d h7 reads the folded weight W_v[:, :256] @ W_f.
-    `chain(dG, d_raw, mask, mask_rows, wstream, w_alpha)` is `Engine.mlp_delta_chain` (`pgn_mlp_delta_chain`): the
+    `chain(dG, d_raw, mask, mask_rows, layer_mask)` is `Engine.mlp_delta_chain_net` bound to this net
+    (`pgn_mlp_delta_chain_net`; the library packs the chain's weight stream when the weights are uploaded): the
     whole trunk chain dG -> dZ_7 .. dZ_0 (+ bias gradients) as one tcgen05 kernel; without it the chain runs layer by
     layer (a cuBLAS GEMM and a `fuse` pass per layer), which is also what the host-logic test exercises.
     mask_dump = (trunk_mask int32 [8,m,8], view_mask int32 [m,4]) with `view_delta` = `Engine.view_delta_from_mask`
@@ -125,8 +127,7 @@ def mlp_backward(params: Dict[str, torch.Tensor], enc: torch.Tensor, acts: torch
     if chain is not None:
         # trunk: one fused kernel for the eight deltas; the weight gradients are GEMMs over (dZ_l, h_{l-1})
         mask, mask_rows = (mask_dump[0], m) if mask_dump is not None else act_masks(acts)
-        dz, colsum = chain(dG, d_raw, mask, mask_rows, chain_wstream(P), P["alpha_linear.weight"].reshape(-1).float().contiguous(),
-                           0xFF if wg else 0x21)               # a frozen network's pose gradient reads only dZ_0 and dZ_5
+        dz, colsum = chain(dG, d_raw, mask, mask_rows, 0xFF if wg else 0x21)   # a frozen network's pose gradient reads only dZ_0, dZ_5
         if wg:
             g["alpha_linear.weight"] = _mm32(d_raw[:, 3:4].to(bf).t(), H[7])
             g["alpha_linear.bias"] = d_raw[:, 3:4].sum(0)
@@ -209,8 +210,9 @@ class _RenderTrainFn(torch.autograd.Function):
             d_raw = eng.composite_backward(rb, sk, cy, raw_p, z, gr, ga, noise=nz)
             enc = eng.encode_bf16(rb, sk, cy, z).reshape(-1, 1080) if want_w else None
             pd = dict(net.named_parameters())
+            net_id = 0 if net is rc.network else 1
             gd = mlp_backward(pd, enc, acts, d_raw.reshape(-1, 4), eng.mlp_delta, want_input_grad=want_sk, want_weight_grad=want_w,
-                              chain=eng.mlp_delta_chain if USE_DELTA_CHAIN else None)
+                              chain=functools.partial(eng.mlp_delta_chain_net, net_id) if USE_DELTA_CHAIN else None)
             grads += [gd[k].reshape(pd[k].shape).to(pd[k].dtype) for k in PARAM_ORDER] if want_w else [None] * len(PARAM_ORDER)
             if want_sk:          # pose gradient: dL/d(network input) -> dL/d skts (per ray), both passes add up
                 d = eng.encode_backward_bf16(rb, sk, cy, z, gd["_g_xp"], gd["_g_d"])

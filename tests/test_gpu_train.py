@@ -308,6 +308,14 @@ def test_delta_chain_kernel_matches_layerwise_reference(engine):
                                           P["alpha_linear.weight"].reshape(-1).float().contiguous(), layer_mask=0x21)
         engine.check_status()
         assert torch.equal(dz2[0], dz[0]) and torch.equal(dz2[5], dz[5])
+        # the weight stream the library packs at upload time (pgn_mlp_delta_chain_net) against the torch-packed one: same
+        # weights, the fold W_v[:, :256] W_f summed in another order (a bf16 rounding apart in a few elements)
+        engine.upload_net(0, {k: v for k, v in P.items()})
+        dz3, cs3 = engine.mlp_delta_chain_net(0, dG, d_raw.contiguous(), mask, rows)
+        engine.check_status()
+        for l in range(8):
+            rel = float((dz3[l].float() - dz[l].float()).norm() / dz[l].float().norm().clamp_min(1e-12))
+            assert rel <= 1e-2, (m, l, rel)
         assert float(cs2[[1, 2, 3, 4, 6, 7]].abs().max()) == 0.0 and float((cs2[0] - colsum[0]).abs().max()) <= 1e-3 * max(1.0, float(colsum[0].abs().max()))
 
 
