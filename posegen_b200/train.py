@@ -102,7 +102,9 @@ def mlp_backward(params: Dict[str, torch.Tensor], enc: torch.Tensor, acts: torch
         H = [act_layer(acts, l, m) for l in range(8)]
         G = act_layer(acts, 8, m)
     P = {k: v.detach() for k, v in params.items()}
-    W = {k: v.to(bf) for k, v in P.items() if k.startswith("pts_linears") and k.endswith("weight")}
+    # bf16 trunk weights: only the input-gradient GEMMs and the layer-by-layer fallback read them
+    need_w = (0, 5) if (chain is not None and want_input_grad) else (range(8) if chain is None else ())
+    W = {f"pts_linears.{l}.weight": P[f"pts_linears.{l}.weight"].to(bf) for l in need_w}
     g: Dict[str, torch.Tensor] = {}
     # rgb head + view layer:  g = relu(W_v [f | d_emb] + b_v),  f = W_f h7 + b_f,  rgb_raw = W_rgb g + b_rgb
     wg = want_weight_grad
