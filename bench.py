@@ -13,6 +13,15 @@ no data-path collective); the frames of all K steps are exchanged by ONE final a
 timed (CUDA events) and added to the rank's step time (BASELINE.json configs[2]: "no communication
 except a final gather").
 Metric: rays/s over all ranks (max-over-ranks device time, CUDA events).
+
+The same invocation also measures the other three BASELINE.json configurations and attaches them to the JSON line as
+`aux` (each with its own warm-up, CUDA-event timing and max over ranks; `--aux none` skips them):
+  aux.genloop_256  configs[2]: 256 synthetic poses -> device FK -> bbox -> fused render -> frame -> HMR input, poses
+                   sharded pose_idx % N, one final all_gather (tools/generation_loop_bench.py)
+  aux.train_step   configs[3]: 3072-ray training step per GPU, forward + backward + NCCL all-reduce + Adam, CUDA graph;
+                   the all-reduce is also timed alone (tools/train_step_bench.py)
+  aux.gan_step     configs[4]: generator -> device FK -> differentiable 512x512 render -> HMR stand-in -> MPJPE ->
+                   backward to the generator, all-reduce of the generator gradients (tools/gan_step_bench.py)
 """
 from __future__ import annotations
 
@@ -35,9 +44,14 @@ N_POSES = 5                          # distinct synthetic poses cycled through t
                                      # every rank renders the same pool, different images at any one time)
 
 
+NCU_CAPTURE = "r2_bf16_render_512.json"        # ncu --set full capture of the shipped render kernel (profiles/)
+
+
 def ncu_traffic():
     """DRAM bytes of one launch of the dominant kernel from the committed ncu capture (profiles/)."""
-    path = os.path.join(ROOT, "profiles", "r1_bf16_render_512.json")
+    path = os.path.join(ROOT, "profiles", NCU_CAPTURE)
+    if not os.path.exists(path):
+        path = os.path.join(ROOT, "profiles", "r1_bf16_render_512.json")
     try:
         prof = json.load(open(path))
         m = prof["kernels"][0]["metrics"]
@@ -107,34 +121,41 @@ def run_reference(args, rank, world):
     torch.set_num_threads(threads)
     ckpt = syn.synthetic_raycaster_state(0, alpha_gain=400.)
     nets, emb = orc.nets_from_ckpt(ckpt), orc.embed_params_from_ckpt(ckpt)
-    frame, rb = make_jobs(args.res, 0, 1)[0]
-    n_sample = min(args.cpu_rays, rb.shape[0])
-    sel = np.linspace(0, rb.shape[0] - 1, n_sample).astype(np.int64)
-    rbt = torch.from_numpy(rb[sel])
-    sk, cy = torch.from_numpy(frame.pose.skts), torch.from_numpy(frame.pose.cyl)
-    times = []
+    # the SAME pose pool as our arm (step i renders pose i % N_POSES), each step a bounded strided sample of that frame
+    jobs = make_jobs(args.res, 0, 1)
+    samples = []
+    for frame, rb in jobs:
+        n_sample = min(args.cpu_rays, rb.shape[0])
+        sel = np.linspace(0, rb.shape[0] - 1, n_sample).astype(np.int64)
+        samples.append((torch.from_numpy(rb[sel]), torch.from_numpy(frame.pose.skts), torch.from_numpy(frame.pose.cyl)))
+    sec_total, rays_total, frame_rays = 0.0, 0, []
     for it in range(args.warmup + args.steps):
+        rbt, sk, cy = samples[it % N_POSES]
         t0 = time.perf_counter()
         orc.render(rbt, sk, cy, nets, emb, chunk=4096)
         if it >= args.warmup:
-            times.append(time.perf_counter() - t0)
-    sec = float(np.mean(times))
-    value = n_sample / sec
+            sec_total += time.perf_counter() - t0
+            rays_total += rbt.shape[0]
+            frame_rays.append(jobs[it % N_POSES][1].shape[0])
+    value = rays_total / sec_total
+    rays_per_frame = float(np.mean(frame_rays)) if frame_rays else float(jobs[0][1].shape[0])
     line = {"impl": "reference", "metric": "rays_per_sec", "value": value, "unit": "rays/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec_total / max(args.steps, 1) * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, rb.shape[0]),
+            "config": workload_config(args, float(np.mean([rb.shape[0] for _, rb in jobs]))),
             "cpu_baseline": {"value": value, "unit": "rays/s", "cores": threads, "kind": "port",
-                             "sample": f"{n_sample} rays evenly strided from the {rb.shape[0]}-ray bbox of one 512x512 frame, chunk 4096"},
+                             "sample": f"per step {args.cpu_rays} rays evenly strided from the bbox of one {args.res}x{args.res} frame of the "
+                                       f"{N_POSES}-pose pool, chunk 4096"},
             "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "frames_per_sec_512": value / rb.shape[0]}
+            "frames_per_sec_512": value / rays_per_frame}
     print(json.dumps(line), flush=True)
 
 
 def workload_config(args, rays_per_frame):
     return {"workload": f"A-NeRF surreal.txt render, 1 synthetic SMPL pose per step at {args.res}x{args.res}, coarse+fine "
                         "(64+16 samples, 2x 8x256 MLP), cylinder-bbox rays, white_bkgd, random-init weights (x400 alpha head)",
-            "rays_per_frame": int(rays_per_frame), "res": args.res, "precision": args.precision,
+            "rays_per_frame": int(round(rays_per_frame)), "res": args.res,
+            "weights": "x400 alpha head: bf16 parity on these weights is held to the PSNR bound only (SURVEY.md §8d; tests/test_gpu_render.py)",
             "poses_cycled": N_POSES, "l2": "256 MiB buffer written between timed steps (L2 flush)",
             "parallelism": f"dp{args.gpus} (images sharded by rank, no data-path collective; one final all_gather of the frames)"}
 
@@ -245,7 +266,7 @@ def run_ours(args, rank, world, local):
         dist.all_reduce(tot)
     total_rays, total_rays_e2e = float(tot[0]), float(tot[1])
     if rank != 0:
-        return
+        return None
     value = total_rays / (ms_max * 1e-3)
     e2e_value = total_rays_e2e / (ms_e2e_max * 1e-3)
     peaks = measured_peaks()
@@ -256,7 +277,7 @@ def run_ours(args, rank, world, local):
         "metric": "rays_per_sec", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-        "config": workload_config(args, rays_per_frame),
+        "config": workload_config(args, float(np.mean([rb.shape[0] for _, rb in jobs]))),      # mean of the pose pool, both arms
         "frames_per_sec_512": value / rays_per_frame,
         "step_ms_min_max": [round(min(resident_step_ms), 3), round(max(resident_step_ms), 3)],
         "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": int(io[0]), "d2h_bytes_per_step": int(io[1]),
@@ -266,7 +287,7 @@ def run_ours(args, rank, world, local):
         "roofline": {"bound": "tensor", "achieved": per_gpu_tflops, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                      "frac": per_gpu_tflops / peaks["bf16_sustained"],
                      "traffic": ncu_traffic() if args.precision == "bf16" else None,
-                     "traffic_note": "DRAM bytes read+written by one launch (239,148-ray frame), ncu --set full, profiles/r1_bf16_render_512.json; "
+                     "traffic_note": f"DRAM bytes read+written by one launch (239,148-ray frame), ncu --set full, profiles/{NCU_CAPTURE}; "
                                      "algorithmic bytes per launch = 84 B/ray + 2 x 1.83 MB weights = 23.7 MB (HBM is not the bound)",
                      "peak_source": f"{peaks['src']} bf16 sustained (40-55 ms launches back to back inside a seconds-long step loop at the power cap); burst {peaks['bf16_burst']}",
                      "flop_per_ray": FLOP_PER_RAY, "kernel": "pgn_render_bf16_kernel" if args.precision == "bf16" else "pgn_render_fp32_kernel",
@@ -275,7 +296,39 @@ def run_ours(args, rank, world, local):
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args, jobs[0])
-    print(json.dumps(line), flush=True)
+    return line
+
+
+def run_aux(args, rank, world, local):
+    """The other BASELINE.json configurations (configs[2..4]) as auxiliary legs; every rank runs them (they shard /
+    all-reduce over the same process group), the dicts are identical on all ranks."""
+    legs = [x for x in args.aux.split(",") if x and x != "none"]
+    aux = {}
+    peaks = measured_peaks()
+    for leg in legs:
+        try:
+            if leg == "train":
+                from tools import train_step_bench
+                r = train_step_bench.run(rank, world, local, steps=20, warmup=3, deterministic=False, graph=True)
+                r["roofline"] = {"bound": "tensor", "achieved": r["tflops_per_gpu"], "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                                 "frac": r["tflops_per_gpu"] / peaks["bf16_sustained"],
+                                 "note": "algorithmic 3 x 248.2 MFLOP per ray (forward + dX + dW), whole step incl. all-reduce and Adam"}
+                aux["train_step"] = r
+            elif leg == "gan":
+                from tools import gan_step_bench
+                aux["gan_step"] = gan_step_bench.run(rank, world, local, steps=3, warmup=1, poses_per_gpu=args.gan_poses_per_gpu)
+            elif leg == "genloop":
+                from tools import generation_loop_bench
+                aux[f"genloop_{args.genloop_poses}"] = generation_loop_bench.run(rank, world, local, poses=args.genloop_poses, res=args.res)
+            else:
+                aux[leg] = {"error": "unknown leg"}
+        except Exception as e:  # noqa: BLE001  (a failing leg must not take the headline line down; it is reported as failed)
+            import traceback
+            aux[{"train": "train_step", "gan": "gan_step", "genloop": f"genloop_{args.genloop_poses}"}.get(leg, leg)] = \
+                {"error": f"{type(e).__name__}: {e}", "trace": traceback.format_exc().splitlines()[-3:]}
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
+    return aux
 
 
 def cpu_baseline(args, job):
@@ -308,6 +361,10 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-rays", type=int, default=8192, help="rays in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--aux", default="genloop,train,gan", help="auxiliary legs (BASELINE.json configs[2..4]): comma list of "
+                    "genloop,train,gan or 'none'")
+    ap.add_argument("--genloop-poses", type=int, default=256)
+    ap.add_argument("--gan-poses-per-gpu", type=int, default=2)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -320,7 +377,11 @@ def main():
         raise SystemExit("bench.py: no CUDA device; posegen_b200 has no CPU fallback (use --impl reference for the CPU arm)")
     pdist.init_process_group("nccl" if world > 1 else None)
     try:
-        run_ours(args, rank, world, local)
+        line = run_ours(args, rank, world, local)
+        aux = run_aux(args, rank, world, local)
+        if rank == 0:
+            line["aux"] = aux
+            print(json.dumps(line), flush=True)
     finally:
         import torch.distributed as dist
         if dist.is_initialized():

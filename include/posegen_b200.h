@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PGN_ABI_VERSION 1
+#define PGN_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define PGN_API __attribute__((visibility("default")))
@@ -105,6 +105,11 @@ typedef struct pgn_render_inputs {
                                   (core/utils/ray_utils.py:328-342 takes the mean over
                                   the batchify chunk); <=0 => whole call               */
   int32_t        precision;    /* PGN_PRECISION_* */
+  /* ABI v2: optional explicit chunk table for the near/far fill, device int64 [n_chunks + 1] ascending ray indices with
+   * chunk c = rays [chunk_starts[c], chunk_starts[c+1]).  When non-NULL it overrides nanfill_chunk: a batch that holds
+   * the rays of several images keeps the reference's per-image batchify chunks (run_nerf.py:77-95). */
+  const int64_t* chunk_starts;
+  int64_t        n_chunks;
 } pgn_render_inputs;
 
 /* Outputs of one render call (core/raycasters.py:711-724).  Any pointer may be NULL
@@ -199,6 +204,9 @@ PGN_API int64_t pgn_launch_count(const pgn_context* ctx);
 
 /* after a stream sync: 0 if no device-side watchdog tripped since the last call */
 PGN_API int  pgn_check_device_status(pgn_context* ctx);
+/* device address of the int32 status word pgn_check_device_status reads (0 = healthy): lets a host binding queue an
+ * asynchronous 4-byte read-back behind its launches instead of synchronising (Engine.poll_status). */
+PGN_API const int32_t* pgn_device_status_ptr(pgn_context* ctx);
 
 /* ------------------------------------------------- stage-level entry points
  * (unit parity against the oracle; each replaces one reference function) */
@@ -308,6 +316,29 @@ PGN_API int  pgn_pose_to_skts(pgn_context* ctx, const float* bones, const float*
                               float cyl_extend, float top_expand_ratio, float bot_expand_ratio,
                               float* skts, float* kps, float* cyls, float* l2ws, void* stream);
 
+/* Backward of pgn_pose_to_skts (core/utils/skeleton_utils.py:379-463 get_smpl_l2ws_torch + the rigid inverse, as torch
+ * autograd differentiates them for the pose generator / core/pose_opt.py:372-445): g_skts device [n,24,4,4] = dL/d skts
+ * (bottom rows ignored), g_kps device [n,24,3] = dL/d kps or NULL, rest_pose HOST [24,3] -> g_bones device [n,24,3]. */
+PGN_API int  pgn_pose_fk_backward(pgn_context* ctx, const float* bones, const float* rest_pose, int32_t n_poses,
+                                  const float* g_skts, const float* g_kps, float* g_bones, void* stream);
+
+/* "next" row 1, batched (run_nerf.py:27-147 renders image by image; here B images share launches):
+ * pgn_cylinder_bboxes: cylinder_to_box_2d (core/utils/skeleton_utils.py:700-787) for n cylinders, one camera:
+ *   cyls device [n,5], w2c HOST double[16] (row-major inverse of the OpenCV-convention c2w), -> bbox device int32 [n,4]
+ *   = (x0, y0, x1, y1), rows [y0,y1) x cols [x0,x1) are rendered (kp_to_valid_rays, core/utils/ray_utils.py:124-130).
+ * pgn_generate_rays_batch: get_rays of every bbox into ONE ray batch; offsets device int64 [n_poses + 1] (prefix sums of
+ *   the bbox areas, computed by the caller from the bboxes), c2w HOST [3,4]; writes ray_batch [offsets[n],11] and
+ *   pose_idx int32 [offsets[n]] (the pose_idx form of pgn_render_inputs).
+ * pgn_compose_frames_batch: images device [n_poses,H,W,3] = bg, bbox pixels = rgb + (1 - acc) * bg (run_nerf.py:100-133). */
+PGN_API int  pgn_cylinder_bboxes(pgn_context* ctx, const float* cyls, int32_t n, const double* w2c, int32_t H, int32_t W,
+                                 float focal, int32_t* bbox, void* stream);
+PGN_API int  pgn_generate_rays_batch(pgn_context* ctx, int32_t H, int32_t W, float focal, const float* c2w, const int32_t* bbox,
+                                     const int64_t* offsets, int32_t n_poses, int64_t max_rays_per_pose, float* ray_batch,
+                                     int32_t* pose_idx, void* stream);
+PGN_API int  pgn_compose_frames_batch(pgn_context* ctx, int32_t H, int32_t W, const int32_t* bbox, const int64_t* offsets,
+                                      int32_t n_poses, const float* rgb_map, const float* acc_map, float bg, float* images,
+                                      void* stream);
+
 /* "next" row 4: rendered frame -> HMR input without the PNG round trip
  * (run_gan.py:2057-2071, 2326, 2433-2445): optional uint8 quantisation, crop [y0:y1, x0:x1], /255,
  * Normalize(mean, std), skimage.transform.resize(..., (3,R,R), anti_aliasing=True).
@@ -326,7 +357,7 @@ PGN_API int  pgn_debug_phase_timers(pgn_context* ctx, int32_t enable, uint64_t* 
 /* bring-up probe of the tcgen05 plumbing: D[128,N] = A[128,K] * B[N,K]^T with bf16 inputs
  * and fp32 accumulation, one CTA.  variant bit 1 selects the CTA-pair form (cta_group::2, UMMA M=256):
  * A is [256,K], D is [256,N], two CTAs of one cluster each stage half of A and half of B.
- * (variant bit 0 swaps the descriptor LBO/SBO fields: known-bad, faults; bring-up only.) */
+ * (variant bit 0 is rejected with PGN_E_INVALID: it was a bring-up experiment that is not reachable any more.) */
 PGN_API int  pgn_debug_umma_gemm(pgn_context* ctx, const float* A, const float* B, float* D, int32_t K, int32_t N,
                                  int32_t variant, void* stream);
 

@@ -21,8 +21,9 @@ EXPORTED = [
     "pgn_abi_version", "pgn_last_error", "pgn_create", "pgn_destroy", "pgn_upload_weights",
     "pgn_set_embed_scalars", "pgn_workspace_bytes", "pgn_render_forward", "pgn_activation_dump_bytes",
     "pgn_render_forward_train", "pgn_launch_count",
-    "pgn_check_device_status", "pgn_near_far", "pgn_encode", "pgn_mlp", "pgn_composite", "pgn_composite_backward", "pgn_encode_backward", "pgn_encode_bf16", "pgn_encode_backward_bf16", "pgn_mlp_delta", "pgn_mlp_delta_chain", "pgn_mlp_delta_chain_net", "pgn_mask_dump_bytes", "pgn_render_forward_masks", "pgn_view_delta_from_mask",
+    "pgn_check_device_status", "pgn_device_status_ptr", "pgn_near_far", "pgn_encode", "pgn_mlp", "pgn_composite", "pgn_composite_backward", "pgn_encode_backward", "pgn_encode_bf16", "pgn_encode_backward_bf16", "pgn_mlp_delta", "pgn_mlp_delta_chain", "pgn_mlp_delta_chain_net", "pgn_mask_dump_bytes", "pgn_render_forward_masks", "pgn_view_delta_from_mask",
     "pgn_sample_pdf", "pgn_generate_rays", "pgn_compose_frame", "pgn_pose_to_skts", "pgn_frame_to_hmr_input",
+    "pgn_pose_fk_backward", "pgn_cylinder_bboxes", "pgn_generate_rays_batch", "pgn_compose_frames_batch",
     "pgn_debug_umma_gemm", "pgn_debug_phase_timers",
 ]
 
@@ -39,7 +40,7 @@ class NetWeights(C.Structure):
 class RenderInputs(C.Structure):
     _fields_ = [("ray_batch", C.c_void_p), ("n_rays", C.c_int64), ("skts", C.c_void_p), ("skts_stride", C.c_int64),
                 ("cyls", C.c_void_p), ("cyls_stride", C.c_int64), ("pose_idx", C.c_void_p),
-                ("nanfill_chunk", C.c_int64), ("precision", C.c_int32)]
+                ("nanfill_chunk", C.c_int64), ("precision", C.c_int32), ("chunk_starts", C.c_void_p), ("n_chunks", C.c_int64)]
 
 
 class RenderOutputs(C.Structure):
@@ -86,6 +87,8 @@ def load() -> C.CDLL:
     lib.pgn_launch_count.argtypes = [vp]
     lib.pgn_launch_count.restype = i64
     lib.pgn_check_device_status.argtypes = [vp]
+    lib.pgn_device_status_ptr.argtypes = [vp]
+    lib.pgn_device_status_ptr.restype = vp
     lib.pgn_near_far.argtypes = [vp, C.POINTER(RenderInputs), vp, vp]
     lib.pgn_encode.argtypes = [vp, C.POINTER(RenderInputs), vp, i32, vp, vp]
     lib.pgn_mlp.argtypes = [vp, C.c_int, vp, i64, vp, i32, vp]
@@ -106,6 +109,10 @@ def load() -> C.CDLL:
     lib.pgn_compose_frame.argtypes = [vp, i32, i32, i32, i32, i32, i32, vp, vp, f32, vp, vp]
     lib.pgn_pose_to_skts.argtypes = [vp, vp, C.POINTER(f32), i32, f32, f32, f32, vp, vp, vp, vp, vp]
     lib.pgn_frame_to_hmr_input.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, C.POINTER(f32), C.POINTER(f32), i32, vp, vp]
+    lib.pgn_pose_fk_backward.argtypes = [vp, vp, C.POINTER(f32), i32, vp, vp, vp, vp]
+    lib.pgn_cylinder_bboxes.argtypes = [vp, vp, i32, C.POINTER(C.c_double), i32, i32, f32, vp, vp]
+    lib.pgn_generate_rays_batch.argtypes = [vp, i32, i32, f32, C.POINTER(f32), vp, vp, i32, i64, vp, vp, vp]
+    lib.pgn_compose_frames_batch.argtypes = [vp, i32, i32, vp, vp, i32, vp, vp, f32, vp, vp]
     lib.pgn_debug_umma_gemm.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp]
     lib.pgn_debug_phase_timers.argtypes = [vp, i32, C.POINTER(C.c_uint64)]
     for name in EXPORTED:

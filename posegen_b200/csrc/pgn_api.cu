@@ -25,6 +25,21 @@ int fail(int code, const char* fmt, ...) {
                                        __FILE__, __LINE__);                                         \
   } while (0)
 
+// Every entry point runs on its context's device and leaves the caller's current device as it found it (torch keeps
+// its own notion of the current device; a DataParallel replica thread must not move it for the others).
+struct DeviceGuard {
+  int prev = -1;
+  cudaError_t err;
+  explicit DeviceGuard(int dev) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != dev) err = cudaSetDevice(dev); else if (err == cudaSuccess) prev = -1;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define PGN_ON_DEVICE(c)                                                                              \
+  DeviceGuard _guard((c)->cfg.device);                                                               \
+  if (_guard.err != cudaSuccess) return fail(PGN_E_CUDA, "cudaSetDevice(%d): %s", (c)->cfg.device, cudaGetErrorString(_guard.err))
+
 // (out, in) of the 12 linear layers, include/posegen_b200.h order
 const int kOut[PGN_N_LINEAR] = {256, 256, 256, 256, 256, 256, 256, 256, 1, 256, 128, 3};
 const int kIn[PGN_N_LINEAR]  = {432, 256, 256, 256, 256, 688, 256, 256, 256, 256, 904, 128};
@@ -81,7 +96,8 @@ int pgn_create(const pgn_config* cfg, pgn_context** out) {
     return fail(PGN_E_CUDA, "pgn_create: no CUDA device (%s); posegen_b200 has no CPU fallback",
                 e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
   if (cfg->device < 0 || cfg->device >= ndev) return fail(PGN_E_INVALID, "pgn_create: bad device ordinal %d", cfg->device);
-  PGN_CUDA(cudaSetDevice(cfg->device));
+  DeviceGuard _guard(cfg->device);
+  if (_guard.err != cudaSuccess) return fail(PGN_E_CUDA, "cudaSetDevice(%d): %s", cfg->device, cudaGetErrorString(_guard.err));
   cudaDeviceProp prop;
   PGN_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
   if (prop.major != 10) return fail(PGN_E_INVALID, "pgn_create: device is sm_%d%d; this library is built for sm_100a only", prop.major, prop.minor);
@@ -133,7 +149,7 @@ int pgn_create(const pgn_config* cfg, pgn_context** out) {
 
 void pgn_destroy(pgn_context* c) {
   if (!c) return;
-  cudaSetDevice(c->cfg.device);
+  DeviceGuard _guard(c->cfg.device);
   cudaFree(c->d_sc); cudaFree(c->d_status); cudaFree(c->d_c2w); cudaFree(c->d_rest); cudaFree(c->d_fold); cudaFree(c->d_chain_w[0]); cudaFree(c->d_chain_w[1]);
   for (int n = 0; n < 2; ++n) {
     cudaFree(c->d_w[n]); cudaFree(c->d_b[n]); cudaFree(c->d_wt[n]); cudaFree(c->d_wstream[n]); cudaFree(c->d_bf16_aux[n]);
@@ -144,7 +160,7 @@ void pgn_destroy(pgn_context* c) {
 int pgn_upload_weights(pgn_context* c, int net_id, const pgn_net_weights* w, int pointers_are_device, void* stream_) {
   if (!c || !w || net_id < 0 || net_id > 1) return fail(PGN_E_INVALID, "pgn_upload_weights: bad argument");
   cudaStream_t stream = (cudaStream_t)stream_;
-  PGN_CUDA(cudaSetDevice(c->cfg.device));
+  PGN_ON_DEVICE(c);
   const cudaMemcpyKind kind = pointers_are_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
   for (int l = 0; l < PGN_N_LINEAR; ++l) {
     if (!w->weight[l] || !w->bias[l]) return fail(PGN_E_INVALID, "pgn_upload_weights: null tensor %d", l);
@@ -182,7 +198,7 @@ int pgn_set_embed_scalars(pgn_context* c, float tau_v, float tau_d, const float*
                           float density_scale, float rgb_eps) {
   if (!c || !cutoff_v || !cutoff_d) return fail(PGN_E_INVALID, "pgn_set_embed_scalars: null argument");
   if (!(density_scale > 0.f)) return fail(PGN_E_INVALID, "pgn_set_embed_scalars: density_scale must be > 0");
-  PGN_CUDA(cudaSetDevice(c->cfg.device));
+  PGN_ON_DEVICE(c);
   c->h_sc.tau_v = tau_v; c->h_sc.tau_d = tau_d;
   memcpy(c->h_sc.cutoff_v, cutoff_v, PGN_J * sizeof(float));
   memcpy(c->h_sc.cutoff_d, cutoff_d, PGN_J * sizeof(float));
@@ -271,9 +287,13 @@ static int render_forward_impl(pgn_context* c, const pgn_render_inputs* in, cons
   if (in->n_rays == 0) return PGN_OK;
   if (!workspace || workspace_bytes < pgn_workspace_bytes(c, in->n_rays)) return fail(PGN_E_INVALID, "pgn_render_forward: workspace too small");
   cudaStream_t stream = (cudaStream_t)stream_;
-  PGN_CUDA(cudaSetDevice(c->cfg.device));
+  PGN_ON_DEVICE(c);
   const PgnRayRefs refs = make_refs(in);
   float* near_far = (float*)workspace;
+  if (in->chunk_starts) {
+    if (in->n_chunks <= 0) return fail(PGN_E_INVALID, "pgn_render_forward: chunk_starts without n_chunks");
+    PGN_CUDA(pgn_launch_near_far_chunks(refs, (const long long*)in->chunk_starts, in->n_chunks, near_far, stream));
+  } else
   PGN_CUDA(pgn_launch_near_far(refs, in->nanfill_chunk, near_far, stream));
   c->launches++;
   PgnOutputs o;
@@ -299,7 +319,7 @@ int64_t pgn_launch_count(const pgn_context* c) { return c ? c->launches : 0; }
 
 int pgn_check_device_status(pgn_context* c) {
   if (!c) return fail(PGN_E_INVALID, "pgn_check_device_status: null context");
-  PGN_CUDA(cudaSetDevice(c->cfg.device));
+  PGN_ON_DEVICE(c);
   int st = 0;
   PGN_CUDA(cudaMemcpy(&st, c->d_status, sizeof(int), cudaMemcpyDeviceToHost));
   if (st != 0) {
@@ -309,11 +329,16 @@ int pgn_check_device_status(pgn_context* c) {
   return PGN_OK;
 }
 
+const int32_t* pgn_device_status_ptr(pgn_context* c) { return c ? c->d_status : nullptr; }
+
 int pgn_near_far(pgn_context* c, const pgn_render_inputs* in, float* near_far, void* stream) {
   int rc = check_inputs(c, in, "pgn_near_far");
   if (rc) return rc;
   if (!near_far) return fail(PGN_E_INVALID, "pgn_near_far: null output");
-  PGN_CUDA(cudaSetDevice(c->cfg.device));
+  PGN_ON_DEVICE(c);
+  if (in->chunk_starts)
+    PGN_CUDA(pgn_launch_near_far_chunks(make_refs(in), (const long long*)in->chunk_starts, in->n_chunks, near_far, (cudaStream_t)stream));
+  else
   PGN_CUDA(pgn_launch_near_far(make_refs(in), in->nanfill_chunk, near_far, (cudaStream_t)stream));
   c->launches++;
   return PGN_OK;
@@ -324,7 +349,7 @@ int pgn_encode(pgn_context* c, const pgn_render_inputs* in, const float* z, int3
   if (rc) return rc;
   if (!z || !enc || n_z <= 0) return fail(PGN_E_INVALID, "pgn_encode: bad argument");
   if (!c->have_sc) return fail(PGN_E_STATE, "pgn_encode: scalars not set");
-  PGN_CUDA(cudaSetDevice(c->cfg.device));
+  PGN_ON_DEVICE(c);
   PGN_CUDA(pgn_launch_encode(make_refs(in), c->d_sc, z, n_z, enc, (cudaStream_t)stream));
   c->launches++;
   return PGN_OK;
@@ -335,7 +360,7 @@ int pgn_encode_bf16(pgn_context* c, const pgn_render_inputs* in, const float* z,
   if (rc) return rc;
   if (!z || !enc || n_z <= 0) return fail(PGN_E_INVALID, "pgn_encode_bf16: bad argument");
   if (!c->have_sc) return fail(PGN_E_STATE, "pgn_encode_bf16: scalars not set");
-  PGN_CUDA(cudaSetDevice(c->cfg.device));
+  PGN_ON_DEVICE(c);
   PGN_CUDA(pgn_launch_encode_bf16(make_refs(in), c->d_sc, z, n_z, reinterpret_cast<__nv_bfloat16*>(enc), (cudaStream_t)stream));
   c->launches++;
   return PGN_OK;
@@ -348,7 +373,7 @@ int pgn_mlp_delta(pgn_context* c, void* dh, int32_t has_input, const void* act, 
     return fail(PGN_E_INVALID, "pgn_mlp_delta: supported shapes are 256 columns with 0/1 head rows, 128 columns with 0/3");
   if (nrs > 0 && (!rs || !wr || rs_stride < nrs)) return fail(PGN_E_INVALID, "pgn_mlp_delta: head deltas / weights missing");
   if (!has_input && nrs == 0) return fail(PGN_E_INVALID, "pgn_mlp_delta: nothing to do");
-  PGN_CUDA(cudaSetDevice(c->cfg.device));
+  PGN_ON_DEVICE(c);
   PGN_CUDA(pgn_launch_mlp_delta(dh, has_input, act, m, n_cols, rs, rs_stride, nrs, wr, colsum, wsum, c->num_sms, (cudaStream_t)stream));
   c->launches++;
   return PGN_OK;
@@ -357,7 +382,7 @@ int pgn_mlp_delta(pgn_context* c, void* dh, int32_t has_input, const void* act, 
 int pgn_view_delta_from_mask(pgn_context* c, void* dG, const float* d_raw, const float* w_rgb, const void* vmask, int64_t m,
                              void* stream) {
   if (!c || !dG || !d_raw || !w_rgb || !vmask || m < 0) return fail(PGN_E_INVALID, "pgn_view_delta_from_mask: bad argument");
-  PGN_CUDA(cudaSetDevice(c->cfg.device));
+  PGN_ON_DEVICE(c);
   PGN_CUDA(pgn_launch_view_delta_bits(dG, d_raw, w_rgb, vmask, m, c->num_sms, (cudaStream_t)stream));
   c->launches++;
   return PGN_OK;
@@ -367,7 +392,7 @@ int pgn_mlp_delta_chain(pgn_context* c, const void* dG, const float* d_raw, cons
                         const void* wstream, const float* w_alpha, void* dz, float* colsum, uint32_t layer_mask, void* stream) {
   if (!c || !dG || !d_raw || !mask || !wstream || !w_alpha || !dz || !colsum || m < 0 || mask_rows < m)
     return fail(PGN_E_INVALID, "pgn_mlp_delta_chain: bad argument");
-  PGN_CUDA(cudaSetDevice(c->cfg.device));
+  PGN_ON_DEVICE(c);
   PGN_CUDA(pgn_launch_delta_chain(dG, d_raw, mask, mask_rows, m, wstream, w_alpha, dz, colsum, layer_mask, c->d_status, c->num_sms, (cudaStream_t)stream));
   c->launches++;
   return PGN_OK;
@@ -383,7 +408,7 @@ int pgn_mlp_delta_chain_net(pgn_context* c, int32_t net_id, const void* dG, cons
 int pgn_mlp(pgn_context* c, int net_id, const float* enc, int64_t m, float* raw, int32_t precision, void* stream) {
   if (!c || !enc || !raw || net_id < 0 || net_id > 1 || m < 0) return fail(PGN_E_INVALID, "pgn_mlp: bad argument");
   if (!c->have_w[net_id]) return fail(PGN_E_STATE, "pgn_mlp: weights not uploaded");
-  PGN_CUDA(cudaSetDevice(c->cfg.device));
+  PGN_ON_DEVICE(c);
   if (precision == PGN_PRECISION_FP32) {
     int rc2 = ensure_fp32_tier(c, (cudaStream_t)stream);
     if (rc2) return rc2;
@@ -403,7 +428,7 @@ int pgn_composite(pgn_context* c, const pgn_render_inputs* in, const float* raw,
   if (rc) return rc;
   if (!raw || !z || (s != PGN_S && s != PGN_T)) return fail(PGN_E_INVALID, "pgn_composite: s must be 64 or 80");
   if (!c->have_sc) return fail(PGN_E_STATE, "pgn_composite: scalars not set");
-  PGN_CUDA(cudaSetDevice(c->cfg.device));
+  PGN_ON_DEVICE(c);
   PGN_CUDA(pgn_launch_composite(make_refs(in), c->d_sc, raw, z, s, rgb_map, disp_map, acc_map, weights, alpha, (cudaStream_t)stream));
   c->launches++;
   return PGN_OK;
@@ -415,7 +440,7 @@ int pgn_encode_backward(pgn_context* c, const pgn_render_inputs* in, const float
   if (rc) return rc;
   if (!z || !g_enc || !d_skts || n_z <= 0) return fail(PGN_E_INVALID, "pgn_encode_backward: bad argument");
   if (!c->have_sc) return fail(PGN_E_STATE, "pgn_encode_backward: scalars not set");
-  PGN_CUDA(cudaSetDevice(c->cfg.device));
+  PGN_ON_DEVICE(c);
   PGN_CUDA(pgn_launch_encode_backward(make_refs(in), c->d_sc, z, n_z, g_enc, d_skts, (cudaStream_t)stream));
   c->launches++;
   return PGN_OK;
@@ -427,7 +452,7 @@ int pgn_encode_backward_bf16(pgn_context* c, const pgn_render_inputs* in, const 
   if (rc) return rc;
   if (!z || !g_xp || !g_d || !d_skts || n_z <= 0) return fail(PGN_E_INVALID, "pgn_encode_backward_bf16: bad argument");
   if (!c->have_sc) return fail(PGN_E_STATE, "pgn_encode_backward_bf16: scalars not set");
-  PGN_CUDA(cudaSetDevice(c->cfg.device));
+  PGN_ON_DEVICE(c);
   PGN_CUDA(pgn_launch_encode_backward_bf16(make_refs(in), c->d_sc, z, n_z, reinterpret_cast<const __nv_bfloat16*>(g_xp),
                                            reinterpret_cast<const __nv_bfloat16*>(g_d), d_skts, (cudaStream_t)stream));
   c->launches++;
@@ -440,7 +465,7 @@ int pgn_composite_backward(pgn_context* c, const pgn_render_inputs* in, const fl
   if (rc) return rc;
   if (!raw || !z || !g_rgb || !d_raw || (s != PGN_S && s != PGN_T)) return fail(PGN_E_INVALID, "pgn_composite_backward: bad argument");
   if (!c->have_sc) return fail(PGN_E_STATE, "pgn_composite_backward: scalars not set");
-  PGN_CUDA(cudaSetDevice(c->cfg.device));
+  PGN_ON_DEVICE(c);
   PGN_CUDA(pgn_launch_composite_backward(make_refs(in), c->d_sc, raw, z, s, g_rgb, g_acc, noise, d_raw, (cudaStream_t)stream));
   c->launches++;
   return PGN_OK;
@@ -449,7 +474,7 @@ int pgn_composite_backward(pgn_context* c, const pgn_render_inputs* in, const fl
 int pgn_sample_pdf(pgn_context* c, const float* z, const float* weights, int64_t n, float* z_samples, float* z_sorted,
                    int32_t* pdf_inds, int32_t* sorted_idxs, void* stream) {
   if (!c || !z || !weights || n < 0) return fail(PGN_E_INVALID, "pgn_sample_pdf: bad argument");
-  PGN_CUDA(cudaSetDevice(c->cfg.device));
+  PGN_ON_DEVICE(c);
   if (!c->have_sc) {  // only the linspace tables are needed
     PGN_CUDA(cudaMemcpy(c->d_sc, &c->h_sc, sizeof(PgnScalars), cudaMemcpyHostToDevice));
   }
@@ -462,7 +487,7 @@ int pgn_generate_rays(pgn_context* c, int32_t H, int32_t W, float focal, const f
                       int32_t x1, int32_t y1, float* ray_batch, void* stream_) {
   if (!c || !c2w || !ray_batch || x1 < x0 || y1 < y0) return fail(PGN_E_INVALID, "pgn_generate_rays: bad argument");
   cudaStream_t stream = (cudaStream_t)stream_;
-  PGN_CUDA(cudaSetDevice(c->cfg.device));
+  PGN_ON_DEVICE(c);
   PGN_CUDA(cudaMemcpyAsync(c->d_c2w, c2w, 12 * sizeof(float), cudaMemcpyHostToDevice, stream));
   PGN_CUDA(pgn_launch_generate_rays(H, W, focal, c->d_c2w, x0, y0, x1, y1, ray_batch, stream));
   c->launches++;
@@ -472,7 +497,7 @@ int pgn_generate_rays(pgn_context* c, int32_t H, int32_t W, float focal, const f
 int pgn_compose_frame(pgn_context* c, int32_t H, int32_t W, int32_t x0, int32_t y0, int32_t x1, int32_t y1,
                       const float* rgb_map, const float* acc_map, float bg, float* image, void* stream) {
   if (!c || !image || ((x1 > x0 && y1 > y0) && (!rgb_map || !acc_map))) return fail(PGN_E_INVALID, "pgn_compose_frame: bad argument");
-  PGN_CUDA(cudaSetDevice(c->cfg.device));
+  PGN_ON_DEVICE(c);
   PGN_CUDA(pgn_launch_compose_frame(H, W, x0, y0, x1, y1, rgb_map, acc_map, bg, image, (cudaStream_t)stream));
   c->launches++;
   return PGN_OK;
@@ -483,9 +508,51 @@ int pgn_pose_to_skts(pgn_context* c, const float* bones, const float* rest_pose,
                      void* stream_) {
   if (!c || !bones || !rest_pose || !skts || n_poses < 0) return fail(PGN_E_INVALID, "pgn_pose_to_skts: bad argument");
   cudaStream_t stream = (cudaStream_t)stream_;
-  PGN_CUDA(cudaSetDevice(c->cfg.device));
+  PGN_ON_DEVICE(c);
   PGN_CUDA(cudaMemcpyAsync(c->d_rest, rest_pose, PGN_J * 3 * sizeof(float), cudaMemcpyHostToDevice, stream));
   PGN_CUDA(pgn_launch_pose_fk(bones, c->d_rest, n_poses, cyl_extend, top_expand_ratio, bot_expand_ratio, skts, kps, cyls, l2ws, stream));
+  c->launches++;
+  return PGN_OK;
+}
+
+int pgn_pose_fk_backward(pgn_context* c, const float* bones, const float* rest_pose, int32_t n_poses, const float* g_skts,
+                         const float* g_kps, float* g_bones, void* stream_) {
+  if (!c || !bones || !rest_pose || !g_skts || !g_bones || n_poses < 0) return fail(PGN_E_INVALID, "pgn_pose_fk_backward: bad argument");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  PGN_ON_DEVICE(c);
+  PGN_CUDA(cudaMemcpyAsync(c->d_rest, rest_pose, PGN_J * 3 * sizeof(float), cudaMemcpyHostToDevice, stream));
+  PGN_CUDA(pgn_launch_pose_fk_backward(bones, c->d_rest, n_poses, g_skts, g_kps, g_bones, stream));
+  c->launches++;
+  return PGN_OK;
+}
+
+int pgn_cylinder_bboxes(pgn_context* c, const float* cyls, int32_t n, const double* w2c, int32_t H, int32_t W, float focal,
+                        int32_t* bbox, void* stream) {
+  if (!c || !cyls || !w2c || !bbox || n < 0 || H <= 0 || W <= 0) return fail(PGN_E_INVALID, "pgn_cylinder_bboxes: bad argument");
+  PGN_ON_DEVICE(c);
+  PGN_CUDA(pgn_launch_cyl_bboxes(cyls, n, w2c, H, W, (double)focal, bbox, (cudaStream_t)stream));
+  c->launches++;
+  return PGN_OK;
+}
+
+int pgn_generate_rays_batch(pgn_context* c, int32_t H, int32_t W, float focal, const float* c2w, const int32_t* bbox,
+                            const int64_t* offsets, int32_t n_poses, int64_t max_rays_per_pose, float* ray_batch,
+                            int32_t* pose_idx, void* stream_) {
+  if (!c || !c2w || !bbox || !offsets || !ray_batch || !pose_idx || n_poses < 0) return fail(PGN_E_INVALID, "pgn_generate_rays_batch: bad argument");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  PGN_ON_DEVICE(c);
+  PGN_CUDA(cudaMemcpyAsync(c->d_c2w, c2w, 12 * sizeof(float), cudaMemcpyHostToDevice, stream));
+  PGN_CUDA(pgn_launch_generate_rays_batch(H, W, focal, c->d_c2w, bbox, (const long long*)offsets, n_poses, max_rays_per_pose,
+                                          ray_batch, pose_idx, stream));
+  c->launches++;
+  return PGN_OK;
+}
+
+int pgn_compose_frames_batch(pgn_context* c, int32_t H, int32_t W, const int32_t* bbox, const int64_t* offsets, int32_t n_poses,
+                             const float* rgb_map, const float* acc_map, float bg, float* images, void* stream) {
+  if (!c || !bbox || !offsets || !images || !rgb_map || !acc_map || n_poses < 0) return fail(PGN_E_INVALID, "pgn_compose_frames_batch: bad argument");
+  PGN_ON_DEVICE(c);
+  PGN_CUDA(pgn_launch_compose_frames_batch(H, W, bbox, (const long long*)offsets, n_poses, rgb_map, acc_map, bg, images, (cudaStream_t)stream));
   c->launches++;
   return PGN_OK;
 }
@@ -495,7 +562,7 @@ int pgn_frame_to_hmr_input(pgn_context* c, const float* image, int32_t H, int32_
                            float* out, void* stream) {
   if (!c || !image || !out || !mean3 || !std3 || x0 < 0 || y0 < 0 || x1 > W || y1 > H || x1 <= x0 || y1 <= y0 || out_res <= 0)
     return fail(PGN_E_INVALID, "pgn_frame_to_hmr_input: bad argument");
-  PGN_CUDA(cudaSetDevice(c->cfg.device));
+  PGN_ON_DEVICE(c);
   PGN_CUDA(pgn_launch_hmr_input(image, H, W, x0, y0, x1, y1, out_res, mean3, std3, quantize_u8, out, (cudaStream_t)stream));
   c->launches++;
   return PGN_OK;
@@ -503,7 +570,7 @@ int pgn_frame_to_hmr_input(pgn_context* c, const float* image, int32_t H, int32_
 
 int pgn_debug_phase_timers(pgn_context* c, int32_t enable, uint64_t* out32) {
   if (!c) return fail(PGN_E_INVALID, "pgn_debug_phase_timers: null context");
-  PGN_CUDA(cudaSetDevice(c->cfg.device));
+  PGN_ON_DEVICE(c);
   if (out32) {
     const size_t n = (size_t)c->num_sms * 32;
     unsigned long long* h = new unsigned long long[n];
@@ -519,7 +586,8 @@ int pgn_debug_umma_gemm(pgn_context* c, const float* A, const float* B, float* D
                         int32_t variant, void* stream) {
   if (!c || !A || !B || !D || K <= 0 || K % 16 || N < 16 || N > 256 || N % 16) return fail(PGN_E_INVALID, "pgn_debug_umma_gemm: bad argument");
   if ((size_t)(K / 8) * 2048 + (size_t)(K / 8) * N * 16 > 200 * 1024) return fail(PGN_E_INVALID, "pgn_debug_umma_gemm: K too large");
-  PGN_CUDA(cudaSetDevice(c->cfg.device));
+  if (variant & 1) return fail(PGN_E_INVALID, "pgn_debug_umma_gemm: variant bit 0 (swapped LBO/SBO bring-up experiment) is not part of the shipped ABI");
+  PGN_ON_DEVICE(c);
   PGN_CUDA(pgn_launch_probe_umma(A, B, D, K, N, variant, c->d_status, (cudaStream_t)stream));
   c->launches++;
   return PGN_OK;

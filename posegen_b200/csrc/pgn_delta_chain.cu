@@ -326,11 +326,11 @@ cudaError_t pgn_launch_delta_chain(const void* dG, const float* d_raw, const voi
   cudaError_t e = cudaMemsetAsync(colsum, 0, sizeof(float) * kLayers * 256, stream);
   if (e != cudaSuccess || m == 0) return e;
   const size_t smem = sizeof(ChainSmem) + 1024;
-  static bool configured = false;
-  if (!configured) {
+  static PgnPerDeviceOnce configured;
+  if (configured.need()) {
     e = cudaFuncSetAttribute(pgn_delta_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    configured = true;
+    configured.set();
   }
   const long long n_blocks = (m + kBlockRows - 1) / kBlockRows;
   const unsigned grid = (unsigned)(n_blocks < num_sms ? n_blocks : num_sms);

@@ -5,6 +5,15 @@
 #include <stdint.h>
 #include "pgn_common.cuh"
 
+// One-time launch configuration (cudaFuncSetAttribute) is PER DEVICE: a process may hold contexts on several GPUs
+// (nn.DataParallel, core/raycasters.py:157), so the "configured" latch is indexed by the current device ordinal.
+struct PgnPerDeviceOnce {
+  bool done[64] = {};
+  int dev() const { int d = 0; cudaGetDevice(&d); return d & 63; }
+  bool need() const { return !done[dev()]; }
+  void set() { done[dev()] = true; }
+};
+
 // ---- fp32 CUDA-core engine -------------------------------------------------
 // wt[l]: transposed weights [K][N] of linear l (PGN linear order, include/posegen_b200.h);
 // small heads keep nn.Linear layout.
@@ -99,6 +108,17 @@ cudaError_t pgn_launch_pose_fk(const float* bones, const float* rest, int n_pose
                                float* skts, float* kps, float* cyls, float* l2ws, cudaStream_t stream);
 cudaError_t pgn_launch_hmr_input(const float* image, int H, int W, int x0, int y0, int x1, int y1, int R,
                                  const float* mean3, const float* std3, int quantize, float* out, cudaStream_t stream);
+
+// ---- batched generation-loop ends + FK backward (pgn_batch_kernels.cu) ----
+cudaError_t pgn_launch_cyl_bboxes(const float* cyls, int n, const double* w2c16, int H, int W, double focal, int* bbox, cudaStream_t stream);
+cudaError_t pgn_launch_generate_rays_batch(int H, int W, float focal, const float* c2w12_dev, const int* bbox, const long long* offsets,
+                                           int n_poses, long long max_rays_per_pose, float* ray_batch, int* pose_idx, cudaStream_t stream);
+cudaError_t pgn_launch_compose_frames_batch(int H, int W, const int* bbox, const long long* offsets, int n_poses, const float* rgb,
+                                            const float* acc, float bg, float* images, cudaStream_t stream);
+cudaError_t pgn_launch_pose_fk_backward(const float* bones, const float* rest, int n_poses, const float* g_skts, const float* g_kps,
+                                        float* g_bones, cudaStream_t stream);
+cudaError_t pgn_launch_near_far_chunks(const PgnRayRefs& rays, const long long* chunk_starts, long long n_chunks, float* near_far,
+                                       cudaStream_t stream);
 
 // bring-up probe (pgn_probe.cu)
 cudaError_t pgn_launch_probe_umma(const float* A, const float* B, float* D, int K, int N, int variant, int* status,

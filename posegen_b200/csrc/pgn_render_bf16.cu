@@ -1017,8 +1017,8 @@ cudaError_t pgn_pack_bf16_net(const float* const* w_dev, const float* const* b_d
 }
 
 static cudaError_t configure_bf16() {
-  static bool done = false;
-  if (done) return cudaSuccess;
+  static PgnPerDeviceOnce done;
+  if (!done.need()) return cudaSuccess;
   cudaError_t e = cudaFuncSetAttribute(pgn_render_bf16_kernel<false, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem) + 1024);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(pgn_render_bf16_kernel<false, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem) + 1024);
@@ -1029,7 +1029,7 @@ static cudaError_t configure_bf16() {
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(pgn_render_bf16_kernel<false, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem) + 1024);
   if (e != cudaSuccess) return e;
-  done = true;
+  done.set();
   return cudaSuccess;
 }
 

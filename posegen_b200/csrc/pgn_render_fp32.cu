@@ -386,13 +386,13 @@ size_t pgn_fp32_smem_bytes() { return sizeof(Smem); }
 cudaError_t pgn_launch_render_fp32(const PgnRayRefs& rays, const PgnOutputs& out, const PgnFp32Net& nc,
                                    const PgnFp32Net& nf, const PgnScalars* sc_dev, const float* near_far,
                                    int num_sms, cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
+  static PgnPerDeviceOnce configured;
+  if (configured.need()) {
     cudaError_t e = cudaFuncSetAttribute(pgn_render_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(pgn_mlp_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
     if (e != cudaSuccess) return e;
-    configured = true;
+    configured.set();
   }
   const long long n_groups = (rays.n_rays + kRPG - 1) / kRPG;
   if (n_groups == 0) return cudaSuccess;
@@ -403,11 +403,11 @@ cudaError_t pgn_launch_render_fp32(const PgnRayRefs& rays, const PgnOutputs& out
 
 cudaError_t pgn_launch_mlp_fp32(const PgnFp32Net& net, const float* enc, long long m, float* raw,
                                 int num_sms, cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
+  static PgnPerDeviceOnce configured;
+  if (configured.need()) {
     cudaError_t e = cudaFuncSetAttribute(pgn_mlp_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
     if (e != cudaSuccess) return e;
-    configured = true;
+    configured.set();
   }
   const long long n_tiles = (m + kTM - 1) / kTM;
   if (n_tiles == 0) return cudaSuccess;

@@ -12,13 +12,15 @@
 // accumulated in fp64 (numpy.nanmean is a float32 pairwise sum; difference <= 1 ulp).
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024)
-pgn_near_far_kernel(PgnRayRefs rays, long long chunk, float* __restrict__ near_far) {
+pgn_near_far_kernel(PgnRayRefs rays, long long chunk, const long long* __restrict__ chunk_starts, float* __restrict__ near_far) {
   __shared__ double s_sum[2][32];
   __shared__ int s_cnt[2][32];
   __shared__ float s_mean[2];
   __shared__ int s_any_nan;
-  const long long r0 = (long long)blockIdx.x * chunk;
-  const long long r1 = min(r0 + chunk, rays.n_rays);
+  // chunk_starts (optional): explicit chunk table [n_chunks + 1] for multi-image batches, so that a chunk never
+  // straddles two images (the reference chunks every image separately, run_nerf.py:77-95 -> core/trainer.py:64-81)
+  const long long r0 = chunk_starts ? chunk_starts[blockIdx.x] : (long long)blockIdx.x * chunk;
+  const long long r1 = chunk_starts ? min(chunk_starts[blockIdx.x + 1], rays.n_rays) : min(r0 + chunk, rays.n_rays);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x == 0) s_any_nan = 0;
   __syncthreads();
@@ -68,7 +70,14 @@ cudaError_t pgn_launch_near_far(const PgnRayRefs& rays, long long chunk, float* 
   if (rays.n_rays == 0) return cudaSuccess;
   if (chunk <= 0 || chunk > rays.n_rays) chunk = rays.n_rays;
   const long long n_chunks = (rays.n_rays + chunk - 1) / chunk;
-  pgn_near_far_kernel<<<(unsigned)n_chunks, 1024, 0, stream>>>(rays, chunk, near_far);
+  pgn_near_far_kernel<<<(unsigned)n_chunks, 1024, 0, stream>>>(rays, chunk, nullptr, near_far);
+  return cudaGetLastError();
+}
+
+cudaError_t pgn_launch_near_far_chunks(const PgnRayRefs& rays, const long long* chunk_starts, long long n_chunks, float* near_far,
+                                       cudaStream_t stream) {
+  if (rays.n_rays == 0 || n_chunks <= 0) return cudaSuccess;
+  pgn_near_far_kernel<<<(unsigned)n_chunks, 1024, 0, stream>>>(rays, 0, chunk_starts, near_far);
   return cudaGetLastError();
 }
 

@@ -44,7 +44,7 @@ class Engine:
         handle = C.c_void_p()
         _lib.check(self.lib.pgn_create(C.byref(cfg), C.byref(handle)))
         self.handle = handle
-        self._workspace = None
+        self._status_poll = None       # (pinned int32 tensor, event) of the last asynchronous watchdog read-back
 
     def close(self):
         if getattr(self, "handle", None):
@@ -104,10 +104,47 @@ class Engine:
         return int(self.lib.pgn_launch_count(self.handle))
 
     def check_status(self):
+        """Synchronous watchdog check (PGN_E_KERNEL if a bounded device-side wait gave up since the last check)."""
         _lib.check(self.lib.pgn_check_device_status(self.handle))
 
+    def poll_status(self):
+        """Asynchronous watchdog check for the hot paths: queues a 4-byte read-back of the device status word behind the
+        work issued so far and raises for the PREVIOUS read-back if it has completed and latched a code.  Never blocks."""
+        prev = self._status_poll
+        if prev is not None and prev[1].query():
+            code = int(prev[0][0])
+            if code != 0:
+                self._status_poll = None
+                self.check_status()                       # clears the latch and raises with the library's message
+                raise _lib.PosegenError(_lib.PGN_E_KERNEL, f"device watchdog tripped: pipeline wait code {code}")
+            prev = None
+        if prev is None:
+            if torch.cuda.is_current_stream_capturing():
+                return
+            host = torch.empty(1, dtype=torch.int32, pin_memory=True)
+            with torch.cuda.device(self.device):
+                host.copy_(self._status_tensor(), non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(self.device))
+            self._status_poll = (host, ev)
+
+    def _status_tensor(self):
+        if getattr(self, "_status_view", None) is None:
+            ptr = int(self.lib.pgn_device_status_ptr(self.handle))
+
+            class _Raw:
+                __cuda_array_interface__ = {"shape": (1,), "typestr": "<i4", "data": (ptr, False), "version": 2}
+            self._status_view = torch.as_tensor(_Raw(), device=self.device)
+        return self._status_view
+
+    def _scratch(self, n_rays: int, dev) -> torch.Tensor:
+        """The library's per-call workspace (8 B per ray: near/far).  Allocated per call from torch's caching allocator
+        instead of a cached, growable buffer: a CUDA-graph capture bakes the pointer into the graph and gets it from
+        the graph's private pool, so a later, larger eager call can never free memory a captured step still uses."""
+        return torch.empty(int(self.lib.pgn_workspace_bytes(self.handle, n_rays)), dtype=torch.uint8, device=dev)
+
     # ------------------------------------------------------------------ inputs
-    def _inputs(self, ray_batch, skts, cyls, pose_idx=None, nanfill_chunk=0, precision="bf16"):
+    def _inputs(self, ray_batch, skts, cyls, pose_idx=None, nanfill_chunk=0, precision="bf16", chunk_starts=None):
         _check_f32_cuda(ray_batch, "ray_batch")
         n = ray_batch.shape[0]
         if ray_batch.dim() != 2 or ray_batch.shape[1] != 11:
@@ -150,14 +187,19 @@ class Engine:
         inp.skts, inp.skts_stride = skts_t.data_ptr(), s_stride
         inp.cyls, inp.cyls_stride = cyls_t.data_ptr(), c_stride
         inp.nanfill_chunk = int(nanfill_chunk)
+        if chunk_starts is not None:         # explicit chunk table (multi-image batches): int64 [n_chunks + 1] on the device
+            if chunk_starts.dtype != torch.int64 or not chunk_starts.is_cuda or not chunk_starts.is_contiguous() or chunk_starts.numel() < 2:
+                raise ValueError("chunk_starts must be a contiguous CUDA int64 [n_chunks + 1] tensor")
+            inp.chunk_starts, inp.n_chunks = chunk_starts.data_ptr(), chunk_starts.numel() - 1
+            keep.append(chunk_starts)
         inp.precision = {"fp32": _lib.PRECISION_FP32, "bf16": _lib.PRECISION_BF16}[precision]
         return inp, keep
 
     # ---------------------------------------------------------------- hot path
     def render(self, ray_batch, skts, cyls, pose_idx=None, nanfill_chunk=0, precision="bf16",
-               return_alpha=True, taps=False) -> Dict[str, torch.Tensor]:
+               return_alpha=True, taps=False, chunk_starts=None) -> Dict[str, torch.Tensor]:
         """pgn_render_forward: the reference's RayCaster.render_rays (eval path)."""
-        inp, keep = self._inputs(ray_batch, skts, cyls, pose_idx, nanfill_chunk, precision)
+        inp, keep = self._inputs(ray_batch, skts, cyls, pose_idx, nanfill_chunk, precision, chunk_starts)
         n, dev = inp.n_rays, ray_batch.device
         f = lambda *sh: torch.empty(sh, dtype=torch.float32, device=dev)  # noqa: E731
         ret = {"rgb_map": f(n, 3), "disp_map": f(n), "acc_map": f(n), "rgb0": f(n, 3), "disp0": f(n), "acc0": f(n)}
@@ -169,12 +211,10 @@ class Engine:
         out = _lib.RenderOutputs()
         for k, v in ret.items():
             setattr(out, k, v.data_ptr())
-        need = self.lib.pgn_workspace_bytes(self.handle, n)
-        if self._workspace is None or self._workspace.numel() < need or self._workspace.device != dev:
-            self._workspace = torch.empty(max(need, 1 << 20), dtype=torch.uint8, device=dev)
+        ws = self._scratch(n, dev)
         with torch.cuda.device(dev):
             _lib.check(self.lib.pgn_render_forward(self.handle, C.byref(inp), C.byref(out),
-                                                   C.c_void_p(self._workspace.data_ptr()), self._workspace.numel(),
+                                                   C.c_void_p(ws.data_ptr()), ws.numel(),
                                                    self._stream()))
         return ret
 
@@ -200,9 +240,7 @@ class Engine:
                 continue
             nbytes = self.lib.pgn_activation_dump_bytes(n, p)
             acts[key] = torch.empty((nbytes // 2,), dtype=torch.bfloat16, device=dev)
-        need = self.lib.pgn_workspace_bytes(self.handle, n)
-        if self._workspace is None or self._workspace.numel() < need or self._workspace.device != dev:
-            self._workspace = torch.empty(max(need, 1 << 20), dtype=torch.uint8, device=dev)
+        ws = self._scratch(n, dev)
         with torch.cuda.device(dev):
             rnd = None
             if rand:
@@ -216,7 +254,7 @@ class Engine:
                         setattr(rnd, k, v.data_ptr())
             _lib.check(self.lib.pgn_render_forward_train(self.handle, C.byref(inp), C.byref(out), _ptr(acts["c"]), _ptr(acts["f"]),
                                                          C.byref(rnd) if rnd is not None else None,
-                                                         C.c_void_p(self._workspace.data_ptr()), self._workspace.numel(),
+                                                         C.c_void_p(ws.data_ptr()), ws.numel(),
                                                          self._stream()))
         return ret, acts
 
@@ -236,12 +274,10 @@ class Engine:
         nbytes = self.lib.pgn_mask_dump_bytes(n)
         rows = nbytes // 272
         buf = torch.empty((nbytes // 4,), dtype=torch.int32, device=dev)
-        need = self.lib.pgn_workspace_bytes(self.handle, n)
-        if self._workspace is None or self._workspace.numel() < need or self._workspace.device != dev:
-            self._workspace = torch.empty(max(need, 1 << 20), dtype=torch.uint8, device=dev)
+        ws = self._scratch(n, dev)
         with torch.cuda.device(dev):
             _lib.check(self.lib.pgn_render_forward_masks(self.handle, C.byref(inp), C.byref(out), _ptr(buf),
-                                                         C.c_void_p(self._workspace.data_ptr()), self._workspace.numel(),
+                                                         C.c_void_p(ws.data_ptr()), ws.numel(),
                                                          self._stream()))
         return ret, (buf[:rows * 64].view(8, rows, 8), buf[rows * 64:].view(rows, 4))
 
@@ -436,6 +472,54 @@ class Engine:
         _lib.check(self.lib.pgn_pose_to_skts(self.handle, _ptr(b), rest, n, float(extend_mm * ext_scale), float(top_expand_ratio),
                                              float(bot_expand_ratio), _ptr(skts), _ptr(kps), _ptr(cyls), _ptr(l2ws), self._stream()))
         return (skts, kps, cyls, l2ws) if return_l2ws else (skts, kps, cyls)
+
+    def pose_fk_backward(self, bones, rest_pose, g_skts, g_kps=None):
+        """pgn_pose_fk_backward: dL/d bones [B,24,3] from dL/d skts [B,24,4,4] (+ optional dL/d kps [B,24,3])."""
+        _check_f32_cuda(bones, "bones")
+        b = bones.contiguous()
+        n = b.shape[0]
+        gs = g_skts.float().contiguous()
+        gk = g_kps.float().contiguous() if g_kps is not None else None
+        if tuple(gs.shape) != (n, 24, 4, 4) or (gk is not None and tuple(gk.shape) != (n, 24, 3)):
+            raise ValueError("g_skts must be [B,24,4,4] and g_kps [B,24,3]")
+        rest = (C.c_float * 72)(*[float(v) for v in torch.as_tensor(rest_pose, dtype=torch.float32).reshape(-1).tolist()])
+        out = torch.empty((n, 24, 3), dtype=torch.float32, device=b.device)
+        _lib.check(self.lib.pgn_pose_fk_backward(self.handle, _ptr(b), rest, n, _ptr(gs), _ptr(gk), _ptr(out), self._stream()))
+        return out
+
+    def cylinder_bboxes(self, cyls, c2w, H, W, focal):
+        """pgn_cylinder_bboxes: cyls [B,5] (CUDA) -> int32 [B,4] (x0, y0, x1, y1) on the device (cylinder_to_box_2d)."""
+        import numpy as np
+        _check_f32_cuda(cyls, "cyls")
+        cy = cyls.contiguous()
+        c = np.asarray(c2w, dtype=np.float32)
+        full = np.vstack([c[:3, :4], [0, 0, 0, 1]]).astype(np.float32) if c.shape[0] == 3 else c
+        sw = np.array(full, copy=True)
+        sw[..., 1] = -sw[..., 1]
+        sw[..., 2] = -sw[..., 2]
+        w2c = np.linalg.inv(sw).astype(np.float64)          # nerf_c2w_to_extrinsic (skeleton_utils.py:1412-1421), float32 inverse
+        m = (C.c_double * 16)(*w2c.reshape(-1).tolist())
+        out = torch.empty((cy.shape[0], 4), dtype=torch.int32, device=cy.device)
+        _lib.check(self.lib.pgn_cylinder_bboxes(self.handle, _ptr(cy), cy.shape[0], m, int(H), int(W), float(focal), _ptr(out), self._stream()))
+        return out
+
+    def generate_rays_batch(self, H, W, focal, c2w, bboxes, offsets, n_total, max_rays):
+        """pgn_generate_rays_batch: (ray_batch [n_total,11], pose_idx int32 [n_total]) for B bboxes (device int32 [B,4]),
+        offsets device int64 [B+1]."""
+        c = (C.c_float * 12)(*[float(v) for v in torch.as_tensor(c2w)[:3, :4].reshape(-1).tolist()])
+        rb = torch.empty((n_total, 11), dtype=torch.float32, device=self.device)
+        pidx = torch.empty((n_total,), dtype=torch.int32, device=self.device)
+        _lib.check(self.lib.pgn_generate_rays_batch(self.handle, int(H), int(W), float(focal), c, _ptr(bboxes), _ptr(offsets),
+                                                    bboxes.shape[0], int(max_rays), _ptr(rb), _ptr(pidx), self._stream()))
+        return rb, pidx
+
+    def compose_frames_batch(self, H, W, bboxes, offsets, rgb_map, acc_map, bg=1.0):
+        """pgn_compose_frames_batch: [B,H,W,3] white-background frames from the batch's rgb / acc rows."""
+        n = bboxes.shape[0]
+        img = torch.empty((n, H, W, 3), dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.pgn_compose_frames_batch(self.handle, int(H), int(W), _ptr(bboxes), _ptr(offsets), n, _ptr(rgb_map.contiguous()),
+                                                     _ptr(acc_map.contiguous()), float(bg), _ptr(img), self._stream()))
+        return img
 
     def frame_to_hmr_input(self, image, crop=(100, 100, 412, 412), out_res=224, mean=(0.485, 0.456, 0.406),
                            std=(0.485, 0.456, 0.406), quantize_u8=True):

@@ -141,20 +141,18 @@ def render_pose_images(rc, bones: torch.Tensor, rest_pose: torch.Tensor, c2w: np
                        focal: float = 1000.0, ext_scale: float = 0.001, chunk: int = 16384, bg: float = 1.0):
     """bones [B,24,3] axis-angle (requires grad) -> frames [B,H,W,3] with autograd back to `bones`.
 
-    FK with autograd (`fk.smpl_skts`), bbox from the detached key points (`kp_to_valid_rays`), rays on the device."""
+    FK forward and backward on the device (`fk.device_smpl_skts`: `pgn_pose_to_skts` / `pgn_pose_fk_backward`), cylinders
+    and bboxes on the device (`pgn_cylinder_bboxes`, detached like the reference's numpy `kp_to_valid_rays`; one read-back
+    of the B integer bboxes sizes the launches), rays on the device."""
     from . import fk
     dev = bones.device
     eng = rc.engine(dev)
-    skts, kps = fk.smpl_skts(bones.double(), torch.as_tensor(rest_pose, dtype=torch.float64, device=dev))
-    skts = skts.float()
-    kps_np = kps.detach().cpu().numpy()
+    skts, kps, cyls = fk.device_smpl_skts(eng, bones, rest_pose, ext_scale)
+    bb = eng.cylinder_bboxes(cyls, c2w, H, W, float(focal)).cpu().numpy()
     frames = []
     for b in range(bones.shape[0]):
-        cyl_np = syn.bounding_cylinder(kps_np[b], ext_scale=ext_scale)
-        tl, br = syn.cylinder_bbox_2d(cyl_np, H, W, focal, c2w)
-        x0, y0, x1, y1 = int(tl[0]), int(tl[1]), int(br[0]), int(br[1])
+        x0, y0, x1, y1 = (int(v) for v in bb[b])
         rb = eng.generate_rays(H, W, float(focal), c2w, x0, y0, x1, y1)
-        cyl = torch.as_tensor(cyl_np, dtype=torch.float32, device=dev)
-        rgb, acc = render_frame(rc, rb, skts[b], cyl, chunk)
+        rgb, acc = render_frame(rc, rb, skts[b], cyls[b], chunk)
         frames.append(compose_white(rgb, acc, H, W, x0, y0, x1, y1, bg))
     return torch.stack(frames), kps

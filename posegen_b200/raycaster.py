@@ -17,8 +17,9 @@ Unsupported reference options raise NotImplementedError (never a silent fallback
 """
 from __future__ import annotations
 
+import os
 from types import SimpleNamespace
-from typing import Optional
+from typing import Dict, Optional
 
 import torch
 import torch.nn as nn
@@ -58,6 +59,19 @@ class NeRF(nn.Module):
     def forward(self, *a, **k):
         raise NotImplementedError("NeRF.forward runs only inside posegen_b200's fused CUDA kernels "
                                   "(use RayCaster.forward or Engine.mlp)")
+
+
+def net_tensors(net: nn.Module) -> Dict[str, torch.Tensor]:
+    """'<layer>.weight' / '<layer>.bias' tensors of one NeRF by attribute access.  Unlike `named_parameters()` /
+    `state_dict()` this also works on an `nn.DataParallel` replica, whose parameters are plain (non-leaf) tensor
+    attributes produced by Broadcast (torch/nn/parallel/replicate.py) - gradients flow back through them."""
+    out = {}
+    for name in LINEAR_ORDER:
+        mod = net
+        for part in name.split("."):
+            mod = mod[int(part)] if part.isdigit() else getattr(mod, part)
+        out[f"{name}.weight"], out[f"{name}.bias"] = mod.weight, mod.bias
+    return out
 
 
 class Embedder(nn.Module):
@@ -130,7 +144,7 @@ class RayCaster(nn.Module):
 
     # -- engine / weight sync ---------------------------------------------------
     def _param_signature(self):
-        ps = list(self.parameters())
+        ps = list(net_tensors(self.network).values()) + list(net_tensors(self.network_fine).values())
         return tuple(p._version for p in ps) + tuple(p.data_ptr() for p in ps)
 
     def _scalar_signature(self):
@@ -157,9 +171,11 @@ class RayCaster(nn.Module):
         eng = self._engines[key]
         sig_w, sig_s = self._param_signature(), self._scalar_signature()
         up = self._uploaded.get(key, (None, None))
-        if up[0] != sig_w or self._dirty.pop(key, False):
-            eng.upload_net(0, self.network.state_dict())
-            eng.upload_net(1, self.network_fine.state_dict())
+        # a DataParallel replica receives freshly broadcast parameter copies every forward (possibly at recycled
+        # addresses): its packed copy is always refreshed
+        if up[0] != sig_w or self._dirty.pop(key, False) or getattr(self, "_is_replica", False):
+            eng.upload_net(0, net_tensors(self.network))
+            eng.upload_net(1, net_tensors(self.network_fine))
         if up[1] != sig_s:
             eng.set_scalars(float(self.embed_fn.tau), float(self.embeddirs_fn.tau),
                             self.embed_fn.cutoff_dist.detach().flatten().tolist(),
@@ -269,8 +285,9 @@ class RayCaster(nn.Module):
         ret = eng.render(ray_batch.float(), skts.to(ray_batch.device).float(), cyls.to(ray_batch.device).float(),
                          nanfill_chunk=n if nanfill_chunk is None else nanfill_chunk,
                          precision=precision or self.precision, return_alpha=self.return_alpha)
-        if not self.return_alpha:
-            ret["alpha"] = ret["alpha0"] = None
+        # alpha / alpha0 are simply absent when not requested: the reference's batchify_rays concatenates every key
+        # of the returned dict (core/trainer.py:75-80), so a None entry would break it
+        eng.poll_status()
         return ret
 
     # -- reference API surface -------------------------------------------------------
@@ -295,6 +312,8 @@ class RayCaster(nn.Module):
                 "embeddirs_state_dict": self.embeddirs_fn.state_dict()}
 
     def load_state_dict(self, ckpt, strict=True):
+        """core/raycasters.py:768-788: a checkpoint dict with the five reference keys (extra keys such as global_step /
+        optimizer_state_dict of a `Trainer.save_nerf` .tar are ignored here; `load_ckpt_from_path` reads them)."""
         def conv(sd):
             return {k: torch.as_tensor(v) for k, v in sd.items()}
         self.network.load_state_dict(conv(ckpt["network_fn_state_dict"]), strict=strict)
@@ -355,26 +374,52 @@ def create_raycaster(args, data_attrs, device=None, precision="bf16"):
     grad_vars = [p for p in ray_caster.parameters() if p.requires_grad]
     optimizer = torch.optim.Adam(params=grad_vars, lr=args.lrate, betas=(0.9, 0.999))
     start, loaded_ckpt = 0, None
+    # checkpoint discovery of core/raycasters.py:125-142: an explicit ft_path, else the newest *.tar of basedir/expname
     ft_path = getattr(args, "ft_path", None)
-    if ft_path not in (None, "None") and not getattr(args, "no_reload", False):
-        loaded_ckpt = torch.load(ft_path, map_location="cpu")
-        ray_caster.load_state_dict(loaded_ckpt)
-        start = 0 if getattr(args, "finetune", False) else loaded_ckpt.get("global_step", 0)
+    if ft_path not in (None, "None"):
+        ckpts = [ft_path]
+    else:
+        ckpts = []
+        basedir, expname = getattr(args, "basedir", None), getattr(args, "expname", None)
+        if basedir is not None and expname is not None and os.path.isdir(os.path.join(basedir, expname)):
+            ckpts = [os.path.join(basedir, expname, f) for f in sorted(os.listdir(os.path.join(basedir, expname)))
+                     if "tar" in f and "pose" not in f]
+    if len(ckpts) > 0 and not getattr(args, "no_reload", False):
+        start, ray_caster, optimizer, loaded_ckpt = load_ckpt_from_path(ray_caster, optimizer, ckpts[-1],
+                                                                        getattr(args, "finetune", False))
+        if getattr(args, "finetune", False):
+            start = 0
     preproc_kwargs = {
         "pts_tr_fn": _EncoderTag("W2LEncoder", N_JOINTS), "kp_input_fn": _EncoderTag("RelDist", N_JOINTS),
         "view_input_fn": _EncoderTag("VecNorm", N_JOINTS * 3), "bone_input_fn": _EncoderTag("VecNorm", N_JOINTS * 3),
         "density_scale": args.density_scale, "density_fn": torch.nn.functional.relu,
     }
+    # the reference hands the TRAINING kwargs an nn.DataParallel wrapper (core/raycasters.py:157) and its trainer
+    # dereferences `.module` (core/trainer.py:267,272,506); the test kwargs keep the bare module (:172)
+    # (without a CUDA device nn.DataParallel is a pass-through that still has `.module`)
+    debug_one = getattr(args, "debug", False) and torch.cuda.is_available()
+    wrapped = nn.DataParallel(ray_caster, device_ids=[0]) if debug_one else nn.DataParallel(ray_caster)
     render_kwargs_train = {
-        "ray_caster": ray_caster, "perturb": args.perturb, "N_importance": args.N_importance,
+        "ray_caster": wrapped, "perturb": args.perturb, "N_importance": args.N_importance,
         "N_samples": args.N_samples, "use_viewdirs": args.use_viewdirs, "raw_noise_std": args.raw_noise_std,
         "ray_noise_std": args.ray_noise_std, "ext_scale": args.ext_scale, "preproc_kwargs": preproc_kwargs,
         "lindisp": args.lindisp, "nerf_type": args.nerf_type,
     }
     render_kwargs_test = dict(render_kwargs_train)
-    render_kwargs_test.update(perturb=False, raw_noise_std=0., ray_noise_std=0.)
+    render_kwargs_test.update(ray_caster=ray_caster, perturb=False, raw_noise_std=0., ray_noise_std=0.)
     optimizer.zero_grad()
     return render_kwargs_train, render_kwargs_test, start, grad_vars, optimizer, loaded_ckpt
+
+
+def load_ckpt_from_path(ray_caster, optimizer, ckpt_path, finetune=False):
+    """core/cutoff_embedder.py:227-238: weights + embedder buffers, and (unless fine-tuning) the optimizer state;
+    returns (global_step, ray_caster, optimizer, ckpt)."""
+    ckpt = torch.load(ckpt_path, map_location="cpu", weights_only=False)
+    global_step = ckpt["global_step"]
+    ray_caster.load_state_dict(ckpt)
+    if optimizer is not None and not finetune and "optimizer_state_dict" in ckpt:
+        optimizer.load_state_dict(ckpt["optimizer_state_dict"])
+    return global_step, ray_caster, optimizer, ckpt
 
 
 def raycaster_from_checkpoint(ckpt: dict, device="cuda", precision="bf16") -> RayCaster:

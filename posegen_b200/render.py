@@ -5,6 +5,10 @@ reference driver keeps working; `render_path` is the per-image driver of run_ner
 re-designed for the GPU: rays of the cylinder bbox are generated on the device, each image is
 one kernel launch over all of its rays (no 4096-ray Python chunk loop, no per-chunk H2D of
 replicated pose tensors), and the white-background composite + scatter happens on the device.
+`render_pose_batch` is the batched, host-free form for the PoseGen generation loop (one camera, B generated
+poses): device FK -> device cylinders -> device bboxes -> ONE ray batch and ONE fused render launch per group
+of poses (the `pose_idx` form of the C ABI) -> device frame composition; the only host round trip is one
+read-back of the B integer bboxes (16 B per pose) that sizes the launches.
 """
 from __future__ import annotations
 
@@ -106,6 +110,55 @@ def render_path(render_poses, hwf, chunk, render_kwargs, kp=None, skts=None, cyl
         disps.append(disp.view(H, W, 1))
         accs.append(acc.view(H, W, 1))
     rgbs, disps, accs = torch.stack(rgbs), torch.nan_to_num(torch.stack(disps), nan=0.0), torch.stack(accs)
+    torch.cuda.current_stream(dev).synchronize()
+    eng.check_status()                 # a tripped device-side watchdog must not hand back garbage frames silently
     if to_numpy:
         return rgbs.cpu().numpy(), disps.cpu().numpy(), (accs.cpu().numpy() if ret_acc else []), valid_idxs, bboxes
     return rgbs, disps, (accs if ret_acc else []), valid_idxs, bboxes
+
+
+@torch.no_grad()
+def render_pose_batch(ray_caster, bones, rest_pose, c2w, hwf, crop=None, bg=1.0, chunk=4096, poses_per_launch=16,
+                      ext_scale=0.001, precision=None, hmr_res=224):
+    """bones [B,24,3] axis-angle (CUDA) -> (frames [B,H,W,3], HMR inputs [B,3,R,R] or None, number of rays rendered).
+
+    The generation loop of run_gan.py:2299-2347 (render every generated pose from the fixed camera, hand the crop to
+    HMR) without per-image host work: `pgn_pose_to_skts` -> `pgn_cylinder_bboxes` -> [one 16 B/pose read-back] ->
+    per group of `poses_per_launch` poses: `pgn_generate_rays_batch` -> `pgn_render_forward` (pose_idx form, explicit
+    per-image chunk table so the near/far NaN fill keeps the reference's per-image 4096-ray chunks) ->
+    `pgn_compose_frames_batch`; then `pgn_frame_to_hmr_input` per frame when `crop` is given."""
+    H, W, focal = hwf
+    dev = bones.device
+    eng = ray_caster.engine(dev)
+    B = bones.shape[0]
+    skts, kps, cyls = eng.pose_to_skts(bones.float().contiguous(), rest_pose, ext_scale=ext_scale)
+    bboxes = eng.cylinder_bboxes(cyls, c2w, H, W, float(focal))
+    bb = bboxes.cpu().numpy().astype(np.int64)                       # the loop's only device->host read
+    areas = np.clip(bb[:, 2] - bb[:, 0], 0, None) * np.clip(bb[:, 3] - bb[:, 1], 0, None)
+    # launch tables for every group, built and uploaded once, before the first render launch
+    groups, flat = [], []
+    for s in range(0, B, poses_per_launch):
+        a = areas[s:s + poses_per_launch]
+        off = np.concatenate([[0], np.cumsum(a)]).astype(np.int64)
+        cs = [np.arange(off[i], off[i + 1], chunk, dtype=np.int64) for i in range(len(a))]
+        cs = np.concatenate(cs + [off[-1:]]) if off[-1] > 0 else np.zeros(1, np.int64)
+        groups.append((s, len(a), int(off[-1]), int(a.max()) if len(a) else 0, len(off), len(cs)))
+        flat += [off, cs]
+    table = torch.from_numpy(np.concatenate(flat)).pin_memory().to(dev, non_blocking=True)
+    frames = torch.empty((B, H, W, 3), dtype=torch.float32, device=dev)
+    pos = 0
+    for s, nb, n_total, max_rays, n_off, n_cs in groups:
+        off_d, cs_d = table[pos:pos + n_off], table[pos + n_off:pos + n_off + n_cs]
+        pos += n_off + n_cs
+        if n_total == 0:
+            frames[s:s + nb] = bg
+            continue
+        rb, pidx = eng.generate_rays_batch(H, W, float(focal), c2w, bboxes[s:s + nb], off_d, n_total, max_rays)
+        ret = eng.render(rb, skts[s:s + nb], cyls[s:s + nb], pose_idx=pidx, chunk_starts=cs_d,
+                         precision=precision or ray_caster.precision, return_alpha=False)
+        frames[s:s + nb] = eng.compose_frames_batch(H, W, bboxes[s:s + nb], off_d, ret["rgb_map"], ret["acc_map"], bg)
+    hmr = None
+    if crop is not None:
+        hmr = torch.stack([eng.frame_to_hmr_input(f, crop=crop, out_res=hmr_res) for f in frames])
+    eng.poll_status()
+    return frames, hmr, int(areas.sum())

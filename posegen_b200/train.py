@@ -26,6 +26,8 @@ from typing import Callable, Dict, List
 import torch
 import torch.distributed as dist
 
+from .raycaster import net_tensors
+
 S, T = 64, 80
 USE_DELTA_CHAIN = True        # trunk backward through pgn_mlp_delta_chain (False: layer by layer, for A/B runs)
 PARAM_ORDER = [f"pts_linears.{i}.{k}" for i in range(8) for k in ("weight", "bias")] + \
@@ -211,7 +213,7 @@ class _RenderTrainFn(torch.autograd.Function):
             z = z.contiguous()
             d_raw = eng.composite_backward(rb, sk, cy, raw_p, z, gr, ga, noise=nz)
             enc = eng.encode_bf16(rb, sk, cy, z).reshape(-1, 1080) if want_w else None
-            pd = dict(net.named_parameters())
+            pd = net_tensors(net)
             net_id = 0 if net is rc.network else 1
             gd = mlp_backward(pd, enc, acts, d_raw.reshape(-1, 4), eng.mlp_delta, want_input_grad=want_sk, want_weight_grad=want_w,
                               chain=functools.partial(eng.mlp_delta_chain_net, net_id) if USE_DELTA_CHAIN else None)
@@ -241,14 +243,13 @@ def render_train(rc, ray_batch, skts, cyls, nanfill_chunk=None, perturb: float =
                  rand: Dict[str, torch.Tensor] | None = None) -> Dict[str, torch.Tensor]:
     """Differentiable (w.r.t. the two MLPs' parameters and `skts`) render of a ray batch: the train-mode body of
     RayCaster.forward.  Returns the reference's dict (core/raycasters.py:711-724) without alpha/alpha0."""
-    params = [dict(net.named_parameters())[k] for net in (rc.network, rc.network_fine) for k in PARAM_ORDER]
+    params = [net_tensors(net)[k] for net in (rc.network, rc.network_fine) for k in PARAM_ORDER]
     n = ray_batch.shape[0]
     if rand is None:
         rand = draw_train_random(n, ray_batch.device, perturb, raw_noise_std, float(rc.network.density_scale))
     out = _RenderTrainFn.apply(rc, ray_batch.float().contiguous(), skts if skts.dtype == torch.float32 else skts.float(), cyls.float(),
                                n if nanfill_chunk is None else nanfill_chunk, rand or None, *params)
-    return {"rgb_map": out[0], "acc_map": out[1], "rgb0": out[2], "acc0": out[3], "disp_map": out[4], "disp0": out[5],
-            "alpha": None, "alpha0": None}
+    return {"rgb_map": out[0], "acc_map": out[1], "rgb0": out[2], "acc0": out[3], "disp_map": out[4], "disp0": out[5]}
 
 
 def allreduce_gradients(parameters, average: bool = True):

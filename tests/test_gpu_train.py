@@ -353,3 +353,45 @@ def test_graphed_training_step_follows_the_eager_one(engine, train_case):
                 loss = g(ray_batch=rbt, skts=sk, cyls=cy, target=t)
             losses[mode] = float(loss)
     assert abs(losses["eager"] - losses["graph"]) <= 2e-3 * max(1.0, abs(losses["eager"])), losses
+
+
+def test_graph_replay_survives_a_larger_eager_render(engine, train_case):
+    """the per-call near/far scratch must not be a cached, growable buffer - a captured step would keep the
+    old pointer.  Capture a step, render a much larger batch eagerly through the SAME module, empty the allocator
+    cache, replay: the replayed losses continue the trajectory of an undisturbed twin."""
+    from posegen_b200.train import GraphedTrainStep
+    frame, ckpt, rb, tgt = train_case
+    n, dev = 512, torch.device("cuda")
+    rbt = torch.as_tensor(rb[:n], device=dev)
+    sk = torch.as_tensor(np.repeat(frame.pose.skts[None], n, 0), device=dev)
+    cy = torch.as_tensor(np.repeat(frame.pose.cyl[None], n, 0), device=dev)
+    t = torch.full((n, 3), 0.25, device=dev)
+
+    def loss_fn(ret, tg):
+        return ((ret["rgb_map"] + (1 - ret["acc_map"][:, None]) - tg) ** 2).mean() + ((ret["rgb0"] + (1 - ret["acc0"][:, None]) - tg) ** 2).mean()
+
+    big = torch.as_tensor(np.tile(rb, (200, 1)), device=dev)             # 307k rays: a 2.4 MB near/far scratch
+    out = {}
+    for disturb in (False, True):
+        rc = raycaster_from_checkpoint(ckpt, device="cuda", precision="bf16")
+        rc.train()
+        opt = torch.optim.Adam([p for p in rc.parameters() if p.requires_grad], lr=5e-4, fused=True, capturable=True)
+        g = GraphedTrainStep(rc, opt, loss_fn, {"ray_batch": rbt, "skts": sk, "cyls": cy, "target": t}, warmup=3, perturb=0., raw_noise_std=0.)
+        g(ray_batch=rbt, skts=sk, cyls=cy, target=t)
+        if disturb:
+            rc.eval()
+            with torch.no_grad():
+                r = rc(big, N_samples=64, N_importance=16, kp_batch=None, skts=torch.as_tensor(frame.pose.skts, device=dev),
+                       cyls=torch.as_tensor(frame.pose.cyl, device=dev), bones=None, cams=None)
+            assert torch.isfinite(r["rgb_map"]).all()
+            rc.train()
+            del r
+            torch.cuda.synchronize()
+            torch.cuda.empty_cache()
+            junk = [torch.full((1 << 20,), float("nan"), device=dev) for _ in range(8)]      # recycle freed blocks with poison
+        losses = [float(g(ray_batch=rbt, skts=sk, cyls=cy, target=t)) for _ in range(3)]
+        torch.cuda.synchronize()
+        rc.engine(dev).check_status()
+        out[disturb] = losses
+    assert np.isfinite(out[True]).all()
+    assert np.allclose(out[True], out[False], rtol=2e-3, atol=1e-5), out

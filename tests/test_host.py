@@ -23,7 +23,7 @@ def test_library_exports_every_header_symbol(lib_path):
     lib = ctypes.CDLL(lib_path)
     for name in declared:
         assert hasattr(lib, name), f"{name} not exported by {lib_path}"
-    assert lib.pgn_abi_version() == 1
+    assert lib.pgn_abi_version() == 2
 
 
 def test_no_cpu_fallback_without_gpu(lib_path):
@@ -103,6 +103,45 @@ def test_raycaster_drop_in_surface():
     with pytest.raises(RuntimeError):
         rc.eval()(torch.zeros(4, 11), N_samples=64, N_importance=16, kp_batch=None,
                   skts=torch.zeros(4, 24, 4, 4), cyls=torch.zeros(4, 5))      # CPU tensors: no fallback
+
+
+def test_create_raycaster_dataparallel_contract_and_checkpoint_reload(tmp_path):
+    """core/raycasters.py:125-142,157,172 + core/cutoff_embedder.py:227-238: the training kwargs carry an nn.DataParallel
+    (`.module` is dereferenced by core/trainer.py:267,272,506), the test kwargs the bare module; the newest *.tar of
+    basedir/expname is reloaded with global_step and the optimizer state unless no_reload / finetune say otherwise."""
+    kw_train, kw_test, start, grad_vars, optim, ckpt = rcmod.create_raycaster(rcmod.surreal_args(), {"skel_type": None})
+    assert isinstance(kw_train["ray_caster"], torch.nn.DataParallel)
+    assert kw_train["ray_caster"].module is kw_test["ray_caster"] and isinstance(kw_test["ray_caster"], rcmod.RayCaster)
+    assert start == 0 and ckpt is None
+    rc = kw_test["ray_caster"]
+    # what Trainer.save_nerf writes (core/trainer.py:486-509)
+    for p in grad_vars:
+        p.grad = torch.full_like(p, 1e-3)
+    optim.step()
+    rc.update_embed_fns(125000, rcmod.surreal_args())
+    exp = tmp_path / "exp"
+    exp.mkdir()
+    torch.save({"global_step": 100, "optimizer_state_dict": optim.state_dict(), "poseopt_layer_state_dict": None,
+                **kw_train["ray_caster"].module.state_dict()}, exp / "000100.tar")
+    torch.save({"global_step": 7, **rc.state_dict()}, exp / "000007.tar")            # older: must not be picked
+    torch.save({"global_step": 999}, exp / "pose_000999.tar")                          # pose-only files are skipped
+    args = rcmod.surreal_args(no_reload=False, basedir=str(tmp_path), expname="exp")
+    _, kw2, start2, gv2, optim2, ckpt2 = rcmod.create_raycaster(args, {"skel_type": None})
+    rc2 = kw2["ray_caster"]
+    assert start2 == 100 and ckpt2["global_step"] == 100
+    for a, b in zip(rc.parameters(), rc2.parameters()):
+        assert torch.equal(a, b)
+    assert abs(rc2.embed_fn.get_tau() - rc.embed_fn.get_tau()) < 1e-4 and rc2.embed_fn.get_tau() > 20.
+    st = optim2.state[gv2[0]]
+    assert int(st["step"]) == 1 and torch.equal(st["exp_avg"], optim.state[grad_vars[0]]["exp_avg"])
+    # finetune: weights yes, step counter and optimizer state no
+    _, _, start3, gv3, optim3, _ = rcmod.create_raycaster(rcmod.surreal_args(no_reload=False, finetune=True, basedir=str(tmp_path),
+                                                                          expname="exp"), {"skel_type": None})
+    assert start3 == 0 and len(optim3.state) == 0
+    # explicit ft_path wins over the directory listing
+    _, _, start4, _, _, _ = rcmod.create_raycaster(rcmod.surreal_args(no_reload=False, ft_path=str(exp / "000007.tar"),
+                                                                      basedir=str(tmp_path), expname="exp"), {"skel_type": None})
+    assert start4 == 7
 
 
 def test_unsupported_options_raise():

@@ -99,17 +99,8 @@ def joints_from_rotmats(R, rest):
     return torch.stack(out_t, 1)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--steps", type=int, default=3)
-    ap.add_argument("--warmup", type=int, default=1)
-    ap.add_argument("--poses-per-gpu", type=int, default=2)
-    ap.add_argument("--res", type=int, default=512)
-    ap.add_argument("--chunk", type=int, default=16384)
-    ap.add_argument("--profile", default=None, help="write a torch.profiler kernel table of one step to this file")
-    a = ap.parse_args()
-    rank, world, local = pdist.env_rank_world()
-    pdist.init_process_group("nccl" if world > 1 else None)
+def run(rank, world, local, steps=3, warmup=1, poses_per_gpu=2, res=512, chunk=16384, profile=None):
+    """One leg (process group already initialised for world > 1): returns the result dict on every rank."""
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     torch.manual_seed(1234 + rank)
@@ -122,19 +113,20 @@ def main():
     for p in hmr.parameters():
         p.requires_grad_(False)
     opt = torch.optim.Adam(gen.parameters(), lr=1e-4)
-    rest = torch.as_tensor(syn.SMPL_REST_POSE * syn.BODY_SCALE, dtype=torch.float32, device=dev)
-    H = W = a.res
-    focal = 1000.0 * a.res / 512
+    rest_np = (syn.SMPL_REST_POSE * syn.BODY_SCALE).astype(np.float32)
+    rest = torch.as_tensor(rest_np, device=dev)
+    H = W = res
+    focal = 1000.0 * res / 512
     c2w = syn.run_gan_c2w()
-    crop = tuple(int(round(v * a.res / 512)) for v in (100, 100, 412, 412))
+    crop = tuple(int(round(v * res / 512)) for v in (100, 100, 412, 412))
     eng = rc.engine(dev)
     gan.resize_operator(eng, crop[2] - crop[0], 224)              # one-time probe of the resize operator
     stats = {}
 
     def step():
         opt.zero_grad(set_to_none=True)
-        bones = gen(a.poses_per_gpu, dev)
-        frames, kps = gan.render_pose_images(rc, bones, rest, c2w, H, W, focal, chunk=a.chunk)
+        bones = gen(poses_per_gpu, dev)
+        frames, kps = gan.render_pose_images(rc, bones, rest_np, c2w, H, W, focal, chunk=chunk)
         x = torch.stack([gan.hmr_input(eng, f, crop=crop) for f in frames])
         pred = joints_from_rotmats(hmr(x), rest)
         tgt = kps.float()
@@ -147,32 +139,51 @@ def main():
         opt.step()
         stats["loss"], stats["gnorm"] = loss.detach(), gnorm.detach()
 
-    for _ in range(a.warmup):
+    for _ in range(warmup):
         step()
     torch.cuda.synchronize()
     if world > 1:
         torch.distributed.barrier()
+    l0 = eng.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(a.steps):
+    for _ in range(steps):
         step()
     e1.record()
     torch.cuda.synchronize()
-    ms = pdist.max_over_ranks(e0.elapsed_time(e1), dev) / a.steps
-    n_img = a.poses_per_gpu * world
+    eng.check_status()
+    ms = pdist.max_over_ranks(e0.elapsed_time(e1), dev) / steps
+    n_img = poses_per_gpu * world
     line = {"metric": "gan_steps_per_sec", "value": 1e3 / ms, "ms_per_step": ms, "n_gpus": world, "images_per_step": n_img,
-            "images_per_sec": n_img / ms * 1e3, "loss": float(stats["loss"]), "generator_grad_norm": float(stats["gnorm"]),
-            "config": f"{a.poses_per_gpu} poses/GPU, {a.res}x{a.res} bbox rays, frozen A-NeRF (bf16 tcgen05) forward + "
-                      f"masks-only dump, backward to skts over the rays the crop reads (chunk {a.chunk} rays), crop/resize 224, ResNet-50 HMR stand-in, MPJPE, Adam on the generator"}
-    if rank == 0:
-        print(json.dumps(line), flush=True)
-    if a.profile and rank == 0:
-        from torch.profiler import profile, ProfilerActivity
-        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+            "images_per_sec": n_img / ms * 1e3, "ms_per_image_per_gpu": ms / poses_per_gpu, "loss": float(stats["loss"]),
+            "generator_grad_norm": float(stats["gnorm"]), "gpu_launches_per_step_rank0": int((eng.launch_count - l0) // steps),
+            "config": f"{poses_per_gpu} poses/GPU, {res}x{res} bbox rays, frozen A-NeRF (bf16 tcgen05) forward + "
+                      f"masks-only dump, backward to skts over the rays the crop reads (chunk {chunk} rays), device FK forward/backward, "
+                      "crop/resize 224, ResNet-50 HMR stand-in, MPJPE, Adam on the generator, one all-reduce of the generator gradients"}
+    if profile and rank == 0:
+        from torch.profiler import profile as tprofile, ProfilerActivity
+        with tprofile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
             step()
             torch.cuda.synchronize()
-        with open(a.profile, "w") as f:
+        with open(profile, "w") as f:
             f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=50, max_name_column_width=70))
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=1)
+    ap.add_argument("--poses-per-gpu", type=int, default=2)
+    ap.add_argument("--res", type=int, default=512)
+    ap.add_argument("--chunk", type=int, default=16384)
+    ap.add_argument("--profile", default=None, help="write a torch.profiler kernel table of one step to this file")
+    a = ap.parse_args()
+    rank, world, local = pdist.env_rank_world()
+    pdist.init_process_group("nccl" if world > 1 else None)
+    line = run(rank, world, local, a.steps, a.warmup, a.poses_per_gpu, a.res, a.chunk, a.profile)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
 

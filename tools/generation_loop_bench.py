@@ -21,7 +21,52 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from posegen_b200 import dist as pdist, synthetic as syn                         # noqa: E402
 from posegen_b200.raycaster import raycaster_from_checkpoint                     # noqa: E402
-from posegen_b200.render import render_path                                      # noqa: E402
+from posegen_b200.render import render_pose_batch                                # noqa: E402
+
+
+def run(rank, world, local, poses=256, res=512):
+    """One leg (process group already initialised for world > 1): returns the result dict on every rank."""
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    rc = raycaster_from_checkpoint(syn.synthetic_raycaster_state(0, alpha_gain=400.), device=dev, precision="bf16")
+    rc.eval()
+    eng = rc.engine(dev)
+    mine = pdist.shard_indices(poses, rank, world)
+    bones = np.stack([syn.synthetic_pose(s).bones for s in mine]).astype(np.float32)
+    rest = (syn.SMPL_REST_POSE * syn.BODY_SCALE).astype(np.float32)
+    c2w = syn.run_gan_c2w()
+    focal = 1000.0 * res / 512
+    crop = tuple(int(round(v * res / 512)) for v in (100, 100, 412, 412))
+
+    def go(bones_np):
+        b = torch.as_tensor(bones_np, device=dev)
+        rgbs, hmr, n_rays = render_pose_batch(rc, b, rest, c2w, (res, res, focal), crop=crop)
+        return rgbs, hmr, n_rays
+
+    go(bones[:2])                                                      # warm-up
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    l0 = eng.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    rgbs, hmr, n_rays = go(bones)
+    frames_u8 = (rgbs.clamp(0, 1) * 255).to(torch.uint8)               # what the reference writes to PNG (run_nerf.py to8b)
+    all_frames = pdist.gather_frames(frames_u8, poses, rank, world)
+    e1.record()
+    torch.cuda.synchronize()
+    eng.check_status()
+    ms = pdist.max_over_ranks(e0.elapsed_time(e1), dev)
+    tot = torch.tensor([float(n_rays)], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(tot)
+    assert all_frames.shape[0] == poses
+    return {"metric": "frames_per_sec_512", "value": poses / ms * 1e3, "unit": "frames/s", "n_gpus": world,
+            "poses": poses, "seconds": ms * 1e-3, "rays_per_sec": float(tot[0]) / ms * 1e3,
+            "hmr_inputs": list(hmr.shape), "finite": bool(torch.isfinite(hmr).all()), "gpu_launches_rank0": int(eng.launch_count - l0),
+            "config": f"{poses} synthetic poses x {res}x{res} bbox renders sharded pose_idx % {world}; device FK + cylinder + bbox, "
+                      "device rays, ONE fused bf16 render launch per pose batch (pose_idx form), white-bg frames, HMR input 224; "
+                      "one final all_gather of the uint8 frames"}
 
 
 def main():
@@ -31,51 +76,9 @@ def main():
     a = ap.parse_args()
     rank, world, local = pdist.env_rank_world()
     pdist.init_process_group("nccl" if world > 1 else None)
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    rc = raycaster_from_checkpoint(syn.synthetic_raycaster_state(0, alpha_gain=400.), device=dev, precision="bf16")
-    rc.eval()
-    eng = rc.engine(dev)
-    mine = pdist.shard_indices(a.poses, rank, world)
-    bones = np.stack([syn.synthetic_pose(s).bones for s in mine]).astype(np.float32)
-    rest = (syn.SMPL_REST_POSE * syn.BODY_SCALE).astype(np.float32)
-    c2w = syn.run_gan_c2w()
-    focal = 1000.0 * a.res / 512
-    crop = tuple(int(round(v * a.res / 512)) for v in (100, 100, 412, 412))
-    kwargs = {"ray_caster": rc}
-
-    def run(bones_np):
-        b = torch.as_tensor(bones_np, device=dev)
-        skts, kps, cyls = eng.pose_to_skts(b, rest)
-        poses = np.repeat(c2w[None], len(bones_np), 0)
-        rgbs, _, _, valid, _ = render_path(poses, (a.res, a.res, focal), 4096, kwargs, kp=kps, skts=skts, cyls=cyls,
-                                           white_bkgd=True, to_numpy=False)
-        hmr = torch.stack([eng.frame_to_hmr_input(f, crop=crop) for f in rgbs])
-        return rgbs, hmr, sum(len(v) for v in valid)
-
-    run(bones[:2])                                                     # warm-up
-    torch.cuda.synchronize()
-    if world > 1:
-        torch.distributed.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    rgbs, hmr, n_rays = run(bones)
-    frames_u8 = (rgbs.clamp(0, 1) * 255).to(torch.uint8)               # what the reference writes to PNG (run_nerf.py to8b)
-    all_frames = pdist.gather_frames(frames_u8, a.poses, rank, world)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = pdist.max_over_ranks(e0.elapsed_time(e1), dev)
-    tot = torch.tensor([float(n_rays)], dtype=torch.float64, device=dev)
-    if world > 1:
-        torch.distributed.all_reduce(tot)
+    line = run(rank, world, local, a.poses, a.res)
     if rank == 0:
-        assert all_frames.shape[0] == a.poses
-        print(json.dumps({"metric": "frames_per_sec_512", "value": a.poses / ms * 1e3, "unit": "frames/s", "n_gpus": world,
-                          "poses": a.poses, "seconds": ms * 1e-3, "rays_per_sec": float(tot[0]) / ms * 1e3,
-                          "hmr_inputs": list(hmr.shape), "finite": bool(torch.isfinite(hmr).all()),
-                          "config": f"{a.poses} synthetic poses x {a.res}x{a.res} bbox renders sharded pose_idx % {world}; device FK, "
-                                    "device rays, fused bf16 render, white-bg frame, HMR input 224; one final all_gather of the uint8 frames"}),
-              flush=True)
+        print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
 
