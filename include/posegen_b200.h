@@ -258,6 +258,28 @@ PGN_API int  pgn_mlp_delta_chain(pgn_context* ctx, const void* dG, const float* 
 PGN_API int  pgn_mlp_delta_chain_net(pgn_context* ctx, int32_t net_id, const void* dG, const float* d_raw, const void* mask,
                                      int64_t mask_rows, int64_t m, void* dz, float* colsum, uint32_t layer_mask, void* stream);
 
+/* The weight gradients of one NeRF MLP (what autograd computes as dW_l = dZ_l^T h_{l-1} for every nn.Linear of
+ * core/networks/nerf.py:94-148) as ONE split-K tcgen05 kernel over all samples of the pass - no library GEMM:
+ *   dz   bf16 [8][m][256]   the trunk deltas written by pgn_mlp_delta_chain (all eight layers)
+ *   dG   bf16 [m][128]      the view layer's delta (pgn_mlp_delta)
+ *   act  the pass's activation dump of pgn_render_forward_train (dump_rows = pgn_activation_dump_bytes / 4608)
+ *   enc  bf16 [m][1080]     the network input (pgn_encode_bf16)
+ *   d_raw fp32 [m][4] (column 3 = d_sigma), bias_v fp32 [128] = column sums of dG (pgn_mlp_delta's colsum)
+ * Outputs: flat fp32 [pgn_weight_grad_floats()] = the 12 weight gradients back to back in the pgn_net_weights order and
+ * nn.Linear layouts ([out,in] row-major; slot 11, rgb_linear.weight, is left zero: pgn_mlp_delta produces it), and
+ * feat_bias fp32 [256] = feature_linear.bias' gradient.  feature_linear has no activation, so its gradients and the
+ * feature block of views_linears.0 are formed from T = dG^T h7 [128,256] with the uploaded weights of `net_id`. */
+PGN_API size_t pgn_weight_grad_floats(void);
+PGN_API int  pgn_mlp_weight_grads(pgn_context* ctx, int32_t net_id, const void* dz, const void* dG, const void* act, int64_t dump_rows,
+                                  const void* enc, int64_t m, const float* d_raw, const float* bias_v, float* flat,
+                                  float* feat_bias, void* stream);
+
+/* the split-K kernel on one explicit product, for unit tests: out[Ma, Nb] (fp32, row stride ld_out) += A[m, :Ma]^T B[m, :Nb],
+ * A / B bf16 row-major with row strides lda / ldb (elements), Ma in {128, 256}, Nb a multiple of 8 <= 256, n_ctas CTAs
+ * share the rows (split-K; out must be zero-initialised by the caller). */
+PGN_API int  pgn_debug_wgrad(pgn_context* ctx, const void* A, int32_t lda, int32_t Ma, const void* B, int32_t ldb, int32_t Nb,
+                             int64_t m, float* out, int32_t ld_out, int32_t n_ctas, void* stream);
+
 /* NeRF.forward (core/networks/nerf.py:133-148) on explicit encodings:
  * enc [m,1080] -> raw [m,4].  precision selects the MLP engine. */
 PGN_API int  pgn_mlp(pgn_context* ctx, int net_id, const float* enc, int64_t m, float* raw,

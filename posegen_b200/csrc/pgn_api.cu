@@ -74,6 +74,7 @@ struct pgn_context {
   bool fp32_stale[2] = {false, false};   // fp32-tier transposes pending since the last pgn_upload_weights
   unsigned long long* d_prof;   // optional phase timers [num_sms][32]
   bool prof_on;
+  float* d_tm = nullptr;    // T = dG^T h7 [128,256] scratch of pgn_mlp_weight_grads
   float* d_c2w;
   float* d_rest;            // rest pose [24,3] of the last pgn_pose_to_skts call
   int64_t launches;
@@ -116,6 +117,7 @@ int pgn_create(const pgn_config* cfg, pgn_context** out) {
   PGN_CUDA(cudaMalloc(&c->d_c2w, 12 * sizeof(float)));
   PGN_CUDA(cudaMalloc(&c->d_rest, PGN_J * 3 * sizeof(float)));
   PGN_CUDA(cudaMalloc(&c->d_fold, (128 * 256 + 128) * sizeof(float)));
+  PGN_CUDA(cudaMalloc(&c->d_tm, 128 * 256 * sizeof(float)));
   for (int n = 0; n < 2; ++n) PGN_CUDA(cudaMalloc(&c->d_chain_w[n], (size_t)120 * 4096 * sizeof(__nv_bfloat16)));
   for (int n = 0; n < 2; ++n) {
     PGN_CUDA(cudaMalloc(&c->d_w[n], weight_floats() * sizeof(float)));
@@ -150,7 +152,7 @@ int pgn_create(const pgn_config* cfg, pgn_context** out) {
 void pgn_destroy(pgn_context* c) {
   if (!c) return;
   DeviceGuard _guard(c->cfg.device);
-  cudaFree(c->d_sc); cudaFree(c->d_status); cudaFree(c->d_c2w); cudaFree(c->d_rest); cudaFree(c->d_fold); cudaFree(c->d_chain_w[0]); cudaFree(c->d_chain_w[1]);
+  cudaFree(c->d_sc); cudaFree(c->d_status); cudaFree(c->d_c2w); cudaFree(c->d_rest); cudaFree(c->d_fold); cudaFree(c->d_tm); cudaFree(c->d_chain_w[0]); cudaFree(c->d_chain_w[1]);
   for (int n = 0; n < 2; ++n) {
     cudaFree(c->d_w[n]); cudaFree(c->d_b[n]); cudaFree(c->d_wt[n]); cudaFree(c->d_wstream[n]); cudaFree(c->d_bf16_aux[n]);
   }
@@ -403,6 +405,31 @@ int pgn_mlp_delta_chain_net(pgn_context* c, int32_t net_id, const void* dG, cons
   if (!c || net_id < 0 || net_id > 1) return fail(PGN_E_INVALID, "pgn_mlp_delta_chain_net: bad argument");
   if (!c->have_w[net_id]) return fail(PGN_E_STATE, "pgn_mlp_delta_chain_net: weights not uploaded");
   return pgn_mlp_delta_chain(c, dG, d_raw, mask, mask_rows, m, c->d_chain_w[net_id], c->w_ptr[net_id][8], dz, colsum, layer_mask, stream);
+}
+
+size_t pgn_weight_grad_floats(void) { return pgn_wgrad_flat_floats(); }
+
+int pgn_mlp_weight_grads(pgn_context* c, int32_t net_id, const void* dz, const void* dG, const void* act, int64_t dump_rows,
+                         const void* enc, int64_t m, const float* d_raw, const float* bias_v, float* flat, float* feat_bias,
+                         void* stream) {
+  if (!c || net_id < 0 || net_id > 1 || !dz || !dG || !act || !enc || !d_raw || !bias_v || !flat || !feat_bias || m < 0 || dump_rows < m)
+    return fail(PGN_E_INVALID, "pgn_mlp_weight_grads: bad argument");
+  if (!c->have_w[net_id]) return fail(PGN_E_STATE, "pgn_mlp_weight_grads: weights not uploaded");
+  PGN_ON_DEVICE(c);
+  PGN_CUDA(pgn_launch_weight_grads(dz, dG, act, dump_rows, enc, m, d_raw, bias_v, c->w_ptr[net_id][9], c->b_ptr[net_id][9],
+                                   c->w_ptr[net_id][10], flat, feat_bias, c->d_tm, c->d_status, c->num_sms, (cudaStream_t)stream));
+  c->launches += 3;
+  return PGN_OK;
+}
+
+int pgn_debug_wgrad(pgn_context* c, const void* A, int32_t lda, int32_t Ma, const void* B, int32_t ldb, int32_t Nb, int64_t m,
+                    float* out, int32_t ld_out, int32_t n_ctas, void* stream) {
+  if (!c || !A || !B || !out || (Ma != 128 && Ma != 256) || Nb <= 0 || Nb > 256 || Nb % 8 || lda % 8 || ldb % 8 || ld_out % 4 || m < 0 || n_ctas <= 0)
+    return fail(PGN_E_INVALID, "pgn_debug_wgrad: bad argument");
+  PGN_ON_DEVICE(c);
+  PGN_CUDA(pgn_launch_wgrad_single(A, lda, Ma, B, ldb, Nb, m, out, ld_out, n_ctas, c->d_status, (cudaStream_t)stream));
+  c->launches++;
+  return PGN_OK;
 }
 
 int pgn_mlp(pgn_context* c, int net_id, const float* enc, int64_t m, float* raw, int32_t precision, void* stream) {

@@ -120,6 +120,15 @@ cudaError_t pgn_launch_pose_fk_backward(const float* bones, const float* rest, i
 cudaError_t pgn_launch_near_far_chunks(const PgnRayRefs& rays, const long long* chunk_starts, long long n_chunks, float* near_far,
                                        cudaStream_t stream);
 
+// ---- split-K tcgen05 weight gradients (pgn_wgrad.cu) ----
+size_t pgn_wgrad_flat_floats();
+cudaError_t pgn_launch_weight_grads(const void* dz, const void* dG, const void* act, long long dump_rows, const void* enc,
+                                    long long m, const float* d_raw, const float* bias_v, const float* w_f, const float* b_f,
+                                    const float* w_v, float* flat, float* feat_bias, float* tm_scratch, int* status, int num_sms,
+                                    cudaStream_t stream);
+cudaError_t pgn_launch_wgrad_single(const void* A, int lda, int Ma, const void* B, int ldb, int Nb, long long m, float* out, int ld_out,
+                                    int n_ctas, int* status, cudaStream_t stream);
+
 // bring-up probe (pgn_probe.cu)
 cudaError_t pgn_launch_probe_umma(const float* A, const float* B, float* D, int K, int N, int variant, int* status,
                                   cudaStream_t stream);

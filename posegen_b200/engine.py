@@ -376,6 +376,40 @@ class Engine:
                                                         _ptr(dz), _ptr(colsum), int(layer_mask), self._stream()))
         return dz, colsum
 
+    def mlp_weight_grads(self, net_id, dz, dG, acts, enc, d_raw, bias_v):
+        """pgn_mlp_weight_grads: every weight gradient of one NeRF MLP as one split-K tcgen05 kernel (+ two small fold
+        kernels).  dz bf16 [8,m,256], dG bf16 [m,128], acts = the pass's activation dump (flat bf16), enc bf16 [m,1080],
+        d_raw fp32 [m,4], bias_v fp32 [128].  Returns ({'<layer>.weight': fp32 view}, feature_linear.bias grad [256]); the
+        views share one flat buffer in the C ABI's layer order (rgb_linear.weight is left zero: `mlp_delta` produces it)."""
+        m = dG.shape[0]
+        for t, shape, dt in ((dz, (8, m, 256), torch.bfloat16), (dG, (m, 128), torch.bfloat16), (enc, (m, 1080), torch.bfloat16),
+                             (d_raw, (m, 4), torch.float32), (bias_v, (128,), torch.float32)):
+            if tuple(t.shape) != shape or t.dtype != dt or not t.is_contiguous() or not t.is_cuda:
+                raise ValueError(f"mlp_weight_grads: expected a contiguous CUDA {dt} tensor of shape {shape}, got {tuple(t.shape)} {t.dtype}")
+        if acts.dtype != torch.bfloat16 or not acts.is_contiguous():
+            raise ValueError("acts must be the flat bf16 activation dump")
+        rows = acts.numel() // 2304
+        n = int(self.lib.pgn_weight_grad_floats())
+        flat = torch.empty((n,), dtype=torch.float32, device=dG.device)
+        fb = torch.empty((256,), dtype=torch.float32, device=dG.device)
+        _lib.check(self.lib.pgn_mlp_weight_grads(self.handle, int(net_id), _ptr(dz), _ptr(dG), _ptr(acts), rows, _ptr(enc), m,
+                                                 _ptr(d_raw), _ptr(bias_v), _ptr(flat), _ptr(fb), self._stream()))
+        out, o = {}, 0
+        for name in LINEAR_ORDER:
+            sh = _SHAPES[name]
+            out[f"{name}.weight"] = flat[o:o + sh[0] * sh[1]].view(sh)
+            o += sh[0] * sh[1]
+        return out, fb
+
+    def debug_wgrad(self, A, B, Ma, Nb, n_ctas=8, out=None):
+        """pgn_debug_wgrad: out[Ma, Nb] += A[:, :Ma]^T B[:, :Nb] (bf16 row-major operands, fp32 result) through the split-K kernel."""
+        m = A.shape[0]
+        if out is None:
+            out = torch.zeros((Ma, Nb), dtype=torch.float32, device=A.device)
+        _lib.check(self.lib.pgn_debug_wgrad(self.handle, _ptr(A), A.stride(0), Ma, _ptr(B), B.stride(0), Nb, m, _ptr(out), out.stride(0),
+                                            int(n_ctas), self._stream()))
+        return out
+
     def mlp(self, net_id, enc, precision="bf16"):
         _check_f32_cuda(enc, "enc")
         enc2 = enc.reshape(-1, 1080).contiguous()

@@ -30,6 +30,7 @@ from .raycaster import net_tensors
 
 S, T = 64, 80
 USE_DELTA_CHAIN = True        # trunk backward through pgn_mlp_delta_chain (False: layer by layer, for A/B runs)
+USE_WGRAD_KERNEL = True       # weight gradients through pgn_mlp_weight_grads (False: torch.mm, for A/B runs)
 PARAM_ORDER = [f"pts_linears.{i}.{k}" for i in range(8) for k in ("weight", "bias")] + \
     [f"{m}.{k}" for m in ("alpha_linear", "feature_linear", "views_linears.0", "rgb_linear") for k in ("weight", "bias")]
 
@@ -74,7 +75,8 @@ def chain_wstream(P: Dict[str, torch.Tensor]) -> torch.Tensor:
 
 def mlp_backward(params: Dict[str, torch.Tensor], enc: torch.Tensor, acts: torch.Tensor, d_raw: torch.Tensor,
                  fuse: Callable, want_input_grad: bool = False, want_weight_grad: bool = True,
-                 chain: Callable | None = None, mask_dump=None, view_delta: Callable | None = None) -> Dict[str, torch.Tensor]:
+                 chain: Callable | None = None, mask_dump=None, view_delta: Callable | None = None,
+                 wgrad: Callable | None = None) -> Dict[str, torch.Tensor]:
     """Weight gradients of one NeRF MLP (core/networks/nerf.py:94-148).
 
     params: fp32 nn.Linear tensors; enc [m,1080] bf16 network input (`pgn_encode_bf16`; may be None when
@@ -89,6 +91,9 @@ def mlp_backward(params: Dict[str, torch.Tensor], enc: torch.Tensor, acts: torch
     (`pgn_mlp_delta_chain_net`; the library packs the chain's weight stream when the weights are uploaded): the
     whole trunk chain dG -> dZ_7 .. dZ_0 (+ bias gradients) as one tcgen05 kernel; without it the chain runs layer by
     layer (a cuBLAS GEMM and a `fuse` pass per layer), which is also what the host-logic test exercises.
+    `wgrad(dz, dG, acts, enc, d_raw, bias_v)` is `Engine.mlp_weight_grads` bound to this net (`pgn_mlp_weight_grads`):
+    with it (and `chain`) every weight gradient is formed by the library's split-K tcgen05 kernel and no library GEMM
+    runs in the step; without it the products below go through `torch.mm` (the CPU host-logic test, A/B runs).
     mask_dump = (trunk_mask int32 [8,m,8], view_mask int32 [m,4]) with `view_delta` = `Engine.view_delta_from_mask`
     replaces `acts` for a frozen network (want_weight_grad False, `chain` required): the masks-only dump of
     `pgn_render_forward_masks` is all the input-gradient chain reads.
@@ -117,9 +122,11 @@ def mlp_backward(params: Dict[str, torch.Tensor], enc: torch.Tensor, acts: torch
         bias_v, g_rgb = fuse(dG, G, d_raw[:, :3], P["rgb_linear.weight"], False, wg)
     W_v, W_f, b_f = P["views_linears.0.weight"], P["feature_linear.weight"], P["feature_linear.bias"]
     W_vf = W_v[:, :256]
+    fused_w = wg and wgrad is not None and chain is not None
     if wg:
         g["rgb_linear.weight"] = g_rgb
         g["rgb_linear.bias"] = d_raw[:, :3].sum(0)
+    if wg and not fused_w:
         dGt = dG.t()
         Tm = _mm32(dGt, H[7])                                                # [128,256] = dG^T h7
         g["views_linears.0.weight"] = torch.cat([Tm @ W_f.t() + bias_v[:, None] * b_f[None, :], _mm32(dGt, d_emb)], 1)
@@ -132,7 +139,17 @@ def mlp_backward(params: Dict[str, torch.Tensor], enc: torch.Tensor, acts: torch
         # trunk: one fused kernel for the eight deltas; the weight gradients are GEMMs over (dZ_l, h_{l-1})
         mask, mask_rows = (mask_dump[0], m) if mask_dump is not None else act_masks(acts)
         dz, colsum = chain(dG, d_raw, mask, mask_rows, 0xFF if wg else 0x21)   # a frozen network's pose gradient reads only dZ_0, dZ_5
-        if wg:
+        if fused_w:
+            gw, feat_b = wgrad(dz, dG, acts, enc, d_raw, bias_v)
+            for k, v in gw.items():
+                if k != "rgb_linear.weight":
+                    g[k] = v
+            g["views_linears.0.bias"] = bias_v
+            g["feature_linear.bias"] = feat_b
+            g["alpha_linear.bias"] = d_raw[:, 3:4].sum(0)
+            for l in range(8):
+                g[f"pts_linears.{l}.bias"] = colsum[l]
+        elif wg:
             g["alpha_linear.weight"] = _mm32(d_raw[:, 3:4].to(bf).t(), H[7])
             g["alpha_linear.bias"] = d_raw[:, 3:4].sum(0)
             for l in range(8):
@@ -216,7 +233,8 @@ class _RenderTrainFn(torch.autograd.Function):
             pd = net_tensors(net)
             net_id = 0 if net is rc.network else 1
             gd = mlp_backward(pd, enc, acts, d_raw.reshape(-1, 4), eng.mlp_delta, want_input_grad=want_sk, want_weight_grad=want_w,
-                              chain=functools.partial(eng.mlp_delta_chain_net, net_id) if USE_DELTA_CHAIN else None)
+                              chain=functools.partial(eng.mlp_delta_chain_net, net_id) if USE_DELTA_CHAIN else None,
+                              wgrad=functools.partial(eng.mlp_weight_grads, net_id) if (USE_DELTA_CHAIN and USE_WGRAD_KERNEL) else None)
             grads += [gd[k].reshape(pd[k].shape).to(pd[k].dtype) for k in PARAM_ORDER] if want_w else [None] * len(PARAM_ORDER)
             if want_sk:          # pose gradient: dL/d(network input) -> dL/d skts (per ray), both passes add up
                 d = eng.encode_backward_bf16(rb, sk, cy, z, gd["_g_xp"], gd["_g_d"])

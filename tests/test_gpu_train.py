@@ -395,3 +395,56 @@ def test_graph_replay_survives_a_larger_eager_render(engine, train_case):
         out[disturb] = losses
     assert np.isfinite(out[True]).all()
     assert np.allclose(out[True], out[False], rtol=2e-3, atol=1e-5), out
+
+
+@pytest.mark.parametrize("m,Ma,Nb,n_ctas", [(4096, 256, 256, 7), (1000, 256, 176, 3), (4097, 128, 136, 148), (33, 128, 256, 5), (20000, 256, 256, 148)])
+def test_wgrad_split_k_kernel_matches_torch(engine, m, Ma, Nb, n_ctas):
+    """pgn_debug_wgrad: out[Ma,Nb] = A[:, :Ma]^T B[:, :Nb] over all rows, bf16 operands (strided row-major views, as the
+    activation dump / the [m,1080] network input are), fp32 accumulation in TMEM, split-K over n_ctas CTAs."""
+    g = torch.Generator(device="cuda").manual_seed(m + Ma + Nb)
+    A_full = (torch.randn((m, 256), device="cuda", generator=g) * 0.5).to(torch.bfloat16)
+    B_full = (torch.randn((m, 1080), device="cuda", generator=g) * 0.5).to(torch.bfloat16)
+    A = A_full[:, :Ma]
+    B = B_full[:, 432:432 + Nb]
+    got = engine.debug_wgrad(A, B, Ma, Nb, n_ctas=n_ctas)
+    torch.cuda.synchronize()
+    engine.check_status()
+    want = A.double().t() @ B.double()
+    err = float((got.double() - want).abs().max())
+    scale = float(want.abs().max())
+    assert err <= 2e-4 * max(1.0, scale) + 1e-3 * (m ** 0.5) * 1e-3, (err, scale)
+    # accumulates into `out` (split-K partials are added): a second call doubles the result
+    got2 = engine.debug_wgrad(A, B, Ma, Nb, n_ctas=n_ctas, out=got.clone())
+    assert float((got2.double() - 2 * want).abs().max()) <= 4e-4 * max(1.0, scale) + 2e-6 * m ** 0.5
+
+
+def test_fused_weight_gradients_match_the_gemm_formulation(engine, train_case):
+    """pgn_mlp_weight_grads (split-K tcgen05 + the feature/view fold + the alpha head) against the same gradients formed
+    by plain matrix products (posegen_b200.train.mlp_backward without the kernel) on the same deltas."""
+    import posegen_b200.train as tr
+    frame, ckpt, rb, tgt = train_case
+    n, dev = 1024, torch.device("cuda")
+    rbt = torch.as_tensor(rb[:n], device=dev)
+    sk = torch.as_tensor(frame.pose.skts, device=dev)
+    cy = torch.as_tensor(frame.pose.cyl, device=dev)
+    t = torch.as_tensor(tgt[:n], device=dev)
+    grads = {}
+    for use in (True, False):
+        tr.USE_WGRAD_KERNEL = use
+        try:
+            rc = raycaster_from_checkpoint(ckpt, device="cuda", precision="bf16")
+            rc.train()
+            ret = rc(rbt, N_samples=64, N_importance=16, kp_batch=None, skts=sk, cyls=cy, bones=None, cams=None, perturb=0., raw_noise_std=0.)
+            loss = ((ret["rgb_map"] + (1 - ret["acc_map"][:, None]) - t) ** 2).mean() + ((ret["rgb0"] + (1 - ret["acc0"][:, None]) - t) ** 2).mean()
+            loss.backward()
+            torch.cuda.synchronize()
+            rc.engine(dev).check_status()
+            grads[use] = {(i, k): p.grad.detach().double().clone() for i, net in enumerate((rc.network, rc.network_fine)) for k, p in net.named_parameters()}
+        finally:
+            tr.USE_WGRAD_KERNEL = True
+    for key, ref in grads[False].items():
+        got = grads[True][key]
+        assert got.shape == ref.shape and torch.isfinite(got).all(), key
+        if float(ref.norm()) > 1e-9:
+            rel = float((got - ref).norm() / ref.norm())
+            assert rel <= 5e-3, (key, rel)           # same bf16 operands, fp32 accumulation in a different order
