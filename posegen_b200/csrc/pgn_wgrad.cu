@@ -4,27 +4,31 @@
 // whose contraction runs over ALL samples of the batch (2-2.5 x 10^5 rows per pass).  Both operands already sit in HBM
 // as row-major bf16 matrices with the contraction dimension (rows) outermost: the deltas dZ_l [rows,256] written by
 // pgn_delta_chain, the activations h_l [rows,256] dumped by the training forward, the regenerated network input
-// [rows,1080].  In UMMA terms both are "MN-major" operands (8 consecutive M/N elements = 16 contiguous bytes, K strided),
-// so no transpose is ever materialised:
+// [rows,1080].  In UMMA terms both are "MN-major" operands (M/N contiguous, K strided), so no transpose is ever
+// materialised:
 //
-//   * a stage is 32 rows of A (<= 256 columns) and of B (<= 256 columns), staged with 16-byte cp.async into the
-//     SWIZZLE_NONE MN-major canonical image [column / 8][row][8] (core matrix = 8 rows x 16 B contiguous; LBO = 128 B to
-//     the next 8 rows, SBO = 512 B to the next 8 columns).  A warp copy covers 8 rows x 4 column chunks: 64-byte
-//     global segments (whole sectors) and four conflict-free 128-byte shared-memory wavefronts.
+//   * a stage is 32 rows of A (<= 256 columns) and of B (<= 256 columns), moved by the TMA engine as boxes of
+//     64 columns x 32 rows (cp.async.bulk.tensor.3d, SWIZZLE_128B; SASS UTMALDG): a box lands as 32 rows of 128 bytes
+//     with the 16-byte chunks XOR-swizzled by the row - exactly the canonical MN-major SWIZZLE_128B UMMA operand
+//     (LBO = 4 KB to the next 64 columns, SBO = 1 KB to the next 8 rows).  One elected thread issues up to 8 boxes per
+//     stage; out-of-range rows / columns are zero-filled by the tensor map.  (A first version staged the operands with
+//     per-thread 16-byte cp.async into the SWIZZLE_NONE image: correct, but the L1's outstanding-request tracking capped
+//     it at ~12 B/clk/SM, 2.5 TB/s over the chip; bulk tensor copies do not go through it.)
 //   * one elected thread issues tcgen05.mma kind::f16 (M = 128, N <= 256, K = 16) with a_major = b_major = MN:
 //     per stage 2 K-steps x (1 or 2) M-halves, fp32 accumulators in TMEM (2 x 256 columns = a 256 x 256 output tile).
 //   * split-K: the units (one output tile each: an (A matrix, B column range) pair) get a number of CTAs proportional
 //     to the bytes they stream; CTA k of a unit takes stages k, k + n, k + 2n, ... so that every unit sweeps the rows at
 //     the same rate and operands shared by several units (dZ_5, dG, x_p are each read by 2-4 units) come from the 126 MB
-//     L2 instead of HBM a second time.  At the end every CTA adds its partial tile to the fp32 gradient with
-//     red.global.add.v4.f32 (the gradient buffer is zeroed by the launch wrapper).
+//     L2 instead of HBM a second time (ncu: DRAM bytes = the algorithmic bytes).  At the end every CTA adds its partial
+//     tile to the fp32 gradient with red.global.add.v4.f32 (the gradient buffer is zeroed by the launch wrapper).
 //
 // Roofline: HBM-bound.  Algorithmic bytes per row and pass = 8 x 512 (dZ) + 256 (dG) + 8 x 512 (h) + 2,160 (input)
-// = 10.6 KB against 1.72 MFLOP (162 FLOP/B; the machine balance is ~210), i.e. ~0.37 ms per 245,760-row pass at the
+// = 10.6 KB against 1.72 MFLOP (162 FLOP/B; the machine balance is ~210), i.e. ~0.40 ms per 245,760-row pass at the
 // measured 6.5 TB/s; the tensor pipe is <= 45 % busy by construction.
 //
-// Roles (192 threads): warps 0-3 = cp.async loaders, then the TMEM -> red.add epilogue; warp 4 = MMA issuer (one lane);
-// warp 5 owns the TMEM allocation.  6 stages x 32 KB in flight per SM.
+// Roles (192 threads): warp 0 = TMA producer (one lane) + TMEM allocation, warp 1 = MMA issuer (one lane), warps 2-5 =
+// TMEM -> red.add epilogue.  6 stages x 32 KB in flight per SM.
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include "pgn_common.cuh"
 #include "pgn_kernels.h"
@@ -36,25 +40,28 @@ namespace {
 
 constexpr int kRows = 32;                      // rows (K of the GEMM) per stage
 constexpr int kStages = 6;
-constexpr int kOpBytes = 32 * kRows * 16;      // one operand of a stage: [32 column chunks][32 rows][16 B] = 16 KB
+constexpr int kBoxCols = 64;                   // 128 bytes of bf16: the SWIZZLE_128B span
+constexpr int kBoxBytes = kRows * 128;         // one TMA box: 32 rows x 128 B = 4 KB
+constexpr int kOpBytes = 4 * kBoxBytes;        // one operand of a stage: up to 4 boxes (256 columns) = 16 KB
 constexpr int kThreads = 192;
-constexpr int kLoaders = 128;
 constexpr int kMaxUnits = 16;
+constexpr int kMaxMaps = 4;
 
 struct Unit {
-  const __nv_bfloat16* A;    // [rows, lda] row-major, Ma columns used from column 0
-  const __nv_bfloat16* B;    // [rows, ldb] row-major, Nb columns used from column 0 of this pointer
-  float* out;                // fp32 [Ma, ld_out] tile origin (row = A column, column = B column)
-  int lda, ldb, ld_out;
-  int Ma;                    // 128 | 256
-  int Nb;                    // valid B columns (multiple of 8)
-  int Nmma;                  // UMMA N: Nb rounded up to 16 (the extra columns are zero-filled, never stored)
-  int cta0, ncta;            // CTAs [cta0, cta0 + ncta) work on this unit
+  int a_map, a_layer, a_col;   // A operand: tensor map, its third coordinate (layer), first column
+  int b_map, b_layer, b_col;   // B operand
+  float* out;                  // fp32 [Ma, ld_out] tile origin (row = A column, column = B column)
+  int ld_out;
+  int Ma;                      // 128 | 256
+  int Nb;                      // valid B columns (multiple of 8)
+  int Nmma;                    // UMMA N: Nb rounded up to 16 (columns beyond Nb are never stored)
+  int cta0, ncta;              // CTAs [cta0, cta0 + ncta) work on this unit
 };
-struct Params {
+struct __align__(64) Params {
+  CUtensorMap maps[kMaxMaps];  // [layer][row][column] bf16 views of the operands, box = 64 columns x 32 rows
   Unit u[kMaxUnits];
   int n_units;
-  long long m;               // rows
+  long long m;                 // rows
 };
 
 struct __align__(1024) Smem {
@@ -64,17 +71,16 @@ struct __align__(1024) Smem {
   uint32_t tmem_slot;
 };
 
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
-  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(bar) : "memory");
-}
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
-// MN-major SWIZZLE_NONE descriptor of this kernel's stage image: LBO = 128 B (next 8 rows = K), SBO = 512 B (next 8 columns)
-__device__ __forceinline__ uint64_t mn_desc(uint32_t saddr) { return umma_smem_desc(saddr, 128, kRows * 16); }
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n"
+               ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+// MN-major SWIZZLE_128B descriptor of a stage operand: LBO = 4 KB (next 64 columns = next box), SBO = 1 KB (next 8 rows),
+// layout type 2 (SWIZZLE_128B) in bits [61,64)
+__device__ __forceinline__ uint64_t mn_desc(uint32_t saddr) { return umma_smem_desc(saddr, kBoxBytes, 1024) | (2ull << 61); }
 
 __global__ void __launch_bounds__(kThreads, 1) pgn_wgrad_kernel(const __grid_constant__ Params p, int* __restrict__ status_g) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -87,94 +93,94 @@ __global__ void __launch_bounds__(kThreads, 1) pgn_wgrad_kernel(const __grid_con
   const Unit& u = p.u[ui];
   const bool active = (int)blockIdx.x >= u.cta0 && (int)blockIdx.x < u.cta0 + u.ncta;
   const int k = (int)blockIdx.x - u.cta0;
+  const int ncta = u.ncta, Ma = u.Ma, Nb = u.Nb, Nmma = u.Nmma;
   const long long n_stages_total = (p.m + kRows - 1) / kRows;
-  const long long n_mine = (active && n_stages_total > k) ? (n_stages_total - k + u.ncta - 1) / u.ncta : 0;
+  const long long n_mine = (active && n_stages_total > k) ? (n_stages_total - k + ncta - 1) / ncta : 0;
 
   if (tid == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(&sm.full[s], kLoaders); mbar_init(&sm.empty[s], 1); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
     mbar_init(&sm.acc_full, 1);
     fence_mbar_init();
   }
-  if (warp == 5) { tmem_alloc(&sm.tmem_slot, 512); tmem_relinquish(); }
+  if (warp == 0) { tmem_alloc(&sm.tmem_slot, 512); tmem_relinquish(); }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = sm.tmem_slot;
-  const int halves = u.Ma / 128;
+  const int halves = Ma / 128;
+  const uint32_t full0 = smem_u32(&sm.full[0]), empty0 = smem_u32(&sm.empty[0]);
+  const uint32_t a_s0 = smem_u32(sm.a[0]), b_s0 = smem_u32(sm.b[0]);
 
-  if (warp < 4) {
-    // ------------------------------------------------------------ loaders: warp w owns rows 8w .. 8w+7 of every stage
-    const int r = warp * 8 + (lane & 7), c4 = lane >> 3;
-    const int a_groups = u.Ma / 32, b_groups = (u.Nmma + 31) / 32;
-    for (long long it = 0; it < n_mine; ++it) {
-      const int s = (int)(it % kStages);
-      const uint32_t use = (uint32_t)(it / kStages);
-      if (use > 0 && !mbar_wait(&sm.empty[s], (use - 1) & 1, status, 801)) break;
-      const long long row = ((long long)k + it * u.ncta) * kRows + r;
-      const bool in = row < p.m;
-      const long long rr = in ? row : 0;
-      const uint8_t* ga = reinterpret_cast<const uint8_t*>(u.A + rr * u.lda);
-      const uint8_t* gb = reinterpret_cast<const uint8_t*>(u.B + rr * u.ldb);
-      const uint32_t da = smem_u32(sm.a[s]) + r * 16, db = smem_u32(sm.b[s]) + r * 16;
-#pragma unroll 4
-      for (int g = 0; g < a_groups; ++g) {
-        const int ch = g * 4 + c4;
-        cp_async16(da + ch * (kRows * 16), ga + ch * 16, in ? 16u : 0u);
-      }
-#pragma unroll 4
-      for (int g = 0; g < b_groups; ++g) {
-        const int ch = g * 4 + c4;
-        if (ch * 8 < u.Nmma) {
-          const bool ok = in && ch * 8 < u.Nb;
-          cp_async16(db + ch * (kRows * 16), ok ? gb + ch * 16 : gb, ok ? 16u : 0u);     // zero-fill beyond Nb / beyond the last row
-        }
-      }
-      cp_async_arrive_noinc(smem_u32(&sm.full[s]));
-    }
-    // ------------------------------------------------------------ epilogue: partial tile -> fp32 gradient (atomic adds)
-    if (n_mine > 0 && mbar_wait(&sm.acc_full, 0, status, 803)) {
-      tc_fence_after_sync();
-      for (int h = 0; h < halves; ++h) {
-        float* orow = u.out + (size_t)(h * 128 + warp * 32 + lane) * u.ld_out;
-        const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)h * 256u;
-        for (int c0 = 0; c0 < u.Nmma; c0 += 16) {
-          uint32_t v[16];
-          tmem_ld_32x16(taddr + (uint32_t)c0, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            if (c0 + 4 * q < u.Nb)
-              red_add_v4(orow + c0 + 4 * q, __uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
-                         __uint_as_float(v[4 * q + 3]));
-        }
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0 && n_mine > 0) {
+      const CUtensorMap* ma = &p.maps[u.a_map];
+      const CUtensorMap* mb = &p.maps[u.b_map];
+      const int a_col = u.a_col, a_layer = u.a_layer, b_col = u.b_col, b_layer = u.b_layer;
+      const int a_boxes = Ma / kBoxCols, b_boxes = (Nmma + kBoxCols - 1) / kBoxCols;
+      const uint32_t bytes = (uint32_t)(a_boxes + b_boxes) * kBoxBytes;
+      int s = 0;
+      uint32_t ph = 1;                             // "empty" barriers start released
+      int row = k * kRows;
+      for (long long it = 0; it < n_mine; ++it, row += ncta * kRows) {
+        if (!mbar_wait_s(empty0 + s * 8, ph, status, 801)) break;
+        const uint32_t bar = full0 + s * 8;
+        mbar_arrive_expect_tx_s(bar, bytes);
+        for (int i = 0; i < a_boxes; ++i) tma_load_3d(a_s0 + s * kOpBytes + i * kBoxBytes, ma, a_col + i * kBoxCols, row, a_layer, bar);
+        for (int i = 0; i < b_boxes; ++i) tma_load_3d(b_s0 + s * kOpBytes + i * kBoxBytes, mb, b_col + i * kBoxCols, row, b_layer, bar);
+        if (++s == kStages) { s = 0; ph ^= 1; }
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0 && n_mine > 0) {
-      const uint32_t idesc = umma_idesc_bf16(128, u.Nmma) | (1u << 15) | (1u << 16);      // A and B MN-major
+      const uint32_t idesc = umma_idesc_bf16(128, Nmma) | (1u << 15) | (1u << 16);      // A and B MN-major
       bool ok = true;
-      for (long long it = 0; it < n_mine && ok; ++it) {
-        const int s = (int)(it % kStages);
-        const uint32_t use = (uint32_t)(it / kStages);
-        if (!mbar_wait(&sm.full[s], use & 1, status, 802)) { ok = false; break; }
-        fence_proxy_async_smem();                 // cp.async wrote through the generic proxy; the tensor core reads through the async one
+      int s = 0;
+      uint32_t ph = 0;
+      for (long long it = 0; it < n_mine; ++it) {
+        if (!mbar_wait_s(full0 + s * 8, ph, status, 802)) { ok = false; break; }
         tc_fence_after_sync();
-        const uint32_t a0 = smem_u32(sm.a[s]), b0 = smem_u32(sm.b[s]);
+        const uint32_t a0 = a_s0 + s * kOpBytes, b0 = b_s0 + s * kOpBytes;
 #pragma unroll
-        for (int kk = 0; kk < kRows / 16; ++kk) {
-          const uint64_t bd = mn_desc(b0 + kk * 256);
-          for (int h = 0; h < halves; ++h)
-            umma_bf16(tmem + (uint32_t)h * 256u, mn_desc(a0 + h * (16 * kRows * 16) + kk * 256), bd, idesc, (it > 0 || kk > 0) ? 1u : 0u);
+        for (int kk = 0; kk < kRows / 16; ++kk) {                       // 16 rows = 2 KB inside every box
+          const uint64_t bd = mn_desc(b0 + kk * 2048);
+          for (int h = 0; h < halves; ++h)                              // 128 A columns = 2 boxes
+            umma_bf16(tmem + (uint32_t)h * 256u, mn_desc(a0 + h * (2 * kBoxBytes) + kk * 2048), bd, idesc, (it > 0 || kk > 0) ? 1u : 0u);
         }
         umma_commit(&sm.empty[s]);
+        if (++s == kStages) { s = 0; ph ^= 1; }
       }
       if (ok) umma_commit(&sm.acc_full);
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue: partial tile -> fp32 gradient (atomic adds)
+    const int q = warp & 3;                                              // TMEM lane quarter this warp may read
+    if (n_mine > 0 && mbar_wait(&sm.acc_full, 0, status, 803)) {
+      tc_fence_after_sync();
+      const int ld_out = u.ld_out;
+      float* out0 = u.out;
+      for (int h = 0; h < halves; ++h) {
+        float* orow = out0 + (size_t)(h * 128 + q * 32 + lane) * ld_out;
+        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)h * 256u;
+        uint32_t v[2][16];
+        tmem_ld_32x16(taddr, v[0]);
+        for (int c0 = 0, b = 0; c0 < Nmma; c0 += 16, ++b) {
+          tmem_ld_wait();
+          if (c0 + 16 < Nmma) tmem_ld_32x16(taddr + (uint32_t)(c0 + 16), v[(b + 1) & 1]);
+          const uint32_t* vb = v[b & 1];
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            if (c0 + 4 * g < Nb)
+              red_add_v4(orow + c0 + 4 * g, __uint_as_float(vb[4 * g]), __uint_as_float(vb[4 * g + 1]), __uint_as_float(vb[4 * g + 2]),
+                         __uint_as_float(vb[4 * g + 3]));
+        }
+      }
     }
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 5) { tc_fence_after_sync(); tmem_dealloc(tmem, 512); }
+  if (warp == 0) { tc_fence_after_sync(); tmem_dealloc(tmem, 512); }
 }
 
 // alpha_linear.weight gradient: out[c] = sum_r w[r * w_stride] * X[r, c]  (d_sigma^T h7; a [1 x 256] "GEMM"), bf16 X
@@ -247,6 +253,34 @@ __global__ void __launch_bounds__(256) pgn_view_fold_grads_kernel(const float* _
 
 }  // namespace
 
+// ---------------------------------------------------------------------------------------------------------------
+// host side: tensor maps (cuTensorMapEncodeTiled through the runtime's driver entry point: no link-time libcuda
+// dependency, so the library still loads on a box without a driver and fails with PGN_E_CUDA there)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static cudaError_t make_map(CUtensorMap* map, const void* base, long long cols, long long ld, long long rows, long long layers,
+                            long long layer_stride_elems) {
+  static EncodeTiledFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+    if (e != cudaSuccess) return e;
+    if (!fn || q != cudaDriverEntryPointSuccess) return cudaErrorNotSupported;
+    encode = (EncodeTiledFn)fn;
+  }
+  const cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)layers};
+  const cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)(layers > 1 ? layer_stride_elems : ld * rows) * 2};
+  const cuuint32_t box[3] = {(cuuint32_t)kBoxCols, (cuuint32_t)kRows, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
 // Offsets (floats) of the 12 weight gradients inside the flat buffer: include/posegen_b200.h linear order, nn.Linear layouts
 static const int kW_out[12] = {256, 256, 256, 256, 256, 256, 256, 256, 1, 256, 128, 3};
 static const int kW_in[12] = {432, 256, 256, 256, 256, 688, 256, 256, 256, 256, 904, 128};
@@ -257,46 +291,7 @@ size_t pgn_wgrad_flat_floats() {
   return t;
 }
 
-cudaError_t pgn_launch_weight_grads(const void* dz_, const void* dG_, const void* act_, long long dump_rows, const void* enc_,
-                                    long long m, const float* d_raw, const float* bias_v, const float* w_f, const float* b_f,
-                                    const float* w_v, float* flat, float* feat_bias, float* tm_scratch, int* status, int num_sms,
-                                    cudaStream_t stream) {
-  const __nv_bfloat16* dz = reinterpret_cast<const __nv_bfloat16*>(dz_);
-  const __nv_bfloat16* dG = reinterpret_cast<const __nv_bfloat16*>(dG_);
-  const __nv_bfloat16* act = reinterpret_cast<const __nv_bfloat16*>(act_);
-  const __nv_bfloat16* enc = reinterpret_cast<const __nv_bfloat16*>(enc_);
-  size_t off[12], o = 0;
-  for (int i = 0; i < 12; ++i) { off[i] = o; o += (size_t)kW_out[i] * kW_in[i]; }
-  cudaError_t e = cudaMemsetAsync(flat, 0, o * sizeof(float), stream);
-  if (e != cudaSuccess) return e;
-  e = cudaMemsetAsync(tm_scratch, 0, 128 * 256 * sizeof(float), stream);
-  if (e != cudaSuccess || m == 0) return e;
-  auto H = [&](int l) { return act + (size_t)l * dump_rows * 256; };        // activation dump: layers 0-7 [dump_rows,256] each
-  auto DZ = [&](int l) { return dz + (size_t)l * m * 256; };
-  Params p;
-  int n = 0;
-  auto add = [&](const __nv_bfloat16* A, int lda, int Ma, const __nv_bfloat16* B, int ldb, int Nb, float* out, int ld_out) {
-    Unit& u = p.u[n++];
-    u.A = A; u.B = B; u.out = out; u.lda = lda; u.ldb = ldb; u.ld_out = ld_out; u.Ma = Ma; u.Nb = Nb; u.Nmma = (Nb + 15) / 16 * 16;
-    u.cta0 = 0; u.ncta = 0;
-  };
-  // pts_linears.0: dZ_0^T x_p (432 = 256 + 176 columns)
-  add(DZ(0), 256, 256, enc, 1080, 256, flat + off[0], 432);
-  add(DZ(0), 256, 256, enc + 256, 1080, 176, flat + off[0] + 256, 432);
-  for (int l = 1; l < 8; ++l) {
-    if (l == 5) {       // pts_linears.5 reads [x_p | h4] (skip connection, nerf.py:100-101)
-      add(DZ(5), 256, 256, enc, 1080, 256, flat + off[5], 688);
-      add(DZ(5), 256, 256, enc + 256, 1080, 176, flat + off[5] + 256, 688);
-      add(DZ(5), 256, 256, H(4), 256, 256, flat + off[5] + 432, 688);
-    } else {
-      add(DZ(l), 256, 256, H(l - 1), 256, 256, flat + off[l], 256);
-    }
-  }
-  // views_linears.0: dG^T [h7 -> T scratch | d_emb (648 = 256 + 256 + 136 columns)]
-  add(dG, 128, 128, H(7), 256, 256, tm_scratch, 256);
-  add(dG, 128, 128, enc + 432, 1080, 256, flat + off[10] + 256, 904);
-  add(dG, 128, 128, enc + 688, 1080, 256, flat + off[10] + 512, 904);
-  add(dG, 128, 128, enc + 944, 1080, 136, flat + off[10] + 768, 904);
+static cudaError_t launch_units(Params& p, int n, long long m, int num_sms, int* status, cudaStream_t stream) {
   p.n_units = n;
   p.m = m;
   // CTAs per unit proportional to the bytes a stage streams (Ma + Nmma columns): every unit then sweeps the rows at the
@@ -329,15 +324,57 @@ cudaError_t pgn_launch_weight_grads(const void* dz_, const void* dG_, const void
   const size_t smem = sizeof(Smem) + 1024;
   static PgnPerDeviceOnce configured;
   if (configured.need()) {
-    e = cudaFuncSetAttribute(pgn_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(pgn_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     configured.set();
   }
   pgn_wgrad_kernel<<<c0, kThreads, smem, stream>>>(p, status);
-  e = cudaGetLastError();
+  return cudaGetLastError();
+}
+
+cudaError_t pgn_launch_weight_grads(const void* dz_, const void* dG_, const void* act_, long long dump_rows, const void* enc_,
+                                    long long m, const float* d_raw, const float* bias_v, const float* w_f, const float* b_f,
+                                    const float* w_v, float* flat, float* feat_bias, float* tm_scratch, int* status, int num_sms,
+                                    cudaStream_t stream) {
+  const __nv_bfloat16* act = reinterpret_cast<const __nv_bfloat16*>(act_);
+  size_t off[12], o = 0;
+  for (int i = 0; i < 12; ++i) { off[i] = o; o += (size_t)kW_out[i] * kW_in[i]; }
+  cudaError_t e = cudaMemsetAsync(flat, 0, o * sizeof(float), stream);
   if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(tm_scratch, 0, 128 * 256 * sizeof(float), stream);
+  if (e != cudaSuccess || m == 0) return e;
+  Params p;
+  enum { kDz = 0, kDg = 1, kAct = 2, kEnc = 3 };
+  if ((e = make_map(&p.maps[kDz], dz_, 256, 256, m, 8, m * 256)) != cudaSuccess) return e;            // dZ_l: [8][m][256]
+  if ((e = make_map(&p.maps[kDg], dG_, 128, 128, m, 1, 0)) != cudaSuccess) return e;                   // dG:   [m][128]
+  if ((e = make_map(&p.maps[kAct], act_, 256, 256, m, 8, dump_rows * 256)) != cudaSuccess) return e;   // h_l:  [8][dump_rows][256], rows < m
+  if ((e = make_map(&p.maps[kEnc], enc_, 1080, 1080, m, 1, 0)) != cudaSuccess) return e;               // input: [m][1080]
+  int n = 0;
+  auto add = [&](int am, int al, int Ma, int bm, int bl, int bc, int Nb, float* out, int ld_out) {
+    Unit& u = p.u[n++];
+    u.a_map = am; u.a_layer = al; u.a_col = 0; u.b_map = bm; u.b_layer = bl; u.b_col = bc;
+    u.out = out; u.ld_out = ld_out; u.Ma = Ma; u.Nb = Nb; u.Nmma = (Nb + 15) / 16 * 16; u.cta0 = 0; u.ncta = 0;
+  };
+  // pts_linears.0: dZ_0^T x_p (432 = 256 + 176 columns)
+  add(kDz, 0, 256, kEnc, 0, 0, 256, flat + off[0], 432);
+  add(kDz, 0, 256, kEnc, 0, 256, 176, flat + off[0] + 256, 432);
+  for (int l = 1; l < 8; ++l) {
+    if (l == 5) {       // pts_linears.5 reads [x_p | h4] (skip connection, nerf.py:100-101)
+      add(kDz, 5, 256, kEnc, 0, 0, 256, flat + off[5], 688);
+      add(kDz, 5, 256, kEnc, 0, 256, 176, flat + off[5] + 256, 688);
+      add(kDz, 5, 256, kAct, 4, 0, 256, flat + off[5] + 432, 688);
+    } else {
+      add(kDz, l, 256, kAct, l - 1, 0, 256, flat + off[l], 256);
+    }
+  }
+  // views_linears.0: dG^T [h7 -> T scratch | d_emb (648 = 256 + 256 + 136 columns)]
+  add(kDg, 0, 128, kAct, 7, 0, 256, tm_scratch, 256);
+  add(kDg, 0, 128, kEnc, 0, 432, 256, flat + off[10] + 256, 904);
+  add(kDg, 0, 128, kEnc, 0, 688, 256, flat + off[10] + 512, 904);
+  add(kDg, 0, 128, kEnc, 0, 944, 136, flat + off[10] + 768, 904);
+  if ((e = launch_units(p, n, m, num_sms, status, stream)) != cudaSuccess) return e;
   // alpha_linear.weight = d_sigma^T h7
-  pgn_weighted_colsum_kernel<<<num_sms * 2, 256, 0, stream>>>(H(7), m, d_raw + 3, 4, flat + off[8]);
+  pgn_weighted_colsum_kernel<<<num_sms * 2, 256, 0, stream>>>(act + (size_t)7 * dump_rows * 256, m, d_raw + 3, 4, flat + off[8]);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   pgn_view_fold_grads_kernel<<<128 + 256, 256, 0, stream>>>(tm_scratch, bias_v, w_f, b_f, w_v, flat + off[10], flat + off[9], feat_bias);
@@ -349,19 +386,12 @@ cudaError_t pgn_launch_wgrad_single(const void* A, int lda, int Ma, const void* 
                                     int n_ctas, int* status, cudaStream_t stream) {
   if (m == 0) return cudaSuccess;
   Params p;
+  cudaError_t e;
+  if ((e = make_map(&p.maps[0], A, Ma, lda, m, 1, 0)) != cudaSuccess) return e;
+  if ((e = make_map(&p.maps[1], B, Nb, ldb, m, 1, 0)) != cudaSuccess) return e;
+  p.maps[2] = p.maps[0]; p.maps[3] = p.maps[0];
   Unit& u = p.u[0];
-  u.A = reinterpret_cast<const __nv_bfloat16*>(A); u.B = reinterpret_cast<const __nv_bfloat16*>(B); u.out = out;
-  u.lda = lda; u.ldb = ldb; u.ld_out = ld_out; u.Ma = Ma; u.Nb = Nb; u.Nmma = (Nb + 15) / 16 * 16;
-  const long long n_stages = (m + kRows - 1) / kRows;
-  u.cta0 = 0; u.ncta = (int)(n_ctas < n_stages ? n_ctas : n_stages);
-  p.n_units = 1; p.m = m;
-  const size_t smem = sizeof(Smem) + 1024;
-  static PgnPerDeviceOnce configured;
-  if (configured.need()) {
-    cudaError_t e = cudaFuncSetAttribute(pgn_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured.set();
-  }
-  pgn_wgrad_kernel<<<u.ncta, kThreads, smem, stream>>>(p, status);
-  return cudaGetLastError();
+  u.a_map = 0; u.a_layer = 0; u.a_col = 0; u.b_map = 1; u.b_layer = 0; u.b_col = 0;
+  u.out = out; u.ld_out = ld_out; u.Ma = Ma; u.Nb = Nb; u.Nmma = (Nb + 15) / 16 * 16; u.cta0 = 0; u.ncta = 0;
+  return launch_units(p, 1, m, n_ctas, status, stream);
 }
