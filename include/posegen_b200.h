@@ -70,6 +70,11 @@ typedef struct pgn_config {
   int32_t net_width;       /* 256 */
   int32_t skip_layer;      /* 4 */
   int32_t device;          /* CUDA device ordinal */
+  /* ABI v2: Optcodes frame codes (core/networks/embedding.py:4-46; `opt_framecode = True` in the h36m / mixamo /
+   * perfcap configs): every NeRF owns n_framecodes learned codes of framecode_ch (16) channels and views_linears.0
+   * reads [feature(256) | input_views(648) | code(16)] = 920 inputs (core/networks/nerf.py:52-56,104-131).  0 = off. */
+  int32_t n_framecodes;
+  int32_t framecode_ch;
 } pgn_config;
 
 /* One NeRF MLP's parameters in nn.Linear layout ([out,in] row-major weight, [out] bias),
@@ -77,12 +82,13 @@ typedef struct pgn_config {
  *   0..7  pts_linears.0-7   (432->256, 4x 256->256, 688->256, 2x 256->256)
  *   8     alpha_linear      (256->1)
  *   9     feature_linear    (256->256)
- *   10    views_linears.0   (904->128)
+ *   10    views_linears.0   (904->128; 920->128 with frame codes)
  *   11    rgb_linear        (128->3)
  * Pointers may be host or device memory (flag in pgn_upload_weights). */
 typedef struct pgn_net_weights {
   const float* weight[PGN_N_LINEAR];
   const float* bias[PGN_N_LINEAR];
+  const float* framecodes;   /* ABI v2: framecodes.codes.weight [n_framecodes,16] (NULL when the config has none) */
 } pgn_net_weights;
 
 /* Inputs of one render call.  Replaces the arguments of RayCaster.render_rays
@@ -110,6 +116,10 @@ typedef struct pgn_render_inputs {
    * the rays of several images keeps the reference's per-image batchify chunks (run_nerf.py:77-95). */
   const int64_t* chunk_starts;
   int64_t        n_chunks;
+  /* ABI v2: the `cams` kwarg of RayCaster.render_rays (core/raycasters.py:368,429,453): optional device int32 [n_rays]
+   * frame-code index per ray.  NULL or an index outside [0, n_framecodes) selects the mean code, the reference's
+   * evaluation rule for idx < 0 (core/networks/embedding.py:23-24).  Ignored by a context without frame codes. */
+  const int32_t* cams;
 } pgn_render_inputs;
 
 /* Outputs of one render call (core/raycasters.py:711-724).  Any pointer may be NULL
@@ -265,14 +275,21 @@ PGN_API int  pgn_mlp_delta_chain_net(pgn_context* ctx, int32_t net_id, const voi
  *   act  the pass's activation dump of pgn_render_forward_train (dump_rows = pgn_activation_dump_bytes / 4608)
  *   enc  bf16 [m][1080]     the network input (pgn_encode_bf16)
  *   d_raw fp32 [m][4] (column 3 = d_sigma), bias_v fp32 [128] = column sums of dG (pgn_mlp_delta's colsum)
- * Outputs: flat fp32 [pgn_weight_grad_floats()] = the 12 weight gradients back to back in the pgn_net_weights order and
+ * Outputs: flat fp32 [pgn_weight_grad_floats(ctx)] = the 12 weight gradients back to back in the pgn_net_weights order and
  * nn.Linear layouts ([out,in] row-major; slot 11, rgb_linear.weight, is left zero: pgn_mlp_delta produces it), and
  * feat_bias fp32 [256] = feature_linear.bias' gradient.  feature_linear has no activation, so its gradients and the
  * feature block of views_linears.0 are formed from T = dG^T h7 [128,256] with the uploaded weights of `net_id`. */
-PGN_API size_t pgn_weight_grad_floats(void);
+PGN_API size_t pgn_weight_grad_floats(const pgn_context* ctx);
 PGN_API int  pgn_mlp_weight_grads(pgn_context* ctx, int32_t net_id, const void* dz, const void* dG, const void* act, int64_t dump_rows,
                                   const void* enc, int64_t m, const float* d_raw, const float* bias_v, float* flat,
                                   float* feat_bias, void* stream);
+
+/* Backward of the frame-code term (Optcodes): dG bf16 [n_rays * n_z, 128] (the view layer's delta), cams int32 [n_rays] or
+ * NULL -> g_view_weight fp32 [128, 920]: columns 904..919 += dGr^T code[cam]; g_codes fp32 [n_framecodes,16] +=
+ * scatter over cam of dGr W_v[:, 904:920], with dGr the per-ray sum of dG over the ray's samples.  Both outputs are
+ * accumulated into (the caller zeroes g_codes; g_view_weight is the views_linears.0 slot of pgn_mlp_weight_grads). */
+PGN_API int  pgn_framecode_backward(pgn_context* ctx, int32_t net_id, const void* dG, int64_t n_rays, int32_t n_z,
+                                    const int32_t* cams, float* g_view_weight, float* g_codes, void* stream);
 
 /* the split-K kernel on one explicit product, for unit tests: out[Ma, Nb] (fp32, row stride ld_out) += A[m, :Ma]^T B[m, :Nb],
  * A / B bf16 row-major with row strides lda / ldb (elements), Ma in {128, 256}, Nb a multiple of 8 <= 256, n_ctas CTAs

@@ -115,7 +115,7 @@ class Taps:
         return torch.cat(self.data[key], 0).numpy()
 
 
-def reference_render(render_kwargs, frame, ckpt, chunk=4096, cyl_override=None):
+def reference_render(render_kwargs, frame, ckpt, chunk=4096, cyl_override=None, cams=None):
     from core.trainer import render
     rcast = render_kwargs["ray_caster"]
     rcast.load_state_dict(to_torch_ckpt(ckpt))
@@ -129,13 +129,13 @@ def reference_render(render_kwargs, frame, ckpt, chunk=4096, cyl_override=None):
         with contextlib.redirect_stdout(io.StringIO()), torch.no_grad():
             out = render(frame.H, frame.W, frame.focal, rays=rays, chunk=chunk,
                          kp_batch=exp(frame.pose.kps), skts=exp(frame.pose.skts), cyls=exp(cyl),
-                         bones=exp(frame.pose.bones), cams=None, subject_idxs=None, **render_kwargs)
+                         bones=exp(frame.pose.bones), cams=cams, subject_idxs=None, **render_kwargs)
     finally:
         taps.remove()
     return {k: v.cpu().numpy() for k, v in out.items()}, taps
 
 
-def oracle_render(frame, ckpt, chunk=4096, cyl_override=None, dtype=torch.float32):
+def oracle_render(frame, ckpt, chunk=4096, cyl_override=None, dtype=torch.float32, cams=None):
     rb = torch.from_numpy(syn.ray_batch(frame.rays_o, frame.rays_d)).to(dtype)
     cyl = frame.pose.cyl if cyl_override is None else cyl_override
     taps = {}
@@ -144,10 +144,10 @@ def oracle_render(frame, ckpt, chunk=4096, cyl_override=None, dtype=torch.float3
     if rb.shape[0] <= chunk:
         with torch.no_grad():
             out = orc.render_rays(rb, torch.from_numpy(frame.pose.skts).to(dtype)[None].expand(rb.shape[0], -1, -1, -1),
-                                  torch.from_numpy(cyl).to(dtype)[None].expand(rb.shape[0], -1), nets, emb, taps=taps)
+                                  torch.from_numpy(cyl).to(dtype)[None].expand(rb.shape[0], -1), nets, emb, taps=taps, cams=cams)
     else:
         out = orc.render(rb, torch.from_numpy(frame.pose.skts).to(dtype), torch.from_numpy(cyl).to(dtype),
-                         nets, emb, chunk=chunk)
+                         nets, emb, chunk=chunk, cams=cams)
     return {k: v.numpy() for k, v in out.items()}, {k: v.numpy() for k, v in taps.items()}
 
 
@@ -247,6 +247,84 @@ def make_case(render_kwargs, name, pose_seed, res, weight_seed, alpha_gain, full
     print(f"  wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB)")
 
 
+def build_framecode_raycaster(tmpdir, n_framecodes):
+    """The reference's create_raycaster for configs/h36m/h36m_prot2.txt (opt_framecode = True: Optcodes frame codes,
+    core/networks/embedding.py:4-46), which differs from surreal.txt in nothing else the render path reads."""
+    import run_nerf
+    from core.raycasters import create_raycaster
+    from core.utils.skeleton_utils import SMPLSkeleton, smpl_rest_pose, get_per_joint_coords
+    with contextlib.redirect_stdout(io.StringIO()):
+        os.makedirs(os.path.join(tmpdir, "fc"), exist_ok=True)
+        args = run_nerf.config_parser().parse_args(
+            ["--config", os.path.join(ref_shim.REFERENCE_ROOT, "configs/h36m/h36m_prot2.txt"),
+             "--basedir", tmpdir, "--expname", "fc", "--no_reload"])
+        assert args.opt_framecode and args.framecode_size == 16
+        data_attrs = {"skel_type": SMPLSkeleton, "near": 60., "far": 100., "n_views": n_framecodes,
+                      "joint_coords": get_per_joint_coords(smpl_rest_pose.astype(np.float32))}
+        _, render_kwargs_test, _, _, _, _ = create_raycaster(args, data_attrs)
+    return render_kwargs_test
+
+
+def make_framecode_case(render_kwargs, name, pose_seed, res, weight_seed, n_framecodes, chunk=4096):
+    """Optcodes case (h36m_prot2-shaped model): calibrated head, one render with a real camera index per ray and one with
+    cams = -1 (the mean code, embedding.py:23-24), plus the reference's density-only query on random points (pins
+    `fwd_type='density'`, core/raycasters.py:597-648)."""
+    print(f"[{name}] pose_seed={pose_seed} res={res} weight_seed={weight_seed} n_framecodes={n_framecodes}")
+    frame = syn.synthetic_frame(pose_seed, res, res)
+    check_geometry(frame)
+    ckpt = syn.synthetic_raycaster_state(weight_seed, alpha_gain=None, n_framecodes=n_framecodes)
+    n = frame.rays_o.shape[0]
+    cams = torch.full((n,), 3, dtype=torch.long)
+    cams[: n // 2] = 1                                   # two cameras in one batch (chunks see a mix of valid indices)
+    extra = {}
+    for key in ("network_fn_state_dict", "network_fine_state_dict"):
+        ckpt[key]["alpha_linear.bias"] = np.zeros_like(ckpt[key]["alpha_linear.bias"])
+    _, taps0 = reference_render(render_kwargs, frame, ckpt, chunk, cams=cams)
+    for key, raw_key in (("network_fn_state_dict", "raw_coarse"), ("network_fine_state_dict", "raw_fine")):
+        sig_far = float(taps0.get(raw_key)[:, -1, 3].max())
+        syn.calibrate_alpha_head(ckpt[key], sig_far)
+        extra[f"sigma_far_max_{raw_key}"] = np.float32(sig_far)
+    worst = 0.0
+    fix = {}
+    for tag, c in (("", cams), ("_mean", torch.full((n,), -1, dtype=torch.long))):
+        ref, taps = reference_render(render_kwargs, frame, ckpt, chunk, cams=c)
+        got, otaps = oracle_render(frame, ckpt, chunk, cams=c)
+        worst = max(worst, compare(name + tag, ref, got))
+        for k in ("rgb_map", "disp_map", "acc_map", "rgb0", "disp0", "acc0"):
+            fix[k + tag] = ref[k]
+        print(f"  {tag or 'cams':>6}: acc mean {ref['acc_map'].mean():.4f} max {ref['acc_map'].max():.4f}")
+    fix["rgb_delta_mean_vs_cam"] = np.float32(np.abs(fix["rgb_map"] - fix["rgb_map_mean"]).max())
+    assert fix["rgb_delta_mean_vs_cam"] > 1e-4, "the frame code must be visible in the image"
+    # density-only query of the reference on random points around the body
+    rcast = render_kwargs["ray_caster"]
+    rng = np.random.RandomState(5)
+    pts = (frame.pose.kps[0] + (rng.rand(2000, 3).astype(np.float32) - 0.5) * 1.2).astype(np.float32)
+    exp = lambda a: torch.from_numpy(np.ascontiguousarray(a))[None].expand(len(pts), *a.shape).clone()  # noqa: E731
+    with contextlib.redirect_stdout(io.StringIO()), torch.no_grad():
+        dens = rcast(torch.from_numpy(pts).reshape(-1, 1, 3), exp(frame.pose.kps), exp(frame.pose.skts), exp(frame.pose.bones),
+                     render_kwargs=render_kwargs["preproc_kwargs"], fwd_type="density")
+    dens = dens.reshape(-1).cpu().numpy()
+    from oracle import next_oracle as nxt
+    nets, emb = orc.nets_from_ckpt(ckpt), orc.embed_params_from_ckpt(ckpt)
+    dens_o = nxt.density_of_points(torch.from_numpy(pts), torch.from_numpy(frame.pose.skts), nets[1], emb).numpy()
+    d_err = float(np.abs(dens - dens_o).max())
+    print(f"  oracle vs reference worst max-abs: {worst:.3e}; density query {d_err:.3e} (|raw| max {np.abs(dens).max():.2f})")
+    assert worst <= 2e-6 and d_err <= 2e-5 * max(1.0, float(np.abs(dens).max())), "oracle restatement deviates from the reference"
+    rb = syn.ray_batch(frame.rays_o, frame.rays_d)
+    fix.update({
+        "meta_pose_seed": np.int64(pose_seed), "meta_res": np.int64(res), "meta_weight_seed": np.int64(weight_seed),
+        "meta_alpha_gain": np.float32(0.0), "meta_calibrated": np.bool_(True), "meta_chunk": np.int64(chunk),
+        "meta_n_framecodes": np.int64(n_framecodes), "meta_oracle_vs_ref_maxabs": np.float64(worst),
+        "in_ray_batch_sha": np.array(sha(rb)), "in_skts_sha": np.array(sha(frame.pose.skts)),
+        "in_cyl": frame.pose.cyl.astype(np.float32), "in_ray_batch_head": rb[:16], "in_cams": cams.numpy().astype(np.int32),
+        "density_pts": pts, "density_raw": dens.astype(np.float32),
+    })
+    fix.update(extra)
+    path = os.path.join(GOLDEN_DIR, f"{name}.npz")
+    np.savez_compressed(path, **fix)
+    print(f"  wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB)")
+
+
 def main():
     torch.manual_seed(0)
     os.makedirs(GOLDEN_DIR, exist_ok=True)
@@ -264,7 +342,14 @@ def main():
         # E: 32x32 with a shrunken cylinder so bbox-corner rays miss it: chunk-level NaN fill
         make_case(render_kwargs, "e_32_nanfill", pose_seed=3, res=32, weight_seed=0, alpha_gain=400., full_taps=False,
                   shrink_cyl=0.8)
+        # F: 64x64, h36m_prot2-shaped model (opt_framecode = True, 5 frame codes), calibrated head, + density-only query
+        make_framecode_case(build_framecode_raycaster(tmp, 5), "f_64_framecode", pose_seed=4, res=64, weight_seed=2, n_framecodes=5)
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "--framecode-only":
+        with tempfile.TemporaryDirectory() as tmp:
+            ref_shim.install()
+            make_framecode_case(build_framecode_raycaster(tmp, 5), "f_64_framecode", pose_seed=4, res=64, weight_seed=2, n_framecodes=5)
+    else:
+        main()

@@ -45,5 +45,5 @@ def density_of_points(pts: torch.Tensor, skts: torch.Tensor, net: dict, emb: dic
     n = pts.shape[0]
     sk = skts[None].expand(n, 24, 4, 4)
     enc = orc.encode(pts[:, None, :], torch.zeros_like(pts), sk, emb)          # view part unused by the density head
-    raw = orc.nerf_forward(enc.reshape(n, -1), net)
+    raw = orc.nerf_forward(enc.reshape(n, -1), net, frame_code=orc.frame_codes(net, None, 1, n))   # the density head ignores it
     return raw[:, 3]

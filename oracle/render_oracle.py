@@ -134,9 +134,25 @@ def encode(pts, rays_d, skts, emb):
 
 
 # ----------------------------------------------------------------------------
-# core/networks/nerf.py:94-148  NeRF.forward (use_viewdirs, skips=[4], no framecode)
+# core/networks/nerf.py:94-148  NeRF.forward (use_viewdirs, skips=[4]); frame_code [rows,16] = the Optcodes
+# frame code of each row's camera (nerf.py:104-131: input_views = cat([input_views, framecodes])), None without
 # ----------------------------------------------------------------------------
-def nerf_forward(x, net, chunk=1024 * 64):
+def frame_codes(net, cams, n_rows_per_ray, n_rays, training=False):
+    """core/networks/embedding.py:19-31: codes[cam] per ray, the mean code in eval when every index is < 0 (cams None
+    counts as -1), repeated for the ray's samples -> [n_rays * n_rows_per_ray, 16]; None for a net without codes."""
+    if "framecodes.codes.weight" not in net:
+        return None
+    codes = net["framecodes.codes.weight"]
+    if cams is None:
+        cams = torch.full((n_rays,), -1, dtype=torch.long)
+    if not training and int(cams.max()) < 0:
+        c = codes.mean(0, keepdim=True).expand(n_rays, -1)
+    else:
+        c = codes[cams.long()]
+    return c[:, None, :].expand(-1, n_rows_per_ray, -1).reshape(-1, codes.shape[1])
+
+
+def nerf_forward(x, net, chunk=1024 * 64, frame_code=None):
     outs = []
     for i in range(0, x.shape[0], chunk):
         xi = x[i:i + chunk]
@@ -148,7 +164,8 @@ def nerf_forward(x, net, chunk=1024 * 64):
                 h = torch.cat([x_p, h], -1)
         alpha = F.linear(h, net["alpha_linear.weight"], net["alpha_linear.bias"])
         feat = F.linear(h, net["feature_linear.weight"], net["feature_linear.bias"])
-        g = F.relu(F.linear(torch.cat([feat, x_v], -1), net["views_linears.0.weight"],
+        vin = [feat, x_v] if frame_code is None else [feat, x_v, frame_code[i:i + chunk]]
+        g = F.relu(F.linear(torch.cat(vin, -1), net["views_linears.0.weight"],
                             net["views_linears.0.bias"]))
         rgb = F.linear(g, net["rgb_linear.weight"], net["rgb_linear.bias"])
         outs.append(torch.cat([rgb, alpha], -1))
@@ -216,7 +233,7 @@ def importance_z_vals(z_vals, weights, n_importance, u=None):
 # core/raycasters.py:361-474  render_rays  (eval path: perturb 0, no noise)
 # ----------------------------------------------------------------------------
 def render_rays(ray_batch, skts, cyls, nets, emb, n_samples=64, n_importance=16,
-                density_scale=1.0, taps=None):
+                density_scale=1.0, taps=None, cams=None):
     """ray_batch [N,11]; skts [N,24,4,4]; cyls [N,5]; nets = (coarse, fine) state dicts.
     Returns the reference's output dict (core/raycasters.py:711-724).  `taps`, if a
     dict, receives intermediate tensors for stage-level parity tests."""
@@ -226,7 +243,8 @@ def render_rays(ray_batch, skts, cyls, nets, emb, n_samples=64, n_importance=16,
     z_vals = coarse_z_vals(near, far, n_samples)
     pts = rays_o[:, None, :] + rays_d[:, None, :] * z_vals[:, :, None]
     enc = encode(pts, rays_d, skts, emb)
-    raw = nerf_forward(enc.reshape(-1, enc.shape[-1]), nets[0]).reshape(*enc.shape[:2], 4)
+    raw = nerf_forward(enc.reshape(-1, enc.shape[-1]), nets[0],
+                       frame_code=frame_codes(nets[0], cams, enc.shape[1], enc.shape[0])).reshape(*enc.shape[:2], 4)
     ret0 = raw2outputs(raw, z_vals, rays_d, density_scale)
     if taps is not None:
         taps.update(near=near, far=far, z_coarse=z_vals, enc_coarse=enc, raw_coarse=raw,
@@ -238,7 +256,8 @@ def render_rays(ray_batch, skts, cyls, nets, emb, n_samples=64, n_importance=16,
     # core/raycasters.py:679-709,796-812: concat coarse + new encodings, gather in z order
     merged = torch.cat([enc, enc_is], dim=1)
     merged = torch.gather(merged, 1, sorted_idxs[..., None].expand(-1, -1, merged.shape[-1]))
-    raw_f = nerf_forward(merged.reshape(-1, merged.shape[-1]), nets[1]).reshape(*merged.shape[:2], 4)
+    raw_f = nerf_forward(merged.reshape(-1, merged.shape[-1]), nets[1],
+                         frame_code=frame_codes(nets[1], cams, merged.shape[1], merged.shape[0])).reshape(*merged.shape[:2], 4)
     ret = raw2outputs(raw_f, z_all, rays_d, density_scale)
     if taps is not None:
         taps.update(z_samples=z_samples, z_fine=z_all, sorted_idxs=sorted_idxs, pdf_inds=inds,
@@ -260,8 +279,10 @@ def render(ray_batch, skts, cyls, nets, emb, chunk=4096, **kw):
     if cyls.dim() == 1:
         cyls = cyls[None].expand(n, -1)
     outs = {}
+    cams = kw.pop("cams", None)
     for i in range(0, n, chunk):
-        ret = render_rays(ray_batch[i:i + chunk], skts[i:i + chunk], cyls[i:i + chunk], nets, emb, **kw)
+        ret = render_rays(ray_batch[i:i + chunk], skts[i:i + chunk], cyls[i:i + chunk], nets, emb,
+                          cams=None if cams is None else cams[i:i + chunk], **kw)
         for k, v in ret.items():
             outs.setdefault(k, []).append(v)
     return {k: torch.cat(v, 0) for k, v in outs.items()}

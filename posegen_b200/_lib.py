@@ -23,7 +23,7 @@ EXPORTED = [
     "pgn_render_forward_train", "pgn_launch_count",
     "pgn_check_device_status", "pgn_device_status_ptr", "pgn_near_far", "pgn_encode", "pgn_mlp", "pgn_composite", "pgn_composite_backward", "pgn_encode_backward", "pgn_encode_bf16", "pgn_encode_backward_bf16", "pgn_mlp_delta", "pgn_mlp_delta_chain", "pgn_mlp_delta_chain_net", "pgn_mask_dump_bytes", "pgn_render_forward_masks", "pgn_view_delta_from_mask",
     "pgn_sample_pdf", "pgn_generate_rays", "pgn_compose_frame", "pgn_pose_to_skts", "pgn_frame_to_hmr_input",
-    "pgn_weight_grad_floats", "pgn_mlp_weight_grads", "pgn_debug_wgrad",
+    "pgn_weight_grad_floats", "pgn_mlp_weight_grads", "pgn_debug_wgrad", "pgn_framecode_backward",
     "pgn_pose_fk_backward", "pgn_cylinder_bboxes", "pgn_generate_rays_batch", "pgn_compose_frames_batch",
     "pgn_debug_umma_gemm", "pgn_debug_phase_timers",
 ]
@@ -31,17 +31,18 @@ EXPORTED = [
 
 class Config(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("n_joints", "n_samples", "n_importance", "multires", "multires_views",
-                                         "net_depth", "net_width", "skip_layer", "device")]
+                                         "net_depth", "net_width", "skip_layer", "device", "n_framecodes", "framecode_ch")]
 
 
 class NetWeights(C.Structure):
-    _fields_ = [("weight", C.c_void_p * N_LINEAR), ("bias", C.c_void_p * N_LINEAR)]
+    _fields_ = [("weight", C.c_void_p * N_LINEAR), ("bias", C.c_void_p * N_LINEAR), ("framecodes", C.c_void_p)]
 
 
 class RenderInputs(C.Structure):
     _fields_ = [("ray_batch", C.c_void_p), ("n_rays", C.c_int64), ("skts", C.c_void_p), ("skts_stride", C.c_int64),
                 ("cyls", C.c_void_p), ("cyls_stride", C.c_int64), ("pose_idx", C.c_void_p),
-                ("nanfill_chunk", C.c_int64), ("precision", C.c_int32), ("chunk_starts", C.c_void_p), ("n_chunks", C.c_int64)]
+                ("nanfill_chunk", C.c_int64), ("precision", C.c_int32), ("chunk_starts", C.c_void_p), ("n_chunks", C.c_int64),
+                ("cams", C.c_void_p)]
 
 
 class RenderOutputs(C.Structure):
@@ -110,7 +111,8 @@ def load() -> C.CDLL:
     lib.pgn_compose_frame.argtypes = [vp, i32, i32, i32, i32, i32, i32, vp, vp, f32, vp, vp]
     lib.pgn_pose_to_skts.argtypes = [vp, vp, C.POINTER(f32), i32, f32, f32, f32, vp, vp, vp, vp, vp]
     lib.pgn_frame_to_hmr_input.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, C.POINTER(f32), C.POINTER(f32), i32, vp, vp]
-    lib.pgn_weight_grad_floats.argtypes = []
+    lib.pgn_framecode_backward.argtypes = [vp, i32, vp, i64, i32, vp, vp, vp, vp]
+    lib.pgn_weight_grad_floats.argtypes = [vp]
     lib.pgn_weight_grad_floats.restype = C.c_size_t
     lib.pgn_mlp_weight_grads.argtypes = [vp, i32, vp, vp, vp, i64, vp, i64, vp, vp, vp, vp, vp]
     lib.pgn_debug_wgrad.argtypes = [vp, vp, i32, i32, vp, i32, i32, i64, vp, i32, i32, vp]

@@ -44,7 +44,9 @@ struct DeviceGuard {
 const int kOut[PGN_N_LINEAR] = {256, 256, 256, 256, 256, 256, 256, 256, 1, 256, 128, 3};
 const int kIn[PGN_N_LINEAR]  = {432, 256, 256, 256, 256, 688, 256, 256, 256, 256, 904, 128};
 
-size_t weight_floats() { size_t t = 0; for (int i = 0; i < PGN_N_LINEAR; ++i) t += (size_t)kOut[i] * kIn[i]; return t; }
+// views_linears.0 reads 16 more columns (the frame code) when the model has Optcodes (core/networks/nerf.py:52-56)
+int in_of(int l, int view_in) { return l == 10 ? view_in : kIn[l]; }
+size_t weight_floats(int view_in) { size_t t = 0; for (int i = 0; i < PGN_N_LINEAR; ++i) t += (size_t)kOut[i] * in_of(i, view_in); return t; }
 size_t bias_floats() { size_t t = 0; for (int i = 0; i < PGN_N_LINEAR; ++i) t += kOut[i]; return t; }
 
 }  // namespace
@@ -75,6 +77,10 @@ struct pgn_context {
   unsigned long long* d_prof;   // optional phase timers [num_sms][32]
   bool prof_on;
   float* d_tm = nullptr;    // T = dG^T h7 [128,256] scratch of pgn_mlp_weight_grads
+  int view_in = 904;        // input width of views_linears.0: 904, + framecode_ch with Optcodes
+  int n_codes = 0;          // frame codes per net (0: none)
+  float* d_codes_ext[2] = {nullptr, nullptr};   // [n_codes + 1][16]: the codes + their mean
+  float* d_fc_table[2] = {nullptr, nullptr};    // [n_codes + 1][128]: W_v[:, 904:920] codes^T
   float* d_c2w;
   float* d_rest;            // rest pose [24,3] of the last pgn_pose_to_skts call
   int64_t launches;
@@ -96,6 +102,8 @@ int pgn_create(const pgn_config* cfg, pgn_context** out) {
   if (e != cudaSuccess || ndev == 0)
     return fail(PGN_E_CUDA, "pgn_create: no CUDA device (%s); posegen_b200 has no CPU fallback",
                 e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  if (cfg->n_framecodes < 0 || (cfg->n_framecodes > 0 && cfg->framecode_ch != 16))
+    return fail(PGN_E_INVALID, "pgn_create: frame codes (Optcodes) need n_framecodes >= 0 and framecode_ch == 16");
   if (cfg->device < 0 || cfg->device >= ndev) return fail(PGN_E_INVALID, "pgn_create: bad device ordinal %d", cfg->device);
   DeviceGuard _guard(cfg->device);
   if (_guard.err != cudaSuccess) return fail(PGN_E_CUDA, "cudaSetDevice(%d): %s", cfg->device, cudaGetErrorString(_guard.err));
@@ -107,6 +115,8 @@ int pgn_create(const pgn_config* cfg, pgn_context** out) {
   memset(c, 0, sizeof(*c));
   c->cfg = *cfg;
   c->num_sms = prop.multiProcessorCount;
+  c->n_codes = cfg->n_framecodes;
+  c->view_in = 904 + (cfg->n_framecodes > 0 ? cfg->framecode_ch : 0);
   for (int i = 0; i < PGN_S; ++i) c->h_sc.t_coarse[i] = pgn_linspace01(i, PGN_S);
   for (int i = 0; i < PGN_I; ++i) c->h_sc.u_det[i] = pgn_linspace01(i, PGN_I);
   PGN_CUDA(cudaMalloc(&c->d_sc, sizeof(PgnScalars)));
@@ -120,9 +130,13 @@ int pgn_create(const pgn_config* cfg, pgn_context** out) {
   PGN_CUDA(cudaMalloc(&c->d_tm, 128 * 256 * sizeof(float)));
   for (int n = 0; n < 2; ++n) PGN_CUDA(cudaMalloc(&c->d_chain_w[n], (size_t)120 * 4096 * sizeof(__nv_bfloat16)));
   for (int n = 0; n < 2; ++n) {
-    PGN_CUDA(cudaMalloc(&c->d_w[n], weight_floats() * sizeof(float)));
+    PGN_CUDA(cudaMalloc(&c->d_w[n], weight_floats(c->view_in) * sizeof(float)));
     PGN_CUDA(cudaMalloc(&c->d_b[n], bias_floats() * sizeof(float)));
-    PGN_CUDA(cudaMalloc(&c->d_wt[n], weight_floats() * sizeof(float)));
+    PGN_CUDA(cudaMalloc(&c->d_wt[n], weight_floats(c->view_in) * sizeof(float)));
+    if (c->n_codes > 0) {
+      PGN_CUDA(cudaMalloc(&c->d_codes_ext[n], (size_t)(c->n_codes + 1) * 16 * sizeof(float)));
+      PGN_CUDA(cudaMalloc(&c->d_fc_table[n], (size_t)(c->n_codes + 1) * 128 * sizeof(float)));
+    }
     PGN_CUDA(cudaMalloc(&c->d_wstream[n], pgn_bf16_wstream_elems() * sizeof(__nv_bfloat16)));
     PGN_CUDA(cudaMalloc(&c->d_bf16_aux[n], (9 * 256 + 256 + 384) * sizeof(float)));
     size_t wo = 0, bo = 0;
@@ -131,13 +145,15 @@ int pgn_create(const pgn_config* cfg, pgn_context** out) {
       c->b_ptr[n][l] = c->d_b[n] + bo;
       c->fp32[n].wt[l] = c->d_wt[n] + wo;
       c->fp32[n].b[l] = c->d_b[n] + bo;
-      wo += (size_t)kOut[l] * kIn[l];
+      wo += (size_t)kOut[l] * in_of(l, c->view_in);
       bo += kOut[l];
     }
     c->fp32[n].w_alpha = c->w_ptr[n][8];
     c->fp32[n].b_alpha = c->b_ptr[n][8];
     c->fp32[n].w_rgb = c->w_ptr[n][11];
     c->fp32[n].b_rgb = c->b_ptr[n][11];
+    c->fp32[n].codes_ext = c->d_codes_ext[n];
+    c->bf16[n].fc_table = c->d_fc_table[n];
     c->bf16[n].wstream = c->d_wstream[n];
     c->bf16[n].bias = c->d_bf16_aux[n];
     c->bf16[n].w_alpha = c->d_bf16_aux[n] + 9 * 256;
@@ -154,6 +170,7 @@ void pgn_destroy(pgn_context* c) {
   DeviceGuard _guard(c->cfg.device);
   cudaFree(c->d_sc); cudaFree(c->d_status); cudaFree(c->d_c2w); cudaFree(c->d_rest); cudaFree(c->d_fold); cudaFree(c->d_tm); cudaFree(c->d_chain_w[0]); cudaFree(c->d_chain_w[1]);
   for (int n = 0; n < 2; ++n) {
+    cudaFree(c->d_codes_ext[n]); cudaFree(c->d_fc_table[n]);
     cudaFree(c->d_w[n]); cudaFree(c->d_b[n]); cudaFree(c->d_wt[n]); cudaFree(c->d_wstream[n]); cudaFree(c->d_bf16_aux[n]);
   }
   delete c;
@@ -166,14 +183,20 @@ int pgn_upload_weights(pgn_context* c, int net_id, const pgn_net_weights* w, int
   const cudaMemcpyKind kind = pointers_are_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
   for (int l = 0; l < PGN_N_LINEAR; ++l) {
     if (!w->weight[l] || !w->bias[l]) return fail(PGN_E_INVALID, "pgn_upload_weights: null tensor %d", l);
-    PGN_CUDA(cudaMemcpyAsync((void*)c->w_ptr[net_id][l], w->weight[l], (size_t)kOut[l] * kIn[l] * sizeof(float), kind, stream));
+    PGN_CUDA(cudaMemcpyAsync((void*)c->w_ptr[net_id][l], w->weight[l], (size_t)kOut[l] * in_of(l, c->view_in) * sizeof(float), kind, stream));
     PGN_CUDA(cudaMemcpyAsync((void*)c->b_ptr[net_id][l], w->bias[l], (size_t)kOut[l] * sizeof(float), kind, stream));
   }
   // the fp32 CUDA-core tier's transposed copies are rebuilt lazily, by the first fp32 call after an upload
   // (ensure_fp32_tier): a bf16 training loop re-packs every step and never reads them
   c->fp32_stale[net_id] = true;
   PGN_CUDA(pgn_pack_bf16_net(c->w_ptr[net_id], c->b_ptr[net_id], c->d_wstream[net_id], c->d_bf16_aux[net_id],
-                             c->d_bf16_aux[net_id] + 9 * 256, c->d_bf16_aux[net_id] + 9 * 256 + 256, c->d_fold, stream));
+                             c->d_bf16_aux[net_id] + 9 * 256, c->d_bf16_aux[net_id] + 9 * 256 + 256, c->d_fold, c->view_in, stream));
+  if (c->n_codes > 0) {         // Optcodes: the codes, their mean and the per-code view-layer term
+    if (!w->framecodes) return fail(PGN_E_INVALID, "pgn_upload_weights: the context was created with frame codes but framecodes is NULL");
+    PGN_CUDA(cudaMemcpyAsync(c->d_codes_ext[net_id], w->framecodes, (size_t)c->n_codes * 16 * sizeof(float), kind, stream));
+    PGN_CUDA(pgn_launch_framecode_tables(c->d_codes_ext[net_id], c->n_codes, c->w_ptr[net_id][10], c->view_in, c->d_fc_table[net_id], stream));
+    c->launches++;
+  }
   // the backward's delta-chain weight stream (reads the fold the pack above left in d_fold)
   PGN_CUDA(pgn_launch_pack_chain_weights(c->w_ptr[net_id], c->d_fold, c->d_chain_w[net_id], stream));
   c->launches += 3;
@@ -188,7 +211,7 @@ static int ensure_fp32_tier(pgn_context* c, cudaStream_t stream) {
     if (!c->fp32_stale[n] || !c->have_w[n]) continue;
     for (int l = 0; l < PGN_N_LINEAR; ++l) {
       if (l == 8 || l == 11) continue;   // small heads keep nn.Linear layout
-      PGN_CUDA(pgn_launch_transpose(c->w_ptr[n][l], kOut[l], kIn[l], (float*)c->fp32[n].wt[l], stream));
+      PGN_CUDA(pgn_launch_transpose(c->w_ptr[n][l], kOut[l], in_of(l, c->view_in), (float*)c->fp32[n].wt[l], stream));
       c->launches++;
     }
     c->fp32_stale[n] = false;
@@ -227,10 +250,11 @@ static int check_inputs(const pgn_context* c, const pgn_render_inputs* in, const
   return PGN_OK;
 }
 
-static PgnRayRefs make_refs(const pgn_render_inputs* in) {
+static PgnRayRefs make_refs(const pgn_context* c, const pgn_render_inputs* in) {
   PgnRayRefs r;
   r.ray_batch = in->ray_batch; r.n_rays = in->n_rays; r.skts = in->skts; r.skts_stride = in->skts_stride;
   r.cyls = in->cyls; r.cyls_stride = in->cyls_stride; r.pose_idx = in->pose_idx;
+  r.cams = c->n_codes > 0 ? in->cams : nullptr; r.n_codes = c->n_codes;
   return r;
 }
 
@@ -290,7 +314,7 @@ static int render_forward_impl(pgn_context* c, const pgn_render_inputs* in, cons
   if (!workspace || workspace_bytes < pgn_workspace_bytes(c, in->n_rays)) return fail(PGN_E_INVALID, "pgn_render_forward: workspace too small");
   cudaStream_t stream = (cudaStream_t)stream_;
   PGN_ON_DEVICE(c);
-  const PgnRayRefs refs = make_refs(in);
+  const PgnRayRefs refs = make_refs(c, in);
   float* near_far = (float*)workspace;
   if (in->chunk_starts) {
     if (in->n_chunks <= 0) return fail(PGN_E_INVALID, "pgn_render_forward: chunk_starts without n_chunks");
@@ -339,9 +363,9 @@ int pgn_near_far(pgn_context* c, const pgn_render_inputs* in, float* near_far, v
   if (!near_far) return fail(PGN_E_INVALID, "pgn_near_far: null output");
   PGN_ON_DEVICE(c);
   if (in->chunk_starts)
-    PGN_CUDA(pgn_launch_near_far_chunks(make_refs(in), (const long long*)in->chunk_starts, in->n_chunks, near_far, (cudaStream_t)stream));
+    PGN_CUDA(pgn_launch_near_far_chunks(make_refs(c, in), (const long long*)in->chunk_starts, in->n_chunks, near_far, (cudaStream_t)stream));
   else
-  PGN_CUDA(pgn_launch_near_far(make_refs(in), in->nanfill_chunk, near_far, (cudaStream_t)stream));
+  PGN_CUDA(pgn_launch_near_far(make_refs(c, in), in->nanfill_chunk, near_far, (cudaStream_t)stream));
   c->launches++;
   return PGN_OK;
 }
@@ -352,7 +376,7 @@ int pgn_encode(pgn_context* c, const pgn_render_inputs* in, const float* z, int3
   if (!z || !enc || n_z <= 0) return fail(PGN_E_INVALID, "pgn_encode: bad argument");
   if (!c->have_sc) return fail(PGN_E_STATE, "pgn_encode: scalars not set");
   PGN_ON_DEVICE(c);
-  PGN_CUDA(pgn_launch_encode(make_refs(in), c->d_sc, z, n_z, enc, (cudaStream_t)stream));
+  PGN_CUDA(pgn_launch_encode(make_refs(c, in), c->d_sc, z, n_z, enc, (cudaStream_t)stream));
   c->launches++;
   return PGN_OK;
 }
@@ -363,7 +387,7 @@ int pgn_encode_bf16(pgn_context* c, const pgn_render_inputs* in, const float* z,
   if (!z || !enc || n_z <= 0) return fail(PGN_E_INVALID, "pgn_encode_bf16: bad argument");
   if (!c->have_sc) return fail(PGN_E_STATE, "pgn_encode_bf16: scalars not set");
   PGN_ON_DEVICE(c);
-  PGN_CUDA(pgn_launch_encode_bf16(make_refs(in), c->d_sc, z, n_z, reinterpret_cast<__nv_bfloat16*>(enc), (cudaStream_t)stream));
+  PGN_CUDA(pgn_launch_encode_bf16(make_refs(c, in), c->d_sc, z, n_z, reinterpret_cast<__nv_bfloat16*>(enc), (cudaStream_t)stream));
   c->launches++;
   return PGN_OK;
 }
@@ -407,7 +431,20 @@ int pgn_mlp_delta_chain_net(pgn_context* c, int32_t net_id, const void* dG, cons
   return pgn_mlp_delta_chain(c, dG, d_raw, mask, mask_rows, m, c->d_chain_w[net_id], c->w_ptr[net_id][8], dz, colsum, layer_mask, stream);
 }
 
-size_t pgn_weight_grad_floats(void) { return pgn_wgrad_flat_floats(); }
+size_t pgn_weight_grad_floats(const pgn_context* c) { return pgn_wgrad_flat_floats_ld(c ? c->view_in : 904); }
+
+int pgn_framecode_backward(pgn_context* c, int32_t net_id, const void* dG, int64_t n_rays, int32_t n_z, const int32_t* cams,
+                           float* g_view_weight, float* g_codes, void* stream) {
+  if (!c || net_id < 0 || net_id > 1 || !dG || !g_view_weight || !g_codes || n_rays < 0 || (n_z != PGN_S && n_z != PGN_T))
+    return fail(PGN_E_INVALID, "pgn_framecode_backward: bad argument");
+  if (c->n_codes <= 0) return fail(PGN_E_STATE, "pgn_framecode_backward: the context has no frame codes");
+  if (!c->have_w[net_id]) return fail(PGN_E_STATE, "pgn_framecode_backward: weights not uploaded");
+  PGN_ON_DEVICE(c);
+  PGN_CUDA(pgn_launch_framecode_backward(dG, n_rays, n_z, cams, c->n_codes, c->d_codes_ext[net_id], c->w_ptr[net_id][10], c->view_in,
+                                         g_view_weight + 904, c->view_in, g_codes, (cudaStream_t)stream));
+  c->launches++;
+  return PGN_OK;
+}
 
 int pgn_mlp_weight_grads(pgn_context* c, int32_t net_id, const void* dz, const void* dG, const void* act, int64_t dump_rows,
                          const void* enc, int64_t m, const float* d_raw, const float* bias_v, float* flat, float* feat_bias,
@@ -417,7 +454,7 @@ int pgn_mlp_weight_grads(pgn_context* c, int32_t net_id, const void* dz, const v
   if (!c->have_w[net_id]) return fail(PGN_E_STATE, "pgn_mlp_weight_grads: weights not uploaded");
   PGN_ON_DEVICE(c);
   PGN_CUDA(pgn_launch_weight_grads(dz, dG, act, dump_rows, enc, m, d_raw, bias_v, c->w_ptr[net_id][9], c->b_ptr[net_id][9],
-                                   c->w_ptr[net_id][10], flat, feat_bias, c->d_tm, c->d_status, c->num_sms, (cudaStream_t)stream));
+                                   c->w_ptr[net_id][10], c->view_in, flat, feat_bias, c->d_tm, c->d_status, c->num_sms, (cudaStream_t)stream));
   c->launches += 3;
   return PGN_OK;
 }
@@ -441,9 +478,9 @@ int pgn_mlp(pgn_context* c, int net_id, const float* enc, int64_t m, float* raw,
     if (rc2) return rc2;
   }
   if (precision == PGN_PRECISION_FP32)
-    PGN_CUDA(pgn_launch_mlp_fp32(c->fp32[net_id], enc, m, raw, c->num_sms, (cudaStream_t)stream));
+    PGN_CUDA(pgn_launch_mlp_fp32(c->fp32[net_id], enc, m, raw, c->num_sms, c->n_codes, (cudaStream_t)stream));
   else if (precision == PGN_PRECISION_BF16)
-    PGN_CUDA(pgn_launch_mlp_bf16(c->bf16[net_id], enc, m, raw, c->d_sc, c->d_status, c->num_sms, (cudaStream_t)stream));
+    PGN_CUDA(pgn_launch_mlp_bf16(c->bf16[net_id], enc, m, raw, c->d_sc, c->d_status, c->num_sms, c->n_codes, (cudaStream_t)stream));
   else return fail(PGN_E_INVALID, "pgn_mlp: bad precision");
   c->launches++;
   return PGN_OK;
@@ -456,7 +493,7 @@ int pgn_composite(pgn_context* c, const pgn_render_inputs* in, const float* raw,
   if (!raw || !z || (s != PGN_S && s != PGN_T)) return fail(PGN_E_INVALID, "pgn_composite: s must be 64 or 80");
   if (!c->have_sc) return fail(PGN_E_STATE, "pgn_composite: scalars not set");
   PGN_ON_DEVICE(c);
-  PGN_CUDA(pgn_launch_composite(make_refs(in), c->d_sc, raw, z, s, rgb_map, disp_map, acc_map, weights, alpha, (cudaStream_t)stream));
+  PGN_CUDA(pgn_launch_composite(make_refs(c, in), c->d_sc, raw, z, s, rgb_map, disp_map, acc_map, weights, alpha, (cudaStream_t)stream));
   c->launches++;
   return PGN_OK;
 }
@@ -468,7 +505,7 @@ int pgn_encode_backward(pgn_context* c, const pgn_render_inputs* in, const float
   if (!z || !g_enc || !d_skts || n_z <= 0) return fail(PGN_E_INVALID, "pgn_encode_backward: bad argument");
   if (!c->have_sc) return fail(PGN_E_STATE, "pgn_encode_backward: scalars not set");
   PGN_ON_DEVICE(c);
-  PGN_CUDA(pgn_launch_encode_backward(make_refs(in), c->d_sc, z, n_z, g_enc, d_skts, (cudaStream_t)stream));
+  PGN_CUDA(pgn_launch_encode_backward(make_refs(c, in), c->d_sc, z, n_z, g_enc, d_skts, (cudaStream_t)stream));
   c->launches++;
   return PGN_OK;
 }
@@ -480,7 +517,7 @@ int pgn_encode_backward_bf16(pgn_context* c, const pgn_render_inputs* in, const 
   if (!z || !g_xp || !g_d || !d_skts || n_z <= 0) return fail(PGN_E_INVALID, "pgn_encode_backward_bf16: bad argument");
   if (!c->have_sc) return fail(PGN_E_STATE, "pgn_encode_backward_bf16: scalars not set");
   PGN_ON_DEVICE(c);
-  PGN_CUDA(pgn_launch_encode_backward_bf16(make_refs(in), c->d_sc, z, n_z, reinterpret_cast<const __nv_bfloat16*>(g_xp),
+  PGN_CUDA(pgn_launch_encode_backward_bf16(make_refs(c, in), c->d_sc, z, n_z, reinterpret_cast<const __nv_bfloat16*>(g_xp),
                                            reinterpret_cast<const __nv_bfloat16*>(g_d), d_skts, (cudaStream_t)stream));
   c->launches++;
   return PGN_OK;
@@ -493,7 +530,7 @@ int pgn_composite_backward(pgn_context* c, const pgn_render_inputs* in, const fl
   if (!raw || !z || !g_rgb || !d_raw || (s != PGN_S && s != PGN_T)) return fail(PGN_E_INVALID, "pgn_composite_backward: bad argument");
   if (!c->have_sc) return fail(PGN_E_STATE, "pgn_composite_backward: scalars not set");
   PGN_ON_DEVICE(c);
-  PGN_CUDA(pgn_launch_composite_backward(make_refs(in), c->d_sc, raw, z, s, g_rgb, g_acc, noise, d_raw, (cudaStream_t)stream));
+  PGN_CUDA(pgn_launch_composite_backward(make_refs(c, in), c->d_sc, raw, z, s, g_rgb, g_acc, noise, d_raw, (cudaStream_t)stream));
   c->launches++;
   return PGN_OK;
 }

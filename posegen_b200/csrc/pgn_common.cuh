@@ -39,7 +39,17 @@ struct PgnRayRefs {
   const float*   cyls;
   long long      cyls_stride;
   const int*     pose_idx;
+  const int*     cams;          // optional [n] frame-code index per ray (Optcodes, core/networks/embedding.py:4-46); NULL or
+                                // an index outside [0, n_codes) selects the mean code (the reference's eval rule for idx < 0)
+  int            n_codes;       // rows of the per-net frame-code tables (0: the model has no frame codes)
 };
+
+// row of the frame-code tables for ray i: the code of its camera, or row n_codes = the mean code
+__device__ __forceinline__ int pgn_ray_code_row(const PgnRayRefs& r, long long i) {
+  if (!r.cams) return r.n_codes;
+  const int c = r.cams[i];
+  return (c < 0 || c >= r.n_codes) ? r.n_codes : c;
+}
 
 struct PgnOutputs {
   float *rgb_map, *disp_map, *acc_map, *alpha, *rgb0, *disp0, *acc0, *alpha0;

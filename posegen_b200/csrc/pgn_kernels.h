@@ -24,6 +24,7 @@ struct PgnFp32Net {
   const float* b_alpha;
   const float* w_rgb;    // [3][128]
   const float* b_rgb;
+  const float* codes_ext;   // frame codes [n_codes + 1][16] (last row = mean code) or NULL: the 16 extra input columns of views_linears.0
 };
 
 size_t pgn_fp32_smem_bytes();
@@ -31,7 +32,7 @@ cudaError_t pgn_launch_render_fp32(const PgnRayRefs& rays, const PgnOutputs& out
                                    const PgnFp32Net& nf, const PgnScalars* sc_dev, const float* near_far,
                                    int num_sms, cudaStream_t stream);
 cudaError_t pgn_launch_mlp_fp32(const PgnFp32Net& net, const float* enc, long long m, float* raw,
-                                int num_sms, cudaStream_t stream);
+                                int num_sms, int n_codes, cudaStream_t stream);
 
 // ---- bf16 tcgen05 engine ---------------------------------------------------
 // The packed weight stream of one net: UMMA K-major slabs in consumption order
@@ -43,6 +44,8 @@ struct PgnBf16Net {
   const float* w_rgb;             // [3][128]
   const float* b_alpha;           // [1]
   const float* b_rgb;             // [3]
+  const float* fc_table;          // [n_codes + 1][128] = W_v[:, 904:920] codes^T (last row: mean code) or NULL (no frame codes):
+                                  // a per-ray additive term of the view layer's pre-activation
 };
 
 // Training forward: post-ReLU activations of the 8 trunk layers (256 columns) and of the view layer (128), bf16,
@@ -64,12 +67,17 @@ long long pgn_bf16_dump_rows(long long n_rays, int samples_per_ray);
 size_t pgn_bf16_wstream_elems();
 // pack one net (device fp32 nn.Linear tensors) into wstream/bias; runs on `stream`
 cudaError_t pgn_pack_bf16_net(const float* const* w_dev, const float* const* b_dev, __nv_bfloat16* wstream,
-                              float* bias, float* w_alpha, float* w_rgb, float* fold_tmp, cudaStream_t stream);
+                              float* bias, float* w_alpha, float* w_rgb, float* fold_tmp, int view_ld, cudaStream_t stream);
+// frame codes (Optcodes): codes_ext [n+1][16] (rows 0..n-1 given, row n <- mean) and fc_table [n+1][128] = codes_ext W_v[:, 904:920]^T
+cudaError_t pgn_launch_framecode_tables(float* codes_ext, int n_codes, const float* w_view, int view_ld, float* fc_table, cudaStream_t stream);
+// backward of the frame-code term: dG bf16 [n_rays * nz][128] -> g_wvc [128][16] (+=), g_codes [n_codes][16] (+=)
+cudaError_t pgn_launch_framecode_backward(const void* dG, long long n_rays, int nz, const int* cams, int n_codes, const float* codes_ext,
+                                          const float* w_view, int view_ld, float* g_wvc, int g_wvc_ld, float* g_codes, cudaStream_t stream);
 cudaError_t pgn_launch_render_bf16(const PgnRayRefs& rays, const PgnOutputs& out, const PgnBf16Net& nc,
                                    const PgnBf16Net& nf, const PgnScalars* sc_dev, const float* near_far,
                                    int* status, unsigned long long* prof, const PgnActDump* dump, int num_sms, cudaStream_t stream);
 cudaError_t pgn_launch_mlp_bf16(const PgnBf16Net& net, const float* enc, long long m, float* raw,
-                                const PgnScalars* sc_dev, int* status, int num_sms, cudaStream_t stream);
+                                const PgnScalars* sc_dev, int* status, int num_sms, int n_codes, cudaStream_t stream);
 
 // ---- stage kernels ---------------------------------------------------------
 cudaError_t pgn_launch_near_far(const PgnRayRefs& rays, long long chunk, float* near_far, cudaStream_t stream);
@@ -124,8 +132,9 @@ cudaError_t pgn_launch_near_far_chunks(const PgnRayRefs& rays, const long long* 
 size_t pgn_wgrad_flat_floats();
 cudaError_t pgn_launch_weight_grads(const void* dz, const void* dG, const void* act, long long dump_rows, const void* enc,
                                     long long m, const float* d_raw, const float* bias_v, const float* w_f, const float* b_f,
-                                    const float* w_v, float* flat, float* feat_bias, float* tm_scratch, int* status, int num_sms,
+                                    const float* w_v, int view_ld, float* flat, float* feat_bias, float* tm_scratch, int* status, int num_sms,
                                     cudaStream_t stream);
+size_t pgn_wgrad_flat_floats_ld(int view_ld);
 cudaError_t pgn_launch_wgrad_single(const void* A, int lda, int Ma, const void* B, int ldb, int Nb, long long m, float* out, int ld_out,
                                     int n_ctas, int* status, cudaStream_t stream);
 

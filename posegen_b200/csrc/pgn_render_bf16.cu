@@ -258,7 +258,10 @@ __device__ __forceinline__ void stg256(void* p, const uint32_t (&v)[8]) {
 template <int MODE>
 __device__ __forceinline__ void epilogue(Smem& sm, uint32_t tmem_acc, uint32_t act_saddr, int slot, const float* __restrict__ w_alpha,
                                          const float* __restrict__ w_rgb, int warp, int lane, float& sig_keep,
-                                         uint4* dump = nullptr, uint4* dump_mask = nullptr, uint2* dump_vmask = nullptr) {
+                                         uint4* dump = nullptr, uint4* dump_mask = nullptr, uint2* dump_vmask = nullptr,
+                                         const float* __restrict__ fc = nullptr) {
+  // fc (view layer only): this row's frame-code term [128] (Optcodes: W_v[:, 904:920] code[cam], fp32), added to the
+  // pre-activation before the ReLU; nullptr when the model has no frame codes
   // dump (training forward only): this thread's row of the layer's row-major activation dump ([rows, 256 | 128] bf16);
   // a thread owns 128 (view layer: 64) consecutive columns, i.e. 256 (128) contiguous bytes of its row
   const int q = warp & 3, half = warp >> 2;
@@ -278,7 +281,15 @@ __device__ __forceinline__ void epilogue(Smem& sm, uint32_t tmem_acc, uint32_t a
     tmem_ld_wait();
     if (b + 1 < kBatches) tmem_ld_32x16(taddr + (uint32_t)(b + 1) * 16, v[(b + 1) & 1]);
     const int c0 = col0 + b * 16;
-    const uint32_t* vb = v[b & 1];
+    uint32_t* vb = v[b & 1];
+    if (MODE == 2 && fc) {
+#pragma unroll
+      for (int i4 = 0; i4 < 4; ++i4) {
+        const float4 f = __ldg(reinterpret_cast<const float4*>(fc + c0) + i4);
+        vb[4 * i4] = __float_as_uint(__uint_as_float(vb[4 * i4]) + f.x); vb[4 * i4 + 1] = __float_as_uint(__uint_as_float(vb[4 * i4 + 1]) + f.y);
+        vb[4 * i4 + 2] = __float_as_uint(__uint_as_float(vb[4 * i4 + 2]) + f.z); vb[4 * i4 + 3] = __float_as_uint(__uint_as_float(vb[4 * i4 + 3]) + f.w);
+      }
+    }
     if (MODE == 1) {
 #pragma unroll
       for (int i4 = 0; i4 < 4; ++i4) {
@@ -771,6 +782,7 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
 
     // ---- POST(job): drain the accumulator (epilogue)
     float sig_keep = 0.f;             // this thread's sigma-head partial, carried from L7's epilogue to V's
+    int fc_row = rays.n_codes;        // frame-code table row of this thread's ray (set before the next tile's row context replaces rc)
     auto post = [&](int L, const TileCtx& tc) -> bool {
       const PgnBf16Net& net = (kStage || tc.pass == 0) ? net_c : net_f;
       { PROF_T0(); const bool okw = mbar_wait_s(acc_full_a, accs & 1, status, 303); if (timed) { PROF_ADD(9); PROF_ADD(16 + L); } if (!okw) return false; }
@@ -800,7 +812,8 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
         if (L < 8) mptr = base + (size_t)272 * (size_t)m + ((size_t)L * (size_t)m + (size_t)grow) * 2 + (gwarp >> 2);
       }
       { PROF_T0();
-        if (L == 8) epilogue<2>(sm, tmem_acc, act_saddr, s, net.w_alpha, net.w_rgb, gwarp, lane, sig_keep, dptr, mptr, vptr);
+        if (L == 8) epilogue<2>(sm, tmem_acc, act_saddr, s, net.w_alpha, net.w_rgb, gwarp, lane, sig_keep, dptr, mptr, vptr,
+                                net.fc_table ? net.fc_table + (size_t)fc_row * 128 : nullptr);
         else if (L == 7) epilogue<1>(sm, tmem_acc, act_saddr, s, net.w_alpha, net.w_rgb, gwarp, lane, sig_keep, dptr, mptr, vptr);
         else epilogue<0>(sm, tmem_acc, act_saddr, s, net.w_alpha, net.w_rgb, gwarp, lane, sig_keep, dptr, mptr, vptr);
         compute_arrive(act_ready_a, lane); if (timed) PROF_ADD(8); }
@@ -881,6 +894,8 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
         for (int L = 0; L < 9; ++L) {
           { PROF_T0(); const bool okp = pre(L, tc); if (timed && (L == 0 || L == 5 || L == 8)) PROF_ADD(L == 0 ? 25 : (L == 5 ? 26 : 27)); if (!okp) goto done; }
           if (!kStage && pending && L >= 1 && L <= 3) { PROF_T0(); composite_stage(prev, L); if (timed) PROF_ADD(11); }
+          if (!kStage && L == 8 && net_c.fc_table)      // this row's ray -> frame-code row (while rc still describes THIS tile)
+            fc_row = (tc.nr > 0) ? pgn_ray_code_row(rays, tc.ray0 + min(tc.tile_ray0 + rc.tr, tc.nr - 1)) : rays.n_codes;
           if (!kStage && L == 8 && (k + 1 < kTiles || i + 1 < n_slot)) {
             // the view layer's last chunks are still in the tensor core: build the next tile's tables now
             PROF_T0();
@@ -923,17 +938,17 @@ done:
 
 // ------------------------------------------------------------------ weight packing
 // wsrc[l]: device fp32 nn.Linear weights in the include/posegen_b200.h order.
-__global__ void pgn_fold_view_kernel(const float* __restrict__ w_view /*[128][904]*/, const float* __restrict__ w_feat /*[256][256]*/,
+__global__ void pgn_fold_view_kernel(const float* __restrict__ w_view /*[128][view_ld]*/, const float* __restrict__ w_feat /*[256][256]*/,
                                      const float* __restrict__ b_view, const float* __restrict__ b_feat,
-                                     float* __restrict__ fold /*[128][256] + [128]*/) {
+                                     float* __restrict__ fold /*[128][256] + [128]*/, int view_ld) {
   // fold[n][k] = sum_m w_view[n][m] * w_feat[m][k];  fold_b[n] = b_view[n] + sum_m w_view[n][m] * b_feat[m]
   const int n = blockIdx.x, k = threadIdx.x;
   float acc = 0.f;
-  for (int m = 0; m < 256; ++m) acc = fmaf(w_view[n * 904 + m], w_feat[m * 256 + k], acc);
+  for (int m = 0; m < 256; ++m) acc = fmaf(w_view[n * view_ld + m], w_feat[m * 256 + k], acc);
   fold[n * 256 + k] = acc;
   if (k == 0) {
     float b = b_view[n];
-    for (int m = 0; m < 256; ++m) b = fmaf(w_view[n * 904 + m], b_feat[m], b);
+    for (int m = 0; m < 256; ++m) b = fmaf(w_view[n * view_ld + m], b_feat[m], b);
     fold[128 * 256 + n] = b;
   }
 }
@@ -941,7 +956,7 @@ __global__ void pgn_fold_view_kernel(const float* __restrict__ w_view /*[128][90
 struct PackPtrs { const float* w[12]; const float* b[12]; };
 
 __global__ void pgn_pack_wstream_kernel(PackPtrs p, const float* __restrict__ fold, __nv_bfloat16* __restrict__ wstream,
-                                        float* __restrict__ bias, float* __restrict__ w_alpha, float* __restrict__ w_rgb) {
+                                        float* __restrict__ bias, float* __restrict__ w_alpha, float* __restrict__ w_rgb, int view_ld) {
   const size_t total = pgn_wstream_elems();
   for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
     // locate layer
@@ -982,7 +997,7 @@ __global__ void pgn_pack_wstream_kernel(PackPtrs p, const float* __restrict__ fo
     }
     else if (L == 8) {
       if (kp < 256) v = fold[n * 256 + kp];
-      else { const int rc = pgn_dperm_refcol(kp - 256); v = rc >= 0 ? p.w[10][(size_t)n * 904 + 256 + (rc - 432)] : 0.f; }
+      else { const int rc = pgn_dperm_refcol(kp - 256); v = rc >= 0 ? p.w[10][(size_t)n * view_ld + 256 + (rc - 432)] : 0.f; }
     } else v = p.w[L][(size_t)n * 256 + kp];
     wstream[idx] = __float2bfloat16_rn(v);
   }
@@ -1008,11 +1023,11 @@ long long pgn_bf16_dump_rows(long long n_rays, int samples_per_ray) {
 }
 
 cudaError_t pgn_pack_bf16_net(const float* const* w_dev, const float* const* b_dev, __nv_bfloat16* wstream,
-                              float* bias, float* w_alpha, float* w_rgb, float* fold_tmp, cudaStream_t stream) {
+                              float* bias, float* w_alpha, float* w_rgb, float* fold_tmp, int view_ld, cudaStream_t stream) {
   PackPtrs p;
   for (int i = 0; i < 12; ++i) { p.w[i] = w_dev[i]; p.b[i] = b_dev[i]; }
-  pgn_fold_view_kernel<<<128, 256, 0, stream>>>(w_dev[10], w_dev[9], b_dev[10], b_dev[9], fold_tmp);
-  pgn_pack_wstream_kernel<<<148 * 4, 256, 0, stream>>>(p, fold_tmp, wstream, bias, w_alpha, w_rgb);
+  pgn_fold_view_kernel<<<128, 256, 0, stream>>>(w_dev[10], w_dev[9], b_dev[10], b_dev[9], fold_tmp, view_ld);
+  pgn_pack_wstream_kernel<<<148 * 4, 256, 0, stream>>>(p, fold_tmp, wstream, bias, w_alpha, w_rgb, view_ld);
   return cudaGetLastError();
 }
 
@@ -1059,13 +1074,14 @@ cudaError_t pgn_launch_render_bf16(const PgnRayRefs& rays, const PgnOutputs& out
 }
 
 cudaError_t pgn_launch_mlp_bf16(const PgnBf16Net& net, const float* enc, long long m, float* raw,
-                                const PgnScalars* sc_dev, int* status, int num_sms, cudaStream_t stream) {
+                                const PgnScalars* sc_dev, int* status, int num_sms, int n_codes, cudaStream_t stream) {
   cudaError_t e = configure_bf16();
   if (e != cudaSuccess) return e;
   const long long n_tiles = (m + kTM - 1) / kTM;
   if (n_tiles == 0) return cudaSuccess;
   const int grid = 2 * (int)min((long long)(num_sms / 2), (n_tiles + 1) / 2);
   PgnRayRefs rays{};
+  rays.n_codes = n_codes;          // explicit encodings carry no camera index: a frame-code model uses its mean code
   PgnOutputs out{};
   pgn_render_bf16_kernel<true, false, 0><<<grid, kThreads, sizeof(Smem) + 1024, stream>>>(rays, out, net, net, sc_dev, nullptr,
                                                                                               enc, m, raw, status, nullptr, PgnActDump{});

@@ -34,6 +34,7 @@ struct Smem {
   float scratch[kRPG][128];
   float ray_o[kRPG][3], ray_d[kRPG][3], dnorm[kRPG];
   float part[kTM * 4];                   // per-row network output (rgb_raw, sigma_raw)
+  int code_row[kRPG];                    // frame-code table row per ray of the group (Optcodes)
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -44,7 +45,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
 // A-operand sources -----------------------------------------------------------
-enum ASrc { A_FROM_H = 0, A_ENC_P = 1, A_ENC_D = 2, A_GLOBAL = 3 };
+enum ASrc { A_FROM_H = 0, A_ENC_P = 1, A_ENC_D = 2, A_GLOBAL = 3, A_FRAMECODE = 4 };
 
 // value of encoded column `col` (reference channel order) for tile row `row`
 __device__ __forceinline__ float enc_value(const Smem& sm, int row, int ray_local, int col) {
@@ -68,7 +69,8 @@ struct Seg { int src; int k; int col0; };
 template <int N>   // N = 256 or 128
 __device__ void dense_layer(Smem& sm, const Seg* segs, int nseg, const float* __restrict__ Wt,
                             const float* __restrict__ bias, bool relu, const float* h_in, float* h_out,
-                            const int* row_ray, const float* __restrict__ a_global, int a_ld, int rows_valid) {
+                            const int* row_ray, const float* __restrict__ a_global, int a_ld, int rows_valid,
+                            const float* __restrict__ codes_ext = nullptr) {
   constexpr int NPT = N / 32;                 // output columns per thread
   const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
   float acc[8][NPT];
@@ -114,6 +116,7 @@ __device__ void dense_layer(Smem& sm, const Seg* segs, int nseg, const float* __
         float v = 0.f;
         if (src == A_ENC_P || src == A_ENC_D) v = enc_value(sm, row, row_ray[row], col);
         else if (src == A_GLOBAL) v = (row < rows_valid) ? a_global[(size_t)row * a_ld + col] : 0.f;
+        else if (src == A_FRAMECODE) v = codes_ext[sm.code_row[row_ray[row]] * 16 + col];     // framecodes(frame_idxs), nerf.py:122-124
         else v = h_in[col * kHStride + row];
         sm.As[buf][kk * kTM + row] = v;
       }
@@ -219,9 +222,9 @@ __device__ void mlp_tile(Smem& sm, const PgnFp32Net& net, const int* row_ray, bo
     dense_layer<256>(sm, s, 1, net.wt[9], net.b[9], false, cur, nxt, row_ray, a_global, PGN_ENC, rows_valid);
     float* t = cur; cur = nxt; nxt = t;
   }
-  {  // views_linears.0 : [feature(256) | input_views(648)] -> 128, ReLU
-    Seg s[2] = {{A_FROM_H, 256, 0}, {srcD, PGN_ENC_D, PGN_ENC_P}};
-    dense_layer<128>(sm, s, 2, net.wt[10], net.b[10], true, cur, nxt, row_ray, a_global, PGN_ENC, rows_valid);
+  {  // views_linears.0 : [feature(256) | input_views(648) | frame code(16, optional)] -> 128, ReLU
+    Seg s[3] = {{A_FROM_H, 256, 0}, {srcD, PGN_ENC_D, PGN_ENC_P}, {A_FRAMECODE, 16, 0}};
+    dense_layer<128>(sm, s, net.codes_ext ? 3 : 2, net.wt[10], net.b[10], true, cur, nxt, row_ray, a_global, PGN_ENC, rows_valid, net.codes_ext);
     float* t = cur; cur = nxt; nxt = t;
   }
   small_head<3>(sm, cur, 128, net.w_rgb, net.b_rgb, sm.part, 0);
@@ -276,6 +279,7 @@ pgn_render_fp32_kernel(PgnRayRefs rays, PgnOutputs out, PgnFp32Net net_c, PgnFp3
         sm.ray_d[rl][a] = rays.ray_batch[(ray0 + rl) * 11 + 3 + a];
       } else { sm.ray_o[rl][a] = 0.f; sm.ray_d[rl][a] = (a == 2) ? 1.f : 0.f; }
     }
+    if (tid < kRPG) sm.code_row[tid] = tid < nr ? pgn_ray_code_row(rays, ray0 + tid) : rays.n_codes;
     __syncthreads();
     if (tid < kRPG) {
       const float* d = sm.ray_d[tid];
@@ -362,7 +366,7 @@ pgn_render_fp32_kernel(PgnRayRefs rays, PgnOutputs out, PgnFp32Net net_c, PgnFp3
 // stage kernel: NeRF.forward on explicit encodings (pgn_mlp, fp32 engine)
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads, 1)
-pgn_mlp_fp32_kernel(PgnFp32Net net, const float* __restrict__ enc, long long m, float* __restrict__ raw) {
+pgn_mlp_fp32_kernel(PgnFp32Net net, const float* __restrict__ enc, long long m, float* __restrict__ raw, int n_codes) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
   __shared__ int row_ray[kTM];
@@ -371,6 +375,7 @@ pgn_mlp_fp32_kernel(PgnFp32Net net, const float* __restrict__ enc, long long m, 
     const long long row0 = t * kTM;
     const int rows_valid = (int)min((long long)kTM, m - row0);
     if (threadIdx.x < kTM) row_ray[threadIdx.x] = 0;
+    if (threadIdx.x < kRPG) sm.code_row[threadIdx.x] = n_codes;      // explicit encodings carry no camera index: mean code
     __syncthreads();
     mlp_tile(sm, net, row_ray, true, enc + row0 * PGN_ENC, rows_valid);
     if (threadIdx.x < rows_valid) {
@@ -402,7 +407,7 @@ cudaError_t pgn_launch_render_fp32(const PgnRayRefs& rays, const PgnOutputs& out
 }
 
 cudaError_t pgn_launch_mlp_fp32(const PgnFp32Net& net, const float* enc, long long m, float* raw,
-                                int num_sms, cudaStream_t stream) {
+                                int num_sms, int n_codes, cudaStream_t stream) {
   static PgnPerDeviceOnce configured;
   if (configured.need()) {
     cudaError_t e = cudaFuncSetAttribute(pgn_mlp_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
@@ -412,6 +417,6 @@ cudaError_t pgn_launch_mlp_fp32(const PgnFp32Net& net, const float* enc, long lo
   const long long n_tiles = (m + kTM - 1) / kTM;
   if (n_tiles == 0) return cudaSuccess;
   const int grid = (int)min((long long)num_sms, n_tiles);
-  pgn_mlp_fp32_kernel<<<grid, kThreads, sizeof(Smem), stream>>>(net, enc, m, raw);
+  pgn_mlp_fp32_kernel<<<grid, kThreads, sizeof(Smem), stream>>>(net, enc, m, raw, n_codes);
   return cudaGetLastError();
 }

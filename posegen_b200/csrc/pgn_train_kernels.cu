@@ -223,3 +223,105 @@ cudaError_t pgn_launch_mlp_delta(void* dh, int has_in, const void* act, long lon
   if (C == 128 && nrs == 3) return launch_delta<128, 3>(dh, has_in, act, m, rs, rs_stride, wr, colsum, wsum, num_sms, stream);
   return cudaErrorInvalidValue;
 }
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Optcodes frame codes (core/networks/embedding.py:4-46; core/networks/nerf.py:104-131: views_linears.0 reads
+// [feature | input_views | framecodes(frame_idx)], 16 extra input columns).  A ray's code is constant along the ray,
+// so its contribution W_v[:, 904:920] code[cam] is a per-ray additive term of the view layer's pre-activation:
+//   codes_ext[n]   <- mean over the n codes (the reference's eval rule for idx < 0, embedding.py:23-24)
+//   fc_table[i][c] <- sum_k W_v[c][904 + k] codes_ext[i][k]            (fp32; the tensor-core tier adds it in its epilogue)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void pgn_framecode_tables_kernel(float* __restrict__ codes_ext, int n, const float* __restrict__ w_view, int view_ld,
+                                            float* __restrict__ fc_table) {
+  __shared__ float code[16];
+  const int i = blockIdx.x;                 // 0 .. n (row n: the mean code)
+  if (threadIdx.x < 16) {
+    float v;
+    if (i < n) v = codes_ext[i * 16 + threadIdx.x];
+    else {
+      float sacc = 0.f;
+      for (int r = 0; r < n; ++r) sacc += codes_ext[r * 16 + threadIdx.x];
+      v = sacc / (float)n;
+      codes_ext[n * 16 + threadIdx.x] = v;
+    }
+    code[threadIdx.x] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const float* w = w_view + (size_t)threadIdx.x * view_ld + (view_ld - 16);
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc = fmaf(w[k], code[k], acc);
+    fc_table[(size_t)i * 128 + threadIdx.x] = acc;
+  }
+}
+
+cudaError_t pgn_launch_framecode_tables(float* codes_ext, int n_codes, const float* w_view, int view_ld, float* fc_table, cudaStream_t stream) {
+  if (n_codes <= 0) return cudaSuccess;
+  pgn_framecode_tables_kernel<<<n_codes + 1, 128, 0, stream>>>(codes_ext, n_codes, w_view, view_ld, fc_table);
+  return cudaGetLastError();
+}
+
+// backward: with dGr[ray] = sum over the ray's samples of dG (the code is shared by them)
+//   g_wvc[c][k]        += dGr[ray][c] code[row(ray)][k]        (the 16 extra columns of views_linears.0.weight)
+//   g_codes[cam][k]    += sum_c dGr[ray][c] W_v[c][904 + k]    (rays with a real camera index; in eval the mean row gets none)
+// one warp per ray: lane owns 4 of the 128 columns.
+__global__ void __launch_bounds__(256) pgn_framecode_backward_kernel(const uint2* __restrict__ dG, long long n_rays, int nz,
+                                                                     const int* __restrict__ cams, int n_codes,
+                                                                     const float* __restrict__ codes_ext, const float* __restrict__ w_view,
+                                                                     int view_ld, float* __restrict__ g_wvc, int g_ld, float* __restrict__ g_codes) {
+  __shared__ float s_w[128 * 16];            // block-local partial of g_wvc
+  for (int i = threadIdx.x; i < 128 * 16; i += blockDim.x) s_w[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  float wv[4][16];                            // this lane's 4 rows of W_v[:, 904:920]
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int k = 0; k < 16; ++k) wv[c][k] = __ldg(w_view + (size_t)(lane * 4 + c) * view_ld + (view_ld - 16) + k);
+  for (long long ray = (long long)blockIdx.x * 8 + wib; ray < n_rays; ray += (long long)gridDim.x * 8) {
+    float g[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int sidx = 0; sidx < nz; ++sidx) {
+      const uint2 v = __ldg(dG + (ray * nz + sidx) * 32 + lane);      // 4 bf16 = this lane's columns
+      g[0] += __uint_as_float(v.x << 16); g[1] += __uint_as_float(v.x & 0xffff0000u);
+      g[2] += __uint_as_float(v.y << 16); g[3] += __uint_as_float(v.y & 0xffff0000u);
+    }
+    int cam = cams ? cams[ray] : -1;
+    const int row = (cam < 0 || cam >= n_codes) ? n_codes : cam;
+    float gc[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const float ck = __ldg(codes_ext + row * 16 + k);
+      float acc = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        atomicAdd(&s_w[(lane * 4 + c) * 16 + k], g[c] * ck);
+        acc = fmaf(g[c], wv[c][k], acc);
+      }
+      gc[k] = acc;
+    }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) gc[k] += __shfl_xor_sync(0xffffffffu, gc[k], off);
+    }
+    if (row < n_codes && lane < 16) {
+      float mine = 0.f;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) if (k == lane) mine = gc[k];
+      atomicAdd(g_codes + row * 16 + lane, mine);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 128 * 16; i += blockDim.x) atomicAdd(g_wvc + (size_t)(i >> 4) * g_ld + (i & 15), s_w[i]);
+}
+
+cudaError_t pgn_launch_framecode_backward(const void* dG, long long n_rays, int nz, const int* cams, int n_codes, const float* codes_ext,
+                                          const float* w_view, int view_ld, float* g_wvc, int g_wvc_ld, float* g_codes, cudaStream_t stream) {
+  if (n_rays <= 0 || n_codes <= 0) return cudaSuccess;
+  const long long blocks = (n_rays + 7) / 8;
+  pgn_framecode_backward_kernel<<<(unsigned)(blocks < 148 * 2 ? blocks : 148 * 2), 256, 0, stream>>>(
+      reinterpret_cast<const uint2*>(dG), n_rays, nz, cams, n_codes, codes_ext, w_view, view_ld, g_wvc, g_wvc_ld, g_codes);
+  return cudaGetLastError();
+}

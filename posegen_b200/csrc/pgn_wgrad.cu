@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(256) pgn_weighted_colsum_kernel(const __nv_bfl
 __global__ void __launch_bounds__(256) pgn_view_fold_grads_kernel(const float* __restrict__ T, const float* __restrict__ bv,
                                                                   const float* __restrict__ w_f, const float* __restrict__ b_f,
                                                                   const float* __restrict__ w_v, float* __restrict__ g_views,
-                                                                  float* __restrict__ g_feat_w, float* __restrict__ g_feat_b) {
+                                                                  float* __restrict__ g_feat_w, float* __restrict__ g_feat_b, int view_ld) {
   const int t = threadIdx.x;
   if (blockIdx.x < 128) {
     // g_views[n][c] = sum_k T[n][k] W_f[c][k] + bv[n] b_f[c]; this block: row n, thread: column c
@@ -232,12 +232,12 @@ __global__ void __launch_bounds__(256) pgn_view_fold_grads_kernel(const float* _
       acc = fmaf(trow[4 * k4], w.x, acc); acc = fmaf(trow[4 * k4 + 1], w.y, acc);
       acc = fmaf(trow[4 * k4 + 2], w.z, acc); acc = fmaf(trow[4 * k4 + 3], w.w, acc);
     }
-    g_views[(size_t)n * 904 + t] = fmaf(bv[n], b_f[t], acc);
+    g_views[(size_t)n * view_ld + t] = fmaf(bv[n], b_f[t], acc);
   } else {
     // g_feature.weight[j][c] = sum_n W_v[n][j] T[n][c]; this block: row j, thread: column c
     const int j = blockIdx.x - 128;
     __shared__ float wcol[128];
-    if (t < 128) wcol[t] = w_v[(size_t)t * 904 + j];
+    if (t < 128) wcol[t] = w_v[(size_t)t * view_ld + j];
     __syncthreads();
     float acc = 0.f;
 #pragma unroll 8
@@ -285,11 +285,12 @@ static cudaError_t make_map(CUtensorMap* map, const void* base, long long cols, 
 static const int kW_out[12] = {256, 256, 256, 256, 256, 256, 256, 256, 1, 256, 128, 3};
 static const int kW_in[12] = {432, 256, 256, 256, 256, 688, 256, 256, 256, 256, 904, 128};
 
-size_t pgn_wgrad_flat_floats() {
+size_t pgn_wgrad_flat_floats_ld(int view_ld) {
   size_t t = 0;
-  for (int i = 0; i < 12; ++i) t += (size_t)kW_out[i] * kW_in[i];
+  for (int i = 0; i < 12; ++i) t += (size_t)kW_out[i] * (i == 10 ? view_ld : kW_in[i]);
   return t;
 }
+size_t pgn_wgrad_flat_floats() { return pgn_wgrad_flat_floats_ld(904); }
 
 static cudaError_t launch_units(Params& p, int n, long long m, int num_sms, int* status, cudaStream_t stream) {
   p.n_units = n;
@@ -334,11 +335,11 @@ static cudaError_t launch_units(Params& p, int n, long long m, int num_sms, int*
 
 cudaError_t pgn_launch_weight_grads(const void* dz_, const void* dG_, const void* act_, long long dump_rows, const void* enc_,
                                     long long m, const float* d_raw, const float* bias_v, const float* w_f, const float* b_f,
-                                    const float* w_v, float* flat, float* feat_bias, float* tm_scratch, int* status, int num_sms,
+                                    const float* w_v, int view_ld, float* flat, float* feat_bias, float* tm_scratch, int* status, int num_sms,
                                     cudaStream_t stream) {
   const __nv_bfloat16* act = reinterpret_cast<const __nv_bfloat16*>(act_);
   size_t off[12], o = 0;
-  for (int i = 0; i < 12; ++i) { off[i] = o; o += (size_t)kW_out[i] * kW_in[i]; }
+  for (int i = 0; i < 12; ++i) { off[i] = o; o += (size_t)kW_out[i] * (i == 10 ? view_ld : kW_in[i]); }
   cudaError_t e = cudaMemsetAsync(flat, 0, o * sizeof(float), stream);
   if (e != cudaSuccess) return e;
   e = cudaMemsetAsync(tm_scratch, 0, 128 * 256 * sizeof(float), stream);
@@ -369,15 +370,15 @@ cudaError_t pgn_launch_weight_grads(const void* dz_, const void* dG_, const void
   }
   // views_linears.0: dG^T [h7 -> T scratch | d_emb (648 = 256 + 256 + 136 columns)]
   add(kDg, 0, 128, kAct, 7, 0, 256, tm_scratch, 256);
-  add(kDg, 0, 128, kEnc, 0, 432, 256, flat + off[10] + 256, 904);
-  add(kDg, 0, 128, kEnc, 0, 688, 256, flat + off[10] + 512, 904);
-  add(kDg, 0, 128, kEnc, 0, 944, 136, flat + off[10] + 768, 904);
+  add(kDg, 0, 128, kEnc, 0, 432, 256, flat + off[10] + 256, view_ld);
+  add(kDg, 0, 128, kEnc, 0, 688, 256, flat + off[10] + 512, view_ld);
+  add(kDg, 0, 128, kEnc, 0, 944, 136, flat + off[10] + 768, view_ld);      // (frame-code columns 904..919: pgn_framecode_backward)
   if ((e = launch_units(p, n, m, num_sms, status, stream)) != cudaSuccess) return e;
   // alpha_linear.weight = d_sigma^T h7
   pgn_weighted_colsum_kernel<<<num_sms * 2, 256, 0, stream>>>(act + (size_t)7 * dump_rows * 256, m, d_raw + 3, 4, flat + off[8]);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  pgn_view_fold_grads_kernel<<<128 + 256, 256, 0, stream>>>(tm_scratch, bias_v, w_f, b_f, w_v, flat + off[10], flat + off[9], feat_bias);
+  pgn_view_fold_grads_kernel<<<128 + 256, 256, 0, stream>>>(tm_scratch, bias_v, w_f, b_f, w_v, flat + off[10], flat + off[9], feat_bias, view_ld);
   return cudaGetLastError();
 }
 

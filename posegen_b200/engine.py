@@ -33,14 +33,16 @@ def _check_f32_cuda(t: torch.Tensor, name: str):
 class Engine:
     """One renderer context on one CUDA device."""
 
-    def __init__(self, device: Optional[torch.device] = None):
+    def __init__(self, device: Optional[torch.device] = None, n_framecodes: int = 0):
+        """n_framecodes > 0: the nets carry Optcodes frame codes (views_linears.0 reads 920 inputs, `cams` selects a code)."""
         self.lib = _lib.load()
+        self.n_framecodes = int(n_framecodes)
         if not torch.cuda.is_available():
             raise RuntimeError("posegen_b200 requires a CUDA device (no CPU fallback)")
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         if self.device.index is None:
             self.device = torch.device("cuda", torch.cuda.current_device())
-        cfg = _lib.Config(J, S, I, 7, 4, 8, 256, 4, self.device.index)
+        cfg = _lib.Config(J, S, I, 7, 4, 8, 256, 4, self.device.index, self.n_framecodes, 16 if self.n_framecodes else 0)
         handle = C.c_void_p()
         _lib.check(self.lib.pgn_create(C.byref(cfg), C.byref(handle)))
         self.handle = handle
@@ -69,7 +71,7 @@ class Engine:
         for k, name in enumerate(LINEAR_ORDER):
             for kind, arr in (("weight", w.weight), ("bias", w.bias)):
                 t = torch.as_tensor(state[f"{name}.{kind}"]).detach()
-                exp = _SHAPES[name] if kind == "weight" else (_SHAPES[name][0],)
+                exp = self._shape(name) if kind == "weight" else (_SHAPES[name][0],)
                 if tuple(t.shape) != exp:
                     raise ValueError(f"{name}.{kind}: expected shape {exp}, got {tuple(t.shape)}")
                 t = t.to(dtype=torch.float32).contiguous()
@@ -79,10 +81,23 @@ class Engine:
                     t = t.to(self.device) if on_device else t.cpu()
                 keep.append(t)
                 arr[k] = t.data_ptr()
+        if self.n_framecodes:
+            t = torch.as_tensor(state["framecodes.codes.weight"]).detach()
+            if tuple(t.shape) != (self.n_framecodes, 16):
+                raise ValueError(f"framecodes.codes.weight: expected {(self.n_framecodes, 16)}, got {tuple(t.shape)}")
+            t = t.to(dtype=torch.float32).contiguous()
+            t = (t.to(self.device) if on_device else t.cpu()) if t.is_cuda != on_device else t
+            keep.append(t)
+            w.framecodes = t.data_ptr()
         with torch.cuda.device(self.device):
             _lib.check(self.lib.pgn_upload_weights(self.handle, net_id, C.byref(w), 1 if on_device else 0, self._stream()))
             if not on_device:
                 torch.cuda.current_stream(self.device).synchronize()   # host staging must outlive the copies
+
+    def _shape(self, name):
+        """nn.Linear weight shape of layer `name` (views_linears.0 has 16 more inputs with frame codes)."""
+        sh = _SHAPES[name]
+        return (sh[0], sh[1] + 16) if (name == "views_linears.0" and self.n_framecodes) else sh
 
     def set_scalars(self, tau_v: float, tau_d: float, cutoff_v, cutoff_d, density_scale: float = 1.0, rgb_eps: float = 1e-3):
         cv = (C.c_float * J)(*[float(x) for x in cutoff_v])
@@ -144,7 +159,7 @@ class Engine:
         return torch.empty(int(self.lib.pgn_workspace_bytes(self.handle, n_rays)), dtype=torch.uint8, device=dev)
 
     # ------------------------------------------------------------------ inputs
-    def _inputs(self, ray_batch, skts, cyls, pose_idx=None, nanfill_chunk=0, precision="bf16", chunk_starts=None):
+    def _inputs(self, ray_batch, skts, cyls, pose_idx=None, nanfill_chunk=0, precision="bf16", chunk_starts=None, cams=None):
         _check_f32_cuda(ray_batch, "ray_batch")
         n = ray_batch.shape[0]
         if ray_batch.dim() != 2 or ray_batch.shape[1] != 11:
@@ -192,14 +207,20 @@ class Engine:
                 raise ValueError("chunk_starts must be a contiguous CUDA int64 [n_chunks + 1] tensor")
             inp.chunk_starts, inp.n_chunks = chunk_starts.data_ptr(), chunk_starts.numel() - 1
             keep.append(chunk_starts)
+        if cams is not None and self.n_framecodes:      # frame-code index per ray (Optcodes); None = the mean code
+            cams = torch.as_tensor(cams).reshape(-1).to(device=ray_batch.device, dtype=torch.int32).contiguous()
+            if cams.numel() != n:
+                raise ValueError("cams must have one entry per ray")
+            inp.cams = cams.data_ptr()
+            keep.append(cams)
         inp.precision = {"fp32": _lib.PRECISION_FP32, "bf16": _lib.PRECISION_BF16}[precision]
         return inp, keep
 
     # ---------------------------------------------------------------- hot path
     def render(self, ray_batch, skts, cyls, pose_idx=None, nanfill_chunk=0, precision="bf16",
-               return_alpha=True, taps=False, chunk_starts=None) -> Dict[str, torch.Tensor]:
+               return_alpha=True, taps=False, chunk_starts=None, cams=None) -> Dict[str, torch.Tensor]:
         """pgn_render_forward: the reference's RayCaster.render_rays (eval path)."""
-        inp, keep = self._inputs(ray_batch, skts, cyls, pose_idx, nanfill_chunk, precision, chunk_starts)
+        inp, keep = self._inputs(ray_batch, skts, cyls, pose_idx, nanfill_chunk, precision, chunk_starts, cams)
         n, dev = inp.n_rays, ray_batch.device
         f = lambda *sh: torch.empty(sh, dtype=torch.float32, device=dev)  # noqa: E731
         ret = {"rgb_map": f(n, 3), "disp_map": f(n), "acc_map": f(n), "rgb0": f(n, 3), "disp0": f(n), "acc0": f(n)}
@@ -218,14 +239,14 @@ class Engine:
                                                    self._stream()))
         return ret
 
-    def render_train(self, ray_batch, skts, cyls, pose_idx=None, nanfill_chunk=0, rand=None, dump_coarse=True):
+    def render_train(self, ray_batch, skts, cyls, pose_idx=None, nanfill_chunk=0, rand=None, dump_coarse=True, cams=None):
         """pgn_render_forward_train: the fused bf16 forward + per-layer activation dump for the weight gradients.
         Returns (outputs incl. the taps the backward needs, {"c": dump, "f": dump}); dump[p] is a flat bf16 buffer of
         rows * 2304 elements: layers 0-7 row-major [rows,256] each, then the view layer [rows,128], then the ReLU mask
         bits of layers 0-7 (`train.act_layer` / `train.act_masks` return the views), rows in (ray, sample) order.
         rand: optional dict of CUDA fp32 tensors t_rand [n,64], u_is [n,16], noise0 [n,64], noise [n,80] (training-time
         randomness drawn by the caller; missing keys = deterministic)."""
-        inp, keep = self._inputs(ray_batch, skts, cyls, pose_idx, nanfill_chunk, "bf16")
+        inp, keep = self._inputs(ray_batch, skts, cyls, pose_idx, nanfill_chunk, "bf16", cams=cams)
         n, dev = inp.n_rays, ray_batch.device
         f = lambda *sh: torch.empty(sh, dtype=torch.float32, device=dev)  # noqa: E731
         ret = {"rgb_map": f(n, 3), "disp_map": f(n), "acc_map": f(n), "rgb0": f(n, 3), "disp0": f(n), "acc0": f(n),
@@ -389,17 +410,28 @@ class Engine:
         if acts.dtype != torch.bfloat16 or not acts.is_contiguous():
             raise ValueError("acts must be the flat bf16 activation dump")
         rows = acts.numel() // 2304
-        n = int(self.lib.pgn_weight_grad_floats())
+        n = int(self.lib.pgn_weight_grad_floats(self.handle))
         flat = torch.empty((n,), dtype=torch.float32, device=dG.device)
         fb = torch.empty((256,), dtype=torch.float32, device=dG.device)
         _lib.check(self.lib.pgn_mlp_weight_grads(self.handle, int(net_id), _ptr(dz), _ptr(dG), _ptr(acts), rows, _ptr(enc), m,
                                                  _ptr(d_raw), _ptr(bias_v), _ptr(flat), _ptr(fb), self._stream()))
         out, o = {}, 0
         for name in LINEAR_ORDER:
-            sh = _SHAPES[name]
+            sh = self._shape(name)
             out[f"{name}.weight"] = flat[o:o + sh[0] * sh[1]].view(sh)
             o += sh[0] * sh[1]
         return out, fb
+
+    def framecode_backward(self, net_id, dG, n_rays, n_z, cams, g_view_weight):
+        """pgn_framecode_backward: adds dGr^T code[cam] into columns 904..919 of g_view_weight [128,920] (in place) and
+        returns the gradient of framecodes.codes.weight [n_framecodes,16]."""
+        if tuple(g_view_weight.shape) != (128, 920) or not g_view_weight.is_contiguous() or g_view_weight.dtype != torch.float32:
+            raise ValueError("g_view_weight must be a contiguous fp32 [128,920] tensor")
+        g_codes = torch.zeros((self.n_framecodes, 16), dtype=torch.float32, device=dG.device)
+        c = None if cams is None else torch.as_tensor(cams).reshape(-1).to(device=dG.device, dtype=torch.int32).contiguous()
+        _lib.check(self.lib.pgn_framecode_backward(self.handle, int(net_id), _ptr(dG), int(n_rays), int(n_z), _ptr(c), _ptr(g_view_weight),
+                                                   _ptr(g_codes), self._stream()))
+        return g_codes
 
     def debug_wgrad(self, A, B, Ma, Nb, n_ctas=8, out=None):
         """pgn_debug_wgrad: out[Ma, Nb] += A[:, :Ma]^T B[:, :Nb] (bf16 row-major operands, fp32 result) through the split-K kernel."""

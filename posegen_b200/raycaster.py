@@ -38,23 +38,28 @@ class NeRF(nn.Module):
                  skips=(4,), use_viewdirs=True, use_framecode=False, framecode_ch=16, n_framecodes=0,
                  skel_type=None, density_scale=1.0):
         super().__init__()
-        if (D, W, input_ch, input_ch_bones, input_ch_views, tuple(skips), use_viewdirs, use_framecode) != \
-                (8, 256, 360, 72, 648, (4,), True, False):
-            raise NotImplementedError("posegen_b200 implements the configs/surreal/surreal.txt A-NeRF only "
-                                      "(8x256, skip 4, 360+72 | 648 inputs, viewdirs, no frame codes)")
+        if (D, W, input_ch, input_ch_bones, input_ch_views, tuple(skips), use_viewdirs) != (8, 256, 360, 72, 648, (4,), True):
+            raise NotImplementedError("posegen_b200 implements the A-NeRF of the shipped configs only "
+                                      "(8x256, skip 4, 360+72 | 648 inputs, viewdirs; optional 16-channel frame codes)")
+        if use_framecode and (framecode_ch != 16 or n_framecodes <= 0):
+            raise NotImplementedError("frame codes: framecode_size must be 16 (parser default, run_nerf.py:316) and n_framecodes > 0")
         self.D, self.W = D, W
         self.input_ch, self.input_ch_bones, self.input_ch_views = input_ch, input_ch_bones, input_ch_views
         self.skips, self.use_viewdirs, self.use_framecode = list(skips), use_viewdirs, use_framecode
         self.output_ch, self.skel_type, self.density_scale = output_ch, skel_type, density_scale
+        self.framecode_ch, self.n_framecodes = framecode_ch, (n_framecodes if use_framecode else 0)
+        self.cam_ch = 1 if use_framecode else 0
         dnet = input_ch + input_ch_bones
         layers = [nn.Linear(dnet, W)]
         for i in range(D - 1):
             layers.append(nn.Linear(W + dnet if i in self.skips else W, W))
         self.pts_linears = nn.ModuleList(layers)
         self.alpha_linear = nn.Linear(W, 1)
-        self.views_linears = nn.ModuleList([nn.Linear(input_ch_views + W, W // 2)])
+        self.views_linears = nn.ModuleList([nn.Linear(input_ch_views + (framecode_ch if use_framecode else 0) + W, W // 2)])
         self.feature_linear = nn.Linear(W, W)
         self.rgb_linear = nn.Linear(W // 2, 3)
+        if use_framecode:            # core/networks/nerf.py:87-88
+            self.framecodes = Optcodes(n_framecodes, framecode_ch)
 
     def forward(self, *a, **k):
         raise NotImplementedError("NeRF.forward runs only inside posegen_b200's fused CUDA kernels "
@@ -71,7 +76,20 @@ def net_tensors(net: nn.Module) -> Dict[str, torch.Tensor]:
         for part in name.split("."):
             mod = mod[int(part)] if part.isdigit() else getattr(mod, part)
         out[f"{name}.weight"], out[f"{name}.bias"] = mod.weight, mod.bias
+    if getattr(net, "use_framecode", False):
+        out["framecodes.codes.weight"] = net.framecodes.codes.weight
     return out
+
+
+class Optcodes(nn.Module):
+    """Learned per-frame (per-camera) codes (core/networks/embedding.py:4-46): parameter container with the reference's
+    state_dict name `codes.weight`; the gather / mean rule runs inside the kernels (pgn_render_inputs.cams)."""
+
+    def __init__(self, n_codes, code_ch):
+        super().__init__()
+        self.n_codes, self.code_ch = n_codes, code_ch
+        self.codes = nn.Embedding(n_codes, code_ch)
+        nn.init.xavier_normal_(self.codes.weight)
 
 
 class Embedder(nn.Module):
@@ -143,6 +161,10 @@ class RayCaster(nn.Module):
         self._dirty = {}
 
     # -- engine / weight sync ---------------------------------------------------
+    @property
+    def n_framecodes(self):
+        return int(getattr(self.network, "n_framecodes", 0))
+
     def _param_signature(self):
         ps = list(net_tensors(self.network).values()) + list(net_tensors(self.network_fine).values())
         return tuple(p._version for p in ps) + tuple(p.data_ptr() for p in ps)
@@ -167,7 +189,7 @@ class RayCaster(nn.Module):
         device = torch.device(device)
         key = device.index if device.index is not None else torch.cuda.current_device()
         if key not in self._engines:
-            self._engines[key] = Engine(torch.device("cuda", key))
+            self._engines[key] = Engine(torch.device("cuda", key), n_framecodes=self.n_framecodes)
         eng = self._engines[key]
         sig_w, sig_s = self._param_signature(), self._scalar_signature()
         up = self._uploaded.get(key, (None, None))
@@ -266,8 +288,8 @@ class RayCaster(nn.Module):
                                       "the render path is deterministic (render_kwargs_test, core/raycasters.py:176-178)")
         if N_samples != 64 or N_importance != 16:
             raise NotImplementedError("only N_samples=64, N_importance=16 (surreal.txt) is implemented")
-        if cams is not None:
-            raise NotImplementedError("frame codes (opt_framecode) are not part of the surreal.txt path")
+        if cams is not None and not self.n_framecodes:
+            cams = None                # the reference appends the index column and a net without frame codes never reads it
         if skts is None or cyls is None:
             raise ValueError("skts and cyls are required (skeleton-relative encoding / cylinder near-far)")
         if not ray_batch.is_cuda:
@@ -279,12 +301,12 @@ class RayCaster(nn.Module):
             if (precision or self.precision) != "bf16":
                 raise NotImplementedError("the training step runs on the bf16 tensor-core path only")
             return render_train(self, ray_batch, skts.to(ray_batch.device), cyls.to(ray_batch.device), nanfill_chunk,
-                                perturb=float(perturb), raw_noise_std=float(raw_noise_std), rand=_ignored.get("train_random"))
+                                perturb=float(perturb), raw_noise_std=float(raw_noise_std), rand=_ignored.get("train_random"), cams=cams)
         eng = self.engine(ray_batch.device)
         n = ray_batch.shape[0]
         ret = eng.render(ray_batch.float(), skts.to(ray_batch.device).float(), cyls.to(ray_batch.device).float(),
                          nanfill_chunk=n if nanfill_chunk is None else nanfill_chunk,
-                         precision=precision or self.precision, return_alpha=self.return_alpha)
+                         precision=precision or self.precision, return_alpha=self.return_alpha, cams=cams)
         # alpha / alpha0 are simply absent when not requested: the reference's batchify_rays concatenates every key
         # of the returned dict (core/trainer.py:75-80), so a None entry would break it
         eng.poll_status()
@@ -356,14 +378,20 @@ def create_raycaster(args, data_attrs, device=None, precision="bf16"):
     optimizer, loaded_ckpt) with the B200 RayCaster inside."""
     _require(args, netdepth=8, netwidth=256, multires=7, multires_views=4, multires_bones=0, use_viewdirs=True,
              use_cutoff=True, cutoff_viewdir=True, cutoff_inputs=True, kp_dist_type="reldist", bone_type="reldir",
-             view_type="relray", pts_tr_type="local", density_type="relu", opt_framecode=False, single_net=False,
+             view_type="relray", pts_tr_type="local", density_type="relu", single_net=False,
              N_importance=16, N_samples=64)
+    use_fc = bool(getattr(args, "opt_framecode", False))
+    n_fc = 0
+    if use_fc:          # core/raycasters.py:22: one code per training view unless --n_framecodes overrides it
+        n_fc = data_attrs["n_views"] if getattr(args, "n_framecodes", None) is None else args.n_framecodes
+        _require(args, framecode_size=16)
     cutoff = args.cutoff_mm * args.ext_scale
     embed_fn = CutoffEmbedder(N_JOINTS, args.multires, cutoff, dist_inputs=False)
     embedbones_fn = Embedder(N_JOINTS * 3, args.multires_bones)
     embeddirs_fn = CutoffEmbedder(N_JOINTS * 3, args.multires_views, cutoff, dist_inputs=True)
     kw = dict(D=args.netdepth, W=args.netwidth, input_ch=embed_fn.out_dim, input_ch_bones=embedbones_fn.out_dim,
               input_ch_views=embeddirs_fn.out_dim, output_ch=5, skips=(4,), use_viewdirs=True,
+              use_framecode=use_fc, framecode_ch=getattr(args, "framecode_size", 16), n_framecodes=n_fc,
               skel_type=data_attrs.get("skel_type"), density_scale=args.density_scale)
     model, model_fine = NeRF(**kw), NeRF(**kw)
     ray_caster = RayCaster(model, embed_fn, embedbones_fn, embeddirs_fn, network_fine=model_fine,
@@ -425,7 +453,9 @@ def load_ckpt_from_path(ray_caster, optimizer, ckpt_path, finetune=False):
 def raycaster_from_checkpoint(ckpt: dict, device="cuda", precision="bf16") -> RayCaster:
     """Build a RayCaster and load a reference-format checkpoint dict (key names of
     core/raycasters.py:752-766), e.g. posegen_b200.synthetic.synthetic_raycaster_state()."""
-    _, kw_test, _, _, _, _ = create_raycaster(surreal_args(), {"skel_type": None}, device=device, precision=precision)
+    fc = ckpt["network_fn_state_dict"].get("framecodes.codes.weight")          # Optcodes checkpoint (h36m / mixamo / perfcap)
+    args = surreal_args() if fc is None else surreal_args(opt_framecode=True, n_framecodes=int(fc.shape[0]))
+    _, kw_test, _, _, _, _ = create_raycaster(args, {"skel_type": None}, device=device, precision=precision)
     rc = kw_test["ray_caster"]
     rc.load_state_dict(ckpt)
     rc.eval()

@@ -267,11 +267,29 @@ def synthetic_nerf_state(seed: int) -> dict:
     return state
 
 
-def synthetic_raycaster_state(seed: int, alpha_gain: float | None = None) -> dict:
+FRAMECODE_CH = 16
+
+
+def add_framecodes(net_state: dict, n_framecodes: int, seed: int) -> dict:
+    """Optcodes variant of a net (opt_framecode = True: h36m / mixamo / perfcap configs): views_linears.0 grows by 16
+    input columns (core/networks/nerf.py:52-56) and the net owns `framecodes.codes.weight` [n,16] (xavier-normal,
+    core/networks/embedding.py:38-41).  The first 904 columns keep the values of the frame-code-free state."""
+    rng = np.random.RandomState(seed)
+    w = net_state["views_linears.0.weight"]
+    bound = 1.0 / math.sqrt(w.shape[1] + FRAMECODE_CH)
+    extra = rng.uniform(-bound, bound, size=(w.shape[0], FRAMECODE_CH)).astype(np.float32)
+    net_state["views_linears.0.weight"] = np.concatenate([w, extra], 1)
+    std = math.sqrt(2.0 / (n_framecodes + FRAMECODE_CH))
+    net_state["framecodes.codes.weight"] = (rng.randn(n_framecodes, FRAMECODE_CH) * std).astype(np.float32)
+    return net_state
+
+
+def synthetic_raycaster_state(seed: int, alpha_gain: float | None = None, n_framecodes: int = 0) -> dict:
     """Checkpoint-shaped dict (core/raycasters.py:752-766 key names) with two nets.
 
     alpha_gain: fp32-tier "boosted head" recipe of SURVEY.md §8d — multiply
     alpha_linear.weight by the gain and zero its bias so the volume is not empty.
+    n_framecodes > 0: both nets get Optcodes frame codes (`add_framecodes`).
     """
     ckpt = {
         "network_fn_state_dict": synthetic_nerf_state(2 * seed + 1000),
@@ -286,6 +304,9 @@ def synthetic_raycaster_state(seed: int, alpha_gain: float | None = None) -> dic
         for k in ("network_fn_state_dict", "network_fine_state_dict"):
             ckpt[k]["alpha_linear.weight"] = ckpt[k]["alpha_linear.weight"] * np.float32(alpha_gain)
             ckpt[k]["alpha_linear.bias"] = np.zeros_like(ckpt[k]["alpha_linear.bias"])
+    if n_framecodes > 0:
+        add_framecodes(ckpt["network_fn_state_dict"], n_framecodes, 7000 + 2 * seed)
+        add_framecodes(ckpt["network_fine_state_dict"], n_framecodes, 7001 + 2 * seed)
     return ckpt
 
 

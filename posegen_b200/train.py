@@ -134,7 +134,7 @@ def mlp_backward(params: Dict[str, torch.Tensor], enc: torch.Tensor, acts: torch
         g["feature_linear.weight"] = W_vf.t() @ Tm
         g["feature_linear.bias"] = W_vf.t() @ bias_v
     if want_input_grad:                         # dL/d(network input) stays two bf16 GEMM outputs: x_p part and view part
-        g["_g_d"] = torch.mm(dG, W_v[:, 256:].to(bf))
+        g["_g_d"] = torch.mm(dG, W_v[:, 256:904].to(bf))
     if chain is not None:
         # trunk: one fused kernel for the eight deltas; the weight gradients are GEMMs over (dZ_l, h_{l-1})
         mask, mask_rows = (mask_dump[0], m) if mask_dump is not None else act_masks(acts)
@@ -146,6 +146,7 @@ def mlp_backward(params: Dict[str, torch.Tensor], enc: torch.Tensor, acts: torch
                     g[k] = v
             g["views_linears.0.bias"] = bias_v
             g["feature_linear.bias"] = feat_b
+            g["_dG"] = dG
             g["alpha_linear.bias"] = d_raw[:, 3:4].sum(0)
             for l in range(8):
                 g[f"pts_linears.{l}.bias"] = colsum[l]
@@ -193,11 +194,11 @@ def mlp_backward(params: Dict[str, torch.Tensor], enc: torch.Tensor, acts: torch
 
 class _RenderTrainFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, rc, ray_batch, skts, cyls, nanfill_chunk, rand, *params):
+    def forward(ctx, rc, ray_batch, skts, cyls, nanfill_chunk, rand, cams, *params):
         eng = rc.engine(ray_batch.device)
-        ret, acts = eng.render_train(ray_batch, skts, cyls, nanfill_chunk=nanfill_chunk, rand=rand)
+        ret, acts = eng.render_train(ray_batch, skts, cyls, nanfill_chunk=nanfill_chunk, rand=rand, cams=cams)
         rc.mark_weights_dirty()            # an optimizer step follows; not every optimizer bumps the version counters
-        ctx.rc, ctx.eng, ctx.acts, ctx.rand = rc, eng, acts, (rand or {})
+        ctx.rc, ctx.eng, ctx.acts, ctx.rand, ctx.cams = rc, eng, acts, (rand or {}), cams
         ctx.set_materialize_grads(False)   # outputs the loss does not read arrive as None: their pass is skipped
         ctx.save_for_backward(ray_batch, skts, cyls, ret["raw0"], ret["raw"], ret["z_fine"], ret["near_far"])
         ctx.mark_non_differentiable(ret["disp_map"], ret["disp0"])
@@ -218,12 +219,13 @@ class _RenderTrainFn(torch.autograd.Function):
             z_c = lower + (upper - lower) * rand["t_rand"]
         grads: List[torch.Tensor] = []
         want_sk = ctx.needs_input_grad[2]
-        want_w = any(ctx.needs_input_grad[6:])               # False for a frozen NeRF (the GAN step)
+        want_w = any(ctx.needs_input_grad[7:])               # False for a frozen NeRF (the GAN step)
+        order = param_order(rc.network)
         d_skts = None
         for net, acts, z, raw_p, gr, ga, nz in ((rc.network, ctx.acts["c"], z_c, raw0, g_rgb0, g_acc0, rand.get("noise0")),
                                                 (rc.network_fine, ctx.acts["f"], z_fine, raw, g_rgb, g_acc, rand.get("noise"))):
             if (gr is None and ga is None) or not (want_w or want_sk):      # the loss does not read this pass
-                grads += [None] * len(PARAM_ORDER)
+                grads += [None] * len(order)
                 continue
             gr = zero3 if gr is None else gr.contiguous().float()
             ga = zero1 if ga is None else ga.contiguous().float()
@@ -235,14 +237,19 @@ class _RenderTrainFn(torch.autograd.Function):
             gd = mlp_backward(pd, enc, acts, d_raw.reshape(-1, 4), eng.mlp_delta, want_input_grad=want_sk, want_weight_grad=want_w,
                               chain=functools.partial(eng.mlp_delta_chain_net, net_id) if USE_DELTA_CHAIN else None,
                               wgrad=functools.partial(eng.mlp_weight_grads, net_id) if (USE_DELTA_CHAIN and USE_WGRAD_KERNEL) else None)
-            grads += [gd[k].reshape(pd[k].shape).to(pd[k].dtype) for k in PARAM_ORDER] if want_w else [None] * len(PARAM_ORDER)
+            if want_w and rc.n_framecodes:      # Optcodes: the 16 frame-code columns of views_linears.0 and the codes themselves
+                gv = gd["views_linears.0.weight"]
+                if tuple(gv.shape) != (128, 920) or not gv.is_contiguous():
+                    raise RuntimeError("frame-code gradients need the fused weight-gradient path (USE_WGRAD_KERNEL)")
+                gd["framecodes.codes.weight"] = eng.framecode_backward(net_id, gd["_dG"], n, z.shape[1], ctx.cams, gv)
+            grads += [gd[k].reshape(pd[k].shape).to(pd[k].dtype) for k in order] if want_w else [None] * len(order)
             if want_sk:          # pose gradient: dL/d(network input) -> dL/d skts (per ray), both passes add up
                 d = eng.encode_backward_bf16(rb, sk, cy, z, gd["_g_xp"], gd["_g_d"])
                 d_skts = d if d_skts is None else d_skts + d
         ctx.acts = None
         if want_sk and d_skts is not None and sk.dim() == 3:
             d_skts = d_skts.sum(0)                     # one pose shared by every ray of the batch
-        return (None, None, d_skts, None, None, None) + tuple(grads)
+        return (None, None, d_skts, None, None, None, None) + tuple(grads)
 
 
 def draw_train_random(n: int, device, perturb: float = 0., raw_noise_std: float = 0., density_scale: float = 1.0) -> Dict[str, torch.Tensor]:
@@ -257,16 +264,21 @@ def draw_train_random(n: int, device, perturb: float = 0., raw_noise_std: float 
     return rand
 
 
+def param_order(net) -> List[str]:
+    """PARAM_ORDER, plus the frame codes of an Optcodes net."""
+    return PARAM_ORDER + (["framecodes.codes.weight"] if getattr(net, "use_framecode", False) else [])
+
+
 def render_train(rc, ray_batch, skts, cyls, nanfill_chunk=None, perturb: float = 0., raw_noise_std: float = 0.,
-                 rand: Dict[str, torch.Tensor] | None = None) -> Dict[str, torch.Tensor]:
+                 rand: Dict[str, torch.Tensor] | None = None, cams=None) -> Dict[str, torch.Tensor]:
     """Differentiable (w.r.t. the two MLPs' parameters and `skts`) render of a ray batch: the train-mode body of
     RayCaster.forward.  Returns the reference's dict (core/raycasters.py:711-724) without alpha/alpha0."""
-    params = [net_tensors(net)[k] for net in (rc.network, rc.network_fine) for k in PARAM_ORDER]
+    params = [net_tensors(net)[k] for net in (rc.network, rc.network_fine) for k in param_order(net)]
     n = ray_batch.shape[0]
     if rand is None:
         rand = draw_train_random(n, ray_batch.device, perturb, raw_noise_std, float(rc.network.density_scale))
     out = _RenderTrainFn.apply(rc, ray_batch.float().contiguous(), skts if skts.dtype == torch.float32 else skts.float(), cyls.float(),
-                               n if nanfill_chunk is None else nanfill_chunk, rand or None, *params)
+                               n if nanfill_chunk is None else nanfill_chunk, rand or None, cams, *params)
     return {"rgb_map": out[0], "acc_map": out[1], "rgb0": out[2], "acc0": out[3], "disp_map": out[4], "disp0": out[5]}
 
 

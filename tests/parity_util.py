@@ -27,7 +27,8 @@ def case_from_golden(g):
     frame = syn.synthetic_frame(int(g["meta_pose_seed"]), int(g["meta_res"]), int(g["meta_res"]))
     gain = float(g["meta_alpha_gain"])
     calibrated = bool(g["meta_calibrated"])
-    ckpt = syn.synthetic_raycaster_state(int(g["meta_weight_seed"]), alpha_gain=None if (calibrated or gain == 0) else gain)
+    ckpt = syn.synthetic_raycaster_state(int(g["meta_weight_seed"]), alpha_gain=None if (calibrated or gain == 0) else gain,
+                                         n_framecodes=int(g["meta_n_framecodes"]) if "meta_n_framecodes" in g else 0)
     if calibrated:
         for key, raw_key in (("network_fn_state_dict", "raw_coarse"), ("network_fine_state_dict", "raw_fine")):
             ckpt[key]["alpha_linear.bias"] = np.zeros_like(ckpt[key]["alpha_linear.bias"])
@@ -37,7 +38,7 @@ def case_from_golden(g):
     return frame, ckpt, rb, cyl
 
 
-def oracle_render(rb, skts, cyl, ckpt, chunk=4096, dtype=torch.float32, device="cpu", taps=None):
+def oracle_render(rb, skts, cyl, ckpt, chunk=4096, dtype=torch.float32, device="cpu", taps=None, cams=None):
     rbt = torch.as_tensor(rb).to(device=device, dtype=dtype)
     nets = orc.nets_from_ckpt(ckpt, dtype, device)
     emb = orc.embed_params_from_ckpt(ckpt, dtype, device)
@@ -46,9 +47,9 @@ def oracle_render(rb, skts, cyl, ckpt, chunk=4096, dtype=torch.float32, device="
     with torch.no_grad():
         if taps is not None and rbt.shape[0] <= chunk:
             n = rbt.shape[0]
-            out = orc.render_rays(rbt, sk[None].expand(n, -1, -1, -1), cy[None].expand(n, -1), nets, emb, taps=taps)
+            out = orc.render_rays(rbt, sk[None].expand(n, -1, -1, -1), cy[None].expand(n, -1), nets, emb, taps=taps, cams=cams)
         else:
-            out = orc.render(rbt, sk, cy, nets, emb, chunk=chunk)
+            out = orc.render(rbt, sk, cy, nets, emb, chunk=chunk, cams=cams)
     return {k: v.float().cpu().numpy() for k, v in out.items()}
 
 
@@ -63,14 +64,14 @@ def psnr(a, b, peak=1.0):
     return 99.0 if mse == 0 else 10.0 * np.log10(peak * peak / mse)
 
 
-def gpu_render(engine, rb, skts, cyl, ckpt, precision, chunk=4096, taps=False):
+def gpu_render(engine, rb, skts, cyl, ckpt, precision, chunk=4096, taps=False, cams=None):
     """Render through the C ABI in batchify-sized calls (the reference's chunk semantics)."""
     dev = engine.device
     engine.load_checkpoint(ckpt)
     rbt = torch.as_tensor(rb, device=dev)
     sk = torch.as_tensor(skts, device=dev)
     cy = torch.as_tensor(cyl, device=dev)
-    ret = engine.render(rbt, sk, cy, nanfill_chunk=chunk, precision=precision, return_alpha=True, taps=taps)
+    ret = engine.render(rbt, sk, cy, nanfill_chunk=chunk, precision=precision, return_alpha=True, taps=taps, cams=cams)
     torch.cuda.synchronize()
     engine.check_status()
     return {k: v.cpu().numpy() for k, v in ret.items()}

@@ -13,7 +13,7 @@ from posegen_b200.train import PARAM_ORDER, allreduce_gradients
 pytestmark = pytest.mark.gpu
 
 
-def _oracle_loss(rb, sk, cy, nets, emb, tgt, bg=1.0, rand=None):
+def _oracle_loss(rb, sk, cy, nets, emb, tgt, bg=1.0, rand=None, cams=None):
     """render_rays with the reference's detach of the importance samples (core/utils/ray_utils.py:286) and the
     trainer's loss: MSE(rgb_map + (1 - acc) bg, tgt) + MSE(rgb0 + (1 - acc0) bg, tgt)  (core/trainer.py:355-370)."""
     rays_o, rays_d = rb[:, 0:3], rb[:, 3:6]
@@ -21,11 +21,12 @@ def _oracle_loss(rb, sk, cy, nets, emb, tgt, bg=1.0, rand=None):
     rand = rand or {}
     z = orc.coarse_z_vals(near, far, 64, t_rand=rand.get("t_rand"))
     enc = orc.encode(rays_o[:, None] + rays_d[:, None] * z[:, :, None], rays_d, sk, emb)
-    raw0 = orc.nerf_forward(enc.reshape(-1, 1080), nets[0]).reshape(-1, 64, 4)
+    n = rb.shape[0]
+    raw0 = orc.nerf_forward(enc.reshape(-1, 1080), nets[0], frame_code=orc.frame_codes(nets[0], cams, 64, n, training=True)).reshape(-1, 64, 4)
     r0 = orc.raw2outputs(raw0, z, rays_d, noise=rand.get("noise0"))
     z_all, _, _, _, _ = orc.importance_z_vals(z, r0["weights"].detach(), 16, u=rand.get("u_is"))
     enc_f = orc.encode(rays_o[:, None] + rays_d[:, None] * z_all[:, :, None], rays_d, sk, emb)
-    raw = orc.nerf_forward(enc_f.reshape(-1, 1080), nets[1]).reshape(-1, 80, 4)
+    raw = orc.nerf_forward(enc_f.reshape(-1, 1080), nets[1], frame_code=orc.frame_codes(nets[1], cams, 80, n, training=True)).reshape(-1, 80, 4)
     r = orc.raw2outputs(raw, z_all, rays_d, noise=rand.get("noise"))
     loss = ((r["rgb_map"] + (1 - r["acc_map"][:, None]) * bg - tgt) ** 2).mean() + \
         ((r0["rgb_map"] + (1 - r0["acc_map"][:, None]) * bg - tgt) ** 2).mean()

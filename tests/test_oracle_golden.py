@@ -2,10 +2,11 @@
 unmodified reference (oracle/make_golden.py), and the synthetic inputs regenerate exactly."""
 import numpy as np
 import pytest
+import torch
 
 from tests import parity_util as pu
 
-CASES = ["a_32_boost_taps", "b_64_boost", "c_64_plain", "d_64_calibrated", "e_32_nanfill"]
+CASES = ["a_32_boost_taps", "b_64_boost", "c_64_plain", "d_64_calibrated", "e_32_nanfill", "f_64_framecode"]
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -22,7 +23,8 @@ def test_oracle_matches_reference_golden(name):
     g = pu.load_golden(name)
     frame, ckpt, rb, cyl = pu.case_from_golden(g)
     taps = {} if "z_samples" in g else None
-    out = pu.oracle_render(rb, frame.pose.skts, cyl, ckpt, chunk=int(g["meta_chunk"]), taps=taps)
+    cams = torch.as_tensor(g["in_cams"]).long() if "in_cams" in g else None          # Optcodes case: camera index per ray
+    out = pu.oracle_render(rb, frame.pose.skts, cyl, ckpt, chunk=int(g["meta_chunk"]), taps=taps, cams=cams)
     # same machine class, same op order: the restatement was bit-identical when the fixtures were
     # made; allow 2e-6 for a different BLAS/ISA on the test host
     for k in pu.IMAGE_KEYS:
@@ -49,3 +51,18 @@ def test_nanfill_case_actually_fills():
 def test_degenerate_and_nonempty_volumes_present():
     assert pu.load_golden("c_64_plain")["acc_map"].max() == 0.0      # empty volume edge case
     assert pu.load_golden("b_64_boost")["acc_map"].mean() > 0.2      # occluding volume
+
+
+def test_framecode_case_mean_code_and_density_pin():
+    """Optcodes (h36m_prot2-shaped model): cams = -1 selects the mean code (core/networks/embedding.py:23-24); the
+    reference's density-only query (fwd_type='density', core/raycasters.py:597-648) is reproduced by the oracle."""
+    from oracle import next_oracle as nxt, render_oracle as orc
+    g = pu.load_golden("f_64_framecode")
+    frame, ckpt, rb, cyl = pu.case_from_golden(g)
+    out = pu.oracle_render(rb, frame.pose.skts, cyl, ckpt, chunk=int(g["meta_chunk"]), cams=torch.full((rb.shape[0],), -1))
+    for k in pu.IMAGE_KEYS:
+        assert pu.max_abs(out[k], g[k + "_mean"]) <= 2e-6, k
+    assert pu.max_abs(g["rgb_map"], g["rgb_map_mean"]) > 1e-4            # the code is visible in the image
+    nets, emb = orc.nets_from_ckpt(ckpt), orc.embed_params_from_ckpt(ckpt)
+    dens = nxt.density_of_points(torch.as_tensor(g["density_pts"]), torch.as_tensor(frame.pose.skts), nets[1], emb).numpy()
+    assert pu.max_abs(dens, g["density_raw"]) <= 2e-5 * max(1.0, float(np.abs(g["density_raw"]).max()))
