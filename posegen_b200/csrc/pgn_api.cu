@@ -77,6 +77,7 @@ struct pgn_context {
   unsigned long long* d_prof;   // optional phase timers [num_sms][32]
   bool prof_on;
   float* d_tm = nullptr;    // T = dG^T h7 [128,256] scratch of pgn_mlp_weight_grads
+  int* d_epoch = nullptr;   // epoch counters of the weight-gradient kernel's soft lock-step
   int view_in = 904;        // input width of views_linears.0: 904, + framecode_ch with Optcodes
   int n_codes = 0;          // frame codes per net (0: none)
   float* d_codes_ext[2] = {nullptr, nullptr};   // [n_codes + 1][16]: the codes + their mean
@@ -128,6 +129,7 @@ int pgn_create(const pgn_config* cfg, pgn_context** out) {
   PGN_CUDA(cudaMalloc(&c->d_rest, PGN_J * 3 * sizeof(float)));
   PGN_CUDA(cudaMalloc(&c->d_fold, (128 * 256 + 128) * sizeof(float)));
   PGN_CUDA(cudaMalloc(&c->d_tm, 128 * 256 * sizeof(float)));
+  PGN_CUDA(cudaMalloc(&c->d_epoch, PGN_WGRAD_MAX_EPOCHS * sizeof(int)));
   for (int n = 0; n < 2; ++n) PGN_CUDA(cudaMalloc(&c->d_chain_w[n], (size_t)120 * 4096 * sizeof(__nv_bfloat16)));
   for (int n = 0; n < 2; ++n) {
     PGN_CUDA(cudaMalloc(&c->d_w[n], weight_floats(c->view_in) * sizeof(float)));
@@ -168,7 +170,7 @@ int pgn_create(const pgn_config* cfg, pgn_context** out) {
 void pgn_destroy(pgn_context* c) {
   if (!c) return;
   DeviceGuard _guard(c->cfg.device);
-  cudaFree(c->d_sc); cudaFree(c->d_status); cudaFree(c->d_c2w); cudaFree(c->d_rest); cudaFree(c->d_fold); cudaFree(c->d_tm); cudaFree(c->d_chain_w[0]); cudaFree(c->d_chain_w[1]);
+  cudaFree(c->d_sc); cudaFree(c->d_status); cudaFree(c->d_c2w); cudaFree(c->d_rest); cudaFree(c->d_fold); cudaFree(c->d_tm); cudaFree(c->d_epoch); cudaFree(c->d_chain_w[0]); cudaFree(c->d_chain_w[1]);
   for (int n = 0; n < 2; ++n) {
     cudaFree(c->d_codes_ext[n]); cudaFree(c->d_fc_table[n]);
     cudaFree(c->d_w[n]); cudaFree(c->d_b[n]); cudaFree(c->d_wt[n]); cudaFree(c->d_wstream[n]); cudaFree(c->d_bf16_aux[n]);
@@ -454,7 +456,7 @@ int pgn_mlp_weight_grads(pgn_context* c, int32_t net_id, const void* dz, const v
   if (!c->have_w[net_id]) return fail(PGN_E_STATE, "pgn_mlp_weight_grads: weights not uploaded");
   PGN_ON_DEVICE(c);
   PGN_CUDA(pgn_launch_weight_grads(dz, dG, act, dump_rows, enc, m, d_raw, bias_v, c->w_ptr[net_id][9], c->b_ptr[net_id][9],
-                                   c->w_ptr[net_id][10], c->view_in, flat, feat_bias, c->d_tm, c->d_status, c->num_sms, (cudaStream_t)stream));
+                                   c->w_ptr[net_id][10], c->view_in, flat, feat_bias, c->d_tm, c->d_epoch, c->d_status, c->num_sms, (cudaStream_t)stream));
   c->launches += 3;
   return PGN_OK;
 }
@@ -464,7 +466,7 @@ int pgn_debug_wgrad(pgn_context* c, const void* A, int32_t lda, int32_t Ma, cons
   if (!c || !A || !B || !out || (Ma != 128 && Ma != 256) || Nb <= 0 || Nb > 256 || Nb % 8 || lda % 8 || ldb % 8 || ld_out % 4 || m < 0 || n_ctas <= 0)
     return fail(PGN_E_INVALID, "pgn_debug_wgrad: bad argument");
   PGN_ON_DEVICE(c);
-  PGN_CUDA(pgn_launch_wgrad_single(A, lda, Ma, B, ldb, Nb, m, out, ld_out, n_ctas, c->d_status, (cudaStream_t)stream));
+  PGN_CUDA(pgn_launch_wgrad_single(A, lda, Ma, B, ldb, Nb, m, out, ld_out, n_ctas, c->d_epoch, c->d_status, (cudaStream_t)stream));
   c->launches++;
   return PGN_OK;
 }

@@ -132,11 +132,12 @@ cudaError_t pgn_launch_near_far_chunks(const PgnRayRefs& rays, const long long* 
 size_t pgn_wgrad_flat_floats();
 cudaError_t pgn_launch_weight_grads(const void* dz, const void* dG, const void* act, long long dump_rows, const void* enc,
                                     long long m, const float* d_raw, const float* bias_v, const float* w_f, const float* b_f,
-                                    const float* w_v, int view_ld, float* flat, float* feat_bias, float* tm_scratch, int* status, int num_sms,
-                                    cudaStream_t stream);
+                                    const float* w_v, int view_ld, float* flat, float* feat_bias, float* tm_scratch, int* epoch_ctr,
+                                    int* status, int num_sms, cudaStream_t stream);
+#define PGN_WGRAD_MAX_EPOCHS 65536        // epochs of 2,048 rows: 134 M rows per launch
 size_t pgn_wgrad_flat_floats_ld(int view_ld);
 cudaError_t pgn_launch_wgrad_single(const void* A, int lda, int Ma, const void* B, int ldb, int Nb, long long m, float* out, int ld_out,
-                                    int n_ctas, int* status, cudaStream_t stream);
+                                    int n_ctas, int* epoch_ctr, int* status, cudaStream_t stream);
 
 // bring-up probe (pgn_probe.cu)
 cudaError_t pgn_launch_probe_umma(const float* A, const float* B, float* D, int K, int N, int variant, int* status,

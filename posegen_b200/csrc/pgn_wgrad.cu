@@ -46,6 +46,12 @@ constexpr int kOpBytes = 4 * kBoxBytes;        // one operand of a stage: up to 
 constexpr int kThreads = 192;
 constexpr int kMaxUnits = 16;
 constexpr int kMaxMaps = 4;
+// Soft lock-step of the sweep: operands shared by several units (dZ_5 by 3, dG by 4, x_p by 2 ...) are only served by L2
+// if all units pass the same rows within the L2's reach.  The rows are cut into epochs of 2,048 (27 MB of operands); a
+// CTA does not start loading epoch e before every CTA has issued its loads of epoch e - kEpochWindow (bounded wait: a
+// CTA that is not co-resident can only delay the others by the timeout, never dead-lock them).
+constexpr int kEpochRows = 2048;
+constexpr int kEpochWindow = 2;
 
 struct Unit {
   int a_map, a_layer, a_col;   // A operand: tensor map, its third coordinate (layer), first column
@@ -62,6 +68,8 @@ struct __align__(64) Params {
   Unit u[kMaxUnits];
   int n_units;
   long long m;                 // rows
+  int* epoch_ctr;              // [ceil(m / kEpochRows)] zeroed per launch: CTAs that have issued every load of an epoch
+  int n_ctas;                  // CTAs of the launch
 };
 
 struct __align__(1024) Smem {
@@ -122,7 +130,18 @@ __global__ void __launch_bounds__(kThreads, 1) pgn_wgrad_kernel(const __grid_con
       int s = 0;
       uint32_t ph = 1;                             // "empty" barriers start released
       int row = k * kRows;
+      int cur_e = 0;
+      volatile int* ectr = p.epoch_ctr;
+      const int n_all = p.n_ctas;
       for (long long it = 0; it < n_mine; ++it, row += ncta * kRows) {
+        const int e = row / kEpochRows;
+        if (e != cur_e) {
+          while (cur_e < e) { atomicAdd(p.epoch_ctr + cur_e, 1); ++cur_e; }
+          if (e >= kEpochWindow) {
+            const long long t0 = clock64();
+            while (ectr[e - kEpochWindow] < n_all && clock64() - t0 < 400000) __nanosleep(200);
+          }
+        }
         if (!mbar_wait_s(empty0 + s * 8, ph, status, 801)) break;
         const uint32_t bar = full0 + s * 8;
         mbar_arrive_expect_tx_s(bar, bytes);
@@ -130,6 +149,12 @@ __global__ void __launch_bounds__(kThreads, 1) pgn_wgrad_kernel(const __grid_con
         for (int i = 0; i < b_boxes; ++i) tma_load_3d(b_s0 + s * kOpBytes + i * kBoxBytes, mb, b_col + i * kBoxCols, row, b_layer, bar);
         if (++s == kStages) { s = 0; ph ^= 1; }
       }
+      const int n_epochs = (int)((p.m + kEpochRows - 1) / kEpochRows);
+      while (cur_e < n_epochs) { atomicAdd(p.epoch_ctr + cur_e, 1); ++cur_e; }
+    }
+    if (lane == 0 && n_mine == 0) {                // an idle CTA must not hold the others back
+      const int n_epochs = (int)((p.m + kEpochRows - 1) / kEpochRows);
+      for (int e = 0; e < n_epochs; ++e) atomicAdd(p.epoch_ctr + e, 1);
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
@@ -292,9 +317,16 @@ size_t pgn_wgrad_flat_floats_ld(int view_ld) {
 }
 size_t pgn_wgrad_flat_floats() { return pgn_wgrad_flat_floats_ld(904); }
 
-static cudaError_t launch_units(Params& p, int n, long long m, int num_sms, int* status, cudaStream_t stream) {
+static cudaError_t launch_units(Params& p, int n, long long m, int num_sms, int* status, int* epoch_ctr, cudaStream_t stream) {
   p.n_units = n;
   p.m = m;
+  p.epoch_ctr = epoch_ctr;
+  {
+    const long long n_epochs = (m + kEpochRows - 1) / kEpochRows;
+    if (n_epochs > PGN_WGRAD_MAX_EPOCHS) return cudaErrorInvalidValue;
+    cudaError_t e0 = cudaMemsetAsync(epoch_ctr, 0, (size_t)n_epochs * sizeof(int), stream);
+    if (e0 != cudaSuccess) return e0;
+  }
   // CTAs per unit proportional to the bytes a stage streams (Ma + Nmma columns): every unit then sweeps the rows at the
   // same rate and shared operands are served by L2.  Largest-remainder rounding, at least one CTA per unit.
   const long long n_stages = (m + kRows - 1) / kRows;
@@ -329,14 +361,15 @@ static cudaError_t launch_units(Params& p, int n, long long m, int num_sms, int*
     if (e != cudaSuccess) return e;
     configured.set();
   }
+  p.n_ctas = c0;
   pgn_wgrad_kernel<<<c0, kThreads, smem, stream>>>(p, status);
   return cudaGetLastError();
 }
 
 cudaError_t pgn_launch_weight_grads(const void* dz_, const void* dG_, const void* act_, long long dump_rows, const void* enc_,
                                     long long m, const float* d_raw, const float* bias_v, const float* w_f, const float* b_f,
-                                    const float* w_v, int view_ld, float* flat, float* feat_bias, float* tm_scratch, int* status, int num_sms,
-                                    cudaStream_t stream) {
+                                    const float* w_v, int view_ld, float* flat, float* feat_bias, float* tm_scratch, int* epoch_ctr,
+                                    int* status, int num_sms, cudaStream_t stream) {
   const __nv_bfloat16* act = reinterpret_cast<const __nv_bfloat16*>(act_);
   size_t off[12], o = 0;
   for (int i = 0; i < 12; ++i) { off[i] = o; o += (size_t)kW_out[i] * (i == 10 ? view_ld : kW_in[i]); }
@@ -373,7 +406,7 @@ cudaError_t pgn_launch_weight_grads(const void* dz_, const void* dG_, const void
   add(kDg, 0, 128, kEnc, 0, 432, 256, flat + off[10] + 256, view_ld);
   add(kDg, 0, 128, kEnc, 0, 688, 256, flat + off[10] + 512, view_ld);
   add(kDg, 0, 128, kEnc, 0, 944, 136, flat + off[10] + 768, view_ld);      // (frame-code columns 904..919: pgn_framecode_backward)
-  if ((e = launch_units(p, n, m, num_sms, status, stream)) != cudaSuccess) return e;
+  if ((e = launch_units(p, n, m, num_sms, status, epoch_ctr, stream)) != cudaSuccess) return e;
   // alpha_linear.weight = d_sigma^T h7
   pgn_weighted_colsum_kernel<<<num_sms * 2, 256, 0, stream>>>(act + (size_t)7 * dump_rows * 256, m, d_raw + 3, 4, flat + off[8]);
   e = cudaGetLastError();
@@ -384,7 +417,7 @@ cudaError_t pgn_launch_weight_grads(const void* dz_, const void* dG_, const void
 
 // Generic entry for tests: out[Ma, Nb] (fp32, ld_out) += A[m, :Ma]^T B[m, :Nb]
 cudaError_t pgn_launch_wgrad_single(const void* A, int lda, int Ma, const void* B, int ldb, int Nb, long long m, float* out, int ld_out,
-                                    int n_ctas, int* status, cudaStream_t stream) {
+                                    int n_ctas, int* epoch_ctr, int* status, cudaStream_t stream) {
   if (m == 0) return cudaSuccess;
   Params p;
   cudaError_t e;
@@ -394,5 +427,5 @@ cudaError_t pgn_launch_wgrad_single(const void* A, int lda, int Ma, const void* 
   Unit& u = p.u[0];
   u.a_map = 0; u.a_layer = 0; u.a_col = 0; u.b_map = 1; u.b_layer = 0; u.b_col = 0;
   u.out = out; u.ld_out = ld_out; u.Ma = Ma; u.Nb = Nb; u.Nmma = (Nb + 15) / 16 * 16; u.cta0 = 0; u.ncta = 0;
-  return launch_units(p, 1, m, n_ctas, status, stream);
+  return launch_units(p, 1, m, n_ctas, status, epoch_ctr, stream);
 }
