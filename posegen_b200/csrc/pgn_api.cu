@@ -271,7 +271,7 @@ int pgn_render_forward(pgn_context* c, const pgn_render_inputs* in, const pgn_re
 size_t pgn_activation_dump_bytes(int64_t n_rays, int32_t pass) {
   if (n_rays < 0 || (pass != 0 && pass != 1)) return 0;
   // activations (8 x 256 + 128 bf16 per row) followed by the ReLU masks of the 8 trunk layers (256 bits per row each)
-  return (size_t)pgn_bf16_dump_rows(n_rays, pass == 0 ? PGN_S : PGN_T) * ((8 * 256 + 128) * sizeof(__nv_bfloat16) + 8 * 32);
+  return (size_t)pgn_bf16_dump_rows(n_rays, pass == 0 ? PGN_S : PGN_T, 0) * ((8 * 256 + 128) * sizeof(__nv_bfloat16) + 8 * 32);
 }
 
 int pgn_render_forward_train(pgn_context* c, const pgn_render_inputs* in, const pgn_render_outputs* out,
@@ -282,7 +282,7 @@ int pgn_render_forward_train(pgn_context* c, const pgn_render_inputs* in, const 
   PgnActDump d;
   d.c = (__nv_bfloat16*)act_coarse; d.f = (__nv_bfloat16*)act_fine;
   d.masks_only = 0;
-  d.rows_c = pgn_bf16_dump_rows(in->n_rays, PGN_S); d.rows_f = pgn_bf16_dump_rows(in->n_rays, PGN_T);
+  d.rows_c = pgn_bf16_dump_rows(in->n_rays, PGN_S, 0); d.rows_f = pgn_bf16_dump_rows(in->n_rays, PGN_T, 0);
   d.t_rand = rnd ? rnd->t_rand : nullptr; d.u_is = rnd ? rnd->u_is : nullptr;
   d.noise0 = rnd ? rnd->noise0 : nullptr; d.noise = rnd ? rnd->noise : nullptr;
   return render_forward_impl(c, in, out, workspace, workspace_bytes, stream_, &d);
@@ -290,7 +290,7 @@ int pgn_render_forward_train(pgn_context* c, const pgn_render_inputs* in, const 
 
 size_t pgn_mask_dump_bytes(int64_t n_rays) {
   if (n_rays < 0) return 0;
-  return (size_t)pgn_bf16_dump_rows(n_rays, PGN_T) * (8 * 32 + 16);
+  return (size_t)pgn_bf16_dump_rows(n_rays, PGN_T, 1) * (8 * 32 + 16);
 }
 
 int pgn_render_forward_masks(pgn_context* c, const pgn_render_inputs* in, const pgn_render_outputs* out, void* masks_fine,
@@ -299,7 +299,7 @@ int pgn_render_forward_masks(pgn_context* c, const pgn_render_inputs* in, const 
   if (!masks_fine) return fail(PGN_E_INVALID, "pgn_render_forward_masks: null mask buffer");
   PgnActDump d;
   d.c = nullptr; d.f = (__nv_bfloat16*)masks_fine;
-  d.rows_c = pgn_bf16_dump_rows(in->n_rays, PGN_S); d.rows_f = pgn_bf16_dump_rows(in->n_rays, PGN_T);
+  d.rows_c = pgn_bf16_dump_rows(in->n_rays, PGN_S, 1); d.rows_f = pgn_bf16_dump_rows(in->n_rays, PGN_T, 1);
   d.masks_only = 1;
   d.t_rand = nullptr; d.u_is = nullptr; d.noise0 = nullptr; d.noise = nullptr;
   return render_forward_impl(c, in, out, workspace, workspace_bytes, stream_, &d);

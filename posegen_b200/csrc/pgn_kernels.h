@@ -62,7 +62,8 @@ struct PgnActDump {
   const float* noise0;   // [n,64] raw-density noise of the coarse pass, already scaled by raw_noise_std * B
   const float* noise;    // [n,80] same for the fine pass
 };
-long long pgn_bf16_dump_rows(long long n_rays, int samples_per_ray);
+long long pgn_bf16_dump_rows(long long n_rays, int samples_per_ray, int masks_only);
+int pgn_bf16_group_rays(long long n_rays, int masks_only);
 
 size_t pgn_bf16_wstream_elems();
 // pack one net (device fp32 nn.Linear tensors) into wstream/bias; runs on `stream`

@@ -52,7 +52,7 @@ constexpr int kGroupWarps = kGroupThreads / 32;
 constexpr int kThreads = 640;
 constexpr int kProducerWarp0 = 16;      // + slot
 constexpr int kIssuerWarp0 = 18;        // + slot
-constexpr int kRPG = 8;                 // rays per group
+constexpr int kRPG = 8;                 // rays per group (large batches); small batches use groups of 4 (template kG)
 constexpr int kTM = 128;                // rows per CTA tile (UMMA M = 256 over the pair)
 constexpr int kRunBytes = kTM * 16;     // one 8-wide K run of all 128 rows
 constexpr int kActBytes = 256 / 8 * kRunBytes;                 // 65536
@@ -85,10 +85,19 @@ struct __align__(128) Smem {
 };
 static_assert(sizeof(Smem) + 1024 <= 232448, "shared memory budget of one CTA exceeded");
 
-// tile k of a ray group: C0 C1 F0 C2 F1 C3 F2 F3 F4
+// tile k of a ray group.  8 rays: C0 C1 F0 C2 F1 C3 F2 F3 F4 (4 coarse tiles of 2 rays, 640 fine rows = 5 tiles);
+// 4 rays: C0 C1 F0 F1 F2 (320 fine rows = 2.5 tiles, the last one half empty).  Small batches use the groups of 4: a
+// 3,072-ray training batch is 192 pair-units of 8 rays for 148 tile pipelines - two rounds, the second one with most
+// pipelines idle - but 384 pair-units of half the length (pgn_bf16_group_rays decides, from the ray count alone).
+template <int kG>
 __device__ __forceinline__ void tile_of(int k, int& pass, int& t) {
-  pass = (0x1D4 >> k) & 1;
-  t = (int)((0x432312010ull >> (4 * k)) & 0xF);
+  if (kG == 8) {
+    pass = (0x1D4 >> k) & 1;
+    t = (int)((0x432312010ull >> (4 * k)) & 0xF);
+  } else {
+    pass = k >= 2 ? 1 : 0;
+    t = k >= 2 ? k - 2 : k;
+  }
 }
 
 struct TileCtx {
@@ -447,7 +456,7 @@ __device__ __forceinline__ bool issue_layer(IssuerCtx& ic) {
 // ------------------------------------------------------------------ the kernel
 // kDump: 0 = inference, 1 = training forward (activation + mask dump, training-time randomness), 2 = masks only
 // (deterministic sampling; the fine pass's ReLU masks for the pose gradient through a frozen network)
-template <bool kStage, bool kProf, int kDump>
+template <bool kStage, bool kProf, int kDump, int kG = 8>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf16Net net_f,
                        const PgnScalars* __restrict__ scp, const float* __restrict__ near_far,
@@ -469,10 +478,10 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
 
   // work units: ray groups of 8 (stage mode: 128-row tiles); a pair-unit = one unit per CTA of the pair.
   // Pair-units are dealt round-robin to clusters; inside a cluster, alternately to the two slots.
-  const long long n_units = kStage ? (enc_rows_total + kTM - 1) / kTM : (rays.n_rays + kRPG - 1) / kRPG;
+  const long long n_units = kStage ? (enc_rows_total + kTM - 1) / kTM : (rays.n_rays + kG - 1) / kG;
   const long long n_pairs = (n_units + 1) / 2;
   const int n_local = (int)((n_pairs > cluster_id) ? (n_pairs - cluster_id + n_clusters - 1) / n_clusters : 0);
-  constexpr int kTiles = kStage ? 1 : kTilesPerGroup;
+  constexpr int kTiles = kStage ? 1 : (kG == 8 ? kTilesPerGroup : 5);
 
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
@@ -512,7 +521,7 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
       for (int i = 0; i < n_slot; ++i) {
         for (int k = 0; k < kTiles; ++k) {
           int pass, t;
-          tile_of(k, pass, t);
+          tile_of<kG>(k, pass, t);
           const uint8_t* wbase = reinterpret_cast<const uint8_t*>((kStage || pass == 0) ? net_c.wstream : net_f.wstream);
           const uint8_t* src = wbase;          // layers are contiguous in consumption order
           for (int L = 0; L < 9; ++L) {
@@ -620,13 +629,13 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
       const long long q = 2ll * i + s;
       const long long u = cluster_id + q * n_clusters;
       tc.unit = 2 * u + rank;
-      tc.ray0 = tc.unit * kRPG;
-      tc.nr = kStage ? 0 : (int)max(0ll, min((long long)kRPG, rays.n_rays - tc.ray0));
-      if (kStage) { tc.pass = 0; tc.t = 0; } else tile_of(k, tc.pass, tc.t);
+      tc.ray0 = tc.unit * kG;
+      tc.nr = kStage ? 0 : (int)max(0ll, min((long long)kG, rays.n_rays - tc.ray0));
+      if (kStage) { tc.pass = 0; tc.t = 0; } else tile_of<kG>(k, tc.pass, tc.t);
       tc.S = tc.pass == 0 ? PGN_S : PGN_T;
       tc.row0 = tc.t * kTM;
       tc.total_rows = kStage ? kTM : tc.nr * tc.S;
-      tc.tile_ray0 = min(tc.row0 / tc.S, kRPG - 1);
+      tc.tile_ray0 = min(tc.row0 / tc.S, kG - 1);
     };
 
     // ---- per-tile tables (jtab, dtab) for the <=3 rays of the tile: one (ray, joint, axis) item per thread
@@ -795,17 +804,18 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
         // masks only (frozen network, pose gradient): trunk masks [layer 0..7][row][half] x 128 bits of the fine pass,
         // then the view layer's [row][half] x 64 bits
         const long long m = dump.rows_f;
-        const long long grow = tc.unit * (long long)(kRPG * tc.S) + tc.row0 + ((gwarp & 3) * 32 + lane);
+        const long long grow = tc.unit * (long long)(kG * tc.S) + tc.row0 + ((gwarp & 3) * 32 + lane);
         uint4* base = reinterpret_cast<uint4*>(dump.f);
         if (L < 8) mptr = base + ((size_t)L * (size_t)m + (size_t)grow) * 2 + (gwarp >> 2);
         else vptr = reinterpret_cast<uint2*>(base + (size_t)16 * (size_t)m) + (size_t)grow * 2 + (gwarp >> 2);
       }
-      if (kDump == 1 && (tc.pass == 0 ? dump.c : dump.f) != nullptr) {       // a pass without a buffer is not dumped
+      // (groups of 4: the third fine tile holds 64 rows of the group; its upper half would land in the next group's rows)
+      if (kDump == 1 && (tc.pass == 0 ? dump.c : dump.f) != nullptr && tc.row0 + ((gwarp & 3) * 32 + lane) < kG * tc.S) {   // a pass without a buffer is not dumped
         // training forward: post-ReLU activations of every layer, bf16, per pass [layer][row][256] row-major (view
         // layer: [row][128], after the eight trunk layers); rows in (ray, sample) order:
         // row = unit * rows_per_group + tile * 128 + row_in_tile (units padded to pairs)
         const long long m = tc.pass == 0 ? dump.rows_c : dump.rows_f;
-        const long long grow = tc.unit * (long long)(kRPG * tc.S) + tc.row0 + ((gwarp & 3) * 32 + lane);
+        const long long grow = tc.unit * (long long)(kG * tc.S) + tc.row0 + ((gwarp & 3) * 32 + lane);
         uint4* base = reinterpret_cast<uint4*>(tc.pass == 0 ? dump.c : dump.f);
         dptr = base + (size_t)L * 32 * (size_t)m + (size_t)grow * (L == 8 ? 16 : 32);
         // ReLU masks of the trunk layers behind the activations: [layer 0..7][row][column half] x 128 bits
@@ -1016,10 +1026,24 @@ __global__ void pgn_pack_wstream_kernel(PackPtrs p, const float* __restrict__ fo
 
 size_t pgn_bf16_wstream_elems() { return pgn_wstream_elems(); }
 
+// Rays per group of a launch over n_rays rays: 8, or 4 when that shortens the critical path of the 148 tile pipelines
+// (2 per CTA, pair-units dealt round-robin): rounds(8-ray units) vs rounds(4-ray units) at 0.55 of the length (half the
+// rays, 10 % padding in the last fine tile).  A pure function of the ray count (a 148-SM B200 is assumed), so that the
+// dump-size queries and the launch agree.  The masks-only (GAN) forward always uses 8.
+int pgn_bf16_group_rays(long long n_rays, int masks_only) {
+  if (masks_only || n_rays <= 0) return kRPG;
+  const long long slots = 148;                       // 74 CTA pairs x 2 pipelines
+  const long long p8 = ((n_rays + 7) / 8 + 1) / 2, p4 = ((n_rays + 3) / 4 + 1) / 2;
+  const double t8 = (double)((p8 + slots - 1) / slots), t4 = 0.55 * (double)((p4 + slots - 1) / slots);
+  return t4 < t8 ? 4 : kRPG;
+}
+
 // rows of the activation dump of one pass (units are padded to CTA pairs): samples_per_ray = 64 | 80
-long long pgn_bf16_dump_rows(long long n_rays, int samples_per_ray) {
-  const long long n_groups = (n_rays + kRPG - 1) / kRPG;
-  return ((n_groups + 1) / 2) * 2 * (long long)kRPG * samples_per_ray;
+long long pgn_bf16_dump_rows(long long n_rays, int samples_per_ray, int masks_only) {
+  const int g = pgn_bf16_group_rays(n_rays, masks_only);
+  const long long n_groups = (n_rays + g - 1) / g;
+  const long long rows = ((n_groups + 1) / 2) * 2 * (long long)g * samples_per_ray;
+  return (rows + 127) / 128 * 128;
 }
 
 cudaError_t pgn_pack_bf16_net(const float* const* w_dev, const float* const* b_dev, __nv_bfloat16* wstream,
@@ -1044,6 +1068,10 @@ static cudaError_t configure_bf16() {
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(pgn_render_bf16_kernel<false, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem) + 1024);
   if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(pgn_render_bf16_kernel<false, false, 0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem) + 1024);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(pgn_render_bf16_kernel<false, false, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem) + 1024);
+  if (e != cudaSuccess) return e;
   done.set();
   return cudaSuccess;
 }
@@ -1053,7 +1081,8 @@ cudaError_t pgn_launch_render_bf16(const PgnRayRefs& rays, const PgnOutputs& out
                                    int* status, unsigned long long* prof, const PgnActDump* dump, int num_sms, cudaStream_t stream) {
   cudaError_t e = configure_bf16();
   if (e != cudaSuccess) return e;
-  const long long n_groups = (rays.n_rays + kRPG - 1) / kRPG;
+  const int g = prof ? kRPG : pgn_bf16_group_rays(rays.n_rays, dump && dump->masks_only);
+  const long long n_groups = (rays.n_rays + g - 1) / g;
   if (n_groups == 0) return cudaSuccess;
   const long long n_pairs = (n_groups + 1) / 2;
   const int grid = 2 * (int)min((long long)(num_sms / 2), n_pairs);      // clusters of 2 CTAs
@@ -1061,9 +1090,15 @@ cudaError_t pgn_launch_render_bf16(const PgnRayRefs& rays, const PgnOutputs& out
   if (dump && dump->masks_only)
     pgn_render_bf16_kernel<false, false, 2><<<grid, kThreads, sizeof(Smem) + 1024, stream>>>(rays, out, nc, nf, sc_dev, near_far,
                                                                                              nullptr, 0, nullptr, status, nullptr, *dump);
+  else if (dump && g == 4)
+    pgn_render_bf16_kernel<false, false, 1, 4><<<grid, kThreads, sizeof(Smem) + 1024, stream>>>(rays, out, nc, nf, sc_dev, near_far,
+                                                                                                nullptr, 0, nullptr, status, nullptr, *dump);
   else if (dump)
     pgn_render_bf16_kernel<false, false, 1><<<grid, kThreads, sizeof(Smem) + 1024, stream>>>(rays, out, nc, nf, sc_dev, near_far,
                                                                                              nullptr, 0, nullptr, status, nullptr, *dump);
+  else if (g == 4)
+    pgn_render_bf16_kernel<false, false, 0, 4><<<grid, kThreads, sizeof(Smem) + 1024, stream>>>(rays, out, nc, nf, sc_dev, near_far,
+                                                                                                nullptr, 0, nullptr, status, nullptr, nodump);
   else if (prof)
     pgn_render_bf16_kernel<false, true, 0><<<grid, kThreads, sizeof(Smem) + 1024, stream>>>(rays, out, nc, nf, sc_dev, near_far,
                                                                                                 nullptr, 0, nullptr, status, prof, nodump);

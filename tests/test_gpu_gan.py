@@ -64,8 +64,12 @@ def test_masks_only_forward_matches_the_full_dump(rc):
     ret_d, acts = eng.render_train(rb, sk, cy, dump_coarse=False)
     eng.check_status()
     m = n * 80
-    for k in ("rgb_map", "acc_map", "raw", "z_fine"):
+    # per-sample network outputs and sample positions are identical; the composited maps agree up to the association order
+    # of the fine-pass compositing (the two forwards cut this small batch into groups of 8 and of 4 rays)
+    for k in ("raw", "z_fine"):
         assert torch.equal(ret_m[k], ret_d[k]), k
+    for k in ("rgb_map", "acc_map"):
+        assert float((ret_m[k] - ret_d[k]).abs().max()) <= 1e-5, k
     full, rows = act_masks(acts["f"])
     assert torch.equal(trunk[:, :m], full.view(torch.int32).view(8, rows, 8)[:, :m])
     bits = ((view[:m, :, None] >> torch.arange(32, device=dev, dtype=torch.int32)) & 1).reshape(m, 128).bool()
