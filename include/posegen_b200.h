@@ -291,6 +291,14 @@ PGN_API int  pgn_mlp_weight_grads(pgn_context* ctx, int32_t net_id, const void* 
 PGN_API int  pgn_framecode_backward(pgn_context* ctx, int32_t net_id, const void* dG, int64_t n_rays, int32_t n_z,
                                     const int32_t* cams, float* g_view_weight, float* g_codes, void* stream);
 
+/* dL/d(network input) of one NeRF MLP on tcgen05 (the pose gradient, BASELINE.json configs[4]; what autograd computes as
+ * grad_input of pts_linears.0 / .5 and views_linears.0, core/networks/nerf.py:94-131 backwards) with the uploaded
+ * weights of `net_id`:  g_xp bf16 [m,432] = dZ_5 W_5[:, :432] + dZ_0 W_0,  g_d bf16 [m,648] = dG W_v[:, 256:904];
+ * dz bf16 [8][m][256] as written by pgn_mlp_delta_chain (layers 0 and 5 are read), dG bf16 [m,128].  The outputs are
+ * the operands of pgn_encode_backward_bf16. */
+PGN_API int  pgn_mlp_input_grads(pgn_context* ctx, int32_t net_id, const void* dz, const void* dG, int64_t m, void* g_xp, void* g_d,
+                                 void* stream);
+
 /* the split-K kernel on one explicit product, for unit tests: out[Ma, Nb] (fp32, row stride ld_out) += A[m, :Ma]^T B[m, :Nb],
  * A / B bf16 row-major with row strides lda / ldb (elements), Ma in {128, 256}, Nb a multiple of 8 <= 256, n_ctas CTAs
  * share the rows (split-K; out must be zero-initialised by the caller). */

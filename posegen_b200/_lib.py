@@ -23,7 +23,7 @@ EXPORTED = [
     "pgn_render_forward_train", "pgn_launch_count",
     "pgn_check_device_status", "pgn_device_status_ptr", "pgn_near_far", "pgn_encode", "pgn_mlp", "pgn_composite", "pgn_composite_backward", "pgn_encode_backward", "pgn_encode_bf16", "pgn_encode_backward_bf16", "pgn_mlp_delta", "pgn_mlp_delta_chain", "pgn_mlp_delta_chain_net", "pgn_mask_dump_bytes", "pgn_render_forward_masks", "pgn_view_delta_from_mask",
     "pgn_sample_pdf", "pgn_generate_rays", "pgn_compose_frame", "pgn_pose_to_skts", "pgn_frame_to_hmr_input",
-    "pgn_weight_grad_floats", "pgn_mlp_weight_grads", "pgn_debug_wgrad", "pgn_framecode_backward",
+    "pgn_weight_grad_floats", "pgn_mlp_weight_grads", "pgn_debug_wgrad", "pgn_framecode_backward", "pgn_mlp_input_grads",
     "pgn_pose_fk_backward", "pgn_cylinder_bboxes", "pgn_generate_rays_batch", "pgn_compose_frames_batch",
     "pgn_debug_umma_gemm", "pgn_debug_phase_timers",
 ]
@@ -111,6 +111,7 @@ def load() -> C.CDLL:
     lib.pgn_compose_frame.argtypes = [vp, i32, i32, i32, i32, i32, i32, vp, vp, f32, vp, vp]
     lib.pgn_pose_to_skts.argtypes = [vp, vp, C.POINTER(f32), i32, f32, f32, f32, vp, vp, vp, vp, vp]
     lib.pgn_frame_to_hmr_input.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, C.POINTER(f32), C.POINTER(f32), i32, vp, vp]
+    lib.pgn_mlp_input_grads.argtypes = [vp, i32, vp, vp, i64, vp, vp, vp]
     lib.pgn_framecode_backward.argtypes = [vp, i32, vp, i64, i32, vp, vp, vp, vp]
     lib.pgn_weight_grad_floats.argtypes = [vp]
     lib.pgn_weight_grad_floats.restype = C.c_size_t

@@ -78,6 +78,7 @@ struct pgn_context {
   bool prof_on;
   float* d_tm = nullptr;    // T = dG^T h7 [128,256] scratch of pgn_mlp_weight_grads
   int* d_epoch = nullptr;   // epoch counters of the weight-gradient kernel's soft lock-step
+  __nv_bfloat16* d_igw[2] = {nullptr, nullptr};   // per net: bf16 [W_5[:, :432] | W_0 | W_v[:, 256:904]] for pgn_mlp_input_grads
   int view_in = 904;        // input width of views_linears.0: 904, + framecode_ch with Optcodes
   int n_codes = 0;          // frame codes per net (0: none)
   float* d_codes_ext[2] = {nullptr, nullptr};   // [n_codes + 1][16]: the codes + their mean
@@ -131,6 +132,7 @@ int pgn_create(const pgn_config* cfg, pgn_context** out) {
   PGN_CUDA(cudaMalloc(&c->d_tm, 128 * 256 * sizeof(float)));
   PGN_CUDA(cudaMalloc(&c->d_epoch, PGN_WGRAD_MAX_EPOCHS * sizeof(int)));
   for (int n = 0; n < 2; ++n) PGN_CUDA(cudaMalloc(&c->d_chain_w[n], (size_t)120 * 4096 * sizeof(__nv_bfloat16)));
+  for (int n = 0; n < 2; ++n) PGN_CUDA(cudaMalloc(&c->d_igw[n], pgn_input_grad_weight_elems() * sizeof(__nv_bfloat16)));
   for (int n = 0; n < 2; ++n) {
     PGN_CUDA(cudaMalloc(&c->d_w[n], weight_floats(c->view_in) * sizeof(float)));
     PGN_CUDA(cudaMalloc(&c->d_b[n], bias_floats() * sizeof(float)));
@@ -170,7 +172,7 @@ int pgn_create(const pgn_config* cfg, pgn_context** out) {
 void pgn_destroy(pgn_context* c) {
   if (!c) return;
   DeviceGuard _guard(c->cfg.device);
-  cudaFree(c->d_sc); cudaFree(c->d_status); cudaFree(c->d_c2w); cudaFree(c->d_rest); cudaFree(c->d_fold); cudaFree(c->d_tm); cudaFree(c->d_epoch); cudaFree(c->d_chain_w[0]); cudaFree(c->d_chain_w[1]);
+  cudaFree(c->d_sc); cudaFree(c->d_status); cudaFree(c->d_c2w); cudaFree(c->d_rest); cudaFree(c->d_fold); cudaFree(c->d_tm); cudaFree(c->d_epoch); cudaFree(c->d_chain_w[0]); cudaFree(c->d_chain_w[1]); cudaFree(c->d_igw[0]); cudaFree(c->d_igw[1]);
   for (int n = 0; n < 2; ++n) {
     cudaFree(c->d_codes_ext[n]); cudaFree(c->d_fc_table[n]);
     cudaFree(c->d_w[n]); cudaFree(c->d_b[n]); cudaFree(c->d_wt[n]); cudaFree(c->d_wstream[n]); cudaFree(c->d_bf16_aux[n]);
@@ -201,7 +203,9 @@ int pgn_upload_weights(pgn_context* c, int net_id, const pgn_net_weights* w, int
   }
   // the backward's delta-chain weight stream (reads the fold the pack above left in d_fold)
   PGN_CUDA(pgn_launch_pack_chain_weights(c->w_ptr[net_id], c->d_fold, c->d_chain_w[net_id], stream));
-  c->launches += 3;
+  // bf16 weight blocks of the input-gradient kernel (pose gradient)
+  PGN_CUDA(pgn_launch_pack_input_grad_weights(c->w_ptr[net_id][5], c->w_ptr[net_id][0], c->w_ptr[net_id][10], c->view_in, c->d_igw[net_id], stream));
+  c->launches += 4;
   c->have_w[net_id] = true;
   return PGN_OK;
 }
@@ -458,6 +462,15 @@ int pgn_mlp_weight_grads(pgn_context* c, int32_t net_id, const void* dz, const v
   PGN_CUDA(pgn_launch_weight_grads(dz, dG, act, dump_rows, enc, m, d_raw, bias_v, c->w_ptr[net_id][9], c->b_ptr[net_id][9],
                                    c->w_ptr[net_id][10], c->view_in, flat, feat_bias, c->d_tm, c->d_epoch, c->d_status, c->num_sms, (cudaStream_t)stream));
   c->launches += 3;
+  return PGN_OK;
+}
+
+int pgn_mlp_input_grads(pgn_context* c, int32_t net_id, const void* dz, const void* dG, int64_t m, void* g_xp, void* g_d, void* stream) {
+  if (!c || net_id < 0 || net_id > 1 || !dz || !dG || !g_xp || !g_d || m < 0) return fail(PGN_E_INVALID, "pgn_mlp_input_grads: bad argument");
+  if (!c->have_w[net_id]) return fail(PGN_E_STATE, "pgn_mlp_input_grads: weights not uploaded");
+  PGN_ON_DEVICE(c);
+  PGN_CUDA(pgn_launch_input_grads(dz, dG, m, c->d_igw[net_id], g_xp, g_d, c->d_status, c->num_sms, (cudaStream_t)stream));
+  c->launches++;
   return PGN_OK;
 }
 

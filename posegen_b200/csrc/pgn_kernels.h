@@ -140,6 +140,13 @@ size_t pgn_wgrad_flat_floats_ld(int view_ld);
 cudaError_t pgn_launch_wgrad_single(const void* A, int lda, int Ma, const void* B, int ldb, int Nb, long long m, float* out, int ld_out,
                                     int n_ctas, int* epoch_ctr, int* status, cudaStream_t stream);
 
+// ---- input gradients of the MLP on tcgen05 (pgn_input_grads.cu) ----
+size_t pgn_input_grad_weight_elems();
+cudaError_t pgn_launch_pack_input_grad_weights(const float* w5, const float* w0, const float* wv, int view_ld, __nv_bfloat16* out,
+                                               cudaStream_t stream);
+cudaError_t pgn_launch_input_grads(const void* dz, const void* dG, long long m, const __nv_bfloat16* wpack, void* g_xp, void* g_d,
+                                   int* status, int num_sms, cudaStream_t stream);
+
 // bring-up probe (pgn_probe.cu)
 cudaError_t pgn_launch_probe_umma(const float* A, const float* B, float* D, int K, int N, int variant, int* status,
                                   cudaStream_t stream);

@@ -422,6 +422,18 @@ class Engine:
             o += sh[0] * sh[1]
         return out, fb
 
+    def mlp_input_grads(self, net_id, dz, dG):
+        """pgn_mlp_input_grads: (g_xp bf16 [m,432], g_d bf16 [m,648]) = dL/d(network input) from dz bf16 [8,m,256] (layers 0
+        and 5) and dG bf16 [m,128], with the uploaded weights of net `net_id` - tcgen05, no library GEMM."""
+        m = dG.shape[0]
+        for t, shape in ((dz, (8, m, 256)), (dG, (m, 128))):
+            if tuple(t.shape) != shape or t.dtype != torch.bfloat16 or not t.is_contiguous() or not t.is_cuda:
+                raise ValueError(f"mlp_input_grads: expected a contiguous CUDA bf16 tensor of shape {shape}, got {tuple(t.shape)} {t.dtype}")
+        g_xp = torch.empty((m, 432), dtype=torch.bfloat16, device=dG.device)
+        g_d = torch.empty((m, 648), dtype=torch.bfloat16, device=dG.device)
+        _lib.check(self.lib.pgn_mlp_input_grads(self.handle, int(net_id), _ptr(dz), _ptr(dG), m, _ptr(g_xp), _ptr(g_d), self._stream()))
+        return g_xp, g_d
+
     def framecode_backward(self, net_id, dG, n_rays, n_z, cams, g_view_weight):
         """pgn_framecode_backward: adds dGr^T code[cam] into columns 904..919 of g_view_weight [128,920] (in place) and
         returns the gradient of framecodes.codes.weight [n_framecodes,16]."""

@@ -64,7 +64,8 @@ class _FrameRenderFn(torch.autograd.Function):
                                            g_acc.index_select(0, idx).contiguous())
             mask_dump = (trunk_mask.index_select(1, rows), view_mask.index_select(0, rows))
             gd = mlp_backward(pd, None, None, d_raw.reshape(-1, 4), eng.mlp_delta, want_input_grad=True, want_weight_grad=False,
-                              chain=functools.partial(eng.mlp_delta_chain_net, 1), mask_dump=mask_dump, view_delta=eng.view_delta_from_mask)
+                              chain=functools.partial(eng.mlp_delta_chain_net, 1), mask_dump=mask_dump, view_delta=eng.view_delta_from_mask,
+                              input_grads=functools.partial(eng.mlp_input_grads, 1))
             d = eng.encode_backward_bf16(rb, sk, cy, z, gd["_g_xp"], gd["_g_d"])
             d_skts += d.sum(0)
             del gd, d, mask_dump

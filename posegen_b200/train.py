@@ -31,6 +31,7 @@ from .raycaster import net_tensors
 S, T = 64, 80
 USE_DELTA_CHAIN = True        # trunk backward through pgn_mlp_delta_chain (False: layer by layer, for A/B runs)
 USE_WGRAD_KERNEL = True       # weight gradients through pgn_mlp_weight_grads (False: torch.mm, for A/B runs)
+USE_INPUT_GRAD_KERNEL = True  # dL/d(network input) through pgn_mlp_input_grads (False: torch.mm, for A/B runs)
 PARAM_ORDER = [f"pts_linears.{i}.{k}" for i in range(8) for k in ("weight", "bias")] + \
     [f"{m}.{k}" for m in ("alpha_linear", "feature_linear", "views_linears.0", "rgb_linear") for k in ("weight", "bias")]
 
@@ -76,7 +77,7 @@ def chain_wstream(P: Dict[str, torch.Tensor]) -> torch.Tensor:
 def mlp_backward(params: Dict[str, torch.Tensor], enc: torch.Tensor, acts: torch.Tensor, d_raw: torch.Tensor,
                  fuse: Callable, want_input_grad: bool = False, want_weight_grad: bool = True,
                  chain: Callable | None = None, mask_dump=None, view_delta: Callable | None = None,
-                 wgrad: Callable | None = None) -> Dict[str, torch.Tensor]:
+                 wgrad: Callable | None = None, input_grads: Callable | None = None) -> Dict[str, torch.Tensor]:
     """Weight gradients of one NeRF MLP (core/networks/nerf.py:94-148).
 
     params: fp32 nn.Linear tensors; enc [m,1080] bf16 network input (`pgn_encode_bf16`; may be None when
@@ -94,6 +95,8 @@ def mlp_backward(params: Dict[str, torch.Tensor], enc: torch.Tensor, acts: torch
     `wgrad(dz, dG, acts, enc, d_raw, bias_v)` is `Engine.mlp_weight_grads` bound to this net (`pgn_mlp_weight_grads`):
     with it (and `chain`) every weight gradient is formed by the library's split-K tcgen05 kernel and no library GEMM
     runs in the step; without it the products below go through `torch.mm` (the CPU host-logic test, A/B runs).
+    `input_grads(dz, dG)` is `Engine.mlp_input_grads` bound to this net (`pgn_mlp_input_grads`): dL/d(network input) on
+    tcgen05 instead of three library GEMMs (needs `chain`).
     mask_dump = (trunk_mask int32 [8,m,8], view_mask int32 [m,4]) with `view_delta` = `Engine.view_delta_from_mask`
     replaces `acts` for a frozen network (want_weight_grad False, `chain` required): the masks-only dump of
     `pgn_render_forward_masks` is all the input-gradient chain reads.
@@ -110,7 +113,7 @@ def mlp_backward(params: Dict[str, torch.Tensor], enc: torch.Tensor, acts: torch
         G = act_layer(acts, 8, m)
     P = {k: v.detach() for k, v in params.items()}
     # bf16 trunk weights: only the input-gradient GEMMs and the layer-by-layer fallback read them
-    need_w = (0, 5) if (chain is not None and want_input_grad) else (range(8) if chain is None else ())
+    need_w = (0, 5) if (chain is not None and want_input_grad and input_grads is None) else (range(8) if chain is None else ())
     W = {f"pts_linears.{l}.weight": P[f"pts_linears.{l}.weight"].to(bf) for l in need_w}
     g: Dict[str, torch.Tensor] = {}
     # rgb head + view layer:  g = relu(W_v [f | d_emb] + b_v),  f = W_f h7 + b_f,  rgb_raw = W_rgb g + b_rgb
@@ -133,7 +136,8 @@ def mlp_backward(params: Dict[str, torch.Tensor], enc: torch.Tensor, acts: torch
         g["views_linears.0.bias"] = bias_v
         g["feature_linear.weight"] = W_vf.t() @ Tm
         g["feature_linear.bias"] = W_vf.t() @ bias_v
-    if want_input_grad:                         # dL/d(network input) stays two bf16 GEMM outputs: x_p part and view part
+    fused_in = want_input_grad and input_grads is not None and chain is not None
+    if want_input_grad and not fused_in:        # dL/d(network input) stays two bf16 GEMM outputs: x_p part and view part
         g["_g_d"] = torch.mm(dG, W_v[:, 256:904].to(bf))
     if chain is not None:
         # trunk: one fused kernel for the eight deltas; the weight gradients are GEMMs over (dZ_l, h_{l-1})
@@ -162,7 +166,9 @@ def mlp_backward(params: Dict[str, torch.Tensor], enc: torch.Tensor, acts: torch
                 else:
                     g[f"pts_linears.{l}.weight"] = _mm32(dZt, H[l - 1])
                 g[f"pts_linears.{l}.bias"] = colsum[l]
-        if want_input_grad:
+        if fused_in:
+            g["_g_xp"], g["_g_d"] = input_grads(dz, dG)
+        elif want_input_grad:
             g["_g_xp"] = torch.mm(dz[5], W["pts_linears.5.weight"][:, :432]).addmm_(dz[0], W["pts_linears.0.weight"])
         return g
     # sigma head + last trunk layer: dL/d h7 = dG (W_vf W_f) + d_sigma w_alpha
@@ -236,7 +242,8 @@ class _RenderTrainFn(torch.autograd.Function):
             net_id = 0 if net is rc.network else 1
             gd = mlp_backward(pd, enc, acts, d_raw.reshape(-1, 4), eng.mlp_delta, want_input_grad=want_sk, want_weight_grad=want_w,
                               chain=functools.partial(eng.mlp_delta_chain_net, net_id) if USE_DELTA_CHAIN else None,
-                              wgrad=functools.partial(eng.mlp_weight_grads, net_id) if (USE_DELTA_CHAIN and USE_WGRAD_KERNEL) else None)
+                              wgrad=functools.partial(eng.mlp_weight_grads, net_id) if (USE_DELTA_CHAIN and USE_WGRAD_KERNEL) else None,
+                              input_grads=functools.partial(eng.mlp_input_grads, net_id) if (USE_DELTA_CHAIN and USE_INPUT_GRAD_KERNEL) else None)
             if want_w and rc.n_framecodes:      # Optcodes: the 16 frame-code columns of views_linears.0 and the codes themselves
                 gv = gd["views_linears.0.weight"]
                 if tuple(gv.shape) != (128, 920) or not gv.is_contiguous():

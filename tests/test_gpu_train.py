@@ -449,3 +449,25 @@ def test_fused_weight_gradients_match_the_gemm_formulation(engine, train_case):
         if float(ref.norm()) > 1e-9:
             rel = float((got - ref).norm() / ref.norm())
             assert rel <= 5e-3, (key, rel)           # same bf16 operands, fp32 accumulation in a different order
+
+
+@pytest.mark.parametrize("m", [128, 1000, 40000])
+def test_input_grad_kernel_matches_matrix_products(engine, m):
+    """pgn_mlp_input_grads (tcgen05: K-major SWIZZLE_128B deltas x MN-major weights, five <= 256-column jobs per 128-row
+    tile) against the three matrix products it replaces, on random deltas and the uploaded synthetic weights."""
+    ckpt = syn.synthetic_raycaster_state(4, alpha_gain=40.0)
+    engine.load_checkpoint(ckpt)
+    g = torch.Generator(device="cuda").manual_seed(m)
+    dz = (torch.randn((8, m, 256), device="cuda", generator=g) * 0.3).to(torch.bfloat16)
+    dG = (torch.randn((m, 128), device="cuda", generator=g) * 0.3).to(torch.bfloat16)
+    g_xp, g_d = engine.mlp_input_grads(1, dz, dG)
+    torch.cuda.synchronize()
+    engine.check_status()
+    net = {k: torch.as_tensor(v, device="cuda") for k, v in ckpt["network_fine_state_dict"].items()}
+    bf = lambda w: w.to(torch.bfloat16).double()                                   # noqa: E731  (the kernel reads bf16 weights)
+    want_xp = dz[5].double() @ bf(net["pts_linears.5.weight"][:, :432]) + dz[0].double() @ bf(net["pts_linears.0.weight"])
+    want_d = dG.double() @ bf(net["views_linears.0.weight"][:, 256:904])
+    for got, want in ((g_xp, want_xp), (g_d, want_d)):
+        assert got.shape == want.shape
+        err = float((got.double() - want).abs().max())
+        assert err <= 8e-3 * max(1.0, float(want.abs().max())), err               # one bf16 rounding of the result
