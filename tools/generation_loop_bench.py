@@ -61,8 +61,25 @@ def run(rank, world, local, poses=256, res=512):
     if world > 1:
         torch.distributed.all_reduce(tot)
     assert all_frames.shape[0] == poses
+    # the same kernel back to back on one resident pose, no driver work: what the loop is compared with (the headline
+    # bench line pauses between steps to flush L2, so its clocks sit higher than a seconds-long loop at the power cap)
+    f0 = syn.synthetic_frame(int(mine[0]) if len(mine) else 0, res, res)
+    rb0 = torch.as_tensor(syn.ray_batch(f0.rays_o, f0.rays_d), device=dev)
+    sk0, cy0 = torch.as_tensor(f0.pose.skts, device=dev), torch.as_tensor(f0.pose.cyl, device=dev)
+    reps = 24
+    for _ in range(2):
+        eng.render(rb0, sk0, cy0, nanfill_chunk=4096, return_alpha=False)
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record()
+    for _ in range(reps):
+        eng.render(rb0, sk0, cy0, nanfill_chunk=4096, return_alpha=False)
+    k1.record()
+    torch.cuda.synchronize()
+    kernel_rps = rb0.shape[0] * reps / (k0.elapsed_time(k1) * 1e-3)
+    loop_rps_rank = n_rays / (ms * 1e-3)
     return {"metric": "frames_per_sec_512", "value": poses / ms * 1e3, "unit": "frames/s", "n_gpus": world,
             "poses": poses, "seconds": ms * 1e-3, "rays_per_sec": float(tot[0]) / ms * 1e3,
+            "kernel_only_sustained_rays_per_sec_rank0": kernel_rps, "loop_over_kernel_only_rank0": loop_rps_rank / kernel_rps,
             "hmr_inputs": list(hmr.shape), "finite": bool(torch.isfinite(hmr).all()), "gpu_launches_rank0": int(eng.launch_count - l0),
             "config": f"{poses} synthetic poses x {res}x{res} bbox renders sharded pose_idx % {world}; device FK + cylinder + bbox, "
                       "device rays, ONE fused bf16 render launch per pose batch (pose_idx form), white-bg frames, HMR input 224; "
