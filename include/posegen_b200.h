@@ -175,10 +175,13 @@ PGN_API int  pgn_render_forward(pgn_context* ctx, const pgn_render_inputs* in,
 
 /* Training-step forward (reference core/trainer.py:232-275, eval-style sampling: perturb = 0, no noise): the same
  * fused bf16 pipeline as pgn_render_forward that additionally stores the post-ReLU activations of every MLP layer
- * (bf16) so that the weight gradients can be formed by plain GEMMs.  Per pass the dump is row-major per layer:
- * layers 0-7 (pts_linears) [rows,256] each, then layer 8 (views_linears.0) [rows,128], then the ReLU masks of
- * layers 0-7 as bits ([layer][row][256 bits], bit c = [activation c > 0]); rows are samples in (ray, sample) order,
- * padded to rows = pgn_activation_dump_bytes(n, pass) / 4608.  act_coarse / act_fine: device buffers of
+ * (bf16) for the weight-gradient kernel (pgn_mlp_weight_grads).  Per pass the dump holds: layers 0-7 (pts_linears),
+ * each TILE-BLOCKED as [rows / 128][256 / 8][128][8] (element (r, c) of a layer at bf16 index
+ * ((r / 128) * 32 + c / 8) * 1024 + (r % 128) * 8 + c % 8: the UMMA operand image of a 128-row tile, so that the
+ * forward's stores are fully coalesced and the weight-gradient kernel loads a tile with one 64 KB bulk copy); then
+ * layer 8 (views_linears.0) row-major [rows,128]; then the ReLU masks of layers 0-7 as bits ([layer][row][256 bits],
+ * bit c = [activation c > 0]); rows are samples in (ray, sample) order, padded to
+ * rows = pgn_activation_dump_bytes(n, pass) / 4608 (a multiple of 128).  act_coarse / act_fine: device buffers of
  * pgn_activation_dump_bytes(n_rays, 0 / 1) bytes; one of them may be NULL (that pass is not dumped: a loss that reads
  * only the fine outputs sends no gradient into the coarse network).  Request out->raw0 / raw / z_fine / near_far for the backward.
  * rnd (may be NULL = deterministic eval sampling) carries the training-time randomness as explicit device arrays so
@@ -301,9 +304,10 @@ PGN_API int  pgn_mlp_input_grads(pgn_context* ctx, int32_t net_id, const void* d
 
 /* the split-K kernel on one explicit product, for unit tests: out[Ma, Nb] (fp32, row stride ld_out) += A[m, :Ma]^T B[m, :Nb],
  * A / B bf16 row-major with row strides lda / ldb (elements), Ma in {128, 256}, Nb a multiple of 8 <= 256, n_ctas CTAs
- * share the rows (split-K; out must be zero-initialised by the caller). */
+ * share the rows (split-K; out must be zero-initialised by the caller).  b_tile_blocked != 0: B is a 256-column matrix in
+ * the training forward's tile-blocked dump layout [row / 128][column / 8][128][8] (ldb ignored; rows padded to 128). */
 PGN_API int  pgn_debug_wgrad(pgn_context* ctx, const void* A, int32_t lda, int32_t Ma, const void* B, int32_t ldb, int32_t Nb,
-                             int64_t m, float* out, int32_t ld_out, int32_t n_ctas, void* stream);
+                             int64_t m, float* out, int32_t ld_out, int32_t n_ctas, int32_t b_tile_blocked, void* stream);
 
 /* NeRF.forward (core/networks/nerf.py:133-148) on explicit encodings:
  * enc [m,1080] -> raw [m,4].  precision selects the MLP engine. */

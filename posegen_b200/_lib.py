@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libposegen_b200.so")
+LIB_PATH = os.environ.get("POSEGEN_B200_LIB") or os.path.join(_HERE, "lib", "libposegen_b200.so")   # (override: experiment builds)
 
 PGN_OK = 0
 PGN_E_INVALID, PGN_E_CUDA, PGN_E_STATE, PGN_E_KERNEL = -1, -2, -3, -4
@@ -116,7 +116,7 @@ def load() -> C.CDLL:
     lib.pgn_weight_grad_floats.argtypes = [vp]
     lib.pgn_weight_grad_floats.restype = C.c_size_t
     lib.pgn_mlp_weight_grads.argtypes = [vp, i32, vp, vp, vp, i64, vp, i64, vp, vp, vp, vp, vp]
-    lib.pgn_debug_wgrad.argtypes = [vp, vp, i32, i32, vp, i32, i32, i64, vp, i32, i32, vp]
+    lib.pgn_debug_wgrad.argtypes = [vp, vp, i32, i32, vp, i32, i32, i64, vp, i32, i32, i32, vp]
     lib.pgn_pose_fk_backward.argtypes = [vp, vp, C.POINTER(f32), i32, vp, vp, vp, vp]
     lib.pgn_cylinder_bboxes.argtypes = [vp, vp, i32, C.POINTER(C.c_double), i32, i32, f32, vp, vp]
     lib.pgn_generate_rays_batch.argtypes = [vp, i32, i32, f32, C.POINTER(f32), vp, vp, i32, i64, vp, vp, vp]

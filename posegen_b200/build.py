@@ -30,8 +30,11 @@ def sources():
     return deps
 
 
-def build(verbose: bool = False, force: bool = False) -> str:
+def build(verbose: bool = False, force: bool = False, extra_flags=(), out: str | None = None) -> str:
+    """extra_flags / out: experiment builds (`-DPGN_EXP_...`) into another file, loaded with POSEGEN_B200_LIB=<path>."""
     os.makedirs(LIB_DIR, exist_ok=True)
+    if out is not None:
+        return _build_variant(list(extra_flags), out, verbose)
     if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= _newest(sources()):
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -55,6 +58,25 @@ def build(verbose: bool = False, force: bool = False) -> str:
     link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH, *objs]
     subprocess.run(link, check=True)
     return LIB_PATH
+
+
+def _build_variant(flags, out, verbose):
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    tag = os.path.splitext(os.path.basename(out))[0]
+    objs, procs = [], []
+    for src in SOURCES:
+        obj = os.path.join(LIB_DIR, f"{tag}_{src.replace('.cu', '.o')}")
+        procs.append((src, subprocess.Popen([nvcc, *NVCC_FLAGS, *flags, "-c", os.path.join(CSRC, src), "-o", obj],
+                                            stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    for src, p in procs:
+        o, _ = p.communicate()
+        if p.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n{o}")
+    subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out, *objs], check=True)
+    for o in objs:
+        os.remove(o)
+    return out
 
 
 if __name__ == "__main__":

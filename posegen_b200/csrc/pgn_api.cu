@@ -475,11 +475,12 @@ int pgn_mlp_input_grads(pgn_context* c, int32_t net_id, const void* dz, const vo
 }
 
 int pgn_debug_wgrad(pgn_context* c, const void* A, int32_t lda, int32_t Ma, const void* B, int32_t ldb, int32_t Nb, int64_t m,
-                    float* out, int32_t ld_out, int32_t n_ctas, void* stream) {
+                    float* out, int32_t ld_out, int32_t n_ctas, int32_t b_tile_blocked, void* stream) {
   if (!c || !A || !B || !out || (Ma != 128 && Ma != 256) || Nb <= 0 || Nb > 256 || Nb % 8 || lda % 8 || ldb % 8 || ld_out % 4 || m < 0 || n_ctas <= 0)
     return fail(PGN_E_INVALID, "pgn_debug_wgrad: bad argument");
   PGN_ON_DEVICE(c);
-  PGN_CUDA(pgn_launch_wgrad_single(A, lda, Ma, B, ldb, Nb, m, out, ld_out, n_ctas, c->d_epoch, c->d_status, (cudaStream_t)stream));
+  if (b_tile_blocked && Nb != 256) return fail(PGN_E_INVALID, "pgn_debug_wgrad: a tile-blocked B is a 256-column matrix");
+  PGN_CUDA(pgn_launch_wgrad_single(A, lda, Ma, B, ldb, Nb, m, out, ld_out, n_ctas, b_tile_blocked, c->d_epoch, c->d_status, (cudaStream_t)stream));
   c->launches++;
   return PGN_OK;
 }

@@ -138,7 +138,7 @@ cudaError_t pgn_launch_weight_grads(const void* dz, const void* dG, const void* 
 #define PGN_WGRAD_MAX_EPOCHS 65536        // epochs of 2,048 rows: 134 M rows per launch
 size_t pgn_wgrad_flat_floats_ld(int view_ld);
 cudaError_t pgn_launch_wgrad_single(const void* A, int lda, int Ma, const void* B, int ldb, int Nb, long long m, float* out, int ld_out,
-                                    int n_ctas, int* epoch_ctr, int* status, cudaStream_t stream);
+                                    int n_ctas, int b_tile_blocked, int* epoch_ctr, int* status, cudaStream_t stream);
 
 // ---- input gradients of the MLP on tcgen05 (pgn_input_grads.cu) ----
 size_t pgn_input_grad_weight_elems();

@@ -260,6 +260,11 @@ __device__ __forceinline__ void stg256(void* p, const uint32_t (&v)[8]) {
                : "memory");
 }
 
+// 128-bit streaming global store
+__device__ __forceinline__ void stg128(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.global.cs.v4.b32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
 // ------------------------------------------------------------------ epilogue (compute group)
 // The bias is already in the accumulator (bias K-step), so a hidden layer is TMEM -> ReLU+bf16 -> smem.
 // MODE 0: hidden layer -> act.  MODE 1: same + sigma head (fp32).  MODE 2: view layer -> rgb head (fp32).
@@ -271,8 +276,12 @@ __device__ __forceinline__ void epilogue(Smem& sm, uint32_t tmem_acc, uint32_t a
                                          const float* __restrict__ fc = nullptr) {
   // fc (view layer only): this row's frame-code term [128] (Optcodes: W_v[:, 904:920] code[cam], fp32), added to the
   // pre-activation before the ReLU; nullptr when the model has no frame codes
-  // dump (training forward only): this thread's row of the layer's row-major activation dump ([rows, 256 | 128] bf16);
-  // a thread owns 128 (view layer: 64) consecutive columns, i.e. 256 (128) contiguous bytes of its row
+  // dump (training forward only).  Trunk layers (MODE 0/1): this thread's row inside its tile of the TILE-BLOCKED dump
+  // [rows / 128][256 / 8][128][8] bf16 - the same image the epilogue writes into shared memory - so the 16-byte store of
+  // one 8-column run by the 32 lanes of a warp (32 consecutive rows) is 512 contiguous bytes: 4 full lines per store
+  // instruction instead of the 32 sectors in 32 lines of a row-major dump (which made the training forward 1.75 instead
+  // of 1.0 ms: the epilogue, on each slot's critical path, was bound by the LSU's line throughput).  View layer
+  // (MODE 2): row-major [rows,128], 64 consecutive columns of this thread's row.
   const int q = warp & 3, half = warp >> 2;
   const int row = q * 32 + lane;
   constexpr int kCols = (MODE == 2) ? 64 : 128;        // columns per thread
@@ -330,7 +339,14 @@ __device__ __forceinline__ void epilogue(Smem& sm, uint32_t tmem_acc, uint32_t a
           pk[4 * g + i] = pack_relu_bf16x2(__uint_as_float(vb[8 * g + 2 * i]), __uint_as_float(vb[8 * g + 2 * i + 1]));
         sts128(dst0 + (uint32_t)(2 * b + g) * kRunBytes, pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
       }
-      if (dump) stg256(dump + (col0 >> 3) + 2 * b, pk);          // 16 columns = one full 32-byte sector
+#ifndef PGN_EXP_NOSTG      // (-DPGN_EXP_NOSTG: timing experiment, the trunk activations are not stored)
+      if (dump) {                                                // runs (col0 / 8 + 2 b) and (+ 1): 128 rows x 16 B = 2 KB apart
+        uint4* d = dump + (size_t)((col0 >> 3) + 2 * b) * 128;
+        stg128(d, pk[0], pk[1], pk[2], pk[3]);
+        stg128(d + 128, pk[4], pk[5], pk[6], pk[7]);
+      }
+#endif
+#ifndef PGN_EXP_NOMASK     // (-DPGN_EXP_NOMASK: timing experiment, no mask bits)
       if (dump_mask) {
         // ReLU mask of the 16 columns (what the fused delta chain of the backward reads instead of the activations):
         // one funnel shift per column collects the accumulators' sign bits (last column first, so column 0 ends up in
@@ -342,6 +358,7 @@ __device__ __forceinline__ void epilogue(Smem& sm, uint32_t tmem_acc, uint32_t a
         if (b & 1) reinterpret_cast<uint32_t*>(dump_mask)[b >> 1] = mask_w | ((~mb & 0xffffu) << 16);
         else mask_w = ~mb & 0xffffu;
       }
+#endif
     }
     if (MODE == 2 && dump) {      // view layer: relu(g) of this thread's 16 columns
       uint32_t pk[8];
@@ -817,7 +834,9 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
         const long long m = tc.pass == 0 ? dump.rows_c : dump.rows_f;
         const long long grow = tc.unit * (long long)(kG * tc.S) + tc.row0 + ((gwarp & 3) * 32 + lane);
         uint4* base = reinterpret_cast<uint4*>(tc.pass == 0 ? dump.c : dump.f);
-        dptr = base + (size_t)L * 32 * (size_t)m + (size_t)grow * (L == 8 ? 16 : 32);
+        // trunk layer L: tile-blocked, tile grow / 128 (64 KB = 4096 uint4), this row's 16 bytes of run 0; view layer: row-major
+        dptr = L == 8 ? base + (size_t)8 * 32 * (size_t)m + (size_t)grow * 16
+                      : base + (size_t)L * 32 * (size_t)m + (size_t)(grow >> 7) * 4096 + (size_t)(grow & 127);
         // ReLU masks of the trunk layers behind the activations: [layer 0..7][row][column half] x 128 bits
         if (L < 8) mptr = base + (size_t)272 * (size_t)m + ((size_t)L * (size_t)m + (size_t)grow) * 2 + (gwarp >> 2);
       }

@@ -14,6 +14,10 @@
 //     stage; out-of-range rows / columns are zero-filled by the tensor map.  (A first version staged the operands with
 //     per-thread 16-byte cp.async into the SWIZZLE_NONE image: correct, but the L1's outstanding-request tracking capped
 //     it at ~12 B/clk/SM, 2.5 TB/s over the chip; bulk tensor copies do not go through it.)
+//     The activations h_l come TILE-BLOCKED from the training forward ([row / 128][column / 8][128][8]: the image its
+//     epilogue threads hold, written with fully coalesced 16-byte stores): a 128-row tile of a layer is 64 contiguous
+//     KB, moved by ONE 1-D cp.async.bulk into a ring of two tiles and used in place as a SWIZZLE_NONE MN-major operand
+//     (LBO = 128 B, SBO = 2 KB) by the tile's four 32-row A stages.  Each operand carries its own descriptor layout.
 //   * one elected thread issues tcgen05.mma kind::f16 (M = 128, N <= 256, K = 16) with a_major = b_major = MN:
 //     per stage 2 K-steps x (1 or 2) M-halves, fp32 accumulators in TMEM (2 x 256 columns = a 256 x 256 output tile).
 //   * split-K: the units (one output tile each: an (A matrix, B column range) pair) get a number of CTAs proportional
@@ -43,6 +47,9 @@ constexpr int kStages = 6;
 constexpr int kBoxCols = 64;                   // 128 bytes of bf16: the SWIZZLE_128B span
 constexpr int kBoxBytes = kRows * 128;         // one TMA box: 32 rows x 128 B = 4 KB
 constexpr int kOpBytes = 4 * kBoxBytes;        // one operand of a stage: up to 4 boxes (256 columns) = 16 KB
+constexpr int kTileRows = 128;                 // work is dealt in 128-row tiles = 4 stages (= one tile of the tile-blocked dump)
+constexpr int kTbTileBytes = 65536;            // one tile of a tile-blocked [rows,256] matrix: [32 runs][128 rows][8] bf16
+constexpr int kTbTiles = 2;                    // tile-blocked B operand: ring of 2 whole tiles
 constexpr int kThreads = 192;
 constexpr int kMaxUnits = 16;
 constexpr int kMaxMaps = 4;
@@ -55,7 +62,9 @@ constexpr int kEpochWindow = 2;
 
 struct Unit {
   int a_map, a_layer, a_col;   // A operand: tensor map, its third coordinate (layer), first column
-  int b_map, b_layer, b_col;   // B operand
+  int b_map, b_layer, b_col;   // B operand (tensor-map form)
+  const uint8_t* b_tb;         // B operand, tile-blocked form (non-NULL): one layer of the training forward's activation dump,
+                               // [tile = row / 128][column / 8][128 rows][8] bf16 - a tile is 64 contiguous KB
   float* out;                  // fp32 [Ma, ld_out] tile origin (row = A column, column = B column)
   int ld_out;
   int Ma;                      // 128 | 256
@@ -74,10 +83,14 @@ struct __align__(64) Params {
 
 struct __align__(1024) Smem {
   uint8_t a[kStages][kOpBytes];
-  uint8_t b[kStages][kOpBytes];
-  uint64_t full[kStages], empty[kStages], acc_full;
+  union {
+    uint8_t b[kStages][kOpBytes];              // B through tensor-map boxes: same stages as A
+    uint8_t bt[kTbTiles][kTbTileBytes];        // tile-blocked B: whole 128-row tiles, one 64 KB bulk copy each
+  };
+  uint64_t full[kStages], empty[kStages], bt_full[kTbTiles], bt_empty[kTbTiles], acc_full;
   uint32_t tmem_slot;
 };
+static_assert(sizeof(Smem) + 1024 <= 232448, "shared memory budget exceeded");
 
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
@@ -89,6 +102,9 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
 // MN-major SWIZZLE_128B descriptor of a stage operand: LBO = 4 KB (next 64 columns = next box), SBO = 1 KB (next 8 rows),
 // layout type 2 (SWIZZLE_128B) in bits [61,64)
 __device__ __forceinline__ uint64_t mn_desc(uint32_t saddr) { return umma_smem_desc(saddr, kBoxBytes, 1024) | (2ull << 61); }
+// MN-major SWIZZLE_NONE descriptor into a tile-blocked tile [column / 8][128 rows][8]: LBO = 128 B (next 8 rows = K),
+// SBO = 2 KB (next 8 columns); the start address selects the first row
+__device__ __forceinline__ uint64_t mn_desc_tb(uint32_t saddr) { return umma_smem_desc(saddr, 128, 2048); }
 
 __global__ void __launch_bounds__(kThreads, 1) pgn_wgrad_kernel(const __grid_constant__ Params p, int* __restrict__ status_g) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -102,11 +118,13 @@ __global__ void __launch_bounds__(kThreads, 1) pgn_wgrad_kernel(const __grid_con
   const bool active = (int)blockIdx.x >= u.cta0 && (int)blockIdx.x < u.cta0 + u.ncta;
   const int k = (int)blockIdx.x - u.cta0;
   const int ncta = u.ncta, Ma = u.Ma, Nb = u.Nb, Nmma = u.Nmma;
-  const long long n_stages_total = (p.m + kRows - 1) / kRows;
-  const long long n_mine = (active && n_stages_total > k) ? (n_stages_total - k + ncta - 1) / ncta : 0;
+  // CTA k of a unit takes the 128-row tiles k, k + ncta, ...; a tile is 4 stages of 32 rows
+  const long long n_tiles_total = (p.m + kTileRows - 1) / kTileRows;
+  const long long n_mine = 4 * ((active && n_tiles_total > k) ? (n_tiles_total - k + ncta - 1) / ncta : 0);
 
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
+    for (int s = 0; s < kTbTiles; ++s) { mbar_init(&sm.bt_full[s], 1); mbar_init(&sm.bt_empty[s], 1); }
     mbar_init(&sm.acc_full, 1);
     fence_mbar_init();
   }
@@ -125,15 +143,19 @@ __global__ void __launch_bounds__(kThreads, 1) pgn_wgrad_kernel(const __grid_con
       const CUtensorMap* ma = &p.maps[u.a_map];
       const CUtensorMap* mb = &p.maps[u.b_map];
       const int a_col = u.a_col, a_layer = u.a_layer, b_col = u.b_col, b_layer = u.b_layer;
+      const uint8_t* b_tb = u.b_tb;
       const int a_boxes = Ma / kBoxCols, b_boxes = (Nmma + kBoxCols - 1) / kBoxCols;
-      const uint32_t bytes = (uint32_t)(a_boxes + b_boxes) * kBoxBytes;
-      int s = 0;
-      uint32_t ph = 1;                             // "empty" barriers start released
-      int row = k * kRows;
+      const uint32_t bytes = (uint32_t)(a_boxes + (b_tb ? 0 : b_boxes)) * kBoxBytes;
+      const uint32_t bt_full0 = smem_u32(&sm.bt_full[0]), bt_empty0 = smem_u32(&sm.bt_empty[0]), bt_s0 = smem_u32(sm.bt[0]);
+      int s = 0, bts = 0;
+      uint32_t ph = 1, bt_ph = 1;                  // "empty" barriers start released
       int cur_e = 0;
       volatile int* ectr = p.epoch_ctr;
       const int n_all = p.n_ctas;
-      for (long long it = 0; it < n_mine; ++it, row += ncta * kRows) {
+      for (long long it = 0; it < n_mine; ++it) {
+        const long long tile = (long long)k + (it >> 2) * ncta;
+        const int sub = (int)(it & 3);
+        const int row = (int)(tile * kTileRows) + sub * kRows;
         const int e = row / kEpochRows;
         if (e != cur_e) {
           while (cur_e < e) { atomicAdd(p.epoch_ctr + cur_e, 1); ++cur_e; }
@@ -142,11 +164,18 @@ __global__ void __launch_bounds__(kThreads, 1) pgn_wgrad_kernel(const __grid_con
             while (ectr[e - kEpochWindow] < n_all && clock64() - t0 < 400000) __nanosleep(200);
           }
         }
+        if (b_tb && sub == 0) {                    // the tile's B operand: 64 contiguous KB, one bulk copy
+          if (!mbar_wait_s(bt_empty0 + bts * 8, bt_ph, status, 804)) break;
+          mbar_arrive_expect_tx_s(bt_full0 + bts * 8, (uint32_t)kTbTileBytes);
+          bulk_g2s_s(bt_s0 + bts * kTbTileBytes, b_tb + (size_t)tile * kTbTileBytes, (uint32_t)kTbTileBytes, bt_full0 + bts * 8);
+          if (++bts == kTbTiles) { bts = 0; bt_ph ^= 1; }
+        }
         if (!mbar_wait_s(empty0 + s * 8, ph, status, 801)) break;
         const uint32_t bar = full0 + s * 8;
         mbar_arrive_expect_tx_s(bar, bytes);
         for (int i = 0; i < a_boxes; ++i) tma_load_3d(a_s0 + s * kOpBytes + i * kBoxBytes, ma, a_col + i * kBoxCols, row, a_layer, bar);
-        for (int i = 0; i < b_boxes; ++i) tma_load_3d(b_s0 + s * kOpBytes + i * kBoxBytes, mb, b_col + i * kBoxCols, row, b_layer, bar);
+        if (!b_tb)
+          for (int i = 0; i < b_boxes; ++i) tma_load_3d(b_s0 + s * kOpBytes + i * kBoxBytes, mb, b_col + i * kBoxCols, row, b_layer, bar);
         if (++s == kStages) { s = 0; ph ^= 1; }
       }
       const int n_epochs = (int)((p.m + kEpochRows - 1) / kEpochRows);
@@ -160,21 +189,32 @@ __global__ void __launch_bounds__(kThreads, 1) pgn_wgrad_kernel(const __grid_con
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0 && n_mine > 0) {
       const uint32_t idesc = umma_idesc_bf16(128, Nmma) | (1u << 15) | (1u << 16);      // A and B MN-major
+      const bool b_is_tb = u.b_tb != nullptr;
+      const uint32_t bt_full0 = smem_u32(&sm.bt_full[0]), bt_s0 = smem_u32(sm.bt[0]);
       bool ok = true;
-      int s = 0;
-      uint32_t ph = 0;
+      int s = 0, bts = 0;
+      uint32_t ph = 0, bt_ph = 0;
       for (long long it = 0; it < n_mine; ++it) {
+        const int sub = (int)(it & 3);
+        if (b_is_tb && sub == 0) {
+          if (!mbar_wait_s(bt_full0 + bts * 8, bt_ph, status, 805)) { ok = false; break; }
+        }
         if (!mbar_wait_s(full0 + s * 8, ph, status, 802)) { ok = false; break; }
         tc_fence_after_sync();
         const uint32_t a0 = a_s0 + s * kOpBytes, b0 = b_s0 + s * kOpBytes;
+        const uint32_t bt0 = bt_s0 + bts * kTbTileBytes + sub * (kRows * 16);       // rows [32 sub, 32 sub + 32) of the tile
 #pragma unroll
-        for (int kk = 0; kk < kRows / 16; ++kk) {                       // 16 rows = 2 KB inside every box
-          const uint64_t bd = mn_desc(b0 + kk * 2048);
+        for (int kk = 0; kk < kRows / 16; ++kk) {                       // 16 rows = 2 KB inside every box / 256 B inside a run
+          const uint64_t bd = b_is_tb ? mn_desc_tb(bt0 + kk * 256) : mn_desc(b0 + kk * 2048);
           for (int h = 0; h < halves; ++h)                              // 128 A columns = 2 boxes
             umma_bf16(tmem + (uint32_t)h * 256u, mn_desc(a0 + h * (2 * kBoxBytes) + kk * 2048), bd, idesc, (it > 0 || kk > 0) ? 1u : 0u);
         }
         umma_commit(&sm.empty[s]);
         if (++s == kStages) { s = 0; ph ^= 1; }
+        if (b_is_tb && sub == 3) {
+          umma_commit(&sm.bt_empty[bts]);
+          if (++bts == kTbTiles) { bts = 0; bt_ph ^= 1; }
+        }
       }
       if (ok) umma_commit(&sm.acc_full);
     }
@@ -208,30 +248,36 @@ __global__ void __launch_bounds__(kThreads, 1) pgn_wgrad_kernel(const __grid_con
   if (warp == 0) { tc_fence_after_sync(); tmem_dealloc(tmem, 512); }
 }
 
-// alpha_linear.weight gradient: out[c] = sum_r w[r * w_stride] * X[r, c]  (d_sigma^T h7; a [1 x 256] "GEMM"), bf16 X
-__global__ void __launch_bounds__(256) pgn_weighted_colsum_kernel(const __nv_bfloat16* __restrict__ X, long long m, const float* __restrict__ w,
+// alpha_linear.weight gradient: out[c] = sum_r w[r * w_stride] * X[r, c]  (d_sigma^T h7; a [1 x 256] "GEMM") on the
+// tile-blocked activation dump X = [tile][column / 8][128 rows][8] bf16: warp w of a block owns the 8-column run
+// 8 * blockIdx.y + w; a warp load is 32 consecutive rows of its run = 512 contiguous bytes.
+__global__ void __launch_bounds__(256) pgn_weighted_colsum_kernel(const uint8_t* __restrict__ X, long long m, const float* __restrict__ w,
                                                                   int w_stride, float* __restrict__ out) {
-  // thread t owns columns 8 * (t & 31) .. +7 of rows (t >> 5) + 8 i: a warp reads one 512-byte row per instruction
-  const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, run = blockIdx.y * 8 + (threadIdx.x >> 5);
   float acc[8] = {};
-  for (long long r = (long long)blockIdx.x * 8 + rl; r < m; r += (long long)gridDim.x * 8) {
-    const uint4 v = __ldg(reinterpret_cast<const uint4*>(X + r * 256) + cg);
-    const float wr = __ldg(w + r * w_stride);
-    const uint32_t q[4] = {v.x, v.y, v.z, v.w};
+  const long long n_groups = (m + 31) / 32;                       // groups of 32 rows
+  for (long long g = blockIdx.x; g < n_groups; g += gridDim.x) {
+    const long long r = g * 32 + lane;
+    if (r < m) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(X + (size_t)(r >> 7) * 65536u + (size_t)run * 2048u + (size_t)(r & 127) * 16u));
+      const float wr = __ldg(w + r * w_stride);
+      const uint32_t q[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      acc[2 * e] = fmaf(wr, __uint_as_float(q[e] << 16), acc[2 * e]);
-      acc[2 * e + 1] = fmaf(wr, __uint_as_float(q[e] & 0xffff0000u), acc[2 * e + 1]);
+      for (int e = 0; e < 4; ++e) {
+        acc[2 * e] = fmaf(wr, __uint_as_float(q[e] << 16), acc[2 * e]);
+        acc[2 * e + 1] = fmaf(wr, __uint_as_float(q[e] & 0xffff0000u), acc[2 * e + 1]);
+      }
     }
   }
-  __shared__ float red[8][256];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) red[rl][cg * 8 + e] = acc[e];
-  __syncthreads();
-  float s = 0.f;
+  for (int e = 0; e < 8; ++e) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) s += red[i][threadIdx.x];
-  atomicAdd(out + threadIdx.x, s);
+    for (int off = 16; off > 0; off >>= 1) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], off);
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) atomicAdd(out + run * 8 + e, acc[e]);
+  }
 }
 
 // The feature_linear / views_linears.0 block that never exists at batch size (feature_linear has no activation,
@@ -329,7 +375,7 @@ static cudaError_t launch_units(Params& p, int n, long long m, int num_sms, int*
   }
   // CTAs per unit proportional to the bytes a stage streams (Ma + Nmma columns): every unit then sweeps the rows at the
   // same rate and shared operands are served by L2.  Largest-remainder rounding, at least one CTA per unit.
-  const long long n_stages = (m + kRows - 1) / kRows;
+  const long long n_stages = (m + kTileRows - 1) / kTileRows;      // CTAs are dealt whole 128-row tiles
   int grid = num_sms;
   if (grid < n) grid = n;
   double tot = 0;
@@ -370,7 +416,6 @@ cudaError_t pgn_launch_weight_grads(const void* dz_, const void* dG_, const void
                                     long long m, const float* d_raw, const float* bias_v, const float* w_f, const float* b_f,
                                     const float* w_v, int view_ld, float* flat, float* feat_bias, float* tm_scratch, int* epoch_ctr,
                                     int* status, int num_sms, cudaStream_t stream) {
-  const __nv_bfloat16* act = reinterpret_cast<const __nv_bfloat16*>(act_);
   size_t off[12], o = 0;
   for (int i = 0; i < 12; ++i) { off[i] = o; o += (size_t)kW_out[i] * (i == 10 ? view_ld : kW_in[i]); }
   cudaError_t e = cudaMemsetAsync(flat, 0, o * sizeof(float), stream);
@@ -381,12 +426,14 @@ cudaError_t pgn_launch_weight_grads(const void* dz_, const void* dG_, const void
   enum { kDz = 0, kDg = 1, kAct = 2, kEnc = 3 };
   if ((e = make_map(&p.maps[kDz], dz_, 256, 256, m, 8, m * 256)) != cudaSuccess) return e;            // dZ_l: [8][m][256]
   if ((e = make_map(&p.maps[kDg], dG_, 128, 128, m, 1, 0)) != cudaSuccess) return e;                   // dG:   [m][128]
-  if ((e = make_map(&p.maps[kAct], act_, 256, 256, m, 8, dump_rows * 256)) != cudaSuccess) return e;   // h_l:  [8][dump_rows][256], rows < m
+  p.maps[kAct] = p.maps[kDz];                                                                          // h_l: tile-blocked, no tensor map (b_tb)
   if ((e = make_map(&p.maps[kEnc], enc_, 1080, 1080, m, 1, 0)) != cudaSuccess) return e;               // input: [m][1080]
   int n = 0;
+  const uint8_t* act_b = reinterpret_cast<const uint8_t*>(act_);
   auto add = [&](int am, int al, int Ma, int bm, int bl, int bc, int Nb, float* out, int ld_out) {
     Unit& u = p.u[n++];
     u.a_map = am; u.a_layer = al; u.a_col = 0; u.b_map = bm; u.b_layer = bl; u.b_col = bc;
+    u.b_tb = bm == kAct ? act_b + (size_t)bl * (size_t)dump_rows * 512u : nullptr;     // activations: tile-blocked dump of layer bl
     u.out = out; u.ld_out = ld_out; u.Ma = Ma; u.Nb = Nb; u.Nmma = (Nb + 15) / 16 * 16; u.cta0 = 0; u.ncta = 0;
   };
   // pts_linears.0: dZ_0^T x_p (432 = 256 + 176 columns)
@@ -408,7 +455,7 @@ cudaError_t pgn_launch_weight_grads(const void* dz_, const void* dG_, const void
   add(kDg, 0, 128, kEnc, 0, 944, 136, flat + off[10] + 768, view_ld);      // (frame-code columns 904..919: pgn_framecode_backward)
   if ((e = launch_units(p, n, m, num_sms, status, epoch_ctr, stream)) != cudaSuccess) return e;
   // alpha_linear.weight = d_sigma^T h7
-  pgn_weighted_colsum_kernel<<<num_sms * 2, 256, 0, stream>>>(act + (size_t)7 * dump_rows * 256, m, d_raw + 3, 4, flat + off[8]);
+  pgn_weighted_colsum_kernel<<<dim3((unsigned)num_sms, 4), 256, 0, stream>>>(act_b + (size_t)7 * (size_t)dump_rows * 512u, m, d_raw + 3, 4, flat + off[8]);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   pgn_view_fold_grads_kernel<<<128 + 256, 256, 0, stream>>>(tm_scratch, bias_v, w_f, b_f, w_v, flat + off[10], flat + off[9], feat_bias, view_ld);
@@ -417,15 +464,17 @@ cudaError_t pgn_launch_weight_grads(const void* dz_, const void* dG_, const void
 
 // Generic entry for tests: out[Ma, Nb] (fp32, ld_out) += A[m, :Ma]^T B[m, :Nb]
 cudaError_t pgn_launch_wgrad_single(const void* A, int lda, int Ma, const void* B, int ldb, int Nb, long long m, float* out, int ld_out,
-                                    int n_ctas, int* epoch_ctr, int* status, cudaStream_t stream) {
+                                    int n_ctas, int b_tile_blocked, int* epoch_ctr, int* status, cudaStream_t stream) {
   if (m == 0) return cudaSuccess;
   Params p;
   cudaError_t e;
   if ((e = make_map(&p.maps[0], A, Ma, lda, m, 1, 0)) != cudaSuccess) return e;
-  if ((e = make_map(&p.maps[1], B, Nb, ldb, m, 1, 0)) != cudaSuccess) return e;
+  if (b_tile_blocked) p.maps[1] = p.maps[0];
+  else if ((e = make_map(&p.maps[1], B, Nb, ldb, m, 1, 0)) != cudaSuccess) return e;
   p.maps[2] = p.maps[0]; p.maps[3] = p.maps[0];
   Unit& u = p.u[0];
   u.a_map = 0; u.a_layer = 0; u.a_col = 0; u.b_map = 1; u.b_layer = 0; u.b_col = 0;
+  u.b_tb = b_tile_blocked ? reinterpret_cast<const uint8_t*>(B) : nullptr;
   u.out = out; u.ld_out = ld_out; u.Ma = Ma; u.Nb = Nb; u.Nmma = (Nb + 15) / 16 * 16; u.cta0 = 0; u.ncta = 0;
   return launch_units(p, 1, m, n_ctas, status, epoch_ctr, stream);
 }

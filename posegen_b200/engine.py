@@ -242,8 +242,9 @@ class Engine:
     def render_train(self, ray_batch, skts, cyls, pose_idx=None, nanfill_chunk=0, rand=None, dump_coarse=True, cams=None):
         """pgn_render_forward_train: the fused bf16 forward + per-layer activation dump for the weight gradients.
         Returns (outputs incl. the taps the backward needs, {"c": dump, "f": dump}); dump[p] is a flat bf16 buffer of
-        rows * 2304 elements: layers 0-7 row-major [rows,256] each, then the view layer [rows,128], then the ReLU mask
-        bits of layers 0-7 (`train.act_layer` / `train.act_masks` return the views), rows in (ray, sample) order.
+        rows * 2304 elements: layers 0-7 tile-blocked [rows/128][32][128][8] each (the kernel's coalesced operand-image
+        stores), then the view layer row-major [rows,128], then the ReLU mask bits of layers 0-7 (`train.act_layer`
+        returns a row-major copy / view, `train.act_masks` the mask area), rows in (ray, sample) order.
         rand: optional dict of CUDA fp32 tensors t_rand [n,64], u_is [n,16], noise0 [n,64], noise [n,80] (training-time
         randomness drawn by the caller; missing keys = deterministic)."""
         inp, keep = self._inputs(ray_batch, skts, cyls, pose_idx, nanfill_chunk, "bf16", cams=cams)
@@ -445,13 +446,15 @@ class Engine:
                                                    _ptr(g_codes), self._stream()))
         return g_codes
 
-    def debug_wgrad(self, A, B, Ma, Nb, n_ctas=8, out=None):
-        """pgn_debug_wgrad: out[Ma, Nb] += A[:, :Ma]^T B[:, :Nb] (bf16 row-major operands, fp32 result) through the split-K kernel."""
+    def debug_wgrad(self, A, B, Ma, Nb, n_ctas=8, out=None, b_tile_blocked=False):
+        """pgn_debug_wgrad: out[Ma, Nb] += A[:, :Ma]^T B[:, :Nb] (bf16 operands, fp32 result) through the split-K kernel.
+        A row-major [m, >=Ma]; B row-major [m, >=Nb], or with b_tile_blocked a flat 256-column buffer in the activation
+        dump's tile-blocked layout (`train.to_tile_blocked`)."""
         m = A.shape[0]
         if out is None:
             out = torch.zeros((Ma, Nb), dtype=torch.float32, device=A.device)
-        _lib.check(self.lib.pgn_debug_wgrad(self.handle, _ptr(A), A.stride(0), Ma, _ptr(B), B.stride(0), Nb, m, _ptr(out), out.stride(0),
-                                            int(n_ctas), self._stream()))
+        _lib.check(self.lib.pgn_debug_wgrad(self.handle, _ptr(A), A.stride(0), Ma, _ptr(B), 256 if b_tile_blocked else B.stride(0), Nb, m,
+                                            _ptr(out), out.stride(0), int(n_ctas), 1 if b_tile_blocked else 0, self._stream()))
         return out
 
     def mlp(self, net_id, enc, precision="bf16"):

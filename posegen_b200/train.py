@@ -50,12 +50,24 @@ ACT_ROW_ELEMS = 2304          # bf16 elements per dump row: 8 x 256 + 128 activa
 
 
 def act_layer(acts: torch.Tensor, l: int, m: int) -> torch.Tensor:
-    """Activation matrix of layer l (0..7: 256 columns, 8: view layer, 128) for the first m rows of the kernel's
-    row-major dump (a view, no copy): [m, cols] bf16."""
+    """Activation matrix [m, cols] bf16 of layer l (0..7: 256 columns, 8: view layer, 128) for the first m rows of the
+    kernel's dump.  The trunk layers are stored tile-blocked ([rows/128][32][128][8]: the UMMA operand image, coalesced
+    stores in the forward, one bulk copy per tile in the weight-gradient kernel) and come back as a row-major COPY
+    (tests, the matrix-product formulation); the view layer is a row-major view."""
     rows = acts.numel() // ACT_ROW_ELEMS
     if l < 8:
-        return acts[l * rows * 256:(l + 1) * rows * 256].view(rows, 256)[:m]
+        tb = acts[l * rows * 256:(l + 1) * rows * 256].view(rows // 128, 32, 128, 8)
+        return tb.permute(0, 2, 1, 3).reshape(rows, 256)[:m]
     return acts[8 * rows * 256:rows * 2176].view(rows, 128)[:m]
+
+
+def to_tile_blocked(x: torch.Tensor) -> torch.Tensor:
+    """Row-major [rows, 256] -> the dump's tile-blocked layout (rows padded to a multiple of 128 with zeros), flat."""
+    rows = x.shape[0]
+    pad = (-rows) % 128
+    if pad:
+        x = torch.cat([x, x.new_zeros((pad, x.shape[1]))], 0)
+    return x.reshape(-1, 128, 32, 8).permute(0, 2, 1, 3).contiguous().reshape(-1)
 
 
 def act_masks(acts: torch.Tensor):
@@ -108,8 +120,10 @@ def mlp_backward(params: Dict[str, torch.Tensor], enc: torch.Tensor, acts: torch
         x_p, d_emb = enc[:, :432], enc[:, 432:]
     if mask_dump is not None and (want_weight_grad or chain is None or view_delta is None):
         raise ValueError("a masks-only dump serves the input-gradient chain only (want_weight_grad=False, chain, view_delta)")
+    fused_w = want_weight_grad and wgrad is not None and chain is not None
     if mask_dump is None:
-        H = [act_layer(acts, l, m) for l in range(8)]
+        # (row-major copies of the tile-blocked trunk activations: only the matrix-product formulation reads them)
+        H = [act_layer(acts, l, m) for l in range(8)] if (want_weight_grad and not fused_w) or chain is None else None
         G = act_layer(acts, 8, m)
     P = {k: v.detach() for k, v in params.items()}
     # bf16 trunk weights: only the input-gradient GEMMs and the layer-by-layer fallback read them
@@ -125,7 +139,6 @@ def mlp_backward(params: Dict[str, torch.Tensor], enc: torch.Tensor, acts: torch
         bias_v, g_rgb = fuse(dG, G, d_raw[:, :3], P["rgb_linear.weight"], False, wg)
     W_v, W_f, b_f = P["views_linears.0.weight"], P["feature_linear.weight"], P["feature_linear.bias"]
     W_vf = W_v[:, :256]
-    fused_w = wg and wgrad is not None and chain is not None
     if wg:
         g["rgb_linear.weight"] = g_rgb
         g["rgb_linear.bias"] = d_raw[:, :3].sum(0)

@@ -414,6 +414,14 @@ def test_wgrad_split_k_kernel_matches_torch(engine, m, Ma, Nb, n_ctas):
     err = float((got.double() - want).abs().max())
     scale = float(want.abs().max())
     assert err <= 2e-4 * max(1.0, scale) + 1e-3 * (m ** 0.5) * 1e-3, (err, scale)
+    # the same product with B in the tile-blocked layout of the activation dump (one 64 KB bulk copy per 128-row tile,
+    # SWIZZLE_NONE descriptor)
+    if Nb == 256:
+        from posegen_b200.train import to_tile_blocked
+        got_tb = engine.debug_wgrad(A, to_tile_blocked(B.contiguous()), Ma, Nb, n_ctas=n_ctas, b_tile_blocked=True)
+        torch.cuda.synchronize()
+        engine.check_status()
+        assert float((got_tb.double() - want).abs().max()) <= 2e-4 * max(1.0, scale) + 1e-3 * (m ** 0.5) * 1e-3
     # accumulates into `out` (split-K partials are added): a second call doubles the result
     got2 = engine.debug_wgrad(A, B, Ma, Nb, n_ctas=n_ctas, out=got.clone())
     assert float((got2.double() - 2 * want).abs().max()) <= 4e-4 * max(1.0, scale) + 2e-6 * m ** 0.5

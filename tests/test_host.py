@@ -180,7 +180,7 @@ def test_hmr_input_oracle_properties():
 
 def test_mlp_backward_matches_autograd_on_cpu():
     """Host logic of the training step (posegen_b200/train.py): the GEMM weight / input gradients of one NeRF MLP,
-    fed with an activation dump in the kernel's layout (row-major per layer) built from a torch forward and a torch
+    fed with an activation dump in the kernel's layout (trunk layers tile-blocked, view layer row-major) built from a torch forward and a torch
     restatement of the fused delta pass (`pgn_mlp_delta`), against autograd through the oracle's nerf_forward."""
     import numpy as np
     import torch
@@ -209,8 +209,11 @@ def test_mlp_backward_matches_autograd_on_cpu():
         g = torch.relu(torch.nn.functional.linear(torch.cat([feat, x_v], -1), net["views_linears.0.weight"], net["views_linears.0.bias"]))
         rows = 256
         dump = torch.zeros((rows * 2304,), dtype=torch.bfloat16)            # 2176 activations + 128 (mask bits, unused here) per row
-        for l in range(8):
-            dump[l * rows * 256:(l + 1) * rows * 256].view(rows, 256)[:m] = acts[l].to(torch.bfloat16)
+        from posegen_b200.train import to_tile_blocked
+        for l in range(8):                                                    # trunk layers: tile-blocked like the kernel's stores
+            full = torch.zeros((rows, 256), dtype=torch.bfloat16)
+            full[:m] = acts[l].to(torch.bfloat16)
+            dump[l * rows * 256:(l + 1) * rows * 256] = to_tile_blocked(full)
         dump[8 * rows * 256:rows * 2176].view(rows, 128)[:m] = g.to(torch.bfloat16)
 
     def fuse(dh, act, rs, wr, has_input, want_wsum):          # what pgn_mlp_delta computes, in torch
@@ -279,7 +282,13 @@ def test_activation_dump_views():
     rows, m = 1024, 1000
     buf = torch.arange(rows * ACT_ROW_ELEMS, dtype=torch.float32).to(torch.bfloat16)
     assert act_layer(buf, 0, m).shape == (m, 256) and act_layer(buf, 8, m).shape == (m, 128)
-    assert act_layer(buf, 3, m).data_ptr() == buf.data_ptr() + 3 * rows * 256 * 2
     assert act_layer(buf, 8, m).data_ptr() == buf.data_ptr() + 8 * rows * 256 * 2
+    # trunk layers are tile-blocked: element (r, c) of layer l sits at ((r // 128) * 32 + c // 8) * 1024 + (r % 128) * 8 + c % 8
+    from posegen_b200.train import to_tile_blocked
+    x = torch.randn(rows, 256).to(torch.bfloat16)
+    buf[3 * rows * 256:4 * rows * 256] = to_tile_blocked(x)
+    assert torch.equal(act_layer(buf, 3, m), x[:m])
+    r, c = 517, 203
+    assert buf[3 * rows * 256 + ((r // 128) * 32 + c // 8) * 1024 + (r % 128) * 8 + c % 8] == x[r, c]
     mask, r = act_masks(buf)
     assert r == rows and mask.data_ptr() == buf.data_ptr() + rows * 4352 and mask.numel() * 2 == rows * 256
