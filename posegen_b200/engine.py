@@ -398,11 +398,17 @@ class Engine:
                                                         _ptr(dz), _ptr(colsum), int(layer_mask), self._stream()))
         return dz, colsum
 
-    def mlp_weight_grads(self, net_id, dz, dG, acts, enc, d_raw, bias_v):
+    def weight_grad_floats(self) -> int:
+        """Floats of the flat weight-gradient buffer of one net (pgn_weight_grad_floats)."""
+        return int(self.lib.pgn_weight_grad_floats(self.handle))
+
+    def mlp_weight_grads(self, net_id, dz, dG, acts, enc, d_raw, bias_v, out=None):
         """pgn_mlp_weight_grads: every weight gradient of one NeRF MLP as one split-K tcgen05 kernel (+ two small fold
         kernels).  dz bf16 [8,m,256], dG bf16 [m,128], acts = the pass's activation dump (flat bf16), enc bf16 [m,1080],
         d_raw fp32 [m,4], bias_v fp32 [128].  Returns ({'<layer>.weight': fp32 view}, feature_linear.bias grad [256]); the
-        views share one flat buffer in the C ABI's layer order (rgb_linear.weight is left zero: `mlp_delta` produces it)."""
+        views share one flat buffer in the C ABI's layer order (rgb_linear.weight is left zero: `mlp_delta` produces it);
+        `out`: an fp32 CUDA buffer of `weight_grad_floats()` elements to use as that flat buffer (the training step's
+        gradient arena, so that one all-reduce covers every gradient)."""
         m = dG.shape[0]
         for t, shape, dt in ((dz, (8, m, 256), torch.bfloat16), (dG, (m, 128), torch.bfloat16), (enc, (m, 1080), torch.bfloat16),
                              (d_raw, (m, 4), torch.float32), (bias_v, (128,), torch.float32)):
@@ -412,7 +418,9 @@ class Engine:
             raise ValueError("acts must be the flat bf16 activation dump")
         rows = acts.numel() // 2304
         n = int(self.lib.pgn_weight_grad_floats(self.handle))
-        flat = torch.empty((n,), dtype=torch.float32, device=dG.device)
+        if out is not None and (out.numel() != n or out.dtype != torch.float32 or not out.is_contiguous() or out.device != dG.device):
+            raise ValueError("out must be a contiguous fp32 buffer of weight_grad_floats() elements on the operands' device")
+        flat = torch.empty((n,), dtype=torch.float32, device=dG.device) if out is None else out
         fb = torch.empty((256,), dtype=torch.float32, device=dG.device)
         _lib.check(self.lib.pgn_mlp_weight_grads(self.handle, int(net_id), _ptr(dz), _ptr(dG), _ptr(acts), rows, _ptr(enc), m,
                                                  _ptr(d_raw), _ptr(bias_v), _ptr(flat), _ptr(fb), self._stream()))

@@ -241,8 +241,17 @@ class _RenderTrainFn(torch.autograd.Function):
         want_w = any(ctx.needs_input_grad[7:])               # False for a frozen NeRF (the GAN step)
         order = param_order(rc.network)
         d_skts = None
+        # Gradient arena: every weight / bias gradient of both nets lives in ONE fp32 buffer (the weight-gradient kernel
+        # writes its flat result straight into it, the small tensors are copied behind), so that the data-parallel step
+        # needs one in-place all-reduce and no flatten / scatter copies (`allreduce_gradients`).
+        fused = want_w and USE_DELTA_CHAIN and USE_WGRAD_KERNEL
+        n_w = eng.weight_grad_floats() if fused else 0
+        n_small = 8 * 256 + 1 + 256 + 128 + 3 + 3 * 128 + rc.n_framecodes * 16
+        arena = torch.empty((2 * (n_w + n_small),), dtype=torch.float32, device=rb.device) if fused else None
+        net_no = -1
         for net, acts, z, raw_p, gr, ga, nz in ((rc.network, ctx.acts["c"], z_c, raw0, g_rgb0, g_acc0, rand.get("noise0")),
                                                 (rc.network_fine, ctx.acts["f"], z_fine, raw, g_rgb, g_acc, rand.get("noise"))):
+            net_no += 1
             if (gr is None and ga is None) or not (want_w or want_sk):      # the loss does not read this pass
                 grads += [None] * len(order)
                 continue
@@ -255,13 +264,25 @@ class _RenderTrainFn(torch.autograd.Function):
             net_id = 0 if net is rc.network else 1
             gd = mlp_backward(pd, enc, acts, d_raw.reshape(-1, 4), eng.mlp_delta, want_input_grad=want_sk, want_weight_grad=want_w,
                               chain=functools.partial(eng.mlp_delta_chain_net, net_id) if USE_DELTA_CHAIN else None,
-                              wgrad=functools.partial(eng.mlp_weight_grads, net_id) if (USE_DELTA_CHAIN and USE_WGRAD_KERNEL) else None,
+                              wgrad=functools.partial(eng.mlp_weight_grads, net_id,
+                                                      out=arena[net_no * (n_w + n_small):net_no * (n_w + n_small) + n_w] if fused else None)
+                              if (USE_DELTA_CHAIN and USE_WGRAD_KERNEL) else None,
                               input_grads=functools.partial(eng.mlp_input_grads, net_id) if (USE_DELTA_CHAIN and USE_INPUT_GRAD_KERNEL) else None)
             if want_w and rc.n_framecodes:      # Optcodes: the 16 frame-code columns of views_linears.0 and the codes themselves
                 gv = gd["views_linears.0.weight"]
                 if tuple(gv.shape) != (128, 920) or not gv.is_contiguous():
                     raise RuntimeError("frame-code gradients need the fused weight-gradient path (USE_WGRAD_KERNEL)")
                 gd["framecodes.codes.weight"] = eng.framecode_backward(net_id, gd["_dG"], n, z.shape[1], ctx.cams, gv)
+            if fused:            # small tensors (biases, rgb head, frame codes) -> the arena's tail of this net
+                o = net_no * (n_w + n_small) + n_w
+                base = arena.untyped_storage().data_ptr()
+                for k in order:
+                    t = gd[k]
+                    if t.untyped_storage().data_ptr() != base:
+                        slot = arena[o:o + t.numel()].view(t.shape)
+                        slot.copy_(t)
+                        gd[k] = slot
+                        o += t.numel()
             grads += [gd[k].reshape(pd[k].shape).to(pd[k].dtype) for k in order] if want_w else [None] * len(order)
             if want_sk:          # pose gradient: dL/d(network input) -> dL/d skts (per ray), both passes add up
                 d = eng.encode_backward_bf16(rb, sk, cy, z, gd["_g_xp"], gd["_g_d"])
@@ -303,9 +324,21 @@ def render_train(rc, ray_batch, skts, cyls, nanfill_chunk=None, perturb: float =
 
 
 def allreduce_gradients(parameters, average: bool = True):
-    """One all-reduce of the flattened gradient bucket (NCCL on GPUs, gloo in the CPU tests)."""
+    """One all-reduce of the gradient bucket (NCCL on GPUs, gloo in the CPU tests).  The training backward hands out
+    gradients that are views of one arena buffer: then the all-reduce runs in place on that buffer - one collective, no
+    flatten / scatter copies.  Gradients from anywhere else are flattened, reduced and copied back."""
     ps = [p for p in parameters if p.grad is not None]
     if not ps or not dist.is_initialized() or dist.get_world_size() == 1:
+        return
+    g0 = ps[0].grad
+    if all(p.grad.is_contiguous() and p.grad.dtype == g0.dtype and p.grad.device == g0.device and
+           p.grad.untyped_storage().data_ptr() == g0.untyped_storage().data_ptr() for p in ps):
+        lo = min(p.grad.storage_offset() for p in ps)
+        hi = max(p.grad.storage_offset() + p.grad.numel() for p in ps)
+        flat = torch.empty(0, dtype=g0.dtype, device=g0.device).set_(g0.untyped_storage(), lo, (hi - lo,))
+        dist.all_reduce(flat)
+        if average:
+            flat /= dist.get_world_size()
         return
     flat = torch.cat([p.grad.reshape(-1) for p in ps])
     dist.all_reduce(flat)

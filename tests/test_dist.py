@@ -56,6 +56,20 @@ def _grad_worker(rank, world, port, ok):
     good = net[1].bias.grad is None
     for i, p in enumerate(list(net.parameters())[:3]):
         good &= bool(torch.allclose(p.grad, torch.full_like(p, 1.5 * (i + 1))))     # mean of ranks' (1, 2) * (i + 1)
+    # gradients that are views of one arena buffer (what the training backward hands out): one in-place all-reduce,
+    # the views see the result, untouched gaps of the arena stay out of the parameters
+    arena = torch.full((200,), 1000.0)
+    o = 3
+    for i, p in enumerate(net.parameters()):
+        v = arena[o:o + p.numel()].view(p.shape)
+        v.fill_(float(rank + 1) * (i + 2))
+        p.grad = v
+        o += p.numel() + 2
+    allreduce_gradients(net.parameters(), average=True)
+    for i, p in enumerate(net.parameters()):
+        good &= bool(torch.allclose(p.grad, torch.full_like(p, 1.5 * (i + 2))))
+        good &= p.grad.untyped_storage().data_ptr() == arena.untyped_storage().data_ptr()
+    good &= float(arena[0]) == 1000.0                          # outside [lo, hi) nothing was reduced
     ok[rank] = int(good)
     dist.destroy_process_group()
 

@@ -479,3 +479,21 @@ def test_input_grad_kernel_matches_matrix_products(engine, m):
         assert got.shape == want.shape
         err = float((got.double() - want).abs().max())
         assert err <= 8e-3 * max(1.0, float(want.abs().max())), err               # one bf16 rounding of the result
+
+
+def test_training_gradients_share_one_arena(engine, train_case):
+    """Every weight / bias gradient of both nets is a view of ONE buffer after backward (the weight-gradient kernel writes
+    into it, the small tensors are copied behind): the data-parallel all-reduce is a single in-place collective."""
+    frame, ckpt, rb, tgt = train_case
+    n, dev = 512, torch.device("cuda")
+    rc = raycaster_from_checkpoint(ckpt, device="cuda", precision="bf16")
+    rc.train()
+    ret = rc(torch.as_tensor(rb[:n], device=dev), N_samples=64, N_importance=16, kp_batch=None, skts=torch.as_tensor(frame.pose.skts, device=dev),
+             cyls=torch.as_tensor(frame.pose.cyl, device=dev), bones=None, cams=None, perturb=0., raw_noise_std=0.)
+    t = torch.as_tensor(tgt[:n], device=dev)
+    (((ret["rgb_map"] + (1 - ret["acc_map"][:, None]) - t) ** 2).mean() + ((ret["rgb0"] + (1 - ret["acc0"][:, None]) - t) ** 2).mean()).backward()
+    ps = [p for p in rc.parameters() if p.grad is not None]
+    assert len(ps) == 48
+    assert len({p.grad.untyped_storage().data_ptr() for p in ps}) == 1
+    spans = sorted((p.grad.storage_offset(), p.grad.storage_offset() + p.grad.numel()) for p in ps)
+    assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:]))            # disjoint views
