@@ -120,6 +120,9 @@ typedef struct pgn_render_inputs {
    * frame-code index per ray.  NULL or an index outside [0, n_framecodes) selects the mean code, the reference's
    * evaluation rule for idx < 0 (core/networks/embedding.py:23-24).  Ignored by a context without frame codes. */
   const int32_t* cams;
+  /* ABI v2: the `lindisp` kwarg (core/raycasters.py:650-663 -> sample_from_lineseg, core/utils/ray_utils.py:224-227):
+   * non-zero = the 64 coarse samples are linear in inverse depth, z = 1 / (1/near (1 - t) + 1/far t). */
+  int32_t        lindisp;
 } pgn_render_inputs;
 
 /* Outputs of one render call (core/raycasters.py:711-724).  Any pointer may be NULL

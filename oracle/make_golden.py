@@ -115,7 +115,7 @@ class Taps:
         return torch.cat(self.data[key], 0).numpy()
 
 
-def reference_render(render_kwargs, frame, ckpt, chunk=4096, cyl_override=None, cams=None):
+def reference_render(render_kwargs, frame, ckpt, chunk=4096, cyl_override=None, cams=None, lindisp=None):
     from core.trainer import render
     rcast = render_kwargs["ray_caster"]
     rcast.load_state_dict(to_torch_ckpt(ckpt))
@@ -124,6 +124,8 @@ def reference_render(render_kwargs, frame, ckpt, chunk=4096, cyl_override=None, 
     rays = (torch.from_numpy(frame.rays_o), torch.from_numpy(frame.rays_d))
     cyl = frame.pose.cyl if cyl_override is None else cyl_override
     exp = lambda a: torch.from_numpy(np.ascontiguousarray(a))[None].expand(n, *a.shape).clone()  # noqa: E731
+    if lindisp is not None:
+        render_kwargs = dict(render_kwargs, lindisp=lindisp)
     taps = Taps().install()
     try:
         with contextlib.redirect_stdout(io.StringIO()), torch.no_grad():
@@ -135,7 +137,7 @@ def reference_render(render_kwargs, frame, ckpt, chunk=4096, cyl_override=None, 
     return {k: v.cpu().numpy() for k, v in out.items()}, taps
 
 
-def oracle_render(frame, ckpt, chunk=4096, cyl_override=None, dtype=torch.float32, cams=None):
+def oracle_render(frame, ckpt, chunk=4096, cyl_override=None, dtype=torch.float32, cams=None, lindisp=False):
     rb = torch.from_numpy(syn.ray_batch(frame.rays_o, frame.rays_d)).to(dtype)
     cyl = frame.pose.cyl if cyl_override is None else cyl_override
     taps = {}
@@ -144,10 +146,10 @@ def oracle_render(frame, ckpt, chunk=4096, cyl_override=None, dtype=torch.float3
     if rb.shape[0] <= chunk:
         with torch.no_grad():
             out = orc.render_rays(rb, torch.from_numpy(frame.pose.skts).to(dtype)[None].expand(rb.shape[0], -1, -1, -1),
-                                  torch.from_numpy(cyl).to(dtype)[None].expand(rb.shape[0], -1), nets, emb, taps=taps, cams=cams)
+                                  torch.from_numpy(cyl).to(dtype)[None].expand(rb.shape[0], -1), nets, emb, taps=taps, cams=cams, lindisp=lindisp)
     else:
         out = orc.render(rb, torch.from_numpy(frame.pose.skts).to(dtype), torch.from_numpy(cyl).to(dtype),
-                         nets, emb, chunk=chunk, cams=cams)
+                         nets, emb, chunk=chunk, cams=cams, lindisp=lindisp)
     return {k: v.numpy() for k, v in out.items()}, {k: v.numpy() for k, v in taps.items()}
 
 
@@ -186,7 +188,7 @@ def compare(name, ref, got):
 
 
 def make_case(render_kwargs, name, pose_seed, res, weight_seed, alpha_gain, full_taps,
-              calibrated=False, shrink_cyl=None, chunk=4096):
+              calibrated=False, shrink_cyl=None, chunk=4096, lindisp=False):
     print(f"[{name}] pose_seed={pose_seed} res={res} weight_seed={weight_seed} gain={alpha_gain} "
           f"calibrated={calibrated} shrink_cyl={shrink_cyl}")
     frame = syn.synthetic_frame(pose_seed, res, res)
@@ -201,13 +203,13 @@ def make_case(render_kwargs, name, pose_seed, res, weight_seed, alpha_gain, full
         # SURVEY.md §8d calibrated-head recipe: one zero-bias pass, theta per net
         for key, raw_key in (("network_fn_state_dict", "raw_coarse"), ("network_fine_state_dict", "raw_fine")):
             ckpt[key]["alpha_linear.bias"] = np.zeros_like(ckpt[key]["alpha_linear.bias"])
-        _, taps0 = reference_render(render_kwargs, frame, ckpt, chunk)
+        _, taps0 = reference_render(render_kwargs, frame, ckpt, chunk, lindisp=lindisp)
         for key, raw_key in (("network_fn_state_dict", "raw_coarse"), ("network_fine_state_dict", "raw_fine")):
             sig_far = float(taps0.get(raw_key)[:, -1, 3].max())
             syn.calibrate_alpha_head(ckpt[key], sig_far)
             extra[f"sigma_far_max_{raw_key}"] = np.float32(sig_far)
-    ref, taps = reference_render(render_kwargs, frame, ckpt, chunk, cyl)
-    got, otaps = oracle_render(frame, ckpt, chunk, cyl)
+    ref, taps = reference_render(render_kwargs, frame, ckpt, chunk, cyl, lindisp=lindisp)
+    got, otaps = oracle_render(frame, ckpt, chunk, cyl, lindisp=lindisp)
     worst = compare(name, ref, got)
     for k in ("near", "far", "z_coarse", "z_samples", "z_fine", "sorted_idxs", "pdf_inds", "raw_coarse", "raw_fine"):
         if k in otaps:
@@ -228,6 +230,8 @@ def make_case(render_kwargs, name, pose_seed, res, weight_seed, alpha_gain, full
         "rgb0": ref["rgb0"], "disp0": ref["disp0"], "acc0": ref["acc0"],
     }
     fix.update(extra)
+    if lindisp:
+        fix["meta_lindisp"] = np.bool_(True)
     if full_taps:
         fix.update({
             "alpha": ref["alpha"], "alpha0": ref["alpha0"],
@@ -342,12 +346,19 @@ def main():
         # E: 32x32 with a shrunken cylinder so bbox-corner rays miss it: chunk-level NaN fill
         make_case(render_kwargs, "e_32_nanfill", pose_seed=3, res=32, weight_seed=0, alpha_gain=400., full_taps=False,
                   shrink_cyl=0.8)
+        # G: 32x32, calibrated head, coarse samples linear in inverse depth (render_kwargs['lindisp'] = True)
+        make_case(render_kwargs, "g_32_lindisp", pose_seed=5, res=32, weight_seed=3, alpha_gain=None, full_taps=False,
+                  calibrated=True, lindisp=True)
         # F: 64x64, h36m_prot2-shaped model (opt_framecode = True, 5 frame codes), calibrated head, + density-only query
         make_framecode_case(build_framecode_raycaster(tmp, 5), "f_64_framecode", pose_seed=4, res=64, weight_seed=2, n_framecodes=5)
 
 
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "--framecode-only":
+    if len(sys.argv) > 1 and sys.argv[1] == "--lindisp-only":
+        with tempfile.TemporaryDirectory() as tmp:
+            rk, _ = ref_shim.build_reference_raycaster(tmp)
+            make_case(rk, "g_32_lindisp", pose_seed=5, res=32, weight_seed=3, alpha_gain=None, full_taps=False, calibrated=True, lindisp=True)
+    elif len(sys.argv) > 1 and sys.argv[1] == "--framecode-only":
         with tempfile.TemporaryDirectory() as tmp:
             ref_shim.install()
             make_framecode_case(build_framecode_raycaster(tmp, 5), "f_64_framecode", pose_seed=4, res=64, weight_seed=2, n_framecodes=5)

@@ -64,10 +64,13 @@ def _nanmean32(x):
 # core/utils/ray_utils.py:204-251  sample_from_lineseg (lindisp False).  perturb > 0 (training): the
 # stratified jitter takes its uniform numbers from `t_rand` [N,n_samples] (the reference draws torch.rand).
 # ----------------------------------------------------------------------------
-def coarse_z_vals(near, far, n_samples, t_rand=None):
+def coarse_z_vals(near, far, n_samples, t_rand=None, lindisp=False):
     t = torch.linspace(0., 1., steps=n_samples, dtype=near.dtype, device=near.device)
     t = t.expand(near.shape[0], n_samples)
-    z_vals = near * (1. - t) + far * t
+    if not lindisp:
+        z_vals = near * (1. - t) + far * t
+    else:                                   # linear in inverse depth (ray_utils.py:224-227)
+        z_vals = 1. / (1. / near * (1. - t) + 1. / far * t)
     if t_rand is not None:
         mids = .5 * (z_vals[..., 1:] + z_vals[..., :-1])
         upper = torch.cat([mids, z_vals[..., -1:]], -1)
@@ -233,14 +236,14 @@ def importance_z_vals(z_vals, weights, n_importance, u=None):
 # core/raycasters.py:361-474  render_rays  (eval path: perturb 0, no noise)
 # ----------------------------------------------------------------------------
 def render_rays(ray_batch, skts, cyls, nets, emb, n_samples=64, n_importance=16,
-                density_scale=1.0, taps=None, cams=None):
+                density_scale=1.0, taps=None, cams=None, lindisp=False):
     """ray_batch [N,11]; skts [N,24,4,4]; cyls [N,5]; nets = (coarse, fine) state dicts.
     Returns the reference's output dict (core/raycasters.py:711-724).  `taps`, if a
     dict, receives intermediate tensors for stage-level parity tests."""
     rays_o, rays_d = ray_batch[:, 0:3], ray_batch[:, 3:6]
     near, far = ray_batch[:, 6:7], ray_batch[:, 7:8]
     near, far = near_far_in_cylinder(rays_o, rays_d, cyls, near, far)
-    z_vals = coarse_z_vals(near, far, n_samples)
+    z_vals = coarse_z_vals(near, far, n_samples, lindisp=lindisp)
     pts = rays_o[:, None, :] + rays_d[:, None, :] * z_vals[:, :, None]
     enc = encode(pts, rays_d, skts, emb)
     raw = nerf_forward(enc.reshape(-1, enc.shape[-1]), nets[0],

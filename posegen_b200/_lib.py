@@ -42,7 +42,7 @@ class RenderInputs(C.Structure):
     _fields_ = [("ray_batch", C.c_void_p), ("n_rays", C.c_int64), ("skts", C.c_void_p), ("skts_stride", C.c_int64),
                 ("cyls", C.c_void_p), ("cyls_stride", C.c_int64), ("pose_idx", C.c_void_p),
                 ("nanfill_chunk", C.c_int64), ("precision", C.c_int32), ("chunk_starts", C.c_void_p), ("n_chunks", C.c_int64),
-                ("cams", C.c_void_p)]
+                ("cams", C.c_void_p), ("lindisp", C.c_int32)]
 
 
 class RenderOutputs(C.Structure):

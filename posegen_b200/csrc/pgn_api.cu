@@ -261,6 +261,7 @@ static PgnRayRefs make_refs(const pgn_context* c, const pgn_render_inputs* in) {
   r.ray_batch = in->ray_batch; r.n_rays = in->n_rays; r.skts = in->skts; r.skts_stride = in->skts_stride;
   r.cyls = in->cyls; r.cyls_stride = in->cyls_stride; r.pose_idx = in->pose_idx;
   r.cams = c->n_codes > 0 ? in->cams : nullptr; r.n_codes = c->n_codes;
+  r.lindisp = in->lindisp != 0;
   return r;
 }
 

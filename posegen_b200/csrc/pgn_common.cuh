@@ -42,6 +42,7 @@ struct PgnRayRefs {
   const int*     cams;          // optional [n] frame-code index per ray (Optcodes, core/networks/embedding.py:4-46); NULL or
                                 // an index outside [0, n_codes) selects the mean code (the reference's eval rule for idx < 0)
   int            n_codes;       // rows of the per-net frame-code tables (0: the model has no frame codes)
+  int            lindisp;       // coarse samples linear in inverse depth (sample_from_lineseg(lindisp=True), ray_utils.py:224-227)
 };
 
 // row of the frame-code tables for ray i: the code of its camera, or row n_codes = the mean code
@@ -94,17 +95,19 @@ __device__ __forceinline__ void pgn_near_far_ray(const float* __restrict__ rb, c
   new_far  = __fadd_rn(near, __fdiv_rn(__fadd_rn(K, Q), scale));
 }
 
-// sample_from_lineseg, core/utils/ray_utils.py:204-251 (perturb=0, lindisp=False)
-__device__ __forceinline__ float pgn_coarse_z(float near, float far, float t) {
+// sample_from_lineseg, core/utils/ray_utils.py:204-251 (perturb=0):
+//   z = near (1 - t) + far t,   or with lindisp   z = 1 / (1/near (1 - t) + 1/far t)
+__device__ __forceinline__ float pgn_coarse_z(float near, float far, float t, int lindisp = 0) {
+  if (lindisp) return __fdiv_rn(1.0f, __fadd_rn(__fmul_rn(__fdiv_rn(1.0f, near), __fsub_rn(1.0f, t)), __fmul_rn(__fdiv_rn(1.0f, far), t)));
   return __fadd_rn(__fmul_rn(near, __fsub_rn(1.0f, t)), __fmul_rn(far, t));
 }
 
 // stratified jitter of the coarse samples (training, perturb > 0; ray_utils.py:236-246):
 //   mids = .5 (z[1:] + z[:-1]); upper = [mids, z[-1]]; lower = [z[0], mids]; z = lower + (upper - lower) t_rand
-__device__ __forceinline__ float pgn_coarse_z_jitter(float near, float far, const float* __restrict__ t, int i, float t_rand) {
-  const float zi = pgn_coarse_z(near, far, t[i]);
-  const float lower = i > 0 ? __fmul_rn(0.5f, __fadd_rn(zi, pgn_coarse_z(near, far, t[i - 1]))) : zi;
-  const float upper = i + 1 < PGN_S ? __fmul_rn(0.5f, __fadd_rn(pgn_coarse_z(near, far, t[i + 1]), zi)) : zi;
+__device__ __forceinline__ float pgn_coarse_z_jitter(float near, float far, const float* __restrict__ t, int i, float t_rand, int lindisp = 0) {
+  const float zi = pgn_coarse_z(near, far, t[i], lindisp);
+  const float lower = i > 0 ? __fmul_rn(0.5f, __fadd_rn(zi, pgn_coarse_z(near, far, t[i - 1], lindisp))) : zi;
+  const float upper = i + 1 < PGN_S ? __fmul_rn(0.5f, __fadd_rn(pgn_coarse_z(near, far, t[i + 1], lindisp), zi)) : zi;
   return __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), t_rand));
 }
 

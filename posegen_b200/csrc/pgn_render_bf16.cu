@@ -128,7 +128,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
 
 __device__ __forceinline__ RowCtx make_row_ctx(const Smem& sm, const PgnScalars& sc, const TileCtx& tc,
                                                const float* __restrict__ near_far, int slot, int row,
-                                               const float* __restrict__ t_rand = nullptr) {
+                                               const float* __restrict__ t_rand = nullptr, int lindisp = 0) {
   RowCtx rc;
   const int grow = tc.row0 + row;
   rc.valid = grow < tc.total_rows;
@@ -139,8 +139,8 @@ __device__ __forceinline__ RowCtx make_row_ctx(const Smem& sm, const PgnScalars&
     const long long ri = tc.ray0 + rl;
     rc.tr = rl - tc.tile_ray0;
     if (tc.pass != 0) rc.z = sm.zf[slot][rl][s];
-    else if (t_rand) rc.z = pgn_coarse_z_jitter(__ldg(near_far + ri * 2), __ldg(near_far + ri * 2 + 1), sc.t_coarse, s, __ldg(t_rand + ri * PGN_S + s));
-    else rc.z = pgn_coarse_z(__ldg(near_far + ri * 2), __ldg(near_far + ri * 2 + 1), sc.t_coarse[s]);
+    else if (t_rand) rc.z = pgn_coarse_z_jitter(__ldg(near_far + ri * 2), __ldg(near_far + ri * 2 + 1), sc.t_coarse, s, __ldg(t_rand + ri * PGN_S + s), lindisp);
+    else rc.z = pgn_coarse_z(__ldg(near_far + ri * 2), __ldg(near_far + ri * 2 + 1), sc.t_coarse[s], lindisp);
   }
   return rc;
 }
@@ -725,11 +725,11 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
             }
             const float nn = __ldg(near_far + ri * 2), ff = __ldg(near_far + ri * 2 + 1);
             if (kDump == 1 && dump.t_rand) {
-              zc[lane] = pgn_coarse_z_jitter(nn, ff, sc.t_coarse, lane, __ldg(dump.t_rand + ri * PGN_S + lane));
-              zc[lane + 32] = pgn_coarse_z_jitter(nn, ff, sc.t_coarse, lane + 32, __ldg(dump.t_rand + ri * PGN_S + lane + 32));
+              zc[lane] = pgn_coarse_z_jitter(nn, ff, sc.t_coarse, lane, __ldg(dump.t_rand + ri * PGN_S + lane), rays.lindisp);
+              zc[lane + 32] = pgn_coarse_z_jitter(nn, ff, sc.t_coarse, lane + 32, __ldg(dump.t_rand + ri * PGN_S + lane + 32), rays.lindisp);
             } else {
-              zc[lane] = pgn_coarse_z(nn, ff, sc.t_coarse[lane]);
-              zc[lane + 32] = pgn_coarse_z(nn, ff, sc.t_coarse[lane + 32]);
+              zc[lane] = pgn_coarse_z(nn, ff, sc.t_coarse[lane], rays.lindisp);
+              zc[lane + 32] = pgn_coarse_z(nn, ff, sc.t_coarse[lane + 32], rays.lindisp);
             }
             const float d0 = __ldg(rays.ray_batch + ri * 11 + 3), d1 = __ldg(rays.ray_batch + ri * 11 + 4), d2 = __ldg(rays.ray_batch + ri * 11 + 5);
             const float dn = sqrtf(d0 * d0 + d1 * d1 + d2 * d2);
@@ -875,7 +875,7 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
       if (!kStage && L == 0 && !tables_ready) {      // (normally built ahead, in the shadow of the previous tile's view layer)
         PROF_T0();
         build_tables(tc);
-        rc = make_row_ctx(sm, sc, tc, near_far, s, row, kDump == 1 ? dump.t_rand : nullptr);
+        rc = make_row_ctx(sm, sc, tc, near_far, s, row, kDump == 1 ? dump.t_rand : nullptr, rays.lindisp);
         group_bar_sync(s);                 // tables visible to every thread of the group
         if (timed) PROF_ADD(14);
       }
@@ -932,7 +932,7 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
             if (k + 1 < kTiles) make_ctx(i, k + 1, nx); else make_ctx(i + 1, 0, nx);
             group_bar_sync(s);               // every thread is done reading this tile's tables
             build_tables(nx);
-            rc = make_row_ctx(sm, sc, nx, near_far, s, row, kDump == 1 ? dump.t_rand : nullptr);
+            rc = make_row_ctx(sm, sc, nx, near_far, s, row, kDump == 1 ? dump.t_rand : nullptr, rays.lindisp);
             group_bar_sync(s);               // tables visible to every thread of the group
             tables_ready = true;
             if (timed) PROF_ADD(14);

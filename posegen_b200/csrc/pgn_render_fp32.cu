@@ -288,7 +288,7 @@ pgn_render_fp32_kernel(PgnRayRefs rays, PgnOutputs out, PgnFp32Net net_c, PgnFp3
     for (int i = tid; i < kRPG * PGN_S; i += kThreads) {
       const int rl = i / PGN_S, s = i % PGN_S;
       float z = 0.f;
-      if (rl < nr) z = pgn_coarse_z(near_far[(ray0 + rl) * 2], near_far[(ray0 + rl) * 2 + 1], sc.t_coarse[s]);
+      if (rl < nr) z = pgn_coarse_z(near_far[(ray0 + rl) * 2], near_far[(ray0 + rl) * 2 + 1], sc.t_coarse[s], rays.lindisp);
       sm.zc[rl][s] = z;
     }
     for (int i = tid; i < kRPG * PGN_J; i += kThreads) {

@@ -159,7 +159,8 @@ class Engine:
         return torch.empty(int(self.lib.pgn_workspace_bytes(self.handle, n_rays)), dtype=torch.uint8, device=dev)
 
     # ------------------------------------------------------------------ inputs
-    def _inputs(self, ray_batch, skts, cyls, pose_idx=None, nanfill_chunk=0, precision="bf16", chunk_starts=None, cams=None):
+    def _inputs(self, ray_batch, skts, cyls, pose_idx=None, nanfill_chunk=0, precision="bf16", chunk_starts=None, cams=None,
+                lindisp=False):
         _check_f32_cuda(ray_batch, "ray_batch")
         n = ray_batch.shape[0]
         if ray_batch.dim() != 2 or ray_batch.shape[1] != 11:
@@ -213,14 +214,15 @@ class Engine:
                 raise ValueError("cams must have one entry per ray")
             inp.cams = cams.data_ptr()
             keep.append(cams)
+        inp.lindisp = 1 if lindisp else 0
         inp.precision = {"fp32": _lib.PRECISION_FP32, "bf16": _lib.PRECISION_BF16}[precision]
         return inp, keep
 
     # ---------------------------------------------------------------- hot path
     def render(self, ray_batch, skts, cyls, pose_idx=None, nanfill_chunk=0, precision="bf16",
-               return_alpha=True, taps=False, chunk_starts=None, cams=None) -> Dict[str, torch.Tensor]:
+               return_alpha=True, taps=False, chunk_starts=None, cams=None, lindisp=False) -> Dict[str, torch.Tensor]:
         """pgn_render_forward: the reference's RayCaster.render_rays (eval path)."""
-        inp, keep = self._inputs(ray_batch, skts, cyls, pose_idx, nanfill_chunk, precision, chunk_starts, cams)
+        inp, keep = self._inputs(ray_batch, skts, cyls, pose_idx, nanfill_chunk, precision, chunk_starts, cams, lindisp)
         n, dev = inp.n_rays, ray_batch.device
         f = lambda *sh: torch.empty(sh, dtype=torch.float32, device=dev)  # noqa: E731
         ret = {"rgb_map": f(n, 3), "disp_map": f(n), "acc_map": f(n), "rgb0": f(n, 3), "disp0": f(n), "acc0": f(n)}
@@ -239,7 +241,8 @@ class Engine:
                                                    self._stream()))
         return ret
 
-    def render_train(self, ray_batch, skts, cyls, pose_idx=None, nanfill_chunk=0, rand=None, dump_coarse=True, cams=None):
+    def render_train(self, ray_batch, skts, cyls, pose_idx=None, nanfill_chunk=0, rand=None, dump_coarse=True, cams=None,
+                     lindisp=False):
         """pgn_render_forward_train: the fused bf16 forward + per-layer activation dump for the weight gradients.
         Returns (outputs incl. the taps the backward needs, {"c": dump, "f": dump}); dump[p] is a flat bf16 buffer of
         rows * 2304 elements: layers 0-7 tile-blocked [rows/128][32][128][8] each (the kernel's coalesced operand-image
@@ -247,7 +250,7 @@ class Engine:
         returns a row-major copy / view, `train.act_masks` the mask area), rows in (ray, sample) order.
         rand: optional dict of CUDA fp32 tensors t_rand [n,64], u_is [n,16], noise0 [n,64], noise [n,80] (training-time
         randomness drawn by the caller; missing keys = deterministic)."""
-        inp, keep = self._inputs(ray_batch, skts, cyls, pose_idx, nanfill_chunk, "bf16", cams=cams)
+        inp, keep = self._inputs(ray_batch, skts, cyls, pose_idx, nanfill_chunk, "bf16", cams=cams, lindisp=lindisp)
         n, dev = inp.n_rays, ray_batch.device
         f = lambda *sh: torch.empty(sh, dtype=torch.float32, device=dev)  # noqa: E731
         ret = {"rgb_map": f(n, 3), "disp_map": f(n), "acc_map": f(n), "rgb0": f(n, 3), "disp0": f(n), "acc0": f(n),

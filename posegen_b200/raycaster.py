@@ -281,8 +281,9 @@ class RayCaster(nn.Module):
                     pytest=False, preproc_kwargs=None, nerf_type="nerf", use_viewdirs=True,
                     precision=None, nanfill_chunk=None, **_ignored):
         train_step = self.training and torch.is_grad_enabled()
-        if ray_noise_std or lindisp:
-            raise NotImplementedError("ray_noise_std / lindisp are not part of the surreal.txt path")
+        if ray_noise_std:
+            raise NotImplementedError("ray_noise_std (off in every shipped config) is not implemented: it makes a sample's "
+                                      "position more than a function of (ray, z)")
         if (perturb or raw_noise_std) and not train_step:
             raise NotImplementedError("perturb / raw_noise_std (training-time sampling noise) need .train() and grad mode; "
                                       "the render path is deterministic (render_kwargs_test, core/raycasters.py:176-178)")
@@ -301,12 +302,13 @@ class RayCaster(nn.Module):
             if (precision or self.precision) != "bf16":
                 raise NotImplementedError("the training step runs on the bf16 tensor-core path only")
             return render_train(self, ray_batch, skts.to(ray_batch.device), cyls.to(ray_batch.device), nanfill_chunk,
-                                perturb=float(perturb), raw_noise_std=float(raw_noise_std), rand=_ignored.get("train_random"), cams=cams)
+                                perturb=float(perturb), raw_noise_std=float(raw_noise_std), rand=_ignored.get("train_random"), cams=cams,
+                                lindisp=bool(lindisp))
         eng = self.engine(ray_batch.device)
         n = ray_batch.shape[0]
         ret = eng.render(ray_batch.float(), skts.to(ray_batch.device).float(), cyls.to(ray_batch.device).float(),
                          nanfill_chunk=n if nanfill_chunk is None else nanfill_chunk,
-                         precision=precision or self.precision, return_alpha=self.return_alpha, cams=cams)
+                         precision=precision or self.precision, return_alpha=self.return_alpha, cams=cams, lindisp=bool(lindisp))
         # alpha / alpha0 are simply absent when not requested: the reference's batchify_rays concatenates every key
         # of the returned dict (core/trainer.py:75-80), so a None entry would break it
         eng.poll_status()

@@ -213,9 +213,10 @@ def mlp_backward(params: Dict[str, torch.Tensor], enc: torch.Tensor, acts: torch
 
 class _RenderTrainFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, rc, ray_batch, skts, cyls, nanfill_chunk, rand, cams, *params):
+    def forward(ctx, rc, ray_batch, skts, cyls, nanfill_chunk, rand, cams, lindisp, *params):
         eng = rc.engine(ray_batch.device)
-        ret, acts = eng.render_train(ray_batch, skts, cyls, nanfill_chunk=nanfill_chunk, rand=rand, cams=cams)
+        ret, acts = eng.render_train(ray_batch, skts, cyls, nanfill_chunk=nanfill_chunk, rand=rand, cams=cams, lindisp=lindisp)
+        ctx.lindisp = lindisp
         rc.mark_weights_dirty()            # an optimizer step follows; not every optimizer bumps the version counters
         ctx.rc, ctx.eng, ctx.acts, ctx.rand, ctx.cams = rc, eng, acts, (rand or {}), cams
         ctx.set_materialize_grads(False)   # outputs the loss does not read arrive as None: their pass is skipped
@@ -230,7 +231,10 @@ class _RenderTrainFn(torch.autograd.Function):
         n = rb.shape[0]
         zero3, zero1 = torch.zeros((n, 3), device=rb.device), torch.zeros(n, device=rb.device)
         t = torch.linspace(0., 1., S, device=rb.device)                       # sample_from_lineseg, ray_utils.py:204-251
-        z_c = near_far[:, :1] * (1. - t) + near_far[:, 1:2] * t
+        if ctx.lindisp:
+            z_c = 1. / (1. / near_far[:, :1] * (1. - t) + 1. / near_far[:, 1:2] * t)
+        else:
+            z_c = near_far[:, :1] * (1. - t) + near_far[:, 1:2] * t
         rand = ctx.rand
         if rand.get("t_rand") is not None:                                    # stratified jitter, ray_utils.py:236-246
             mids = .5 * (z_c[:, 1:] + z_c[:, :-1])
@@ -238,7 +242,7 @@ class _RenderTrainFn(torch.autograd.Function):
             z_c = lower + (upper - lower) * rand["t_rand"]
         grads: List[torch.Tensor] = []
         want_sk = ctx.needs_input_grad[2]
-        want_w = any(ctx.needs_input_grad[7:])               # False for a frozen NeRF (the GAN step)
+        want_w = any(ctx.needs_input_grad[8:])               # False for a frozen NeRF (the GAN step)
         order = param_order(rc.network)
         d_skts = None
         # Gradient arena: every weight / bias gradient of both nets lives in ONE fp32 buffer (the weight-gradient kernel
@@ -290,7 +294,7 @@ class _RenderTrainFn(torch.autograd.Function):
         ctx.acts = None
         if want_sk and d_skts is not None and sk.dim() == 3:
             d_skts = d_skts.sum(0)                     # one pose shared by every ray of the batch
-        return (None, None, d_skts, None, None, None, None) + tuple(grads)
+        return (None, None, d_skts, None, None, None, None, None) + tuple(grads)
 
 
 def draw_train_random(n: int, device, perturb: float = 0., raw_noise_std: float = 0., density_scale: float = 1.0) -> Dict[str, torch.Tensor]:
@@ -311,7 +315,7 @@ def param_order(net) -> List[str]:
 
 
 def render_train(rc, ray_batch, skts, cyls, nanfill_chunk=None, perturb: float = 0., raw_noise_std: float = 0.,
-                 rand: Dict[str, torch.Tensor] | None = None, cams=None) -> Dict[str, torch.Tensor]:
+                 rand: Dict[str, torch.Tensor] | None = None, cams=None, lindisp: bool = False) -> Dict[str, torch.Tensor]:
     """Differentiable (w.r.t. the two MLPs' parameters and `skts`) render of a ray batch: the train-mode body of
     RayCaster.forward.  Returns the reference's dict (core/raycasters.py:711-724) without alpha/alpha0."""
     params = [net_tensors(net)[k] for net in (rc.network, rc.network_fine) for k in param_order(net)]
@@ -319,7 +323,7 @@ def render_train(rc, ray_batch, skts, cyls, nanfill_chunk=None, perturb: float =
     if rand is None:
         rand = draw_train_random(n, ray_batch.device, perturb, raw_noise_std, float(rc.network.density_scale))
     out = _RenderTrainFn.apply(rc, ray_batch.float().contiguous(), skts if skts.dtype == torch.float32 else skts.float(), cyls.float(),
-                               n if nanfill_chunk is None else nanfill_chunk, rand or None, cams, *params)
+                               n if nanfill_chunk is None else nanfill_chunk, rand or None, cams, bool(lindisp), *params)
     return {"rgb_map": out[0], "acc_map": out[1], "rgb0": out[2], "acc0": out[3], "disp_map": out[4], "disp0": out[5]}
 
 

@@ -38,7 +38,7 @@ def case_from_golden(g):
     return frame, ckpt, rb, cyl
 
 
-def oracle_render(rb, skts, cyl, ckpt, chunk=4096, dtype=torch.float32, device="cpu", taps=None, cams=None):
+def oracle_render(rb, skts, cyl, ckpt, chunk=4096, dtype=torch.float32, device="cpu", taps=None, cams=None, lindisp=False):
     rbt = torch.as_tensor(rb).to(device=device, dtype=dtype)
     nets = orc.nets_from_ckpt(ckpt, dtype, device)
     emb = orc.embed_params_from_ckpt(ckpt, dtype, device)
@@ -47,9 +47,9 @@ def oracle_render(rb, skts, cyl, ckpt, chunk=4096, dtype=torch.float32, device="
     with torch.no_grad():
         if taps is not None and rbt.shape[0] <= chunk:
             n = rbt.shape[0]
-            out = orc.render_rays(rbt, sk[None].expand(n, -1, -1, -1), cy[None].expand(n, -1), nets, emb, taps=taps, cams=cams)
+            out = orc.render_rays(rbt, sk[None].expand(n, -1, -1, -1), cy[None].expand(n, -1), nets, emb, taps=taps, cams=cams, lindisp=lindisp)
         else:
-            out = orc.render(rbt, sk, cy, nets, emb, chunk=chunk, cams=cams)
+            out = orc.render(rbt, sk, cy, nets, emb, chunk=chunk, cams=cams, lindisp=lindisp)
     return {k: v.float().cpu().numpy() for k, v in out.items()}
 
 
@@ -64,14 +64,14 @@ def psnr(a, b, peak=1.0):
     return 99.0 if mse == 0 else 10.0 * np.log10(peak * peak / mse)
 
 
-def gpu_render(engine, rb, skts, cyl, ckpt, precision, chunk=4096, taps=False, cams=None):
+def gpu_render(engine, rb, skts, cyl, ckpt, precision, chunk=4096, taps=False, cams=None, lindisp=False):
     """Render through the C ABI in batchify-sized calls (the reference's chunk semantics)."""
     dev = engine.device
     engine.load_checkpoint(ckpt)
     rbt = torch.as_tensor(rb, device=dev)
     sk = torch.as_tensor(skts, device=dev)
     cy = torch.as_tensor(cyl, device=dev)
-    ret = engine.render(rbt, sk, cy, nanfill_chunk=chunk, precision=precision, return_alpha=True, taps=taps, cams=cams)
+    ret = engine.render(rbt, sk, cy, nanfill_chunk=chunk, precision=precision, return_alpha=True, taps=taps, cams=cams, lindisp=lindisp)
     torch.cuda.synchronize()
     engine.check_status()
     return {k: v.cpu().numpy() for k, v in ret.items()}

@@ -44,6 +44,19 @@ def test_bf16_tensor_path_matches_reference(engine, name):
     assert pu.psnr(out["acc_map"], g["acc_map"]) >= BF16_PSNR
 
 
+@pytest.mark.parametrize("precision,tol", [("fp32", FP32_TOL), ("bf16", BF16_TOL)])
+def test_lindisp_sampling_matches_reference(engine, precision, tol):
+    """`lindisp = True` (coarse samples linear in inverse depth, core/utils/ray_utils.py:224-227) against the golden
+    rendered by the unmodified reference with render_kwargs['lindisp'] = True."""
+    g = pu.load_golden("g_32_lindisp")
+    frame, ckpt, rb, cyl = pu.case_from_golden(g)
+    out = pu.gpu_render(engine, rb, frame.pose.skts, cyl, ckpt, precision, chunk=int(g["meta_chunk"]), lindisp=True)
+    lin = pu.gpu_render(engine, rb, frame.pose.skts, cyl, ckpt, precision, chunk=int(g["meta_chunk"]), lindisp=False)
+    for k in ("rgb_map", "acc_map", "rgb0", "acc0"):
+        assert pu.max_abs(out[k], g[k]) <= tol, k
+    assert pu.max_abs(out["acc_map"], lin["acc_map"]) > 0          # the option changes the sample positions
+
+
 def test_bf16_on_uncalibrated_boosted_head_psnr(engine):
     """with the x400 head the last sample (delta = 1e10) turns alpha into step(sigma), so
     max-abs is unreachable for ANY bf16 implementation (reference-vs-itself: 1.0); PSNR still holds."""

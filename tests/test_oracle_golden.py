@@ -6,7 +6,7 @@ import torch
 
 from tests import parity_util as pu
 
-CASES = ["a_32_boost_taps", "b_64_boost", "c_64_plain", "d_64_calibrated", "e_32_nanfill", "f_64_framecode"]
+CASES = ["a_32_boost_taps", "b_64_boost", "c_64_plain", "d_64_calibrated", "e_32_nanfill", "f_64_framecode", "g_32_lindisp"]
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -24,7 +24,8 @@ def test_oracle_matches_reference_golden(name):
     frame, ckpt, rb, cyl = pu.case_from_golden(g)
     taps = {} if "z_samples" in g else None
     cams = torch.as_tensor(g["in_cams"]).long() if "in_cams" in g else None          # Optcodes case: camera index per ray
-    out = pu.oracle_render(rb, frame.pose.skts, cyl, ckpt, chunk=int(g["meta_chunk"]), taps=taps, cams=cams)
+    out = pu.oracle_render(rb, frame.pose.skts, cyl, ckpt, chunk=int(g["meta_chunk"]), taps=taps, cams=cams,
+                           lindisp="meta_lindisp" in g)
     # same machine class, same op order: the restatement was bit-identical when the fixtures were
     # made; allow 2e-6 for a different BLAS/ISA on the test host
     for k in pu.IMAGE_KEYS:
