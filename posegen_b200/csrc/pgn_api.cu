@@ -185,10 +185,22 @@ int pgn_upload_weights(pgn_context* c, int net_id, const pgn_net_weights* w, int
   cudaStream_t stream = (cudaStream_t)stream_;
   PGN_ON_DEVICE(c);
   const cudaMemcpyKind kind = pointers_are_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-  for (int l = 0; l < PGN_N_LINEAR; ++l) {
+  for (int l = 0; l < PGN_N_LINEAR; ++l)
     if (!w->weight[l] || !w->bias[l]) return fail(PGN_E_INVALID, "pgn_upload_weights: null tensor %d", l);
-    PGN_CUDA(cudaMemcpyAsync((void*)c->w_ptr[net_id][l], w->weight[l], (size_t)kOut[l] * in_of(l, c->view_in) * sizeof(float), kind, stream));
-    PGN_CUDA(cudaMemcpyAsync((void*)c->b_ptr[net_id][l], w->bias[l], (size_t)kOut[l] * sizeof(float), kind, stream));
+  if (pointers_are_device) {          // the per-step refresh: one gather launch for the 24 tensors
+    float* dw[PGN_N_LINEAR]; float* db[PGN_N_LINEAR];
+    int nw[PGN_N_LINEAR], nb[PGN_N_LINEAR];
+    for (int l = 0; l < PGN_N_LINEAR; ++l) {
+      dw[l] = (float*)c->w_ptr[net_id][l]; db[l] = (float*)c->b_ptr[net_id][l];
+      nw[l] = kOut[l] * in_of(l, c->view_in); nb[l] = kOut[l];
+    }
+    PGN_CUDA(pgn_launch_gather_params(w->weight, w->bias, dw, db, nw, nb, stream));
+    c->launches++;
+  } else {
+    for (int l = 0; l < PGN_N_LINEAR; ++l) {
+      PGN_CUDA(cudaMemcpyAsync((void*)c->w_ptr[net_id][l], w->weight[l], (size_t)kOut[l] * in_of(l, c->view_in) * sizeof(float), kind, stream));
+      PGN_CUDA(cudaMemcpyAsync((void*)c->b_ptr[net_id][l], w->bias[l], (size_t)kOut[l] * sizeof(float), kind, stream));
+    }
   }
   // the fp32 CUDA-core tier's transposed copies are rebuilt lazily, by the first fp32 call after an upload
   // (ensure_fp32_tier): a bf16 training loop re-packs every step and never reads them

@@ -147,6 +147,9 @@ cudaError_t pgn_launch_pack_input_grad_weights(const float* w5, const float* w0,
 cudaError_t pgn_launch_input_grads(const void* dz, const void* dG, long long m, const __nv_bfloat16* wpack, void* g_xp, void* g_d,
                                    int* status, int num_sms, cudaStream_t stream);
 
+cudaError_t pgn_launch_gather_params(const float* const* src_w, const float* const* src_b, float* const* dst_w, float* const* dst_b,
+                                     const int* n_w, const int* n_b, cudaStream_t stream);
+
 // bring-up probe (pgn_probe.cu)
 cudaError_t pgn_launch_probe_umma(const float* A, const float* B, float* D, int K, int N, int variant, int* status,
                                   cudaStream_t stream);
