@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libposegen_b200.so")
-SOURCES = ["pgn_api.cu", "pgn_stage_kernels.cu", "pgn_render_fp32.cu", "pgn_render_bf16.cu", "pgn_train_kernels.cu", "pgn_delta_chain.cu", "pgn_batch_kernels.cu", "pgn_wgrad.cu", "pgn_input_grads.cu", "pgn_probe.cu"]
+SOURCES = ["pgn_api.cu", "pgn_stage_kernels.cu", "pgn_render_fp32.cu", "pgn_render_bf16.cu", "pgn_render_bf16_fc.cu", "pgn_train_kernels.cu", "pgn_delta_chain.cu", "pgn_batch_kernels.cu", "pgn_wgrad.cu", "pgn_input_grads.cu", "pgn_probe.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
 

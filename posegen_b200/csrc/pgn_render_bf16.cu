@@ -473,7 +473,10 @@ __device__ __forceinline__ bool issue_layer(IssuerCtx& ic) {
 // ------------------------------------------------------------------ the kernel
 // kDump: 0 = inference, 1 = training forward (activation + mask dump, training-time randomness), 2 = masks only
 // (deterministic sampling; the fine pass's ReLU masks for the pose gradient through a frozen network)
-template <bool kStage, bool kProf, int kDump, int kG = 8>
+// kFC: the model has Optcodes frame codes (the view layer's epilogue adds the ray's code term).  A separate instantiation
+// (compiled in its own translation unit, pgn_render_bf16_fc.cu) because the hooks cost 2.4 % of the frame-code-free
+// kernel when they are only switched off at run time (4.38 vs 4.49 M rays/s, A/B on one box).
+template <bool kStage, bool kProf, int kDump, int kG = 8, bool kFC = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf16Net net_f,
                        const PgnScalars* __restrict__ scp, const float* __restrict__ near_far,
@@ -842,7 +845,7 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
       }
       { PROF_T0();
         if (L == 8) epilogue<2>(sm, tmem_acc, act_saddr, s, net.w_alpha, net.w_rgb, gwarp, lane, sig_keep, dptr, mptr, vptr,
-                                net.fc_table ? net.fc_table + (size_t)fc_row * 128 : nullptr);
+                                kFC ? net.fc_table + (size_t)fc_row * 128 : nullptr);
         else if (L == 7) epilogue<1>(sm, tmem_acc, act_saddr, s, net.w_alpha, net.w_rgb, gwarp, lane, sig_keep, dptr, mptr, vptr);
         else epilogue<0>(sm, tmem_acc, act_saddr, s, net.w_alpha, net.w_rgb, gwarp, lane, sig_keep, dptr, mptr, vptr);
         compute_arrive(act_ready_a, lane); if (timed) PROF_ADD(8); }
@@ -923,7 +926,7 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
         for (int L = 0; L < 9; ++L) {
           { PROF_T0(); const bool okp = pre(L, tc); if (timed && (L == 0 || L == 5 || L == 8)) PROF_ADD(L == 0 ? 25 : (L == 5 ? 26 : 27)); if (!okp) goto done; }
           if (!kStage && pending && L >= 1 && L <= 3) { PROF_T0(); composite_stage(prev, L); if (timed) PROF_ADD(11); }
-          if (!kStage && L == 8 && net_c.fc_table)      // this row's ray -> frame-code row (while rc still describes THIS tile)
+          if (kFC && !kStage && L == 8)                 // this row's ray -> frame-code row (while rc still describes THIS tile)
             fc_row = (tc.nr > 0) ? pgn_ray_code_row(rays, tc.ray0 + min(tc.tile_ray0 + rc.tr, tc.nr - 1)) : rays.n_codes;
           if (!kStage && L == 8 && (k + 1 < kTiles || i + 1 < n_slot)) {
             // the view layer's last chunks are still in the tensor core: build the next tile's tables now
@@ -965,6 +968,7 @@ done:
   }
 }
 
+#ifndef PGN_RENDER_FC_UNIT
 // ------------------------------------------------------------------ weight packing
 // wsrc[l]: device fp32 nn.Linear weights in the include/posegen_b200.h order.
 __global__ void pgn_fold_view_kernel(const float* __restrict__ w_view /*[128][view_ld]*/, const float* __restrict__ w_feat /*[256][256]*/,
@@ -1074,61 +1078,89 @@ cudaError_t pgn_pack_bf16_net(const float* const* w_dev, const float* const* b_d
   return cudaGetLastError();
 }
 
+#else
+}  // namespace
+#endif  // !PGN_RENDER_FC_UNIT  (weight packing, dump geometry: main unit only)
+
+// ------------------------------------------------------------------ launch (compiled twice: kFC = false here, kFC = true in
+// pgn_render_bf16_fc.cu, which defines PGN_RENDER_FC_UNIT and includes this file)
+#ifdef PGN_RENDER_FC_UNIT
+#define PGN_FC true
+#define PGN_LAUNCH_RENDER pgn_launch_render_bf16_fc
+#define PGN_LAUNCH_MLP pgn_launch_mlp_bf16_fc
+#else
+#define PGN_FC false
+#define PGN_LAUNCH_RENDER pgn_launch_render_bf16
+#define PGN_LAUNCH_MLP pgn_launch_mlp_bf16
+cudaError_t pgn_launch_render_bf16_fc(const PgnRayRefs& rays, const PgnOutputs& out, const PgnBf16Net& nc, const PgnBf16Net& nf,
+                                      const PgnScalars* sc_dev, const float* near_far, int* status, unsigned long long* prof,
+                                      const PgnActDump* dump, int num_sms, cudaStream_t stream);
+cudaError_t pgn_launch_mlp_bf16_fc(const PgnBf16Net& net, const float* enc, long long m, float* raw, const PgnScalars* sc_dev,
+                                   int* status, int num_sms, int n_codes, cudaStream_t stream);
+#endif
+
 static cudaError_t configure_bf16() {
   static PgnPerDeviceOnce done;
   if (!done.need()) return cudaSuccess;
-  cudaError_t e = cudaFuncSetAttribute(pgn_render_bf16_kernel<false, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem) + 1024);
+  const int bytes = (int)sizeof(Smem) + 1024;
+  cudaError_t e = cudaFuncSetAttribute(pgn_render_bf16_kernel<false, false, 0, 8, PGN_FC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(pgn_render_bf16_kernel<false, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem) + 1024);
+#ifndef PGN_RENDER_FC_UNIT
+  e = cudaFuncSetAttribute(pgn_render_bf16_kernel<false, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(pgn_render_bf16_kernel<true, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem) + 1024);
+#endif
+  e = cudaFuncSetAttribute(pgn_render_bf16_kernel<true, false, 0, 8, PGN_FC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(pgn_render_bf16_kernel<false, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem) + 1024);
+  e = cudaFuncSetAttribute(pgn_render_bf16_kernel<false, false, 1, 8, PGN_FC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(pgn_render_bf16_kernel<false, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem) + 1024);
+  e = cudaFuncSetAttribute(pgn_render_bf16_kernel<false, false, 2, 8, PGN_FC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(pgn_render_bf16_kernel<false, false, 0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem) + 1024);
+  e = cudaFuncSetAttribute(pgn_render_bf16_kernel<false, false, 0, 4, PGN_FC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(pgn_render_bf16_kernel<false, false, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem) + 1024);
+  e = cudaFuncSetAttribute(pgn_render_bf16_kernel<false, false, 1, 4, PGN_FC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   if (e != cudaSuccess) return e;
   done.set();
   return cudaSuccess;
 }
 
-cudaError_t pgn_launch_render_bf16(const PgnRayRefs& rays, const PgnOutputs& out, const PgnBf16Net& nc,
-                                   const PgnBf16Net& nf, const PgnScalars* sc_dev, const float* near_far,
-                                   int* status, unsigned long long* prof, const PgnActDump* dump, int num_sms, cudaStream_t stream) {
+cudaError_t PGN_LAUNCH_RENDER(const PgnRayRefs& rays, const PgnOutputs& out, const PgnBf16Net& nc,
+                              const PgnBf16Net& nf, const PgnScalars* sc_dev, const float* near_far,
+                              int* status, unsigned long long* prof, const PgnActDump* dump, int num_sms, cudaStream_t stream) {
+#ifndef PGN_RENDER_FC_UNIT
+  if (nc.fc_table) return pgn_launch_render_bf16_fc(rays, out, nc, nf, sc_dev, near_far, status, prof, dump, num_sms, stream);
+#endif
   cudaError_t e = configure_bf16();
   if (e != cudaSuccess) return e;
-  const int g = prof ? kRPG : pgn_bf16_group_rays(rays.n_rays, dump && dump->masks_only);
+  const bool use_prof = prof != nullptr && !PGN_FC;          // the phase timers exist for the frame-code-free inference kernel
+  const int g = use_prof ? kRPG : pgn_bf16_group_rays(rays.n_rays, dump && dump->masks_only);
   const long long n_groups = (rays.n_rays + g - 1) / g;
   if (n_groups == 0) return cudaSuccess;
   const long long n_pairs = (n_groups + 1) / 2;
   const int grid = 2 * (int)min((long long)(num_sms / 2), n_pairs);      // clusters of 2 CTAs
+  const size_t smem = sizeof(Smem) + 1024;
   const PgnActDump nodump{};
   if (dump && dump->masks_only)
-    pgn_render_bf16_kernel<false, false, 2><<<grid, kThreads, sizeof(Smem) + 1024, stream>>>(rays, out, nc, nf, sc_dev, near_far,
-                                                                                             nullptr, 0, nullptr, status, nullptr, *dump);
+    pgn_render_bf16_kernel<false, false, 2, 8, PGN_FC><<<grid, kThreads, smem, stream>>>(rays, out, nc, nf, sc_dev, near_far, nullptr, 0, nullptr, status, nullptr, *dump);
   else if (dump && g == 4)
-    pgn_render_bf16_kernel<false, false, 1, 4><<<grid, kThreads, sizeof(Smem) + 1024, stream>>>(rays, out, nc, nf, sc_dev, near_far,
-                                                                                                nullptr, 0, nullptr, status, nullptr, *dump);
+    pgn_render_bf16_kernel<false, false, 1, 4, PGN_FC><<<grid, kThreads, smem, stream>>>(rays, out, nc, nf, sc_dev, near_far, nullptr, 0, nullptr, status, nullptr, *dump);
   else if (dump)
-    pgn_render_bf16_kernel<false, false, 1><<<grid, kThreads, sizeof(Smem) + 1024, stream>>>(rays, out, nc, nf, sc_dev, near_far,
-                                                                                             nullptr, 0, nullptr, status, nullptr, *dump);
+    pgn_render_bf16_kernel<false, false, 1, 8, PGN_FC><<<grid, kThreads, smem, stream>>>(rays, out, nc, nf, sc_dev, near_far, nullptr, 0, nullptr, status, nullptr, *dump);
   else if (g == 4)
-    pgn_render_bf16_kernel<false, false, 0, 4><<<grid, kThreads, sizeof(Smem) + 1024, stream>>>(rays, out, nc, nf, sc_dev, near_far,
-                                                                                                nullptr, 0, nullptr, status, nullptr, nodump);
-  else if (prof)
-    pgn_render_bf16_kernel<false, true, 0><<<grid, kThreads, sizeof(Smem) + 1024, stream>>>(rays, out, nc, nf, sc_dev, near_far,
-                                                                                                nullptr, 0, nullptr, status, prof, nodump);
+    pgn_render_bf16_kernel<false, false, 0, 4, PGN_FC><<<grid, kThreads, smem, stream>>>(rays, out, nc, nf, sc_dev, near_far, nullptr, 0, nullptr, status, nullptr, nodump);
+#ifndef PGN_RENDER_FC_UNIT
+  else if (use_prof)
+    pgn_render_bf16_kernel<false, true, 0><<<grid, kThreads, smem, stream>>>(rays, out, nc, nf, sc_dev, near_far, nullptr, 0, nullptr, status, prof, nodump);
+#endif
   else
-    pgn_render_bf16_kernel<false, false, 0><<<grid, kThreads, sizeof(Smem) + 1024, stream>>>(rays, out, nc, nf, sc_dev, near_far,
-                                                                                                 nullptr, 0, nullptr, status, nullptr, nodump);
+    pgn_render_bf16_kernel<false, false, 0, 8, PGN_FC><<<grid, kThreads, smem, stream>>>(rays, out, nc, nf, sc_dev, near_far, nullptr, 0, nullptr, status, nullptr, nodump);
   return cudaGetLastError();
 }
 
-cudaError_t pgn_launch_mlp_bf16(const PgnBf16Net& net, const float* enc, long long m, float* raw,
-                                const PgnScalars* sc_dev, int* status, int num_sms, int n_codes, cudaStream_t stream) {
+cudaError_t PGN_LAUNCH_MLP(const PgnBf16Net& net, const float* enc, long long m, float* raw,
+                           const PgnScalars* sc_dev, int* status, int num_sms, int n_codes, cudaStream_t stream) {
+#ifndef PGN_RENDER_FC_UNIT
+  if (net.fc_table) return pgn_launch_mlp_bf16_fc(net, enc, m, raw, sc_dev, status, num_sms, n_codes, stream);
+#endif
   cudaError_t e = configure_bf16();
   if (e != cudaSuccess) return e;
   const long long n_tiles = (m + kTM - 1) / kTM;
@@ -1137,7 +1169,7 @@ cudaError_t pgn_launch_mlp_bf16(const PgnBf16Net& net, const float* enc, long lo
   PgnRayRefs rays{};
   rays.n_codes = n_codes;          // explicit encodings carry no camera index: a frame-code model uses its mean code
   PgnOutputs out{};
-  pgn_render_bf16_kernel<true, false, 0><<<grid, kThreads, sizeof(Smem) + 1024, stream>>>(rays, out, net, net, sc_dev, nullptr,
-                                                                                              enc, m, raw, status, nullptr, PgnActDump{});
+  pgn_render_bf16_kernel<true, false, 0, 8, PGN_FC><<<grid, kThreads, sizeof(Smem) + 1024, stream>>>(rays, out, net, net, sc_dev, nullptr,
+                                                                                                   enc, m, raw, status, nullptr, PgnActDump{});
   return cudaGetLastError();
 }
