@@ -261,8 +261,9 @@ PGN_API int  pgn_mlp_delta(pgn_context* ctx, void* dh, int32_t has_input, const 
  * d_sigma); mask: the ReLU-mask area of the activation dump of pgn_render_forward_train (starts
  * rows * 4352 bytes into the pass's buffer, rows = mask_rows = pgn_activation_dump_bytes / 4608); w_alpha fp32 [256].
  * wstream: the eight weights W'_j [256, K_j] bf16 (W'_0 = (W_v[:, :256] W_f)^T with K = 128; W'_j = W_l^T for
- * l = 8 - j, K = 256, the skip layer l = 5 without its 432 input columns), each cut into K = 16 slabs laid out
- * [K/16][2][256][8] (UMMA K-major core matrices), concatenated: 120 slabs of 8 KB.
+ * l = 8 - j, K = 256, the skip layer l = 5 without its 432 input columns), each cut into fills of two K = 16 steps laid
+ * out [K/32][2 N halves][2 K-steps][2][128][8] (UMMA K-major core matrices; one N half per CTA of the pair that works
+ * on a 512-row block, 8 KB per fill and CTA), concatenated: 60 fills of 16 KB.
  * Outputs: dz bf16 [8][m][256] (dz[l] = dZ_l, row-major) and colsum fp32 [8][256] (bias gradients), for the layers
  * whose bit is set in layer_mask (0xFF: all; a frozen network's pose gradient reads only dZ_0 and dZ_5: 0x21). */
 PGN_API int  pgn_mlp_delta_chain(pgn_context* ctx, const void* dG, const float* d_raw, const void* mask, int64_t mask_rows,

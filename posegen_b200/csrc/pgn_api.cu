@@ -70,7 +70,7 @@ struct pgn_context {
   __nv_bfloat16* d_wstream[2];
   float* d_bf16_aux[2];     // bias[9*256] | w_alpha[256] | w_rgb[384]
   float* d_fold;
-  __nv_bfloat16* d_chain_w[2] = {nullptr, nullptr};   // per net: the delta chain's weight stream (120 slabs of 8 KB)
+  __nv_bfloat16* d_chain_w[2] = {nullptr, nullptr};   // per net: the delta chain's weight stream (60 fills of 16 KB)
   PgnBf16Net bf16[2];
   int* d_status;
   bool fp32_stale[2] = {false, false};   // fp32-tier transposes pending since the last pgn_upload_weights

@@ -1,8 +1,8 @@
-// Fused delta chain of the A-NeRF trunk backward (training step / GAN step) on tcgen05.
+// Fused delta chain of the A-NeRF trunk backward (training step / GAN step) on tcgen05, CTA pairs.
 //
 // What autograd does per trunk layer (core/networks/nerf.py:94-102 backwards) is a GEMM dL/dh_{l-1} = dZ_l W_l followed
-// by a ReLU mask; done layer by layer through HBM that is 5 passes over a [rows,256] matrix per layer.  Here one CTA
-// keeps a 256-row block of deltas in shared memory for the whole chain:
+// by a ReLU mask; done layer by layer through HBM that is 5 passes over a [rows,256] matrix per layer.  Here a pair of
+// CTAs keeps a 512-row block of deltas in shared memory for the whole chain:
 //
 //     dG [rows,128]  --W_fold-->  dL/dh7 (+ d_sigma w_alpha)  --mask h7-->  dZ7  --W_7--> ... --W_1--> dZ0
 //
@@ -12,15 +12,27 @@
 // Algorithmic bytes per row: 8 x 512 B written + 8 x 32 B masks + 256 B dG + 4 B d_sigma = 4.6 KB (HBM-bound:
 // 0.47 TFLOP over 2.0 GB for a 3,072-ray batch).
 //
-// Roles (768 threads, 1 CTA per SM, persistent over row blocks): warp 0 lane 0 streams the weights of all eight layers
-// in consumption order through a 10 x 8 KB ring with cp.async.bulk (one K-step slab = [2][256][8] bf16, UMMA K-major
-// SWIZZLE_NONE); warp 1 lane 0 issues the MMAs (UMMA M = 128, two row tiles share every weight slab, cta_group::1);
-// warps 4-19 drain the two accumulators (8 warps each; tcgen05.ld 32x32b), add the sigma head's outer product on the
-// first layer, mask, pack to bf16 and store the next layer's A operand into shared memory ([k/8][row][8]); warps 20-23 then read that
-// tile back from shared memory - while the tensor core already runs the next layer on it - and write the dZ rows to
-// HBM (4 rows x 128 B per warp store: full lines) and accumulate the bias gradients (column sums; every column has
-// one owner thread, no atomics).  Draining and storing from the accumulator-owning threads directly costs 2x: a
-// thread owns one row, so each of its stores touches 32 different lines and the column sums need 128 shuffles.
+// Schedule.  A cluster of two CTAs works on two 256-row tiles (UMMA M = 256, cta_group::2: 128 rows of each tile per
+// CTA, the weight operand split along N between the two CTAs' shared memory, so a CTA streams HALF of every weight
+// slab).  The leader CTA's issuer runs the layers in the order (j, tile 0), (j, tile 1), (j+1, tile 0), ...: while the
+// tensor core works on one tile the other tile's accumulator is drained, masked and written back as the next layer's
+// A operand - MMA and drain overlap, which the round-1 kernel (both tiles issued together, cta_group::1) did not do,
+// and the MMA reads 8 instead of 12 KB of shared memory per K-step per SM (that kernel's MMAs ran at half rate because
+// the drain / store warps competed with them for shared-memory bandwidth).  Both tiles use the same weight slabs: the
+// 10 x 8 KB ring (fills of two K-steps) holds one whole layer (8 fills) plus 2 fills of prefetch; a stage is released by
+// tile 1's MMAs.  (A CTA's share of the stream is contiguous per fill: one 8 KB bulk copy.  Two 2 KB copies per K-step
+// out of the round-1 slab layout starved the issuer - the copy engine's per-request cost, not bytes, was the limit.)
+//
+// Roles per CTA (768 threads, 1 CTA per SM, persistent over 512-row blocks): warp 0 lane 0 streams this CTA's N half
+// of the weights of all eight layers in consumption order with cp.async.bulk (UMMA K-major SWIZZLE_NONE, [2][128][8] bf16
+// per K = 16 step); warp 1 lane 0 issues the MMAs (leader CTA) or relays "my half has landed" to the
+// leader's barrier (peer CTA); warps 4-19 drain the two accumulators (8 warps each; tcgen05.ld 32x32b), add the sigma
+// head's outer product on the first layer, mask, pack to bf16 and store the next layer's A operand into shared memory
+// ([k/8][row][8]); warps 20-23 then read that tile back from shared memory - while the tensor core already runs the
+// next layer on it - and write the dZ rows to HBM (4 rows x 128 B per warp store: full lines) and accumulate the bias
+// gradients (column sums; every column has one owner thread, no atomics).  Draining and storing from the
+// accumulator-owning threads directly costs 2x: a thread owns one row, so each of its stores touches 32 different
+// lines and the column sums need 128 shuffles.
 #include "pgn_common.cuh"
 #include "pgn_kernels.h"
 #include "pgn_umma.cuh"
@@ -31,32 +43,35 @@ using namespace pgn;
 #ifdef PGN_CHAIN_PROF
 __device__ unsigned long long g_chain_prof[16];
 #define CP_T0() const long long cp_t0 = clock64()
-#define CP_ADD(slot) do { if (blockIdx.x == 0) atomicAdd(&g_chain_prof[slot], (unsigned long long)(clock64() - cp_t0)); } while (0)
+#define CP_ADD(slot) do { cp_acc[slot] += (unsigned long long)(clock64() - cp_t0); } while (0)
+#define CP_ARGS , unsigned long long (&cp_acc)[10]
+#define CP_PASS , cp_acc
 #else
 #define CP_T0()
 #define CP_ADD(slot)
+#define CP_ARGS
+#define CP_PASS
 #endif
 
 namespace {
 
-constexpr int kTile = 128;                       // rows per UMMA tile
-constexpr int kTiles = 2;                        // row tiles per CTA block (share the weight slabs)
-constexpr int kBlockRows = kTile * kTiles;
+constexpr int kTile = 128;                       // rows of a tile held by one CTA (UMMA M = 256 over the pair)
+constexpr int kTiles = 2;                        // tiles in flight per CTA pair (MMA of one overlaps the drain of the other)
+constexpr int kPairRows = 2 * kTile * kTiles;    // 512 rows per pair-block
 constexpr int kRun = kTile * 16;                 // bytes of one 8-wide K run of a tile
 constexpr int kABytes = 32 * kRun;               // 64 KB: [256/8 runs][128 rows][8] bf16
-constexpr int kSlabBytes = 2 * 256 * 16;         // one K = 16 step of a [256 x K] weight: [2][256][8] bf16
-constexpr int kStages = 10;                     // 80 KB of weight slabs in flight (a 16-slab layer is 128 KB)
+constexpr int kFillBytes = 2 * 2 * 128 * 16;     // one ring stage: two K = 16 steps of this CTA's N half, [2 ks][2][128][8] bf16 (8 KB)
+constexpr int kStages = 10;                      // 80 KB: one layer (8 fills, read by both tiles) + 2 fills of prefetch
 constexpr int kLayers = 8;                       // fold layer (K = 128) + W_7 .. W_1 (K = 256)
-constexpr int kSlabsPerBlock = 8 + 7 * 16;       // 120
+constexpr int kFillsPerBlock = 4 + 7 * 8;        // 60 (x 2 CTAs x 8 KB = the 960 KB weight stream)
 constexpr int kThreads = 768;
-constexpr int kGroup = 4;                       // weight slabs (K-steps) issued per tile before switching accumulators
 
 struct __align__(1024) ChainSmem {
   uint8_t a[kTiles][kABytes];
-  uint8_t w[kStages][kSlabBytes];
+  uint8_t w[kStages][kFillBytes];
   float colsum[kLayers][256];
   float w_alpha[256];
-  uint64_t w_full[kStages], w_empty[kStages], acc_full, act_ready[kTiles], cs_ready[kTiles], cs_done[kTiles];
+  uint64_t w_full[kStages], w_empty[kStages], acc_full[kTiles], act_ready[kTiles], cs_ready[kTiles], cs_done[kTiles];
   uint32_t tmem_slot;
 };
 
@@ -66,7 +81,57 @@ __device__ __forceinline__ void mbar_arrive_local(uint64_t* bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__global__ void __launch_bounds__(kThreads, 1)
+
+// One layer of the chain for both tiles, issued by the leader CTA's issuer warp (whole warp convergent, one elected
+// lane per tcgen05 instruction).  A single warp retires about one instruction per 5-6 cycles and a K-step is 131 cycles
+// of tensor time, so the loop has to be lean: ring stages, barrier parities and operand offsets are compile-time
+// (120 slabs per block = 6 turns of the 20-stage ring, 8 layers per block: every parity repeats per block), descriptors
+// are base + immediate.  (The first version computed stage = slab % 20 and the descriptors per K-step at run time:
+// ~390 cycles per K-step, no faster than the round-1 kernel.)
+// The issuer, the weight producer and the peer relay are single latency-critical warps: they spin on test_wait.  Parked in
+// try_wait (hardware suspend) their wake-up latency sat on the tensor pipe's critical path: 295 -> 253 us per pass.
+#define CHAIN_ISSUER_WAIT mbar_spin_s
+template <int J>
+__device__ __forceinline__ bool chain_issue_layer(uint32_t w_full0, uint32_t w_empty0, uint32_t acc_full0, uint32_t act_ready0,
+                                                  uint32_t a_lo0, uint32_t ring_lo, uint32_t tmem, volatile int* status CP_ARGS) {
+  constexpr int nfills = J == 0 ? 4 : 8;
+  constexpr int fill0 = J == 0 ? 0 : 4 + (J - 1) * 8;
+  constexpr uint32_t idesc = umma_idesc_bf16(2 * kTile, 256);
+  constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);                 // SBO = 128 B, descriptor version 1
+  constexpr uint32_t b_lbo = ((kTile * 16u) >> 4) << 16;                 // B: LBO = 128 rows x 16 B (this CTA's N half)
+#pragma unroll
+  for (int t = 0; t < kTiles; ++t) {
+    { CP_T0(); if (!CHAIN_ISSUER_WAIT(act_ready0 + t * 8, J & 1, status, 702)) return false; CP_ADD(0); }
+    tc_fence_after_sync();
+#pragma unroll
+    for (int f = 0; f < nfills; ++f) {
+      const int fl = fill0 + f, st = fl % kStages;
+      if (t == 0) {                                                       // (tile 1 re-reads the resident fill)
+        CP_T0();
+        if (!CHAIN_ISSUER_WAIT(w_full0 + st * 8, (fl / kStages) & 1, status, 703)) return false;
+        CP_ADD(1);
+        tc_fence_after_sync();
+      }
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        const int ks = 2 * f + g;
+        const uint32_t a_lo = a_lo0 + (uint32_t)t * (kABytes >> 4) + (uint32_t)ks * ((2 * kRun) >> 4);
+        const uint32_t b_lo = (ring_lo + (uint32_t)st * (kFillBytes >> 4) + (uint32_t)g * (kFillBytes >> 5)) | b_lbo;
+        umma_bf16_2cta_elect(tmem + (uint32_t)t * 256, ((uint64_t)kDescHi << 32) | a_lo, ((uint64_t)kDescHi << 32) | b_lo, idesc,
+                             ks > 0 ? 1u : 0u);
+      }
+      if (t == kTiles - 1) umma_commit_2cta_elect_s(w_empty0 + st * 8);   // both CTAs' ring stages
+    }
+    umma_commit_2cta_elect_s(acc_full0 + t * 8);
+  }
+  return true;
+}
+
+// A failed (timed-out) wait has already written the status word: every role then leaves through the common tail, so both
+// CTAs of the pair still meet at the closing cluster barrier.
+#define CHAIN_WAIT(bar, parity, code) do { if (!mbar_wait((bar), (parity), status, (code))) goto tail; } while (0)
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 pgn_delta_chain_kernel(const uint4* __restrict__ dG, const float* __restrict__ d_raw, const uint4* __restrict__ mask,
                        long long mask_rows, long long m, const uint8_t* __restrict__ wstream,
                        const float* __restrict__ w_alpha, uint4* __restrict__ dz, float* __restrict__ colsum_g,
@@ -75,76 +140,75 @@ pgn_delta_chain_kernel(const uint4* __restrict__ dG, const float* __restrict__ d
   ChainSmem& sm = *reinterpret_cast<ChainSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   volatile int* status = status_g;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const long long n_blocks = (m + kBlockRows - 1) / kBlockRows;
+  const uint32_t rank = cluster_ctarank();
+  const long long n_blocks = (m + kPairRows - 1) / kPairRows;
+  const long long cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
 
   if (tid == 0) {
-    for (int i = 0; i < kStages; ++i) { mbar_init(&sm.w_full[i], 1); mbar_init(&sm.w_empty[i], 1); }
-    mbar_init(&sm.acc_full, 1);
-    for (int t = 0; t < kTiles; ++t) { mbar_init(&sm.act_ready[t], 8); mbar_init(&sm.cs_ready[t], 8); mbar_init(&sm.cs_done[t], 4); }
+    for (int i = 0; i < kStages; ++i) { mbar_init(&sm.w_full[i], rank == 0 ? 2 : 1); mbar_init(&sm.w_empty[i], 1); }
+    for (int t = 0; t < kTiles; ++t) {
+      mbar_init(&sm.acc_full[t], 1);
+      mbar_init(&sm.act_ready[t], 16);           // the 8 drain warps of the tile in BOTH CTAs (leader's barrier is the one waited on)
+      mbar_init(&sm.cs_ready[t], 8); mbar_init(&sm.cs_done[t], 4);
+    }
     fence_mbar_init();
   }
   for (int i = tid; i < kLayers * 256; i += kThreads) (&sm.colsum[0][0])[i] = 0.f;
   for (int i = tid; i < 256; i += kThreads) sm.w_alpha[i] = w_alpha[i];
-  if (warp == 0) { tmem_alloc(&sm.tmem_slot, 512); tmem_relinquish(); }
+  if (warp == 0) { tmem_alloc_2cta(&sm.tmem_slot, 512); tmem_relinquish_2cta(); }
   tc_fence_before_sync();
   __syncthreads();
+  cluster_sync_all();
   tc_fence_after_sync();
   const uint32_t tmem = sm.tmem_slot;
+#ifdef PGN_CHAIN_PROF
+  unsigned long long cp_acc[10] = {};
+  const long long cp_k0 = clock64();
+#endif
 
   if (warp == 0) {
-    // ---------------------------------------------------------------- weight producer
+    // ---------------------------------------------------------------- weight producer (this CTA's N half of every fill)
     if (lane == 0) {
-      uint32_t slab = 0;
-      for (long long blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
-        for (int i = 0; i < kSlabsPerBlock; ++i, ++slab) {
-          const uint32_t st = slab % kStages, use = slab / kStages;
-          if (use > 0 && !mbar_wait(&sm.w_empty[st], (use - 1) & 1, status, 701)) return;
-          mbar_expect_tx(&sm.w_full[st], kSlabBytes);
-          bulk_g2s_s(smem_u32(sm.w[st]), wstream + (size_t)i * kSlabBytes, kSlabBytes, smem_u32(&sm.w_full[st]));
+      uint32_t fill = 0;
+      for (long long blk = cluster_id; blk < n_blocks; blk += n_clusters) {
+        for (int i = 0; i < kFillsPerBlock; ++i, ++fill) {
+          const uint32_t st = fill % kStages, use = fill / kStages;
+          if (use > 0 && !CHAIN_ISSUER_WAIT(smem_u32(&sm.w_empty[st]), (use - 1) & 1, status, 701)) goto tail;
+          mbar_expect_tx(&sm.w_full[st], kFillBytes);
+          bulk_g2s_s(smem_u32(sm.w[st]), wstream + ((size_t)i * 2 + rank) * kFillBytes, kFillBytes, smem_u32(&sm.w_full[st]));
+        }
+      }
+    }
+  } else if (warp == 1 && rank == 1) {
+    // ---------------------------------------------------------------- peer relay: "my half of fill f has landed"
+    if (lane == 0) {
+      uint32_t fill = 0;
+      for (long long blk = cluster_id; blk < n_blocks; blk += n_clusters) {
+        for (int i = 0; i < kFillsPerBlock; ++i, ++fill) {
+          const uint32_t st = fill % kStages, use = fill / kStages;
+          if (!CHAIN_ISSUER_WAIT(smem_u32(&sm.w_full[st]), use & 1, status, 708)) goto tail;
+          mbar_arrive_cluster(&sm.w_full[st], 0);
         }
       }
     }
   } else if (warp == 1) {
-    // ---------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(kTile, 256);
-      uint32_t slab = 0, ready_phase = 0;
-      for (long long blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
-        for (int j = 0; j < kLayers; ++j, ++ready_phase) {
-          { CP_T0();
-          for (int t = 0; t < kTiles; ++t)
-            if (!mbar_wait(&sm.act_ready[t], ready_phase & 1, status, 702)) return;
-          CP_ADD(0); }
-          tc_fence_after_sync();
-          // K-steps are issued in groups of kGroup slabs per tile: consecutive MMAs that accumulate into the SAME TMEM
-          // tile pipeline back to back (131 cycles each); alternating the two accumulators every instruction costs 2x
-          const int nks = j == 0 ? 8 : 16;
-          for (int ks0 = 0; ks0 < nks; ks0 += kGroup) {
-#pragma unroll
-            for (int g = 0; g < kGroup; ++g) {
-              const uint32_t sl = slab + g, st = sl % kStages, use = sl / kStages;
-              CP_T0();
-              if (!mbar_wait(&sm.w_full[st], use & 1, status, 703)) return;
-              CP_ADD(1);
-            }
-            tc_fence_after_sync();
-#pragma unroll
-            for (int t = 0; t < kTiles; ++t) {
-#pragma unroll
-              for (int g = 0; g < kGroup; ++g) {
-                const uint32_t st = (slab + g) % kStages;
-                const uint64_t bd = umma_smem_desc(smem_u32(sm.w[st]), 256 * 16, 128);
-                const uint64_t ad = umma_smem_desc(smem_u32(sm.a[t]) + (uint32_t)(ks0 + g) * 2 * kRun, kRun, 128);
-                umma_bf16(tmem + (uint32_t)t * 256, ad, bd, idesc, (ks0 + g) > 0 ? 1u : 0u);
-              }
-            }
-#pragma unroll
-            for (int g = 0; g < kGroup; ++g) umma_commit(&sm.w_empty[(slab + g) % kStages]);
-            slab += kGroup;
-          }
-          umma_commit(&sm.acc_full);
-        }
-      }
+    // ---------------------------------------------------------------- MMA issuer (leader CTA, UMMA M = 256 over the pair)
+    static_assert(kFillsPerBlock % kStages == 0 && ((kFillsPerBlock / kStages) & 1) == 0 && (kLayers & 1) == 0,
+                  "chain_issue_layer's compile-time ring stages / parities assume whole, even ring turns per block");
+    const uint32_t w_full0 = smem_u32(&sm.w_full[0]), w_empty0 = smem_u32(&sm.w_empty[0]);
+    const uint32_t acc_full0 = smem_u32(&sm.acc_full[0]), act_ready0 = smem_u32(&sm.act_ready[0]);
+    const uint32_t a_lo0 = (smem_u32(sm.a[0]) >> 4) | ((uint32_t)(kRun >> 4) << 16);       // A: LBO = one 8-column run
+    const uint32_t ring_lo = smem_u32(sm.w[0]) >> 4;
+    for (long long blk = cluster_id; blk < n_blocks; blk += n_clusters) {
+      bool ok = chain_issue_layer<0>(w_full0, w_empty0, acc_full0, act_ready0, a_lo0, ring_lo, tmem, status CP_PASS);
+      ok = ok && chain_issue_layer<1>(w_full0, w_empty0, acc_full0, act_ready0, a_lo0, ring_lo, tmem, status CP_PASS);
+      ok = ok && chain_issue_layer<2>(w_full0, w_empty0, acc_full0, act_ready0, a_lo0, ring_lo, tmem, status CP_PASS);
+      ok = ok && chain_issue_layer<3>(w_full0, w_empty0, acc_full0, act_ready0, a_lo0, ring_lo, tmem, status CP_PASS);
+      ok = ok && chain_issue_layer<4>(w_full0, w_empty0, acc_full0, act_ready0, a_lo0, ring_lo, tmem, status CP_PASS);
+      ok = ok && chain_issue_layer<5>(w_full0, w_empty0, acc_full0, act_ready0, a_lo0, ring_lo, tmem, status CP_PASS);
+      ok = ok && chain_issue_layer<6>(w_full0, w_empty0, acc_full0, act_ready0, a_lo0, ring_lo, tmem, status CP_PASS);
+      ok = ok && chain_issue_layer<7>(w_full0, w_empty0, acc_full0, act_ready0, a_lo0, ring_lo, tmem, status CP_PASS);
+      if (!ok) goto tail;
     }
   } else if (warp >= 20) {
     // ---------------------------------------------------------------- dZ store + bias-gradient group (128 threads)
@@ -153,15 +217,15 @@ pgn_delta_chain_kernel(const uint4* __restrict__ dG, const float* __restrict__ d
     // 64-byte row pieces made this group 1.6x slower: it is bound by its global stores, all SMs storing at once.)
     const int dw = warp - 20, rr = lane & 3, run = dw * 8 + (lane >> 2);
     uint32_t phase = 0;
-    for (long long blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
-      const long long r0 = blk * kBlockRows;
+    for (long long blk = cluster_id; blk < n_blocks; blk += n_clusters) {
+      const long long r0 = blk * kPairRows + rank * kTile;
       for (int j = 0; j < kLayers; ++j, ++phase) {
         const int L = 7 - j;
         for (int t = 0; t < kTiles; ++t) {
-          { CP_T0(); if (!mbar_wait(&sm.cs_ready[t], phase & 1, status, 705)) return; if (warp == 20 && lane == 0) CP_ADD(2); }
+          { CP_T0(); CHAIN_WAIT(&sm.cs_ready[t], phase & 1, 705); CP_ADD(2); }
           CP_T0();
           const uint32_t src = smem_u32(sm.a[t]) + (uint32_t)run * kRun + rr * 16;
-          const long long g0 = r0 + t * kTile + rr;
+          const long long g0 = r0 + t * 2 * kTile + rr;
           uint4* out = dz + ((size_t)L * m + (size_t)g0) * 32 + run;
           float acc[8];
 #pragma unroll
@@ -188,7 +252,7 @@ pgn_delta_chain_kernel(const uint4* __restrict__ dG, const float* __restrict__ d
             for (int e = 0; e < 8; ++e) sm.colsum[L][run * 8 + e] += acc[e];
           }
           __syncwarp();
-          if (warp == 20 && lane == 0) CP_ADD(3);
+          CP_ADD(3);
           if (lane == 0) mbar_arrive_local(&sm.cs_done[t]);
         }
       }
@@ -201,25 +265,24 @@ pgn_delta_chain_kernel(const uint4* __restrict__ dG, const float* __restrict__ d
     }
   } else if (warp >= 4) {
     // ---------------------------------------------------------------- epilogue / staging groups (2 x 256 threads)
-    // warps 4-11 own tile 0, warps 12-19 tile 1: both accumulators are drained at the same time (a drain is a long
-    // dependent chain per thread, so its rate grows with the number of warps on it)
+    // warps 4-11 own tile 0, warps 12-19 tile 1 (this CTA's 128 rows of each)
     const int ew = warp - 4, t = ew >> 3, q = ew & 3, half = (ew >> 2) & 1;
     const int et = (tid - 128) & 255;               // thread of the tile's group
-    const int row = q * 32 + lane;                  // TMEM lane = row of the tile
+    const int row = q * 32 + lane;                  // TMEM lane = row of this CTA's part of the tile
     const int col0 = half * 128;
     const uint32_t a_base = smem_u32(sm.a[t]);
     const uint32_t taddr = tmem + (uint32_t)t * 256 + ((uint32_t)(q * 32) << 16) + (uint32_t)col0;
     const uint32_t dst0 = a_base + (uint32_t)(col0 >> 3) * kRun + row * 16;
     uint32_t acc_phase = 0, csd_phase = 0;          // csd_phase: completed store/sum passes over the A tile waited for so far
     bool first = true;
-    for (long long blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
-      const long long r0 = blk * kBlockRows + t * kTile;
+    for (long long blk = cluster_id; blk < n_blocks; blk += n_clusters) {
+      const long long r0 = blk * kPairRows + t * 2 * kTile + rank * kTile;
       // stage in dG: [128 rows x 128 columns] -> the first 16 runs of the A tile (once the store group has read the
       // previous block's last deltas out of it)
       {
         const int srow = et & 127, sh = et >> 7;    // row of the tile, 64-column half
         if (!first) {
-          if (!mbar_wait(&sm.cs_done[t], csd_phase & 1, status, 706)) return;
+          CHAIN_WAIT(&sm.cs_done[t], csd_phase & 1, 706);
           ++csd_phase;
         }
         first = false;
@@ -233,19 +296,19 @@ pgn_delta_chain_kernel(const uint4* __restrict__ dG, const float* __restrict__ d
         }
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive_local(&sm.act_ready[t]);
+        if (lane == 0) mbar_arrive_cluster(&sm.act_ready[t], 0);
       }
       const long long gr = r0 + row;
       const float dsig = gr < m ? __ldg(d_raw + (size_t)gr * 4 + 3) : 0.f;
       for (int j = 0; j < kLayers; ++j, ++acc_phase) {
         const int L = 7 - j;                        // this layer's output is dL/dh_L; its mask is [h_L > 0]
         const uint4 mk = gr < m ? __ldg(mask + ((size_t)L * mask_rows + gr) * 2 + half) : make_uint4(0u, 0u, 0u, 0u);
-        { CP_T0(); if (!mbar_wait(&sm.acc_full, acc_phase & 1, status, 704)) return; if (tid == 128) CP_ADD(4); }
+        { CP_T0(); CHAIN_WAIT(&sm.acc_full[t], acc_phase & 1, 704); CP_ADD(4); }
         tc_fence_after_sync();
         if (j > 0) {                                 // the previous deltas have been stored / summed out of the A tile
           CP_T0();
-          if (!mbar_wait(&sm.cs_done[t], csd_phase & 1, status, 707)) return;
-          if (tid == 128) CP_ADD(5);
+          CHAIN_WAIT(&sm.cs_done[t], csd_phase & 1, 707);
+          CP_ADD(5);
           ++csd_phase;
         }
         CP_T0();
@@ -276,17 +339,25 @@ pgn_delta_chain_kernel(const uint4* __restrict__ dG, const float* __restrict__ d
         tc_fence_before_sync();
         if (j + 1 < kLayers) fence_proxy_async_smem();
         __syncwarp();
-        if (tid == 128) CP_ADD(6);
+        CP_ADD(6);
         if (lane == 0) {
-          if (j + 1 < kLayers) mbar_arrive_local(&sm.act_ready[t]);      // next layer's A operand (and a free accumulator)
+          if (j + 1 < kLayers) mbar_arrive_cluster(&sm.act_ready[t], 0);  // next layer's A operand (and a free accumulator)
           mbar_arrive_local(&sm.cs_ready[t]);                            // dZ_L of this tile is in shared memory
         }
       }
     }
   }
+tail:
+#ifdef PGN_CHAIN_PROF
+  if (blockIdx.x == 0 && (tid == 32 || tid == 128 || tid == 640)) {
+    cp_acc[tid == 32 ? 7 : (tid == 128 ? 8 : 9)] = (unsigned long long)(clock64() - cp_k0);
+    for (int k = 0; k < 10; ++k) atomicAdd(&g_chain_prof[k], cp_acc[k]);
+  }
+#endif
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 0) { tc_fence_after_sync(); tmem_dealloc(tmem, 512); }
+  cluster_sync_all();                 // the peer's shared memory / TMEM stay alive until every MMA has retired
+  if (warp == 0) { tc_fence_after_sync(); tmem_dealloc_2cta(tmem, 512); }
 }
 
 // the chain's weight stream from the context's fp32 copies (include/posegen_b200.h: pgn_mlp_delta_chain): slab element
@@ -294,16 +365,16 @@ pgn_delta_chain_kernel(const uint4* __restrict__ dG, const float* __restrict__ d
 // W'_j = W_l^T for l = 8 - j (nn.Linear layout [out][in]; the skip layer l = 5 without its first 432 input columns)
 struct ChainPackPtrs { const float* w[8]; };       // pts_linears.0 .. 7
 __global__ void pgn_pack_chain_kernel(ChainPackPtrs p, const float* __restrict__ fold, __nv_bfloat16* __restrict__ out) {
-  const int total = kSlabsPerBlock * 4096;
+  const int total = kFillsPerBlock * 2 * (kFillBytes / 2);
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-    const int slab = idx >> 12, r = idx & 4095;
-    const int kc = r >> 11, n = (r >> 3) & 255, e = r & 7;
+    const int fill = idx >> 13, r = idx & 8191;                       // 8192 elements per fill (both CTA halves)
+    const int h = r >> 12, g = (r >> 11) & 1, kc = (r >> 10) & 1, n = h * 128 + ((r >> 3) & 127), e = r & 7;
     float v;
-    if (slab < 8) {
-      const int k = slab * 16 + kc * 8 + e;
+    if (fill < 4) {
+      const int k = (2 * fill + g) * 16 + kc * 8 + e;
       v = fold[k * 256 + n];
     } else {
-      const int j = 1 + (slab - 8) / 16, ks = (slab - 8) % 16, l = 8 - j;
+      const int j = 1 + (fill - 4) / 8, ks = 2 * ((fill - 4) % 8) + g, l = 8 - j;
       const int k = ks * 16 + kc * 8 + e;
       v = (l == 5) ? p.w[5][k * 688 + 432 + n] : p.w[l][k * 256 + n];
     }
@@ -332,8 +403,9 @@ cudaError_t pgn_launch_delta_chain(const void* dG, const float* d_raw, const voi
     if (e != cudaSuccess) return e;
     configured.set();
   }
-  const long long n_blocks = (m + kBlockRows - 1) / kBlockRows;
-  const unsigned grid = (unsigned)(n_blocks < num_sms ? n_blocks : num_sms);
+  const long long n_blocks = (m + kPairRows - 1) / kPairRows;
+  const long long pairs = num_sms / 2;
+  const unsigned grid = 2u * (unsigned)(n_blocks < pairs ? n_blocks : pairs);       // clusters of 2 CTAs
   pgn_delta_chain_kernel<<<grid, kThreads, smem, stream>>>(reinterpret_cast<const uint4*>(dG), d_raw,
                                                            reinterpret_cast<const uint4*>(mask), mask_rows, m,
                                                            reinterpret_cast<const uint8_t*>(wstream), w_alpha,

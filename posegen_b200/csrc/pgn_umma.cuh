@@ -92,6 +92,26 @@ __device__ __forceinline__ bool mbar_wait_s(uint32_t bar, uint32_t parity, volat
   }
   return true;
 }
+// pure spin on test_wait (no hardware suspend): for a single latency-critical warp (an MMA issuer) whose wake-up latency
+// from a parked try_wait would sit on the tensor pipe's critical path
+__device__ __forceinline__ bool mbar_test_wait_s(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n .reg .pred p;\n mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ bool mbar_spin_s(uint32_t bar, uint32_t parity, volatile int* status, int code) {
+  if (mbar_test_wait_s(bar, parity)) return true;
+  const long long t0 = clock64();
+  int spins = 0;
+  while (!mbar_test_wait_s(bar, parity)) {
+    if ((++spins & 1023) == 0) {
+      if (*status != 0) return false;
+      if (clock64() - t0 > (1ll << 31)) { *status = code; return false; }
+    }
+  }
+  return true;
+}
 __device__ __forceinline__ void mbar_arrive_cluster_s(uint32_t bar, uint32_t cta) {
   asm volatile("{\n .reg .b32 ra;\n mapa.shared::cluster.u32 ra, %0, %1;\n"
                " mbarrier.arrive.shared::cluster.b64 _, [ra];\n}\n" ::"r"(bar), "r"(cta) : "memory");

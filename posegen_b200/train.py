@@ -77,13 +77,13 @@ def act_masks(acts: torch.Tensor):
 
 
 def chain_wstream(P: Dict[str, torch.Tensor]) -> torch.Tensor:
-    """The eight weights of the delta chain in the slab layout `pgn_mlp_delta_chain` streams (include/posegen_b200.h):
+    """The eight weights of the delta chain in the fill layout `pgn_mlp_delta_chain` streams (include/posegen_b200.h):
     W'_0 = (W_v[:, :256] W_f)^T [256,128], W'_j = W_l^T [256,256] for l = 7..1 (layer 5 without its 432 skip columns),
-    each as [K/16][2][256][8] bf16."""
+    each as [K/32 fills][2 N halves][2 K-steps][2][128][8] bf16 (one 8 KB bulk copy per fill and CTA of the pair)."""
     fold = P["views_linears.0.weight"][:, :256] @ P["feature_linear.weight"]
     mats = [fold.t()] + [(P[f"pts_linears.{l}.weight"][:, 432:] if l == 5 else P[f"pts_linears.{l}.weight"]).t()
                          for l in range(7, 0, -1)]
-    return torch.cat([w.to(torch.bfloat16).reshape(256, -1, 2, 8).permute(1, 2, 0, 3).reshape(-1) for w in mats])
+    return torch.cat([w.to(torch.bfloat16).reshape(2, 128, -1, 2, 2, 8).permute(2, 0, 3, 4, 1, 5).reshape(-1) for w in mats])
 
 
 def mlp_backward(params: Dict[str, torch.Tensor], enc: torch.Tensor, acts: torch.Tensor, d_raw: torch.Tensor,

@@ -254,8 +254,8 @@ def test_torch_fk_matches_numpy_helpers_and_is_differentiable():
 
 
 def test_chain_weight_stream_layout():
-    """train.chain_wstream: the 120 K=16 slabs pgn_mlp_delta_chain streams, [K/16][2][256][8] per weight, in the order
-    fold layer, W_7 .. W_1 (include/posegen_b200.h)."""
+    """train.chain_wstream: the 60 fills (two K=16 steps each) pgn_mlp_delta_chain streams,
+    [K/32][2 N halves][2 K-steps][2][128][8] per weight, in the order fold layer, W_7 .. W_1 (include/posegen_b200.h)."""
     import torch
     from posegen_b200 import synthetic as syn
     from posegen_b200.train import chain_wstream
@@ -268,9 +268,9 @@ def test_chain_weight_stream_layout():
     off = 0
     for w in mats:
         K = w.shape[1]
-        slabs = ws[off:off + 256 * K].view(K // 16, 2, 256, 8)
-        for (ks, kc, n, e) in ((0, 0, 0, 0), (K // 16 - 1, 1, 255, 7), (1, 0, 17, 3), (2, 1, 200, 5)):
-            assert slabs[ks, kc, n, e] == w[n, ks * 16 + kc * 8 + e]
+        fills = ws[off:off + 256 * K].view(K // 32, 2, 2, 2, 128, 8)
+        for (f, h, g, kc, n, e) in ((0, 0, 0, 0, 0, 0), (K // 32 - 1, 1, 1, 1, 127, 7), (1, 0, 1, 0, 17, 3), (2, 1, 0, 1, 72, 5)):
+            assert fills[f, h, g, kc, n, e] == w[h * 128 + n, (2 * f + g) * 16 + kc * 8 + e]
         off += 256 * K
     assert off == ws.numel()
 

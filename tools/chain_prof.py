@@ -17,8 +17,9 @@ torch.cuda.synchronize()
 buf = (C.c_uint64 * 16)()
 eng.lib.pgn_debug_chain_prof(buf, 1)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record(); eng.mlp_delta_chain(dG, d_raw, mask, rows, ws, wa); e1.record(); torch.cuda.synchronize()
+lm = int(sys.argv[1], 0) if len(sys.argv) > 1 else 0xFF
+e0.record(); eng.mlp_delta_chain(dG, d_raw, mask, rows, ws, wa, layer_mask=lm); e1.record(); torch.cuda.synchronize()
 eng.lib.pgn_debug_chain_prof(buf, 0)
-names = ["issuer wait act_ready", "issuer wait w_full", "store-grp wait cs_ready", "store-grp work", "epi wait acc_full", "epi wait cs_done", "epi drain"]
+names = ["issuer wait act_ready", "issuer wait w_full", "store-grp wait cs_ready", "store-grp work", "epi wait acc_full", "epi wait cs_done", "epi drain", "issuer total", "epi total", "store-grp total"]
 print("kernel us", e0.elapsed_time(e1) * 1e3, "block-layers per CTA", (m // 256 + 147) // 148 * 8)
 for n, v in zip(names, buf): print(f"{n:26s} {v:12d} cycles")
