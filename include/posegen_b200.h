@@ -394,6 +394,13 @@ PGN_API int  pgn_compose_frames_batch(pgn_context* ctx, int32_t H, int32_t W, co
                                       int32_t n_poses, const float* rgb_map, const float* acc_map, float bg, float* images,
                                       void* stream);
 
+/* Rows of selected rays out of per-sample planes: dst[p][i] = src[p][idx[i]], n_planes planes of rows of row_bytes bytes
+ * (a multiple of 16; planes 16-byte aligned), idx device int64 [n_idx].  The pose gradient of a frame (run_gan.py:2040-2091
+ * made differentiable, BASELINE.json configs[4]) walks the rays the HMR crop reads in chunks and selects their samples out
+ * of the frame's mask dump / raw / z_fine with it (torch.index_select took 6 ms per image on these shapes). */
+PGN_API int  pgn_gather_ray_rows(pgn_context* ctx, const void* src, void* dst, const int64_t* idx, int64_t n_idx, int64_t row_bytes,
+                                 int32_t n_planes, int64_t src_plane_bytes, int64_t dst_plane_bytes, void* stream);
+
 /* "next" row 4: rendered frame -> HMR input without the PNG round trip
  * (run_gan.py:2057-2071, 2326, 2433-2445): optional uint8 quantisation, crop [y0:y1, x0:x1], /255,
  * Normalize(mean, std), skimage.transform.resize(..., (3,R,R), anti_aliasing=True).

@@ -24,7 +24,7 @@ EXPORTED = [
     "pgn_check_device_status", "pgn_device_status_ptr", "pgn_near_far", "pgn_encode", "pgn_mlp", "pgn_composite", "pgn_composite_backward", "pgn_encode_backward", "pgn_encode_bf16", "pgn_encode_backward_bf16", "pgn_mlp_delta", "pgn_mlp_delta_chain", "pgn_mlp_delta_chain_net", "pgn_mask_dump_bytes", "pgn_render_forward_masks", "pgn_view_delta_from_mask",
     "pgn_sample_pdf", "pgn_generate_rays", "pgn_compose_frame", "pgn_pose_to_skts", "pgn_frame_to_hmr_input",
     "pgn_weight_grad_floats", "pgn_mlp_weight_grads", "pgn_debug_wgrad", "pgn_framecode_backward", "pgn_mlp_input_grads",
-    "pgn_pose_fk_backward", "pgn_cylinder_bboxes", "pgn_generate_rays_batch", "pgn_compose_frames_batch",
+    "pgn_pose_fk_backward", "pgn_cylinder_bboxes", "pgn_generate_rays_batch", "pgn_compose_frames_batch", "pgn_gather_ray_rows",
     "pgn_debug_umma_gemm", "pgn_debug_phase_timers",
 ]
 
@@ -121,6 +121,7 @@ def load() -> C.CDLL:
     lib.pgn_cylinder_bboxes.argtypes = [vp, vp, i32, C.POINTER(C.c_double), i32, i32, f32, vp, vp]
     lib.pgn_generate_rays_batch.argtypes = [vp, i32, i32, f32, C.POINTER(f32), vp, vp, i32, i64, vp, vp, vp]
     lib.pgn_compose_frames_batch.argtypes = [vp, i32, i32, vp, vp, i32, vp, vp, f32, vp, vp]
+    lib.pgn_gather_ray_rows.argtypes = [vp, vp, vp, vp, i64, i64, i32, i64, i64, vp]
     lib.pgn_debug_umma_gemm.argtypes = [vp, vp, vp, vp, i32, i32, i32, vp]
     lib.pgn_debug_phase_timers.argtypes = [vp, i32, C.POINTER(C.c_uint64)]
     for name in EXPORTED:

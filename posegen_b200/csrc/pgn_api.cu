@@ -641,6 +641,18 @@ int pgn_generate_rays_batch(pgn_context* c, int32_t H, int32_t W, float focal, c
   return PGN_OK;
 }
 
+int pgn_gather_ray_rows(pgn_context* c, const void* src, void* dst, const int64_t* idx, int64_t n_idx, int64_t row_bytes,
+                        int32_t n_planes, int64_t src_plane_bytes, int64_t dst_plane_bytes, void* stream) {
+  if (!c || !src || !dst || !idx || n_idx < 0 || n_planes < 0 || row_bytes <= 0 || (row_bytes & 15) || (src_plane_bytes & 15) ||
+      (dst_plane_bytes & 15) || ((uintptr_t)src & 15) || ((uintptr_t)dst & 15))
+    return fail(PGN_E_INVALID, "pgn_gather_ray_rows: bad argument (rows and planes are multiples of 16 bytes, 16-byte aligned)");
+  PGN_ON_DEVICE(c);
+  PGN_CUDA(pgn_launch_gather_ray_rows(src, dst, (const long long*)idx, n_idx, row_bytes, n_planes, src_plane_bytes, dst_plane_bytes,
+                                      c->num_sms, (cudaStream_t)stream));
+  c->launches++;
+  return PGN_OK;
+}
+
 int pgn_compose_frames_batch(pgn_context* c, int32_t H, int32_t W, const int32_t* bbox, const int64_t* offsets, int32_t n_poses,
                              const float* rgb_map, const float* acc_map, float bg, float* images, void* stream) {
   if (!c || !bbox || !offsets || !images || !rgb_map || !acc_map || n_poses < 0) return fail(PGN_E_INVALID, "pgn_compose_frames_batch: bad argument");

@@ -36,6 +36,7 @@
 #include "pgn_common.cuh"
 #include "pgn_kernels.h"
 #include "pgn_umma.cuh"
+#include "pgn_tma.h"
 
 using namespace pgn;
 
@@ -58,8 +59,8 @@ namespace {
 constexpr int kTile = 128;                       // rows of a tile held by one CTA (UMMA M = 256 over the pair)
 constexpr int kTiles = 2;                        // tiles in flight per CTA pair (MMA of one overlaps the drain of the other)
 constexpr int kPairRows = 2 * kTile * kTiles;    // 512 rows per pair-block
-constexpr int kRun = kTile * 16;                 // bytes of one 8-wide K run of a tile
-constexpr int kABytes = 32 * kRun;               // 64 KB: [256/8 runs][128 rows][8] bf16
+constexpr int kPanel = kTile * 128;              // bytes of one 64-column panel of a tile: 128 rows x 128 B (SWIZZLE_128B)
+constexpr int kABytes = 4 * kPanel;              // 64 KB: [4 panels][128 rows][64] bf16, 16-byte chunks XOR-swizzled by row & 7
 constexpr int kFillBytes = 2 * 2 * 128 * 16;     // one ring stage: two K = 16 steps of this CTA's N half, [2 ks][2][128][8] bf16 (8 KB)
 constexpr int kStages = 10;                      // 80 KB: one layer (8 fills, read by both tiles) + 2 fills of prefetch
 constexpr int kLayers = 8;                       // fold layer (K = 128) + W_7 .. W_1 (K = 256)
@@ -75,6 +76,18 @@ struct __align__(1024) ChainSmem {
   uint32_t tmem_slot;
 };
 
+// byte offset of the 16-byte chunk gc (8 columns 8 gc .. 8 gc + 7) of row r inside an A tile: K-major SWIZZLE_128B, the
+// layout a TMA box of 64 columns x 128 rows has in shared memory (so the tile can be stored with cp.async.bulk.tensor)
+__device__ __forceinline__ uint32_t a_off(int r, int gc) {
+  return (uint32_t)(gc >> 3) * kPanel + (uint32_t)r * 128u + (uint32_t)(((gc & 7) ^ (r & 7)) << 4);
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];\n"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_group0() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive_local(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -97,7 +110,8 @@ __device__ __forceinline__ bool chain_issue_layer(uint32_t w_full0, uint32_t w_e
   constexpr int nfills = J == 0 ? 4 : 8;
   constexpr int fill0 = J == 0 ? 0 : 4 + (J - 1) * 8;
   constexpr uint32_t idesc = umma_idesc_bf16(2 * kTile, 256);
-  constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);                 // SBO = 128 B, descriptor version 1
+  constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);                 // B: SBO = 128 B, descriptor version 1 (SWIZZLE_NONE)
+  constexpr uint32_t kADescHi = (1024u >> 4) | (1u << 14) | (2u << 29);   // A: SBO = 1 KB (8 rows), version 1, SWIZZLE_128B
   constexpr uint32_t b_lbo = ((kTile * 16u) >> 4) << 16;                 // B: LBO = 128 rows x 16 B (this CTA's N half)
 #pragma unroll
   for (int t = 0; t < kTiles; ++t) {
@@ -114,10 +128,10 @@ __device__ __forceinline__ bool chain_issue_layer(uint32_t w_full0, uint32_t w_e
       }
 #pragma unroll
       for (int g = 0; g < 2; ++g) {
-        const int ks = 2 * f + g;
-        const uint32_t a_lo = a_lo0 + (uint32_t)t * (kABytes >> 4) + (uint32_t)ks * ((2 * kRun) >> 4);
+        const int ks = 2 * f + g;                                         // K-step = 32 B inside the 128-byte rows of panel ks / 4
+        const uint32_t a_lo = a_lo0 + (uint32_t)t * (kABytes >> 4) + (uint32_t)(ks >> 2) * (kPanel >> 4) + (uint32_t)(ks & 3) * 2u;
         const uint32_t b_lo = (ring_lo + (uint32_t)st * (kFillBytes >> 4) + (uint32_t)g * (kFillBytes >> 5)) | b_lbo;
-        umma_bf16_2cta_elect(tmem + (uint32_t)t * 256, ((uint64_t)kDescHi << 32) | a_lo, ((uint64_t)kDescHi << 32) | b_lo, idesc,
+        umma_bf16_2cta_elect(tmem + (uint32_t)t * 256, ((uint64_t)kADescHi << 32) | a_lo, ((uint64_t)kDescHi << 32) | b_lo, idesc,
                              ks > 0 ? 1u : 0u);
       }
       if (t == kTiles - 1) umma_commit_2cta_elect_s(w_empty0 + st * 8);   // both CTAs' ring stages
@@ -134,7 +148,7 @@ __device__ __forceinline__ bool chain_issue_layer(uint32_t w_full0, uint32_t w_e
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 pgn_delta_chain_kernel(const uint4* __restrict__ dG, const float* __restrict__ d_raw, const uint4* __restrict__ mask,
                        long long mask_rows, long long m, const uint8_t* __restrict__ wstream,
-                       const float* __restrict__ w_alpha, uint4* __restrict__ dz, float* __restrict__ colsum_g,
+                       const float* __restrict__ w_alpha, const __grid_constant__ CUtensorMap dz_map, float* __restrict__ colsum_g,
                        int* __restrict__ status_g, unsigned layer_mask) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   ChainSmem& sm = *reinterpret_cast<ChainSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -197,7 +211,7 @@ pgn_delta_chain_kernel(const uint4* __restrict__ dG, const float* __restrict__ d
                   "chain_issue_layer's compile-time ring stages / parities assume whole, even ring turns per block");
     const uint32_t w_full0 = smem_u32(&sm.w_full[0]), w_empty0 = smem_u32(&sm.w_empty[0]);
     const uint32_t acc_full0 = smem_u32(&sm.acc_full[0]), act_ready0 = smem_u32(&sm.act_ready[0]);
-    const uint32_t a_lo0 = (smem_u32(sm.a[0]) >> 4) | ((uint32_t)(kRun >> 4) << 16);       // A: LBO = one 8-column run
+    const uint32_t a_lo0 = (smem_u32(sm.a[0]) >> 4) | (1u << 16);                          // A: K-major SWIZZLE_128B (LBO field = 16 B, unused)
     const uint32_t ring_lo = smem_u32(sm.w[0]) >> 4;
     for (long long blk = cluster_id; blk < n_blocks; blk += n_clusters) {
       bool ok = chain_issue_layer<0>(w_full0, w_empty0, acc_full0, act_ready0, a_lo0, ring_lo, tmem, status CP_PASS);
@@ -212,9 +226,12 @@ pgn_delta_chain_kernel(const uint4* __restrict__ dG, const float* __restrict__ d
     }
   } else if (warp >= 20) {
     // ---------------------------------------------------------------- dZ store + bias-gradient group (128 threads)
-    // warp w owns the 8 runs (64 columns) 8w .. 8w+7 of a tile; lane = (row & 3) + 4 * (run & 7): a warp store covers
-    // 4 rows x 128 contiguous bytes (full lines).  (8 rows x 4 runs would make the LDS.128 conflict-free, but its
-    // 64-byte row pieces made this group 1.6x slower: it is bound by its global stores, all SMs storing at once.)
+    // One lane hands the finished tile to the TMA engine: four tensor stores (one per 64-column panel, box = 64 columns x
+    // 128 rows, SWIZZLE_128B: the engine undoes the swizzle and writes whole 128-byte lines of the row-major dz; rows
+    // beyond m are clipped by the tensor map).  (Round 1 / the first CTA-pair version stored with st.global from these
+    // four warps: ~4.5 k cycles per tile and layer, 2x the tensor time - the whole kernel ran at the store group's pace.)
+    // Meanwhile all four warps read the tile for the bias gradients: warp w owns the 8 chunks (64 columns) of panel w,
+    // lane = (row & 3) + 4 * chunk; every column has one owner thread, no atomics.
     const int dw = warp - 20, rr = lane & 3, run = dw * 8 + (lane >> 2);
     uint32_t phase = 0;
     for (long long blk = cluster_id; blk < n_blocks; blk += n_clusters) {
@@ -224,32 +241,39 @@ pgn_delta_chain_kernel(const uint4* __restrict__ dG, const float* __restrict__ d
         for (int t = 0; t < kTiles; ++t) {
           { CP_T0(); CHAIN_WAIT(&sm.cs_ready[t], phase & 1, 705); CP_ADD(2); }
           CP_T0();
-          const uint32_t src = smem_u32(sm.a[t]) + (uint32_t)run * kRun + rr * 16;
-          const long long g0 = r0 + t * 2 * kTile + rr;
-          uint4* out = dz + ((size_t)L * m + (size_t)g0) * 32 + run;
-          float acc[8];
+          if ((layer_mask >> L) & 1u) {                   // layers nobody reads (frozen network) are neither stored nor summed
+            // (issuing the four panel stores a quarter of the column-sum loop apart, so that weight fills could slip in
+            // between them in the copy engine's queue, was slower: 385 instead of 296 us per pass)
+            const uint32_t a_base = smem_u32(sm.a[t]);
+            if (warp == 20 && lane == 0) {
+              const int grow = (int)(r0 + t * 2 * kTile);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-          if ((layer_mask >> L) & 1u)                     // layers nobody reads (frozen network) are neither stored nor summed
-#pragma unroll 8
-          for (int i = 0; i < 32; ++i) {
-            const uint4 v = lds128(src + (uint32_t)i * 64);
-            if (g0 + 4 * i < m) __stcs(out + (size_t)i * 128, v);      // written once, read by a later kernel: streaming store
-            const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              acc[2 * e] += __uint_as_float(w4[e] << 16);
-              acc[2 * e + 1] += __uint_as_float(w4[e] & 0xffff0000u);
+              for (int pnl = 0; pnl < 4; ++pnl) tma_store_3d(&dz_map, a_base + pnl * kPanel, pnl * 64, grow, L);
+              bulk_commit_group();
             }
-          }
+            float acc[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 1);
-            acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 2);
-          }
-          if (rr == 0) {
+            for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+#pragma unroll 8
+            for (int i = 0; i < 32; ++i) {
+              const uint4 v = lds128(a_base + a_off(rr + 4 * i, run));
+              const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-            for (int e = 0; e < 8; ++e) sm.colsum[L][run * 8 + e] += acc[e];
+              for (int e = 0; e < 4; ++e) {
+                acc[2 * e] += __uint_as_float(w4[e] << 16);
+                acc[2 * e + 1] += __uint_as_float(w4[e] & 0xffff0000u);
+              }
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 1);
+              acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 2);
+            }
+            if (rr == 0) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) sm.colsum[L][run * 8 + e] += acc[e];
+            }
+            if (warp == 20 && lane == 0) bulk_wait_group_read0();      // the engine has read the tile out of shared memory
           }
           __syncwarp();
           CP_ADD(3);
@@ -257,6 +281,7 @@ pgn_delta_chain_kernel(const uint4* __restrict__ dG, const float* __restrict__ d
         }
       }
     }
+    if (warp == 20 && lane == 0) bulk_wait_group0();
     // this thread's columns of the CTA's bias partials -> global
     if (rr == 0) {
       for (int L = 0; L < kLayers; ++L)
@@ -272,7 +297,7 @@ pgn_delta_chain_kernel(const uint4* __restrict__ dG, const float* __restrict__ d
     const int col0 = half * 128;
     const uint32_t a_base = smem_u32(sm.a[t]);
     const uint32_t taddr = tmem + (uint32_t)t * 256 + ((uint32_t)(q * 32) << 16) + (uint32_t)col0;
-    const uint32_t dst0 = a_base + (uint32_t)(col0 >> 3) * kRun + row * 16;
+    const int gc0 = half * 16;                      // this thread's first 16-byte chunk (8 columns) of its row
     uint32_t acc_phase = 0, csd_phase = 0;          // csd_phase: completed store/sum passes over the A tile waited for so far
     bool first = true;
     for (long long blk = cluster_id; blk < n_blocks; blk += n_clusters) {
@@ -287,12 +312,11 @@ pgn_delta_chain_kernel(const uint4* __restrict__ dG, const float* __restrict__ d
         }
         first = false;
         const long long gr = r0 + srow;
-        const uint32_t dst = a_base + (uint32_t)(sh * 8) * kRun + srow * 16;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           uint4 v = make_uint4(0u, 0u, 0u, 0u);
           if (gr < m) v = __ldg(dG + (size_t)gr * 16 + sh * 8 + i);
-          sts128(dst + (uint32_t)i * kRun, v.x, v.y, v.z, v.w);
+          sts128(a_base + a_off(srow, sh * 8 + i), v.x, v.y, v.z, v.w);
         }
         fence_proxy_async_smem();
         __syncwarp();
@@ -333,11 +357,11 @@ pgn_delta_chain_kernel(const uint4* __restrict__ dG, const float* __restrict__ d
             if (!(bits & (1u << (2 * i + 1)))) p1 = 0.f;
             pk[i] = pack_bf16x2(p0, p1);
           }
-          sts128(dst0 + (uint32_t)(2 * b) * kRun, pk[0], pk[1], pk[2], pk[3]);
-          sts128(dst0 + (uint32_t)(2 * b + 1) * kRun, pk[4], pk[5], pk[6], pk[7]);
+          sts128(a_base + a_off(row, gc0 + 2 * b), pk[0], pk[1], pk[2], pk[3]);
+          sts128(a_base + a_off(row, gc0 + 2 * b + 1), pk[4], pk[5], pk[6], pk[7]);
         }
         tc_fence_before_sync();
-        if (j + 1 < kLayers) fence_proxy_async_smem();
+        fence_proxy_async_smem();                    // the tile is read by the tensor core (next layer) and by the TMA store
         __syncwarp();
         CP_ADD(6);
         if (lane == 0) {
@@ -406,10 +430,13 @@ cudaError_t pgn_launch_delta_chain(const void* dG, const float* d_raw, const voi
   const long long n_blocks = (m + kPairRows - 1) / kPairRows;
   const long long pairs = num_sms / 2;
   const unsigned grid = 2u * (unsigned)(n_blocks < pairs ? n_blocks : pairs);       // clusters of 2 CTAs
+  CUtensorMap dz_map;                 // dz: bf16 [8][m][256] row-major, stored in boxes of 64 columns x 128 rows
+  e = pgn_make_map_bf16(&dz_map, dz, 256, 256, m, kLayers, m * 256, kTile);
+  if (e != cudaSuccess) return e;
   pgn_delta_chain_kernel<<<grid, kThreads, smem, stream>>>(reinterpret_cast<const uint4*>(dG), d_raw,
                                                            reinterpret_cast<const uint4*>(mask), mask_rows, m,
                                                            reinterpret_cast<const uint8_t*>(wstream), w_alpha,
-                                                           reinterpret_cast<uint4*>(dz), colsum, status, layer_mask);
+                                                           dz_map, colsum, status, layer_mask);
   return cudaGetLastError();
 }
 

@@ -37,6 +37,7 @@
 #include "pgn_common.cuh"
 #include "pgn_kernels.h"
 #include "pgn_umma.cuh"
+#include "pgn_tma.h"
 
 using namespace pgn;
 
@@ -325,31 +326,11 @@ __global__ void __launch_bounds__(256) pgn_view_fold_grads_kernel(const float* _
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------------------
-// host side: tensor maps (cuTensorMapEncodeTiled through the runtime's driver entry point: no link-time libcuda
-// dependency, so the library still loads on a box without a driver and fails with PGN_E_CUDA there)
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
+// host side: tensor maps (pgn_tma.h), boxes of 64 columns x 32 rows
 static cudaError_t make_map(CUtensorMap* map, const void* base, long long cols, long long ld, long long rows, long long layers,
                             long long layer_stride_elems) {
-  static EncodeTiledFn encode = nullptr;
-  if (!encode) {
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
-    if (e != cudaSuccess) return e;
-    if (!fn || q != cudaDriverEntryPointSuccess) return cudaErrorNotSupported;
-    encode = (EncodeTiledFn)fn;
-  }
-  const cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)layers};
-  const cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)(layers > 1 ? layer_stride_elems : ld * rows) * 2};
-  const cuuint32_t box[3] = {(cuuint32_t)kBoxCols, (cuuint32_t)kRows, 1};
-  const cuuint32_t estr[3] = {1, 1, 1};
-  const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+  static_assert(kBoxCols == 64, "pgn_make_map_bf16 encodes 64-column boxes");
+  return pgn_make_map_bf16(map, base, cols, ld, rows, layers, layer_stride_elems, kRows);
 }
 
 // Offsets (floats) of the 12 weight gradients inside the flat buffer: include/posegen_b200.h linear order, nn.Linear layouts

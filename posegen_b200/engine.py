@@ -613,6 +613,23 @@ class Engine:
                                                      _ptr(acc_map.contiguous()), float(bg), _ptr(img), self._stream()))
         return img
 
+    def gather_ray_rows(self, src, idx, n_planes=1):
+        """pgn_gather_ray_rows: rows `idx` (int64, CUDA) of `src` viewed as [n_planes, n_rows, ...]; `src` [n_rows, ...] when
+        n_planes == 1.  A row (everything behind the row dimension) must be a multiple of 16 bytes."""
+        src = src.contiguous()
+        shape = tuple(src.shape)
+        rows = shape[1] if n_planes > 1 else shape[0]
+        tail = shape[2:] if n_planes > 1 else shape[1:]
+        row_bytes = src.element_size()
+        for d in tail:
+            row_bytes *= int(d)
+        n = int(idx.numel())
+        out = torch.empty(((n_planes, n) if n_planes > 1 else (n,)) + tuple(tail), dtype=src.dtype, device=src.device)
+        if n:
+            _lib.check(self.lib.pgn_gather_ray_rows(self.handle, _ptr(src), _ptr(out), _ptr(idx.contiguous()), n, row_bytes, int(n_planes),
+                                                    rows * row_bytes, n * row_bytes, self._stream()))
+        return out
+
     def frame_to_hmr_input(self, image, crop=(100, 100, 412, 412), out_res=224, mean=(0.485, 0.456, 0.406),
                            std=(0.485, 0.456, 0.406), quantize_u8=True):
         """Rendered frame [H,W,3] in [0,1] (CUDA) -> HMR input [3,out_res,out_res].

@@ -114,3 +114,20 @@ def test_pose_images_backpropagate_to_the_bones(rc):
     x = gan.hmr_input(eng, frames[0], crop=(12, 12, 52, 52), out_res=28)
     (x ** 2).sum().backward()
     assert torch.isfinite(bones.grad).all() and float(bones.grad.abs().max()) > 0
+
+
+@pytest.mark.gpu
+def test_gather_ray_rows_matches_index_select(engine):
+    """pgn_gather_ray_rows (the GAN backward's ray selection) against torch.index_select, single- and multi-plane."""
+    dev = engine.device
+    g = torch.Generator(device="cpu").manual_seed(3)
+    idx = torch.randperm(5000, generator=g)[:1234].to(dev)
+    z = torch.randn((5000, 80), generator=g).to(dev)
+    assert torch.equal(engine.gather_ray_rows(z, idx), z.index_select(0, idx))
+    raw = torch.randn((5000, 80, 4), generator=g).to(dev)
+    assert torch.equal(engine.gather_ray_rows(raw, idx), raw.index_select(0, idx))
+    planes = torch.randint(-2**31, 2**31 - 1, (8, 5000, 640), generator=g, dtype=torch.int32).to(dev)
+    assert torch.equal(engine.gather_ray_rows(planes, idx, n_planes=8), planes.index_select(1, idx))
+    assert engine.gather_ray_rows(z, idx[:0]).shape == (0, 80)
+    with pytest.raises(Exception):
+        engine.gather_ray_rows(torch.zeros((10, 11), device=dev), idx[:3] % 10)          # 44-byte rows: not a multiple of 16
