@@ -41,6 +41,9 @@
 
 using namespace pgn;
 
+// the producer and the issuer are single latency-critical lanes: they spin on test_wait instead of parking in try_wait
+// (wake-up latency of a parked warp; 500 -> 489 us per pass)
+#define PGN_LAT_WAIT mbar_spin_s
 namespace {
 
 constexpr int kRows = 32;                      // rows (K of the GEMM) per stage
@@ -166,12 +169,12 @@ __global__ void __launch_bounds__(kThreads, 1) pgn_wgrad_kernel(const __grid_con
           }
         }
         if (b_tb && sub == 0) {                    // the tile's B operand: 64 contiguous KB, one bulk copy
-          if (!mbar_wait_s(bt_empty0 + bts * 8, bt_ph, status, 804)) break;
+          if (!PGN_LAT_WAIT(bt_empty0 + bts * 8, bt_ph, status, 804)) break;
           mbar_arrive_expect_tx_s(bt_full0 + bts * 8, (uint32_t)kTbTileBytes);
           bulk_g2s_s(bt_s0 + bts * kTbTileBytes, b_tb + (size_t)tile * kTbTileBytes, (uint32_t)kTbTileBytes, bt_full0 + bts * 8);
           if (++bts == kTbTiles) { bts = 0; bt_ph ^= 1; }
         }
-        if (!mbar_wait_s(empty0 + s * 8, ph, status, 801)) break;
+        if (!PGN_LAT_WAIT(empty0 + s * 8, ph, status, 801)) break;
         const uint32_t bar = full0 + s * 8;
         mbar_arrive_expect_tx_s(bar, bytes);
         for (int i = 0; i < a_boxes; ++i) tma_load_3d(a_s0 + s * kOpBytes + i * kBoxBytes, ma, a_col + i * kBoxCols, row, a_layer, bar);
@@ -198,9 +201,9 @@ __global__ void __launch_bounds__(kThreads, 1) pgn_wgrad_kernel(const __grid_con
       for (long long it = 0; it < n_mine; ++it) {
         const int sub = (int)(it & 3);
         if (b_is_tb && sub == 0) {
-          if (!mbar_wait_s(bt_full0 + bts * 8, bt_ph, status, 805)) { ok = false; break; }
+          if (!PGN_LAT_WAIT(bt_full0 + bts * 8, bt_ph, status, 805)) { ok = false; break; }
         }
-        if (!mbar_wait_s(full0 + s * 8, ph, status, 802)) { ok = false; break; }
+        if (!PGN_LAT_WAIT(full0 + s * 8, ph, status, 802)) { ok = false; break; }
         tc_fence_after_sync();
         const uint32_t a0 = a_s0 + s * kOpBytes, b0 = b_s0 + s * kOpBytes;
         const uint32_t bt0 = bt_s0 + bts * kTbTileBytes + sub * (kRows * 16);       // rows [32 sub, 32 sub + 32) of the tile
