@@ -302,9 +302,12 @@ PGN_API int  pgn_framecode_backward(pgn_context* ctx, int32_t net_id, const void
  * grad_input of pts_linears.0 / .5 and views_linears.0, core/networks/nerf.py:94-131 backwards) with the uploaded
  * weights of `net_id`:  g_xp bf16 [m,432] = dZ_5 W_5[:, :432] + dZ_0 W_0,  g_d bf16 [m,648] = dG W_v[:, 256:904];
  * dz bf16 [8][m][256] as written by pgn_mlp_delta_chain (layers 0 and 5 are read), dG bf16 [m,128].  The outputs are
- * the operands of pgn_encode_backward_bf16. */
+ * the operands of pgn_encode_backward_bf16.  tile_blocked != 0: both outputs in 128-row tiles,
+ * [ceil(m / 128)][columns / 8][128][8] (element (r, c) at (r / 128) * 128 * columns + (c / 8) * 1024 + (r % 128) * 8 + c % 8;
+ * the buffers hold whole tiles, rows beyond m are written as zeros) - the form the epilogue stores with full lines
+ * and pgn_encode_backward_bf16 reads back; 0: row-major. */
 PGN_API int  pgn_mlp_input_grads(pgn_context* ctx, int32_t net_id, const void* dz, const void* dG, int64_t m, void* g_xp, void* g_d,
-                                 void* stream);
+                                 int32_t tile_blocked, void* stream);
 
 /* the split-K kernel on one explicit product, for unit tests: out[Ma, Nb] (fp32, row stride ld_out) += A[m, :Ma]^T B[m, :Nb],
  * A / B bf16 row-major with row strides lda / ldb (elements), Ma in {128, 256}, Nb a multiple of 8 <= 256, n_ctas CTAs
@@ -331,9 +334,10 @@ PGN_API int  pgn_encode_backward(pgn_context* ctx, const pgn_render_inputs* in, 
                                  const float* g_enc, float* d_skts, void* stream);
 
 /* the same with dL/d(network input) as the training backward produces it: two bf16 GEMM outputs, g_xp [n * n_z, 432]
- * (channels [0,432): v-embed | r) and g_d [n * n_z, 648] (view embed), no fp32 [.,1080] matrix in between. */
+ * (channels [0,432): v-embed | r) and g_d [n * n_z, 648] (view embed), no fp32 [.,1080] matrix in between;
+ * tile_blocked != 0: in the 128-row tile layout of pgn_mlp_input_grads. */
 PGN_API int  pgn_encode_backward_bf16(pgn_context* ctx, const pgn_render_inputs* in, const float* z, int32_t n_z,
-                                      const void* g_xp, const void* g_d, float* d_skts, void* stream);
+                                      const void* g_xp, const void* g_d, int32_t tile_blocked, float* d_skts, void* stream);
 
 /* backward of NeRF.raw2outputs for the training step (core/trainer.py:321-370 reads rgb_map and acc_map):
  * g_rgb [n,3] = dL/d rgb_map, g_acc [n] = dL/d acc_map (may be NULL) -> d_raw [n,s,4] = dL/d raw.

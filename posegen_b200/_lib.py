@@ -94,7 +94,7 @@ def load() -> C.CDLL:
     lib.pgn_near_far.argtypes = [vp, C.POINTER(RenderInputs), vp, vp]
     lib.pgn_encode.argtypes = [vp, C.POINTER(RenderInputs), vp, i32, vp, vp]
     lib.pgn_mlp.argtypes = [vp, C.c_int, vp, i64, vp, i32, vp]
-    lib.pgn_encode_backward_bf16.argtypes = [vp, C.POINTER(RenderInputs), vp, i32, vp, vp, vp, vp]
+    lib.pgn_encode_backward_bf16.argtypes = [vp, C.POINTER(RenderInputs), vp, i32, vp, vp, i32, vp, vp]
     lib.pgn_encode_bf16.argtypes = [vp, C.POINTER(RenderInputs), vp, i32, vp, vp]
     lib.pgn_mlp_delta.argtypes = [vp, vp, i32, vp, i64, i32, vp, i32, i32, vp, vp, vp, vp]
     lib.pgn_mlp_delta_chain_net.argtypes = [vp, i32, vp, vp, vp, i64, i64, vp, vp, C.c_uint32, vp]
@@ -111,7 +111,7 @@ def load() -> C.CDLL:
     lib.pgn_compose_frame.argtypes = [vp, i32, i32, i32, i32, i32, i32, vp, vp, f32, vp, vp]
     lib.pgn_pose_to_skts.argtypes = [vp, vp, C.POINTER(f32), i32, f32, f32, f32, vp, vp, vp, vp, vp]
     lib.pgn_frame_to_hmr_input.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, i32, C.POINTER(f32), C.POINTER(f32), i32, vp, vp]
-    lib.pgn_mlp_input_grads.argtypes = [vp, i32, vp, vp, i64, vp, vp, vp]
+    lib.pgn_mlp_input_grads.argtypes = [vp, i32, vp, vp, i64, vp, vp, i32, vp]
     lib.pgn_framecode_backward.argtypes = [vp, i32, vp, i64, i32, vp, vp, vp, vp]
     lib.pgn_weight_grad_floats.argtypes = [vp]
     lib.pgn_weight_grad_floats.restype = C.c_size_t

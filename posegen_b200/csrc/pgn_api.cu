@@ -478,11 +478,12 @@ int pgn_mlp_weight_grads(pgn_context* c, int32_t net_id, const void* dz, const v
   return PGN_OK;
 }
 
-int pgn_mlp_input_grads(pgn_context* c, int32_t net_id, const void* dz, const void* dG, int64_t m, void* g_xp, void* g_d, void* stream) {
+int pgn_mlp_input_grads(pgn_context* c, int32_t net_id, const void* dz, const void* dG, int64_t m, void* g_xp, void* g_d,
+                        int32_t tile_blocked, void* stream) {
   if (!c || net_id < 0 || net_id > 1 || !dz || !dG || !g_xp || !g_d || m < 0) return fail(PGN_E_INVALID, "pgn_mlp_input_grads: bad argument");
   if (!c->have_w[net_id]) return fail(PGN_E_STATE, "pgn_mlp_input_grads: weights not uploaded");
   PGN_ON_DEVICE(c);
-  PGN_CUDA(pgn_launch_input_grads(dz, dG, m, c->d_igw[net_id], g_xp, g_d, c->d_status, c->num_sms, (cudaStream_t)stream));
+  PGN_CUDA(pgn_launch_input_grads(dz, dG, m, c->d_igw[net_id], g_xp, g_d, tile_blocked ? 1 : 0, c->d_status, c->num_sms, (cudaStream_t)stream));
   c->launches++;
   return PGN_OK;
 }
@@ -540,14 +541,14 @@ int pgn_encode_backward(pgn_context* c, const pgn_render_inputs* in, const float
 }
 
 int pgn_encode_backward_bf16(pgn_context* c, const pgn_render_inputs* in, const float* z, int32_t n_z, const void* g_xp,
-                             const void* g_d, float* d_skts, void* stream) {
+                             const void* g_d, int32_t tile_blocked, float* d_skts, void* stream) {
   int rc = check_inputs(c, in, "pgn_encode_backward_bf16");
   if (rc) return rc;
   if (!z || !g_xp || !g_d || !d_skts || n_z <= 0) return fail(PGN_E_INVALID, "pgn_encode_backward_bf16: bad argument");
   if (!c->have_sc) return fail(PGN_E_STATE, "pgn_encode_backward_bf16: scalars not set");
   PGN_ON_DEVICE(c);
   PGN_CUDA(pgn_launch_encode_backward_bf16(make_refs(c, in), c->d_sc, z, n_z, reinterpret_cast<const __nv_bfloat16*>(g_xp),
-                                           reinterpret_cast<const __nv_bfloat16*>(g_d), d_skts, (cudaStream_t)stream));
+                                           reinterpret_cast<const __nv_bfloat16*>(g_d), tile_blocked ? 1 : 0, d_skts, (cudaStream_t)stream));
   c->launches++;
   return PGN_OK;
 }

@@ -37,9 +37,10 @@ struct Params {
   CUtensorMap a_dz;      // [8][m][256] bf16 deltas of the trunk (layers 0 and 5 are read)
   CUtensorMap a_dg;      // [1][m][128] bf16 view-layer delta
   CUtensorMap b_w5, b_w0, b_wv;   // bf16 weights [K][N]: W_5[:, :432] (ld 432), W_0 (ld 432), W_v[:, 256:904] (ld 648)
-  __nv_bfloat16* g_xp;   // [m,432]
-  __nv_bfloat16* g_d;    // [m,648]
+  __nv_bfloat16* g_xp;   // [m,432]  (tile_blocked: [ceil(m / 128)][54][128][8])
+  __nv_bfloat16* g_d;    // [m,648]  (tile_blocked: [ceil(m / 128)][81][128][8])
   long long m;
+  int tile_blocked;
 };
 
 struct __align__(1024) Smem {
@@ -171,7 +172,14 @@ __global__ void __launch_bounds__(kThreads, 1) pgn_input_grads_kernel(const __gr
         if (!mbar_wait_s(acc_full0 + buf * 8, acc_ph[buf], status, 906)) return;
         acc_ph[buf] ^= 1;
         tc_fence_after_sync();
-        __nv_bfloat16* orow = (j < 2 ? p.g_xp + grow * 432 : p.g_d + grow * 648) + col0;
+        // row-major: this thread's row; tile-blocked [row / 128][column / 8][128][8]: this row's 16 bytes of the job's first
+        // 8-column chunk (the next chunk is 128 rows x 16 B = 1,024 elements further) - a warp's store is then 512
+        // contiguous bytes instead of 16 bytes in each of 32 rows (32 lines per instruction: the LSU's line throughput
+        // bounded this epilogue, 1.70 ms per 1.3 M rows)
+        __nv_bfloat16* orow = p.tile_blocked
+            ? (j < 2 ? p.g_xp + (size_t)t * (432 * kTile) : p.g_d + (size_t)t * (648 * kTile)) + (size_t)(col0 >> 3) * (kTile * 8) + row * 8
+            : (j < 2 ? p.g_xp + grow * 432 : p.g_d + grow * 648) + col0;
+        const int cstep = p.tile_blocked ? kTile * 8 : 8;      // elements from one 8-column chunk to the next
         const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * 256u;
         uint32_t v[2][16];
         tmem_ld_32x16(taddr, v[0]);
@@ -179,7 +187,7 @@ __global__ void __launch_bounds__(kThreads, 1) pgn_input_grads_kernel(const __gr
           tmem_ld_wait();
           if (c0 + 16 < nmma) tmem_ld_32x16(taddr + (uint32_t)(c0 + 16), v[(b + 1) & 1]);
           const uint32_t* vb = v[b & 1];
-          if (grow < p.m) {
+          if (grow < p.m || p.tile_blocked) {           // (a tile-blocked buffer holds whole tiles: rows beyond m are zeros)
 #pragma unroll
             for (int h = 0; h < 2; ++h)
               if (c0 + 8 * h < nb) {
@@ -188,7 +196,7 @@ __global__ void __launch_bounds__(kThreads, 1) pgn_input_grads_kernel(const __gr
                 o.y = pack_bf16x2(__uint_as_float(vb[8 * h + 2]), __uint_as_float(vb[8 * h + 3]));
                 o.z = pack_bf16x2(__uint_as_float(vb[8 * h + 4]), __uint_as_float(vb[8 * h + 5]));
                 o.w = pack_bf16x2(__uint_as_float(vb[8 * h + 6]), __uint_as_float(vb[8 * h + 7]));
-                *reinterpret_cast<uint4*>(orow + c0 + 8 * h) = o;
+                *reinterpret_cast<uint4*>(orow + (size_t)((c0 >> 3) + h) * cstep) = o;
               }
           }
         }
@@ -231,7 +239,7 @@ cudaError_t pgn_launch_pack_input_grad_weights(const float* w5, const float* w0,
   return cudaGetLastError();
 }
 
-cudaError_t pgn_launch_input_grads(const void* dz, const void* dG, long long m, const __nv_bfloat16* wpack, void* g_xp, void* g_d,
+cudaError_t pgn_launch_input_grads(const void* dz, const void* dG, long long m, const __nv_bfloat16* wpack, void* g_xp, void* g_d, int tile_blocked,
                                    int* status, int num_sms, cudaStream_t stream) {
   if (m == 0) return cudaSuccess;
   Params p;
@@ -244,6 +252,7 @@ cudaError_t pgn_launch_input_grads(const void* dz, const void* dG, long long m, 
   p.g_xp = reinterpret_cast<__nv_bfloat16*>(g_xp);
   p.g_d = reinterpret_cast<__nv_bfloat16*>(g_d);
   p.m = m;
+  p.tile_blocked = tile_blocked;
   const size_t smem = sizeof(Smem) + 1024;
   static PgnPerDeviceOnce configured;
   if (configured.need()) {

@@ -102,7 +102,7 @@ cudaError_t pgn_launch_composite_backward(const PgnRayRefs& rays, const PgnScala
 cudaError_t pgn_launch_encode_backward(const PgnRayRefs& rays, const PgnScalars* sc_dev, const float* z, int n_z,
                                        const float* g_enc, float* d_skts, cudaStream_t stream);
 cudaError_t pgn_launch_encode_backward_bf16(const PgnRayRefs& rays, const PgnScalars* sc_dev, const float* z, int n_z,
-                                            const __nv_bfloat16* g_xp, const __nv_bfloat16* g_d, float* d_skts, cudaStream_t stream);
+                                            const __nv_bfloat16* g_xp, const __nv_bfloat16* g_d, int tile_blocked, float* d_skts, cudaStream_t stream);
 cudaError_t pgn_launch_encode_bf16(const PgnRayRefs& rays, const PgnScalars* sc_dev, const float* z, int n_z,
                                    __nv_bfloat16* enc, cudaStream_t stream);
 cudaError_t pgn_launch_mlp_delta(void* dh, int has_in, const void* act, long long m, int C, const float* rs, int rs_stride,
@@ -146,7 +146,7 @@ cudaError_t pgn_launch_wgrad_single(const void* A, int lda, int Ma, const void* 
 size_t pgn_input_grad_weight_elems();
 cudaError_t pgn_launch_pack_input_grad_weights(const float* w5, const float* w0, const float* wv, int view_ld, __nv_bfloat16* out,
                                                cudaStream_t stream);
-cudaError_t pgn_launch_input_grads(const void* dz, const void* dG, long long m, const __nv_bfloat16* wpack, void* g_xp, void* g_d,
+cudaError_t pgn_launch_input_grads(const void* dz, const void* dG, long long m, const __nv_bfloat16* wpack, void* g_xp, void* g_d, int tile_blocked,
                                    int* status, int num_sms, cudaStream_t stream);
 
 cudaError_t pgn_launch_gather_params(const float* const* src_w, const float* const* src_b, float* const* dst_w, float* const* dst_b,

@@ -547,7 +547,10 @@ __device__ __forceinline__ float pgn_ldg_f(const __nv_bfloat16* p) {
 
 // G = float: one [rows,1080] matrix (g_xp = g_enc, g_d = g_enc + 432, both row strides 1080);
 // G = __nv_bfloat16: the two GEMM outputs of the training backward as they are, [rows,432] and [rows,648].
-template <typename G>
+// kTB (bf16 only): both matrices tile-blocked, [row / 128][column / 8][128][8] - the layout pgn_mlp_input_grads' epilogue
+// writes with fully coalesced stores; element (row, col) sits at (row / 128) * 128 * stride + (col / 8) * 1024 +
+// (row % 128) * 8 + col % 8.
+template <typename G, bool kTB = false>
 __global__ void pgn_encode_backward_kernel(PgnRayRefs rays, const PgnScalars* __restrict__ scp, const float* __restrict__ z,
                                            int n_z, const G* __restrict__ g_xp, int stride_xp, const G* __restrict__ g_d,
                                            int stride_d, float* __restrict__ d_skts) {
@@ -594,16 +597,19 @@ __global__ void pgn_encode_backward_kernel(PgnRayRefs rays, const PgnScalars* __
       const float w = pgn_window<false>(v, sc.tau_v, sc.cutoff_v[j]);
       const float wd = pgn_window<false>(v, sc.tau_d, sc.cutoff_d[j]);
       const float dw = -sc.tau_v * w * (1.0f - w), dwd = -sc.tau_d * wd * (1.0f - wd);
-      const G* ge = g_xp + rs * stride_xp;
+      // row bases and the element offset of column c inside a row
+      const G* ge = kTB ? g_xp + (rs >> 7) * (128ll * stride_xp) + (rs & 127) * 8 : g_xp + rs * stride_xp;
+      const G* gdr = kTB ? g_d + (rs >> 7) * (128ll * stride_d) + (rs & 127) * 8 : g_d + rs * stride_d;
+      auto co = [](int c) -> int { return kTB ? ((c >> 3) << 10) + (c & 7) : c; };
       // v-embed: k = 0 -> v, k = 1 + 2f -> sin(2^f v), 2 + 2f -> cos(2^f v)
-      float gv = pgn_ldg_f(ge + j) * (w + v * dw);
+      float gv = pgn_ldg_f(ge + co(j)) * (w + v * dw);
       float sn, cs;
       sincosf(v, &sn, &cs);
 #pragma unroll
       for (int f = 0; f < PGN_LV; ++f) {
         const float fr = (float)(1 << f);
-        gv += pgn_ldg_f(ge + (1 + 2 * f) * PGN_J + j) * (fr * cs * w + sn * dw);
-        gv += pgn_ldg_f(ge + (2 + 2 * f) * PGN_J + j) * (-fr * sn * w + cs * dw);
+        gv += pgn_ldg_f(ge + co((1 + 2 * f) * PGN_J + j)) * (fr * cs * w + sn * dw);
+        gv += pgn_ldg_f(ge + co((2 + 2 * f) * PGN_J + j)) * (-fr * sn * w + cs * dw);
         const float t2 = cs + cs;                 // double angle
         sn = t2 * sn;
         cs = fmaf(t2, cs, -1.0f);
@@ -611,20 +617,20 @@ __global__ void pgn_encode_backward_kernel(PgnRayRefs rays, const PgnScalars* __
       // view embed: every channel is psi(u_a) * wd(v)
 #pragma unroll
       for (int a = 0; a < 3; ++a) {
-        const G* gq = g_d + rs * stride_d + j * 3 + a;
-        const float g0 = pgn_ldg_f(gq);
+        const int cq = j * 3 + a;
+        const float g0 = pgn_ldg_f(gdr + co(cq));
         gv += g0 * u[a] * dwd;
         gu[a] += g0 * wd;
 #pragma unroll
         for (int f = 0; f < PGN_LD; ++f) {
           const float fr = (float)(1 << f);
-          const float g1 = pgn_ldg_f(gq + (1 + 2 * f) * 72), g2 = pgn_ldg_f(gq + (2 + 2 * f) * 72);
+          const float g1 = pgn_ldg_f(gdr + co(cq + (1 + 2 * f) * 72)), g2 = pgn_ldg_f(gdr + co(cq + (2 + 2 * f) * 72));
           gv += (g1 * usn[a][f] + g2 * ucs[a][f]) * dwd;
           gu[a] += (g1 * ucs[a][f] - g2 * usn[a][f]) * fr * wd;
         }
       }
       // r = pts_t / v
-      const float gr[3] = {pgn_ldg_f(ge + 360 + j * 3), pgn_ldg_f(ge + 360 + j * 3 + 1), pgn_ldg_f(ge + 360 + j * 3 + 2)};
+      const float gr[3] = {pgn_ldg_f(ge + co(360 + j * 3)), pgn_ldg_f(ge + co(360 + j * 3 + 1)), pgn_ldg_f(ge + co(360 + j * 3 + 2))};
       float gp[3];
       if (v > 1e-12f) {
         const float rg = r[0] * gr[0] + r[1] * gr[1] + r[2] * gr[2];
@@ -674,12 +680,17 @@ cudaError_t pgn_launch_encode_backward(const PgnRayRefs& rays, const PgnScalars*
 }
 
 cudaError_t pgn_launch_encode_backward_bf16(const PgnRayRefs& rays, const PgnScalars* sc_dev, const float* z, int n_z,
-                                            const __nv_bfloat16* g_xp, const __nv_bfloat16* g_d, float* d_skts, cudaStream_t stream) {
+                                            const __nv_bfloat16* g_xp, const __nv_bfloat16* g_d, int tile_blocked, float* d_skts,
+                                            cudaStream_t stream) {
   const long long total = rays.n_rays * PGN_J;
   if (total == 0) return cudaSuccess;
   const int block = 96;
   const long long grid = min((total + block - 1) / block, (long long)148 * 32);
-  pgn_encode_backward_kernel<__nv_bfloat16><<<(unsigned)grid, block, 0, stream>>>(rays, sc_dev, z, n_z, g_xp, PGN_ENC_P, g_d,
-                                                                                  PGN_ENC - PGN_ENC_P, d_skts);
+  if (tile_blocked)
+    pgn_encode_backward_kernel<__nv_bfloat16, true><<<(unsigned)grid, block, 0, stream>>>(rays, sc_dev, z, n_z, g_xp, PGN_ENC_P, g_d,
+                                                                                          PGN_ENC - PGN_ENC_P, d_skts);
+  else
+    pgn_encode_backward_kernel<__nv_bfloat16><<<(unsigned)grid, block, 0, stream>>>(rays, sc_dev, z, n_z, g_xp, PGN_ENC_P, g_d,
+                                                                                    PGN_ENC - PGN_ENC_P, d_skts);
   return cudaGetLastError();
 }

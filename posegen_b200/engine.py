@@ -434,17 +434,26 @@ class Engine:
             o += sh[0] * sh[1]
         return out, fb
 
-    def mlp_input_grads(self, net_id, dz, dG):
+    def mlp_input_grads(self, net_id, dz, dG, tile_blocked=False):
         """pgn_mlp_input_grads: (g_xp bf16 [m,432], g_d bf16 [m,648]) = dL/d(network input) from dz bf16 [8,m,256] (layers 0
-        and 5) and dG bf16 [m,128], with the uploaded weights of net `net_id` - tcgen05, no library GEMM."""
+        and 5) and dG bf16 [m,128], with the uploaded weights of net `net_id` - tcgen05, no library GEMM.
+        tile_blocked: the outputs are flat buffers of whole 128-row tiles, [ceil(m/128)][cols/8][128][8] (the operand form
+        of `encode_backward_bf16(..., tile_blocked=True)`; `from_tile_blocked` turns one back into [m, cols])."""
         m = dG.shape[0]
         for t, shape in ((dz, (8, m, 256)), (dG, (m, 128))):
             if tuple(t.shape) != shape or t.dtype != torch.bfloat16 or not t.is_contiguous() or not t.is_cuda:
                 raise ValueError(f"mlp_input_grads: expected a contiguous CUDA bf16 tensor of shape {shape}, got {tuple(t.shape)} {t.dtype}")
-        g_xp = torch.empty((m, 432), dtype=torch.bfloat16, device=dG.device)
-        g_d = torch.empty((m, 648), dtype=torch.bfloat16, device=dG.device)
-        _lib.check(self.lib.pgn_mlp_input_grads(self.handle, int(net_id), _ptr(dz), _ptr(dG), m, _ptr(g_xp), _ptr(g_d), self._stream()))
+        rows = (m + 127) // 128 * 128 if tile_blocked else m
+        g_xp = torch.empty((rows * 432,) if tile_blocked else (m, 432), dtype=torch.bfloat16, device=dG.device)
+        g_d = torch.empty((rows * 648,) if tile_blocked else (m, 648), dtype=torch.bfloat16, device=dG.device)
+        _lib.check(self.lib.pgn_mlp_input_grads(self.handle, int(net_id), _ptr(dz), _ptr(dG), m, _ptr(g_xp), _ptr(g_d),
+                                                1 if tile_blocked else 0, self._stream()))
         return g_xp, g_d
+
+    @staticmethod
+    def from_tile_blocked(buf, m, cols):
+        """[m, cols] view-copy of a tile-blocked buffer [tiles][cols/8][128][8]."""
+        return buf.view(-1, cols // 8, 128, 8).permute(0, 2, 1, 3).reshape(-1, cols)[:m]
 
     def framecode_backward(self, net_id, dG, n_rays, n_z, cams, g_view_weight):
         """pgn_framecode_backward: adds dGr^T code[cam] into columns 904..919 of g_view_weight [128,920] (in place) and
@@ -506,17 +515,19 @@ class Engine:
                                                 self._stream()))
         return d
 
-    def encode_backward_bf16(self, ray_batch, skts, cyls, z, g_xp, g_d):
-        """dL/d skts [n,24,4,4] (per ray) given dL/d(network input) as two bf16 matrices [n * n_z, 432] and [n * n_z, 648]."""
+    def encode_backward_bf16(self, ray_batch, skts, cyls, z, g_xp, g_d, tile_blocked=False):
+        """dL/d skts [n,24,4,4] (per ray) given dL/d(network input) as two bf16 matrices [n * n_z, 432] and [n * n_z, 648]
+        (tile_blocked: the flat whole-tile buffers `mlp_input_grads(..., tile_blocked=True)` returns)."""
         inp, keep = self._inputs(ray_batch, skts, cyls)
         z = z.contiguous()
         rows = inp.n_rays * z.shape[1]
         for t, cols in ((g_xp, 432), (g_d, 648)):
-            if t.dtype != torch.bfloat16 or not t.is_contiguous() or tuple(t.shape) != (rows, cols):
-                raise ValueError(f"expected a contiguous bf16 [{rows},{cols}] matrix, got {tuple(t.shape)} {t.dtype}")
+            want = ((rows + 127) // 128 * 128 * cols,) if tile_blocked else (rows, cols)
+            if t.dtype != torch.bfloat16 or not t.is_contiguous() or tuple(t.shape) != want:
+                raise ValueError(f"expected a contiguous bf16 {want} tensor, got {tuple(t.shape)} {t.dtype}")
         d = torch.empty((inp.n_rays, 24, 4, 4), dtype=torch.float32, device=z.device)
-        _lib.check(self.lib.pgn_encode_backward_bf16(self.handle, C.byref(inp), _ptr(z), z.shape[1], _ptr(g_xp), _ptr(g_d), _ptr(d),
-                                                     self._stream()))
+        _lib.check(self.lib.pgn_encode_backward_bf16(self.handle, C.byref(inp), _ptr(z), z.shape[1], _ptr(g_xp), _ptr(g_d),
+                                                     1 if tile_blocked else 0, _ptr(d), self._stream()))
         return d
 
     def sample_pdf(self, z, weights):

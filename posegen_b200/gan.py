@@ -71,7 +71,7 @@ class _FrameRenderFn(torch.autograd.Function):
             gd = mlp_backward(pd, None, None, d_raw.reshape(-1, 4), eng.mlp_delta, want_input_grad=True, want_weight_grad=False,
                               chain=functools.partial(eng.mlp_delta_chain_net, 1), mask_dump=mask_dump, view_delta=eng.view_delta_from_mask,
                               input_grads=functools.partial(eng.mlp_input_grads, 1))
-            d = eng.encode_backward_bf16(rb, sk, cy, z, gd["_g_xp"], gd["_g_d"])
+            d = eng.encode_backward_bf16(rb, sk, cy, z, gd["_g_xp"], gd["_g_d"], tile_blocked=gd.get("_g_tb", False))
             d_skts += d.sum(0)
             del gd, d, mask_dump
         return None, None, d_skts, None, None

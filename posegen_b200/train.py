@@ -32,6 +32,7 @@ S, T = 64, 80
 USE_DELTA_CHAIN = True        # trunk backward through pgn_mlp_delta_chain (False: layer by layer, for A/B runs)
 USE_WGRAD_KERNEL = True       # weight gradients through pgn_mlp_weight_grads (False: torch.mm, for A/B runs)
 USE_INPUT_GRAD_KERNEL = True  # dL/d(network input) through pgn_mlp_input_grads (False: torch.mm, for A/B runs)
+INPUT_GRADS_TILE_BLOCKED = True   # ... handed to pgn_encode_backward_bf16 in 128-row tiles (coalesced epilogue stores)
 PARAM_ORDER = [f"pts_linears.{i}.{k}" for i in range(8) for k in ("weight", "bias")] + \
     [f"{m}.{k}" for m in ("alpha_linear", "feature_linear", "views_linears.0", "rgb_linear") for k in ("weight", "bias")]
 
@@ -113,7 +114,8 @@ def mlp_backward(params: Dict[str, torch.Tensor], enc: torch.Tensor, acts: torch
     replaces `acts` for a frozen network (want_weight_grad False, `chain` required): the masks-only dump of
     `pgn_render_forward_masks` is all the input-gradient chain reads.
     Returns {name: fp32 gradient}; with want_input_grad also dL/d(network input) as "_g_xp" [m,432] (v-embed | r
-    channels) and "_g_d" [m,648] (view embed), bf16 (the operands of `pgn_encode_backward_bf16`)."""
+    channels) and "_g_d" [m,648] (view embed), bf16 (the operands of `pgn_encode_backward_bf16`; with "_g_tb" set they are
+    the flat 128-row-tile buffers of `Engine.mlp_input_grads(..., tile_blocked=True)`)."""
     m = d_raw.shape[0]
     bf = torch.bfloat16
     if want_weight_grad:
@@ -180,7 +182,8 @@ def mlp_backward(params: Dict[str, torch.Tensor], enc: torch.Tensor, acts: torch
                     g[f"pts_linears.{l}.weight"] = _mm32(dZt, H[l - 1])
                 g[f"pts_linears.{l}.bias"] = colsum[l]
         if fused_in:
-            g["_g_xp"], g["_g_d"] = input_grads(dz, dG)
+            g["_g_xp"], g["_g_d"] = input_grads(dz, dG, tile_blocked=INPUT_GRADS_TILE_BLOCKED)
+            g["_g_tb"] = INPUT_GRADS_TILE_BLOCKED
         elif want_input_grad:
             g["_g_xp"] = torch.mm(dz[5], W["pts_linears.5.weight"][:, :432]).addmm_(dz[0], W["pts_linears.0.weight"])
         return g
@@ -289,7 +292,7 @@ class _RenderTrainFn(torch.autograd.Function):
                         o += t.numel()
             grads += [gd[k].reshape(pd[k].shape).to(pd[k].dtype) for k in order] if want_w else [None] * len(order)
             if want_sk:          # pose gradient: dL/d(network input) -> dL/d skts (per ray), both passes add up
-                d = eng.encode_backward_bf16(rb, sk, cy, z, gd["_g_xp"], gd["_g_d"])
+                d = eng.encode_backward_bf16(rb, sk, cy, z, gd["_g_xp"], gd["_g_d"], tile_blocked=gd.get("_g_tb", False))
                 d_skts = d if d_skts is None else d_skts + d
         ctx.acts = None
         if want_sk and d_skts is not None and sk.dim() == 3:

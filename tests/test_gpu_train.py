@@ -479,6 +479,15 @@ def test_input_grad_kernel_matches_matrix_products(engine, m):
         assert got.shape == want.shape
         err = float((got.double() - want).abs().max())
         assert err <= 8e-3 * max(1.0, float(want.abs().max())), err               # one bf16 rounding of the result
+    # the tile-blocked form (what the training / GAN backward hands to pgn_encode_backward_bf16): the same numbers in
+    # [ceil(m/128)][cols/8][128][8], rows beyond m zero
+    t_xp, t_d = engine.mlp_input_grads(1, dz, dG, tile_blocked=True)
+    torch.cuda.synchronize()
+    engine.check_status()
+    for tb, rm, cols in ((t_xp, g_xp, 432), (t_d, g_d, 648)):
+        full = engine.from_tile_blocked(tb, tb.numel() // cols, cols)
+        assert torch.equal(full[:m], rm)
+        assert float(full[m:].abs().max()) == 0.0 if full.shape[0] > m else True
 
 
 def test_training_gradients_share_one_arena(engine, train_case):
