@@ -272,13 +272,14 @@ def test_forward_dump_masks_match_the_activations(engine, train_case):
 
 
 def test_delta_chain_kernel_matches_layerwise_reference(engine):
-    """pgn_mlp_delta_chain (eight tcgen05 layers per 256-row block, masks from bits, bias column sums) against the same
-    chain in torch with bf16 rounding at the same places (fp32 accumulation, bf16 deltas), ragged row counts."""
+    """pgn_mlp_delta_chain (eight tcgen05 layers per 512-row block of a CTA pair, masks from bits, TMA-stored deltas, bias
+    column sums) against the same chain in torch with bf16 rounding at the same places (fp32 accumulation, bf16 deltas);
+    ragged row counts, incl. blocks whose second tile / peer CTA holds no valid row."""
     from posegen_b200.train import chain_wstream
     dev = torch.device("cuda")
     g = torch.Generator(device="cuda").manual_seed(3)
     P = {k: torch.as_tensor(v, device=dev) for k, v in syn.synthetic_nerf_state(7).items()}
-    for m in (256, 1000, 37 * 1024 + 5):
+    for m in (100, 256, 1000, 37 * 1024 + 5):
         rows = ((m + 1279) // 1280) * 1280
         dG = (torch.randn((m, 128), device=dev, generator=g) * 0.1).to(torch.bfloat16)
         d_raw = torch.randn((m, 4), device=dev, generator=g) * 0.1
