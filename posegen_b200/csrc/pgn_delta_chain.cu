@@ -25,14 +25,16 @@
 //
 // Roles per CTA (768 threads, 1 CTA per SM, persistent over 512-row blocks): warp 0 lane 0 streams this CTA's N half
 // of the weights of all eight layers in consumption order with cp.async.bulk (UMMA K-major SWIZZLE_NONE, [2][128][8] bf16
-// per K = 16 step); warp 1 lane 0 issues the MMAs (leader CTA) or relays "my half has landed" to the
-// leader's barrier (peer CTA); warps 4-19 drain the two accumulators (8 warps each; tcgen05.ld 32x32b), add the sigma
-// head's outer product on the first layer, mask, pack to bf16 and store the next layer's A operand into shared memory
-// ([k/8][row][8]); warps 20-23 then read that tile back from shared memory - while the tensor core already runs the
-// next layer on it - and write the dZ rows to HBM (4 rows x 128 B per warp store: full lines) and accumulate the bias
-// gradients (column sums; every column has one owner thread, no atomics).  Draining and storing from the
-// accumulator-owning threads directly costs 2x: a thread owns one row, so each of its stores touches 32 different
-// lines and the column sums need 128 shuffles.
+// per K = 16 step); warp 1 issues the MMAs (leader CTA, whole warp convergent, one elected lane per instruction) or
+// relays "my half has landed" to the leader's barrier (peer CTA); warps 4-19 drain the two accumulators (8 warps each;
+// tcgen05.ld 32x32b), add the sigma head's outer product on the first layer, mask, pack to bf16 and store the next
+// layer's A operand into shared memory: K-major SWIZZLE_128B, 4 panels of 64 columns x 128 rows x 128 B - the image a
+// TMA box has in shared memory; warps 20-23 then - while the tensor core already runs the next layer on that tile -
+// hand it to the TMA engine (one lane: four cp.async.bulk.tensor stores, whole 128-byte lines of the row-major dz,
+// rows beyond m clipped by the tensor map) and read it back for the bias gradients (column sums; every column has one
+// owner thread, no atomics).  Storing from the accumulator-owning threads directly costs 2x (a thread owns one row: each
+// of its stores touches 32 different lines, and the column sums need 128 shuffles); st.global from the four store warps
+// took 2x the tensor time per tile.
 #include "pgn_common.cuh"
 #include "pgn_kernels.h"
 #include "pgn_umma.cuh"
