@@ -182,8 +182,9 @@ PGN_API int  pgn_render_forward(pgn_context* ctx, const pgn_render_inputs* in,
  * each TILE-BLOCKED as [rows / 128][256 / 8][128][8] (element (r, c) of a layer at bf16 index
  * ((r / 128) * 32 + c / 8) * 1024 + (r % 128) * 8 + c % 8: the UMMA operand image of a 128-row tile, so that the
  * forward's stores are fully coalesced and the weight-gradient kernel loads a tile with one 64 KB bulk copy); then
- * layer 8 (views_linears.0) row-major [rows,128]; then the ReLU masks of layers 0-7 as bits ([layer][row][256 bits],
- * bit c = [activation c > 0]); rows are samples in (ray, sample) order, padded to
+ * layer 8 (views_linears.0) row-major [rows,128]; then the ReLU masks of layers 0-7 as bits in WORD PLANES,
+ * uint32 [layer][word 0..7][rows]: bit b of word w of row r = [activation 32 w + b of row r > 0] (a warp of the forward
+ * writes one 128-byte line per word; the delta chain reads four words per thread); rows are samples in (ray, sample) order, padded to
  * rows = pgn_activation_dump_bytes(n, pass) / 4608 (a multiple of 128).  act_coarse / act_fine: device buffers of
  * pgn_activation_dump_bytes(n_rays, 0 / 1) bytes; one of them may be NULL (that pass is not dumped: a loss that reads
  * only the fine outputs sends no gradient into the coarse network).  Request out->raw0 / raw / z_fine / near_far for the backward.
@@ -203,13 +204,13 @@ PGN_API int  pgn_render_forward_train(pgn_context* ctx, const pgn_render_inputs*
 /* The same forward for a FROZEN network whose pose gradient is wanted (GAN step, run_gan.py:159-160): only the ReLU
  * masks of the fine pass are kept - 272 B per sample instead of 4,608 B - which is all the input-gradient backward
  * needs (pgn_view_delta_from_mask, pgn_mlp_delta_chain).  masks_fine: device buffer of pgn_mask_dump_bytes(n_rays)
- * bytes laid out [layer 0..7][rows][256 bits] then [rows][128 bits] (views_linears.0), rows = bytes / 272, samples in
- * (ray, sample) order.  Sampling is the deterministic eval sampling; request out->raw / z_fine for the backward. */
+ * bytes laid out as word planes: uint32 [layer 0..7][word 0..7][rows] (bit b of word w = [activation 32 w + b > 0]), then
+ * uint32 [word 0..3][rows] for views_linears.0; rows = bytes / 272, samples in (ray, sample) order.  Sampling is the deterministic eval sampling; request out->raw / z_fine for the backward. */
 PGN_API size_t pgn_mask_dump_bytes(int64_t n_rays);
 PGN_API int  pgn_render_forward_masks(pgn_context* ctx, const pgn_render_inputs* in, const pgn_render_outputs* out,
                                       void* masks_fine, void* workspace, size_t workspace_bytes, void* stream);
 
-/* dG [m,128] (bf16) = [g > 0] * (d_rgb W_rgb): the view layer's delta from its mask bits (vmask: [m][128 bits]),
+/* dG [m,128] (bf16) = [g > 0] * (d_rgb W_rgb): the view layer's delta from its mask bits (vmask: word planes uint32 [4][m]),
  * d_raw fp32 [m,4] (columns 0-2 = d_rgb), w_rgb fp32 [3,128] (rgb_linear.weight; core/networks/nerf.py:129-131). */
 PGN_API int  pgn_view_delta_from_mask(pgn_context* ctx, void* dG, const float* d_raw, const float* w_rgb, const void* vmask,
                                       int64_t m, void* stream);
@@ -259,7 +260,8 @@ PGN_API int  pgn_mlp_delta(pgn_context* ctx, void* dh, int32_t has_input, const 
  *   dL/dh7 = dG W_fold + d_sigma w_alpha;  dZ_l = [h_l > 0] * dL/dh_l;  dL/dh_{l-1} = dZ_l W_l   (l = 7..1)
  * dG: bf16 [m,128] = dL/d(pre-activation of views_linears.0) (from pgn_mlp_delta); d_raw: fp32 [m,4] (column 3 =
  * d_sigma); mask: the ReLU-mask area of the activation dump of pgn_render_forward_train (starts
- * rows * 4352 bytes into the pass's buffer, rows = mask_rows = pgn_activation_dump_bytes / 4608); w_alpha fp32 [256].
+ * rows * 4352 bytes into the pass's buffer, rows = mask_rows = pgn_activation_dump_bytes / 4608), i.e. word planes
+ * uint32 [8 layers][8 words][mask_rows]; w_alpha fp32 [256].
  * wstream: the eight weights W'_j [256, K_j] bf16 (W'_0 = (W_v[:, :256] W_f)^T with K = 128; W'_j = W_l^T for
  * l = 8 - j, K = 256, the skip layer l = 5 without its 432 input columns), each cut into fills of two K = 16 steps laid
  * out [K/32][2 N halves][2 K-steps][2][128][8] (UMMA K-major core matrices; one N half per CTA of the pair that works

@@ -148,7 +148,7 @@ __device__ __forceinline__ bool chain_issue_layer(uint32_t w_full0, uint32_t w_e
 #define CHAIN_WAIT(bar, parity, code) do { if (!mbar_wait((bar), (parity), status, (code))) goto tail; } while (0)
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-pgn_delta_chain_kernel(const uint4* __restrict__ dG, const float* __restrict__ d_raw, const uint4* __restrict__ mask,
+pgn_delta_chain_kernel(const uint4* __restrict__ dG, const float* __restrict__ d_raw, const uint32_t* __restrict__ mask,
                        long long mask_rows, long long m, const uint8_t* __restrict__ wstream,
                        const float* __restrict__ w_alpha, const __grid_constant__ CUtensorMap dz_map, float* __restrict__ colsum_g,
                        int* __restrict__ status_g, unsigned layer_mask) {
@@ -328,7 +328,12 @@ pgn_delta_chain_kernel(const uint4* __restrict__ dG, const float* __restrict__ d
       const float dsig = gr < m ? __ldg(d_raw + (size_t)gr * 4 + 3) : 0.f;
       for (int j = 0; j < kLayers; ++j, ++acc_phase) {
         const int L = 7 - j;                        // this layer's output is dL/dh_L; its mask is [h_L > 0]
-        const uint4 mk = gr < m ? __ldg(mask + ((size_t)L * mask_rows + gr) * 2 + half) : make_uint4(0u, 0u, 0u, 0u);
+        uint32_t mw[4] = {0u, 0u, 0u, 0u};           // word planes [layer][word][row]: this thread's 128 columns are words 4 half .. + 3
+        if (gr < m) {
+          const uint32_t* mp = mask + (size_t)(L * 8 + half * 4) * (size_t)mask_rows + (size_t)gr;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) mw[i] = __ldg(mp + (size_t)i * (size_t)mask_rows);
+        }
         { CP_T0(); CHAIN_WAIT(&sm.acc_full[t], acc_phase & 1, 704); CP_ADD(4); }
         tc_fence_after_sync();
         if (j > 0) {                                 // the previous deltas have been stored / summed out of the A tile
@@ -338,7 +343,6 @@ pgn_delta_chain_kernel(const uint4* __restrict__ dG, const float* __restrict__ d
           ++csd_phase;
         }
         CP_T0();
-        const uint32_t mw[4] = {mk.x, mk.y, mk.z, mk.w};
         uint32_t v[2][16];
         tmem_ld_32x16(taddr, v[0]);
 #pragma unroll
@@ -436,7 +440,7 @@ cudaError_t pgn_launch_delta_chain(const void* dG, const float* d_raw, const voi
   e = pgn_make_map_bf16(&dz_map, dz, 256, 256, m, kLayers, m * 256, kTile);
   if (e != cudaSuccess) return e;
   pgn_delta_chain_kernel<<<grid, kThreads, smem, stream>>>(reinterpret_cast<const uint4*>(dG), d_raw,
-                                                           reinterpret_cast<const uint4*>(mask), mask_rows, m,
+                                                           reinterpret_cast<const uint32_t*>(mask), mask_rows, m,
                                                            reinterpret_cast<const uint8_t*>(wstream), w_alpha,
                                                            dz_map, colsum, status, layer_mask);
   return cudaGetLastError();

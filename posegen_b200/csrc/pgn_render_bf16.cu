@@ -272,7 +272,8 @@ __device__ __forceinline__ void stg128(void* p, uint32_t a, uint32_t b, uint32_t
 template <int MODE>
 __device__ __forceinline__ void epilogue(Smem& sm, uint32_t tmem_acc, uint32_t act_saddr, int slot, const float* __restrict__ w_alpha,
                                          const float* __restrict__ w_rgb, int warp, int lane, float& sig_keep,
-                                         uint4* dump = nullptr, uint4* dump_mask = nullptr, uint2* dump_vmask = nullptr,
+                                         uint4* dump = nullptr, uint32_t* dump_mask = nullptr, uint32_t* dump_vmask = nullptr,
+                                         size_t mask_stride = 0,
                                          const float* __restrict__ fc = nullptr) {
   // fc (view layer only): this row's frame-code term [128] (Optcodes: W_v[:, 904:920] code[cam], fp32), added to the
   // pre-activation before the ReLU; nullptr when the model has no frame codes
@@ -355,7 +356,9 @@ __device__ __forceinline__ void epilogue(Smem& sm, uint32_t tmem_acc, uint32_t a
         uint32_t mb = 0;
 #pragma unroll
         for (int i = 15; i >= 0; --i) mb = __funnelshift_l(vb[i], mb, 1);
-        if (b & 1) reinterpret_cast<uint32_t*>(dump_mask)[b >> 1] = mask_w | ((~mb & 0xffffu) << 16);
+        // word planes ([layer][word][row], include/posegen_b200.h): the 32 lanes of a warp (32 consecutive rows) write one
+        // 128-byte line per word instead of 4 bytes in each of 32 sectors
+        if (b & 1) dump_mask[(size_t)(b >> 1) * mask_stride] = mask_w | ((~mb & 0xffffu) << 16);
         else mask_w = ~mb & 0xffffu;
       }
 #endif
@@ -370,7 +373,7 @@ __device__ __forceinline__ void epilogue(Smem& sm, uint32_t tmem_acc, uint32_t a
       uint32_t mb = 0;
 #pragma unroll
       for (int i = 15; i >= 0; --i) mb = __funnelshift_l(vb[i], mb, 1);
-      if (b & 1) reinterpret_cast<uint32_t*>(dump_vmask)[b >> 1] = mask_w | ((~mb & 0xffffu) << 16);
+      if (b & 1) dump_vmask[(size_t)(b >> 1) * mask_stride] = mask_w | ((~mb & 0xffffu) << 16);
       else mask_w = ~mb & 0xffffu;
     }
   }
@@ -818,16 +821,19 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
       ++accs;
       tc_fence_after_sync();
       uint4* dptr = nullptr;
-      uint4* mptr = nullptr;
-      uint2* vptr = nullptr;
+      uint32_t* mptr = nullptr;          // mask words of this thread's (row, column half): word planes [layer][word 0..7][row]
+      uint32_t* vptr = nullptr;          // view layer: [word 0..3][row]
+      size_t mstride = 0;
       if (kDump == 2 && tc.pass == 1) {
-        // masks only (frozen network, pose gradient): trunk masks [layer 0..7][row][half] x 128 bits of the fine pass,
-        // then the view layer's [row][half] x 64 bits
+        // masks only (frozen network, pose gradient): trunk masks of the fine pass as word planes [layer 0..7][word 0..7][row]
+        // (word w = [column 32 w + bit > 0]), then the view layer's [word 0..3][row]
         const long long m = dump.rows_f;
         const long long grow = tc.unit * (long long)(kG * tc.S) + tc.row0 + ((gwarp & 3) * 32 + lane);
         uint4* base = reinterpret_cast<uint4*>(dump.f);
-        if (L < 8) mptr = base + ((size_t)L * (size_t)m + (size_t)grow) * 2 + (gwarp >> 2);
-        else vptr = reinterpret_cast<uint2*>(base + (size_t)16 * (size_t)m) + (size_t)grow * 2 + (gwarp >> 2);
+        uint32_t* words = reinterpret_cast<uint32_t*>(base);
+        mstride = (size_t)m;
+        if (L < 8) mptr = words + (size_t)(L * 8 + (gwarp >> 2) * 4) * (size_t)m + (size_t)grow;
+        else vptr = words + (size_t)(64 + (gwarp >> 2) * 2) * (size_t)m + (size_t)grow;
       }
       // (groups of 4: the third fine tile holds 64 rows of the group; its upper half would land in the next group's rows)
       if (kDump == 1 && (tc.pass == 0 ? dump.c : dump.f) != nullptr && tc.row0 + ((gwarp & 3) * 32 + lane) < kG * tc.S) {   // a pass without a buffer is not dumped
@@ -841,13 +847,14 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
         dptr = L == 8 ? base + (size_t)8 * 32 * (size_t)m + (size_t)grow * 16
                       : base + (size_t)L * 32 * (size_t)m + (size_t)(grow >> 7) * 4096 + (size_t)(grow & 127);
         // ReLU masks of the trunk layers behind the activations: [layer 0..7][row][column half] x 128 bits
-        if (L < 8) mptr = base + (size_t)272 * (size_t)m + ((size_t)L * (size_t)m + (size_t)grow) * 2 + (gwarp >> 2);
+        mstride = (size_t)m;
+        if (L < 8) mptr = reinterpret_cast<uint32_t*>(base + (size_t)272 * (size_t)m) + (size_t)(L * 8 + (gwarp >> 2) * 4) * (size_t)m + (size_t)grow;
       }
       { PROF_T0();
-        if (L == 8) epilogue<2>(sm, tmem_acc, act_saddr, s, net.w_alpha, net.w_rgb, gwarp, lane, sig_keep, dptr, mptr, vptr,
+        if (L == 8) epilogue<2>(sm, tmem_acc, act_saddr, s, net.w_alpha, net.w_rgb, gwarp, lane, sig_keep, dptr, mptr, vptr, mstride,
                                 kFC ? net.fc_table + (size_t)fc_row * 128 : nullptr);
-        else if (L == 7) epilogue<1>(sm, tmem_acc, act_saddr, s, net.w_alpha, net.w_rgb, gwarp, lane, sig_keep, dptr, mptr, vptr);
-        else epilogue<0>(sm, tmem_acc, act_saddr, s, net.w_alpha, net.w_rgb, gwarp, lane, sig_keep, dptr, mptr, vptr);
+        else if (L == 7) epilogue<1>(sm, tmem_acc, act_saddr, s, net.w_alpha, net.w_rgb, gwarp, lane, sig_keep, dptr, mptr, vptr, mstride);
+        else epilogue<0>(sm, tmem_acc, act_saddr, s, net.w_alpha, net.w_rgb, gwarp, lane, sig_keep, dptr, mptr, vptr, mstride);
         compute_arrive(act_ready_a, lane); if (timed) PROF_ADD(8); }
       if (kStage && L == 8) {
         group_bar_sync(s);

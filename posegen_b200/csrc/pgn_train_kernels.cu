@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(256) pgn_view_delta_bits_kernel(uint4* __restr
     for (int i = 0; i < 8; ++i) wv[k][i] = __ldg(w_rgb + k * 128 + cg * 8 + i);
   for (long long row = (long long)blockIdx.x * 16 + (threadIdx.x >> 4); row < m; row += (long long)gridDim.x * 16) {
     const float r0 = __ldg(d_raw + row * 4), r1 = __ldg(d_raw + row * 4 + 1), r2 = __ldg(d_raw + row * 4 + 2);
-    const uint32_t bits = __ldg(vmask + row * 4 + (cg >> 2)) >> ((cg & 3) * 8);
+    const uint32_t bits = __ldg(vmask + (size_t)(cg >> 2) * (size_t)m + row) >> ((cg & 3) * 8);      // word planes [4][m]
     uint32_t ow[4];
 #pragma unroll
     for (int w = 0; w < 4; ++w) {

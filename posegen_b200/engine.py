@@ -286,8 +286,8 @@ class Engine:
     def render_masks(self, ray_batch, skts, cyls, pose_idx=None, nanfill_chunk=0):
         """pgn_render_forward_masks: the fused bf16 forward that keeps only the fine pass's ReLU masks (272 B per sample),
         for the pose gradient through a frozen network.  Returns (outputs incl. raw / z_fine, (trunk_mask, view_mask)):
-        trunk_mask int32 [8, rows, 8] (256 bits per row and trunk layer), view_mask int32 [rows, 4]; rows >= n * 80,
-        samples in (ray, sample) order."""
+        trunk_mask int32 [8, 8, rows] (word planes: word w of a layer = the bits [column 32 w + b > 0] of every row),
+        view_mask int32 [4, rows]; rows >= n * 80, samples in (ray, sample) order."""
         inp, keep = self._inputs(ray_batch, skts, cyls, pose_idx, nanfill_chunk, "bf16")
         n, dev = inp.n_rays, ray_batch.device
         f = lambda *sh: torch.empty(sh, dtype=torch.float32, device=dev)  # noqa: E731
@@ -304,15 +304,15 @@ class Engine:
             _lib.check(self.lib.pgn_render_forward_masks(self.handle, C.byref(inp), C.byref(out), _ptr(buf),
                                                          C.c_void_p(ws.data_ptr()), ws.numel(),
                                                          self._stream()))
-        return ret, (buf[:rows * 64].view(8, rows, 8), buf[rows * 64:].view(rows, 4))
+        return ret, (buf[:rows * 64].view(8, 8, rows), buf[rows * 64:].view(4, rows))
 
     def view_delta_from_mask(self, d_raw, w_rgb, view_mask):
         """pgn_view_delta_from_mask: dG bf16 [m,128] = [g > 0] * (d_rgb W_rgb) from the view layer's mask bits."""
         m = d_raw.shape[0]
         if d_raw.dtype != torch.float32 or not d_raw.is_contiguous() or tuple(d_raw.shape) != (m, 4) or not d_raw.is_cuda:
             raise ValueError("d_raw must be contiguous CUDA fp32 [m,4]")
-        if view_mask.dtype != torch.int32 or not view_mask.is_contiguous() or tuple(view_mask.shape) != (m, 4):
-            raise ValueError("view_mask must be contiguous int32 [m,4]")
+        if view_mask.dtype != torch.int32 or not view_mask.is_contiguous() or tuple(view_mask.shape) != (4, m):
+            raise ValueError("view_mask must be contiguous int32 [4,m] (word planes)")
         w = w_rgb.detach().float().contiguous()
         dG = torch.empty((m, 128), dtype=torch.bfloat16, device=d_raw.device)
         with torch.cuda.device(d_raw.device):

@@ -54,11 +54,11 @@ class _FrameRenderFn(torch.autograd.Function):
         live = ((g_rgb.abs().sum(-1) + g_acc.abs()) > 0).nonzero().squeeze(-1)      # rays the loss reads (e.g. the HMR crop)
         d_skts = torch.zeros((24, 4, 4), dtype=torch.float32, device=dev)
         pd = dict(rc.network_fine.named_parameters())
-        rows_all = trunk_mask.shape[1]
+        rows_all = trunk_mask.shape[2]
         if rows_all % T:
             raise RuntimeError("mask dump rows are not whole rays")
-        trunk_rays = trunk_mask.view(8, rows_all // T, T * 8)                       # per layer and ray: 80 samples x 256 bits
-        view_rays = view_mask.view(rows_all // T, T * 4)
+        trunk_rays = trunk_mask.view(64, rows_all // T, T)                          # per (layer, word) plane and ray: 80 samples
+        view_rays = view_mask.view(4, rows_all // T, T)
         for i in range(0, live.numel(), ctx.chunk):
             idx = live[i:i + ctx.chunk].contiguous()
             k = idx.numel()
@@ -66,8 +66,8 @@ class _FrameRenderFn(torch.autograd.Function):
             z = eng.gather_ray_rows(z_all, idx)                                      # the rays' samples in the fine pass
             d_raw = eng.composite_backward(rb, sk, cy, eng.gather_ray_rows(raw_all, idx), z, g_rgb.index_select(0, idx).contiguous(),
                                            g_acc.index_select(0, idx).contiguous())
-            mask_dump = (eng.gather_ray_rows(trunk_rays, idx, n_planes=8).view(8, k * T, 8),
-                         eng.gather_ray_rows(view_rays, idx).view(k * T, 4))
+            mask_dump = (eng.gather_ray_rows(trunk_rays, idx, n_planes=64).view(8, 8, k * T),
+                         eng.gather_ray_rows(view_rays, idx, n_planes=4).view(4, k * T))
             gd = mlp_backward(pd, None, None, d_raw.reshape(-1, 4), eng.mlp_delta, want_input_grad=True, want_weight_grad=False,
                               chain=functools.partial(eng.mlp_delta_chain_net, 1), mask_dump=mask_dump, view_delta=eng.view_delta_from_mask,
                               input_grads=functools.partial(eng.mlp_input_grads, 1))

@@ -72,7 +72,8 @@ def to_tile_blocked(x: torch.Tensor) -> torch.Tensor:
 
 
 def act_masks(acts: torch.Tensor):
-    """(mask area of the dump, rows): [8 layers][rows][256 bits], the operand of `pgn_mlp_delta_chain`."""
+    """(mask area of the dump, rows): word planes [8 layers][8 words][rows] (word w = the bits [column 32 w + b > 0]),
+    the operand of `pgn_mlp_delta_chain`."""
     rows = acts.numel() // ACT_ROW_ELEMS
     return acts[rows * 2176:], rows
 
@@ -110,7 +111,7 @@ def mlp_backward(params: Dict[str, torch.Tensor], enc: torch.Tensor, acts: torch
     runs in the step; without it the products below go through `torch.mm` (the CPU host-logic test, A/B runs).
     `input_grads(dz, dG)` is `Engine.mlp_input_grads` bound to this net (`pgn_mlp_input_grads`): dL/d(network input) on
     tcgen05 instead of three library GEMMs (needs `chain`).
-    mask_dump = (trunk_mask int32 [8,m,8], view_mask int32 [m,4]) with `view_delta` = `Engine.view_delta_from_mask`
+    mask_dump = (trunk_mask int32 [8,8,m], view_mask int32 [4,m]; word planes) with `view_delta` = `Engine.view_delta_from_mask`
     replaces `acts` for a frozen network (want_weight_grad False, `chain` required): the masks-only dump of
     `pgn_render_forward_masks` is all the input-gradient chain reads.
     Returns {name: fp32 gradient}; with want_input_grad also dL/d(network input) as "_g_xp" [m,432] (v-embed | r

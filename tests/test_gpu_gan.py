@@ -71,8 +71,8 @@ def test_masks_only_forward_matches_the_full_dump(rc):
     for k in ("rgb_map", "acc_map"):
         assert float((ret_m[k] - ret_d[k]).abs().max()) <= 1e-5, k
     full, rows = act_masks(acts["f"])
-    assert torch.equal(trunk[:, :m], full.view(torch.int32).view(8, rows, 8)[:, :m])
-    bits = ((view[:m, :, None] >> torch.arange(32, device=dev, dtype=torch.int32)) & 1).reshape(m, 128).bool()
+    assert torch.equal(trunk[:, :, :m], full.view(torch.int32).view(8, 8, rows)[:, :, :m])
+    bits = ((view[:, :m].t()[:, :, None] >> torch.arange(32, device=dev, dtype=torch.int32)) & 1).reshape(m, 128).bool()
     assert torch.equal(bits, act_layer(acts["f"], 8, m) > 0)
 
 

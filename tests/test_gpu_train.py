@@ -265,7 +265,7 @@ def test_forward_dump_masks_match_the_activations(engine, train_case):
     for key, s in (("c", 64), ("f", 80)):
         m = n * s
         mask, rows = act_masks(acts[key])
-        bits = mask.view(torch.int32).view(8, rows, 8)[:, :m]                       # 8 words of 32 columns per row
+        bits = mask.view(torch.int32).view(8, 8, rows)[:, :, :m].permute(0, 2, 1)   # word planes -> 8 words of 32 columns per row
         got = ((bits[..., None] >> torch.arange(32, device=dev, dtype=torch.int32)) & 1).reshape(8, m, 256).bool()
         for l in range(8):
             assert torch.equal(got[l], act_layer(acts[key], l, m) > 0), (key, l)
@@ -286,7 +286,7 @@ def test_delta_chain_kernel_matches_layerwise_reference(engine):
         act = torch.rand((8, rows, 256), device=dev, generator=g) > 0.4
         words = (act.view(8, rows, 8, 32).to(torch.int64) << torch.arange(32, device=dev)).sum(-1)
         mask = words.to(torch.int32)                                                   # wraps bit 31 into the sign
-        mask = torch.where(words >= 2 ** 31, words - 2 ** 32, words).to(torch.int32).contiguous()
+        mask = torch.where(words >= 2 ** 31, words - 2 ** 32, words).to(torch.int32).permute(0, 2, 1).contiguous()   # word planes [8][8][rows]
         dz, colsum = engine.mlp_delta_chain(dG, d_raw.contiguous(), mask, rows, chain_wstream(P),
                                             P["alpha_linear.weight"].reshape(-1).float().contiguous())
         engine.check_status()

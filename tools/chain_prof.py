@@ -10,7 +10,7 @@ P = {k: torch.as_tensor(v, device=dev) for k, v in syn.synthetic_nerf_state(7).i
 m = 3072 * 80; rows = m
 dG = (torch.randn((m, 128), device=dev) * 0.1).to(torch.bfloat16)
 d_raw = torch.randn((m, 4), device=dev)
-mask = torch.randint(-2**31, 2**31 - 1, (8, rows, 8), device=dev, dtype=torch.int32)
+mask = torch.randint(-2**31, 2**31 - 1, (8, 8, rows), device=dev, dtype=torch.int32)
 ws = chain_wstream(P); wa = P["alpha_linear.weight"].reshape(-1).float().contiguous()
 for _ in range(3): eng.mlp_delta_chain(dG, d_raw, mask, rows, ws, wa)
 torch.cuda.synchronize()
