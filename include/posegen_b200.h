@@ -403,7 +403,8 @@ PGN_API int  pgn_compose_frames_batch(pgn_context* ctx, int32_t H, int32_t W, co
 /* Rows of selected rays out of per-sample planes: dst[p][i] = src[p][idx[i]], n_planes planes of rows of row_bytes bytes
  * (a multiple of 16; planes 16-byte aligned), idx device int64 [n_idx].  The pose gradient of a frame (run_gan.py:2040-2091
  * made differentiable, BASELINE.json configs[4]) walks the rays the HMR crop reads in chunks and selects their samples out
- * of the frame's mask dump / raw / z_fine with it (torch.index_select took 6 ms per image on these shapes). */
+ * of the frame's mask dump / raw / z_fine with it (torch.index_select took 6 ms per image on these shapes).  An index
+ * outside [0, src_plane_bytes / row_bytes) yields a zero row and latches the device status (pgn_check_device_status). */
 PGN_API int  pgn_gather_ray_rows(pgn_context* ctx, const void* src, void* dst, const int64_t* idx, int64_t n_idx, int64_t row_bytes,
                                  int32_t n_planes, int64_t src_plane_bytes, int64_t dst_plane_bytes, void* stream);
 

@@ -369,7 +369,8 @@ int pgn_check_device_status(pgn_context* c) {
   PGN_CUDA(cudaMemcpy(&st, c->d_status, sizeof(int), cudaMemcpyDeviceToHost));
   if (st != 0) {
     cudaMemset(c->d_status, 0, sizeof(int));
-    return fail(PGN_E_KERNEL, "device watchdog tripped: pipeline wait code %d", st);
+    return fail(PGN_E_KERNEL, st == 950 ? "device status %d: pgn_gather_ray_rows index out of range"
+                                         : "device watchdog tripped: pipeline wait code %d", st);
   }
   return PGN_OK;
 }
@@ -648,8 +649,9 @@ int pgn_gather_ray_rows(pgn_context* c, const void* src, void* dst, const int64_
       (dst_plane_bytes & 15) || ((uintptr_t)src & 15) || ((uintptr_t)dst & 15))
     return fail(PGN_E_INVALID, "pgn_gather_ray_rows: bad argument (rows and planes are multiples of 16 bytes, 16-byte aligned)");
   PGN_ON_DEVICE(c);
+  if (src_plane_bytes % row_bytes) return fail(PGN_E_INVALID, "pgn_gather_ray_rows: a source plane is a whole number of rows");
   PGN_CUDA(pgn_launch_gather_ray_rows(src, dst, (const long long*)idx, n_idx, row_bytes, n_planes, src_plane_bytes, dst_plane_bytes,
-                                      c->num_sms, (cudaStream_t)stream));
+                                      c->d_status, c->num_sms, (cudaStream_t)stream));
   c->launches++;
   return PGN_OK;
 }

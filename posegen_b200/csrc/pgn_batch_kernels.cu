@@ -219,26 +219,34 @@ cudaError_t pgn_launch_compose_frames_batch(int H, int W, const int* bbox, const
 // dst[p][i] = src[p][idx[i]] for n_planes planes of rows of row_bytes bytes (a multiple of 16; 16-byte aligned planes).
 // What `index_select` does at 150-230 us per call on these shapes (run_gan.py has no counterpart: its render is not
 // differentiated); here one launch per tensor at HBM speed.
+// An index outside the source plane writes zeros and latches status code 950 (pgn_check_device_status reports it).
 __global__ void pgn_gather_ray_rows_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, const long long* __restrict__ idx,
-                                           long long n_idx, int row_vec, int n_planes, long long src_plane_vec, long long dst_plane_vec) {
+                                           long long n_idx, int row_vec, int n_planes, long long src_plane_vec, long long dst_plane_vec,
+                                           int* __restrict__ status) {
   const long long total = (long long)n_planes * n_idx * row_vec;
+  const long long src_rows = src_plane_vec / row_vec;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long rowi = i / row_vec;
     const int v = (int)(i - rowi * row_vec);
     const long long pl = rowi / n_idx, r = rowi - pl * n_idx;
-    dst[pl * dst_plane_vec + r * row_vec + v] = __ldg(src + pl * src_plane_vec + __ldg(idx + r) * row_vec + v);
+    const long long sr = __ldg(idx + r);
+    uint4 val = make_uint4(0u, 0u, 0u, 0u);
+    if (sr >= 0 && sr < src_rows) val = __ldg(src + pl * src_plane_vec + sr * row_vec + v);
+    else if (v == 0 && pl == 0) *status = 950;
+    dst[pl * dst_plane_vec + r * row_vec + v] = val;
   }
 }
 
 cudaError_t pgn_launch_gather_ray_rows(const void* src, void* dst, const long long* idx, long long n_idx, long long row_bytes,
-                                       int n_planes, long long src_plane_bytes, long long dst_plane_bytes, int num_sms, cudaStream_t stream) {
+                                       int n_planes, long long src_plane_bytes, long long dst_plane_bytes, int* status, int num_sms,
+                                       cudaStream_t stream) {
   if (n_idx <= 0 || n_planes <= 0) return cudaSuccess;
   const long long total = (long long)n_planes * n_idx * (row_bytes / 16);
   const long long blocks = (total + 255) / 256;
   const long long cap = (long long)num_sms * 8;
   pgn_gather_ray_rows_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, stream>>>(
       reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(dst), idx, n_idx, (int)(row_bytes / 16), n_planes,
-      src_plane_bytes / 16, dst_plane_bytes / 16);
+      src_plane_bytes / 16, dst_plane_bytes / 16, status);
   return cudaGetLastError();
 }
 

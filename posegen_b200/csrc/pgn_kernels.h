@@ -123,7 +123,8 @@ cudaError_t pgn_launch_cyl_bboxes(const float* cyls, int n, const double* w2c16,
 cudaError_t pgn_launch_generate_rays_batch(int H, int W, float focal, const float* c2w12_dev, const int* bbox, const long long* offsets,
                                            int n_poses, long long max_rays_per_pose, float* ray_batch, int* pose_idx, cudaStream_t stream);
 cudaError_t pgn_launch_gather_ray_rows(const void* src, void* dst, const long long* idx, long long n_idx, long long row_bytes,
-                                       int n_planes, long long src_plane_bytes, long long dst_plane_bytes, int num_sms, cudaStream_t stream);
+                                       int n_planes, long long src_plane_bytes, long long dst_plane_bytes, int* status, int num_sms,
+                                       cudaStream_t stream);
 cudaError_t pgn_launch_compose_frames_batch(int H, int W, const int* bbox, const long long* offsets, int n_poses, const float* rgb,
                                             const float* acc, float bg, float* images, cudaStream_t stream);
 cudaError_t pgn_launch_pose_fk_backward(const float* bones, const float* rest, int n_poses, const float* g_skts, const float* g_kps,

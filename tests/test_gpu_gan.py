@@ -131,3 +131,9 @@ def test_gather_ray_rows_matches_index_select(engine):
     assert engine.gather_ray_rows(z, idx[:0]).shape == (0, 80)
     with pytest.raises(Exception):
         engine.gather_ray_rows(torch.zeros((10, 11), device=dev), idx[:3] % 10)          # 44-byte rows: not a multiple of 16
+    bad = engine.gather_ray_rows(z, torch.tensor([1, 5000, 7], device=dev))               # 5000 is out of range
+    torch.cuda.synchronize()
+    assert torch.equal(bad[0], z[1]) and torch.equal(bad[2], z[7]) and float(bad[1].abs().max()) == 0.0
+    with pytest.raises(Exception, match="out of range"):
+        engine.check_status()
+    engine.check_status()                                                                  # (the latch is cleared by the report)
