@@ -62,7 +62,6 @@ constexpr int kWStages = 3;
 constexpr int kWStageBytes = 8192;
 constexpr int kTmemCols = 512;          // two 256-column accumulators
 constexpr int kMaxTileRays = 3;
-constexpr int kTilesPerGroup = 9;
 
 static_assert(kStgBufs * kStgBytes <= kActBytes, "staging ring must fit inside the activation buffer");
 
@@ -86,19 +85,26 @@ struct __align__(128) Smem {
 static_assert(sizeof(Smem) + 1024 <= 232448, "shared memory budget of one CTA exceeded");
 
 // tile k of a ray group.  8 rays: C0 C1 F0 C2 F1 C3 F2 F3 F4 (4 coarse tiles of 2 rays, 640 fine rows = 5 tiles);
-// 4 rays: C0 C1 F0 F1 F2 (320 fine rows = 2.5 tiles, the last one half empty).  Small batches use the groups of 4: a
-// 3,072-ray training batch is 192 pair-units of 8 rays for 148 tile pipelines - two rounds, the second one with most
-// pipelines idle - but 384 pair-units of half the length (pgn_bf16_group_rays decides, from the ray count alone).
+// 6 rays: C0 C1 F0 C2 F1 F2 F3 (480 fine rows = 3.75 tiles); 4 rays: C0 C1 F0 F1 F2 (320 fine rows = 2.5 tiles, the last
+// one half empty).  A fine tile always comes at least two tiles after the coarse tile of the last ray it touches (that
+// tile's compositing / resampling runs in the shadow of the tile after it).  Small batches use the smaller groups: a
+// 3,072-ray training batch is 192 pair-units of 8 rays for 148 tile pipelines - two rounds of 9 tiles, the second one with
+// most pipelines idle - or 384 pair-units of 4 (three rounds of 5 tiles) or 256 of 6 (two rounds of 7 tiles);
+// pgn_bf16_group_rays decides, from the ray count alone.
 template <int kG>
 __device__ __forceinline__ void tile_of(int k, int& pass, int& t) {
   if (kG == 8) {
     pass = (0x1D4 >> k) & 1;
     t = (int)((0x432312010ull >> (4 * k)) & 0xF);
+  } else if (kG == 6) {
+    pass = (0x74 >> k) & 1;                          // C C F C F F F
+    t = (int)((0x3212010u >> (4 * k)) & 0xF);        // 0 1 0 2 1 2 3
   } else {
     pass = k >= 2 ? 1 : 0;
     t = k >= 2 ? k - 2 : k;
   }
 }
+template <int kG> constexpr int tiles_per_group() { return kG == 8 ? 9 : (kG == 6 ? 7 : 5); }
 
 struct TileCtx {
   long long ray0;     // first ray of this CTA's group
@@ -504,7 +510,7 @@ pgn_render_bf16_kernel(PgnRayRefs rays, PgnOutputs out, PgnBf16Net net_c, PgnBf1
   const long long n_units = kStage ? (enc_rows_total + kTM - 1) / kTM : (rays.n_rays + kG - 1) / kG;
   const long long n_pairs = (n_units + 1) / 2;
   const int n_local = (int)((n_pairs > cluster_id) ? (n_pairs - cluster_id + n_clusters - 1) / n_clusters : 0);
-  constexpr int kTiles = kStage ? 1 : (kG == 8 ? kTilesPerGroup : 5);
+  constexpr int kTiles = kStage ? 1 : tiles_per_group<kG>();
 
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
@@ -1056,16 +1062,20 @@ __global__ void pgn_pack_wstream_kernel(PackPtrs p, const float* __restrict__ fo
 
 size_t pgn_bf16_wstream_elems() { return pgn_wstream_elems(); }
 
-// Rays per group of a launch over n_rays rays: 8, or 4 when that shortens the critical path of the 148 tile pipelines
-// (2 per CTA, pair-units dealt round-robin): rounds(8-ray units) vs rounds(4-ray units) at 0.55 of the length (half the
-// rays, 10 % padding in the last fine tile).  A pure function of the ray count (a 148-SM B200 is assumed), so that the
+// Rays per group of a launch over n_rays rays: 8, or 6 / 4 when that shortens the critical path of the 148 tile pipelines
+// (2 per CTA, pair-units dealt round-robin): rounds of pair-units x tiles per group (9 / 7 / 5), the larger group on a tie.  A pure function of the ray count (a 148-SM B200 is assumed), so that the
 // dump-size queries and the launch agree.  The masks-only (GAN) forward always uses 8.
 int pgn_bf16_group_rays(long long n_rays, int masks_only) {
   if (masks_only || n_rays <= 0) return kRPG;
   const long long slots = 148;                       // 74 CTA pairs x 2 pipelines
-  const long long p8 = ((n_rays + 7) / 8 + 1) / 2, p4 = ((n_rays + 3) / 4 + 1) / 2;
-  const double t8 = (double)((p8 + slots - 1) / slots), t4 = 0.55 * (double)((p4 + slots - 1) / slots);
-  return t4 < t8 ? 4 : kRPG;
+  int best = kRPG;
+  long long best_tiles = 0;
+  for (int g = 8; g >= 4; g -= 2) {                  // critical path in tiles: rounds of pair-units x tiles per group
+    const long long pairs = ((n_rays + g - 1) / g + 1) / 2;
+    const long long tiles = ((pairs + slots - 1) / slots) * (g == 8 ? 9 : (g == 6 ? 7 : 5));
+    if (g == 8 || tiles < best_tiles) { best = g; best_tiles = tiles; }
+  }
+  return best;
 }
 
 // rows of the activation dump of one pass (units are padded to CTA pairs): samples_per_ray = 64 | 80
@@ -1126,6 +1136,10 @@ static cudaError_t configure_bf16() {
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(pgn_render_bf16_kernel<false, false, 1, 4, PGN_FC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(pgn_render_bf16_kernel<false, false, 0, 6, PGN_FC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(pgn_render_bf16_kernel<false, false, 1, 6, PGN_FC>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return e;
   done.set();
   return cudaSuccess;
 }
@@ -1150,10 +1164,14 @@ cudaError_t PGN_LAUNCH_RENDER(const PgnRayRefs& rays, const PgnOutputs& out, con
     pgn_render_bf16_kernel<false, false, 2, 8, PGN_FC><<<grid, kThreads, smem, stream>>>(rays, out, nc, nf, sc_dev, near_far, nullptr, 0, nullptr, status, nullptr, *dump);
   else if (dump && g == 4)
     pgn_render_bf16_kernel<false, false, 1, 4, PGN_FC><<<grid, kThreads, smem, stream>>>(rays, out, nc, nf, sc_dev, near_far, nullptr, 0, nullptr, status, nullptr, *dump);
+  else if (dump && g == 6)
+    pgn_render_bf16_kernel<false, false, 1, 6, PGN_FC><<<grid, kThreads, smem, stream>>>(rays, out, nc, nf, sc_dev, near_far, nullptr, 0, nullptr, status, nullptr, *dump);
   else if (dump)
     pgn_render_bf16_kernel<false, false, 1, 8, PGN_FC><<<grid, kThreads, smem, stream>>>(rays, out, nc, nf, sc_dev, near_far, nullptr, 0, nullptr, status, nullptr, *dump);
   else if (g == 4)
     pgn_render_bf16_kernel<false, false, 0, 4, PGN_FC><<<grid, kThreads, smem, stream>>>(rays, out, nc, nf, sc_dev, near_far, nullptr, 0, nullptr, status, nullptr, nodump);
+  else if (g == 6)
+    pgn_render_bf16_kernel<false, false, 0, 6, PGN_FC><<<grid, kThreads, smem, stream>>>(rays, out, nc, nf, sc_dev, near_far, nullptr, 0, nullptr, status, nullptr, nodump);
 #ifndef PGN_RENDER_FC_UNIT
   else if (use_prof)
     pgn_render_bf16_kernel<false, true, 0><<<grid, kThreads, smem, stream>>>(rays, out, nc, nf, sc_dev, near_far, nullptr, 0, nullptr, status, prof, nodump);

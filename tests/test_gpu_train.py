@@ -507,3 +507,42 @@ def test_training_gradients_share_one_arena(engine, train_case):
     assert len({p.grad.untyped_storage().data_ptr() for p in ps}) == 1
     spans = sorted((p.grad.storage_offset(), p.grad.storage_offset() + p.grad.numel()) for p in ps)
     assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:]))            # disjoint views
+
+
+def test_ray_group_sizes_agree(engine, train_case):
+    """The fused kernel cuts a batch into ray groups of 8, 6 or 4 (pgn_render_bf16.cu tile_of; chosen from the ray count):
+    3,072 rays run as groups of 6, the same rays in three launches of 1,024 as groups of 4.  Per-sample network outputs,
+    sample positions and the activation dump are identical, the composited maps agree up to the association order of the
+    fine-pass compositing across tile boundaries."""
+    from posegen_b200.train import act_layer, act_masks
+    frame, ckpt, rb, tgt = train_case
+    engine.load_checkpoint(ckpt)
+    dev = torch.device("cuda")
+    big = syn.synthetic_frame(5, 128, 128)
+    rays = torch.as_tensor(syn.ray_batch(big.rays_o, big.rays_d), device=dev)
+    assert rays.shape[0] >= 2 * 3072
+    rays = rays[::rays.shape[0] // 3072][:3072].contiguous()                     # spread over the whole bbox
+    sk, cy = torch.as_tensor(big.pose.skts, device=dev), torch.as_tensor(big.pose.cyl, device=dev)
+    # inference kernels
+    # (near / far of rays that miss the cylinder are filled from their chunk's statistics: same 1,024-ray chunks in both)
+    full = engine.render(rays, sk, cy, nanfill_chunk=1024, precision="bf16", return_alpha=False)
+    parts = [engine.render(rays[i:i + 1024], sk, cy, nanfill_chunk=1024, precision="bf16", return_alpha=False) for i in range(0, 3072, 1024)]
+    engine.check_status()
+    for k in ("rgb_map", "acc_map", "rgb0", "acc0", "disp_map"):
+        got = torch.cat([p[k] for p in parts])
+        assert float((full[k] - got).abs().max()) <= 2e-5, k
+    assert float(full["acc_map"].max()) > 0.5                                    # the rays do hit the body
+    # training kernels: dumps row for row
+    ret, acts = engine.render_train(rays, sk, cy, nanfill_chunk=1024)
+    prt = [engine.render_train(rays[i:i + 1024], sk, cy, nanfill_chunk=1024) for i in range(0, 3072, 1024)]
+    engine.check_status()
+    for k in ("raw", "raw0", "z_fine"):
+        assert torch.equal(ret[k], torch.cat([p[0][k] for p in prt])), k
+    for key, s in (("c", 64), ("f", 80)):
+        for l in (0, 4, 7, 8):
+            want = torch.cat([act_layer(p[1][key], l, 1024 * s) for p in prt])
+            assert torch.equal(act_layer(acts[key], l, 3072 * s), want), (key, l)
+        mask, rows = act_masks(acts[key])
+        bits = mask.view(torch.int32).view(8, 8, rows)[:, :, :3072 * s]
+        want = torch.cat([act_masks(p[1][key])[0].view(torch.int32).view(8, 8, -1)[:, :, :1024 * s] for p in prt], dim=2)
+        assert torch.equal(bits, want), key
