@@ -150,9 +150,10 @@ def test_512_full_frame_matches_oracle_on_device(engine, frame512):
         assert pu.max_abs(h[k].cpu().numpy(), ref[k]) <= BF16_TOL, k
     assert pu.psnr(h["rgb_map"].cpu().numpy(), ref["rgb_map"]) >= BF16_PSNR
     assert pu.psnr(h["acc_map"].cpu().numpy(), ref["acc_map"]) >= BF16_PSNR
-    # fp32 tier on every 8th chunk-aligned block of 4096 rays (the NaN fill is per chunk, so blocks stay comparable)
+    # fp32 tier on EVERY ray of the frame, in chunk-aligned blocks of 4096 rays (the NaN fill is per chunk, so blocks stay
+    # comparable; the CUDA-core tier renders ~60-90 k rays/s: a few seconds for the frame)
     n = rb.shape[0]
-    blocks = [slice(i, min(i + 4096, n)) for i in range(0, n, 8 * 4096)]
+    blocks = [slice(i, min(i + 4096, n)) for i in range(0, n, 4096)]
     for bl in blocks:
         f = engine.render(rb[bl].contiguous(), sk, cy, nanfill_chunk=4096, precision="fp32", return_alpha=False)
         for k in ("rgb_map", "acc_map", "rgb0", "acc0"):
