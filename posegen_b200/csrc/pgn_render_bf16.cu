@@ -988,14 +988,30 @@ __global__ void pgn_fold_view_kernel(const float* __restrict__ w_view /*[128][vi
                                      const float* __restrict__ b_view, const float* __restrict__ b_feat,
                                      float* __restrict__ fold /*[128][256] + [128]*/, int view_ld) {
   // fold[n][k] = sum_m w_view[n][m] * w_feat[m][k];  fold_b[n] = b_view[n] + sum_m w_view[n][m] * b_feat[m]
+  // (runs on every weight upload, i.e. once per training step: four independent accumulation chains per thread and a
+  // block reduction for the bias instead of 256 serial FMAs + a serial bias loop in thread 0)
+  __shared__ float red[8];
   const int n = blockIdx.x, k = threadIdx.x;
-  float acc = 0.f;
-  for (int m = 0; m < 256; ++m) acc = fmaf(w_view[n * view_ld + m], w_feat[m * 256 + k], acc);
-  fold[n * 256 + k] = acc;
+  const float* wv = w_view + (size_t)n * view_ld;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 16
+  for (int m = 0; m < 256; m += 4) {                 // (64 loads in flight per thread: the kernel is L2-latency bound)
+    a0 = fmaf(__ldg(wv + m), __ldg(w_feat + m * 256 + k), a0);
+    a1 = fmaf(__ldg(wv + m + 1), __ldg(w_feat + (m + 1) * 256 + k), a1);
+    a2 = fmaf(__ldg(wv + m + 2), __ldg(w_feat + (m + 2) * 256 + k), a2);
+    a3 = fmaf(__ldg(wv + m + 3), __ldg(w_feat + (m + 3) * 256 + k), a3);
+  }
+  fold[n * 256 + k] = (a0 + a1) + (a2 + a3);
+  float b = __ldg(wv + k) * __ldg(b_feat + k);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) b += __shfl_xor_sync(0xffffffffu, b, o);
+  if ((k & 31) == 0) red[k >> 5] = b;
+  __syncthreads();
   if (k == 0) {
-    float b = b_view[n];
-    for (int m = 0; m < 256; ++m) b = fmaf(w_view[n * view_ld + m], b_feat[m], b);
-    fold[128 * 256 + n] = b;
+    float t = b_view[n];
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w];
+    fold[128 * 256 + n] = t;
   }
 }
 
